@@ -1,0 +1,186 @@
+// Multi-GPU plumbing: one rank per GPU, env shards are independent, the only exchange is the gradient
+// (+ info sums) all-reduce before Adam.  The reference has no distributed path at all.
+//
+// NCCL is resolved at run time with dlopen so that libcrux_cuda.so shares the libnccl.so.2 already mapped
+// by the host process (torch bundles 2.28.9) instead of linking a second copy.
+//
+// Besides NCCL there is a one-shot peer all-reduce for the latency-bound 44 KB gradient: every rank stores
+// its vector into a slot of every peer's receive buffer over NVLink (CUDA IPC mapped pointers), bumps a
+// sequence flag, then each rank sums the slots in rank order (bit-identical on all ranks).
+#include "common.cuh"
+#include <dlfcn.h>
+
+namespace {
+
+typedef struct { char internal[128]; } nccl_uid;
+typedef void *nccl_comm_t;
+typedef int (*fn_getuid)(nccl_uid *);
+typedef int (*fn_initrank)(nccl_comm_t *, int, nccl_uid, int);
+typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t);
+typedef int (*fn_destroy)(nccl_comm_t);
+typedef const char *(*fn_errstr)(int);
+
+struct NcclApi {
+  void *lib = nullptr;
+  fn_getuid get_uid = nullptr;
+  fn_initrank init_rank = nullptr;
+  fn_allreduce all_reduce = nullptr;
+  fn_destroy destroy = nullptr;
+  fn_errstr err = nullptr;
+  std::string why;
+} g_nccl;
+
+bool load_nccl() {
+  if (g_nccl.lib) return true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) { g_nccl.why = dlerror() ? dlerror() : "dlopen(libnccl.so.2) failed"; return false; }
+  g_nccl.get_uid = (fn_getuid)dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.init_rank = (fn_initrank)dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.all_reduce = (fn_allreduce)dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.destroy = (fn_destroy)dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.err = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.all_reduce) { g_nccl.why = "libnccl is missing symbols"; g_nccl.lib = nullptr; return false; }
+  return true;
+}
+
+// ---- one-shot peer all-reduce ----------------------------------------------------------------------
+struct PeerPtrs { float *recv[16]; unsigned long long *flag[16]; };
+
+// each block pushes a slice of `src` into slot `rank` of every peer, then (last block) publishes the sequence number
+__global__ void peer_push_kernel(const float *__restrict__ src, int64_t n, PeerPtrs peers, int rank, int world, int64_t cap,
+                                 unsigned long long seq, unsigned long long *__restrict__ done_ctr) {
+  for (int p = 0; p < world; ++p) {
+    float *dst = peers.recv[p] + (int64_t)rank * cap;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(done_ctr, 1ULL) == (unsigned long long)gridDim.x - 1ULL;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    *done_ctr = 0ULL;
+    __threadfence_system();
+    for (int p = 0; p < world; ++p) {
+      volatile unsigned long long *f = peers.flag[p] + rank;
+      *f = seq;
+    }
+    __threadfence_system();
+  }
+}
+__global__ void peer_reduce_kernel(float *__restrict__ dst, int64_t n, const float *__restrict__ recv, volatile unsigned long long *flags,
+                                   int world, int64_t cap, unsigned long long seq) {
+  if (threadIdx.x < world) {
+    while (flags[threadIdx.x] < seq) { __nanosleep(100); }
+  }
+  __syncthreads();
+  __threadfence_system();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < world; ++p) s += __ldcv(recv + (int64_t)p * cap + i);
+    dst[i] = s;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t crux_nccl_unique_id(uint8_t *id_out_host) {
+  if (!id_out_host) return CRUX_ERR_INVALID;
+  if (!load_nccl()) return crux_set_err(nullptr, CRUX_ERR_NCCL, "NCCL unavailable: %s", g_nccl.why.c_str());
+  nccl_uid id;
+  const int rc = g_nccl.get_uid(&id);
+  if (rc != 0) return crux_set_err(nullptr, CRUX_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.err ? g_nccl.err(rc) : "error");
+  memcpy(id_out_host, id.internal, 128);
+  return CRUX_OK;
+}
+
+int32_t crux_nccl_init(crux_ctx *ctx, int32_t rank, int32_t world, const uint8_t *id_host) {
+  if (!ctx) return CRUX_ERR_INVALID;
+  CRUX_REQUIRE(ctx, world >= 1 && rank >= 0 && rank < world && id_host, "crux_nccl_init: bad rank/world/id");
+  if (!load_nccl()) return crux_set_err(ctx, CRUX_ERR_NCCL, "NCCL unavailable: %s", g_nccl.why.c_str());
+  CRUX_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  nccl_uid id;
+  memcpy(id.internal, id_host, 128);
+  nccl_comm_t comm = nullptr;
+  const int rc = g_nccl.init_rank(&comm, world, id, rank);
+  if (rc != 0) return crux_set_err(ctx, CRUX_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.err ? g_nccl.err(rc) : "error");
+  ctx->nccl_comm = comm; ctx->rank = rank; ctx->world = world;
+  return CRUX_OK;
+}
+
+int32_t crux_peer_allreduce(crux_ctx *ctx, float *buf, int64_t n);
+
+int32_t crux_nccl_allreduce_f32(crux_ctx *ctx, float *buf, int64_t n) {
+  if (!ctx) return CRUX_ERR_INVALID;
+  if (ctx->world <= 1 || n <= 0) return CRUX_OK;
+  if (ctx->peer_ready && n <= ctx->peer_cap) return crux_peer_allreduce(ctx, buf, n);
+  CRUX_REQUIRE(ctx, ctx->nccl_comm, "crux_nccl_allreduce_f32: NCCL not initialised");
+  const int rc = g_nccl.all_reduce(buf, buf, (size_t)n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, (nccl_comm_t)ctx->nccl_comm, ctx->stream);
+  if (rc != 0) return crux_set_err(ctx, CRUX_ERR_NCCL, "ncclAllReduce: %s", g_nccl.err ? g_nccl.err(rc) : "error");
+  return CRUX_OK;
+}
+
+// ---- peer path -----------------------------------------------------------------------------------
+// handle layout (64 bytes used of 2 x cudaIpcMemHandle_t = 128): we return both handles -> 128 bytes
+int32_t crux_peer_handle(crux_ctx *ctx, uint8_t *handle_out_host, int64_t max_floats) {
+  if (!ctx || !handle_out_host) return CRUX_ERR_INVALID;
+  CRUX_REQUIRE(ctx, max_floats >= 1, "crux_peer_handle: max_floats < 1");
+  CRUX_REQUIRE(ctx, ctx->world >= 1 && ctx->world <= 16, "crux_peer_handle: world must be set by crux_nccl_init (<= 16 ranks)");
+  if (!ctx->peer_recv) {
+    ctx->peer_cap = (max_floats + 31) / 32 * 32;
+    // one allocation: [world][cap] floats, then [16] flags + [1] block counter
+    const size_t bytes = (size_t)16 * ctx->peer_cap * sizeof(float) + 32 * sizeof(unsigned long long);
+    CRUX_CHECK_CUDA(ctx, cudaMalloc((void **)&ctx->peer_recv, bytes));
+    CRUX_CHECK_CUDA(ctx, cudaMemset(ctx->peer_recv, 0, bytes));
+    ctx->peer_flags = (unsigned long long *)((char *)ctx->peer_recv + (size_t)16 * ctx->peer_cap * sizeof(float));
+  }
+  cudaIpcMemHandle_t h;
+  CRUX_CHECK_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->peer_recv));
+  memset(handle_out_host, 0, 64);
+  memcpy(handle_out_host, &h, sizeof(h) <= 64 ? sizeof(h) : 64);
+  return CRUX_OK;
+}
+
+int32_t crux_peer_init(crux_ctx *ctx, int32_t rank, int32_t world, const uint8_t *handles_host) {
+  if (!ctx || !handles_host) return CRUX_ERR_INVALID;
+  CRUX_REQUIRE(ctx, world >= 1 && world <= 16 && rank >= 0 && rank < world, "crux_peer_init: bad rank/world");
+  CRUX_REQUIRE(ctx, ctx->peer_recv, "crux_peer_init: call crux_peer_handle first");
+  ctx->rank = rank; ctx->world = world;
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) {
+      ctx->peer_recv_remote[p] = ctx->peer_recv;
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles_host + (size_t)p * 64, sizeof(h));
+      void *ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return crux_set_err(ctx, CRUX_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e));
+      ctx->peer_recv_remote[p] = (float *)ptr;
+    }
+    ctx->peer_flags_remote[p] = (unsigned long long *)((char *)ctx->peer_recv_remote[p] + (size_t)16 * ctx->peer_cap * sizeof(float));
+  }
+  ctx->peer_seq = 0;
+  ctx->peer_ready = true;
+  return CRUX_OK;
+}
+
+int32_t crux_peer_allreduce(crux_ctx *ctx, float *buf, int64_t n) {
+  CRUX_REQUIRE(ctx, ctx->peer_ready && n <= ctx->peer_cap, "crux_peer_allreduce: not initialised or vector too long");
+  PeerPtrs pp;
+  for (int p = 0; p < ctx->world; ++p) { pp.recv[p] = ctx->peer_recv_remote[p]; pp.flag[p] = ctx->peer_flags_remote[p]; }
+  const unsigned long long seq = ++ctx->peer_seq;
+  const int blocks = (int)i64max(1, i64min(cdiv(n, 1024), 16));
+  peer_push_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, n, pp, ctx->rank, ctx->world, ctx->peer_cap, seq, ctx->peer_flags + 16);
+  CRUX_LAUNCHED(ctx);
+  peer_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, n, ctx->peer_recv, ctx->peer_flags, ctx->world, ctx->peer_cap, seq);
+  CRUX_LAUNCHED(ctx);
+  return CRUX_OK;
+}
+
+}  // extern "C"

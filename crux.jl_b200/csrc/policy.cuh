@@ -1,0 +1,31 @@
+// Internal Gaussian policy object.  Not part of the ABI.
+#pragma once
+#include "mlp.cuh"
+
+#define CRUX_MAX_ADIM 64
+#define CRUX_GRAD_TAIL 128  // floats appended to an actor's gradient vector: [logΣ grad (64) | info sums (64)]
+
+struct crux_gaussian {
+  crux_ctx *ctx = nullptr;
+  crux_mlp *mu = nullptr;       // borrowed
+  int adim = 0;
+  bool squashed = false;
+  float ascale = 1.0f;
+  bool head_mode = false;       // mu has 2*adim outputs: [mu | log_sigma]
+  // state-independent log-sigma (ConstantLayer): parameter, gradient (aliases mu->grads tail), Adam moments
+  float *log_sigma = nullptr;
+  float *ls_m = nullptr, *ls_v = nullptr;
+  // PPO workspace
+  float *mb = nullptr;          // gathered minibatch columns
+  size_t mb_bytes = 0;
+  int32_t *order = nullptr;     // device-generated permutations
+  size_t order_bytes = 0;
+  float *info_actor = nullptr, *info_critic = nullptr;
+  size_t info_actor_bytes = 0, info_critic_bytes = 0;
+  int *ctl = nullptr;           // [0]=skip (actor early stop), [1]=pending stop
+  double *partials = nullptr;   // head partial sums
+};
+
+// gradient tail accessors (mlp->grads is allocated with CRUX_GRAD_TAIL extra floats)
+static inline float *tail_ls_grad(crux_mlp *m) { return m->grads + m->n_params; }
+static inline float *tail_sums(crux_mlp *m) { return m->grads + m->n_params + 64; }

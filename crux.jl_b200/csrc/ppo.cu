@@ -1,0 +1,381 @@
+// Hot path (iii): policy_gradient_training (src/model_free/on_policy.jl:56-78) =
+// batch_train!(actor, ppo_loss | a2c_loss) then batch_train!(critic, mse) (src/training.jl:28-55),
+// as one stream-ordered launch sequence with no host synchronisation between minibatches:
+// the KL early stop (rl/ppo.jl:59) is evaluated on the device and later kernels become no-ops.
+//
+// `shuffle!` (experience_buffer.jl:118-124) never moves data here: each epoch is an index order
+// consumed by the gather of the minibatch.
+#include "policy.cuh"
+
+namespace {
+
+#define LOG_SQRT_2PI 0.9189385332046727f
+#define ENT_CONST 1.4189385332046727f
+
+// ---- device-side random permutation: 4-round Feistel network with cycle walking ------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__global__ void perm_fill_kernel(int32_t *__restrict__ out, int64_t n, int half_bits, uint64_t seed, uint32_t epoch) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t mask = (1u << half_bits) - 1u;
+  uint64_t x = (uint64_t)i;
+  do {
+    uint32_t l = (uint32_t)(x >> half_bits) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t f = mix32(r ^ mix32((uint32_t)seed + 0x9E3779B9u * (k + 1)) ^ mix32((uint32_t)(seed >> 32) + epoch * 0x85EBCA6Bu + k)) & mask;
+      const uint32_t nl = r; r = l ^ f; l = nl;
+    }
+    x = ((uint64_t)l << half_bits) | r;
+  } while (x >= (uint64_t)n);
+  out[i] = (int32_t)x;
+}
+
+// ctl[0] = skip, ctl[1] = pending stop.  One thread, first kernel of every actor minibatch.
+__global__ void advance_kernel(int *__restrict__ ctl, float *__restrict__ rec) {
+  if (ctl[1]) ctl[0] = 1;
+  rec[CRUX_PPO_VALID] = ctl[0] ? 0.f : 1.f;
+}
+__global__ void reset_ctl_kernel(int *__restrict__ ctl) { ctl[0] = 0; ctl[1] = 0; }
+
+// gather a minibatch: dst columns [bm][d] <- src[idx[i]][d]
+struct GatherCols { const float *src[5]; float *dst[5]; int dim[5]; int n; };
+__global__ void gather_cols_kernel(GatherCols g, const int32_t *__restrict__ idx, int64_t bm, const int *__restrict__ skip) {
+  if (skip && *skip) return;
+  const int c = blockIdx.y;
+  const int d = g.dim[c];
+  const float *src = g.src[c];
+  float *dst = g.dst[c];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < bm * d; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / d; const int col = (int)(i - row * d);
+    dst[i] = src[(int64_t)idx[row] * d + col];
+  }
+}
+
+// ppo_loss / a2c_loss head (rl/ppo.jl:4-21, rl/a2c.jl:4-16) for a state-independent-logΣ GaussianPolicy.
+// One thread per sample.  Writes dL/dmu and block partial sums:
+//  part[b][0..6] = sum surr|logp*A, sum (old-new), clip count, sum adv, sum ret, 0, 0 ; part[b][8+j] = d/dlogΣ_j
+#define HEAD_STRIDE (8 + CRUX_MAX_ADIM)
+__global__ void __launch_bounds__(128)
+ppo_head_kernel(const float *__restrict__ mu, const float *__restrict__ a, const float *__restrict__ old_logp,
+                const float *__restrict__ adv, const float *__restrict__ ret, const float *__restrict__ ls, int A,
+                int64_t bm, float inv_bg, float eps_clip, float lambda_p, int a2c, float *__restrict__ dmu,
+                double *__restrict__ part, const int *__restrict__ skip) {
+  if (skip && *skip) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float s_obj = 0.f, s_kl = 0.f, s_clip = 0.f, s_adv = 0.f, s_ret = 0.f;
+  float dls[CRUX_MAX_ADIM];
+#pragma unroll 8
+  for (int j = 0; j < CRUX_MAX_ADIM; ++j) dls[j] = 0.f;
+  if (i < bm) {
+    float logp = 0.f;
+    for (int j = 0; j < A; ++j) {
+      const float sg = expf(ls[j]);
+      const float d = a[i * A + j] - mu[i * A + j];
+      logp += -(d * d) / (2.f * (sg * sg)) - LOG_SQRT_2PI - ls[j];
+    }
+    const float Ai = adv[i], old = old_logp[i];
+    float dlogp;
+    if (a2c) {
+      s_obj = logp * Ai;
+      dlogp = -lambda_p * inv_bg * Ai;
+    } else {
+      const float r = expf(logp - old);
+      const float lo = 1.f - eps_clip, hi = 1.f + eps_clip;
+      const float x = r * Ai, y = fminf(fmaxf(r, lo), hi) * Ai;
+      const bool first = !(y < x);  // min(x, y) keeps x on ties (Base.min)
+      s_obj = first ? x : y;
+      dlogp = first ? -lambda_p * inv_bg * x : 0.f;  // the clamped branch is only taken outside [lo, hi]: zero slope
+      s_clip = (r > hi || r < lo) ? 1.f : 0.f;
+    }
+    s_kl = old - logp; s_adv = Ai; s_ret = ret ? ret[i] : 0.f;
+    for (int j = 0; j < A; ++j) {
+      const float sg = expf(ls[j]);
+      const float var = sg * sg;
+      const float d = a[i * A + j] - mu[i * A + j];
+      dmu[i * A + j] = dlogp * d / var;
+      dls[j] = dlogp * (d * d / var - 1.f);
+    }
+  }
+  // block reduction (128 threads = 4 warps) in double
+  __shared__ double sh[4][HEAD_STRIDE];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double v;
+  v = warp_sum_d((double)s_obj); if (lane == 0) sh[w][0] = v;
+  v = warp_sum_d((double)s_kl); if (lane == 0) sh[w][1] = v;
+  v = warp_sum_d((double)s_clip); if (lane == 0) sh[w][2] = v;
+  v = warp_sum_d((double)s_adv); if (lane == 0) sh[w][3] = v;
+  v = warp_sum_d((double)s_ret); if (lane == 0) sh[w][4] = v;
+  for (int j = 0; j < A; ++j) { v = warp_sum_d((double)dls[j]); if (lane == 0) sh[w][8 + j] = v; }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 8 + A; k += blockDim.x) {
+    if (k >= 5 && k < 8) { part[(int64_t)blockIdx.x * HEAD_STRIDE + k] = 0.0; continue; }
+    part[(int64_t)blockIdx.x * HEAD_STRIDE + k] = sh[0][k] + sh[1][k] + sh[2][k] + sh[3][k];
+  }
+}
+
+// one block: reduce head partials -> gradient tail (logΣ gradient, sums).  sums: [obj, kl, clip, adv, ret, count]
+__global__ void ppo_finalize_kernel(const double *__restrict__ part, int nblocks, int A, int64_t bm, float lambda_e,
+                                    float *__restrict__ ls_grad, float *__restrict__ sums, const int *__restrict__ skip) {
+  if (skip && *skip) return;
+  const int k = threadIdx.x;
+  if (k >= 8 + A) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * HEAD_STRIDE + k];
+  if (k < 5) sums[k] = (float)s;
+  else if (k == 5) sums[5] = (float)bm;
+  else if (k >= 8) ls_grad[k - 8] = (float)s;  // entropy term added after the all-reduce (record kernel)
+  (void)lambda_e;
+}
+
+// after the (optional) all-reduce: info record, entropy gradient, early-stop vote.  One thread.
+__global__ void ppo_record_kernel(const float *__restrict__ sums, float *__restrict__ ls_grad, const float *__restrict__ ls,
+                                  int A, float lambda_p, float lambda_e, float target_kl, int a2c, int world,
+                                  float *__restrict__ rec, int *__restrict__ ctl) {
+  if (ctl[0]) return;
+  const float cnt = sums[5];
+  float sls = 0.f;
+  for (int j = 0; j < A; ++j) sls += ls[j];
+  const float entropy = ENT_CONST + sls;     // policies.jl:348
+  const float p_loss = -(sums[0] / cnt);
+  const float e_loss = -entropy;
+  rec[CRUX_PPO_LOSS] = lambda_p * p_loss + lambda_e * e_loss;
+  rec[CRUX_PPO_ENTROPY] = entropy;
+  const float kl = sums[1] / cnt;
+  rec[CRUX_PPO_KL] = kl;
+  rec[CRUX_PPO_CLIP_FRAC] = a2c ? 0.f : sums[2] / cnt;
+  rec[CRUX_PPO_AVG_ADV] = sums[3] / cnt;
+  rec[CRUX_PPO_AVG_RET] = sums[4] / cnt;
+  // d(λe * e_loss)/dlogΣ_j = -λe on every rank's replica: not summed over ranks
+  for (int j = 0; j < A; ++j) ls_grad[j] += -lambda_e;
+  if (kl > target_kl) ctl[1] = 1;  // rl/ppo.jl:59 checked after this minibatch's update (training.jl:46)
+  (void)world;
+}
+
+// critic: mse head, dz = 2 (V - R) / Bg, block partial sums of squared error
+__global__ void critic_head_kernel(const float *__restrict__ v, const float *__restrict__ ret, int64_t bm, float inv_bg,
+                                   float *__restrict__ dv, double *__restrict__ part) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < bm; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = v[i] - ret[i];
+    s += (double)(d * d);
+    dv[i] = 2.f * d * inv_bg;
+  }
+  __shared__ double sh[32];
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    s = warp_sum_d(s);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+  }
+}
+__global__ void critic_finalize_kernel(const double *__restrict__ part, int n, int64_t bm, float *__restrict__ sums) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += part[i];
+    sums[0] = (float)s; sums[5] = (float)bm;
+  }
+}
+__global__ void critic_record_kernel(const float *__restrict__ sums, float *__restrict__ rec) {
+  rec[CRUX_PPO_LOSS] = sums[0] / sums[5];
+  rec[CRUX_PPO_VALID] = 1.f;
+}
+
+int ensure_bytes(crux_ctx *ctx, void **p, size_t *have, size_t need) {
+  if (*have >= need) return CRUX_OK;
+  CRUX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (*p) cudaFree(*p);
+  *p = nullptr; *have = 0;
+  if (cudaMalloc(p, need + need / 4 + 256) != cudaSuccess) return crux_set_err(ctx, CRUX_ERR_OOM, "cudaMalloc(%zu)", need);
+  *have = need + need / 4 + 256;
+  return CRUX_OK;
+}
+
+}  // namespace
+
+int crux_ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, const float *a, const float *logprob,
+                          const float *advantage, const float *ret, int64_t n, const crux_ppo_hp *hp,
+                          const int32_t *order_actor, const int32_t *order_critic, int *handled);
+
+static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *s, const float *a, const float *logprob,
+                           const float *advantage, const float *ret, int64_t n, const crux_ppo_hp *hp,
+                           const int32_t *order_actor, const int32_t *order_critic, uint64_t seed) {
+  crux_ctx *ctx = actor->ctx;
+  CRUX_REQUIRE(ctx, hp, "crux_ppo_update: NULL hyper-parameters");
+  CRUX_REQUIRE(ctx, n >= 1, "crux_ppo_update: empty buffer");
+  CRUX_REQUIRE(ctx, s && a && logprob && advantage, "crux_ppo_update: NULL column");
+  CRUX_REQUIRE(ctx, !actor->head_mode && !actor->squashed, "crux_ppo_update: needs GaussianPolicy with a logΣ vector (ppo.jl examples)");
+  CRUX_REQUIRE(ctx, hp->actor_batch >= 1 && hp->actor_epochs >= 0, "crux_ppo_update: bad actor batch/epochs");
+  CRUX_REQUIRE(ctx, n < (1ll << 31), "crux_ppo_update: n must fit int32 indices");
+  crux_mlp *mu = actor->mu;
+  const int sdim = mu->dims[0], A = actor->adim;
+  const int64_t nmb_a = cdiv(n, hp->actor_batch);
+  const int64_t nmb_c = (critic && hp->critic_epochs > 0) ? cdiv(n, hp->critic_batch) : 0;
+  if (nmb_c) {
+    CRUX_REQUIRE(ctx, ret, "crux_ppo_update: critic training needs the :return column");
+    CRUX_REQUIRE(ctx, hp->critic_batch >= 1, "crux_ppo_update: bad critic batch");
+    CRUX_REQUIRE(ctx, critic->dims[0] == sdim && critic->dims[critic->n_layers] == 1, "crux_ppo_update: critic shape");
+  }
+  int rc;
+  // workspaces
+  const int64_t bmax = i64max(i64min(n, hp->actor_batch), nmb_c ? i64min(n, hp->critic_batch) : 0);
+  const size_t mb_floats = (size_t)bmax * (sdim + A + 3);
+  rc = ensure_bytes(ctx, (void **)&actor->mb, &actor->mb_bytes, mb_floats * sizeof(float)); if (rc) return rc;
+  const size_t ia = (size_t)i64max(1, hp->actor_epochs * nmb_a) * CRUX_PPO_INFO_STRIDE * sizeof(float);
+  const size_t ic = (size_t)i64max(1, (int64_t)hp->critic_epochs * nmb_c) * CRUX_PPO_INFO_STRIDE * sizeof(float);
+  rc = ensure_bytes(ctx, (void **)&actor->info_actor, &actor->info_actor_bytes, ia); if (rc) return rc;
+  rc = ensure_bytes(ctx, (void **)&actor->info_critic, &actor->info_critic_bytes, ic); if (rc) return rc;
+  CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(actor->info_actor, 0, ia, ctx->stream));
+  CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(actor->info_critic, 0, ic, ctx->stream));
+  if (!order_actor || (nmb_c && !order_critic)) {
+    rc = ensure_bytes(ctx, (void **)&actor->order, &actor->order_bytes, (size_t)n * sizeof(int32_t)); if (rc) return rc;
+  }
+  rc = mlp_ensure_workspace(mu, bmax); if (rc) return rc;
+  if (nmb_c) { rc = mlp_ensure_workspace(critic, bmax); if (rc) return rc; }
+  int half_bits = 1;
+  while ((1ll << (2 * half_bits)) < n) ++half_bits;
+
+  float *mb_s = actor->mb, *mb_a = mb_s + (size_t)bmax * sdim, *mb_lp = mb_a + (size_t)bmax * A, *mb_adv = mb_lp + bmax,
+        *mb_ret = mb_adv + bmax;
+  int *skip = actor->ctl;
+  reset_ctl_kernel<<<1, 1, 0, ctx->stream>>>(actor->ctl);
+  CRUX_LAUNCHED(ctx);
+  const int L = mu->n_layers;
+  const float inv_world = 1.0f / (float)ctx->world;
+
+  // ---------------- actor: batch_train!(actor(π), a_opt, 𝒫, 𝒟)  on_policy.jl:65
+  int64_t total = 0;
+  const int64_t maxb_a = hp->actor_max_batches > 0 ? hp->actor_max_batches : INT64_MAX;
+  for (int e = 0; e < hp->actor_epochs && total < maxb_a; ++e) {
+    const int32_t *order;
+    if (order_actor) order = order_actor + (int64_t)e * n;
+    else {
+      perm_fill_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(actor->order, n, half_bits, seed, (uint32_t)e);
+      CRUX_LAUNCHED(ctx);
+      order = actor->order;
+    }
+    for (int64_t mbi = 0; mbi < nmb_a && total < maxb_a; ++mbi, ++total) {
+      const int64_t off = mbi * hp->actor_batch, bm = i64min(hp->actor_batch, n - off);
+      float *rec = actor->info_actor + ((int64_t)e * nmb_a + mbi) * CRUX_PPO_INFO_STRIDE;
+      advance_kernel<<<1, 1, 0, ctx->stream>>>(actor->ctl, rec);
+      CRUX_LAUNCHED(ctx);
+      GatherCols g;
+      g.n = 5;
+      g.src[0] = s; g.dst[0] = mb_s; g.dim[0] = sdim;
+      g.src[1] = a; g.dst[1] = mb_a; g.dim[1] = A;
+      g.src[2] = logprob; g.dst[2] = mb_lp; g.dim[2] = 1;
+      g.src[3] = advantage; g.dst[3] = mb_adv; g.dim[3] = 1;
+      g.src[4] = ret ? ret : advantage; g.dst[4] = mb_ret; g.dim[4] = 1;
+      dim3 gg((unsigned)i64min(cdiv(bm * sdim, 256), 1024), 5);
+      gather_cols_kernel<<<gg, 256, 0, ctx->stream>>>(g, order + off, bm, skip);
+      CRUX_LAUNCHED(ctx);
+      rc = mlp_forward_keep(mu, mb_s, bm, skip); if (rc) return rc;
+      const int hb = (int)cdiv(bm, 128);
+      CRUX_REQUIRE(ctx, (size_t)hb * HEAD_STRIDE <= 4096 || true, "");
+      // head partials live in scratch slot 4 (hb blocks x HEAD_STRIDE doubles)
+      double *part = (double *)crux_scratch(ctx, 4, (size_t)hb * HEAD_STRIDE * sizeof(double));
+      if (!part) return CRUX_ERR_OOM;
+      const float inv_bg = 1.0f / ((float)bm * (float)ctx->world);
+      ppo_head_kernel<<<hb, 128, 0, ctx->stream>>>(mu->act[L], mb_a, mb_lp, mb_adv, ret ? mb_ret : nullptr, actor->log_sigma, A, bm,
+                                                   inv_bg, hp->eps_clip, hp->lambda_p, hp->a2c, mu->dz[L], part, skip);
+      CRUX_LAUNCHED(ctx);
+      ppo_finalize_kernel<<<1, 128, 0, ctx->stream>>>(part, hb, A, bm, hp->lambda_e, tail_ls_grad(mu), tail_sums(mu), skip);
+      CRUX_LAUNCHED(ctx);
+      rc = mlp_backward(mu, mb_s, bm, mu->dz[L], false, false, true, skip); if (rc) return rc;
+      if (ctx->world > 1) { rc = grads_allreduce(ctx, mu->grads, mu->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
+      ppo_record_kernel<<<1, 1, 0, ctx->stream>>>(tail_sums(mu), tail_ls_grad(mu), actor->log_sigma, A, hp->lambda_p, hp->lambda_e,
+                                                  hp->target_kl, hp->a2c, ctx->world, rec, actor->ctl);
+      CRUX_LAUNCHED(ctx);
+      AdamSegs segs;
+      segs.n = 2;
+      segs.s[0] = AdamSeg{mu->params, mu->grads, mu->m, mu->v, mu->n_params};
+      segs.s[1] = AdamSeg{actor->log_sigma, tail_ls_grad(mu), actor->ls_m, actor->ls_v, (int64_t)A};
+      rc = adam_step_segments(ctx, segs, mu->eta, mu->beta1, mu->beta2, mu->eps, mu->step_dev, rec + CRUX_PPO_GRAD_NORM, skip,
+                              mu->norm_part);
+      if (rc) return rc;
+    }
+  }
+  (void)inv_world;
+
+  // ---------------- critic: batch_train!(critic(π), c_opt, 𝒫, 𝒟)  on_policy.jl:68-70
+  total = 0;
+  const int64_t maxb_c = hp->critic_max_batches > 0 ? hp->critic_max_batches : INT64_MAX;
+  for (int e = 0; e < hp->critic_epochs && nmb_c && total < maxb_c; ++e) {
+    const int32_t *order;
+    if (order_critic) order = order_critic + (int64_t)e * n;
+    else {
+      perm_fill_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(actor->order, n, half_bits, seed ^ 0xC2B2AE3D27D4EB4FULL, (uint32_t)e);
+      CRUX_LAUNCHED(ctx);
+      order = actor->order;
+    }
+    const int Lc = critic->n_layers;
+    for (int64_t mbi = 0; mbi < nmb_c && total < maxb_c; ++mbi, ++total) {
+      const int64_t off = mbi * hp->critic_batch, bm = i64min(hp->critic_batch, n - off);
+      float *rec = actor->info_critic + ((int64_t)e * nmb_c + mbi) * CRUX_PPO_INFO_STRIDE;
+      GatherCols g;
+      g.n = 2;
+      g.src[0] = s; g.dst[0] = mb_s; g.dim[0] = sdim;
+      g.src[1] = ret; g.dst[1] = mb_ret; g.dim[1] = 1;
+      dim3 gg((unsigned)i64min(cdiv(bm * sdim, 256), 1024), 2);
+      gather_cols_kernel<<<gg, 256, 0, ctx->stream>>>(g, order + off, bm, nullptr);
+      CRUX_LAUNCHED(ctx);
+      rc = mlp_forward_keep(critic, mb_s, bm, nullptr); if (rc) return rc;
+      const int hb = (int)i64min(cdiv(bm, 256), 512);
+      const float inv_bg = 1.0f / ((float)bm * (float)ctx->world);
+      critic_head_kernel<<<hb, 256, 0, ctx->stream>>>(critic->act[Lc], mb_ret, bm, inv_bg, critic->dz[Lc], actor->partials);
+      CRUX_LAUNCHED(ctx);
+      critic_finalize_kernel<<<1, 32, 0, ctx->stream>>>(actor->partials, hb, bm, tail_sums(critic));
+      CRUX_LAUNCHED(ctx);
+      rc = mlp_backward(critic, mb_s, bm, critic->dz[Lc], false, false, true, nullptr); if (rc) return rc;
+      if (ctx->world > 1) { rc = grads_allreduce(ctx, critic->grads, critic->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
+      critic_record_kernel<<<1, 1, 0, ctx->stream>>>(tail_sums(critic), rec);
+      CRUX_LAUNCHED(ctx);
+      rc = mlp_adam_step(critic, rec + CRUX_PPO_GRAD_NORM, nullptr); if (rc) return rc;
+    }
+  }
+  return CRUX_OK;
+}
+
+extern "C" {
+
+int32_t crux_ppo_update_async(crux_gaussian *actor, crux_mlp *critic, const float *s, const float *a, const float *logprob,
+                              const float *advantage, const float *ret, int64_t n, const crux_ppo_hp *hp,
+                              const int32_t *order_actor, const int32_t *order_critic, uint64_t seed) {
+  if (!actor) return CRUX_ERR_INVALID;
+  return ppo_update_impl(actor, critic, s, a, logprob, advantage, ret, n, hp, order_actor, order_critic, seed);
+}
+
+int32_t crux_ppo_info_ptrs(crux_gaussian *actor, float **info_actor_dev, float **info_critic_dev) {
+  if (!actor) return CRUX_ERR_INVALID;
+  if (info_actor_dev) *info_actor_dev = actor->info_actor;
+  if (info_critic_dev) *info_critic_dev = actor->info_critic;
+  return CRUX_OK;
+}
+
+int32_t crux_ppo_update(crux_gaussian *actor, crux_mlp *critic, const float *s, const float *a, const float *logprob,
+                        const float *advantage, const float *ret, int64_t n, const crux_ppo_hp *hp,
+                        const int32_t *order_actor, const int32_t *order_critic, uint64_t seed, float *info_actor_host,
+                        float *info_critic_host) {
+  if (!actor) return CRUX_ERR_INVALID;
+  crux_ctx *ctx = actor->ctx;
+  int rc = ppo_update_impl(actor, critic, s, a, logprob, advantage, ret, n, hp, order_actor, order_critic, seed);
+  if (rc) return rc;
+  const int64_t nmb_a = cdiv(n, hp->actor_batch);
+  const int64_t nmb_c = (critic && hp->critic_epochs > 0) ? cdiv(n, hp->critic_batch) : 0;
+  if (info_actor_host && hp->actor_epochs > 0)
+    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(info_actor_host, actor->info_actor,
+                                         (size_t)hp->actor_epochs * nmb_a * CRUX_PPO_INFO_STRIDE * sizeof(float),
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+  if (info_critic_host && nmb_c)
+    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(info_critic_host, actor->info_critic,
+                                         (size_t)hp->critic_epochs * nmb_c * CRUX_PPO_INFO_STRIDE * sizeof(float),
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+  return crux_ctx_check(ctx);  // synchronises; CRUX_ERR_NAN if a gradient norm was NaN (training.jl:20)
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+"""Device plumbing for the host-side mirror: a context handle and pointer helpers.
+
+Replaces ``src/devices.jl`` (``device``/``mdcall``/``gpucall``/``cpucall``): data lives in HBM and
+never hops per call.  torch is used only for device memory, streams and ``torch.distributed``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi
+
+_TORCH_DT = {_abi.U8: torch.uint8, _abi.F32: torch.float32, _abi.I32: torch.int32, _abi.I64: torch.int64}
+_NP_TYPESTR = {_abi.U8: "|u1", _abi.F32: "<f4", _abi.I32: "<i4", _abi.I64: "<i8"}
+
+
+class _CudaView:
+    def __init__(self, ptr, shape, dtype_code):
+        self.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": _NP_TYPESTR[dtype_code],
+                                         "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def view(ptr, shape, dtype_code=_abi.F32, device=None):
+    """Zero-copy torch view of library-owned device memory (``b[:key]`` semantics: callers write through)."""
+    if int(np.prod(shape)) == 0:
+        return torch.empty(tuple(shape), dtype=_TORCH_DT[dtype_code], device=device or "cuda")
+    return torch.as_tensor(_CudaView(ptr, shape, dtype_code), device=device or "cuda")
+
+
+def ptr(t):
+    """Raw pointer of a tensor / numpy array / None for the C ABI."""
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        assert t.is_contiguous(), "the C ABI takes dense batch-major arrays"
+        return C.c_void_p(t.data_ptr())
+    if isinstance(t, np.ndarray):
+        assert t.flags["C_CONTIGUOUS"]
+        return C.c_void_p(t.ctypes.data)
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    raise TypeError(type(t))
+
+
+class Context:
+    """One per process/GPU.  Fails loudly when no CUDA device is present (no CPU fallback)."""
+
+    def __init__(self, device_index=None, use_torch_stream=True):
+        self.lib = _abi.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("crux.jl_b200 needs a CUDA (sm_100a) device: torch.cuda.is_available() is False "
+                               "and there is no CPU fallback")
+        if device_index is None:
+            device_index = torch.cuda.current_device()
+        torch.cuda.set_device(device_index)
+        self.device = torch.device("cuda", device_index)
+        stream = torch.cuda.current_stream(self.device).cuda_stream if use_torch_stream else None
+        h = C.c_void_p()
+        _abi.check(self.lib.crux_ctx_create(device_index, C.c_void_p(stream) if stream is not None else None, C.byref(h)))
+        self.h = h
+        self.rank, self.world = 0, 1
+
+    def check(self, rc):
+        _abi.check(rc, self.h)
+
+    def sync(self):
+        self.check(self.lib.crux_ctx_sync(self.h))
+
+    def check_flags(self):
+        """Raises NaNError if a device-side NaN was flagged (training.jl:20, sampler.jl:270)."""
+        self.check(self.lib.crux_ctx_check(self.h))
+
+    def launch_count(self):
+        n = C.c_int64()
+        self.check(self.lib.crux_ctx_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def empty(self, shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype=torch.float32):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def to_device(self, x, dtype=None):
+        t = torch.as_tensor(np.ascontiguousarray(x)) if not isinstance(x, torch.Tensor) else x
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.device).contiguous()
+
+    # ---- multi-GPU -------------------------------------------------------------------------
+    def init_distributed(self, rank, world, peer_floats=0):
+        """One rank per GPU.  The NCCL unique id travels through torch.distributed (any backend)."""
+        import torch.distributed as dist
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            _abi.check(self.lib.crux_nccl_unique_id(buf))
+        obj = [bytes(buf)]
+        dist.broadcast_object_list(obj, src=0)
+        idb = (C.c_uint8 * 128).from_buffer_copy(obj[0])
+        self.check(self.lib.crux_nccl_init(self.h, rank, world, idb))
+        self.rank, self.world = rank, world
+        if peer_floats > 0:
+            hb = (C.c_uint8 * 64)()
+            self.check(self.lib.crux_peer_handle(self.h, hb, peer_floats))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(hb))
+            allh = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+            self.check(self.lib.crux_peer_init(self.h, rank, world, allh))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.crux_ctx_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+_default = None
+
+
+def default_context():
+    global _default
+    if _default is None:
+        _default = Context()
+    return _default

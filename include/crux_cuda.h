@@ -1,0 +1,303 @@
+/* crux_cuda.h -- C ABI of libcrux_cuda.so, the B200 (sm_100a) actor-learner hot path
+ * behind the Crux.jl solver surface.
+ *
+ * The reference (sisl/Crux.jl @ d1b6ab5) has no FFI: its boundary is Julia dispatch on
+ * the names exported in src/Crux.jl:34-63.  Every entry point below cites the reference
+ * function it replaces (paths relative to the reference root).  A Julia shim binds these
+ * with `ccall`; tests bind them with Python ctypes.
+ *
+ * Conventions
+ *  - every function returns an int32 status (CRUX_OK == 0); `crux_last_error` gives text.
+ *    Nothing throws or longjmps across the boundary.
+ *  - handles are opaque pointers; one handle is not thread-safe, distinct handles are.
+ *  - all device work is stream-ordered on the context's stream (crux_ctx_set_stream); raw
+ *    pointers are caller-owned device pointers unless a parameter name ends in `_host`.
+ *  - arrays are batch-major `[batch][features]`, i.e. the memory order of the reference's
+ *    column-major `[features, batch]` arrays (src/devices.jl:23-34).  Rollout columns are
+ *    `[T][N]` (row t*N+e): env stream e is one reference `Sampler`.
+ *  - Dense parameters are flat float32, per layer `W` in Julia memory order
+ *    (column-major [out,in] == row-major [in][out]) followed by `b[out]`: Flux.params order.
+ *  - indices cross the ABI 0-based (the Julia shim adds 1).
+ *  - `*_in` pointers that may be NULL are parity hooks: when given, the kernel consumes
+ *    caller-chosen noise / permutations / sample indices instead of the device Philox RNG.
+ */
+#ifndef CRUX_CUDA_H
+#define CRUX_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRUX_ABI_VERSION 1
+
+enum {
+  CRUX_OK = 0,
+  CRUX_ERR_INVALID = 1, /* bad argument (the reference's @assert / MethodError) */
+  CRUX_ERR_CUDA = 2,    /* CUDA runtime failure */
+  CRUX_ERR_NAN = 3,     /* training.jl:20 `error("NaN detected!")`, sampler.jl:270 @assert !isnan(A) */
+  CRUX_ERR_OOM = 4,
+  CRUX_ERR_NCCL = 5,
+  CRUX_ERR_STATE = 6
+};
+
+enum { CRUX_ACT_IDENTITY = 0, CRUX_ACT_TANH = 1, CRUX_ACT_RELU = 2 };
+enum { CRUX_U8 = 0, CRUX_F32 = 1, CRUX_I32 = 2, CRUX_I64 = 3 };
+
+typedef struct crux_ctx crux_ctx;
+typedef struct crux_mlp crux_mlp;
+typedef struct crux_gaussian crux_gaussian;
+typedef struct crux_buffer crux_buffer;
+
+/* ------------------------------------------------------------------ context / devices
+ * replaces src/devices.jl:1-21 (device/gpucall/cpucall/mdcall): data stays on the device. */
+int32_t crux_abi_version(void);
+int32_t crux_ctx_create(int32_t device, void *stream /* cudaStream_t or NULL: own stream */, crux_ctx **out);
+int32_t crux_ctx_destroy(crux_ctx *ctx);
+int32_t crux_ctx_set_stream(crux_ctx *ctx, void *stream);
+int32_t crux_ctx_stream(crux_ctx *ctx, void **stream_out);
+int32_t crux_ctx_sync(crux_ctx *ctx);
+const char *crux_last_error(crux_ctx *ctx /* NULL: last error of a failed crux_ctx_create */);
+/* number of kernels this context has launched since creation (bench `gpu_launches`) */
+int32_t crux_ctx_launch_count(crux_ctx *ctx, int64_t *out);
+/* sticky device-side error flag (NaN in gradients / advantages); reading synchronises. */
+int32_t crux_ctx_check(crux_ctx *ctx);
+
+int32_t crux_dev_alloc(crux_ctx *ctx, size_t bytes, void **out);
+int32_t crux_dev_free(crux_ctx *ctx, void *ptr);
+int32_t crux_pinned_alloc(crux_ctx *ctx, size_t bytes, void **out_host);
+int32_t crux_pinned_free(crux_ctx *ctx, void *ptr_host);
+int32_t crux_memcpy_h2d(crux_ctx *ctx, void *dst, const void *src_host, size_t bytes); /* async */
+int32_t crux_memcpy_d2h(crux_ctx *ctx, void *dst_host, const void *src, size_t bytes); /* async */
+int32_t crux_memcpy_d2d(crux_ctx *ctx, void *dst, const void *src, size_t bytes);
+int32_t crux_memset(crux_ctx *ctx, void *dst, int32_t byte, size_t bytes);
+/* CUDA-graph capture of a fixed launch sequence on the context stream */
+int32_t crux_graph_begin(crux_ctx *ctx);
+int32_t crux_graph_end(crux_ctx *ctx, void **graph_exec_out);
+int32_t crux_graph_launch(crux_ctx *ctx, void *graph_exec);
+int32_t crux_graph_destroy(crux_ctx *ctx, void *graph_exec);
+
+/* ------------------------------------------------------------------ networks
+ * crux_mlp == a Flux `Chain(Dense...)` held by ContinuousNetwork / DiscreteNetwork
+ * (src/policies.jl:68-98,104-157) plus its Adam state (src/training.jl:3, Flux Adam). */
+int32_t crux_mlp_create(crux_ctx *ctx, int32_t n_layers, const int32_t *dims /* n_layers+1 */,
+                        const int32_t *acts /* n_layers */, crux_mlp **out);
+int32_t crux_mlp_destroy(crux_mlp *mlp);
+int32_t crux_mlp_num_params(crux_mlp *mlp, int64_t *out);
+int32_t crux_mlp_set_params(crux_mlp *mlp, const float *flat_host);
+int32_t crux_mlp_get_params(crux_mlp *mlp, float *flat_host); /* synchronises */
+int32_t crux_mlp_params_ptr(crux_mlp *mlp, float **dev_out);
+int32_t crux_mlp_grads_ptr(crux_mlp *mlp, float **dev_out);   /* gradient of the last backward */
+/* Adam(η, (β1,β2), ϵ) with Flux's Float64 scalars; resets the moments (training.jl:3) */
+int32_t crux_mlp_set_adam(crux_mlp *mlp, double eta, double beta1, double beta2, double eps);
+/* value(π, s)  policies.jl:94,120 */
+int32_t crux_mlp_forward(crux_mlp *mlp, const float *x, int64_t B, float *y);
+/* value(π, s, a) = network(vcat(s, a))  policies.jl:96 */
+int32_t crux_mlp_forward_sa(crux_mlp *mlp, const float *s, int32_t sdim, const float *a, int32_t adim,
+                            int64_t B, float *y);
+/* copyto!(to, from) policies.jl:61-65 and polyak_average!(to, from, τ) policies.jl:48-59 */
+int32_t crux_mlp_copy(crux_mlp *to, crux_mlp *from);
+int32_t crux_mlp_polyak(crux_mlp *to, crux_mlp *from, float tau);
+/* one `train!` (training.jl:15-25) of Flux.mse(net(x), y) -- the PPO/A2C critic loss (ppo.jl:60);
+ * info_out_host[0..1] = loss, grad_norm (synchronises).  Mainly a parity hook. */
+int32_t crux_mlp_train_mse(crux_mlp *mlp, const float *x, const float *y, int64_t B, float *info_out_host);
+
+/* GaussianPolicy(μ::ContinuousNetwork, logΣ::AbstractArray) policies.jl:315-350 and
+ * SquashedGaussianPolicy policies.jl:355-400.
+ *   log_sigma_host != NULL : state-independent logΣ vector (ConstantLayer), trainable
+ *   log_sigma_host == NULL : `mu` has 2*adim outputs = [μ | logΣ] heads on a shared trunk
+ *                            (examples/rl/half_cheetah_mujoco.jl:37-43)
+ * The policy borrows `mu` (it must outlive the policy). */
+int32_t crux_gaussian_create(crux_ctx *ctx, crux_mlp *mu, int32_t adim, const float *log_sigma_host,
+                             int32_t squashed, float ascale, crux_gaussian **out);
+int32_t crux_gaussian_destroy(crux_gaussian *pol);
+int32_t crux_gaussian_log_sigma_ptr(crux_gaussian *pol, float **dev_out);
+/* exploration(π, s): a = ε·σ + μ (tanh-squashed if squashed), logprob.  eps_in NULL => Philox(seed, ctr). */
+int32_t crux_gaussian_explore(crux_gaussian *pol, const float *s, int64_t B, const float *eps_in,
+                              uint64_t seed, uint64_t ctr, float *a_out, float *logp_out);
+/* action(π, s): μ(s) (ascale·tanh μ if squashed)  policies.jl:331,372 */
+int32_t crux_gaussian_action(crux_gaussian *pol, const float *s, int64_t B, float *a_out);
+/* logpdf(π, s, a) policies.jl:346,396 ; entropy(π, s) :348 (scalar -> out[0]) / :398 ([B]) */
+int32_t crux_gaussian_logpdf(crux_gaussian *pol, const float *s, const float *a, int64_t B, float *out);
+int32_t crux_gaussian_entropy(crux_gaussian *pol, const float *s, int64_t B, float *out);
+
+/* DiscreteNetwork policies.jl:104-157.  q is [B][nA] from crux_mlp_forward. */
+/* action: argmax index (first max wins) :124 */
+int32_t crux_discrete_argmax(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, int32_t *a_idx);
+/* exploration(::DiscreteNetwork) :137-142 : softmax -> inverse-CDF sample (u_in NULL => Philox), logprob */
+int32_t crux_discrete_explore(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, const double *u_in,
+                              uint64_t seed, uint64_t ctr, int32_t *a_idx, float *logp);
+/* logpdf :144-150 (a one-hot [B][nA] float) and entropy :152-155 */
+int32_t crux_discrete_logpdf(crux_ctx *ctx, const float *q, const float *a_onehot, int64_t B, int32_t nA, float *out);
+int32_t crux_discrete_entropy(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, float *out);
+/* ϵ-greedy exploration(::MixedPolicy) :474-494 over B env streams: with prob eps a uniform action
+ * (u_in[2B]: [coin, pick] pairs, NULL => Philox) else argmax; writes index, one-hot row and logprob. */
+int32_t crux_discrete_eps_greedy(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, double eps,
+                                 const double *u_in, uint64_t seed, uint64_t ctr, int32_t *a_idx,
+                                 float *a_onehot /* nullable */, float *logp /* nullable */);
+
+/* ------------------------------------------------------------------ hot path (i): Sampler.steps!
+ * One vector step of src/sampler.jl:71-137 for N env streams on a Gaussian actor-critic:
+ * reads obs[N][sdim] (already tovec-normalised, spaces.jl:24-25), writes a, logprob, V(s).
+ * critic may be NULL (then v_out is not written). */
+int32_t crux_rollout_step(crux_gaussian *actor, crux_mlp *critic, const float *obs, int64_t N,
+                          const float *eps_in, uint64_t seed, uint64_t ctr, float *a_out,
+                          float *logp_out, float *v_out);
+/* tovec(o, ContinuousSpace) = (o - μ)/σ  spaces.jl:24-25, utils.jl:42 (in place when out == x) */
+int32_t crux_normalize_obs(crux_ctx *ctx, const float *x, int64_t n, float mu, float sigma, float *out);
+
+/* ------------------------------------------------------------------ hot path (ii): advantages / targets
+ * fill_gae! (sampler.jl:262-273) + fill_returns! (:275-281) for every episode range of every env
+ * stream of a [T][N] rollout, as one segmented reverse scan.  adv or ret may be NULL. */
+int32_t crux_fill_gae_returns(crux_ctx *ctx, const float *r, const uint8_t *done, const uint8_t *episode_end,
+                              const float *v_s, const float *v_sp, int64_t T, int64_t N, float gamma,
+                              float lambda, float *adv, float *ret);
+/* whiten(v) utils.jl:41-42 in place (Bessel std, no epsilon); ppo.jl:61, a2c.jl:48.
+ * With NCCL initialised the statistics are all-reduced so every rank whitens identically. */
+int32_t crux_whiten(crux_ctx *ctx, float *x, int64_t n);
+/* dqn_target rl/dqn.jl:4-6 : y = r + γ(1-done)·max_a Q⁻(sp) */
+int32_t crux_dqn_target(crux_ctx *ctx, const float *r, const uint8_t *done, const float *q_sp, int64_t B,
+                        int32_t nA, float gamma, float *y);
+/* sac_target rl/sac.jl:4-9 : y = r + γ(1-done)(min(Q1⁻,Q2⁻) - e^{logα}·logp) */
+int32_t crux_sac_target(crux_ctx *ctx, const float *r, const uint8_t *done, const float *q1, const float *q2,
+                        const float *logp, int64_t B, float gamma, const float *log_alpha_dev, float *y);
+/* td_error utils.jl:112 : |Q(s,a) - y| ; Q(s,a) for a DiscreteNetwork = Σ Q·onehot (policies.jl:122) */
+int32_t crux_td_error(crux_ctx *ctx, const float *q_sa, const float *y, int64_t B, float *out);
+int32_t crux_discrete_q_sa(crux_ctx *ctx, const float *q, const float *a_onehot, int64_t B, int32_t nA, float *out);
+
+/* ------------------------------------------------------------------ hot path (iii): minibatch updates */
+typedef struct crux_ppo_hp {
+  float eps_clip;   /* 𝒫[:ϵ]  ppo.jl:42 */
+  float lambda_p;   /* 𝒫[:λp] */
+  float lambda_e;   /* 𝒫[:λe] */
+  float target_kl;  /* early stop on the last minibatch's KL (ppo.jl:59); +inf disables */
+  int32_t a2c;      /* 1: a2c_loss (rl/a2c.jl:4-16) instead of ppo_loss */
+  int32_t actor_epochs, actor_batch;   /* a_opt TrainingParams (training.jl:1-11) */
+  int32_t critic_epochs, critic_batch; /* c_opt; critic_epochs == 0 skips the critic */
+  int64_t actor_max_batches, critic_max_batches; /* <= 0 : Inf */
+} crux_ppo_hp;
+
+#define CRUX_PPO_INFO_STRIDE 8
+/* per-minibatch info record (float32): written for every minibatch actually trained */
+enum { CRUX_PPO_LOSS = 0, CRUX_PPO_GRAD_NORM = 1, CRUX_PPO_ENTROPY = 2, CRUX_PPO_KL = 3,
+       CRUX_PPO_CLIP_FRAC = 4, CRUX_PPO_AVG_ADV = 5, CRUX_PPO_AVG_RET = 6, CRUX_PPO_VALID = 7 };
+
+/* policy_gradient_training (src/model_free/on_policy.jl:56-78) = batch_train!(actor) then
+ * batch_train!(critic) (src/training.jl:28-55) over the n rows of a rollout buffer.
+ *   order_actor / order_critic : [epochs][n] int32 row orders (the buffer order after that epoch's
+ *     shuffle!, experience_buffer.jl:118-124); NULL => device-generated random permutations.
+ *   info_actor_host  [actor_epochs * ceil(n/actor_batch)][CRUX_PPO_INFO_STRIDE]
+ *   info_critic_host [critic_epochs * ceil(n/critic_batch)][CRUX_PPO_INFO_STRIDE] (loss, grad_norm, valid)
+ * Early stopping is evaluated on the device (no host sync between minibatches); minibatches after
+ * the stop have VALID == 0.  Returns CRUX_ERR_NAN if a gradient norm was NaN (training.jl:20). */
+int32_t crux_ppo_update(crux_gaussian *actor, crux_mlp *critic, const float *s, const float *a,
+                        const float *logprob, const float *advantage, const float *ret, int64_t n,
+                        const crux_ppo_hp *hp, const int32_t *order_actor, const int32_t *order_critic,
+                        uint64_t seed, float *info_actor_host, float *info_critic_host);
+/* same, but asynchronous: info stays in device memory (crux_ppo_info_ptrs) until the caller reads it */
+int32_t crux_ppo_update_async(crux_gaussian *actor, crux_mlp *critic, const float *s, const float *a,
+                              const float *logprob, const float *advantage, const float *ret, int64_t n,
+                              const crux_ppo_hp *hp, const int32_t *order_actor, const int32_t *order_critic,
+                              uint64_t seed);
+int32_t crux_ppo_info_ptrs(crux_gaussian *actor, float **info_actor_dev, float **info_critic_dev);
+
+/* One DQN critic `train!` (off_policy.jl:91-93 with td_loss utils.jl:76-87 on a DiscreteNetwork):
+ * loss = agg((Σ Q(s)·a_onehot - y)²), agg = mean or weighted_mean(weight) (utils.jl:47).
+ * info_out_host[0..2] = loss, grad_norm, Qavg (synchronises; NULL skips the readback). */
+int32_t crux_dqn_train(crux_mlp *q, const float *s, const float *a_onehot, const float *y,
+                       const float *weight /* nullable */, int64_t B, float *info_out_host);
+
+/* One SAC value_training epoch (off_policy.jl:66-111 with rl/sac.jl:4-52) on a sampled minibatch:
+ * target -> temperature step -> double-Q critic step -> actor step -> polyak of the targets.
+ *   eps_target / eps_temp / eps_actor : [B][adim] noise for the three exploration() draws (NULL => Philox)
+ *   log_alpha_dev : 1 float, trained by Adam(alpha_eta) with moments alpha_state_dev[2] + betas on host side
+ * info_out_host[0..7] = temp_loss, critic_loss, critic_grad_norm, actor_loss, actor_grad_norm, entropy, Q1avg, Q2avg */
+typedef struct crux_sac_state crux_sac_state;
+int32_t crux_sac_create(crux_gaussian *actor, crux_mlp *q1, crux_mlp *q2, crux_mlp *q1_target, crux_mlp *q2_target,
+                        float log_alpha, float h_target, double alpha_eta, float tau, crux_sac_state **out);
+int32_t crux_sac_destroy(crux_sac_state *st);
+int32_t crux_sac_log_alpha(crux_sac_state *st, float *out_host);
+int32_t crux_sac_train(crux_sac_state *st, const float *s, const float *a, const float *sp, const float *r,
+                       const uint8_t *done, int64_t B, float gamma, const float *eps_target,
+                       const float *eps_temp, const float *eps_actor, uint64_t seed, uint64_t ctr,
+                       float *y_out /* nullable [B] */, float *info_out_host /* nullable */);
+
+/* ------------------------------------------------------------------ ExperienceBuffer (src/experience_buffer.jl)
+ * Device-resident structure-of-arrays ring buffer.  Column ids are caller-chosen small integers
+ * (the shim maps Symbols :s,:a,:sp,:r,:done,:episode_end,... to ids). */
+typedef struct crux_col_desc {
+  int32_t id;      /* 0..63 */
+  int32_t dtype;   /* CRUX_U8 / CRUX_F32 / CRUX_I32 / CRUX_I64 */
+  int64_t rowlen;  /* elements per row (prod(dim(space))) */
+  double init;     /* fill value (mdp_data: zeros / ones for weights, experience_buffer.jl:4-35) */
+} crux_col_desc;
+
+int32_t crux_buffer_create(crux_ctx *ctx, int64_t capacity, int32_t n_cols, const crux_col_desc *cols,
+                           int32_t prioritized, float alpha, crux_buffer **out);
+int32_t crux_buffer_destroy(crux_buffer *buf);
+/* b.data[k] : zero-copy device pointer of a whole column (b[:key] is its first `elements` rows, :173) */
+int32_t crux_buffer_col(crux_buffer *buf, int32_t col_id, void **dev_ptr, int64_t *rowlen, int32_t *dtype);
+/* elements, next_ind (0-based), total_count, capacity  (experience_buffer.jl:53-60,183-185) */
+int32_t crux_buffer_state(crux_buffer *buf, int64_t *elements, int64_t *next_ind, int64_t *total_count,
+                          int64_t *capacity);
+int32_t crux_buffer_clear(crux_buffer *buf); /* clear! :97-104 */
+/* push!(b, data; ids) :232-259.  col_ptrs[i] is the source column for col_ids[i] (host memory if
+ * src_on_host, else device); ids (nullable, device int32 if !src_on_host else host) gathers source rows.
+ * New rows of a prioritized buffer get max_priority.  first_index_out: 0-based ring position of row 0. */
+int32_t crux_buffer_push(crux_buffer *buf, int64_t n_rows, int32_t n_src_cols, const int32_t *col_ids,
+                         const void *const *col_ptrs, int32_t src_on_host, const int32_t *ids,
+                         int64_t *first_index_out);
+/* push!(target, source, ids = ids) for two device buffers (uniform_sample! :317-321 after the draw) */
+int32_t crux_buffer_push_from(crux_buffer *target, crux_buffer *source, int64_t n_rows,
+                              const int32_t *ids_dev /* nullable: rows 0..n-1 */);
+/* get_last_N_indices :223-229 -> host int64[min(N,len)] 0-based; returns count in n_out */
+int32_t crux_buffer_last_n_indices(crux_buffer *buf, int64_t N, int64_t *out_host, int64_t *n_out);
+/* uniform_sample! :317-321 : ids_in_host (0-based, nullable => Philox) -> target.indices, rows gathered */
+int32_t crux_buffer_sample_uniform(crux_buffer *target, crux_buffer *source, int64_t B, const int32_t *ids_in_host,
+                                   uint64_t seed, uint64_t ctr);
+/* prioritized_sample! :324-349 : device prefix-sum of priorities (cached until priorities change),
+ * stratified searchsortedfirst with Float64 thresholds (u_in_host[B] nullable => Philox), IS weights written
+ * into the source's weight column (col id weight_col) and rows gathered into target. */
+int32_t crux_buffer_sample_prioritized(crux_buffer *target, crux_buffer *source, int64_t B, float beta,
+                                       int32_t weight_col, const double *u_in_host, uint64_t seed, uint64_t ctr);
+/* target.indices of the last sample (device int32[B]) */
+int32_t crux_buffer_indices(crux_buffer *buf, int32_t **idx_dev, int64_t *n);
+/* update_priorities!(b, I, v) :290-301 : I device int32 (0-based), v device float32 */
+int32_t crux_buffer_update_priorities(crux_buffer *buf, const int32_t *idx_dev, const float *v_dev, int64_t n);
+/* priority state: device pointers to priorities[capacity] and the cached prefix sum; host copies of
+ * max_priority / min_priority (synchronises) */
+int32_t crux_buffer_priorities(crux_buffer *buf, float **prs_dev, float **cumsum_dev, float *max_p, float *min_p);
+/* split_batches(N, fracs) :126-131 (host integer arithmetic) */
+int32_t crux_split_batches(int64_t N, const double *fracs, int32_t n_fracs, int64_t *out);
+/* generic row gather: dst[i] = src[idx[i]] for rows of `rowbytes` bytes (minibatch(), :170) */
+int32_t crux_gather_rows(crux_ctx *ctx, void *dst, const void *src, const int32_t *idx_dev, int64_t n,
+                         int64_t rowbytes);
+
+/* ------------------------------------------------------------------ synthetic device-side MDP (bench `value` leg)
+ * "LinQuad" MDP of SURVEY 8d stepped on the device: s' = clip(A s + B tanh(a) + 0.01 ξ, -10, 10), ...
+ * A_host [sdim][sdim], B_host [sdim][adim] row-major.  Handles reset (done or t >= max_steps):
+ * writes sp (pre-reset), r, done, episode_end and the next obs (post-reset) in one kernel. */
+typedef struct crux_linquad crux_linquad;
+int32_t crux_linquad_create(crux_ctx *ctx, int32_t sdim, int32_t adim, const float *A_host, const float *B_host,
+                            int64_t n_env, int32_t max_steps, uint64_t seed, crux_linquad **out);
+int32_t crux_linquad_destroy(crux_linquad *env);
+int32_t crux_linquad_reset(crux_linquad *env, float *obs_out);
+int32_t crux_linquad_step(crux_linquad *env, const float *obs, const float *a, float *sp, float *r, uint8_t *done,
+                          uint8_t *episode_end, float *next_obs, int32_t force_end /* last step of a rollout */);
+
+/* ------------------------------------------------------------------ multi-GPU (one rank per GPU)
+ * NCCL is resolved at run time (dlopen libnccl.so.2).  After crux_nccl_init every gradient produced by
+ * crux_*_update / crux_*_train is summed over ranks before Adam and minibatch means use the global count. */
+int32_t crux_nccl_unique_id(uint8_t *id_out_host /* 128 bytes */);
+int32_t crux_nccl_init(crux_ctx *ctx, int32_t rank, int32_t world, const uint8_t *id_host);
+int32_t crux_nccl_allreduce_f32(crux_ctx *ctx, float *buf, int64_t n); /* in-place sum */
+/* one-shot peer all-reduce over NVLink (CUDA IPC): exchange handles through the host. */
+int32_t crux_peer_handle(crux_ctx *ctx, uint8_t *handle_out_host /* 64 bytes */, int64_t max_floats);
+int32_t crux_peer_init(crux_ctx *ctx, int32_t rank, int32_t world, const uint8_t *handles_host /* world*64 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRUX_CUDA_H */
