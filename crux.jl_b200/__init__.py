@@ -1,0 +1,15 @@
+"""crux.jl_b200 -- host-side mirror of the Crux.jl solver surface driving libcrux_cuda.so (sm_100a).
+
+Only what the hot path needs: policies, ExperienceBuffer, Sampler, PPO/A2C/DQN/SAC + solve.
+Import as ``import crux_b200 as crux`` (see crux_b200.py at the repo root).  There is no CPU fallback:
+constructing anything that touches the device raises if the CUDA library or a GPU is missing.
+"""
+from . import _abi  # noqa: F401
+from ._abi import CruxError, NaNError  # noqa: F401
+from .device import Context, default_context  # noqa: F401
+from .spaces import ContinuousSpace, DiscreteSpace, dim, state_space, tovec, whiten  # noqa: F401
+from .policies import (ActorCritic, Chain, ContinuousNetwork, Dense, DiscreteNetwork, DoubleNetwork,  # noqa: F401
+                       FirstExplorePolicy, GaussianNoiseExplorationPolicy, GaussianPolicy, LinearDecaySchedule,
+                       MixedPolicy, PolicyParams, SquashedGaussianPolicy, action, action_space, actor, copyto_,
+                       critic, deepcopy, entropy, eps_greedy_policy, exploration, glorot_uniform, identity, logpdf,
+                       polyak_average_, relu, tanh, value)

@@ -16,6 +16,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NAN, ERR_OOM, ERR_NCCL, ERR_STATE = range(7)
 ACT_IDENTITY, ACT_TANH, ACT_RELU = 0, 1, 2
 U8, F32, I32, I64 = 0, 1, 2, 3
 PPO_INFO_STRIDE = 8
+STREAM_LEGACY = 1  # CRUX_STREAM_LEGACY == cudaStreamLegacy
 PPO_LOSS, PPO_GRAD_NORM, PPO_ENTROPY, PPO_KL, PPO_CLIP_FRAC, PPO_AVG_ADV, PPO_AVG_RET, PPO_VALID = range(8)
 
 

@@ -56,7 +56,11 @@ class Context:
             device_index = torch.cuda.current_device()
         torch.cuda.set_device(device_index)
         self.device = torch.device("cuda", device_index)
-        stream = torch.cuda.current_stream(self.device).cuda_stream if use_torch_stream else None
+        # share torch's current stream so torch copies and library kernels are ordered; torch reports the default
+        # stream as 0, which the ABI spells CRUX_STREAM_LEGACY (NULL would mean "create your own stream")
+        stream = None
+        if use_torch_stream:
+            stream = torch.cuda.current_stream(self.device).cuda_stream or _abi.STREAM_LEGACY
         h = C.c_void_p()
         _abi.check(self.lib.crux_ctx_create(device_index, C.c_void_p(stream) if stream is not None else None, C.byref(h)))
         self.h = h

@@ -1,0 +1,148 @@
+"""Vectorised environments driven by ``Sampler`` (the role POMDPs.jl models play for the reference, src/sampler.jl:39-50,89-97).
+
+The reference steps ONE ``mdp`` through ``@gen(:sp,:r)`` / ``isterminal`` / ``initialstate``.  Here an environment object
+steps N independent copies at once (each copy is one reference ``Sampler`` stream):
+
+    env.n_envs, env.obs_dim, env.gamma (= POMDPs.discount), env.action_space
+    env.reset(idx | None) -> obs[len(idx), obs_dim]         # rand(initialstate(mdp)) + convert_s for those streams
+    env.step(a)           -> (sp, r, done)                  # @gen(:sp,:r)(mdp, s, a), convert_s, isterminal
+
+Host environments exchange numpy arrays; a device environment (``on_device = True``) exchanges device pointers and its
+step never leaves the GPU.  These synthetic MDPs are NOT part of the reference: they are the benchmark workloads of
+SURVEY 8d ("LinQuad-17x6") and the restated ``SimpleGridWorld`` of the README example.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .device import default_context, ptr
+from .spaces import ContinuousSpace, DiscreteSpace
+
+F32 = np.float32
+
+
+def linquad_matrices(obs_dim=17, act_dim=6, seed=0):
+    """A = 0.95 I + 0.02 G1, B = 0.1 G2, G ~ default_rng(seed).standard_normal (float32)  (SURVEY 8d)."""
+    rng = np.random.default_rng(seed)
+    G1 = rng.standard_normal((obs_dim, obs_dim)).astype(F32)
+    G2 = rng.standard_normal((obs_dim, act_dim)).astype(F32)
+    A = (F32(0.95) * np.eye(obs_dim, dtype=F32) + F32(0.02) * G1).astype(F32)
+    B = (F32(0.1) * G2).astype(F32)
+    return np.ascontiguousarray(A), np.ascontiguousarray(B)
+
+
+class HostLinQuad:
+    """LinQuad on the host (numpy): s' = clip(A s + B tanh(a) + 0.01 ξ, -10, 10); r = 1 - |s'|²/S - 0.1|a|²/A;
+    terminal if |s'_1| > 5; s0 ~ U(-0.1, 0.1)^S; γ = 0.99."""
+    on_device = False
+
+    def __init__(self, n_envs, obs_dim=17, act_dim=6, seed=0, gamma=0.99):
+        self.n_envs, self.obs_dim, self.act_dim = int(n_envs), obs_dim, act_dim
+        self.A, self.B = linquad_matrices(obs_dim, act_dim, 0)
+        self.AT, self.BT = np.ascontiguousarray(self.A.T), np.ascontiguousarray(self.B.T)
+        self.gamma = F32(gamma)
+        self.rng = np.random.default_rng(seed)
+        self.action_space = ContinuousSpace(act_dim)
+        self.state = np.zeros((self.n_envs, obs_dim), dtype=F32)
+
+    def reset(self, idx=None):
+        n = self.n_envs if idx is None else len(idx)
+        s0 = ((self.rng.random((n, self.obs_dim), dtype=F32) * F32(2) - F32(1)) * F32(0.1)).astype(F32)
+        if idx is None:
+            self.state[:] = s0
+        else:
+            self.state[idx] = s0
+        return s0
+
+    def step(self, a):
+        a = np.asarray(a, dtype=F32)
+        xi = self.rng.standard_normal((self.n_envs, self.obs_dim), dtype=F32)
+        sp = self.state @ self.AT
+        sp += np.tanh(a) @ self.BT
+        sp += F32(0.01) * xi
+        np.clip(sp, F32(-10), F32(10), out=sp)
+        r = (F32(1) - np.einsum("ij,ij->i", sp, sp) / F32(self.obs_dim) - F32(0.1) * np.einsum("ij,ij->i", a, a) / F32(self.act_dim)).astype(F32)
+        done = np.abs(sp[:, 0]) > F32(5)
+        self.state = sp
+        return sp, r, done
+
+
+class DeviceLinQuad:
+    """The same MDP stepped on the GPU (``crux_linquad_*``): observations, actions and transitions never leave HBM.
+    Episode bookkeeping (episode_length, max_steps, reset) is done inside the step kernel like ``step!`` does
+    (sampler.jl:130-136)."""
+    on_device = True
+
+    def __init__(self, n_envs, obs_dim=17, act_dim=6, seed=0, gamma=0.99, max_steps=1000, ctx=None):
+        self.ctx = ctx or default_context()
+        self.n_envs, self.obs_dim, self.act_dim = int(n_envs), obs_dim, act_dim
+        self.gamma, self.max_steps = F32(gamma), int(max_steps)
+        self.action_space = ContinuousSpace(act_dim)
+        A, B = linquad_matrices(obs_dim, act_dim, 0)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.crux_linquad_create(self.ctx.h, obs_dim, act_dim, ptr(A), ptr(B), self.n_envs, self.max_steps,
+                                                        int(seed), C.byref(h)))
+        self.h = h
+
+    def reset_into(self, obs_out):
+        self.ctx.check(self.ctx.lib.crux_linquad_reset(self.h, ptr(obs_out)))
+
+    def step_into(self, obs, a, sp, r, done, episode_end, next_obs, force_end=False):
+        self.ctx.check(self.ctx.lib.crux_linquad_step(self.h, ptr(obs), ptr(a), ptr(sp), ptr(r), ptr(done), ptr(episode_end),
+                                                      ptr(next_obs), 1 if force_end else 0))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.ctx.h:
+                self.ctx.lib.crux_linquad_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class SimpleGridWorld:
+    """POMDPModels.SimpleGridWorld restated [3P]: 10x10 grid, actions up/down/left/right, rewards
+    {(4,3): -10, (4,6): -5, (9,3): +10, (8,8): +3} (acting from a reward cell pays it and ends the episode), the move
+    succeeds with probability 0.7 (otherwise one of the other three directions, uniformly), walls keep the agent in
+    place, γ = 0.95, initial state uniform over the grid.  ``convert_s`` gives the 2-vector (x, y)
+    (test/spaces_tests.jl:42-43).  N independent copies."""
+    on_device = False
+    MOVES = np.array([[0, 1], [0, -1], [-1, 0], [1, 0]])  # :up, :down, :left, :right
+
+    def __init__(self, n_envs=1, size=(10, 10), tprob=0.7, gamma=0.95, seed=0, rewards=None):
+        self.n_envs, self.size, self.tprob = int(n_envs), size, tprob
+        self.obs_dim, self.gamma = 2, F32(gamma)
+        self.rewards = rewards or {(4, 3): -10.0, (4, 6): -5.0, (9, 3): 10.0, (8, 8): 3.0}
+        self.rmap = np.zeros((size[0] + 1, size[1] + 1), dtype=F32)
+        for (x, y), v in self.rewards.items():
+            self.rmap[x, y] = v
+        self.action_space = DiscreteSpace(4, [0, 1, 2, 3])
+        self.rng = np.random.default_rng(seed)
+        self.state = np.ones((self.n_envs, 2), dtype=np.int64)
+
+    def reset(self, idx=None):
+        n = self.n_envs if idx is None else len(idx)
+        s0 = np.stack([self.rng.integers(1, self.size[0] + 1, n), self.rng.integers(1, self.size[1] + 1, n)], 1)
+        if idx is None:
+            self.state[:] = s0
+        else:
+            self.state[idx] = s0
+        return s0.astype(F32)
+
+    def step(self, a):
+        a = np.asarray(a).astype(np.int64).reshape(-1)
+        s = self.state
+        r = self.rmap[s[:, 0], s[:, 1]].copy()
+        done = r != 0  # acting from a reward cell moves to the terminal state
+        ok = self.rng.random(self.n_envs) < self.tprob
+        other = (a + self.rng.integers(1, 4, self.n_envs)) % 4
+        d = np.where(ok, a, other)
+        sp = s + self.MOVES[d]
+        sp[:, 0] = np.clip(sp[:, 0], 1, self.size[0])
+        sp[:, 1] = np.clip(sp[:, 1], 1, self.size[1])
+        sp[done] = -1  # GWPos(-1,-1): the terminal state
+        self.state = sp
+        return sp.astype(F32), r, done

@@ -1,0 +1,300 @@
+"""Host-side mirror of ``src/sampler.jl``: ``Sampler``, ``steps_`` (``steps!``), ``fill_gae_``/``fill_returns_``.
+
+One ``Sampler`` drives N independent env streams at once (the reference steps one env per ``Sampler`` and loops a vector
+of samplers sequentially, sampler.jl:157-173).  Rollout rows are laid out ``[T][N]`` (row ``t*N + e``, the reference's own
+interleaving ``j = (step-1)*Nenv + env``); every stream follows the single-env rules of ``step!`` (sampler.jl:71-137):
+episode_length, ``done || episode_length >= max_steps`` -> ``terminate_episode!`` (episode_end flag, reset), and the
+forced termination of ``steps!(reset=true)`` (:148).  Advantages and returns are filled for all episode ranges at once
+by the segmented scan ``crux_fill_gae_returns`` after V(s) and V(sp) have been evaluated in two batched critic passes
+(the reference calls ``value`` twice per transition, sampler.jl:262-273).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _abi
+from .buffer import ExperienceBuffer, mdp_data, _TORCH
+from .device import ptr
+from .policies import (ActorCritic, ContinuousNetwork, DiscreteNetwork, GaussianPolicy, MixedPolicy, Policy, PolicyParams,
+                       action, actor, critic, exploration)
+from .spaces import ContinuousSpace, DiscreteSpace
+
+F32 = np.float32
+
+
+class Sampler:
+    """sampler.jl:1-22.  ``mdp`` is a vectorised environment (crux.jl_b200/envs.py protocol)."""
+
+    def __init__(self, mdp, agent, S=None, max_steps=100, required_columns=(), lam=float("nan"), gamma=None, seed=0):
+        self.mdp = mdp
+        self.agent = agent if isinstance(agent, PolicyParams) else PolicyParams(agent)
+        self.ctx = self.agent.pi.ctx
+        self.n = int(mdp.n_envs)
+        self.S = S if S is not None else ContinuousSpace(mdp.obs_dim)
+        self.max_steps = int(max_steps)
+        self.required_columns = list(required_columns)
+        self.gamma = F32(mdp.gamma if gamma is None else gamma)
+        self.lam = F32(lam)
+        self.seed = int(seed)
+        self.noise_ctr = 0          # Philox stream position of the exploration noise
+        self.on_device = bool(getattr(mdp, "on_device", False))
+        self.sdim = int(np.prod(self.S.dims))
+        self.episode_length = np.zeros(self.n, dtype=np.int64)
+        self.cur = self.ctx.empty((self.n, self.sdim))   # current observation of every stream (device)
+        self._pinned = None
+        self._scratch = {}
+        self.reset_()
+
+    # ---- reset_sampler! (sampler.jl:31-43) for every stream
+    def reset_(self):
+        if self.on_device:
+            self.mdp.max_steps = self.max_steps
+            self.mdp.reset_into(self.cur)
+        else:
+            o = self._tovec(self.mdp.reset(None))
+            self._pin()
+            self._pinned["obs"].copy_(torch.from_numpy(o))
+            self.cur.copy_(self._pinned["obs"], non_blocking=True)
+        self.episode_length[:] = 0
+
+    def _tovec(self, o):
+        """tovec(o, S) spaces.jl:24-25 for a ContinuousSpace: (o - μ)/σ."""
+        o = np.asarray(o, dtype=F32).reshape(-1, self.sdim)
+        mu, sg = getattr(self.S, "mu", 0), getattr(self.S, "sigma", 1)
+        if np.any(np.asarray(mu) != 0) or np.any(np.asarray(sg) != 1):
+            o = ((o - F32(mu)) / F32(sg)).astype(F32)
+        return o
+
+    def _pin(self):
+        if self._pinned is not None:
+            return
+        n, sd = self.n, self.sdim
+        A = self.agent.space
+        adim = A.N if isinstance(A, DiscreteSpace) else int(np.prod(A.dims))
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+        self._pinned = {"obs": mk((n, sd), torch.float32), "sp": mk((n, sd), torch.float32), "r": mk((n,), torch.float32),
+                        "done": mk((n,), torch.uint8), "ee": mk((n,), torch.uint8), "t": mk((n,), torch.int64),
+                        "a": mk((n, adim), torch.float32), "ai": mk((n,), torch.int32)}
+
+    def _tmp(self, name, shape, dtype=torch.float32):
+        t = self._scratch.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.ctx.device)
+            self._scratch[name] = t
+        return t
+
+    # ---- exploration / action for all streams at once (sampler.jl:73)
+    def _act(self, obs, a_out, logp_out, explore, i, noise=None):
+        """Writes the stored action rows (continuous vector / one-hot) and logprob; returns what the env consumes."""
+        ag, ctx = self.agent, self.ctx
+        pi, pe = ag.pi, ag.pi_explore
+        discrete = isinstance(ag.space, DiscreteSpace)
+        ctr = self.noise_ctr
+        self.noise_ctr += 1
+        if not explore:
+            a = action(pi, obs)
+            if discrete:
+                a_out.zero_()
+                a_out.scatter_(1, a.long().reshape(-1, 1), 1.0)
+                if logp_out is not None:
+                    logp_out.fill_(float("nan"))
+                return a
+            a_out.copy_(a)
+            if logp_out is not None:
+                logp_out.fill_(float("nan"))
+            return a_out
+        if isinstance(pe, Policy) and hasattr(pe, "exploration") and not isinstance(pe, (GaussianPolicy, ActorCritic, DiscreteNetwork, ContinuousNetwork)):
+            if isinstance(pe, MixedPolicy):
+                idx, oh, lp = pe.exploration(obs, pi, i, u=noise, seed=self.seed, ctr=ctr)
+                a_out.copy_(oh)
+                if logp_out is not None:
+                    logp_out.copy_(lp.reshape(logp_out.shape))
+                return idx
+            a, lp = pe.exploration(obs, pi, i, **({"eps": noise} if noise is not None else {}))
+            a_out.copy_(a.reshape(a_out.shape))
+            if logp_out is not None:
+                logp_out.fill_(float("nan") if isinstance(lp, float) else 0.0)
+            return a_out
+        act_pi = actor(pe)
+        if isinstance(act_pi, GaussianPolicy):
+            # hot path (i): one fused launch sequence writes a and logprob straight into the rollout rows
+            eps = None if noise is None else ctx.to_device(noise, torch.float32)
+            ctx.check(ctx.lib.crux_rollout_step(act_pi.h, None, ptr(obs), obs.shape[0], ptr(eps), self.seed, ctr, ptr(a_out),
+                                                ptr(logp_out), None))
+            return a_out
+        if isinstance(act_pi, DiscreteNetwork):
+            idx, lp = exploration(act_pi, obs, eps=noise, seed=self.seed, ctr=ctr)
+            a_out.zero_()
+            a_out.scatter_(1, idx.long().reshape(-1, 1), 1.0)
+            if logp_out is not None:
+                logp_out.copy_(lp.reshape(logp_out.shape))
+            return idx
+        raise TypeError(f"Sampler: unsupported exploration policy {type(pe).__name__}")
+
+    # ---- steps! (sampler.jl:139-155) over N streams
+    def steps_(self, buffer=None, Nsteps=1, explore=False, i=0, reset=False, cb=None, store=None, noise=None):
+        """Collect ``Nsteps`` transitions (= ``Nsteps / n`` vector steps) and push them to ``buffer``.
+        ``noise``: optional per-vector-step list of injected exploration noise (parity runs).  Returns the rollout
+        columns (device views, ``[Nsteps, ...]``)."""
+        n = self.n
+        assert Nsteps % n == 0, f"Nsteps={Nsteps} must be a multiple of the {n} env streams"
+        T = Nsteps // n
+        cols = self.required_columns
+        in_place = False
+        if buffer is not None:
+            start0 = buffer.next_ind - 1
+            in_place = start0 + Nsteps <= buffer.capacity and all(k in buffer.schema for k in cols)
+        if in_place:  # zero-copy: rollout rows are the buffer's own rows (push! would copy them there anyway)
+            data = {k: buffer.column(k)[start0:start0 + Nsteps] for k in buffer.schema}
+        else:
+            data = self._alloc(Nsteps)
+        logp = data.get("logprob")
+        discrete = isinstance(self.agent.space, DiscreteSpace)
+        if self.on_device:
+            self._rollout_device(data, T, explore, i, reset, noise)
+        else:
+            self._rollout_host(data, T, explore, i, reset, noise, discrete)
+        # terminate_episode! bookkeeping for all closed ranges at once (sampler.jl:56-57)
+        if "advantage" in data or "return" in data:
+            self.fill_gae_returns_(data, T)
+        if cb is not None:
+            cb(data)
+        if store is not None:
+            store.append({k: v.clone() for k, v in data.items()})
+        if buffer is not None:
+            if in_place:
+                buffer.commit_rows_(Nsteps)
+            else:
+                buffer.push_(data)
+        return data
+
+    def _alloc(self, Nsteps):
+        schema = mdp_data(self.S, self.agent.space, Nsteps, self.required_columns)
+        out = {}
+        for k, (dt, dims, init) in schema.items():
+            t = self._tmp("col_" + k, (Nsteps, *dims), _TORCH[dt])
+            t.fill_(init)
+            out[k] = t
+        return out
+
+    def _rollout_device(self, data, T, explore, i, reset, noise):
+        n, env = self.n, self.mdp
+        s, a, sp, r = data["s"], data["a"], data["sp"], data["r"]
+        done, ee, logp = data["done"], data["episode_end"], data.get("logprob")
+        s[:n].copy_(self.cur)
+        for t in range(T):
+            rows = slice(t * n, (t + 1) * n)
+            self._act(s[rows], a[rows], None if logp is None else logp[rows], explore, i + t * n, None if noise is None else noise[t])
+            nxt = s[(t + 1) * n:(t + 2) * n] if t + 1 < T else self.cur
+            env.step_into(s[rows], a[rows], sp[rows], r[rows], done[rows], ee[rows], nxt, force_end=(reset and t == T - 1))
+
+    def _rollout_host(self, data, T, explore, i, reset, noise, discrete):
+        n, env, P = self.n, self.mdp, None
+        self._pin()
+        P = self._pinned
+        s, a, sp, r = data["s"], data["a"], data["sp"], data["r"]
+        done, ee, logp, tcol, icol = data["done"], data["episode_end"], data.get("logprob"), data.get("t"), data.get("i")
+        stream = torch.cuda.current_stream(self.ctx.device)
+        for t in range(T):
+            rows = slice(t * n, (t + 1) * n)
+            s[rows].copy_(P["obs"], non_blocking=True)                       # H2D: svec of every stream
+            env_a = self._act(s[rows], a[rows], None if logp is None else logp[rows], explore, i + t * n,
+                              None if noise is None else noise[t])
+            if discrete:
+                P["ai"].copy_(env_a.reshape(-1), non_blocking=True)
+            else:
+                P["a"].copy_(env_a, non_blocking=True)                       # D2H: the env needs the action
+            stream.synchronize()
+            spn, rn, dn = env.step(P["ai"].numpy() if discrete else P["a"].numpy())   # @gen(:sp,:r), isterminal
+            spv = self._tovec(spn)
+            P["t"].copy_(torch.from_numpy(self.episode_length + 1))
+            self.episode_length += 1                                          # sampler.jl:130
+            end = np.asarray(dn, dtype=bool) | (self.episode_length >= self.max_steps)
+            if reset and t == T - 1:
+                end = np.ones(n, dtype=bool)                                  # steps!(reset=true) :148
+            P["sp"].copy_(torch.from_numpy(spv))
+            P["r"].copy_(torch.from_numpy(np.asarray(rn, dtype=F32)))
+            P["done"].copy_(torch.from_numpy(np.asarray(dn, dtype=np.uint8)))
+            P["ee"].copy_(torch.from_numpy(end.astype(np.uint8)))
+            sp[rows].copy_(P["sp"], non_blocking=True)                       # H2D: the transition
+            r[rows].copy_(P["r"].reshape(r[rows].shape), non_blocking=True)
+            done[rows].copy_(P["done"].reshape(done[rows].shape), non_blocking=True)
+            ee[rows].copy_(P["ee"].reshape(ee[rows].shape), non_blocking=True)
+            if tcol is not None:
+                tcol[rows].copy_(P["t"].reshape(tcol[rows].shape), non_blocking=True)
+            if icol is not None:
+                icol[rows].fill_(i + t * n + 1)
+            nxt = spv
+            if end.any():                                                     # terminate_episode! -> reset_sampler!
+                idx = np.flatnonzero(end)
+                nxt = spv.copy()
+                nxt[idx] = self._tovec(env.reset(idx))
+                self.episode_length[idx] = 0
+            P["obs"].copy_(torch.from_numpy(nxt))
+        self.cur.copy_(P["obs"], non_blocking=True)
+
+    # ---- fill_gae! / fill_returns! (sampler.jl:255-281) for every episode range of every stream
+    def fill_gae_returns_(self, data, T):
+        ctx, n = self.ctx, self.n
+        adv, ret = data.get("advantage"), data.get("return")
+        vs = vsp = None
+        if adv is not None:
+            V = critic(self.agent.pi)
+            assert isinstance(V, ContinuousNetwork) and not math.isnan(float(self.lam)), "GAE needs a critic and λ"
+            vs, vsp = self._tmp("v_s", (T * n, 1)), self._tmp("v_sp", (T * n, 1))
+            V.mlp.forward(data["s"], out=vs)      # value(V, s_i) for every row
+            V.mlp.forward(data["sp"], out=vsp)    # value(V, sp_i): the stored next observation (pre-reset at boundaries)
+        else:
+            vs = vsp = data["r"]  # unused by the kernel when adv is NULL
+        ctx.check(ctx.lib.crux_fill_gae_returns(ctx.h, ptr(data["r"]), ptr(data["done"]), ptr(data["episode_end"]), ptr(vs), ptr(vsp),
+                                                T, n, float(self.gamma), float(0.0 if math.isnan(float(self.lam)) else self.lam),
+                                                ptr(adv), ptr(ret)))
+
+    # ---- evaluation helpers (sampler.jl:206-251): mean undiscounted return of greedy episodes on a host env
+    def undiscounted_return(self, Neps=10):
+        assert not self.on_device, "evaluation rollouts use a host environment"
+        self.reset_()
+        total = np.zeros(self.n)
+        finished = []
+        discrete = isinstance(self.agent.space, DiscreteSpace)
+        steps = np.zeros(self.n, dtype=np.int64)
+        while len(finished) < Neps:
+            obs = self.cur
+            a = action(self.agent.pi, obs)
+            sp, r, dn = self.mdp.step(a.cpu().numpy())
+            total += r
+            steps += 1
+            end = np.asarray(dn, bool) | (steps >= self.max_steps)
+            nxt = self._tovec(sp)
+            if end.any():
+                idx = np.flatnonzero(end)
+                finished += total[idx].tolist()
+                total[idx] = 0
+                steps[idx] = 0
+                nxt = nxt.copy()
+                nxt[idx] = self._tovec(self.mdp.reset(idx))
+            self.cur.copy_(torch.from_numpy(nxt))
+        self.reset_()
+        return float(np.mean(finished[:Neps]))
+
+
+def steps_(sampler, buffer=None, **kw):
+    """``steps!(sampler, buffer; Nsteps, explore, i, reset, cb)``."""
+    return sampler.steps_(buffer, **kw)
+
+
+def fill_gae_(data, T, n, V, lam, gamma, ctx=None):
+    """``fill_gae!`` over a whole ``[T][n]`` rollout dict (sampler.jl:255-273)."""
+    ctx = ctx or V.ctx
+    vs, vsp = V.mlp.forward(data["s"]), V.mlp.forward(data["sp"])
+    ctx.check(ctx.lib.crux_fill_gae_returns(ctx.h, ptr(data["r"]), ptr(data["done"]), ptr(data["episode_end"]), ptr(vs), ptr(vsp), T, n,
+                                            float(gamma), float(lam), ptr(data["advantage"]), None))
+
+
+def fill_returns_(data, T, n, gamma, ctx):
+    """``fill_returns!`` (sampler.jl:275-281)."""
+    ctx.check(ctx.lib.crux_fill_gae_returns(ctx.h, ptr(data["r"]), ptr(data["done"]), ptr(data["episode_end"]), ptr(data["r"]),
+                                            ptr(data["r"]), T, n, float(gamma), 0.0, None, ptr(data["return"])))

@@ -53,6 +53,9 @@ typedef struct crux_buffer crux_buffer;
 
 /* ------------------------------------------------------------------ context / devices
  * replaces src/devices.jl:1-21 (device/gpucall/cpucall/mdcall): data stays on the device. */
+/* stream arguments are cudaStream_t values.  NULL asks the context to create (and own) a non-blocking stream;
+ * the legacy default stream is spelled CRUX_STREAM_LEGACY (== cudaStreamLegacy). */
+#define CRUX_STREAM_LEGACY ((void *)0x1)
 int32_t crux_abi_version(void);
 int32_t crux_ctx_create(int32_t device, void *stream /* cudaStream_t or NULL: own stream */, crux_ctx **out);
 int32_t crux_ctx_destroy(crux_ctx *ctx);

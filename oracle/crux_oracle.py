@@ -179,7 +179,7 @@ class ExperienceBuffer:
                 self.pp.beta = beta
             if self.elements:
                 self.update_priorities(np.arange(1, self.elements + 1),
-                                       self.pp.max_priority * np.ones(self.elements, dtype=F32))
+                                       self.pp.max_priority * np.ones(self.elements, dtype=F32))  # :72 ones(Float32, ...)
 
     @classmethod
     def create(cls, sdims, adims, capacity, extras=(), stype=F32, atype=F32, **kw):
@@ -233,20 +233,29 @@ class ExperienceBuffer:
             for j in range(N):
                 self.data[k][I[j] - 1] = v2[j]
         if self.pp is not None:
-            self.update_priorities(I, self.pp.max_priority * np.ones(N, dtype=F32))
+            self.update_priorities(I, np.float64(self.pp.max_priority) * np.ones(N))
         self.elements = min(C, self.elements + N)
         self.next_ind = int(mod1(self.next_ind + N, C))
         return I
 
     def update_priorities(self, I, v):
-        """experience_buffer.jl:290-301."""
+        """experience_buffer.jl:290-301.  The element type of ``v`` decides the arithmetic like in Julia:
+        Float32 ``v`` (``cpu(td_error(...))``, off_policy.jl:83) -> ``val`` and ``val^α`` are Float32;
+        Float64 ``v`` (``max_priority*ones(N)`` in push!, :254; the Float64 literals of the reference test)
+        -> Float64, rounded when stored into the Float32 fields."""
         assert len(I) == len(v)
         pp = self.pp
+        v = np.asarray(v)
+        wide = v.dtype == np.float64
         for i in range(len(I)):
-            val = F32(F32(v[i]) + EPS32)
-            pp.priorities[I[i] - 1] = pow_f32(val, pp.alpha)
-            pp.max_priority = max(val, pp.max_priority)
-            pp.min_priority = min(val, pp.min_priority)
+            if wide:
+                val = np.float64(v[i]) + np.float64(EPS32)
+                pp.priorities[I[i] - 1] = F32(val ** np.float64(pp.alpha))
+            else:
+                val = F32(F32(v[i]) + EPS32)
+                pp.priorities[I[i] - 1] = pow_f32(val, pp.alpha)
+            pp.max_priority = F32(max(val, pp.max_priority))
+            pp.min_priority = F32(min(val, pp.min_priority))
             pp.cumsum_valid = False
 
     def episodes(self):
