@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of one full PPO iteration (BASELINE.json metric) on N B200s, plus the GAE HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input = one iteration of the reference's on-policy solve
+loop (on_policy.jl:91-106) at BASELINE config[1]: 4096 parallel LinQuad-17x6 env streams per GPU x T=32 vector steps
+(ΔN = 131 072 transitions per GPU) -> V(s), V(sp) -> fused GAE/returns scan -> whiten -> 4 epochs x 4 minibatches of 32 768
+for the actor (ppo_loss) and again for the critic (mse), Adam on both.  Nothing is skipped inside the timed region: the KL
+early stop is disabled so every epoch runs.
+
+  value : the env lives on the device (inputs resident in HBM), timed with CUDA events per step, max over ranks.
+  e2e   : the same iteration through the public API (`crux.solve(PPO(...), env)`) with a HOST environment: observations,
+          transitions and actions cross PCIe every vector step from/to pinned host memory, wall-clock timed.
+  --impl reference : the reference algorithm restated on the CPU (oracle/, all host threads), same config and metric.
+
+Only bench.py's cpu_baseline / --impl reference legs import `oracle/` (and smoke()/tests); the product path never does.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ENVS, HORIZON, OBS, ACT, HID = 4096, 32, 17, 6, 64
+EPOCHS, MB = 4, 32768
+WORKLOAD = (f"PPO, synthetic LinQuad {OBS}-obs/{ACT}-act MDP, {N_ENVS} envs/GPU x T={HORIZON} (dN={N_ENVS * HORIZON}/GPU), "
+            f"actor {OBS}-{HID}-{HID}-{ACT} tanh + logSigma, critic {OBS}-{HID}-{HID}-1, {EPOCHS} epochs x {N_ENVS * HORIZON // MB} minibatches of {MB} "
+            f"(actor then critic), Adam 3e-4, eps=0.2, lambda_e=0, KL early stop disabled, gamma=0.99, lambda=0.95")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def build_solver(crux, ctx, seed=1):
+    rng = np.random.default_rng(seed)
+    D = crux.Dense
+    mu = crux.ContinuousNetwork(crux.Chain(D(OBS, HID, crux.tanh, rng=rng), D(HID, HID, crux.tanh, rng=rng), D(HID, ACT, rng=rng)), ctx=ctx)
+    cr = crux.ContinuousNetwork(crux.Chain(D(OBS, HID, crux.tanh, rng=rng), D(HID, HID, crux.tanh, rng=rng), D(HID, 1, rng=rng)), ctx=ctx)
+    pi = crux.ActorCritic(crux.GaussianPolicy(mu, np.full(ACT, -0.5, np.float32)), cr)
+    opt = dict(epochs=EPOCHS, batch_size=MB, optimizer=crux.Adam(np.float32(3e-4)))
+    S = crux.PPO(pi, crux.ContinuousSpace(OBS), eps=0.2, lp=1.0, le=0.0, target_kl=math.inf, a_opt=dict(opt), c_opt=dict(opt),
+                 N=N_ENVS * HORIZON, dN=N_ENVS * HORIZON, max_steps=1000, lam_gae=0.95, log=None, seed=seed)
+    return S
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import crux_b200 as crux
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    ctx = crux.Context(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ctx.init_distributed(rank, world)
+    dN = N_ENVS * HORIZON
+    hbm_peak, peak_src = peaks()
+
+    # ---------------- value leg: device-resident env ------------------------------------------------
+    S = build_solver(crux, ctx)
+    env = crux.DeviceLinQuad(N_ENVS, OBS, ACT, seed=1000 + rank, max_steps=1000, ctx=ctx)
+    S.N = dN
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=ctx.device)  # > 126 MB L2
+
+    def one_step():
+        crux.solve(S, env)
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = ctx.launch_count()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)              # evict the previous iteration's rollout from L2 (outside the event pair)
+        ev[k][0].record()
+        one_step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    launches = ctx.launch_count() - l0
+    ctx.check_flags()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, t_wall * 1e3], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    value = args.steps * dN * world / (dev_ms * 1e-3)
+    info = S.training_info()
+
+    # ---------------- phase breakdown + dominant-kernel roofline (rank-local, untimed extra iterations) -------------
+    phases = phase_breakdown(crux, ctx, S, env, torch)  # every rank: the update all-reduces gradients
+    gae = gae_roofline(crux, ctx, torch, hbm_peak, peak_src) if rank == 0 else None
+
+    # ---------------- e2e leg: host env through the public API --------------------------------------
+    S2 = build_solver(crux, ctx, seed=2)
+    henv = crux.HostLinQuad(N_ENVS, OBS, ACT, seed=2000 + rank)
+    S2.N = dN
+    for _ in range(max(1, args.warmup // 2)):
+        crux.solve(S2, henv)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        crux.solve(S2, henv)
+        loss = S2.training_info()["actor_loss"]   # D2H read of the step's result
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_steps * dN * world / float(t[0])
+    h2d = HORIZON * (2 * N_ENVS * OBS * 4 + N_ENVS * 4 + 2 * N_ENVS)      # obs + sp + r + done + episode_end per vector step
+    d2h = HORIZON * N_ENVS * ACT * 4 + 2 * 16 * 8 * 4                      # actions per vector step + the info records
+
+    if rank == 0:
+        cpu = cpu_baseline()
+        out = {"metric": "env-steps/sec (PPO, 4096 envs)", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": WORKLOAD, "parallelism": f"dp{world} (env shards; one gradient all-reduce per minibatch)",
+                          "l2": "256 MiB flush between timed iterations (outside the per-step event pairs); the GAE roofline shape is 738 MB >> L2",
+                          "timing": "CUDA events per step on the launching stream, summed, max over ranks", "wall_ms_per_step": wall_ms / args.steps},
+               "clocks": clk,
+               "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                       "api": "crux.solve(PPO(...), HostLinQuad(4096)) -- numpy env on the host, pinned H2D/D2H every vector step"},
+               "gpu_launches": int(launches),
+               "roofline": phases["roofline"] if phases else None,
+               "roofline_gae": gae,
+               "phases_ms": phases["phases_ms"] if phases else None,
+               "cpu_baseline": cpu,
+               "last_info": {k: (round(v, 6) if isinstance(v, float) else v) for k, v in info.items()}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def phase_breakdown(crux, ctx, S, env, torch):
+    """CUDA-event phase times of one iteration and the roofline of the dominant kernel family (the minibatch update)."""
+    from crux_b200.device import ptr
+    D, s = S.buffer, S.sampler
+    dN = N_ENVS * HORIZON
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    reps = 3
+    acc = np.zeros(4)
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        evs[0].record()
+        data = {k: D.column(k)[:dN] for k in D.schema}
+        s._rollout_device(data, HORIZON, True, 0, True, None)
+        evs[1].record()
+        s.fill_gae_returns_(data, HORIZON)
+        evs[2].record()
+        ctx.check(ctx.lib.crux_whiten(ctx.h, ptr(data["advantage"]), dN))
+        evs[3].record()
+        S.policy_gradient_training(D)
+        evs[4].record()
+        torch.cuda.synchronize()
+        acc += np.array([evs[k].elapsed_time(evs[k + 1]) for k in range(4)])
+    acc /= reps
+    # algorithmic work of the update: per sample per epoch 3 x (actor 11 136 + critic 10 496) FLOP
+    flops = EPOCHS * dN * 3 * (2 * (OBS * HID + HID * HID + HID * ACT) + 2 * (OBS * HID + HID * HID + HID))
+    tf = flops / (acc[3] * 1e-3) / 1e12
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal fp32 SIMT FFMA peak at max clock (no measured figure in MEASURED_PEAKS)
+    roof = {"kernel": "PPO minibatch update (forward + loss + backward + Adam, actor then critic)", "bound": "fp32-simt",
+            "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak, "traffic": None,
+            "note": "fp32 FFMA path (1e-5 parity excludes TF32/BF16 MMA); peak is the NOMINAL 148 SM x 128 lanes x 2 x 1.965 GHz; "
+                    "share of step = %.0f%%" % (100 * acc[3] / acc.sum())}
+    return {"phases_ms": {"rollout": acc[0], "values+gae": acc[1], "whiten": acc[2], "update": acc[3]}, "roofline": roof}
+
+
+def gae_roofline(crux, ctx, torch, hbm_peak, peak_src, T=2048, N=16384, reps=10):
+    """GAE HBM GB/s at [2048, 16384] (738 MB >> 126 MB L2): 22 algorithmic bytes per transition."""
+    from crux_b200.device import ptr
+    g = torch.Generator(device=ctx.device).manual_seed(2)
+    r, vs, vsp = (torch.randn((T, N), device=ctx.device, generator=g) for _ in range(3))
+    done = (torch.rand((T, N), device=ctx.device, generator=g) < 0.001).to(torch.uint8)
+    ee = done.clone()
+    ee[999::1000] = 1
+    ee[-1] = 1
+    adv, ret = torch.empty_like(r), torch.empty_like(r)
+
+    def run():
+        ctx.check(ctx.lib.crux_fill_gae_returns(ctx.h, ptr(r), ptr(done), ptr(ee), ptr(vs), ptr(vsp), T, N, 0.99, 0.95, ptr(adv), ptr(ret)))
+    for _ in range(3):
+        run()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    nbytes = 22 * T * N
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "gae_returns_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+            "traffic": None, "shape": [T, N], "bytes_per_launch": nbytes, "ms_per_launch": ms, "peak_source": peak_src}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_run(steps, warmup, n_envs=N_ENVS):
+    if os.environ.get("CRUX_BENCH_TINY"):  # contract test only (tests/test_host_logic.py)
+        n_envs = 64
+    """The reference algorithm restated on the CPU (oracle/ppo_cpu.py), vectorised over env streams, all host threads."""
+    import torch
+    from oracle.ppo_cpu import OraclePPO
+    torch.set_num_threads(cpu_threads())
+    p = OraclePPO(n_envs, HORIZON, OBS, ACT, HID, seed=1, epochs=EPOCHS, batch=n_envs * HORIZON // 4, le=0.0)
+    for _ in range(warmup):
+        p.iteration()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        p.iteration()
+    dt = time.perf_counter() - t0
+    return steps * n_envs * HORIZON / dt, dt / steps
+
+
+def cpu_baseline():
+    """Bounded sample for the ours-arm JSON line: 2 iterations at 1024 env streams (1/4 of the workload, same T, same
+    epochs, minibatch scaled to keep 4 per epoch) after 1 warm-up, plus the reference-faithful batch-1 sampling rate."""
+    try:
+        from oracle.ppo_cpu import reference_faithful_steps_per_sec
+        v, s_per = cpu_run(2, 1, n_envs=1024)
+        rf = reference_faithful_steps_per_sec(300)
+        return {"value": v, "unit": "env-steps/s", "cores": cpu_threads(), "kind": "port",
+                "sample": f"2 PPO iterations x 1024 env streams x T={HORIZON} (1/4 of the workload; minibatch 8192), vectorised torch-CPU oracle, {s_per:.2f} s/iteration",
+                "reference_faithful_batch1_sampling_steps_per_s": rf}
+    except Exception as e:  # the baseline must never take the bench down
+        return {"value": None, "unit": "env-steps/s", "cores": cpu_threads(), "kind": "port", "sample": f"failed: {e!r}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    v, s_per = cpu_run(steps, min(args.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sample = f"{steps} full PPO iterations ({N_ENVS} env streams x T={HORIZON}), vectorised torch-CPU oracle port of the reference algorithm"
+    out = {"impl": "reference", "metric": "env-steps/sec (PPO, 4096 envs)", "value": v, "unit": "env-steps/s", "n_gpus": world, "steps": steps,
+           "warmup": min(args.warmup, 1), "ms_per_step": s_per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": {"workload": WORKLOAD, "note": "Julia/Flux cannot run in this image: the reference's CPU path is its restated oracle"},
+           "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cpu_threads(), "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -51,7 +51,7 @@ class Sampler:
     # ---- reset_sampler! (sampler.jl:31-43) for every stream
     def reset_(self):
         if self.on_device:
-            self.mdp.max_steps = self.max_steps
+            assert self.mdp.max_steps == self.max_steps, "a device env bakes max_steps into its step kernel: construct it with the solver's max_steps"
             self.mdp.reset_into(self.cur)
         else:
             o = self._tovec(self.mdp.reset(None))

@@ -1,0 +1,375 @@
+"""Host-side mirror of the solver surface: ``TrainingParams`` (src/training.jl:1-11), ``OnPolicySolver`` +
+``PPO``/``A2C`` (src/model_free/on_policy.jl, rl/ppo.jl, rl/a2c.jl), ``OffPolicySolver`` + ``DQN``/``SAC``
+(src/model_free/off_policy.jl, rl/dqn.jl, rl/sac.jl) and ``solve``.
+
+The reference passes loss closures to a generic ``train!``; here the losses of the four north-star algorithms are
+fused CUDA kernels selected by name (``ppo_loss``, ``a2c_loss``, ``td_loss``, ``double_Q_loss`` + ``sac_actor_loss``
++ ``sac_temp_loss``); anything else raises -- there is no generic autodiff fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import _abi
+from .buffer import ExperienceBuffer, buffer_like, rand_
+from .device import ptr, view
+from .policies import (ActorCritic, ContinuousNetwork, DiscreteNetwork, DoubleNetwork, GaussianNoiseExplorationPolicy,
+                       GaussianPolicy, LinearDecaySchedule, PolicyParams, SquashedGaussianPolicy, action_space, actor,
+                       critic, deepcopy, eps_greedy_policy, polyak_average_)
+from .sampler import Sampler
+from .spaces import DiscreteSpace, dim
+
+F32 = np.float32
+
+
+class Adam:
+    """``Flux.Adam(η, β, ϵ)`` [3P]: float32 moments, Float64 scalars."""
+
+    def __init__(self, eta=F32(3e-4), beta=(0.9, 0.999), eps=1e-8):
+        self.eta, self.beta, self.eps = float(eta), (float(beta[0]), float(beta[1])), float(eps)
+
+
+class TrainingParams:
+    """training.jl:1-11."""
+
+    def __init__(self, loss=None, optimizer=None, batch_size=128, epochs=80, update_every=1, early_stopping=None,
+                 name="", max_batches=math.inf, target_kl=None):
+        self.loss, self.optimizer = loss, optimizer or Adam(F32(3e-4))
+        self.batch_size, self.epochs, self.update_every = int(batch_size), int(epochs), int(update_every)
+        self.early_stopping, self.name, self.max_batches = early_stopping, name, max_batches
+        self.target_kl = target_kl  # the only early-stopping rule the fused update evaluates (rl/ppo.jl:59, a2c.jl:46)
+
+
+class LoggerParams:
+    """logging.jl:12-25 reduced to what the solve loops touch: ``period``, ``fns``, ``verbose``, ``sampler``; scalars are
+    appended to ``history`` (the TensorBoard writer is out of scope)."""
+
+    def __init__(self, dir="log/", period=500, fns=None, verbose=False, sampler=None):
+        self.dir, self.period, self.verbose, self.sampler = dir, int(period), verbose, sampler
+        self.fns = [] if fns is None else list(fns)
+        self.history = []
+
+    @staticmethod
+    def elapsed(i, N):
+        """logging.jl:1-2 (``i`` an int or an inclusive (lo, hi) range)."""
+        if isinstance(i, tuple):
+            lo, hi = i
+            return hi // N > (lo - 1) // N
+        return i % N == 0
+
+    def log(self, i, *dicts, solver=None):
+        if not self.elapsed(i, self.period):
+            return
+        step = i[1] if isinstance(i, tuple) else i
+        rec = {"step": step}
+        for d in list(self.fns) + list(dicts):
+            d = d(s=self.sampler, i=step, solver=solver) if callable(d) else d
+            rec.update({str(k): (v() if callable(v) else v) for k, v in d.items()})
+        self.history.append(rec)
+        if self.verbose:
+            print(", ".join(f"{k}: {v}" for k, v in rec.items()))
+
+
+def log_undiscounted_return(Neps=10):
+    """logging.jl:69-76: greedy evaluation episodes on the logger's sampler (which resets it)."""
+    return lambda s, i, solver=None: {"undiscounted_return": s.undiscounted_return(Neps)}
+
+
+def _set_adam(mlp, opt):
+    mlp.set_adam(opt.eta, opt.beta, opt.eps)
+
+
+# =============================================================================================== on-policy
+class OnPolicySolver:
+    """on_policy.jl:31-54."""
+
+    def __init__(self, agent, S, N=1000, dN=200, max_steps=100, log=None, i=0, a_opt=None, c_opt=None, P=None,
+                 post_sample_callback=None, post_batch_callback=None, lam_gae=0.95, required_columns=(), a2c=False, seed=0,
+                 interaction_storage=None):
+        self.agent = agent if isinstance(agent, PolicyParams) else PolicyParams(agent)
+        self.S, self.N, self.dN, self.max_steps, self.log, self.i = S, int(N), int(dN), int(max_steps), log, int(i)
+        self.a_opt, self.c_opt, self.P = a_opt, c_opt, dict(P or {})
+        self.post_sample_callback, self.post_batch_callback = post_sample_callback, post_batch_callback
+        self.lam_gae, self.required_columns, self.a2c, self.seed = F32(lam_gae), list(required_columns), a2c, int(seed)
+        self.interaction_storage = interaction_storage
+        self.update_count = 0
+        pi = self.agent.pi
+        assert isinstance(pi, ActorCritic) and isinstance(pi.A, GaussianPolicy) and not pi.A.squashed and isinstance(pi.C, ContinuousNetwork), \
+            "the fused on-policy update supports ActorCritic(GaussianPolicy(μ, logΣ vector), ContinuousNetwork) (rl/ppo.jl examples)"
+        _set_adam(pi.A.mu.mlp, a_opt.optimizer)
+        if c_opt is not None:
+            _set_adam(pi.C.mlp, c_opt.optimizer)
+        self.buffer = None
+        self.sampler = None
+        self.last_info = None
+
+    def _hp(self):
+        a, c = self.a_opt, self.c_opt
+        tk = a.target_kl if a.target_kl is not None else math.inf
+        return _abi.PPOHp(eps_clip=float(self.P.get("eps", 0.2)), lambda_p=float(self.P.get("lp", 1.0)), lambda_e=float(self.P.get("le", 0.1)),
+                          target_kl=float(tk), a2c=1 if self.a2c else 0, actor_epochs=a.epochs, actor_batch=a.batch_size,
+                          critic_epochs=0 if c is None else c.epochs, critic_batch=1 if c is None else c.batch_size,
+                          actor_max_batches=0 if math.isinf(a.max_batches) else int(a.max_batches),
+                          critic_max_batches=0 if (c is None or math.isinf(c.max_batches)) else int(c.max_batches))
+
+    def policy_gradient_training(self, D, orders=None):
+        """on_policy.jl:56-78: batch_train!(actor) then batch_train!(critic) as ONE stream-ordered launch sequence.
+        ``orders = (order_actor, order_critic)`` injects the shuffles (int32 [epochs, n], 0-based) for parity runs."""
+        pi, ctx = self.agent.pi, self.agent.pi.ctx
+        n = len(D)
+        hp = self._hp()
+        oa = oc = None
+        if orders is not None:
+            oa = None if orders[0] is None else ctx.to_device(np.ascontiguousarray(orders[0], dtype=np.int32), torch.int32)
+            oc = None if orders[1] is None else ctx.to_device(np.ascontiguousarray(orders[1], dtype=np.int32), torch.int32)
+        self.update_count += 1
+        self._hp_last, self._n_last = hp, n
+        self._keep = (oa, oc)
+        ctx.check(ctx.lib.crux_ppo_update_async(pi.A.h, pi.C.mlp.h if self.c_opt is not None else None, ptr(D["s"]), ptr(D["a"]),
+                                                ptr(D["logprob"]), ptr(D["advantage"]), ptr(D["return"]), n, C.byref(hp), ptr(oa), ptr(oc),
+                                                self.seed * 1000003 + self.update_count))
+        return self.training_info  # lazily evaluated: reading it synchronises
+
+    def training_info(self):
+        """Aggregated info of the last update.  ``batch_train!`` pushes the SAME dict for every minibatch
+        (training.jl:43), so the reference's aggregates equal the last trained minibatch's values."""
+        pi, ctx = self.agent.pi, self.agent.pi.ctx
+        hp, n = self._hp_last, self._n_last
+        pa, pc = C.c_void_p(), C.c_void_p()
+        ctx.check(ctx.lib.crux_ppo_info_ptrs(pi.A.h, C.byref(pa), C.byref(pc)))
+        nmb_a, nmb_c = -(-n // hp.actor_batch), -(-n // hp.critic_batch)
+        ia = view(pa.value, (max(1, hp.actor_epochs * nmb_a), 8), _abi.F32, ctx.device).cpu().numpy()
+        ctx.check_flags()
+        valid = np.flatnonzero(ia[:, _abi.PPO_VALID] > 0)
+        info = {"actor_batches_trained": int(len(valid))}
+        if len(valid):
+            last = ia[valid[-1]]
+            info.update({"actor_loss": float(last[_abi.PPO_LOSS]), "actor_grad_norm": float(last[_abi.PPO_GRAD_NORM]),
+                         "entropy": float(last[_abi.PPO_ENTROPY]), "kl": float(last[_abi.PPO_KL])})
+            if not self.a2c:
+                info.update({"clip_fraction": float(last[_abi.PPO_CLIP_FRAC]), "avg_advantage": float(last[_abi.PPO_AVG_ADV]),
+                             "avg_return": float(last[_abi.PPO_AVG_RET])})
+        if self.c_opt is not None and hp.critic_epochs > 0:
+            ic = view(pc.value, (hp.critic_epochs * nmb_c, 8), _abi.F32, ctx.device).cpu().numpy()
+            v = np.flatnonzero(ic[:, _abi.PPO_VALID] > 0)
+            info["critic_batches_trained"] = int(len(v))
+            if len(v):
+                info.update({"critic_loss": float(ic[v[-1], _abi.PPO_LOSS]), "critic_grad_norm": float(ic[v[-1], _abi.PPO_GRAD_NORM])})
+        self.last_info = info
+        return info
+
+
+def _whiten_advantage(D, **_):
+    """𝒟[:advantage] .= whiten(𝒟[:advantage])  (ppo.jl:61 post_batch_callback / a2c.jl:48 post_sample_callback)."""
+    adv = D["advantage"]
+    ctx = getattr(D, "ctx", None)
+    if ctx is None:
+        from .device import default_context
+        ctx = default_context()
+    ctx.check(ctx.lib.crux_whiten(ctx.h, ptr(adv), adv.shape[0]))
+
+
+def PPO(pi, S, eps=0.2, lp=1.0, le=0.1, target_kl=0.012, a_opt=None, c_opt=None, log=None, required_columns=(), **kw):
+    """``PPO(;π, ϵ=0.2f0, λp=1f0, λe=0.1f0, target_kl=0.012f0, a_opt, c_opt, ...)`` rl/ppo.jl:40-65."""
+    a = TrainingParams(loss="ppo_loss", name="actor_", target_kl=target_kl, **(a_opt or {}))
+    c = TrainingParams(loss="mse", name="critic_", **(c_opt or {}))
+    cols = list(dict.fromkeys(list(required_columns) + ["return", "logprob", "advantage"]))
+    return OnPolicySolver(PolicyParams(pi), S, P={"eps": F32(eps), "lp": F32(lp), "le": F32(le)}, a_opt=a, c_opt=c,
+                          post_batch_callback=_whiten_advantage, required_columns=cols, log=log, **kw)
+
+
+def A2C(pi, S, lp=1.0, le=0.1, a_opt=None, c_opt=None, log=None, required_columns=(), **kw):
+    """``A2C(;π, λp, λe, ...)`` rl/a2c.jl:30-51 (early stop at KL > 0.015; advantages whitened in post_sample_callback)."""
+    a = TrainingParams(loss="a2c_loss", name="actor_", target_kl=0.015, **(a_opt or {}))
+    c = TrainingParams(loss="mse", name="critic_", **(c_opt or {}))
+    cols = list(dict.fromkeys(list(required_columns) + ["return", "logprob", "advantage"]))
+    return OnPolicySolver(PolicyParams(pi), S, P={"lp": F32(lp), "le": F32(le)}, a_opt=a, c_opt=c, a2c=True,
+                          post_sample_callback=_whiten_advantage, required_columns=cols, log=log, **kw)
+
+
+def _solve_on_policy(S, mdp):
+    """``POMDPs.solve(𝒮::OnPolicySolver, mdp)`` on_policy.jl:80-109."""
+    pi = S.agent.pi
+    if S.buffer is None:
+        S.buffer = ExperienceBuffer(S.S, S.agent.space, S.dN, S.required_columns, ctx=pi.ctx)
+    if S.sampler is None or S.sampler.mdp is not mdp:
+        S.sampler = Sampler(mdp, S.agent, S=S.S, required_columns=S.required_columns, lam=S.lam_gae, max_steps=S.max_steps, seed=S.seed)
+    D, s = S.buffer, S.sampler
+    if S.log is not None and S.log.sampler is None:
+        S.log.sampler = s
+    if S.log is not None:
+        S.log.log(S.i, solver=S)
+    i0 = S.i
+    for S.i in range(i0, i0 + S.N - S.dN + 1, S.dN):
+        info = {}
+        cb = (lambda data: S.post_sample_callback(data, info=info, solver=S)) if S.post_sample_callback else None
+        if D.next_ind != 1:
+            pass  # capacity == ΔN: every rollout overwrites the whole buffer (push! wraps back to row 1)
+        s.steps_(D, Nsteps=S.dN, explore=True, i=S.i, reset=True, cb=_wrap_cb(cb, pi.ctx), store=S.interaction_storage)
+        if S.post_batch_callback:
+            S.post_batch_callback(D, info=info, solver=S)
+        training_info = S.policy_gradient_training(D)
+        if S.log is not None:
+            S.log.log((S.i + 1, S.i + S.dN), lambda **_: training_info(), info, solver=S)
+    S.i += S.dN
+    return pi
+
+
+class _DataView(dict):
+    """A rollout dict that also knows its context (so callbacks written against a buffer work on it)."""
+    ctx = None
+
+
+def _wrap_cb(cb, ctx):
+    if cb is None:
+        return None
+
+    def f(data):
+        d = _DataView(data)
+        d.ctx = ctx
+        return cb(d)
+    return f
+
+
+# =============================================================================================== off-policy
+class OffPolicySolver:
+    """off_policy.jl:37-64."""
+
+    def __init__(self, agent, S, N=1000, dN=4, max_steps=100, log=None, i=0, a_opt=None, c_opt=None, P=None, kind="dqn",
+                 tau=0.005, buffer_size=1000, required_columns=(), buffer=None, buffer_init=None, prioritized=False,
+                 priority_params=None, weighted_loss=False, seed=0, post_sample_callback=None):
+        self.agent, self.S = agent, S
+        self.N, self.dN, self.max_steps, self.log, self.i = int(N), int(dN), int(max_steps), log, int(i)
+        self.a_opt, self.c_opt, self.P, self.kind, self.tau = a_opt, c_opt, dict(P or {}), kind, F32(tau)
+        self.required_columns = list(required_columns)
+        ctx = agent.pi.ctx
+        self.buffer = buffer if buffer is not None else ExperienceBuffer(S, agent.space, buffer_size, self.required_columns,
+                                                                         prioritized=prioritized, priority_params=priority_params, ctx=ctx)
+        self.buffer_init = int(buffer_init) if buffer_init is not None else max(c_opt.batch_size, 200)
+        self.weighted_loss, self.seed = weighted_loss, int(seed)
+        self.post_sample_callback = post_sample_callback
+        self.sampler = None
+        self.train_count = 0
+        self.last_info = {}
+        self._sac = None
+        if kind == "dqn":
+            _set_adam(agent.pi.mlp, c_opt.optimizer)
+        else:
+            pi = agent.pi
+            _set_adam(pi.A.mu.mlp, a_opt.optimizer)
+            _set_adam(pi.C.N1.mlp, c_opt.optimizer)
+            _set_adam(pi.C.N2.mlp, c_opt.optimizer)
+            st = C.c_void_p()
+            tg = agent.pi_target
+            ctx.check(ctx.lib.crux_sac_create(pi.A.h, pi.C.N1.mlp.h, pi.C.N2.mlp.h, tg.C.N1.mlp.h, tg.C.N2.mlp.h,
+                                              F32(self.P["SAC_log_alpha"]), F32(self.P["SAC_H_target"]), float(self.P.get("alpha_eta", F32(3e-4))),
+                                              self.tau, C.byref(st)))
+            self._sac = st
+
+    def value_training(self, D, gamma, draws=None, noise=None):
+        """off_policy.jl:66-111.  ``draws[epoch]`` / ``noise[epoch]`` inject the sampling draws and SAC noise (parity runs)."""
+        ctx, lib = self.agent.pi.ctx, self.agent.pi.ctx.lib
+        B = D.capacity
+        infos = []
+        for epoch in range(self.c_opt.epochs):
+            self.train_count += 1
+            rand_(D, self.buffer, i=self.i, draws=None if draws is None else [draws[epoch]], seed=self.seed, ctr=2 * self.train_count)
+            s, a, sp, r, dn = D.column("s"), D.column("a"), D.column("sp"), D.column("r"), D.column("done")
+            if self.kind == "dqn":
+                pi, tgt = self.agent.pi, self.agent.pi_target
+                nA = len(pi.outputs)
+                y = ctx.empty((B,))
+                q_sp = tgt.mlp.forward(sp)
+                ctx.check(lib.crux_dqn_target(ctx.h, ptr(r), ptr(dn), ptr(q_sp), B, nA, float(gamma), ptr(y)))     # rl/dqn.jl:4-6
+                if self.buffer.isprioritized():                                                                       # off_policy.jl:83
+                    q = pi.mlp.forward(s)
+                    qsa, td = ctx.empty((B,)), ctx.empty((B,))
+                    ctx.check(lib.crux_discrete_q_sa(ctx.h, ptr(q), ptr(a), B, nA, ptr(qsa)))
+                    ctx.check(lib.crux_td_error(ctx.h, ptr(qsa), ptr(y), B, ptr(td)))
+                    self.buffer.update_priorities_(D.indices_dev(), td)
+                w = D.column("weight") if (self.weighted_loss and "weight" in D.schema) else None
+                if epoch % self.c_opt.update_every == 0:
+                    ctx.check(lib.crux_dqn_train(pi.mlp.h, ptr(s), ptr(a), ptr(y), ptr(w), B, None))                 # off_policy.jl:91-93
+            else:
+                e = (None, None, None) if noise is None else [ctx.to_device(x, torch.float32) for x in noise[epoch]]
+                ctx.check(lib.crux_sac_train(self._sac, ptr(s), ptr(a), ptr(sp), ptr(r), ptr(dn), B, float(gamma), ptr(e[0]), ptr(e[1]), ptr(e[2]),
+                                             self.seed, 3 * self.train_count, None, None))
+        if self.kind == "dqn":  # no separate actor: target update after the epoch loop (off_policy.jl:108)
+            polyak_average_(self.agent.pi_target, self.agent.pi, self.tau)
+        return infos
+
+    def __del__(self):
+        try:
+            if self._sac is not None and self.agent.pi.ctx.h:
+                self.agent.pi.ctx.lib.crux_sac_destroy(self._sac)
+                self._sac = None
+        except Exception:
+            pass
+
+
+def DQN(pi, S, N, dN=4, pi_explore=None, c_opt=None, log=None, **kw):
+    """``DQN(;π::DiscreteNetwork, N, ΔN=4, π_explore=ϵGreedyPolicy(LinearDecaySchedule(1., 0.1, N÷2), π.outputs), c_opt, ...)``
+    rl/dqn.jl:29-46 (c_opt.epochs = ΔN: one gradient step per env step)."""
+    assert isinstance(pi, DiscreteNetwork)
+    pe = pi_explore or eps_greedy_policy(LinearDecaySchedule(1.0, 0.1, N // 2), pi.outputs)
+    c = TrainingParams(**{"loss": "td_loss", "name": "critic_", "epochs": dN, **(c_opt or {})})
+    agent = PolicyParams(pi, pi_explore=pe, pi_target=deepcopy(pi))
+    return OffPolicySolver(agent, S, N=N, dN=dN, c_opt=c, kind="dqn", log=log, **kw)
+
+
+def SAC(pi, S, N=1000, dN=50, SAC_alpha=1.0, SAC_H_target=None, pi_explore=None, SAC_alpha_opt=None, a_opt=None, c_opt=None,
+        log=None, **kw):
+    """``SAC(;π::ActorCritic{_, DoubleNetwork}, ΔN=50, SAC_α=1f0, SAC_H_target=-dim(A), π_explore=GaussianNoiseExplorationPolicy(0.1f0), ...)``
+    rl/sac.jl:77-106."""
+    assert isinstance(pi, ActorCritic) and isinstance(pi.A, SquashedGaussianPolicy) and isinstance(pi.C, DoubleNetwork)
+    H = F32(-int(np.prod(dim(action_space(pi))))) if SAC_H_target is None else F32(SAC_H_target)
+    a = TrainingParams(**{"loss": "sac_actor_loss", "name": "actor_", **(a_opt or {})})
+    c = TrainingParams(**{"loss": "double_Q_loss", "name": "critic_", "epochs": dN, **(c_opt or {})})
+    t = TrainingParams(**{"loss": "sac_temp_loss", "name": "temp_", **(SAC_alpha_opt or {})})
+    agent = PolicyParams(pi, pi_explore=pi_explore or GaussianNoiseExplorationPolicy(F32(0.1)), pi_target=deepcopy(pi))
+    P = {"SAC_log_alpha": F32(math.log(SAC_alpha)), "SAC_H_target": H, "alpha_eta": t.optimizer.eta}
+    return OffPolicySolver(agent, S, N=N, dN=dN, a_opt=a, c_opt=c, P=P, kind="sac", log=log, **kw)
+
+
+def _solve_off_policy(S, mdp):
+    """``POMDPs.solve(𝒮::OffPolicySolver, mdp)`` off_policy.jl:113-150."""
+    pi = S.agent.pi
+    D = buffer_like(S.buffer, capacity=S.c_opt.batch_size)
+    gamma = F32(mdp.gamma)
+    extra = [k for k in S.buffer.schema if k not in ("s", "a", "sp", "r", "done", "episode_end")]
+    if S.sampler is None or S.sampler.mdp is not mdp:
+        S.sampler = Sampler(mdp, S.agent, S=S.S, max_steps=S.max_steps, required_columns=extra, seed=S.seed)
+    s, n = S.sampler, S.sampler.n
+    if S.log is not None and S.log.sampler is None:
+        S.log.sampler = s
+    up = lambda k: -(-int(k) // n) * n  # vector envs advance n transitions per step
+    Nfill = max(0, S.buffer_init - len(S.buffer))
+    istart = S.i
+    if Nfill > 0:
+        S.i += up(Nfill)
+        s.steps_(S.buffer, Nsteps=up(Nfill), explore=True, i=S.i)
+    if S.log is not None:
+        S.log.log(S.i, solver=S)
+    dN = up(S.dN)
+    for S.i in range(S.i, istart + S.N - dN + 1, dN):
+        s.steps_(S.buffer, Nsteps=dN, explore=True, i=S.i)
+        S.value_training(D, gamma)
+        if S.log is not None:
+            S.log.log((S.i + 1, S.i + dN), S.last_info, solver=S)
+    S.i += dN
+    pi.ctx.check_flags()
+    return pi
+
+
+def solve(S, mdp):
+    """``POMDPs.solve(𝒮, mdp)``."""
+    if isinstance(S, OnPolicySolver):
+        return _solve_on_policy(S, mdp)
+    if isinstance(S, OffPolicySolver):
+        return _solve_off_policy(S, mdp)
+    raise TypeError(type(S))

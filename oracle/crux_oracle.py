@@ -744,9 +744,9 @@ def train_step(params, loss_fn, opt, info, name=""):
     l.backward()
     gn = grad_norm(params)
     if math.isnan(gn):
-        raise FloatingPointError(f"NaN detected! Loss: {float(l)}")
+        raise FloatingPointError(f"NaN detected! Loss: {float(l.detach())}")
     opt.step(params)
-    info[name + "loss"] = float(l)
+    info[name + "loss"] = float(l.detach())
     info[name + "grad_norm"] = gn
     return info
 

@@ -1,0 +1,290 @@
+"""-m gpu: the host-side mirror of the reference surface (ExperienceBuffer, Sampler.steps!, PPO/A2C/DQN/SAC + solve)
+driving libcrux_cuda.so, against the reference's own test expectations and the CPU oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import crux_oracle as o
+from oracle.ppo_cpu import OraclePPO
+from gpu_util import F32, assert_close, assert_params_close, host
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------------ ExperienceBuffer
+def test_experience_buffer_reference_kats(crux, ctx):
+    # test/experience_buffer_tests.jl:32-51,66-147,162-174
+    b = crux.ExperienceBuffer(crux.ContinuousSpace(2), crux.ContinuousSpace(1), 100, ctx=ctx)
+    d = {"s": 2 * np.ones((50, 2)), "a": np.ones((50, 1)), "sp": np.ones((50, 2)), "r": np.ones((50, 1)), "done": np.zeros((50, 1)),
+         "weight": np.zeros((50, 1))}  # extra source keys are ignored (keys(b) drives the loop)
+    I = b.push_(d)
+    assert I.tolist() == list(range(1, 51)) and len(b) == 50 and b.next_ind == 51
+    assert b.get_last_N_indices(10).tolist() == list(range(41, 51)) and b.get_last_N_indices(1000).tolist() == list(range(1, 51))
+    b.push_(d); b.push_(d)
+    assert b.get_last_N_indices(51).tolist() == [100] + list(range(1, 51))
+    assert len(b) == 100 and b.total_count == 150 and b.capacity == 100
+    b = crux.ExperienceBuffer(crux.ContinuousSpace(2), crux.DiscreteSpace(4), 100, ctx=ctx)
+    b.push_({"s": 2 * np.ones((1, 2)), "a": np.ones((1, 4)), "sp": np.ones((1, 2)), "r": np.ones((1, 1)), "done": np.zeros((1, 1))})
+    assert len(b) == 1 and tuple(b["s"].shape) == (1, 2) and tuple(b["a"].shape) == (1, 4) and tuple(b["r"].shape) == (1, 1)
+    assert torch.all(b["s"] == 2) and torch.all(b["a"] == 1) and torch.all(b["done"] == 0)
+    d3 = {"s": 3 * np.ones((3, 2)), "a": (np.random.default_rng(0).random((3, 4)) < 0.5), "sp": 5 * np.ones((3, 2)), "r": 6 * np.ones((3, 1)),
+          "done": np.ones((3, 1))}
+    b.push_(d3)
+    assert len(b) == 4 and np.array_equal(host(b["a"])[1:], d3["a"].astype(F32)) and torch.all(b["sp"][1:] == 5)
+    b.push_(b)  # push!(b, b)
+    assert len(b) == 8
+    for k in b.keys():
+        assert torch.equal(b[k][:4], b[k][4:8])
+    mb = b.minibatch([1, 2, 4])
+    for k in mb:
+        assert torch.equal(mb[k], b[k][[0, 1, 3]])
+    # b[:key] is a view callers write through (ppo.jl:61)
+    b["r"][:] = 7.0
+    assert torch.all(b.column("r")[:8] == 7.0)
+    t = crux.buffer_like(b, capacity=3)
+    crux.uniform_sample_(t, b, ids=[8, 1, 3])
+    assert t.indices.tolist() == [8, 1, 3] and torch.equal(t["s"], b["s"][[7, 0, 2]])
+    b.clear_()
+    assert len(b) == 0 and b.next_ind == 1
+    with pytest.raises(AssertionError):
+        b.push_({"s": np.ones((2, 3))})  # row shape mismatch (experience_buffer.jl:251 @assert)
+
+
+def test_prioritized_buffer_and_multi_source(crux, ctx):
+    # test/experience_buffer_tests.jl:193-205,225-262
+    bp = crux.ExperienceBuffer(crux.ContinuousSpace(2), crux.DiscreteSpace(4), 50, prioritized=True, ctx=ctx)
+    assert "weight" in bp and bp.isprioritized()
+    bp.update_priorities_([1, 2, 3], [1.0, 2.0, 3.0])
+    assert bp.max_priority == 3.0
+    assert_close(host(bp.priorities())[:3], np.array([1, 2, 3], F32) ** F32(0.6), rtol=1e-6)
+    d = {"s": 3 * np.ones((3, 2)), "a": np.ones((3, 4)), "sp": 5 * np.ones((3, 2)), "r": 6 * np.ones((3, 1)), "done": np.ones((3, 1))}
+    bp.push_(d); bp.push_(d)
+    assert bp.max_priority == 3.0
+    assert_close(host(bp.priorities())[:6], np.full(6, F32(3) ** F32(0.6)), rtol=1e-6)
+    bp["s"][:] = torch.rand((6, 2), device=ctx.device)
+    bp.update_priorities_(list(range(1, 7)), np.arange(1, 7, dtype=F32))
+    t = crux.ExperienceBuffer(crux.ContinuousSpace(2), crux.DiscreteSpace(4), 1000, ["weight"], ctx=ctx)
+    crux.rand_(t, bp)
+    pr = host(bp.priorities())[:6]
+    ids = t.indices
+    freqs = np.array([(ids == i).sum() for i in range(1, 7)]) / 1000
+    assert np.all(np.abs(freqs - pr / pr.sum()) / (pr / pr.sum()) < 0.01)
+    assert torch.equal(t["s"], bp["s"][torch.as_tensor(ids - 1, device=ctx.device)])
+    assert torch.all(t["weight"] <= 1.0 + 1e-6)
+    srcs = []
+    for v in (1.0, 2.0, 3.0):
+        s = crux.ExperienceBuffer(crux.ContinuousSpace(2), crux.DiscreteSpace(4), 10, ctx=ctx)
+        s.push_({"s": v * np.ones((1, 2)), "a": np.ones((1, 4)), "sp": np.ones((1, 2)), "r": np.ones((1, 1)), "done": np.zeros((1, 1))})
+        srcs.append(s)
+    t = crux.ExperienceBuffer(crux.ContinuousSpace(2), crux.DiscreteSpace(4), 10, ctx=ctx)
+    assert crux.rand_(t, *srcs) == [4, 3, 3]
+    assert torch.all(t["s"][:4] == 1) and torch.all(t["s"][4:7] == 2) and torch.all(t["s"][7:] == 3)
+    assert t.indices.tolist() == [1, 1, 1]  # only the LAST source's ids survive
+
+
+# ------------------------------------------------------------------------------------------------ Sampler
+def _actor_critic(crux, ctx, seed=0, obs=17, act=6, hid=64):
+    rng = np.random.default_rng(seed)
+    D = crux.Dense
+    mu = crux.ContinuousNetwork(crux.Chain(D(obs, hid, crux.tanh, rng=rng), D(hid, hid, crux.tanh, rng=rng), D(hid, act, rng=rng)), ctx=ctx)
+    cr = crux.ContinuousNetwork(crux.Chain(D(obs, hid, crux.tanh, rng=rng), D(hid, hid, crux.tanh, rng=rng), D(hid, 1, rng=rng)), ctx=ctx)
+    return crux.ActorCritic(crux.GaussianPolicy(mu, np.full(act, -0.5, F32)), cr)
+
+
+def _oracle_mlp(mlp):
+    flat, Ws, bs, off = mlp.get_flat(), [], [], 0
+    for l in range(len(mlp.acts)):
+        i, oo = mlp.dims[l], mlp.dims[l + 1]
+        Ws.append(flat[off:off + i * oo].reshape(i, oo).T.copy()); off += i * oo
+        bs.append(flat[off:off + oo].copy()); off += oo
+    return o.MLP(mlp.dims, mlp.acts, Ws=Ws, bs=bs)
+
+
+@pytest.mark.parametrize("device_env", [False, True])
+def test_sampler_steps_invariants_and_gae(crux, ctx, device_env):
+    """steps!/episode boundaries (test/gym/sampler_tests.jl:32-56) + GAE/returns of every stream against the oracle."""
+    n, T, max_steps = 16, 40, 7
+    pi = _actor_critic(crux, ctx)
+    env = crux.DeviceLinQuad(n, seed=5, max_steps=max_steps, ctx=ctx) if device_env else crux.HostLinQuad(n, seed=5)
+    cols = ["return", "logprob", "advantage", "t"] if not device_env else ["return", "logprob", "advantage"]
+    s = crux.Sampler(env, pi, max_steps=max_steps, required_columns=cols, lam=0.95)
+    buf = crux.ExperienceBuffer(crux.ContinuousSpace(17), crux.ContinuousSpace(6), n * T, cols, ctx=ctx)
+    data = s.steps_(buf, Nsteps=n * T, explore=True, i=0, reset=True)
+    assert len(buf) == n * T and buf.next_ind == 1
+    D = {k: host(v).reshape((T, n) + tuple(v.shape[1:])) for k, v in data.items()}
+    ee, done = D["episode_end"][..., 0].astype(bool), D["done"][..., 0].astype(bool)
+    assert ee[-1].all()                                   # steps!(reset=true) closes the open episode (sampler.jl:148)
+    for e in range(n):
+        ends = np.flatnonzero(ee[:, e])
+        lens = np.diff(np.concatenate([[-1], ends]))
+        assert lens.max() <= max_steps
+        for k, end in enumerate(ends[:-1]):
+            assert done[end, e] or lens[k] == max_steps  # test/gym/sampler_tests.jl:55
+        # inside an episode consecutive rows chain: s[t+1] == sp[t]; after an end the next row is a fresh initial state
+        for t in range(T - 1):
+            if ee[t, e]:
+                assert np.all(np.abs(D["s"][t + 1, e]) <= 0.1)
+            else:
+                assert np.array_equal(D["s"][t + 1, e], D["sp"][t, e])
+        if not device_env:
+            tcol = D["t"][:, e, 0]
+            assert tcol[0] == 1 and all(tcol[t + 1] == (1 if ee[t, e] else tcol[t] + 1) for t in range(T - 1))
+    # logprob of the stored action under the policy (test/policy_tests.jl:101-110)
+    lp = crux.logpdf(pi, data["s"], data["a"])
+    assert_close(host(lp)[:, 0], host(data["logprob"])[:, 0], rtol=1e-5, atol=2e-5)
+    # GAE / returns: the reference's per-episode recurrences on every stream with the oracle critic
+    V = _oracle_mlp(pi.C.mlp)
+    vs = V(D["s"].reshape(T * n, 17)).detach().numpy().reshape(T, n)
+    vsp = V(D["sp"].reshape(T * n, 17)).detach().numpy().reshape(T, n)
+    a0, r0 = o.gae_returns_TN(D["r"][..., 0], done, ee, vs, vsp, F32(0.99), F32(0.95))
+    assert_close(D["advantage"][..., 0], a0, rtol=1e-4, atol=2e-4, what="advantage")
+    assert_close(D["return"][..., 0], r0, rtol=1e-5, atol=2e-5, what="return")
+    assert buf.episodes()[-1][1] == n * T
+
+
+def test_sampler_noise_injection_and_second_call_continues(crux, ctx):
+    n, T = 8, 5
+    pi = _actor_critic(crux, ctx, seed=3)
+    env = crux.HostLinQuad(n, seed=1)
+    s = crux.Sampler(env, pi, max_steps=100, required_columns=["logprob"])
+    eps = [np.random.default_rng(t).standard_normal((n, 6)).astype(F32) for t in range(T)]
+    d = s.steps_(None, Nsteps=n * T, explore=True, noise=eps)
+    mu = _oracle_mlp(pi.A.mu.mlp)
+    ref = o.GaussianPolicy(mu, np.full(6, -0.5, F32))
+    S_ = host(d["s"]).reshape(T, n, 17)
+    for t in range(T):
+        a0, lp0 = ref.exploration(S_[t], eps[t])
+        assert_close(host(d["a"]).reshape(T, n, 6)[t], a0.detach().numpy(), rtol=1e-5, atol=1e-5)
+    last_sp = host(d["sp"]).reshape(T, n, 17)[-1]
+    d2 = s.steps_(None, Nsteps=n, explore=False)  # no reset in between: the streams continue where they stopped
+    assert np.array_equal(host(d2["s"]), last_sp)
+    assert_close(host(d2["a"]), mu(last_sp).detach().numpy(), rtol=1e-5, atol=1e-5)  # action(π, s) = μ(s)
+
+
+# ------------------------------------------------------------------------------------------------ PPO end to end
+def test_ppo_two_iterations_match_oracle(crux, ctx):
+    """The whole on-policy path (steps! -> GAE -> whiten -> batch_train! actor -> batch_train! critic) for two solve
+    iterations on identical inputs (same env stream, injected exploration noise and shuffles): final parameters against
+    the CPU restatement (cf. test/gym/solver_tests.jl:20-52, which asserts 1e-2 between the reference's CPU and GPU)."""
+    n, T, epochs, batch = 32, 16, 2, 128
+    ref = OraclePPO(n, T, seed=1, epochs=epochs, batch=batch, le=0.1, env_seed=7, max_steps=6)
+    rng = np.random.default_rng(1)
+    D_ = crux.Dense
+
+    def net(m):
+        return crux.ContinuousNetwork(crux.Chain(*[D_(m.dims[l], m.dims[l + 1], m.acts[l], m.W[l].detach().numpy(), m.b[l].detach().numpy())
+                                                   for l in range(3)]), ctx=ctx)
+    pi = crux.ActorCritic(crux.GaussianPolicy(net(ref.mu), np.full(6, -0.5, F32)), net(ref.critic))
+    opt = dict(epochs=epochs, batch_size=batch, optimizer=crux.Adam(F32(3e-4)))
+    S = crux.PPO(pi, crux.ContinuousSpace(17), eps=0.2, lp=1.0, le=0.1, target_kl=math.inf, a_opt=dict(opt), c_opt=dict(opt),
+                 N=n * T, dN=n * T, max_steps=6, lam_gae=0.95)
+    env = crux.HostLinQuad(n, seed=7)
+    s = crux.Sampler(env, S.agent, max_steps=6, required_columns=S.required_columns, lam=0.95)
+    buf = crux.ExperienceBuffer(crux.ContinuousSpace(17), crux.ContinuousSpace(6), n * T, S.required_columns, ctx=ctx)
+    noise_rng = np.random.default_rng(99)
+    for it in range(2):
+        eps = [noise_rng.standard_normal((n, 6)).astype(F32) for _ in range(T)]
+        oa = np.stack([noise_rng.permutation(n * T) for _ in range(epochs)])
+        oc = np.stack([noise_rng.permutation(n * T) for _ in range(epochs)])
+        Dref = ref.rollout(eps)
+        ref.update(Dref, (oa, oc))
+        data = s.steps_(buf, Nsteps=n * T, explore=True, i=it * n * T, reset=True, noise=eps)
+        assert_close(host(data["s"]), Dref["s"], rtol=1e-4, atol=1e-5, what=f"s it{it}")
+        assert_close(host(data["r"])[:, 0], Dref["r"], rtol=1e-4, atol=1e-5, what=f"r it{it}")
+        assert np.array_equal(host(data["episode_end"])[:, 0].astype(bool), Dref["episode_end"])
+        assert_close(host(data["advantage"])[:, 0], Dref["advantage"], rtol=1e-3, atol=1e-3, what=f"advantage it{it}")
+        S.post_batch_callback(buf)
+        assert_close(host(buf["advantage"])[:, 0], o.whiten(Dref["advantage"]), rtol=1e-3, atol=1e-3, what="whitened advantage")
+        S.policy_gradient_training(buf, (oa, oc))
+        info = S.training_info()
+        assert info["actor_batches_trained"] == epochs * (n * T // batch)
+        assert_close(info["actor_loss"], ref.last["actor"][-1]["actor_loss"], rtol=2e-3, atol=2e-4, what="actor_loss")
+        assert_close(info["kl"], ref.last["actor"][-1]["kl"], rtol=2e-2, atol=2e-5, what="kl")
+        assert_close(info["critic_loss"], ref.last["critic"][-1]["critic_loss"], rtol=2e-3, what="critic_loss")
+    steps = 2 * epochs * (n * T // batch)
+    assert_params_close(pi.A.mu.mlp.get_flat(), ref.mu.flat(), 3e-4, steps, what="actor", rtol=1e-4, atol=1e-5, frac=5e-3)
+    assert_params_close(pi.C.mlp.get_flat(), ref.critic.flat(), 3e-4, steps, what="critic", rtol=1e-4, atol=1e-5, frac=5e-3)
+    assert_close(host(pi.A.log_sigma), ref.pi.log_sigma.detach().numpy(), rtol=1e-4, atol=1e-5, what="logΣ")
+
+
+@pytest.mark.parametrize("device_env", [False, True])
+def test_solve_ppo_and_a2c_run(crux, ctx, device_env):
+    n, T = 64, 8
+    for ctor in (crux.PPO, crux.A2C):
+        pi = _actor_critic(crux, ctx, seed=4)
+        before = pi.A.mu.mlp.get_flat().copy()
+        opt = dict(epochs=2, batch_size=128)
+        log = crux.LoggerParams(period=n * T, verbose=False)
+        S = ctor(pi, crux.ContinuousSpace(17), a_opt=dict(opt), c_opt=dict(opt), N=3 * n * T, dN=n * T, max_steps=50, log=log)
+        env = crux.DeviceLinQuad(n, seed=1, max_steps=50, ctx=ctx) if device_env else crux.HostLinQuad(n, seed=1)
+        out = crux.solve(S, env)
+        assert out is pi and S.i == 3 * n * T
+        info = S.training_info()
+        assert np.isfinite(info["actor_loss"]) and np.isfinite(info["critic_loss"]) and info["actor_batches_trained"] >= 1
+        assert not np.array_equal(before, pi.A.mu.mlp.get_flat())
+        assert len(log.history) >= 3 and "actor_loss" in log.history[-1]
+        crux.solve(S, env)  # calling solve again continues (on_policy.jl:38,107)
+        assert S.i == 6 * n * T
+
+
+# ------------------------------------------------------------------------------------------------ DQN / SAC
+def test_dqn_value_training_matches_oracle(crux, ctx):
+    """value_training (off_policy.jl:66-111) for DQN with injected sample ids: dqn_target -> td_loss train! x epochs -> polyak."""
+    rng = np.random.default_rng(0)
+    chain = crux.Chain(crux.Dense(2, 8, crux.relu, rng=rng), crux.Dense(8, 4, rng=rng))
+    pi = crux.DiscreteNetwork(chain, [0, 1, 2, 3], ctx=ctx)
+    S = crux.DQN(pi, crux.ContinuousSpace(2), N=1000, dN=4, c_opt=dict(batch_size=32), buffer_size=200)
+    nb = 150
+    d = {"s": rng.standard_normal((nb, 2)).astype(F32), "a": np.eye(4, dtype=F32)[rng.integers(0, 4, nb)], "sp": rng.standard_normal((nb, 2)).astype(F32),
+         "r": rng.standard_normal((nb, 1)).astype(F32), "done": (rng.random((nb, 1)) < 0.2)}
+    S.buffer.push_(d)
+    q = _oracle_mlp(pi.mlp); qt = _oracle_mlp(S.agent.pi_target.mlp)
+    refnet = o.DiscreteNetwork(q, range(4))
+    opt = o.Adam(F32(3e-4))
+    draws = [rng.integers(1, nb + 1, 32) for _ in range(4)]
+    for ids in draws:
+        mb = {k: v[ids - 1] for k, v in d.items()}
+        y = o.dqn_target(qt(mb["sp"]).detach(), mb["r"], mb["done"], F32(0.95))
+        o.train_step(q.params(), lambda inf: o.td_loss(refnet.value(mb["s"], mb["a"]), y, None, inf), opt, {})
+    o.polyak_average(qt.params(), q.params(), 0.005)
+    Dmb = crux.buffer_like(S.buffer, capacity=32)
+    S.value_training(Dmb, F32(0.95), draws=draws)
+    assert_params_close(pi.mlp.get_flat(), q.flat(), 3e-4, 4, what="online Q")
+    assert_params_close(S.agent.pi_target.mlp.get_flat(), qt.flat(), 3e-4, 4, what="target Q")
+
+
+def test_solve_dqn_gridworld_readme_example(crux, ctx):
+    # README.md:72-82 / test/readme.jl (N reduced): DQN(π=DiscreteNetwork(Chain(Dense(2,8,relu), Dense(8,4)), actions), S, N)
+    rng = np.random.default_rng(0)
+    env = crux.SimpleGridWorld(4, seed=0)
+    pi = crux.DiscreteNetwork(crux.Chain(crux.Dense(2, 8, crux.relu, rng=rng), crux.Dense(8, 4, rng=rng)), [0, 1, 2, 3], ctx=ctx)
+    before = pi.mlp.get_flat().copy()
+    S = crux.DQN(pi, crux.ContinuousSpace(2), N=600, buffer_size=1000, buffer_init=200)
+    crux.solve(S, env)
+    assert S.i >= 600 and len(S.buffer) >= 600
+    assert not np.array_equal(before, pi.mlp.get_flat()) and np.isfinite(pi.mlp.get_flat()).all()
+    a = host(S.buffer["a"])
+    assert np.all(a.sum(1) == 1) and set(np.unique(a)) <= {0.0, 1.0}
+    # prioritized variant (off_policy.jl:83)
+    pi2 = crux.DiscreteNetwork(crux.Chain(crux.Dense(2, 8, crux.relu, rng=rng), crux.Dense(8, 4, rng=rng)), [0, 1, 2, 3], ctx=ctx)
+    S2 = crux.DQN(pi2, crux.ContinuousSpace(2), N=400, buffer_size=500, buffer_init=200, prioritized=True)
+    crux.solve(S2, env)
+    pr = host(S2.buffer.priorities())[:len(S2.buffer)]
+    assert np.all(pr > 0) and pr.std() > 0
+
+
+def test_solve_sac_runs(crux, ctx):
+    rng = np.random.default_rng(0)
+    D = crux.Dense
+    obs, act, hid = 17, 6, 32
+    A = crux.SquashedGaussianPolicy(crux.ContinuousNetwork(crux.Chain(D(obs, hid, crux.relu, rng=rng), D(hid, hid, crux.relu, rng=rng), D(hid, 2 * act, rng=rng)), ctx=ctx))
+    Q = lambda: crux.ContinuousNetwork(crux.Chain(D(obs + act, hid, crux.relu, rng=rng), D(hid, hid, crux.relu, rng=rng), D(hid, 1, rng=rng)), ctx=ctx)
+    pi = crux.ActorCritic(A, crux.DoubleNetwork(Q(), Q()))
+    before = A.mu.mlp.get_flat().copy()
+    S = crux.SAC(pi, crux.ContinuousSpace(obs), N=512, dN=64, c_opt=dict(batch_size=64, epochs=4), buffer_size=2000, buffer_init=256)
+    crux.solve(S, crux.HostLinQuad(16, seed=0))
+    after = A.mu.mlp.get_flat()
+    assert np.isfinite(after).all() and not np.array_equal(before, after)
+    assert len(S.buffer) == 512 and S.i == 512  # the initial fill counts toward N (off_policy.jl:122-133)

@@ -1,0 +1,102 @@
+"""CPU: host-side logic that needs no GPU -- schemas, schedules, logger periods, the synthetic environments."""
+import numpy as np
+import pytest
+
+
+def test_mdp_data_schema(crux):
+    # test/experience_buffer_tests.jl:8-20: default columns, extras by name, unknown key
+    A = crux._abi
+    d1 = crux.mdp_data(crux.ContinuousSpace(3), crux.ContinuousSpace(4), 100)
+    assert list(d1) == ["s", "a", "sp", "r", "done", "episode_end"]
+    assert d1["s"] == (A.F32, (3,), 0.0) and d1["a"] == (A.F32, (4,), 0.0) and d1["done"][0] == A.U8
+    d2 = crux.mdp_data(crux.ContinuousSpace(3), crux.ContinuousSpace(4), 100, ["weight", "t", "advantage", "return", "logprob"])
+    assert d2["weight"] == (A.F32, (1,), 1.0) and d2["t"][0] == A.I64 and d2["return"] == (A.F32, (1,), 0.0)
+    with pytest.raises(KeyError):
+        crux.mdp_data(crux.ContinuousSpace(3), crux.ContinuousSpace(4), 100, ["bad_key"])
+    d3 = crux.mdp_data(crux.ContinuousSpace((2, 2), np.uint8), crux.DiscreteSpace(4), 10)  # :271-278
+    assert d3["s"] == (A.U8, (2, 2), 0.0) and d3["a"][1] == (4,)
+
+
+def test_split_batches(crux):
+    assert crux.split_batches(100, [0.5, 0.5]) == [50, 50]
+    assert crux.split_batches(100, [1 / 3, 1 / 3, 1 / 3]) == [34, 33, 33]
+    with pytest.raises(AssertionError):
+        crux.split_batches(100, 0.4)
+
+
+def test_linear_decay_schedule(crux):
+    # utils.jl:116-126; test/util_tests.jl:55-86
+    l = crux.LinearDecaySchedule(1.0, 0.1, 10)
+    assert l(0) == 1.0 and l(31) == 0.1 and abs(l(5) - 0.55) < 1e-12
+
+
+def test_logger_elapsed(crux):
+    # logging.jl:1-2, test/logging_tests.jl
+    E = crux.LoggerParams.elapsed
+    assert E(500, 500) and not E(499, 500) and E(0, 500)
+    assert E((401, 600), 500) and not E((501, 600), 500) and E((1, 500), 500)
+
+
+def test_spaces(crux):
+    # test/spaces_tests.jl:15,24,34-40
+    assert crux.tovec(3, crux.DiscreteSpace(4)).tolist() == [False, False, True, False]
+    S = crux.ContinuousSpace(1, np.float32, np.float32(1), np.float32(2))
+    assert crux.tovec(np.array([0.0], np.float32), S)[0] == np.float32(-0.5)
+
+
+def test_host_linquad_matches_oracle_spec(crux):
+    from oracle import crux_oracle as o
+    spec = o.LinQuadSpec(17, 6, 0)
+    A, B = crux.linquad_matrices(17, 6, 0)
+    assert np.array_equal(A, spec.A) and np.array_equal(B, spec.B)
+    env = crux.HostLinQuad(64, seed=3)
+    s0 = env.reset().copy()
+    assert np.all(np.abs(s0) <= 0.1)
+    rng = np.random.default_rng(3)
+    rng.random((64, 17), dtype=np.float32)  # the reset draw
+    a = np.random.default_rng(1).standard_normal((64, 6)).astype(np.float32)
+    sp, r, done = env.step(a)
+    xi = rng.standard_normal((64, 17), dtype=np.float32)
+    sp0, r0, d0 = spec.step(s0, a, xi)
+    assert np.allclose(sp, sp0, atol=1e-6) and np.allclose(r, r0, atol=1e-6) and np.array_equal(done, d0)
+
+
+def test_gridworld(crux):
+    env = crux.SimpleGridWorld(1000, seed=0)
+    s = env.reset()
+    assert s.min() >= 1 and s.max() <= 10 and env.gamma == np.float32(0.95)
+    env.state[:4] = [[4, 3], [4, 6], [9, 3], [8, 8]]
+    env.state[4] = [1, 1]
+    sp, r, done = env.step(np.zeros(1000, dtype=np.int64))
+    assert r[:4].tolist() == [-10.0, -5.0, 10.0, 3.0] and done[:4].all() and (sp[:4] == -1).all()
+    assert r[4] == 0 and not done[4]
+    # transition statistics: the commanded move succeeds ~70 % of the time
+    env.state[:] = [5, 5]
+    sp, _, _ = env.step(np.full(1000, 3))  # :right
+    assert abs((sp[:, 0] == 6).mean() - 0.7) < 0.05
+    # walls keep the agent in place
+    env.state[:] = [10, 10]
+    sp, _, _ = env.step(np.full(1000, 3))
+    assert sp[:, 0].max() == 10
+
+
+def test_oracle_ppo_iteration_runs():
+    from oracle.ppo_cpu import OraclePPO
+    p = OraclePPO(8, 16, epochs=2, batch=32)
+    D = p.iteration()
+    assert D["s"].shape == (128, 17) and D["episode_end"][-8:].all()
+    assert len(p.last["actor"]) == 8 and np.isfinite(p.last["actor"][-1]["actor_loss"])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` prints one JSON line with the keys the driver reads (small steps; CPU only)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CRUX_BENCH_TINY="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "higher_is_better", "cpu_baseline", "e2e", "config"):
+        assert k in rec
+    assert rec["impl"] == "reference" and rec["value"] > 0 and rec["e2e"]["h2d_bytes_per_step"] == 0
