@@ -11,9 +11,12 @@
 // consecutive time steps of its stream in registers; the W warps of a CTA cover a chunk of W*L
 // steps and exchange carries through shared memory; chunks of the same env tile live in different
 // CTAs and exchange their (coefficient, offset) aggregates through global memory with a
-// look-back over the later chunks only (no serial chain), so the grid fills all SMs even when
-// N is small.  Later chunks get lower block indices, so a CTA only ever waits on CTAs that were
-// dispatched before it.
+// decoupled look-back over the later chunks only, so the grid fills all SMs even when N is small.
+// Blocks are ordered chunk-major, latest chunk first: a CTA only ever waits on CTAs with a lower
+// block index (dispatched earlier, no deadlock), and those were dispatched a whole tile-sweep
+// earlier, so their aggregates are normally already published.  The look-back itself is parallel:
+// warp k of the CTA polls and fetches the aggregate of later chunk k (one L2 round trip in total
+// instead of one per predecessor), then the composition runs out of shared memory.
 #include "common.cuh"
 
 namespace {
@@ -21,7 +24,7 @@ namespace {
 struct Agg { float pa, la, pr, lr; };  // A_in -> la + pa*A_in ; R_in -> lr + pr*R_in
 
 template <int L>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 gae_returns_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done,
                    const uint8_t *__restrict__ ee, const float *__restrict__ vs,
                    const float *__restrict__ vsp, int64_t T, int64_t N, float gamma, float lambda,
@@ -29,8 +32,9 @@ gae_returns_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done
                    float4 *__restrict__ agg_g, unsigned int *__restrict__ flag_g,
                    unsigned int *__restrict__ err_flags) {
   const int lane = threadIdx.x, w = threadIdx.y, W = blockDim.y;
-  const int tile = blockIdx.x / n_chunks;
-  const int chunk = n_chunks - 1 - (blockIdx.x % n_chunks);  // later chunks first
+  const int n_tiles = gridDim.x / n_chunks;
+  const int chunk = n_chunks - 1 - (int)(blockIdx.x / n_tiles);  // chunk-major, later chunks first
+  const int tile = blockIdx.x % n_tiles;
   const int64_t e = (int64_t)tile * 32 + lane;
   const bool live = e < N;
   const int64_t c_lo = (int64_t)chunk * chunk_len;
@@ -84,18 +88,28 @@ gae_returns_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done
     if (lane == 0) atomicExch(flag_g + (int64_t)tile * n_chunks + chunk, 1u);
   }
 
-  // carry into the END of this chunk: compose the aggregates of all later chunks (look-back)
+  // carry into the END of this chunk: compose the aggregates of all later chunks (look-back).
+  // Parallel fetch: warp ww handles later chunks chunk+1+ww, chunk+1+ww+W, ... -> shared memory.
   float Ain = 0.f, Rin = 0.f;
-  for (int k = n_chunks - 1; k > chunk; --k) {
-    if (lane == 0) {
-      const volatile unsigned int *f = flag_g + (int64_t)tile * n_chunks + k;
-      while (*f == 0u) { __nanosleep(20); }
+  const int n_later = n_chunks - 1 - chunk;
+  if (n_later > 0) {
+    __shared__ float4 s_look[64][32];
+    for (int q = w; q < n_later; q += W) {
+      const int k = chunk + 1 + q;
+      if (lane == 0) {
+        const volatile unsigned int *f = flag_g + (int64_t)tile * n_chunks + k;
+        while (*f == 0u) { __nanosleep(32); }
+      }
+      __syncwarp();
+      __threadfence();
+      s_look[q][lane] = __ldcg(agg_g + ((int64_t)tile * n_chunks + k) * 32 + lane);
     }
-    __syncwarp();
-    __threadfence();
-    const float4 x = __ldcg(agg_g + ((int64_t)tile * n_chunks + k) * 32 + lane);
-    Ain = fmaf(x.x, Ain, x.y);
-    Rin = fmaf(x.z, Rin, x.w);
+    __syncthreads();
+    for (int q = n_later - 1; q >= 0; --q) {  // latest chunk first
+      const float4 x = s_look[q][lane];
+      Ain = fmaf(x.x, Ain, x.y);
+      Rin = fmaf(x.z, Rin, x.w);
+    }
   }
   // ... then the later warps of this CTA
   for (int ww = W - 1; ww > w; --ww) {
@@ -214,9 +228,10 @@ int32_t crux_fill_gae_returns(crux_ctx *ctx, const float *r, const uint8_t *done
   int L, W;
   if (T <= 32) { L = 4; W = (int)cdiv(T, 4); }
   else if (T <= 128) { L = 8; W = (int)cdiv(T, 8); }
-  else { L = 16; W = 16; }
-  const int chunk_len = L * W;
-  const int n_chunks = (int)cdiv(T, chunk_len);
+  else { L = 8; W = 16; }  // chunk of 128 steps; 512 threads x <= 64 registers -> 2 CTAs (1024 threads) per SM
+  int chunk_len = L * W;
+  int n_chunks = (int)cdiv(T, chunk_len);
+  CRUX_REQUIRE(ctx, n_chunks <= 65, "crux_fill_gae_returns: T > 8320 steps per rollout is not supported");
   CRUX_REQUIRE(ctx, tiles * n_chunks < (1ll << 31), "crux_fill_gae_returns: grid too large");
   float4 *agg = nullptr;
   unsigned int *flags = nullptr;
@@ -234,7 +249,7 @@ int32_t crux_fill_gae_returns(crux_ctx *ctx, const float *r, const uint8_t *done
   gae_returns_kernel<LL><<<grid, block, 0, ctx->stream>>>(r, done, episode_end, v_s, v_sp, T, N, gamma,  \
                                                           lambda, adv, ret, n_chunks, chunk_len, agg,    \
                                                           flags, ctx->flags_dev)
-  if (L == 4) GAE_LAUNCH(4); else if (L == 8) GAE_LAUNCH(8); else GAE_LAUNCH(16);
+  if (L == 4) GAE_LAUNCH(4); else GAE_LAUNCH(8);
 #undef GAE_LAUNCH
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;

@@ -420,14 +420,15 @@ int32_t crux_mlp_create(crux_ctx *ctx, int32_t n_layers, const int32_t *dims, co
   m->n_params = off;
   const size_t bytes = (size_t)off * sizeof(float);
   const size_t gbytes = bytes + 128 * sizeof(float);  // tail: logΣ gradient + info sums ride the same all-reduce
-  if (cudaMalloc((void **)&m->params, bytes) != cudaSuccess || cudaMalloc((void **)&m->grads, gbytes) != cudaSuccess ||
+  // params is padded: the fused kernels stage it with a 16-byte-granular TMA bulk copy
+  if (cudaMalloc((void **)&m->params, bytes + 64) != cudaSuccess || cudaMalloc((void **)&m->grads, gbytes) != cudaSuccess ||
       cudaMalloc((void **)&m->m, bytes) != cudaSuccess || cudaMalloc((void **)&m->v, bytes) != cudaSuccess ||
       cudaMalloc((void **)&m->step_dev, sizeof(int)) != cudaSuccess ||
       cudaMalloc((void **)&m->norm_part, 1024 * sizeof(double)) != cudaSuccess) {
     crux_mlp_destroy(m);
     return crux_set_err(ctx, CRUX_ERR_OOM, "crux_mlp_create: cudaMalloc failed");
   }
-  cudaMemsetAsync(m->params, 0, bytes, ctx->stream);
+  cudaMemsetAsync(m->params, 0, bytes + 64, ctx->stream);
   cudaMemsetAsync(m->grads, 0, gbytes, ctx->stream);
   cudaMemsetAsync(m->m, 0, bytes, ctx->stream);
   cudaMemsetAsync(m->v, 0, bytes, ctx->stream);
@@ -488,6 +489,9 @@ int32_t crux_mlp_forward(crux_mlp *m, const float *x, int64_t B, float *y) {
   CRUX_REQUIRE(m->ctx, B >= 0, "crux_mlp_forward: negative batch");
   if (B == 0) return CRUX_OK;
   CRUX_REQUIRE(m->ctx, x && y, "crux_mlp_forward: NULL pointer");
+  int handled = 0;
+  const int rc = mlp_forward_fused(m, x, B, y, &handled);
+  if (rc || handled) return rc;
   return mlp_forward_out(m, x, B, y);
 }
 

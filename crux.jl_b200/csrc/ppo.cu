@@ -264,29 +264,34 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
       float *rec = actor->info_actor + ((int64_t)e * nmb_a + mbi) * CRUX_PPO_INFO_STRIDE;
       advance_kernel<<<1, 1, 0, ctx->stream>>>(actor->ctl, rec);
       CRUX_LAUNCHED(ctx);
-      GatherCols g;
-      g.n = 5;
-      g.src[0] = s; g.dst[0] = mb_s; g.dim[0] = sdim;
-      g.src[1] = a; g.dst[1] = mb_a; g.dim[1] = A;
-      g.src[2] = logprob; g.dst[2] = mb_lp; g.dim[2] = 1;
-      g.src[3] = advantage; g.dst[3] = mb_adv; g.dim[3] = 1;
-      g.src[4] = ret ? ret : advantage; g.dst[4] = mb_ret; g.dim[4] = 1;
-      dim3 gg((unsigned)i64min(cdiv(bm * sdim, 256), 1024), 5);
-      gather_cols_kernel<<<gg, 256, 0, ctx->stream>>>(g, order + off, bm, skip);
-      CRUX_LAUNCHED(ctx);
-      rc = mlp_forward_keep(mu, mb_s, bm, skip); if (rc) return rc;
-      const int hb = (int)cdiv(bm, 128);
-      CRUX_REQUIRE(ctx, (size_t)hb * HEAD_STRIDE <= 4096 || true, "");
-      // head partials live in scratch slot 4 (hb blocks x HEAD_STRIDE doubles)
-      double *part = (double *)crux_scratch(ctx, 4, (size_t)hb * HEAD_STRIDE * sizeof(double));
-      if (!part) return CRUX_ERR_OOM;
       const float inv_bg = 1.0f / ((float)bm * (float)ctx->world);
-      ppo_head_kernel<<<hb, 128, 0, ctx->stream>>>(mu->act[L], mb_a, mb_lp, mb_adv, ret ? mb_ret : nullptr, actor->log_sigma, A, bm,
-                                                   inv_bg, hp->eps_clip, hp->lambda_p, hp->a2c, mu->dz[L], part, skip);
-      CRUX_LAUNCHED(ctx);
-      ppo_finalize_kernel<<<1, 128, 0, ctx->stream>>>(part, hb, A, bm, hp->lambda_e, tail_ls_grad(mu), tail_sums(mu), skip);
-      CRUX_LAUNCHED(ctx);
-      rc = mlp_backward(mu, mb_s, bm, mu->dz[L], false, false, true, skip); if (rc) return rc;
+      int handled = 0;
+      rc = fused_minibatch(mu, 0, s, a, logprob, advantage, ret, order + off, bm, actor->log_sigma, inv_bg, hp->eps_clip, hp->lambda_p,
+                           hp->a2c, skip, &handled);
+      if (rc) return rc;
+      if (!handled) {
+        GatherCols g;
+        g.n = 5;
+        g.src[0] = s; g.dst[0] = mb_s; g.dim[0] = sdim;
+        g.src[1] = a; g.dst[1] = mb_a; g.dim[1] = A;
+        g.src[2] = logprob; g.dst[2] = mb_lp; g.dim[2] = 1;
+        g.src[3] = advantage; g.dst[3] = mb_adv; g.dim[3] = 1;
+        g.src[4] = ret ? ret : advantage; g.dst[4] = mb_ret; g.dim[4] = 1;
+        dim3 gg((unsigned)i64min(cdiv(bm * sdim, 256), 1024), 5);
+        gather_cols_kernel<<<gg, 256, 0, ctx->stream>>>(g, order + off, bm, skip);
+        CRUX_LAUNCHED(ctx);
+        rc = mlp_forward_keep(mu, mb_s, bm, skip); if (rc) return rc;
+        const int hb = (int)cdiv(bm, 128);
+        // head partials live in scratch slot 4 (hb blocks x HEAD_STRIDE doubles)
+        double *part = (double *)crux_scratch(ctx, 4, (size_t)hb * HEAD_STRIDE * sizeof(double));
+        if (!part) return CRUX_ERR_OOM;
+        ppo_head_kernel<<<hb, 128, 0, ctx->stream>>>(mu->act[L], mb_a, mb_lp, mb_adv, ret ? mb_ret : nullptr, actor->log_sigma, A, bm,
+                                                     inv_bg, hp->eps_clip, hp->lambda_p, hp->a2c, mu->dz[L], part, skip);
+        CRUX_LAUNCHED(ctx);
+        ppo_finalize_kernel<<<1, 128, 0, ctx->stream>>>(part, hb, A, bm, hp->lambda_e, tail_ls_grad(mu), tail_sums(mu), skip);
+        CRUX_LAUNCHED(ctx);
+        rc = mlp_backward(mu, mb_s, bm, mu->dz[L], false, false, true, skip); if (rc) return rc;
+      }
       if (ctx->world > 1) { rc = grads_allreduce(ctx, mu->grads, mu->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
       ppo_record_kernel<<<1, 1, 0, ctx->stream>>>(tail_sums(mu), tail_ls_grad(mu), actor->log_sigma, A, hp->lambda_p, hp->lambda_e,
                                                   hp->target_kl, hp->a2c, ctx->world, rec, actor->ctl);
@@ -317,21 +322,26 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
     for (int64_t mbi = 0; mbi < nmb_c && total < maxb_c; ++mbi, ++total) {
       const int64_t off = mbi * hp->critic_batch, bm = i64min(hp->critic_batch, n - off);
       float *rec = actor->info_critic + ((int64_t)e * nmb_c + mbi) * CRUX_PPO_INFO_STRIDE;
-      GatherCols g;
-      g.n = 2;
-      g.src[0] = s; g.dst[0] = mb_s; g.dim[0] = sdim;
-      g.src[1] = ret; g.dst[1] = mb_ret; g.dim[1] = 1;
-      dim3 gg((unsigned)i64min(cdiv(bm * sdim, 256), 1024), 2);
-      gather_cols_kernel<<<gg, 256, 0, ctx->stream>>>(g, order + off, bm, nullptr);
-      CRUX_LAUNCHED(ctx);
-      rc = mlp_forward_keep(critic, mb_s, bm, nullptr); if (rc) return rc;
-      const int hb = (int)i64min(cdiv(bm, 256), 512);
       const float inv_bg = 1.0f / ((float)bm * (float)ctx->world);
-      critic_head_kernel<<<hb, 256, 0, ctx->stream>>>(critic->act[Lc], mb_ret, bm, inv_bg, critic->dz[Lc], actor->partials);
-      CRUX_LAUNCHED(ctx);
-      critic_finalize_kernel<<<1, 32, 0, ctx->stream>>>(actor->partials, hb, bm, tail_sums(critic));
-      CRUX_LAUNCHED(ctx);
-      rc = mlp_backward(critic, mb_s, bm, critic->dz[Lc], false, false, true, nullptr); if (rc) return rc;
+      int handled = 0;
+      rc = fused_minibatch(critic, 1, s, nullptr, nullptr, nullptr, ret, order + off, bm, nullptr, inv_bg, 0.f, 0.f, 0, nullptr, &handled);
+      if (rc) return rc;
+      if (!handled) {
+        GatherCols g;
+        g.n = 2;
+        g.src[0] = s; g.dst[0] = mb_s; g.dim[0] = sdim;
+        g.src[1] = ret; g.dst[1] = mb_ret; g.dim[1] = 1;
+        dim3 gg((unsigned)i64min(cdiv(bm * sdim, 256), 1024), 2);
+        gather_cols_kernel<<<gg, 256, 0, ctx->stream>>>(g, order + off, bm, nullptr);
+        CRUX_LAUNCHED(ctx);
+        rc = mlp_forward_keep(critic, mb_s, bm, nullptr); if (rc) return rc;
+        const int hb = (int)i64min(cdiv(bm, 256), 512);
+        critic_head_kernel<<<hb, 256, 0, ctx->stream>>>(critic->act[Lc], mb_ret, bm, inv_bg, critic->dz[Lc], actor->partials);
+        CRUX_LAUNCHED(ctx);
+        critic_finalize_kernel<<<1, 32, 0, ctx->stream>>>(actor->partials, hb, bm, tail_sums(critic));
+        CRUX_LAUNCHED(ctx);
+        rc = mlp_backward(critic, mb_s, bm, critic->dz[Lc], false, false, true, nullptr); if (rc) return rc;
+      }
       if (ctx->world > 1) { rc = grads_allreduce(ctx, critic->grads, critic->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
       critic_record_kernel<<<1, 1, 0, ctx->stream>>>(tail_sums(critic), rec);
       CRUX_LAUNCHED(ctx);

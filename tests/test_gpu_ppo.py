@@ -176,3 +176,32 @@ def test_argument_errors(ctx, crux):
     hp = _hp(crux)
     assert ctx.lib.crux_ppo_update(h, hc, *args, 0, C.byref(hp), None, None, 0, None, None) == 1
     assert ctx.lib.crux_ppo_update(h, hc, args[0], args[1], args[2], args[3], None, n, C.byref(hp), None, None, 0, None, None) == 1
+
+
+def test_fused_path_equals_generic_engine(ctx, crux):
+    """The fused minibatch / forward kernels (ppo_fused.cu) against the generic layer-by-layer engine on the same inputs
+    (CRUX_NO_FUSED=1 selects the generic path at call time)."""
+    import os
+    n = 3000  # not a multiple of the 64-row tile
+    results = []
+    for no_fused in ("", "1"):
+        if no_fused:
+            os.environ["CRUX_NO_FUSED"] = "1"
+        else:
+            os.environ.pop("CRUX_NO_FUSED", None)
+        try:
+            rng, pi, cr, handles, D = _setup(ctx, crux, n, seed=77)
+            hp = _hp(crux, actor_batch=1000, critic_batch=1500, actor_epochs=2, critic_epochs=1)
+            oa = _orders(rng, n, 2); oc = _orders(rng, n, 1, start=oa[-1])
+            ia, ic = _run(ctx, crux, handles, D, hp, oa, oc, n)
+            y = ctx.empty((n, 6))
+            ctx.check(ctx.lib.crux_mlp_forward(handles[0], p(dev(ctx, D["s"])), n, p(y)))
+            results.append((ia.copy(), ic.copy(), mlp_params(ctx, handles[0]).copy(), mlp_params(ctx, handles[1]).copy(), host(y).copy()))
+        finally:
+            os.environ.pop("CRUX_NO_FUSED", None)
+    f, g = results
+    assert_close(f[0][:, :7], g[0][:, :7], rtol=2e-4, atol=2e-6, what="actor info fused vs generic")
+    assert_close(f[1][:, :2], g[1][:, :2], rtol=2e-4, atol=2e-6, what="critic info fused vs generic")
+    assert_params_close(f[2], g[2], 3e-4, 6, what="actor params fused vs generic")
+    assert_params_close(f[3], g[3], 3e-4, 2, what="critic params fused vs generic")
+    assert_close(f[4], g[4], rtol=1e-5, atol=1e-6, what="forward fused vs generic")
