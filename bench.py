@@ -137,7 +137,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
-        flush.fill_(k & 0xFF)              # evict the previous iteration's rollout from L2 (outside the event pair)
+        ctx.check(ctx.lib.crux_memset(ctx.h, flush.data_ptr(), k & 0xFF, flush.numel()))  # evict the previous rollout from L2 (outside the event pair)
         ev[k][0].record()
         one_step()
         ev[k][1].record()
@@ -162,7 +162,7 @@ def run_ours(args):
 
     # ---------------- e2e leg: host env through the public API --------------------------------------
     S2 = build_solver(crux, ctx, seed=2)
-    henv = crux.HostLinQuad(N_ENVS, OBS, ACT, seed=2000 + rank)
+    henv = crux.NativeHostLinQuad(N_ENVS, OBS, ACT, seed=2000 + rank)
     S2.N = dN
     for _ in range(max(1, args.warmup // 2)):
         crux.solve(S2, henv)
@@ -193,7 +193,7 @@ def run_ours(args):
                           "timing": "CUDA events per step on the launching stream, summed, max over ranks", "wall_ms_per_step": wall_ms / args.steps},
                "clocks": clk,
                "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                       "api": "crux.solve(PPO(...), HostLinQuad(4096)) -- numpy env on the host, pinned H2D/D2H every vector step"},
+                       "api": "crux.solve(PPO(...), NativeHostLinQuad(4096)) -- C++ env on %d host threads, pinned H2D/D2H every vector step" % henv.n_threads},
                "gpu_launches": int(launches),
                "roofline": phases["roofline"] if phases else None,
                "roofline_gae": gae,

@@ -15,7 +15,7 @@ from .policies import (ActorCritic, Chain, ContinuousNetwork, Dense, DiscreteNet
                        polyak_average_, relu, tanh, value)
 from .buffer import (ExperienceBuffer, PriorityParams, buffer_like, mdp_data, prioritized_sample_, rand_, split_batches,  # noqa: F401
                      uniform_sample_)
-from .envs import DeviceLinQuad, HostLinQuad, SimpleGridWorld, linquad_matrices  # noqa: F401
+from .envs import DeviceLinQuad, HostLinQuad, NativeHostLinQuad, SimpleGridWorld, linquad_matrices  # noqa: F401
 from .sampler import Sampler, fill_gae_, fill_returns_, steps_  # noqa: F401
 from .solvers import (A2C, DQN, PPO, SAC, Adam, LoggerParams, OffPolicySolver, OnPolicySolver, TrainingParams,  # noqa: F401
                       log_undiscounted_return, solve)

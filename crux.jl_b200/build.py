@@ -54,7 +54,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if jobs or force or _stale(LIB, objs):
         run([NVCC, "-shared", *objs, "-o", LIB, "-lcudart", "-ldl",
              "-gencode", "arch=compute_100a,code=sm_100a"])
+    build_host(force)
     return LIB
+
+
+HOST_LIB = os.path.join(LIBDIR, "libcrux_hostenv.so")
+HOST_LIB_AVX2 = os.path.join(LIBDIR, "libcrux_hostenv_avx2.so")
+
+
+def build_host(force: bool = False) -> str:
+    """g++ builds of the host-side synthetic env stepper (no CUDA): a baseline x86-64 variant that runs anywhere and an
+    AVX2+FMA variant (libmvec-vectorised) that envs.py selects when /proc/cpuinfo advertises avx2 and fma."""
+    src = os.path.join(CSRC, "host", "linquad_host.cpp")
+    cxx = os.environ.get("CXX", "g++")
+    for out, extra in ((HOST_LIB, []), (HOST_LIB_AVX2, ["-mavx2", "-mfma"])):
+        if force or _stale(out, [src]):
+            r = subprocess.run([cxx, "-O3", "-ffast-math", "-fopenmp-simd", "-std=c++17", "-fPIC", "-shared", "-pthread", *extra, src, "-o", out, "-lm"],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return HOST_LIB
 
 
 if __name__ == "__main__":

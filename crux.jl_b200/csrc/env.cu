@@ -51,7 +51,9 @@ __global__ void linquad_reset_kernel(float *__restrict__ obs, int32_t *__restric
   tick_advance(tick_dev);
 }
 
-__global__ void __launch_bounds__(128)
+// 8 lanes per env stream: lane q owns the 4 state dimensions 4q..4q+3 (one Philox draw = the 4 noise values of those
+// dimensions, same counters as before), the |s'|^2 partial sums are combined with width-8 shuffles.
+__global__ void __launch_bounds__(256)
 linquad_step_kernel(const float *__restrict__ Am, const float *__restrict__ Bm, const float *__restrict__ obs,
                     const float *__restrict__ act, int64_t n, int sdim, int adim, int max_steps, uint64_t seed,
                     unsigned long long *__restrict__ tick_dev, int force_end, float *__restrict__ sp_out, float *__restrict__ r_out, uint8_t *__restrict__ done_out,
@@ -61,43 +63,57 @@ linquad_step_kernel(const float *__restrict__ Am, const float *__restrict__ Bm, 
   for (int i = threadIdx.x; i < sdim * adim; i += blockDim.x) sB[i] = Bm[i];
   const uint64_t tick = *(volatile unsigned long long *)tick_dev;
   __syncthreads();
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < n) {
-  float s[LQ_MAX_S], ta[LQ_MAX_A], sp[LQ_MAX_S];
-  for (int k = 0; k < sdim; ++k) s[k] = obs[e * sdim + k];
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = gid >> 3;
+  const int q = (int)(gid & 7);
+  const bool live = e < n;
+  const int64_t ee = live ? e : n - 1;  // clamp: every lane takes part in the shuffles
+  float s[LQ_MAX_S], ta[LQ_MAX_A];
+#pragma unroll 4
+  for (int k = 0; k < sdim; ++k) s[k] = obs[ee * sdim + k];
+  const int len = ep_len[ee] + 1;  // sampler.jl:130 (read by all 8 lanes BEFORE the full-mask shuffles; lane 0 writes after them)
   float a2 = 0.f;
-  for (int j = 0; j < adim; ++j) { const float a = act[e * adim + j]; a2 += a * a; ta[j] = tanhf(a); }
-  float n2 = 0.f;
-  for (int k = 0; k < sdim; k += 4) {
-    const Philox4 p = philox4x32_10(seed, tick, (uint64_t)e * 16 + (k >> 2));
+  for (int j = 0; j < adim; ++j) { const float a = act[ee * adim + j]; a2 += a * a; ta[j] = tanhf(a); }
+  float sp[4] = {0.f, 0.f, 0.f, 0.f}, n2 = 0.f;
+  const int k0 = 4 * q;
+  if (k0 < sdim) {
+    const Philox4 p = philox4x32_10(seed, tick, (uint64_t)ee * 16 + q);
     float xi[4];
     box_muller(p.x, p.y, xi[0], xi[1]);
     box_muller(p.z, p.w, xi[2], xi[3]);
-    for (int q = 0; q < 4 && k + q < sdim; ++q) {
-      const int kk = k + q;
+    for (int i = 0; i < 4 && k0 + i < sdim; ++i) {
+      const int kk = k0 + i;
       float v = 0.f;
       for (int j = 0; j < sdim; ++j) v = fmaf(sA[kk * sdim + j], s[j], v);
       for (int j = 0; j < adim; ++j) v = fmaf(sB[kk * adim + j], ta[j], v);
-      v += 0.01f * xi[q];
+      v += 0.01f * xi[i];
       v = fminf(fmaxf(v, -10.f), 10.f);
-      sp[kk] = v; n2 += v * v;
+      sp[i] = v; n2 += v * v;
     }
   }
-  const float r = 1.f - n2 / (float)sdim - 0.1f * a2 / (float)adim;
-  const bool done = fabsf(sp[0]) > 5.f;
-  const int len = ep_len[e] + 1;  // sampler.jl:130
-  const bool end = done || len >= max_steps || force_end;  // :131 and the forced terminate of steps!(reset=true) :148
-  for (int k = 0; k < sdim; ++k) sp_out[e * sdim + k] = sp[k];
-  r_out[e] = r; done_out[e] = done ? 1 : 0; end_out[e] = end ? 1 : 0;
-  if (end) {
-    float s0[LQ_MAX_S];
-    linquad_s0(seed, tick + 0x100000000ULL, e, sdim, s0);  // reset_sampler! :31-43
-    for (int k = 0; k < sdim; ++k) next_obs[e * sdim + k] = s0[k];
-    ep_len[e] = 0;
-  } else {
-    for (int k = 0; k < sdim; ++k) next_obs[e * sdim + k] = sp[k];
-    ep_len[e] = len;
-  }
+  // |s'|^2 over the 8 lanes of the stream (fixed butterfly order); lane 0 holds s'_1
+  n2 += __shfl_xor_sync(0xffffffffu, n2, 1, 8);
+  n2 += __shfl_xor_sync(0xffffffffu, n2, 2, 8);
+  n2 += __shfl_xor_sync(0xffffffffu, n2, 4, 8);
+  const float sp0 = __shfl_sync(0xffffffffu, sp[0], 0, 8);
+  if (live) {
+    const float r = 1.f - n2 / (float)sdim - 0.1f * a2 / (float)adim;
+    const bool done = fabsf(sp0) > 5.f;
+    const bool end = done || len >= max_steps || force_end;  // :131 and the forced terminate of steps!(reset=true) :148
+    float nx[4] = {sp[0], sp[1], sp[2], sp[3]};
+    if (end && k0 < sdim) {  // reset_sampler! :31-43 (same counters as linquad_s0)
+      const Philox4 p = philox4x32_10(seed ^ 0x5851F42D4C957F2DULL, tick + 0x100000000ULL, (uint64_t)e * 16 + q);
+      const uint32_t u[4] = {p.x, p.y, p.z, p.w};
+      for (int i = 0; i < 4; ++i) nx[i] = (u32_to_unit_open(u[i]) * 2.f - 1.f) * 0.1f;
+    }
+    for (int i = 0; i < 4 && k0 + i < sdim; ++i) {
+      sp_out[e * sdim + k0 + i] = sp[i];
+      next_obs[e * sdim + k0 + i] = nx[i];
+    }
+    if (q == 0) {
+      r_out[e] = r; done_out[e] = done ? 1 : 0; end_out[e] = end ? 1 : 0;
+      ep_len[e] = end ? 0 : len;
+    }
   }
   tick_advance(tick_dev);
 }
@@ -154,7 +170,7 @@ int32_t crux_linquad_step(crux_linquad *env, const float *obs, const float *a, f
   if (!env) return CRUX_ERR_INVALID;
   crux_ctx *ctx = env->ctx;
   CRUX_REQUIRE(ctx, obs && a && sp && r && done && episode_end && next_obs, "crux_linquad_step: NULL pointer");
-  linquad_step_kernel<<<(unsigned)cdiv(env->n_env, 128), 128, 0, ctx->stream>>>(env->A, env->B, obs, a, env->n_env, env->sdim, env->adim,
+  linquad_step_kernel<<<(unsigned)cdiv(env->n_env * 8, 256), 256, 0, ctx->stream>>>(env->A, env->B, obs, a, env->n_env, env->sdim, env->adim,
                                                                                env->max_steps, env->seed, env->tick, force_end, sp, r,
                                                                                done, episode_end, next_obs, env->ep_len);
   CRUX_LAUNCHED(ctx);

@@ -42,21 +42,32 @@ gae_returns_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done
   const int64_t t0 = c_lo + (int64_t)w * L;  // this thread's steps: [t0, t0+L) clipped to c_hi
   const float c = lambda * gamma;
 
+  // Issue ALL loads of this thread's L steps back to back (straight-line, no control dependence: out-of-range steps
+  // and lanes are clamped onto valid rows and masked afterwards), so every warp keeps 5*L cache lines in flight.
   float dl[L], rr[L];
   unsigned int cut = 0;  // bit i: episode_end at step t0+i
+  {
+    const int64_t ec = live ? e : N - 1;
+    float va[L], vb[L];
+    unsigned char dn[L], en[L];
 #pragma unroll
-  for (int i = 0; i < L; ++i) {
-    const int64_t t = t0 + i;
-    float rv = 0.f, d = 0.f;
-    if (live && t < c_hi) {
-      const int64_t j = t * N + e;
-      rv = __ldcs(r + j);
-      const float a = __ldcs(vs + j), b = __ldcs(vsp + j);
-      const float nd = (1.0f - (float)done[j]) * gamma;
-      if (ee[j]) cut |= 1u << i;
-      d = (rv + nd * b) - a;
+    for (int i = 0; i < L; ++i) {
+      const int64_t tt = min(t0 + i, c_hi - 1);
+      const int64_t j = tt * N + ec;
+      rr[i] = __ldcs(r + j);
+      va[i] = __ldcs(vs + j);
+      vb[i] = __ldcs(vsp + j);
+      dn[i] = __ldcs(done + j);
+      en[i] = __ldcs(ee + j);
     }
-    rr[i] = rv; dl[i] = d;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const bool valid = live && (t0 + i < c_hi);
+      const float nd = (1.0f - (float)dn[i]) * gamma;
+      if (valid && en[i]) cut |= 1u << i;
+      dl[i] = valid ? (rr[i] + nd * vb[i]) - va[i] : 0.f;
+      rr[i] = valid ? rr[i] : 0.f;
+    }
   }
   // local aggregate of this thread's L steps (identity for padded steps)
   Agg g = {1.f, 0.f, 1.f, 0.f};

@@ -50,7 +50,3 @@ int grads_allreduce(crux_ctx *ctx, float *g, int64_t n);
 // ---- fused fast path (ppo_fused.cu): Chain(Dense(I,64,act), Dense(64,64,act), Dense(64,O)), I <= 32, O <= 8
 // value(π, s) in one launch; *handled == 0 -> the caller runs the generic engine.
 int mlp_forward_fused(crux_mlp *mlp, const float *x, int64_t B, float *y, int *handled);
-// one minibatch forward + loss + backward into mlp->grads (+ tail sums).  head 0: ppo_loss/a2c_loss, head 1: mse.
-int fused_minibatch(crux_mlp *mlp, int head, const float *s, const float *act, const float *logp_old, const float *adv, const float *ret,
-                    const int32_t *order, int64_t bm, const float *ls, float inv_bg, float eps_clip, float lambda_p, int a2c,
-                    const int *skip, int *handled);

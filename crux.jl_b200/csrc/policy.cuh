@@ -29,3 +29,10 @@ struct crux_gaussian {
 // gradient tail accessors (mlp->grads is allocated with CRUX_GRAD_TAIL extra floats)
 static inline float *tail_ls_grad(crux_mlp *m) { return m->grads + m->n_params; }
 static inline float *tail_sums(crux_mlp *m) { return m->grads + m->n_params + 64; }
+
+// ---- fused PPO update (ppo_fused.cu); *handled == 0 -> the generic engine in ppo.cu runs
+int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, const float *a, const float *logprob, const float *advantage,
+                     const float *ret, int64_t n, const crux_ppo_hp *hp, const int32_t *order_actor, const int32_t *order_critic,
+                     uint64_t seed, int *handled);
+int ppo_fill_order(crux_ctx *ctx, int32_t *out, int64_t n, uint64_t seed, uint32_t epoch);
+int ppo_ensure_bytes(crux_ctx *ctx, void **p, size_t *have, size_t need);

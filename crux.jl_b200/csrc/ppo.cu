@@ -198,9 +198,15 @@ int ensure_bytes(crux_ctx *ctx, void **p, size_t *have, size_t need) {
 
 }  // namespace
 
-int crux_ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, const float *a, const float *logprob,
-                          const float *advantage, const float *ret, int64_t n, const crux_ppo_hp *hp,
-                          const int32_t *order_actor, const int32_t *order_critic, int *handled);
+// helpers shared with the fused implementation (ppo_fused.cu)
+int ppo_fill_order(crux_ctx *ctx, int32_t *out, int64_t n, uint64_t seed, uint32_t epoch) {
+  int half_bits = 1;
+  while ((1ll << (2 * half_bits)) < n) ++half_bits;
+  perm_fill_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(out, n, half_bits, seed, epoch);
+  CRUX_LAUNCHED(ctx);
+  return CRUX_OK;
+}
+int ppo_ensure_bytes(crux_ctx *ctx, void **p, size_t *have, size_t need) { return ensure_bytes(ctx, p, have, need); }
 
 static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *s, const float *a, const float *logprob,
                            const float *advantage, const float *ret, int64_t n, const crux_ppo_hp *hp,
@@ -222,6 +228,11 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
     CRUX_REQUIRE(ctx, critic->dims[0] == sdim && critic->dims[critic->n_layers] == 1, "crux_ppo_update: critic shape");
   }
   int rc;
+  {
+    int handled = 0;
+    rc = ppo_update_fused(actor, nmb_c ? critic : nullptr, s, a, logprob, advantage, ret, n, hp, order_actor, order_critic, seed, &handled);
+    if (rc || handled) return rc;
+  }
   // workspaces
   const int64_t bmax = i64max(i64min(n, hp->actor_batch), nmb_c ? i64min(n, hp->critic_batch) : 0);
   const size_t mb_floats = (size_t)bmax * (sdim + A + 3);
@@ -265,11 +276,7 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
       advance_kernel<<<1, 1, 0, ctx->stream>>>(actor->ctl, rec);
       CRUX_LAUNCHED(ctx);
       const float inv_bg = 1.0f / ((float)bm * (float)ctx->world);
-      int handled = 0;
-      rc = fused_minibatch(mu, 0, s, a, logprob, advantage, ret, order + off, bm, actor->log_sigma, inv_bg, hp->eps_clip, hp->lambda_p,
-                           hp->a2c, skip, &handled);
-      if (rc) return rc;
-      if (!handled) {
+      {
         GatherCols g;
         g.n = 5;
         g.src[0] = s; g.dst[0] = mb_s; g.dim[0] = sdim;
@@ -323,10 +330,7 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
       const int64_t off = mbi * hp->critic_batch, bm = i64min(hp->critic_batch, n - off);
       float *rec = actor->info_critic + ((int64_t)e * nmb_c + mbi) * CRUX_PPO_INFO_STRIDE;
       const float inv_bg = 1.0f / ((float)bm * (float)ctx->world);
-      int handled = 0;
-      rc = fused_minibatch(critic, 1, s, nullptr, nullptr, nullptr, ret, order + off, bm, nullptr, inv_bg, 0.f, 0.f, 0, nullptr, &handled);
-      if (rc) return rc;
-      if (!handled) {
+      {
         GatherCols g;
         g.n = 2;
         g.src[0] = s; g.dst[0] = mb_s; g.dim[0] = sdim;

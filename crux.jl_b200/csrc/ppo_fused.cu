@@ -35,6 +35,14 @@ constexpr int P_SMEM = (P_MAX + 3) / 4 * 4 + 8;
 
 #define LOG_SQRT_2PI 0.9189385332046727f
 
+// tanh(x) = 1 - 2/(exp(2x) + 1) on the SFU (ex2.approx + rcp.approx): absolute error ~1e-7, against ~30 instructions for
+// libdevice tanhf (which was 27 % of the minibatch kernel's instruction stream).  Saturates correctly for |x| large.
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+__device__ __forceinline__ float act_fused(int act, float z) { return act == CRUX_ACT_TANH ? tanh_fast(z) : fmaxf(z, 0.0f); }
+
 // ---- shared memory carve-up (floats) ----------------------------------------------------------------------------------------
 struct SmemMap {
   static constexpr int P = 0;                       // raw params
@@ -93,12 +101,18 @@ __device__ __forceinline__ void stage_params(float *sm, const NetDesc &nd) {
   }
 }
 
-// transposed copies used by the data-backward GEMMs
+// transposed copies used by the data-backward GEMMs.  32x32 blocks with a diagonal skew: lane l handles column (l + i) & 31
+// of row l, so both the read (W2[k][j]) and the write (W2T[j][k]) touch 32 distinct banks.
 __device__ __forceinline__ void build_transposes(float *sm, int I, int O) {
   const float *W2 = sm + SmemMap::P + off_W2(I), *W3 = sm + SmemMap::P + off_W3(I);
-  for (int e = threadIdx.x; e < H * H; e += NT) {
-    const int j = e >> 6, k = e & 63;
-    sm[SmemMap::W2T + e] = W2[k * H + j];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;   // 8 warps: 4 blocks of 32x32, two warps per block (16 diagonals each)
+  {
+    const int blk = w >> 1, k0 = (blk >> 1) * 32, j0 = (blk & 1) * 32, i0 = (w & 1) * 16;
+#pragma unroll 4
+    for (int i = i0; i < i0 + 16; ++i) {
+      const int k = k0 + lane, j = j0 + ((lane + i) & 31);
+      sm[SmemMap::W2T + j * H + k] = W2[k * H + j];
+    }
   }
   for (int e = threadIdx.x; e < MAX_O * H; e += NT) {
     const int o = e >> 6, k = e & 63;
@@ -117,25 +131,29 @@ __device__ __forceinline__ void layer_fwd(const float *__restrict__ AT, int K, c
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const float *ap = AT + 4 * rg, *wp = W + 4 * jg;
+  float4 a = *reinterpret_cast<const float4 *>(ap), w = *reinterpret_cast<const float4 *>(wp);
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
-    const float4 a = *reinterpret_cast<const float4 *>(ap + k * LD);
-    const float4 w = *reinterpret_cast<const float4 *>(wp + k * H);
+    // operands of step k+1 are requested before the 16 FFMA of step k (the last prefetch re-reads row K-1: harmless)
+    const int kn = k + 1 < K ? k + 1 : k;
+    const float4 an = *reinterpret_cast<const float4 *>(ap + kn * LD);
+    const float4 wn = *reinterpret_cast<const float4 *>(wp + kn * H);
     const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    a = an; w = wn;
   }
   const float4 bb = *reinterpret_cast<const float4 *>(b + 4 * jg);
   const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float4 v;
-    v.x = act_fwd_rt(act, acc[0][j] + bv[j]);
-    v.y = act_fwd_rt(act, acc[1][j] + bv[j]);
-    v.z = act_fwd_rt(act, acc[2][j] + bv[j]);
-    v.w = act_fwd_rt(act, acc[3][j] + bv[j]);
+    v.x = act_fused(act, acc[0][j] + bv[j]);
+    v.y = act_fused(act, acc[1][j] + bv[j]);
+    v.z = act_fused(act, acc[2][j] + bv[j]);
+    v.w = act_fused(act, acc[3][j] + bv[j]);
     *reinterpret_cast<float4 *>(CT + (4 * jg + j) * LD + 4 * rg) = v;
   }
 }
@@ -166,15 +184,18 @@ __device__ __forceinline__ void layer_bwd_data(const float *__restrict__ DCT, in
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const float *dp = DCT + 4 * rg, *wp = WT + 4 * kg;
+  float4 d = *reinterpret_cast<const float4 *>(dp), w = *reinterpret_cast<const float4 *>(wp);
 #pragma unroll 4
   for (int j = 0; j < J; ++j) {
-    const float4 d = *reinterpret_cast<const float4 *>(dp + j * LD);
-    const float4 w = *reinterpret_cast<const float4 *>(wp + j * H);
+    const int jn = j + 1 < J ? j + 1 : j;
+    const float4 dn = *reinterpret_cast<const float4 *>(dp + jn * LD);
+    const float4 wn = *reinterpret_cast<const float4 *>(wp + jn * H);
     const float dv[4] = {d.x, d.y, d.z, d.w}, wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(dv[i], wv[c], acc[i][c]);
+    d = dn; w = wn;
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -217,7 +238,38 @@ struct FwdArgs {
   uint64_t seed, ctr;
 };
 
+// ---- small-batch variant pieces: 16-row tiles (4x more CTAs for a 4096-stream vector step), thread = (1 row, 4 cols)
+constexpr int R16 = 16, LD16 = R16 + 4;
+__device__ __forceinline__ void layer_fwd16(const float *__restrict__ AT, int K, const float *__restrict__ W, const float *__restrict__ b,
+                                            float *__restrict__ CT, int act) {
+  const int r = threadIdx.x >> 4, jg = threadIdx.x & 15;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float *ap = AT + r, *wp = W + 4 * jg;
+#pragma unroll 8
+  for (int k = 0; k < K; ++k) {
+    const float av = ap[k * LD16];
+    const float4 w = *reinterpret_cast<const float4 *>(wp + k * H);
+    acc[0] = fmaf(av, w.x, acc[0]); acc[1] = fmaf(av, w.y, acc[1]); acc[2] = fmaf(av, w.z, acc[2]); acc[3] = fmaf(av, w.w, acc[3]);
+  }
+  const float4 bb = *reinterpret_cast<const float4 *>(b + 4 * jg);
+  CT[(4 * jg + 0) * LD16 + r] = act_fused(act, acc[0] + bb.x);
+  CT[(4 * jg + 1) * LD16 + r] = act_fused(act, acc[1] + bb.y);
+  CT[(4 * jg + 2) * LD16 + r] = act_fused(act, acc[2] + bb.z);
+  CT[(4 * jg + 3) * LD16 + r] = act_fused(act, acc[3] + bb.w);
+}
+__device__ __forceinline__ void layer_out16(const float *__restrict__ H2T, const float *__restrict__ W3, const float *__restrict__ b3, int O,
+                                            float *__restrict__ OT) {
+  const int r = threadIdx.x & 15, o = threadIdx.x >> 4;  // 16 output slots >= MAX_O
+  if (o >= O) return;
+  float a0 = b3[o];
+#pragma unroll 8
+  for (int k = 0; k < H; ++k) a0 = fmaf(H2T[k * LD16 + r], W3[k * O + o], a0);
+  OT[o * LD16 + r] = a0;
+}
+
+template <int RT>
 __global__ void __launch_bounds__(NT, 2) fused_forward_kernel(FwdArgs a) {
+  constexpr int LDT = RT + 4;
   extern __shared__ __align__(16) float sm[];
   const int which = blockIdx.y;
   const NetDesc nd = a.net[which];
@@ -225,36 +277,50 @@ __global__ void __launch_bounds__(NT, 2) fused_forward_kernel(FwdArgs a) {
   stage_params(sm, nd);
   int *sidx = reinterpret_cast<int *>(sm + SmemMap::IDX);
   const float *P = sm + SmemMap::P;
-  const int64_t n_tiles = (a.B + R - 1) / R;
+  const int64_t n_tiles = (a.B + RT - 1) / RT;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncthreads();
-    if (threadIdx.x < R) {
-      const int64_t row = tile * R + threadIdx.x;
+    if (threadIdx.x < RT) {
+      const int64_t row = tile * RT + threadIdx.x;
       sidx[threadIdx.x] = row < a.B ? (int)row : -1;
     }
     __syncthreads();
-    load_rows_T(sm + SmemMap::XT, a.x, sidx, I);
-    __syncthreads();
-    layer_fwd(sm + SmemMap::XT, I, P, P + off_b1(I), sm + SmemMap::H1T, nd.act);
-    __syncthreads();
-    layer_fwd(sm + SmemMap::H1T, H, P + off_W2(I), P + off_b2(I), sm + SmemMap::H2T, nd.act);
-    __syncthreads();
-    layer_out(sm + SmemMap::H2T, P + off_W3(I), P + off_b3(I, O), O, sm + SmemMap::OT);
+    if (RT == R) {
+      load_rows_T(sm + SmemMap::XT, a.x, sidx, I);
+      __syncthreads();
+      layer_fwd(sm + SmemMap::XT, I, P, P + off_b1(I), sm + SmemMap::H1T, nd.act);
+      __syncthreads();
+      layer_fwd(sm + SmemMap::H1T, H, P + off_W2(I), P + off_b2(I), sm + SmemMap::H2T, nd.act);
+      __syncthreads();
+      layer_out(sm + SmemMap::H2T, P + off_W3(I), P + off_b3(I, O), O, sm + SmemMap::OT);
+    } else {
+      for (int e = threadIdx.x; e < RT * I; e += NT) {
+        const int r = e / I, i = e - r * I;
+        const int row = sidx[r];
+        sm[SmemMap::XT + i * LDT + r] = row >= 0 ? __ldg(a.x + (int64_t)row * I + i) : 0.f;
+      }
+      __syncthreads();
+      layer_fwd16(sm + SmemMap::XT, I, P, P + off_b1(I), sm + SmemMap::H1T, nd.act);
+      __syncthreads();
+      layer_fwd16(sm + SmemMap::H1T, H, P + off_W2(I), P + off_b2(I), sm + SmemMap::H2T, nd.act);
+      __syncthreads();
+      layer_out16(sm + SmemMap::H2T, P + off_W3(I), P + off_b3(I, O), O, sm + SmemMap::OT);
+    }
     __syncthreads();
     const float *OT = sm + SmemMap::OT;
     if (a.mode[which] == 0) {
       float *y = a.y[which];
-      for (int e = threadIdx.x; e < R * O; e += NT) {
+      for (int e = threadIdx.x; e < RT * O; e += NT) {
         const int r = e / O, o = e - r * O;
-        if (sidx[r] >= 0) y[(int64_t)sidx[r] * O + o] = OT[o * LD + r];
+        if (sidx[r] >= 0) y[(int64_t)sidx[r] * O + o] = OT[o * LDT + r];
       }
-    } else if (threadIdx.x < R && sidx[threadIdx.x] >= 0) {
+    } else if (threadIdx.x < RT && sidx[threadIdx.x] >= 0) {
       // exploration(::GaussianPolicy) policies.jl:338-344 + gaussian_logpdf :333-336 (same expression order as policy.cu)
       const int r = threadIdx.x;
       const int64_t i = sidx[r];
       float logp = 0.f, nrm[4];
       for (int j = 0; j < O; ++j) {
-        const float mu = OT[j * LD + r];
+        const float mu = OT[j * LDT + r];
         const float ls = a.ls[j];
         const float sigma = expf(ls);
         const float var = sigma * sigma;
@@ -290,13 +356,16 @@ struct MbArgs {
   float *partials;                                // [gridDim.x][pstride]
   int pstride;                                    // >= n_params + 16
   int n_params;
-  const int *skip;
+  const int *ctl;   // ctl[1] = 1 + index of the minibatch after which training stopped (0: not stopped); NULL: never skip
+  int mb;           // index of this minibatch in the update
 };
+// a minibatch is skipped when an EARLIER minibatch raised the stop flag (rl/ppo.jl:59 via training.jl:46,49)
+__device__ __forceinline__ bool stopped(const int *ctl, int mb) { return ctl && ctl[1] != 0 && ctl[1] <= mb; }
 
 // HEAD 0: ppo_loss / a2c_loss on a GaussianPolicy with a logΣ vector.  HEAD 1: Flux.mse(V(s), return).
 template <int HEAD>
 __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
-  if (a.skip && *a.skip) return;
+  if (stopped(a.ctl, a.mb)) return;
   extern __shared__ __align__(16) float sm[];
   const NetDesc nd = a.net;
   const int I = nd.I, O = nd.O, act = nd.act;
@@ -513,23 +582,139 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
 //   grads[p]                    p < n_params
 //   grads[n_params + j]         j < 8  : dL/dlogΣ_j           (tail_ls_grad)
 //   grads[n_params + 64 + q]    q < 5  : obj, kl, clip, adv, ret sums ; [5] = row count   (tail_sums)
-__global__ void reduce_fused_partials_kernel(const float *__restrict__ partials, int nparts, int pstride, int n_params, float *__restrict__ grads,
-                                             float count, const int *__restrict__ skip) {
-  if (skip && *skip) return;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_params + 16) return;
+// CTA = 32 parameters x 32 warps; warp w sums partials w, w+32, ... (all loads of a thread are independent: one L2 round
+// trip), the 32 sub-sums are combined in a fixed order.  The logΣ entries get the entropy term d(λe·e_loss)/dlogΣ = -λe here
+// (scaled by 1/world so that the all-reduce sum restores it).  Each CTA also emits the sum of squares of its 32 finished
+// gradient entries (used by the Adam kernel when there is no all-reduce in between).  Block 0 counts the optimiser step.
+constexpr int RW = 32;  // warps per reduce CTA
+__global__ void __launch_bounds__(RW * 32) reduce_fused_partials_kernel(const float *__restrict__ partials, int nparts, int pstride, int n_params,
+                                                                       float *__restrict__ grads, float count, float ls_shift, int n_ls,
+                                                                       double *__restrict__ norm_part, int *__restrict__ step_dev,
+                                                                       const int *__restrict__ ctl, int mb) {
+  if (stopped(ctl, mb)) return;
+  __shared__ double sh[RW][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + lane;
   double s = 0.0;
-  const float *src = partials + p;
-#pragma unroll 4
-  for (int c = 0; c < nparts; ++c) s += (double)src[(int64_t)c * pstride];
-  if (p < n_params) grads[p] = (float)s;
-  else if (p < n_params + 8) grads[p] = (float)s;
-  else {
-    const int q = p - n_params - 8;
-    if (q < 5) grads[n_params + 64 + q] = (float)s;
-    else if (q == 5) grads[n_params + 64 + 5] = count;
+  if (p < n_params + 16) {
+    const float *src = partials + p;
+#pragma unroll 10
+    for (int c = w; c < nparts; c += RW) s += (double)__ldcg(src + (int64_t)c * pstride);
+  }
+  sh[w][lane] = s;
+  __syncthreads();
+  if (w == 0) {
+    double sq = 0.0;
+    if (p < n_params + 16) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < RW; ++q) t += sh[q][lane];
+      if (p < n_params) { grads[p] = (float)t; sq = (double)(float)t * (double)(float)t; }
+      else if (p < n_params + 8) {
+        const int j = p - n_params;
+        const float g = (float)t + (j < n_ls ? ls_shift : 0.f);
+        grads[p] = g;
+        if (j < n_ls) sq = (double)g * (double)g;
+      } else {
+        const int q = p - n_params - 8;
+        if (q < 5) grads[n_params + 64 + q] = (float)t;
+        else if (q == 5) grads[n_params + 64 + 5] = count;
+      }
+    }
+    sq = warp_sum_d(sq);
+    if (lane == 0) norm_part[blockIdx.x] = sq;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;
+}
+
+// `train!` tail (training.jl:18-23) + the loss bookkeeping of the minibatch, one launch:
+//   gnorm = ||all grads||_2 (every CTA recomputes it, identical order -> identical value), NaN -> sticky error flag and no update,
+//   info record (block 0), KL early-stop vote (block 0), Flux Adam on this CTA's slice of the parameters.
+struct AdamArgs {
+  float *p, *g, *m, *v; int n;                       // network parameters
+  float *ls, *ls_g, *ls_m, *ls_v; int A;             // actor only: logΣ vector (A == 0 for a critic)
+  const float *sums;                                 // tail sums (after the optional all-reduce): obj, kl, clip, adv, ret, count
+  double eta, b1, b2, eps;
+  const int *step_dev;
+  float lambda_p, lambda_e, target_kl;
+  int a2c, head;                                     // head 0: actor (ppo/a2c), 1: critic (mse)
+  float *rec;                                        // info record of this minibatch
+  const double *norm_part; int n_norm_part;          // per-CTA sums of squares from the reduce kernel (NULL: recompute)
+  int *ctl; int mb;
+  unsigned int *err_flags;
+};
+__global__ void __launch_bounds__(256) fused_adam_kernel(AdamArgs a) {
+  if (stopped(a.ctl, a.mb)) return;
+  __shared__ double sh[8];
+  __shared__ double s_n2, s_c1, s_c2;
+  // ---- gradient norm over (network grads, logΣ grads incl. the entropy term): from the reduce kernel's per-CTA sums of
+  //      squares when nothing changed the gradient in between, else recomputed here (after an all-reduce)
+  double s = 0.0;
+  if (a.norm_part) {
+    for (int i = threadIdx.x; i < a.n_norm_part; i += blockDim.x) s += a.norm_part[i];
+  } else {
+    for (int i = threadIdx.x; i < a.n; i += blockDim.x) { const double v = (double)a.g[i]; s += v * v; }
+    if (threadIdx.x < a.A) { const double v = (double)a.ls_g[threadIdx.x]; s += v * v; }
+  }
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int q = 0; q < 8; ++q) t += sh[q];
+    s_n2 = t;
+    const int step = *a.step_dev;  // counts this step (incremented by the reduce kernel)
+    s_c1 = 1.0 - pow(a.b1, (double)step);
+    s_c2 = 1.0 - pow(a.b2, (double)step);
+  }
+  __syncthreads();
+  const double n2 = s_n2;
+  const bool bad = isnan(n2);
+  // ---- info record + early-stop vote (block 0, before any parameter changes)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float cnt = a.sums[5];
+    if (a.head == 0) {
+      float sls = 0.f;
+      for (int j = 0; j < a.A; ++j) sls += a.ls[j];
+      const float entropy = 1.4189385332046727f + sls;          // policies.jl:348
+      const float p_loss = -(a.sums[0] / cnt);
+      a.rec[CRUX_PPO_LOSS] = a.lambda_p * p_loss + a.lambda_e * (-entropy);
+      a.rec[CRUX_PPO_ENTROPY] = entropy;
+      const float kl = a.sums[1] / cnt;
+      a.rec[CRUX_PPO_KL] = kl;
+      a.rec[CRUX_PPO_CLIP_FRAC] = a.a2c ? 0.f : a.sums[2] / cnt;
+      a.rec[CRUX_PPO_AVG_ADV] = a.sums[3] / cnt;
+      a.rec[CRUX_PPO_AVG_RET] = a.sums[4] / cnt;
+      if (a.ctl && kl > a.target_kl) a.ctl[1] = a.mb + 1;         // this minibatch is still applied; later ones are skipped
+    } else {
+      a.rec[CRUX_PPO_LOSS] = a.sums[0] / cnt;
+    }
+    a.rec[CRUX_PPO_GRAD_NORM] = (float)sqrt(n2);
+    a.rec[CRUX_PPO_VALID] = 1.f;
+    if (bad) atomicOr(a.err_flags, CRUX_FLAG_NAN);                // training.jl:20: error before Flux.update!
+  }
+  if (bad) return;
+  __syncthreads();
+  // ---- Flux Adam (float32 moments, Float64 scalars)
+  const double c1 = s_c1, c2 = s_c2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    const double g = (double)a.g[i];
+    const float mt = (float)(a.b1 * (double)a.m[i] + (1.0 - a.b1) * g);
+    const float vt = (float)(a.b2 * (double)a.v[i] + (1.0 - a.b2) * g * g);
+    a.m[i] = mt; a.v[i] = vt;
+    a.p[i] = a.p[i] - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < a.A) {
+    const int i = threadIdx.x;
+    const double g = (double)a.ls_g[i];
+    const float mt = (float)(a.b1 * (double)a.ls_m[i] + (1.0 - a.b1) * g);
+    const float vt = (float)(a.b2 * (double)a.ls_v[i] + (1.0 - a.b2) * g * g);
+    a.ls_m[i] = mt; a.ls_v[i] = vt;
+    a.ls[i] = a.ls[i] - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
   }
 }
+
+__global__ void fused_ctl_reset_kernel(int *ctl) { ctl[0] = 0; ctl[1] = 0; }
 
 bool fusable(const crux_mlp *m) {
   return m && m->n_layers == 3 && m->dims[1] == H && m->dims[2] == H && m->dims[0] >= 1 && m->dims[0] <= MAX_I && m->dims[3] >= 1 &&
@@ -544,7 +729,11 @@ NetDesc describe(const crux_mlp *m) {
 }
 int set_smem_attr(crux_ctx *ctx) {
   static bool done[3] = {false, false, false};
-  if (!done[0]) { CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(fused_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)); done[0] = true; }
+  if (!done[0]) {
+    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(fused_forward_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(fused_forward_kernel<R16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    done[0] = true;
+  }
   if (!done[1]) { CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(fused_minibatch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)); done[1] = true; }
   if (!done[2]) { CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(fused_minibatch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)); done[2] = true; }
   return CRUX_OK;
@@ -562,9 +751,12 @@ int mlp_forward_fused(crux_mlp *mlp, const float *x, int64_t B, float *y, int *h
   FwdArgs a;
   memset(&a, 0, sizeof(a));
   a.net[0] = describe(mlp); a.mode[0] = 0; a.x = x; a.B = B; a.y[0] = y;
-  const int64_t tiles = cdiv(B, R);
+  // batches that cannot fill the GPU with 64-row tiles use 16-row tiles (4x the CTAs, latency-bound regime)
+  const bool small = cdiv(B, R) < (int64_t)ctx->num_sms;
+  const int64_t tiles = cdiv(B, small ? R16 : R);
   dim3 grid((unsigned)i64min(tiles, (int64_t)ctx->num_sms * 2), 1);
-  fused_forward_kernel<<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
+  if (small) fused_forward_kernel<R16><<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
+  else fused_forward_kernel<R><<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
   CRUX_LAUNCHED(ctx);
   *handled = 1;
   return CRUX_OK;
@@ -584,46 +776,107 @@ extern "C" int32_t crux_rollout_step_fused(crux_gaussian *actor, crux_mlp *criti
   a.net[0] = describe(actor->mu); a.mode[0] = 1; a.y[0] = a_out; a.logp = logp_out; a.ls = actor->log_sigma; a.eps_in = eps_in;
   a.seed = seed; a.ctr = ctr; a.x = obs; a.B = N;
   if (with_critic) { a.net[1] = describe(critic); a.mode[1] = 0; a.y[1] = v_out; }
-  const int64_t tiles = cdiv(N, R);
+  const bool small = cdiv(N, R) * (with_critic ? 2 : 1) < (int64_t)ctx->num_sms;
+  const int64_t tiles = cdiv(N, small ? R16 : R);
   dim3 grid((unsigned)i64min(tiles, (int64_t)ctx->num_sms * 2), with_critic ? 2 : 1);
-  fused_forward_kernel<<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
+  if (small) fused_forward_kernel<R16><<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
+  else fused_forward_kernel<R><<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
   CRUX_LAUNCHED(ctx);
   *handled = 1;
   return CRUX_OK;
 }
 
-// one minibatch: forward + loss + backward -> mlp->grads (+ tail).  head: 0 actor (ppo/a2c), 1 critic (mse)
-int fused_minibatch(crux_mlp *mlp, int head, const float *s, const float *act, const float *logp_old, const float *adv, const float *ret,
-                    const int32_t *order, int64_t bm, const float *ls, float inv_bg, float eps_clip, float lambda_p, int a2c,
-                    const int *skip, int *handled) {
-  *handled = 0;
-  if (!fusable(mlp) || getenv("CRUX_NO_FUSED")) return CRUX_OK;
+// one minibatch = 3 launches: fused forward/loss/backward -> partial reduction (+ step count) -> [all-reduce] -> norm/record/Adam
+static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const float *s, const float *act, const float *logp_old,
+                           const float *adv, const float *ret, const int32_t *order, int64_t bm, const crux_ppo_hp *hp, float *rec,
+                           int *ctl, int mb) {
   crux_ctx *ctx = mlp->ctx;
-  int rc = set_smem_attr(ctx); if (rc) return rc;
   const int64_t tiles = cdiv(bm, R);
   const int grid = (int)i64min(tiles, (int64_t)ctx->num_sms * 2);
   const int pstride = (int)((mlp->n_params + 16 + 31) / 32 * 32);
-  const size_t need = (size_t)grid * pstride * sizeof(float);
-  if (need > mlp->partials_bytes) {
-    CRUX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (mlp->partials) cudaFree(mlp->partials);
-    mlp->partials = nullptr; mlp->partials_bytes = 0;
-    const size_t want = (size_t)ctx->num_sms * 2 * pstride * sizeof(float);
-    if (cudaMalloc((void **)&mlp->partials, want > need ? want : need) != cudaSuccess) return crux_set_err(ctx, CRUX_ERR_OOM, "fused partials");
-    mlp->partials_bytes = want > need ? want : need;
-  }
+  const size_t need = (size_t)ctx->num_sms * 2 * pstride * sizeof(float);
+  int rc = ppo_ensure_bytes(ctx, (void **)&mlp->partials, &mlp->partials_bytes, need);
+  if (rc) return rc;
+  const float inv_bg = 1.0f / ((float)bm * (float)ctx->world);
   MbArgs a;
   memset(&a, 0, sizeof(a));
-  a.net = describe(mlp); a.s = s; a.act = act; a.logp_old = logp_old; a.adv = adv; a.ret = ret; a.order = order; a.bm = bm; a.ls = ls;
-  a.inv_bg = inv_bg; a.eps_clip = eps_clip; a.lambda_p = lambda_p; a.a2c = a2c; a.partials = mlp->partials; a.pstride = pstride;
-  a.n_params = (int)mlp->n_params; a.skip = skip;
+  a.net = describe(mlp); a.s = s; a.act = act; a.logp_old = logp_old; a.adv = adv; a.ret = ret; a.order = order; a.bm = bm;
+  a.ls = head == 0 ? actor->log_sigma : nullptr;
+  a.inv_bg = inv_bg; a.eps_clip = hp->eps_clip; a.lambda_p = hp->lambda_p; a.a2c = hp->a2c; a.partials = mlp->partials; a.pstride = pstride;
+  a.n_params = (int)mlp->n_params; a.ctl = ctl; a.mb = mb;
   if (head == 0) fused_minibatch_kernel<0><<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
   else fused_minibatch_kernel<1><<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
   CRUX_LAUNCHED(ctx);
   const int n_out = (int)mlp->n_params + 16;
-  reduce_fused_partials_kernel<<<(n_out + 255) / 256, 256, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads,
-                                                                          (float)bm, skip);
+  const int rblocks = (n_out + 31) / 32;   // <= 1024 doubles of norm_part (n_params <= 6792)
+  const float ls_shift = head == 0 ? -hp->lambda_e / (float)ctx->world : 0.f;
+  reduce_fused_partials_kernel<<<rblocks, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
+                                                                   ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb);
   CRUX_LAUNCHED(ctx);
+  if (ctx->world > 1) { rc = grads_allreduce(ctx, mlp->grads, mlp->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
+  AdamArgs g;
+  memset(&g, 0, sizeof(g));
+  g.p = mlp->params; g.g = mlp->grads; g.m = mlp->m; g.v = mlp->v; g.n = (int)mlp->n_params;
+  if (head == 0) { g.ls = actor->log_sigma; g.ls_g = tail_ls_grad(mlp); g.ls_m = actor->ls_m; g.ls_v = actor->ls_v; g.A = actor->adim; }
+  g.lambda_e = hp->lambda_e;
+  g.sums = tail_sums(mlp); g.eta = mlp->eta; g.b1 = mlp->beta1; g.b2 = mlp->beta2; g.eps = mlp->eps; g.step_dev = mlp->step_dev;
+  g.lambda_p = hp->lambda_p; g.target_kl = hp->target_kl; g.a2c = hp->a2c; g.head = head; g.rec = rec; g.ctl = ctl; g.mb = mb;
+  g.err_flags = ctx->flags_dev;
+  if (ctx->world == 1) { g.norm_part = mlp->norm_part; g.n_norm_part = rblocks; }
+  fused_adam_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g);
+  CRUX_LAUNCHED(ctx);
+  return CRUX_OK;
+}
+
+// policy_gradient_training (on_policy.jl:56-78) for fusable shapes: all actor epochs, then all critic epochs
+int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, const float *a, const float *logprob, const float *advantage,
+                     const float *ret, int64_t n, const crux_ppo_hp *hp, const int32_t *order_actor, const int32_t *order_critic,
+                     uint64_t seed, int *handled) {
+  *handled = 0;
+  crux_mlp *mu = actor->mu;
+  if (getenv("CRUX_NO_FUSED") || !fusable(mu) || actor->head_mode || actor->squashed || actor->adim != mu->dims[3]) return CRUX_OK;
+  if (critic && (!fusable(critic) || critic->dims[3] != 1)) return CRUX_OK;
+  crux_ctx *ctx = actor->ctx;
+  int rc = set_smem_attr(ctx); if (rc) return rc;
+  const int64_t nmb_a = cdiv(n, hp->actor_batch);
+  const int64_t nmb_c = critic ? cdiv(n, hp->critic_batch) : 0;
+  const size_t ia = (size_t)i64max(1, hp->actor_epochs * nmb_a) * CRUX_PPO_INFO_STRIDE * sizeof(float);
+  const size_t ic = (size_t)i64max(1, (int64_t)hp->critic_epochs * nmb_c) * CRUX_PPO_INFO_STRIDE * sizeof(float);
+  rc = ppo_ensure_bytes(ctx, (void **)&actor->info_actor, &actor->info_actor_bytes, ia); if (rc) return rc;
+  rc = ppo_ensure_bytes(ctx, (void **)&actor->info_critic, &actor->info_critic_bytes, ic); if (rc) return rc;
+  CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(actor->info_actor, 0, ia, ctx->stream));
+  CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(actor->info_critic, 0, ic, ctx->stream));
+  if (!order_actor || (nmb_c && !order_critic)) {
+    rc = ppo_ensure_bytes(ctx, (void **)&actor->order, &actor->order_bytes, (size_t)n * sizeof(int32_t)); if (rc) return rc;
+  }
+  fused_ctl_reset_kernel<<<1, 1, 0, ctx->stream>>>(actor->ctl);
+  CRUX_LAUNCHED(ctx);
+  int64_t total = 0;
+  const int64_t maxb_a = hp->actor_max_batches > 0 ? hp->actor_max_batches : INT64_MAX;
+  for (int e = 0; e < hp->actor_epochs && total < maxb_a; ++e) {
+    const int32_t *order;
+    if (order_actor) order = order_actor + (int64_t)e * n;
+    else { rc = ppo_fill_order(ctx, actor->order, n, seed, (uint32_t)e); if (rc) return rc; order = actor->order; }
+    for (int64_t mbi = 0; mbi < nmb_a && total < maxb_a; ++mbi, ++total) {
+      const int64_t off = mbi * hp->actor_batch, bm = i64min(hp->actor_batch, n - off);
+      float *rec = actor->info_actor + ((int64_t)e * nmb_a + mbi) * CRUX_PPO_INFO_STRIDE;
+      rc = fused_minibatch(actor, mu, 0, s, a, logprob, advantage, ret, order + off, bm, hp, rec, actor->ctl, (int)total);
+      if (rc) return rc;
+    }
+  }
+  total = 0;
+  const int64_t maxb_c = hp->critic_max_batches > 0 ? hp->critic_max_batches : INT64_MAX;
+  for (int e = 0; e < hp->critic_epochs && nmb_c && total < maxb_c; ++e) {
+    const int32_t *order;
+    if (order_critic) order = order_critic + (int64_t)e * n;
+    else { rc = ppo_fill_order(ctx, actor->order, n, seed ^ 0xC2B2AE3D27D4EB4FULL, (uint32_t)e); if (rc) return rc; order = actor->order; }
+    for (int64_t mbi = 0; mbi < nmb_c && total < maxb_c; ++mbi, ++total) {
+      const int64_t off = mbi * hp->critic_batch, bm = i64min(hp->critic_batch, n - off);
+      float *rec = actor->info_critic + ((int64_t)e * nmb_c + mbi) * CRUX_PPO_INFO_STRIDE;
+      rc = fused_minibatch(actor, critic, 1, s, nullptr, nullptr, nullptr, ret, order + off, bm, hp, rec, nullptr, (int)total);
+      if (rc) return rc;
+    }
+  }
   *handled = 1;
   return CRUX_OK;
 }

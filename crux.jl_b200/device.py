@@ -93,6 +93,26 @@ class Context:
             t = t.to(dtype)
         return t.to(self.device).contiguous()
 
+    # ---- pinned host staging (numpy views over cudaMallocHost memory) and raw async copies on the context stream
+    def pinned_array(self, shape, dtype=np.float32):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self.check(self.lib.crux_pinned_alloc(self.h, max(n, 16), C.byref(p)))
+        buf = (C.c_uint8 * max(n, 16)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned_keep = getattr(self, "_pinned_keep", [])
+        self._pinned_keep.append(p)
+        return arr
+
+    def h2d(self, dst, src_np):
+        """async copy host (pinned numpy) -> device tensor / pointer"""
+        self.check(self.lib.crux_memcpy_h2d(self.h, ptr(dst), C.c_void_p(src_np.ctypes.data), src_np.nbytes))
+
+    def d2h(self, dst_np, src):
+        """async copy device tensor / pointer -> host (pinned numpy)"""
+        self.check(self.lib.crux_memcpy_d2h(self.h, C.c_void_p(dst_np.ctypes.data), ptr(src), dst_np.nbytes))
+
     # ---- multi-GPU -------------------------------------------------------------------------
     def init_distributed(self, rank, world, peer_floats=0):
         """One rank per GPU.  The NCCL unique id travels through torch.distributed (any backend)."""

@@ -70,6 +70,78 @@ class HostLinQuad:
         return sp, r, done
 
 
+class NativeHostLinQuad:
+    """LinQuad on the host in C++ (csrc/host/linquad_host.cpp -> lib/libcrux_hostenv.so): N streams stepped by a pool of
+    worker threads, same Philox noise streams as ``DeviceLinQuad``.  This is the "vectorised CPU env step of a synthetic
+    MDP" of the north-star's e2e path; ``step_into`` writes straight into the sampler's pinned staging buffers."""
+    on_device = False
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            import os
+            libdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+            path = os.path.join(libdir, "libcrux_hostenv.so")
+            try:  # the AVX2+FMA build (libmvec-vectorised) when the CPU has it
+                flags = open("/proc/cpuinfo").read()
+                fast = os.path.join(libdir, "libcrux_hostenv_avx2.so")
+                if " avx2" in flags and " fma" in flags and os.path.exists(fast) and not os.environ.get("CRUX_HOSTENV_BASELINE"):
+                    path = fast
+            except OSError:
+                pass
+            if not os.path.exists(path):
+                raise ImportError(f"{path} is missing: run `python crux.jl_b200/build.py`")
+            L = C.CDLL(path)
+            L.crux_hostenv_create.restype = C.c_void_p
+            L.crux_hostenv_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+            L.crux_hostenv_destroy.argtypes = [C.c_void_p]
+            L.crux_hostenv_threads.argtypes = [C.c_void_p]
+            L.crux_hostenv_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            L.crux_hostenv_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, n_envs, obs_dim=17, act_dim=6, seed=0, gamma=0.99, n_threads=0):
+        self.n_envs, self.obs_dim, self.act_dim = int(n_envs), obs_dim, act_dim
+        self.gamma = F32(gamma)
+        self.action_space = ContinuousSpace(act_dim)
+        A, B = linquad_matrices(obs_dim, act_dim, 0)
+        self.h = self.lib().crux_hostenv_create(self.n_envs, obs_dim, act_dim, A.ctypes.data, B.ctypes.data, int(seed), int(n_threads))
+        assert self.h, "crux_hostenv_create failed"
+        self.n_threads = self.lib().crux_hostenv_threads(self.h)
+        self._sp = np.empty((self.n_envs, obs_dim), F32)
+        self._r = np.empty(self.n_envs, F32)
+        self._done = np.empty(self.n_envs, np.uint8)
+
+    def reset(self, idx=None):
+        if idx is None:
+            out = np.empty((self.n_envs, self.obs_dim), F32)
+            self.lib().crux_hostenv_reset(self.h, None, 0, out.ctypes.data)
+            return out
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        out = np.empty((len(idx), self.obs_dim), F32)
+        self.lib().crux_hostenv_reset(self.h, idx.ctypes.data, len(idx), out.ctypes.data)
+        return out
+
+    def step_into(self, a, sp, r, done):
+        """a [N, act] f32, sp [N, obs] f32, r [N] f32, done [N] u8: contiguous numpy arrays (may be pinned memory)."""
+        self.lib().crux_hostenv_step(self.h, a.ctypes.data, sp.ctypes.data, r.ctypes.data, done.ctypes.data)
+
+    def step(self, a):
+        a = np.ascontiguousarray(a, dtype=F32)
+        self.step_into(a, self._sp, self._r, self._done)
+        return self._sp.copy(), self._r.copy(), self._done.astype(bool)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib().crux_hostenv_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class DeviceLinQuad:
     """The same MDP stepped on the GPU (``crux_linquad_*``): observations, actions and transitions never leave HBM.
     Episode bookkeeping (episode_length, max_steps, reset) is done inside the step kernel like ``step!`` does

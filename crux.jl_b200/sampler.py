@@ -56,8 +56,8 @@ class Sampler:
         else:
             o = self._tovec(self.mdp.reset(None))
             self._pin()
-            self._pinned["obs"].copy_(torch.from_numpy(o))
-            self.cur.copy_(self._pinned["obs"], non_blocking=True)
+            self._pinned["obs"][...] = o
+            self.ctx.h2d(self.cur, self._pinned["obs"])
         self.episode_length[:] = 0
 
     def _tovec(self, o):
@@ -69,15 +69,16 @@ class Sampler:
         return o
 
     def _pin(self):
+        """Pinned host staging buffers (numpy views over cudaMallocHost memory): the env reads actions from and writes
+        transitions into them; copies are raw cudaMemcpyAsync calls on the context stream."""
         if self._pinned is not None:
             return
-        n, sd = self.n, self.sdim
+        n, sd, ctx = self.n, self.sdim, self.ctx
         A = self.agent.space
         adim = A.N if isinstance(A, DiscreteSpace) else int(np.prod(A.dims))
-        mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
-        self._pinned = {"obs": mk((n, sd), torch.float32), "sp": mk((n, sd), torch.float32), "r": mk((n,), torch.float32),
-                        "done": mk((n,), torch.uint8), "ee": mk((n,), torch.uint8), "t": mk((n,), torch.int64),
-                        "a": mk((n, adim), torch.float32), "ai": mk((n,), torch.int32)}
+        self._pinned = {"obs": ctx.pinned_array((n, sd)), "sp": ctx.pinned_array((n, sd)), "r": ctx.pinned_array((n,)),
+                        "done": ctx.pinned_array((n,), np.uint8), "ee": ctx.pinned_array((n,), np.uint8),
+                        "t": ctx.pinned_array((n,), np.int64), "a": ctx.pinned_array((n, adim)), "ai": ctx.pinned_array((n,), np.int32)}
 
     def _tmp(self, name, shape, dtype=torch.float32):
         t = self._scratch.get(name)
@@ -192,49 +193,63 @@ class Sampler:
             env.step_into(s[rows], a[rows], sp[rows], r[rows], done[rows], ee[rows], nxt, force_end=(reset and t == T - 1))
 
     def _rollout_host(self, data, T, explore, i, reset, noise, discrete):
-        n, env, P = self.n, self.mdp, None
+        n, env, ctx = self.n, self.mdp, self.ctx
         self._pin()
         P = self._pinned
         s, a, sp, r = data["s"], data["a"], data["sp"], data["r"]
         done, ee, logp, tcol, icol = data["done"], data["episode_end"], data.get("logprob"), data.get("t"), data.get("i")
-        stream = torch.cuda.current_stream(self.ctx.device)
+        native = hasattr(env, "step_into") and not discrete
         for t in range(T):
             rows = slice(t * n, (t + 1) * n)
-            s[rows].copy_(P["obs"], non_blocking=True)                       # H2D: svec of every stream
+            ctx.h2d(s[rows], P["obs"])                                        # H2D: svec of every stream
             env_a = self._act(s[rows], a[rows], None if logp is None else logp[rows], explore, i + t * n,
                               None if noise is None else noise[t])
             if discrete:
-                P["ai"].copy_(env_a.reshape(-1), non_blocking=True)
+                ctx.d2h(P["ai"], env_a.reshape(-1).to(torch.int32))
             else:
-                P["a"].copy_(env_a, non_blocking=True)                       # D2H: the env needs the action
-            stream.synchronize()
-            spn, rn, dn = env.step(P["ai"].numpy() if discrete else P["a"].numpy())   # @gen(:sp,:r), isterminal
-            spv = self._tovec(spn)
-            P["t"].copy_(torch.from_numpy(self.episode_length + 1))
+                ctx.d2h(P["a"], env_a)                                        # D2H: the env needs the action
+            ctx.sync()
+            if native:                                                        # @gen(:sp,:r), isterminal
+                env.step_into(P["a"], P["sp"], P["r"], P["done"])
+                spv, dn = P["sp"], P["done"].astype(bool)
+                if self._needs_tovec():
+                    P["sp"][...] = self._tovec(P["sp"])
+            else:
+                spn, rn, dn = env.step(P["ai"] if discrete else P["a"])
+                spv = self._tovec(spn)
+                P["sp"][...] = spv
+                P["r"][...] = rn
+                dn = np.asarray(dn, dtype=bool)
+                P["done"][...] = dn
+            if tcol is not None:
+                P["t"][...] = self.episode_length + 1
             self.episode_length += 1                                          # sampler.jl:130
-            end = np.asarray(dn, dtype=bool) | (self.episode_length >= self.max_steps)
+            end = dn | (self.episode_length >= self.max_steps)
             if reset and t == T - 1:
                 end = np.ones(n, dtype=bool)                                  # steps!(reset=true) :148
-            P["sp"].copy_(torch.from_numpy(spv))
-            P["r"].copy_(torch.from_numpy(np.asarray(rn, dtype=F32)))
-            P["done"].copy_(torch.from_numpy(np.asarray(dn, dtype=np.uint8)))
-            P["ee"].copy_(torch.from_numpy(end.astype(np.uint8)))
-            sp[rows].copy_(P["sp"], non_blocking=True)                       # H2D: the transition
-            r[rows].copy_(P["r"].reshape(r[rows].shape), non_blocking=True)
-            done[rows].copy_(P["done"].reshape(done[rows].shape), non_blocking=True)
-            ee[rows].copy_(P["ee"].reshape(ee[rows].shape), non_blocking=True)
+            P["ee"][...] = end
+            ctx.h2d(sp[rows], P["sp"])                                        # H2D: the transition
+            ctx.h2d(r[rows], P["r"])
+            ctx.h2d(done[rows], P["done"])
+            ctx.h2d(ee[rows], P["ee"])
             if tcol is not None:
-                tcol[rows].copy_(P["t"].reshape(tcol[rows].shape), non_blocking=True)
+                ctx.h2d(tcol[rows], P["t"])
             if icol is not None:
                 icol[rows].fill_(i + t * n + 1)
-            nxt = spv
-            if end.any():                                                     # terminate_episode! -> reset_sampler!
+            # next observation: sp, or a fresh initial state where the episode ended (terminate_episode! -> reset_sampler!).
+            # The staging buffers are rewritten only after the next ctx.sync() (after the action D2H), when the copies
+            # queued above have completed -- except obs, whose previous H2D finished before this step's sync.
+            P["obs"][...] = P["sp"]
+            if end.any():
                 idx = np.flatnonzero(end)
-                nxt = spv.copy()
-                nxt[idx] = self._tovec(env.reset(idx))
+                P["obs"][idx] = self._tovec(env.reset(idx))
                 self.episode_length[idx] = 0
-            P["obs"].copy_(torch.from_numpy(nxt))
-        self.cur.copy_(P["obs"], non_blocking=True)
+        ctx.h2d(self.cur, P["obs"])
+        ctx.sync()
+
+    def _needs_tovec(self):
+        mu, sg = getattr(self.S, "mu", 0), getattr(self.S, "sigma", 1)
+        return bool(np.any(np.asarray(mu) != 0) or np.any(np.asarray(sg) != 1))
 
     # ---- fill_gae! / fill_returns! (sampler.jl:255-281) for every episode range of every stream
     def fill_gae_returns_(self, data, T):

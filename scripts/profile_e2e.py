@@ -9,7 +9,7 @@ import bench
 
 ctx = crux.Context(0)
 S = bench.build_solver(crux, ctx, seed=2)
-env = crux.HostLinQuad(bench.N_ENVS, bench.OBS, bench.ACT, seed=5)
+env = (crux.HostLinQuad if '--numpy' in sys.argv else crux.NativeHostLinQuad)(bench.N_ENVS, bench.OBS, bench.ACT, seed=5)
 crux.solve(S, env)
 torch.cuda.synchronize()
 pr = cProfile.Profile()

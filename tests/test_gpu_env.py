@@ -62,3 +62,27 @@ def test_linquad_step(ctx):
     ctx.check(ctx.lib.crux_linquad_step(env, p(cur), p(dev(ctx, a)), p(sp), p(r), p(done), p(ee), p(nxt), 1))
     assert host(ee).all() and not host(done).any()
     ctx.lib.crux_linquad_destroy(env)
+
+
+def test_host_and_device_env_share_noise_streams(ctx, crux):
+    """NativeHostLinQuad (C++) and DeviceLinQuad (CUDA) draw the same Philox streams: same seed + same actions ->
+    the same trajectories up to libm-vs-CUDA math rounding."""
+    n = 512
+    dev_env = crux.DeviceLinQuad(n, seed=21, max_steps=1000, ctx=ctx)
+    host_env = crux.NativeHostLinQuad(n, seed=21)
+    obs = ctx.empty((n, 17))
+    dev_env.reset_into(obs)
+    s0 = host_env.reset()
+    assert np.array_equal(host(obs), s0)
+    rng = np.random.default_rng(0)
+    sp, r, nxt = ctx.empty((n, 17)), ctx.empty((n,)), ctx.empty((n, 17))
+    done = torch.empty(n, dtype=torch.uint8, device=ctx.device); ee = torch.empty(n, dtype=torch.uint8, device=ctx.device)
+    cur = obs
+    for t in range(4):
+        a = rng.standard_normal((n, 6)).astype(F32)
+        dev_env.step_into(cur, dev(ctx, a), sp, r, done, ee, nxt)
+        sph, rh, dh = host_env.step(a)
+        assert_close(host(sp), sph, rtol=1e-5, atol=2e-6, what=f"sp step {t}")
+        assert_close(host(r), rh, rtol=1e-5, atol=1e-5, what=f"r step {t}")
+        assert np.array_equal(host(done).astype(bool), dh)
+        cur = nxt.clone()

@@ -15,7 +15,7 @@ NETS = [([17, 64, 64, 6], [1, 1, 0]), ([17, 64, 64, 1], [1, 1, 0]), ([2, 8, 4], 
 
 
 @pytest.mark.parametrize("dims,acts", NETS)
-@pytest.mark.parametrize("B", [1, 7, 128, 4096])
+@pytest.mark.parametrize("B", [1, 7, 128, 4096, 20000])
 def test_forward(ctx, dims, acts, B):
     rng = np.random.default_rng(B + dims[0])
     ref = o.MLP(dims, acts, rng)

@@ -100,3 +100,35 @@ def test_bench_reference_arm_contract():
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "higher_is_better", "cpu_baseline", "e2e", "config"):
         assert k in rec
     assert rec["impl"] == "reference" and rec["value"] > 0 and rec["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_native_host_linquad(crux):
+    """C++ host env (csrc/host/linquad_host.cpp): the LinQuad specification with Philox noise, multi-threaded."""
+    from oracle import crux_oracle as o
+    spec = o.LinQuadSpec(17, 6, 0)
+    n = 1000
+    env = crux.NativeHostLinQuad(n, seed=9, n_threads=4)
+    env1 = crux.NativeHostLinQuad(n, seed=9, n_threads=1)
+    s0 = env.reset()
+    assert np.array_equal(s0, env1.reset())               # thread count does not change the streams
+    assert np.all(np.abs(s0) <= 0.1) and s0.std() > 0.04
+    rng = np.random.default_rng(0)
+    s = s0
+    for t in range(5):
+        a = rng.standard_normal((n, 6)).astype(np.float32)
+        sp, r, done = env.step(a)
+        sp1, r1, d1 = env1.step(a)
+        assert np.array_equal(sp, sp1) and np.array_equal(r, r1) and np.array_equal(done, d1)
+        mean = s @ spec.A.T + np.tanh(a) @ spec.B.T
+        xi = (sp - mean) / 0.01
+        assert abs(xi.mean()) < 0.03 and abs(xi.std() - 1) < 0.03
+        want_r = 1 - (sp * sp).sum(1) / 17 - 0.1 * (a * a).sum(1) / 6
+        assert np.allclose(r, want_r, atol=1e-5) and np.array_equal(done, np.abs(sp[:, 0]) > 5)
+        s = sp
+    idx = np.array([3, 500, 999], np.int32)
+    o3 = env.reset(idx)
+    assert o3.shape == (3, 17) and np.all(np.abs(o3) <= 0.1)
+    a = np.zeros((n, 6), np.float32)
+    sp, _, _ = env.step(a)
+    # reset streams restart from their new initial state; the others continue from sp
+    assert np.allclose(sp[3], o3[0] @ spec.A.T, atol=0.06) and np.allclose(sp[7], s[7] @ spec.A.T, atol=0.06)
