@@ -38,43 +38,44 @@ gae_returns_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done
   const int64_t e = (int64_t)tile * 32 + lane;
   const bool live = e < N;
   const int64_t c_lo = (int64_t)chunk * chunk_len;
-  const int64_t c_hi = min(T, c_lo + (int64_t)chunk_len);
-  const int64_t t0 = c_lo + (int64_t)w * L;  // this thread's steps: [t0, t0+L) clipped to c_hi
+  const int steps = (int)min((int64_t)chunk_len, T - c_lo);   // steps of this chunk
+  const int s0 = w * L;                                       // this thread's steps: [s0, s0+L) clipped to `steps`
   const float c = lambda * gamma;
+  // 64-bit base once, 32-bit offsets per step (chunk_len * N < 2^31 is checked on the host)
+  const int64_t base = c_lo * N + (live ? e : N - 1);
+  const float *rp = r + base, *vsb = vs + base, *vspb = vsp + base;
+  const uint8_t *dnb = done + base, *eeb = ee + base;
+  const unsigned int Nu = (unsigned int)N;
 
-  // Issue ALL loads of this thread's L steps back to back (straight-line, no control dependence: out-of-range steps
-  // and lanes are clamped onto valid rows and masked afterwards), so every warp keeps 5*L cache lines in flight.
+  // Issue ALL loads of this thread's L steps back to back (predicated, no control dependence), so every warp keeps 5*L
+  // cache lines in flight.
   float dl[L], rr[L];
-  unsigned int cut = 0;  // bit i: episode_end at step t0+i
+  unsigned int cut = 0;  // bit i: episode_end at step s0+i
   {
-    const int64_t ec = live ? e : N - 1;
     float va[L], vb[L];
-    unsigned char dn[L], en[L];
+    unsigned int dn[L], en[L];
 #pragma unroll
     for (int i = 0; i < L; ++i) {
-      const int64_t tt = min(t0 + i, c_hi - 1);
-      const int64_t j = tt * N + ec;
-      rr[i] = __ldcs(r + j);
-      va[i] = __ldcs(vs + j);
-      vb[i] = __ldcs(vsp + j);
-      dn[i] = __ldcs(done + j);
-      en[i] = __ldcs(ee + j);
+      const bool valid = live && (s0 + i < steps);
+      const unsigned int off = (unsigned int)(s0 + i) * Nu;
+      rr[i] = valid ? __ldcs(rp + off) : 0.f;
+      va[i] = valid ? __ldcs(vsb + off) : 0.f;
+      vb[i] = valid ? __ldcs(vspb + off) : 0.f;
+      dn[i] = valid ? (unsigned int)__ldcs(dnb + off) : 0u;
+      en[i] = valid ? (unsigned int)__ldcs(eeb + off) : 1u;   // padded steps behave like cuts with zero payload
     }
 #pragma unroll
     for (int i = 0; i < L; ++i) {
-      const bool valid = live && (t0 + i < c_hi);
-      const float nd = (1.0f - (float)dn[i]) * gamma;
-      if (valid && en[i]) cut |= 1u << i;
-      dl[i] = valid ? (rr[i] + nd * vb[i]) - va[i] : 0.f;
-      rr[i] = valid ? rr[i] : 0.f;
+      const float nd = dn[i] ? 0.f : gamma;                   // (1 - done) * gamma
+      if (en[i]) cut |= 1u << i;
+      dl[i] = (rr[i] + nd * vb[i]) - va[i];
     }
   }
-  // local aggregate of this thread's L steps (identity for padded steps)
+  // local aggregate of this thread's L steps.  Padded steps (beyond `steps`) must be the identity, not a cut:
   Agg g = {1.f, 0.f, 1.f, 0.f};
 #pragma unroll
   for (int i = L - 1; i >= 0; --i) {
-    const int64_t t = t0 + i;
-    if (t < c_hi) {
+    if (s0 + i < steps) {
       const bool k = (cut >> i) & 1u;
       const float ca = k ? 0.f : c, cg = k ? 0.f : gamma;
       g.la = fmaf(ca, g.la, dl[i]); g.pa *= ca;
@@ -82,11 +83,13 @@ gae_returns_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done
     }
   }
   __shared__ float4 s_agg[16][32];
+  __shared__ float2 s_carry[16][32];
+  __shared__ float4 s_look[64][32];
   s_agg[w][lane] = make_float4(g.pa, g.la, g.pr, g.lr);
   __syncthreads();
 
-  // chunk aggregate (composition over the W warps, latest first) -> global, for earlier chunks
-  if (n_chunks > 1 && chunk > 0 && w == 0) {
+  // warp 0 publishes this chunk's aggregate for the earlier chunks BEFORE anybody waits on later chunks
+  if (w == 0 && n_chunks > 1 && chunk > 0) {
     Agg q = {1.f, 0.f, 1.f, 0.f};
     for (int ww = W - 1; ww >= 0; --ww) {
       const float4 x = s_agg[ww][lane];
@@ -98,49 +101,51 @@ gae_returns_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done
     __syncwarp();
     if (lane == 0) atomicExch(flag_g + (int64_t)tile * n_chunks + chunk, 1u);
   }
-
-  // carry into the END of this chunk: compose the aggregates of all later chunks (look-back).
-  // Parallel fetch: warp ww handles later chunks chunk+1+ww, chunk+1+ww+W, ... -> shared memory.
-  float Ain = 0.f, Rin = 0.f;
+  // parallel look-back fetch: warp ww handles later chunks chunk+1+ww, chunk+1+ww+W, ... -> shared memory
   const int n_later = n_chunks - 1 - chunk;
-  if (n_later > 0) {
-    __shared__ float4 s_look[64][32];
-    for (int q = w; q < n_later; q += W) {
-      const int k = chunk + 1 + q;
-      if (lane == 0) {
-        const volatile unsigned int *f = flag_g + (int64_t)tile * n_chunks + k;
-        while (*f == 0u) { __nanosleep(32); }
-      }
-      __syncwarp();
-      __threadfence();
-      s_look[q][lane] = __ldcg(agg_g + ((int64_t)tile * n_chunks + k) * 32 + lane);
+  for (int q = w; q < n_later; q += W) {
+    const int k = chunk + 1 + q;
+    if (lane == 0) {
+      const volatile unsigned int *f = flag_g + (int64_t)tile * n_chunks + k;
+      while (*f == 0u) { __nanosleep(32); }
     }
-    __syncthreads();
+    __syncwarp();
+    __threadfence();
+    s_look[q][lane] = __ldcg(agg_g + ((int64_t)tile * n_chunks + k) * 32 + lane);
+  }
+  __syncthreads();
+
+  // warp 0: compose the carry into the END of this chunk from the later chunks, then walk the warps of this CTA from the
+  // latest to the earliest, leaving each warp's incoming carry in shared memory.
+  if (w == 0) {
+    float Ain = 0.f, Rin = 0.f;
     for (int q = n_later - 1; q >= 0; --q) {  // latest chunk first
       const float4 x = s_look[q][lane];
       Ain = fmaf(x.x, Ain, x.y);
       Rin = fmaf(x.z, Rin, x.w);
     }
+    for (int ww = W - 1; ww >= 0; --ww) {
+      s_carry[ww][lane] = make_float2(Ain, Rin);
+      const float4 x = s_agg[ww][lane];
+      Ain = fmaf(x.x, Ain, x.y);
+      Rin = fmaf(x.z, Rin, x.w);
+    }
   }
-  // ... then the later warps of this CTA
-  for (int ww = W - 1; ww > w; --ww) {
-    const float4 x = s_agg[ww][lane];
-    Ain = fmaf(x.x, Ain, x.y);
-    Rin = fmaf(x.z, Rin, x.w);
-  }
+  __syncthreads();
   // final pass over the registers with the true carry
-  float A = Ain, R = Rin;
+  const float2 cin = s_carry[w][lane];
+  float A = cin.x, R = cin.y;
   bool bad = false;
+  float *ap = adv ? adv + base : nullptr, *rtp = ret ? ret + base : nullptr;
 #pragma unroll
   for (int i = L - 1; i >= 0; --i) {
-    const int64_t t = t0 + i;
-    if (live && t < c_hi) {
+    if (live && s0 + i < steps) {
       const bool k = (cut >> i) & 1u;
       A = fmaf(k ? 0.f : c, A, dl[i]);
       R = fmaf(k ? 0.f : gamma, R, rr[i]);
-      const int64_t j = t * N + e;
-      if (adv) __stcs(adv + j, A);
-      if (ret) __stcs(ret + j, R);
+      const unsigned int off = (unsigned int)(s0 + i) * Nu;
+      if (ap) __stcs(ap + off, A);
+      if (rtp) __stcs(rtp + off, R);
       bad |= isnan(A);
     }
   }
@@ -243,6 +248,7 @@ int32_t crux_fill_gae_returns(crux_ctx *ctx, const float *r, const uint8_t *done
   int chunk_len = L * W;
   int n_chunks = (int)cdiv(T, chunk_len);
   CRUX_REQUIRE(ctx, n_chunks <= 65, "crux_fill_gae_returns: T > 8320 steps per rollout is not supported");
+  CRUX_REQUIRE(ctx, (int64_t)chunk_len * N < (1ll << 31), "crux_fill_gae_returns: N too large for 32-bit in-chunk offsets");
   CRUX_REQUIRE(ctx, tiles * n_chunks < (1ll << 31), "crux_fill_gae_returns: grid too large");
   float4 *agg = nullptr;
   unsigned int *flags = nullptr;

@@ -6,7 +6,9 @@
 //
 // Besides NCCL there is a one-shot peer all-reduce for the latency-bound 44 KB gradient: every rank stores
 // its vector into a slot of every peer's receive buffer over NVLink (CUDA IPC mapped pointers), bumps a
-// sequence flag, then each rank sums the slots in rank order (bit-identical on all ranks).
+// sequence flag, then each rank sums the slots in rank order (bit-identical on all ranks).  Receive slots and flags are
+// double-buffered by the parity of the sequence number: rank A can only start all-reduce N+2 after every peer pushed N+1,
+// which a peer does (stream order) only after its reduce of N has finished reading the buffer of parity N%2.
 #include "common.cuh"
 #include <dlfcn.h>
 
@@ -53,8 +55,9 @@ struct PeerPtrs { float *recv[16]; unsigned long long *flag[16]; };
 // each block pushes a slice of `src` into slot `rank` of every peer, then (last block) publishes the sequence number
 __global__ void peer_push_kernel(const float *__restrict__ src, int64_t n, PeerPtrs peers, int rank, int world, int64_t cap,
                                  unsigned long long seq, unsigned long long *__restrict__ done_ctr) {
+  const int par = (int)(seq & 1ULL);
   for (int p = 0; p < world; ++p) {
-    float *dst = peers.recv[p] + (int64_t)rank * cap;
+    float *dst = peers.recv[p] + ((int64_t)par * 16 + rank) * cap;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
   }
   __threadfence_system();
@@ -66,7 +69,7 @@ __global__ void peer_push_kernel(const float *__restrict__ src, int64_t n, PeerP
     *done_ctr = 0ULL;
     __threadfence_system();
     for (int p = 0; p < world; ++p) {
-      volatile unsigned long long *f = peers.flag[p] + rank;
+      volatile unsigned long long *f = peers.flag[p] + par * 16 + rank;
       *f = seq;
     }
     __threadfence_system();
@@ -74,11 +77,13 @@ __global__ void peer_push_kernel(const float *__restrict__ src, int64_t n, PeerP
 }
 __global__ void peer_reduce_kernel(float *__restrict__ dst, int64_t n, const float *__restrict__ recv, volatile unsigned long long *flags,
                                    int world, int64_t cap, unsigned long long seq) {
+  const int par = (int)(seq & 1ULL);
   if (threadIdx.x < world) {
-    while (flags[threadIdx.x] < seq) { __nanosleep(100); }
+    while (flags[par * 16 + threadIdx.x] < seq) { __nanosleep(100); }
   }
   __syncthreads();
   __threadfence_system();
+  recv += (int64_t)par * 16 * cap;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int p = 0; p < world; ++p) s += __ldcv(recv + (int64_t)p * cap + i);
@@ -134,11 +139,11 @@ int32_t crux_peer_handle(crux_ctx *ctx, uint8_t *handle_out_host, int64_t max_fl
   CRUX_REQUIRE(ctx, ctx->world >= 1 && ctx->world <= 16, "crux_peer_handle: world must be set by crux_nccl_init (<= 16 ranks)");
   if (!ctx->peer_recv) {
     ctx->peer_cap = (max_floats + 31) / 32 * 32;
-    // one allocation: [world][cap] floats, then [16] flags + [1] block counter
-    const size_t bytes = (size_t)16 * ctx->peer_cap * sizeof(float) + 32 * sizeof(unsigned long long);
+    // one allocation: [2 parities][16 ranks][cap] floats, then [2][16] flags + [1] block counter
+    const size_t bytes = (size_t)32 * ctx->peer_cap * sizeof(float) + 64 * sizeof(unsigned long long);
     CRUX_CHECK_CUDA(ctx, cudaMalloc((void **)&ctx->peer_recv, bytes));
     CRUX_CHECK_CUDA(ctx, cudaMemset(ctx->peer_recv, 0, bytes));
-    ctx->peer_flags = (unsigned long long *)((char *)ctx->peer_recv + (size_t)16 * ctx->peer_cap * sizeof(float));
+    ctx->peer_flags = (unsigned long long *)((char *)ctx->peer_recv + (size_t)32 * ctx->peer_cap * sizeof(float));
   }
   cudaIpcMemHandle_t h;
   CRUX_CHECK_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->peer_recv));
@@ -163,7 +168,7 @@ int32_t crux_peer_init(crux_ctx *ctx, int32_t rank, int32_t world, const uint8_t
       if (e != cudaSuccess) return crux_set_err(ctx, CRUX_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e));
       ctx->peer_recv_remote[p] = (float *)ptr;
     }
-    ctx->peer_flags_remote[p] = (unsigned long long *)((char *)ctx->peer_recv_remote[p] + (size_t)16 * ctx->peer_cap * sizeof(float));
+    ctx->peer_flags_remote[p] = (unsigned long long *)((char *)ctx->peer_recv_remote[p] + (size_t)32 * ctx->peer_cap * sizeof(float));
   }
   ctx->peer_seq = 0;
   ctx->peer_ready = true;
@@ -176,7 +181,7 @@ int32_t crux_peer_allreduce(crux_ctx *ctx, float *buf, int64_t n) {
   for (int p = 0; p < ctx->world; ++p) { pp.recv[p] = ctx->peer_recv_remote[p]; pp.flag[p] = ctx->peer_flags_remote[p]; }
   const unsigned long long seq = ++ctx->peer_seq;
   const int blocks = (int)i64max(1, i64min(cdiv(n, 1024), 16));
-  peer_push_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, n, pp, ctx->rank, ctx->world, ctx->peer_cap, seq, ctx->peer_flags + 16);
+  peer_push_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, n, pp, ctx->rank, ctx->world, ctx->peer_cap, seq, ctx->peer_flags + 32);
   CRUX_LAUNCHED(ctx);
   peer_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, n, ctx->peer_recv, ctx->peer_flags, ctx->world, ctx->peer_cap, seq);
   CRUX_LAUNCHED(ctx);

@@ -117,12 +117,7 @@ class Context:
     def init_distributed(self, rank, world, peer_floats=0):
         """One rank per GPU.  The NCCL unique id travels through torch.distributed (any backend)."""
         import torch.distributed as dist
-        buf = (C.c_uint8 * 128)()
-        if rank == 0:
-            _abi.check(self.lib.crux_nccl_unique_id(buf))
-        obj = [bytes(buf)]
-        dist.broadcast_object_list(obj, src=0)
-        idb = (C.c_uint8 * 128).from_buffer_copy(obj[0])
+        idb = (C.c_uint8 * 128).from_buffer_copy(exchange_unique_id(rank))
         self.check(self.lib.crux_nccl_init(self.h, rank, world, idb))
         self.rank, self.world = rank, world
         if peer_floats > 0:
@@ -140,6 +135,23 @@ class Context:
                 self.h = None
         except Exception:
             pass
+
+
+def exchange_unique_id(rank):
+    """Rank 0 creates the NCCL unique id (``crux_nccl_unique_id``), every rank receives the same 128 bytes through the
+    already-initialised ``torch.distributed`` group (gloo or nccl)."""
+    import torch.distributed as dist
+    buf = (C.c_uint8 * 128)()
+    if rank == 0:
+        _abi.check(_abi.load().crux_nccl_unique_id(buf))
+    obj = [bytes(buf)]
+    dist.broadcast_object_list(obj, src=0)
+    return obj[0]
+
+
+def shard_seed(base_seed, rank):
+    """Env-shard seed of a rank: shards must draw different noise streams, parameters must start identical."""
+    return int(base_seed) + 1000003 * int(rank)
 
 
 _default = None

@@ -1,0 +1,134 @@
+"""Multi-GPU parity check, launched with torchrun (one rank per GPU):
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/multigpu_check.py
+Checks: NCCL + one-shot peer all-reduce, data-parallel PPO update == the oracle on the union batch, global whitening."""
+import ctypes as C
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import crux_b200 as crux  # noqa: E402
+from crux_b200.device import ptr  # noqa: E402
+from oracle import crux_oracle as o  # noqa: E402
+
+F32 = np.float32
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = crux.Context(local)
+    ctx.init_distributed(rank, world)
+    dev = lambda x, dt=None: ctx.to_device(x, dt)
+
+    def allreduce_check(tag, iters):
+        for it in range(iters):
+            n = 11085 + 128
+            x = np.random.default_rng(100 * it + rank).standard_normal(n).astype(F32)
+            t = dev(x)
+            ctx.check(ctx.lib.crux_nccl_allreduce_f32(ctx.h, ptr(t), n))
+            want = sum(np.random.default_rng(100 * it + r).standard_normal(n).astype(np.float64) for r in range(world))
+            got = t.cpu().numpy()
+            assert np.allclose(got, want, rtol=1e-5, atol=1e-5), f"{tag} all-reduce mismatch at iteration {it}"
+            gl = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(gl, t)
+            assert all(torch.equal(gl[0], g) for g in gl), f"{tag}: ranks disagree bitwise"
+
+    allreduce_check("nccl", 5)
+
+    # ---- data-parallel PPO update vs the oracle on the union batch
+    n_loc, ab, epochs = 512, 128, 2
+    rng = np.random.default_rng(0)
+    mu = o.MLP([17, 64, 64, 6], [1, 1, 0], rng)
+    cr = o.MLP([17, 64, 64, 1], [1, 1, 0], rng)
+    ls = np.full(6, -0.5, F32)
+    pi = o.GaussianPolicy(mu, ls)
+    n = n_loc * world
+    s = rng.standard_normal((n, 17)).astype(F32)
+    old = o.GaussianPolicy(o.MLP(mu.dims, mu.acts, Ws=[w.detach().numpy() * F32(0.97) for w in mu.W], bs=[b.detach().numpy() for b in mu.b]), ls - F32(0.05))
+    a, lp = old.exploration(s, rng.standard_normal((n, 6)).astype(F32))
+    D = {"s": s, "a": a.detach().numpy(), "logprob": lp.detach().numpy()[:, 0], "advantage": rng.standard_normal(n).astype(F32),
+         "return": rng.standard_normal(n).astype(F32)}
+    orders_a = [[rng.permutation(n_loc) for _ in range(epochs)] for _ in range(world)]
+    orders_c = [[rng.permutation(n_loc) for _ in range(epochs)] for _ in range(world)]
+    # oracle: global minibatch k of epoch e = union over ranks of rank-local rows order[r][e][k*ab:(k+1)*ab] (offset r*n_loc)
+    P = {"eps": F32(0.2), "lp": F32(1.0), "le": F32(0.1)}
+    opt_a, opt_c = o.Adam(F32(3e-4)), o.Adam(F32(3e-4))
+    for e in range(epochs):
+        for k in range(n_loc // ab):
+            idx = np.concatenate([r * n_loc + orders_a[r][e][k * ab:(k + 1) * ab] for r in range(world)])
+            mb = {kk: v[idx] for kk, v in D.items()}
+            o.train_step(pi.params(), lambda inf, mb=mb: o.ppo_loss(pi, P, mb, inf), opt_a, {})
+    for e in range(epochs):
+        for k in range(n_loc // ab):
+            idx = np.concatenate([r * n_loc + orders_c[r][e][k * ab:(k + 1) * ab] for r in range(world)])
+            mb = {kk: v[idx] for kk, v in D.items()}
+            o.train_step(cr.params(), lambda inf, mb=mb: o.value_mse_loss(cr, mb), opt_c, {})
+    # device: every rank starts from the same parameters and sees only its shard
+    rng0 = np.random.default_rng(0)
+    mu0 = o.MLP([17, 64, 64, 6], [1, 1, 0], rng0); cr0 = o.MLP([17, 64, 64, 1], [1, 1, 0], rng0)
+
+    def net(m):
+        return crux.ContinuousNetwork(crux.Chain(*[crux.Dense(m.dims[l], m.dims[l + 1], m.acts[l], m.W[l].detach().numpy(), m.b[l].detach().numpy())
+                                                   for l in range(3)]), ctx=ctx)
+    pol = crux.ActorCritic(crux.GaussianPolicy(net(mu0), ls), net(cr0))
+    pol.A.mu.mlp.set_adam(F32(3e-4)); pol.C.mlp.set_adam(F32(3e-4))
+    sh = slice(rank * n_loc, (rank + 1) * n_loc)
+    d = {k: dev(v[sh]) for k, v in D.items()}
+    hp = crux._abi.PPOHp(eps_clip=0.2, lambda_p=1.0, lambda_e=0.1, target_kl=math.inf, a2c=0, actor_epochs=epochs, actor_batch=ab,
+                         critic_epochs=epochs, critic_batch=ab, actor_max_batches=0, critic_max_batches=0)
+    oa = dev(np.stack(orders_a[rank]).astype(np.int32), torch.int32)
+    oc = dev(np.stack(orders_c[rank]).astype(np.int32), torch.int32)
+    ia = np.zeros((epochs * (n_loc // ab), 8), F32); ic = np.zeros_like(ia)
+    ctx.check(ctx.lib.crux_ppo_update(pol.A.h, pol.C.mlp.h, ptr(d["s"]), ptr(d["a"]), ptr(d["logprob"]), ptr(d["advantage"]), ptr(d["return"]),
+                                      n_loc, C.byref(hp), ptr(oa), ptr(oc), 0, ptr(ia), ptr(ic)))
+    for name, got, want in (("actor", pol.A.mu.mlp.get_flat(), mu.flat()), ("critic", pol.C.mlp.get_flat(), cr.flat())):
+        err = np.abs(got - want)
+        assert err.max() < 2 * 3e-4 * 8 + 2e-6, f"{name}: {err.max()}"
+        assert (err > 2e-6 + 1e-5 * np.abs(want)).mean() < 2e-3, f"{name}: {(err > 2e-6 + 1e-5 * np.abs(want)).sum()} coordinates off"
+        t = dev(got); gl = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gl, t)
+        assert all(torch.equal(gl[0], g) for g in gl), f"{name}: replicas diverged"
+
+    # ---- global whitening: every rank whitens its shard with the all-reduced moments
+    x = np.random.default_rng(5).standard_normal(4000).astype(F32) * 3 + 1
+    t = dev(x[rank::world].copy())
+    ctx.check(ctx.lib.crux_whiten(ctx.h, ptr(t), t.numel()))
+    assert np.allclose(t.cpu().numpy(), o.whiten(x)[rank::world], rtol=1e-4, atol=1e-5), "whiten"
+
+    # ---- one-shot peer all-reduce over NVLink (CUDA IPC), many back-to-back calls (double-buffer race check)
+    ctx.init_distributed(rank, world, peer_floats=16384) if False else None
+    hb = (C.c_uint8 * 64)()
+    ctx.check(ctx.lib.crux_peer_handle(ctx.h, hb, 16384))
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(hb))
+    allh = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+    dist.barrier()
+    ctx.check(ctx.lib.crux_peer_init(ctx.h, rank, world, allh))
+    dist.barrier()
+    allreduce_check("peer", 50)
+    # timing of the two paths for the 44 KB gradient payload
+    for tag in ("peer",):
+        t = dev(np.ones(11213, F32))
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); dist.barrier(); a_.record()
+        for _ in range(200):
+            ctx.check(ctx.lib.crux_nccl_allreduce_f32(ctx.h, ptr(t), 11213))
+        b_.record(); torch.cuda.synchronize()
+        if rank == 0:
+            print(f"{tag} all-reduce of 11213 floats: {a_.elapsed_time(b_) / 200 * 1e3:.1f} us per call")
+    dist.barrier()
+    if rank == 0:
+        print("MULTIGPU OK", world, "ranks")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
