@@ -96,6 +96,9 @@ def build_solver(crux, ctx, seed=1):
 
 
 def run_ours(args):
+    # stdout carries exactly ONE line (the JSON record): library chatter (e.g. NCCL's version banner) goes to stderr
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import crux_b200 as crux
@@ -162,7 +165,7 @@ def run_ours(args):
 
     # ---------------- e2e leg: host env through the public API --------------------------------------
     S2 = build_solver(crux, ctx, seed=2)
-    henv = crux.NativeHostLinQuad(N_ENVS, OBS, ACT, seed=2000 + rank)
+    henv = crux.NativeHostLinQuad(N_ENVS, OBS, ACT, seed=2000 + rank, n_threads=max(1, cpu_threads() // world))
     S2.N = dN
     for _ in range(max(1, args.warmup // 2)):
         crux.solve(S2, henv)
@@ -200,7 +203,9 @@ def run_ours(args):
                "phases_ms": phases["phases_ms"] if phases else None,
                "cpu_baseline": cpu,
                "last_info": {k: (round(v, 6) if isinstance(v, float) else v) for k, v in info.items()}}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -281,6 +286,8 @@ def cpu_run(steps, warmup, n_envs=N_ENVS):
     if os.environ.get("CRUX_BENCH_TINY"):  # contract test only (tests/test_host_logic.py)
         n_envs = 64
     """The reference algorithm restated on the CPU (oracle/ppo_cpu.py), vectorised over env streams, all host threads."""
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):  # torchrun pins these to 1; the CPU arm uses every host core
+        os.environ[k] = str(cpu_threads())
     import torch
     from oracle.ppo_cpu import OraclePPO
     torch.set_num_threads(cpu_threads())

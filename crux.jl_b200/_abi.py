@@ -37,6 +37,11 @@ class PPOHp(C.Structure):
                 ("actor_max_batches", C.c_int64), ("critic_max_batches", C.c_int64)]
 
 
+class RolloutCols(C.Structure):
+    _fields_ = [("s", C.c_void_p), ("a", C.c_void_p), ("sp", C.c_void_p), ("r", C.c_void_p), ("done", C.c_void_p),
+                ("episode_end", C.c_void_p), ("logprob", C.c_void_p)]
+
+
 class ColDesc(C.Structure):
     _fields_ = [("id", C.c_int32), ("dtype", C.c_int32), ("rowlen", C.c_int64), ("init", C.c_double)]
 
@@ -93,6 +98,7 @@ _SIGS = {
     "crux_discrete_entropy": [_vp, _vp, _i64, _i32, _vp],
     "crux_discrete_eps_greedy": [_vp, _vp, _i64, _i32, _f64, _vp, _u64, _u64, _vp, _vp, _vp],
     "crux_rollout_step": [_vp, _vp, _vp, _i64, _vp, _u64, _u64, _vp, _vp, _vp],
+    "crux_rollout_host": [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(RolloutCols), _u64, _u64],
     "crux_normalize_obs": [_vp, _vp, _i64, _f32, _f32, _vp],
     "crux_fill_gae_returns": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _vp, _vp],
     "crux_whiten": [_vp, _vp, _i64],

@@ -32,9 +32,8 @@ gae_returns_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done
                    float4 *__restrict__ agg_g, unsigned int *__restrict__ flag_g,
                    unsigned int *__restrict__ err_flags) {
   const int lane = threadIdx.x, w = threadIdx.y, W = blockDim.y;
-  const int n_tiles = gridDim.x / n_chunks;
-  const int chunk = n_chunks - 1 - (int)(blockIdx.x / n_tiles);  // chunk-major, later chunks first
-  const int tile = blockIdx.x % n_tiles;
+  const int chunk = n_chunks - 1 - (int)blockIdx.y;  // grid (tiles, chunks): chunk-major dispatch, later chunks first
+  const int tile = blockIdx.x;
   const int64_t e = (int64_t)tile * 32 + lane;
   const bool live = e < N;
   const int64_t c_lo = (int64_t)chunk * chunk_len;
@@ -47,8 +46,8 @@ gae_returns_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done
   const uint8_t *dnb = done + base, *eeb = ee + base;
   const unsigned int Nu = (unsigned int)N;
 
-  // Issue ALL loads of this thread's L steps back to back (predicated, no control dependence), so every warp keeps 5*L
-  // cache lines in flight.
+  // Issue ALL loads of this thread's L steps back to back (no control dependence), so every warp keeps 5*L cache lines
+  // in flight.  Out-of-range steps / lanes read a clamped valid address and are masked when they are used.
   float dl[L], rr[L];
   unsigned int cut = 0;  // bit i: episode_end at step s0+i
   {
@@ -56,13 +55,13 @@ gae_returns_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done
     unsigned int dn[L], en[L];
 #pragma unroll
     for (int i = 0; i < L; ++i) {
-      const bool valid = live && (s0 + i < steps);
-      const unsigned int off = (unsigned int)(s0 + i) * Nu;
-      rr[i] = valid ? __ldcs(rp + off) : 0.f;
-      va[i] = valid ? __ldcs(vsb + off) : 0.f;
-      vb[i] = valid ? __ldcs(vspb + off) : 0.f;
-      dn[i] = valid ? (unsigned int)__ldcs(dnb + off) : 0u;
-      en[i] = valid ? (unsigned int)__ldcs(eeb + off) : 1u;   // padded steps behave like cuts with zero payload
+      // unconditional loads from clamped (always valid) addresses: plain address arithmetic + LDG, nothing to branch on
+      const unsigned int off = (unsigned int)min(s0 + i, steps - 1) * Nu;
+      rr[i] = __ldcs(rp + off);
+      va[i] = __ldcs(vsb + off);
+      vb[i] = __ldcs(vspb + off);
+      dn[i] = (unsigned int)__ldcs(dnb + off);
+      en[i] = (unsigned int)__ldcs(eeb + off);
     }
 #pragma unroll
     for (int i = 0; i < L; ++i) {
@@ -261,7 +260,7 @@ int32_t crux_fill_gae_returns(crux_ctx *ctx, const float *r, const uint8_t *done
     flags = (unsigned int *)(p + agg_bytes);
     CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(flags, 0, flag_bytes, ctx->stream));
   }
-  dim3 block(32, W), grid((unsigned)(tiles * n_chunks));
+  dim3 block(32, W), grid((unsigned)tiles, (unsigned)n_chunks);
 #define GAE_LAUNCH(LL)                                                                                   \
   gae_returns_kernel<LL><<<grid, block, 0, ctx->stream>>>(r, done, episode_end, v_s, v_sp, T, N, gamma,  \
                                                           lambda, adv, ret, n_chunks, chunk_len, agg,    \

@@ -26,8 +26,8 @@
 namespace {
 
 constexpr int H = 64;        // hidden width
-constexpr int R = 64;        // rows per tile
-constexpr int LD = R + 4;    // row stride of transposed tiles (floats); keeps 128-bit alignment
+constexpr int R = 64;        // rows per tile (2 CTAs per SM); RB = 128-row tiles (1 CTA per SM, 8x4 register tiles) for big batches
+constexpr int RB = 128;
 constexpr int NT = 256;      // threads per CTA
 constexpr int MAX_I = 32, MAX_O = 8;
 constexpr int P_MAX = MAX_I * H + H + H * H + H + H * MAX_O + MAX_O;  // 6792 floats
@@ -43,8 +43,10 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float act_fused(int act, float z) { return act == CRUX_ACT_TANH ? tanh_fast(z) : fmaxf(z, 0.0f); }
 
-// ---- shared memory carve-up (floats) ----------------------------------------------------------------------------------------
-struct SmemMap {
+// ---- shared memory carve-up (floats), per tile height RT; row stride LD = RT + 4 keeps 128-bit alignment ----------------------
+template <int RT>
+struct SmemMapT {
+  static constexpr int LD = RT + 4;
   static constexpr int P = 0;                       // raw params
   static constexpr int W2T = P + P_SMEM;            // [64][64]  W2T[j][k] = W2[k][j]
   static constexpr int W3T = W2T + H * H;           // [8][64]   W3T[o][k] = W3[k][o]
@@ -56,14 +58,16 @@ struct SmemMap {
   static constexpr int LP = AT + MAX_O * LD;        // [LD] old logprob
   static constexpr int ADV = LP + LD;               // [LD]
   static constexpr int RET = ADV + LD;              // [LD]
-  static constexpr int IDX = RET + LD;              // [R] ints
-  static constexpr int RED = IDX + R;               // [8][24] reduction scratch
+  static constexpr int IDX = RET + LD;              // [RT] ints
+  static constexpr int RED = IDX + RT;              // [8][24] reduction scratch
   static constexpr int MBAR = RED + 8 * 24;         // 2 floats = one 64-bit mbarrier (8-byte aligned: all offsets are even)
   static constexpr int TOTAL = MBAR + 2;
+  static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
+  static_assert(MBAR % 2 == 0, "mbarrier must be 8-byte aligned");
+  static_assert(W2T % 4 == 0 && XT % 4 == 0 && H1T % 4 == 0 && OT % 4 == 0 && AT % 4 == 0, "16-byte alignment");
 };
-static_assert(SmemMap::MBAR % 2 == 0, "mbarrier must be 8-byte aligned");
-static_assert(SmemMap::W2T % 4 == 0 && SmemMap::XT % 4 == 0 && SmemMap::H1T % 4 == 0 && SmemMap::OT % 4 == 0, "16-byte alignment");
-constexpr size_t SMEM_BYTES = (size_t)SmemMap::TOTAL * sizeof(float);
+using SmemMap = SmemMapT<R>;   // offsets that do not depend on the tile height (P, W2T, W3T) are shared by all variants
+constexpr size_t SMEM_BYTES = SmemMapT<R>::BYTES;
 
 struct NetDesc {
   const float *params;  // device, flat
@@ -79,8 +83,8 @@ __device__ __forceinline__ int off_b3(int I, int O) { return I * H + H + H * H +
 // ---- TMA bulk copy of the parameter vector into shared memory ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void stage_params(float *sm, const NetDesc &nd) {
-  const uint32_t mbar = smem_u32(sm + SmemMap::MBAR);
+__device__ __forceinline__ void stage_params(float *sm, const NetDesc &nd, int mbar_off) {
+  const uint32_t mbar = smem_u32(sm + mbar_off);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(1) : "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -121,93 +125,126 @@ __device__ __forceinline__ void build_transposes(float *sm, int I, int O) {
 }
 
 // ---- register-tiled GEMM pieces --------------------------------------------------------------------------------------------
-// C^T[j][r] = act(b[j] + sum_{k<K} A^T[k][r] W[k][j]);  thread = rows 4rg..4rg+3, cols 4jg..4jg+3
+// C^T[j][r] = act(b[j] + sum_{k<K} A^T[k][r] W[k][j]);  thread = rows PR*rg..PR*rg+PR-1, cols 4jg..4jg+3  (PR = RT/16: 4 or 8)
+template <int RT>
 __device__ __forceinline__ void layer_fwd(const float *__restrict__ AT, int K, const float *__restrict__ W, const float *__restrict__ b,
                                           float *__restrict__ CT, int act) {
+  constexpr int LD = RT + 4, PR = RT / 16, NV = PR / 4;
   const int rg = threadIdx.x >> 4, jg = threadIdx.x & 15;
-  float acc[4][4];
+  float acc[PR][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < PR; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const float *ap = AT + 4 * rg, *wp = W + 4 * jg;
-  float4 a = *reinterpret_cast<const float4 *>(ap), w = *reinterpret_cast<const float4 *>(wp);
+  const float *ap = AT + PR * rg, *wp = W + 4 * jg;
+  float4 a[NV], w = *reinterpret_cast<const float4 *>(wp);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) a[v] = *reinterpret_cast<const float4 *>(ap + 4 * v);
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
-    // operands of step k+1 are requested before the 16 FFMA of step k (the last prefetch re-reads row K-1: harmless)
+    // operands of step k+1 are requested before the FFMAs of step k (the last prefetch re-reads row K-1: harmless)
     const int kn = k + 1 < K ? k + 1 : k;
-    const float4 an = *reinterpret_cast<const float4 *>(ap + kn * LD);
+    float4 an[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) an[v] = *reinterpret_cast<const float4 *>(ap + kn * LD + 4 * v);
     const float4 wn = *reinterpret_cast<const float4 *>(wp + kn * H);
-    const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+    const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int v = 0; v < NV; ++v) {
+      const float av[4] = {a[v].x, a[v].y, a[v].z, a[v].w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
-    a = an; w = wn;
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[4 * v + i][j] = fmaf(av[i], wv[j], acc[4 * v + i][j]);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) a[v] = an[v];
+    w = wn;
   }
   const float4 bb = *reinterpret_cast<const float4 *>(b + 4 * jg);
   const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float4 v;
-    v.x = act_fused(act, acc[0][j] + bv[j]);
-    v.y = act_fused(act, acc[1][j] + bv[j]);
-    v.z = act_fused(act, acc[2][j] + bv[j]);
-    v.w = act_fused(act, acc[3][j] + bv[j]);
-    *reinterpret_cast<float4 *>(CT + (4 * jg + j) * LD + 4 * rg) = v;
-  }
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float4 o;
+      o.x = act_fused(act, acc[4 * v + 0][j] + bv[j]);
+      o.y = act_fused(act, acc[4 * v + 1][j] + bv[j]);
+      o.z = act_fused(act, acc[4 * v + 2][j] + bv[j]);
+      o.w = act_fused(act, acc[4 * v + 3][j] + bv[j]);
+      *reinterpret_cast<float4 *>(CT + (4 * jg + j) * LD + PR * rg + 4 * v) = o;
+    }
 }
 
-// out^T[o][r] = b3[o] + sum_k h2^T[k][r] W3[k][o];  thread = (row t&63, outputs og and og+4)
+// out^T[o][r] = b3[o] + sum_k h2^T[k][r] W3[k][o];  thread = (row t % RT, outputs og, og + G, ...), G = NT / RT groups
+template <int RT>
 __device__ __forceinline__ void layer_out(const float *__restrict__ H2T, const float *__restrict__ W3, const float *__restrict__ b3, int O,
                                           float *__restrict__ OT) {
-  const int r = threadIdx.x & 63, og = threadIdx.x >> 6;
-  const bool v0 = og < O, v1 = og + 4 < O;
-  if (!v0) return;
-  float a0 = b3[og], a1 = v1 ? b3[og + 4] : 0.f;
+  constexpr int LD = RT + 4, G = NT / RT, NO = (MAX_O + G - 1) / G;
+  const int r = threadIdx.x % RT, og = threadIdx.x / RT;
+  if (og >= O) return;
+  float acc[NO];
+#pragma unroll
+  for (int q = 0; q < NO; ++q) acc[q] = og + q * G < O ? b3[og + q * G] : 0.f;
 #pragma unroll 8
   for (int k = 0; k < H; ++k) {
     const float h = H2T[k * LD + r];
-    a0 = fmaf(h, W3[k * O + og], a0);
-    if (v1) a1 = fmaf(h, W3[k * O + og + 4], a1);
+#pragma unroll
+    for (int q = 0; q < NO; ++q)
+      if (og + q * G < O) acc[q] = fmaf(h, W3[k * O + og + q * G], acc[q]);
   }
-  OT[og * LD + r] = a0;
-  if (v1) OT[(og + 4) * LD + r] = a1;
+#pragma unroll
+  for (int q = 0; q < NO; ++q)
+    if (og + q * G < O) OT[(og + q * G) * LD + r] = acc[q];
 }
 
-// dA^T[k][r] = act'(A^T[k][r]) * sum_{j<J} dC^T[j][r] WT[j][k]   in place over A^T;  thread = rows 4rg.., cols 4kg..
+// dA^T[k][r] = act'(A^T[k][r]) * sum_{j<J} dC^T[j][r] WT[j][k]   in place over A^T;  thread = rows PR*rg.., cols 4kg..
+template <int RT>
 __device__ __forceinline__ void layer_bwd_data(const float *__restrict__ DCT, int J, const float *__restrict__ WT, float *__restrict__ AT, int act) {
+  constexpr int LD = RT + 4, PR = RT / 16, NV = PR / 4;
   const int rg = threadIdx.x >> 4, kg = threadIdx.x & 15;
-  float acc[4][4];
+  float acc[PR][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < PR; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const float *dp = DCT + 4 * rg, *wp = WT + 4 * kg;
-  float4 d = *reinterpret_cast<const float4 *>(dp), w = *reinterpret_cast<const float4 *>(wp);
+  const float *dp = DCT + PR * rg, *wp = WT + 4 * kg;
+  float4 d[NV], w = *reinterpret_cast<const float4 *>(wp);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) d[v] = *reinterpret_cast<const float4 *>(dp + 4 * v);
 #pragma unroll 4
   for (int j = 0; j < J; ++j) {
     const int jn = j + 1 < J ? j + 1 : j;
-    const float4 dn = *reinterpret_cast<const float4 *>(dp + jn * LD);
+    float4 dn[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) dn[v] = *reinterpret_cast<const float4 *>(dp + jn * LD + 4 * v);
     const float4 wn = *reinterpret_cast<const float4 *>(wp + jn * H);
-    const float dv[4] = {d.x, d.y, d.z, d.w}, wv[4] = {w.x, w.y, w.z, w.w};
+    const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int v = 0; v < NV; ++v) {
+      const float dv[4] = {d[v].x, d[v].y, d[v].z, d[v].w};
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(dv[i], wv[c], acc[i][c]);
-    d = dn; w = wn;
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[4 * v + i][c] = fmaf(dv[i], wv[c], acc[4 * v + i][c]);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) d[v] = dn[v];
+    w = wn;
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    float4 *p = reinterpret_cast<float4 *>(AT + (4 * kg + c) * LD + 4 * rg);
-    const float4 y = *p;
-    float4 v;
-    v.x = acc[0][c] * act_bwd_from_out(act, y.x);
-    v.y = acc[1][c] * act_bwd_from_out(act, y.y);
-    v.z = acc[2][c] * act_bwd_from_out(act, y.z);
-    v.w = acc[3][c] * act_bwd_from_out(act, y.w);
-    *p = v;
-  }
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float4 *p = reinterpret_cast<float4 *>(AT + (4 * kg + c) * LD + PR * rg + 4 * v);
+      const float4 y = *p;
+      float4 o;
+      o.x = acc[4 * v + 0][c] * act_bwd_from_out(act, y.x);
+      o.y = acc[4 * v + 1][c] * act_bwd_from_out(act, y.y);
+      o.z = acc[4 * v + 2][c] * act_bwd_from_out(act, y.z);
+      o.w = acc[4 * v + 3][c] * act_bwd_from_out(act, y.w);
+      *p = o;
+    }
 }
 
 __device__ __forceinline__ float dot4(const float4 &a, const float4 &b, float acc) {
@@ -217,8 +254,10 @@ __device__ __forceinline__ float dot4(const float4 &a, const float4 &b, float ac
 
 // ---- tile loads --------------------------------------------------------------------------------------------------------------
 // x^T[i][r] = x[row(r)][i]; rows beyond n are zero.  idx (shared) holds the source row or -1.
+template <int RT>
 __device__ __forceinline__ void load_rows_T(float *__restrict__ XT, const float *__restrict__ x, const int *__restrict__ sidx, int I) {
-  for (int e = threadIdx.x; e < R * I; e += NT) {
+  constexpr int LD = RT + 4;
+  for (int e = threadIdx.x; e < RT * I; e += NT) {
     const int r = e / I, i = e - r * I;
     const int row = sidx[r];
     XT[i * LD + r] = row >= 0 ? __ldg(x + (int64_t)row * I + i) : 0.f;
@@ -268,15 +307,17 @@ __device__ __forceinline__ void layer_out16(const float *__restrict__ H2T, const
 }
 
 template <int RT>
-__global__ void __launch_bounds__(NT, 2) fused_forward_kernel(FwdArgs a) {
-  constexpr int LDT = RT + 4;
+__global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_forward_kernel(FwdArgs a) {
+  constexpr int TS = RT == R16 ? R : RT;          // the 16-row variant lives in the 64-row carve-up (rows stride LD16)
+  using M = SmemMapT<TS>;
+  constexpr int LDT = RT == R16 ? LD16 : M::LD;
   extern __shared__ __align__(16) float sm[];
   const int which = blockIdx.y;
   const NetDesc nd = a.net[which];
   const int I = nd.I, O = nd.O;
-  stage_params(sm, nd);
-  int *sidx = reinterpret_cast<int *>(sm + SmemMap::IDX);
-  const float *P = sm + SmemMap::P;
+  stage_params(sm, nd, M::MBAR);
+  int *sidx = reinterpret_cast<int *>(sm + M::IDX);
+  const float *P = sm + M::P;
   const int64_t n_tiles = (a.B + RT - 1) / RT;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncthreads();
@@ -285,29 +326,29 @@ __global__ void __launch_bounds__(NT, 2) fused_forward_kernel(FwdArgs a) {
       sidx[threadIdx.x] = row < a.B ? (int)row : -1;
     }
     __syncthreads();
-    if (RT == R) {
-      load_rows_T(sm + SmemMap::XT, a.x, sidx, I);
+    if (RT != R16) {
+      load_rows_T<TS>(sm + M::XT, a.x, sidx, I);
       __syncthreads();
-      layer_fwd(sm + SmemMap::XT, I, P, P + off_b1(I), sm + SmemMap::H1T, nd.act);
+      layer_fwd<TS>(sm + M::XT, I, P, P + off_b1(I), sm + M::H1T, nd.act);
       __syncthreads();
-      layer_fwd(sm + SmemMap::H1T, H, P + off_W2(I), P + off_b2(I), sm + SmemMap::H2T, nd.act);
+      layer_fwd<TS>(sm + M::H1T, H, P + off_W2(I), P + off_b2(I), sm + M::H2T, nd.act);
       __syncthreads();
-      layer_out(sm + SmemMap::H2T, P + off_W3(I), P + off_b3(I, O), O, sm + SmemMap::OT);
+      layer_out<TS>(sm + M::H2T, P + off_W3(I), P + off_b3(I, O), O, sm + M::OT);
     } else {
       for (int e = threadIdx.x; e < RT * I; e += NT) {
         const int r = e / I, i = e - r * I;
         const int row = sidx[r];
-        sm[SmemMap::XT + i * LDT + r] = row >= 0 ? __ldg(a.x + (int64_t)row * I + i) : 0.f;
+        sm[M::XT + i * LDT + r] = row >= 0 ? __ldg(a.x + (int64_t)row * I + i) : 0.f;
       }
       __syncthreads();
-      layer_fwd16(sm + SmemMap::XT, I, P, P + off_b1(I), sm + SmemMap::H1T, nd.act);
+      layer_fwd16(sm + M::XT, I, P, P + off_b1(I), sm + M::H1T, nd.act);
       __syncthreads();
-      layer_fwd16(sm + SmemMap::H1T, H, P + off_W2(I), P + off_b2(I), sm + SmemMap::H2T, nd.act);
+      layer_fwd16(sm + M::H1T, H, P + off_W2(I), P + off_b2(I), sm + M::H2T, nd.act);
       __syncthreads();
-      layer_out16(sm + SmemMap::H2T, P + off_W3(I), P + off_b3(I, O), O, sm + SmemMap::OT);
+      layer_out16(sm + M::H2T, P + off_W3(I), P + off_b3(I, O), O, sm + M::OT);
     }
     __syncthreads();
-    const float *OT = sm + SmemMap::OT;
+    const float *OT = sm + M::OT;
     if (a.mode[which] == 0) {
       float *y = a.y[which];
       for (int e = threadIdx.x; e < RT * O; e += NT) {
@@ -363,18 +404,23 @@ struct MbArgs {
 __device__ __forceinline__ bool stopped(const int *ctl, int mb) { return ctl && ctl[1] != 0 && ctl[1] <= mb; }
 
 // HEAD 0: ppo_loss / a2c_loss on a GaussianPolicy with a logΣ vector.  HEAD 1: Flux.mse(V(s), return).
-template <int HEAD>
-__global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
+// RT = 64 : 2 CTAs per SM, 4x4 register tiles (small and medium minibatches).
+// RT = 128: 1 CTA per SM, 8x4 register tiles in the forward / data-backward GEMMs: a third fewer shared-memory wavefronts
+//           per FFMA (the 64-row variant is shared-memory-bandwidth bound, profiles/).
+template <int HEAD, int RT>
+__global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(MbArgs a) {
   if (stopped(a.ctl, a.mb)) return;
+  using M = SmemMapT<RT>;
+  constexpr int LD = M::LD;
   extern __shared__ __align__(16) float sm[];
   const NetDesc nd = a.net;
   const int I = nd.I, O = nd.O, act = nd.act;
   const int t = threadIdx.x;
-  stage_params(sm, nd);
+  stage_params(sm, nd, M::MBAR);
   build_transposes(sm, I, O);
-  int *sidx = reinterpret_cast<int *>(sm + SmemMap::IDX);
-  const float *P = sm + SmemMap::P;
-  float *XT = sm + SmemMap::XT, *H1T = sm + SmemMap::H1T, *H2T = sm + SmemMap::H2T, *OT = sm + SmemMap::OT, *AT = sm + SmemMap::AT;
+  int *sidx = reinterpret_cast<int *>(sm + M::IDX);
+  const float *P = sm + M::P;
+  float *XT = sm + M::XT, *H1T = sm + M::H1T, *H2T = sm + M::H2T, *OT = sm + M::OT, *AT = sm + M::AT;
 
   // per-CTA gradient accumulators (registers, live across all tiles)
   const int kg = t >> 4, jg = t & 15;  // weight-gradient patch: rows kg + 16a, cols jg + 16b
@@ -387,42 +433,42 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc1[i][j] = 0.f;
-  // head sums of this thread's rows (threads 0..63)
+  // head sums of this thread's rows (threads 0..RT-1)
   float s_obj = 0.f, s_kl = 0.f, s_clip = 0.f, s_adv = 0.f, s_ret = 0.f, dls[MAX_O];
 #pragma unroll
   for (int j = 0; j < MAX_O; ++j) dls[j] = 0.f;
 
-  const int64_t n_tiles = (a.bm + R - 1) / R;
+  const int64_t n_tiles = (a.bm + RT - 1) / RT;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncthreads();
-    if (t < R) {
-      const int64_t row = tile * R + t;
+    if (t < RT) {
+      const int64_t row = tile * RT + t;
       sidx[t] = row < a.bm ? (a.order ? a.order[row] : (int)row) : -1;
     }
     __syncthreads();
-    load_rows_T(XT, a.s, sidx, I);
+    load_rows_T<RT>(XT, a.s, sidx, I);
     if (HEAD == 0) {
-      load_rows_T(AT, a.act, sidx, O);
-      if (t < R) {
+      load_rows_T<RT>(AT, a.act, sidx, O);
+      if (t < RT) {
         const int row = sidx[t];
-        sm[SmemMap::LP + t] = row >= 0 ? a.logp_old[row] : 0.f;
-        sm[SmemMap::ADV + t] = row >= 0 ? a.adv[row] : 0.f;
-        sm[SmemMap::RET + t] = (row >= 0 && a.ret) ? a.ret[row] : 0.f;
+        sm[M::LP + t] = row >= 0 ? a.logp_old[row] : 0.f;
+        sm[M::ADV + t] = row >= 0 ? a.adv[row] : 0.f;
+        sm[M::RET + t] = (row >= 0 && a.ret) ? a.ret[row] : 0.f;
       }
-    } else if (t < R) {
+    } else if (t < RT) {
       const int row = sidx[t];
-      sm[SmemMap::RET + t] = row >= 0 ? a.ret[row] : 0.f;
+      sm[M::RET + t] = row >= 0 ? a.ret[row] : 0.f;
     }
     __syncthreads();
     // ---------------- forward
-    layer_fwd(XT, I, P, P + off_b1(I), H1T, act);
+    layer_fwd<RT>(XT, I, P, P + off_b1(I), H1T, act);
     __syncthreads();
-    layer_fwd(H1T, H, P + off_W2(I), P + off_b2(I), H2T, act);
+    layer_fwd<RT>(H1T, H, P + off_W2(I), P + off_b2(I), H2T, act);
     __syncthreads();
-    layer_out(H2T, P + off_W3(I), P + off_b3(I, O), O, OT);
+    layer_out<RT>(H2T, P + off_W3(I), P + off_b3(I, O), O, OT);
     __syncthreads();
     // ---------------- loss head: dL/dout (scaled by 1/B_global) replaces out^T
-    if (t < R) {
+    if (t < RT) {
       const bool live = sidx[t] >= 0;
       if (HEAD == 0) {
         float logp = 0.f;
@@ -431,7 +477,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
           const float d = AT[j * LD + t] - OT[j * LD + t];
           logp += -(d * d) / (2.f * (sg * sg)) - LOG_SQRT_2PI - a.ls[j];
         }
-        const float Ai = sm[SmemMap::ADV + t], old = sm[SmemMap::LP + t];
+        const float Ai = sm[M::ADV + t], old = sm[M::LP + t];
         float dlogp = 0.f;
         if (live) {
           if (a.a2c) {
@@ -446,7 +492,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
             dlogp = first ? -a.lambda_p * a.inv_bg * x : 0.f;
             s_clip += (rt > hi || rt < lo) ? 1.f : 0.f;
           }
-          s_kl += old - logp; s_adv += Ai; s_ret += sm[SmemMap::RET + t];
+          s_kl += old - logp; s_adv += Ai; s_ret += sm[M::RET + t];
         }
         for (int j = 0; j < O; ++j) {
           const float sg = expf(a.ls[j]);
@@ -456,7 +502,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
           dls[j] += dlogp * (d * d / var - 1.f);
         }
       } else {
-        const float d = OT[t] - sm[SmemMap::RET + t];
+        const float d = OT[t] - sm[M::RET + t];
         if (live) s_obj += d * d;
         OT[t] = live ? 2.f * d * a.inv_bg : 0.f;
       }
@@ -468,7 +514,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
       if (og < O) {
         const bool v1 = og + 4 < O;
 #pragma unroll 4
-        for (int r4 = 0; r4 < R / 4; ++r4) {
+        for (int r4 = 0; r4 < RT / 4; ++r4) {
           const float4 h = *reinterpret_cast<const float4 *>(H2T + k * LD + 4 * r4);
           acc3[0] = dot4(h, *reinterpret_cast<const float4 *>(OT + og * LD + 4 * r4), acc3[0]);
           if (v1) acc3[1] = dot4(h, *reinterpret_cast<const float4 *>(OT + (og + 4) * LD + 4 * r4), acc3[1]);
@@ -476,7 +522,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
       }
       if (t >= 128 && t < 128 + O) {  // db3
         const int o = t - 128;
-        for (int r4 = 0; r4 < R / 4; ++r4) {
+        for (int r4 = 0; r4 < RT / 4; ++r4) {
           const float4 d = *reinterpret_cast<const float4 *>(OT + o * LD + 4 * r4);
           accb += (d.x + d.y) + (d.z + d.w);
         }
@@ -484,11 +530,11 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
     }
     __syncthreads();
     // ---------------- dz2^T in place over h2^T
-    layer_bwd_data(OT, O, sm + SmemMap::W3T, H2T, act);
+    layer_bwd_data<RT>(OT, O, sm + M::W3T, H2T, act);
     __syncthreads();
     // ---------------- dW2 += h1^T dz2 ; db2
 #pragma unroll 2
-    for (int r4 = 0; r4 < R / 4; ++r4) {
+    for (int r4 = 0; r4 < RT / 4; ++r4) {
       float4 hv[4], zv[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -501,18 +547,18 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
         for (int j = 0; j < 4; ++j) acc2[i][j] = dot4(hv[i], zv[j], acc2[i][j]);
     }
     if (t < 64) {  // db2[t]
-      for (int r4 = 0; r4 < R / 4; ++r4) {
+      for (int r4 = 0; r4 < RT / 4; ++r4) {
         const float4 d = *reinterpret_cast<const float4 *>(H2T + t * LD + 4 * r4);
         accb += (d.x + d.y) + (d.z + d.w);
       }
     }
     __syncthreads();
     // ---------------- dz1^T in place over h1^T
-    layer_bwd_data(H2T, H, sm + SmemMap::W2T, H1T, act);
+    layer_bwd_data<RT>(H2T, H, sm + M::W2T, H1T, act);
     __syncthreads();
     // ---------------- dW1 += x^T dz1 ; db1
 #pragma unroll 2
-    for (int r4 = 0; r4 < R / 4; ++r4) {
+    for (int r4 = 0; r4 < RT / 4; ++r4) {
       float4 zv[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) zv[q] = *reinterpret_cast<const float4 *>(H1T + (jg + 16 * q) * LD + 4 * r4);
@@ -527,7 +573,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
       }
     }
     if (t >= 64 && t < 128) {  // db1[t - 64]
-      for (int r4 = 0; r4 < R / 4; ++r4) {
+      for (int r4 = 0; r4 < RT / 4; ++r4) {
         const float4 d = *reinterpret_cast<const float4 *>(H1T + (t - 64) * LD + 4 * r4);
         accb += (d.x + d.y) + (d.z + d.w);
       }
@@ -555,10 +601,10 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
   if (t < 64) out[off_b2(I) + t] = accb;
   else if (t < 128) out[off_b1(I) + (t - 64)] = accb;
   else if (t < 128 + O) out[off_b3(I, O) + (t - 128)] = accb;
-  // head sums: threads 0..63 = warps 0,1
+  // head sums: threads 0..RT-1 = the first RT/32 warps
   __syncthreads();
-  float *red = sm + SmemMap::RED;
-  if (t < 64) {
+  float *red = sm + M::RED;
+  if (t < RT) {
     const int lane = t & 31, w = t >> 5;
     float v;
     v = warp_sum(s_obj); if (lane == 0) red[w * 24 + 0] = v;
@@ -573,7 +619,10 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_kernel(MbArgs a) {
   if (t < 16) {
     // tail layout: [n_params .. +8) = dlogΣ, [n_params+8 .. +16) = obj, kl, clip, adv, ret, 0, 0, 0
     const int src = t < 8 ? 8 + t : t - 8;
-    float v = (src < 5 || src >= 8) ? red[src] + red[24 + src] : 0.f;
+    float v = 0.f;
+    if (src < 5 || src >= 8)
+#pragma unroll
+      for (int w = 0; w < RT / 32; ++w) v += red[w * 24 + src];
     out[a.n_params + t] = v;
   }
 }
@@ -728,14 +777,35 @@ NetDesc describe(const crux_mlp *m) {
   return nd;
 }
 int set_smem_attr(crux_ctx *ctx) {
-  static bool done[3] = {false, false, false};
-  if (!done[0]) {
-    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(fused_forward_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(fused_forward_kernel<R16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    done[0] = true;
+  static bool done = false;
+  if (done) return CRUX_OK;
+#define SET_ATTR(fn, bytes) CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
+  SET_ATTR(fused_forward_kernel<R>, SmemMapT<R>::BYTES);
+  SET_ATTR(fused_forward_kernel<R16>, SmemMapT<R>::BYTES);
+  SET_ATTR(fused_forward_kernel<RB>, SmemMapT<RB>::BYTES);
+  SET_ATTR((fused_minibatch_kernel<0, R>), SmemMapT<R>::BYTES);
+  SET_ATTR((fused_minibatch_kernel<1, R>), SmemMapT<R>::BYTES);
+  SET_ATTR((fused_minibatch_kernel<0, RB>), SmemMapT<RB>::BYTES);
+  SET_ATTR((fused_minibatch_kernel<1, RB>), SmemMapT<RB>::BYTES);
+#undef SET_ATTR
+  done = true;
+  return CRUX_OK;
+}
+
+// forward launch: 16-row tiles when 64-row tiles cannot fill the GPU, 128-row tiles (1 CTA/SM) when they fill it at least once
+int launch_forward(crux_ctx *ctx, FwdArgs &a, int nets) {
+  const int64_t B = a.B;
+  if (cdiv(B, R) * nets < (int64_t)ctx->num_sms) {
+    dim3 grid((unsigned)i64min(cdiv(B, R16), (int64_t)ctx->num_sms * 2), nets);
+    fused_forward_kernel<R16><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
+  } else if (cdiv(B, RB) * nets >= (int64_t)ctx->num_sms && !getenv("CRUX_NO_RB")) {
+    dim3 grid((unsigned)i64min(cdiv(B, RB), (int64_t)ctx->num_sms), nets);
+    fused_forward_kernel<RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
+  } else {
+    dim3 grid((unsigned)i64min(cdiv(B, R), (int64_t)ctx->num_sms * 2), nets);
+    fused_forward_kernel<R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
   }
-  if (!done[1]) { CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(fused_minibatch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)); done[1] = true; }
-  if (!done[2]) { CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(fused_minibatch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)); done[2] = true; }
+  CRUX_LAUNCHED(ctx);
   return CRUX_OK;
 }
 
@@ -751,13 +821,8 @@ int mlp_forward_fused(crux_mlp *mlp, const float *x, int64_t B, float *y, int *h
   FwdArgs a;
   memset(&a, 0, sizeof(a));
   a.net[0] = describe(mlp); a.mode[0] = 0; a.x = x; a.B = B; a.y[0] = y;
-  // batches that cannot fill the GPU with 64-row tiles use 16-row tiles (4x the CTAs, latency-bound regime)
-  const bool small = cdiv(B, R) < (int64_t)ctx->num_sms;
-  const int64_t tiles = cdiv(B, small ? R16 : R);
-  dim3 grid((unsigned)i64min(tiles, (int64_t)ctx->num_sms * 2), 1);
-  if (small) fused_forward_kernel<R16><<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
-  else fused_forward_kernel<R><<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
-  CRUX_LAUNCHED(ctx);
+  rc = launch_forward(ctx, a, 1);
+  if (rc) return rc;
   *handled = 1;
   return CRUX_OK;
 }
@@ -776,12 +841,8 @@ extern "C" int32_t crux_rollout_step_fused(crux_gaussian *actor, crux_mlp *criti
   a.net[0] = describe(actor->mu); a.mode[0] = 1; a.y[0] = a_out; a.logp = logp_out; a.ls = actor->log_sigma; a.eps_in = eps_in;
   a.seed = seed; a.ctr = ctr; a.x = obs; a.B = N;
   if (with_critic) { a.net[1] = describe(critic); a.mode[1] = 0; a.y[1] = v_out; }
-  const bool small = cdiv(N, R) * (with_critic ? 2 : 1) < (int64_t)ctx->num_sms;
-  const int64_t tiles = cdiv(N, small ? R16 : R);
-  dim3 grid((unsigned)i64min(tiles, (int64_t)ctx->num_sms * 2), with_critic ? 2 : 1);
-  if (small) fused_forward_kernel<R16><<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
-  else fused_forward_kernel<R><<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
-  CRUX_LAUNCHED(ctx);
+  rc = launch_forward(ctx, a, with_critic ? 2 : 1);
+  if (rc) return rc;
   *handled = 1;
   return CRUX_OK;
 }
@@ -791,8 +852,8 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
                            const float *adv, const float *ret, const int32_t *order, int64_t bm, const crux_ppo_hp *hp, float *rec,
                            int *ctl, int mb) {
   crux_ctx *ctx = mlp->ctx;
-  const int64_t tiles = cdiv(bm, R);
-  const int grid = (int)i64min(tiles, (int64_t)ctx->num_sms * 2);
+  const bool big = cdiv(bm, RB) >= (int64_t)ctx->num_sms && !getenv("CRUX_NO_RB");   // 128-row tiles fill every SM at least once
+  const int grid = big ? (int)i64min(cdiv(bm, RB), (int64_t)ctx->num_sms) : (int)i64min(cdiv(bm, R), (int64_t)ctx->num_sms * 2);
   const int pstride = (int)((mlp->n_params + 16 + 31) / 32 * 32);
   const size_t need = (size_t)ctx->num_sms * 2 * pstride * sizeof(float);
   int rc = ppo_ensure_bytes(ctx, (void **)&mlp->partials, &mlp->partials_bytes, need);
@@ -804,8 +865,13 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   a.ls = head == 0 ? actor->log_sigma : nullptr;
   a.inv_bg = inv_bg; a.eps_clip = hp->eps_clip; a.lambda_p = hp->lambda_p; a.a2c = hp->a2c; a.partials = mlp->partials; a.pstride = pstride;
   a.n_params = (int)mlp->n_params; a.ctl = ctl; a.mb = mb;
-  if (head == 0) fused_minibatch_kernel<0><<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
-  else fused_minibatch_kernel<1><<<grid, NT, SMEM_BYTES, ctx->stream>>>(a);
+  if (big) {
+    if (head == 0) fused_minibatch_kernel<0, RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
+    else fused_minibatch_kernel<1, RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
+  } else {
+    if (head == 0) fused_minibatch_kernel<0, R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
+    else fused_minibatch_kernel<1, R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
+  }
   CRUX_LAUNCHED(ctx);
   const int n_out = (int)mlp->n_params + 16;
   const int rblocks = (n_out + 31) / 32;   // <= 1024 doubles of norm_part (n_params <= 6792)

@@ -156,6 +156,8 @@ class Sampler:
         discrete = isinstance(self.agent.space, DiscreteSpace)
         if self.on_device:
             self._rollout_device(data, T, explore, i, reset, noise)
+        elif self._can_rollout_native(explore, noise, data, discrete):
+            self._rollout_host_native(data, T, reset)
         else:
             self._rollout_host(data, T, explore, i, reset, noise, discrete)
         # terminate_episode! bookkeeping for all closed ranges at once (sampler.jl:56-57)
@@ -245,6 +247,34 @@ class Sampler:
                 P["obs"][idx] = self._tovec(env.reset(idx))
                 self.episode_length[idx] = 0
         ctx.h2d(self.cur, P["obs"])
+        ctx.sync()
+
+    # ---- the same loop in one C call (crux_rollout_host) when the env exposes C callbacks and nothing is injected
+    def _can_rollout_native(self, explore, noise, data, discrete):
+        pe = self.agent.pi_explore
+        return (explore and noise is None and not discrete and hasattr(self.mdp, "c_callbacks") and not self._needs_tovec()
+                and not getattr(self, "force_python_loop", False)
+                and isinstance(actor(pe), GaussianPolicy) and (pe is self.agent.pi or isinstance(pe, (GaussianPolicy, ActorCritic)))
+                and not actor(pe).squashed and actor(pe).log_sigma is not None and "t" not in data and "i" not in data)
+
+    def _rollout_host_native(self, data, T, reset):
+        import ctypes as C
+        ctx = self.ctx
+        self._pin()
+        if getattr(self, "_ep_len32", None) is None:
+            self._ep_len32 = np.zeros(self.n, dtype=np.int32)
+        self._ep_len32[:] = self.episode_length
+        step_fn, reset_fn, user = self.mdp.c_callbacks()
+        lp = data.get("logprob")
+        cols = _abi.RolloutCols(data["s"].data_ptr(), data["a"].data_ptr(), data["sp"].data_ptr(), data["r"].data_ptr(), data["done"].data_ptr(),
+                                data["episode_end"].data_ptr(), lp.data_ptr() if lp is not None else None)
+        ctr0 = self.noise_ctr
+        self.noise_ctr += T
+        ctx.check(ctx.lib.crux_rollout_host(actor(self.agent.pi_explore).h, self.n, T, self.max_steps, 1 if reset else 0, step_fn, reset_fn, user,
+                                            C.c_void_p(self._pinned["obs"].ctypes.data), C.c_void_p(self._ep_len32.ctypes.data), C.byref(cols),
+                                            self.seed, ctr0))
+        self.episode_length[:] = self._ep_len32
+        ctx.h2d(self.cur, self._pinned["obs"])
         ctx.sync()
 
     def _needs_tovec(self):

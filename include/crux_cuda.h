@@ -148,6 +148,23 @@ int32_t crux_discrete_eps_greedy(crux_ctx *ctx, const float *q, int64_t B, int32
 int32_t crux_rollout_step(crux_gaussian *actor, crux_mlp *critic, const float *obs, int64_t N,
                           const float *eps_in, uint64_t seed, uint64_t ctr, float *a_out,
                           float *logp_out, float *v_out);
+/* The same hot path for a HOST environment: the whole steps! loop (sampler.jl:139-155) of T vector steps in one call.
+ * The environment (the user's POMDPs.jl model) is reached through two callbacks, which a Julia host passes as @cfunction
+ * pointers:  step  = @gen(:sp,:r)(mdp, s, a) + isterminal for all N streams (host arrays in pinned memory),
+ *            reset = rand(initialstate(mdp)) + convert_s for the listed streams (sampler.jl:31-43).
+ * obs_pinned [N][sdim] (pinned host memory, in/out) holds the current observation of every stream (already tovec'ed);
+ * episode_length [N] (host, in/out) is Sampler.episode_length.  Columns are device pointers to rows [T*N] (row t*N+e).
+ * Exploration noise comes from the device Philox stream (seed, ctr0 + t). */
+typedef void (*crux_env_step_fn)(void *user, const float *a, float *sp, float *r, uint8_t *done);
+typedef void (*crux_env_reset_fn)(void *user, const int32_t *idx, int32_t n_idx, float *obs_out);
+typedef struct crux_rollout_cols {
+  float *s, *a, *sp, *r;
+  uint8_t *done, *episode_end;
+  float *logprob; /* nullable */
+} crux_rollout_cols;
+int32_t crux_rollout_host(crux_gaussian *actor, int64_t N, int32_t T, int32_t max_steps, int32_t reset_at_end,
+                          crux_env_step_fn step, crux_env_reset_fn reset, void *user, float *obs_pinned,
+                          int32_t *episode_length, const crux_rollout_cols *cols, uint64_t seed, uint64_t ctr0);
 /* tovec(o, ContinuousSpace) = (o - μ)/σ  spaces.jl:24-25, utils.jl:42 (in place when out == x) */
 int32_t crux_normalize_obs(crux_ctx *ctx, const float *x, int64_t n, float mu, float sigma, float *out);
 

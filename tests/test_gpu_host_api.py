@@ -288,3 +288,24 @@ def test_solve_sac_runs(crux, ctx):
     after = A.mu.mlp.get_flat()
     assert np.isfinite(after).all() and not np.array_equal(before, after)
     assert len(S.buffer) == 512 and S.i == 512  # the initial fill counts toward N (off_policy.jl:122-133)
+
+
+def test_native_rollout_loop_equals_python_loop(crux, ctx):
+    """crux_rollout_host (the steps! loop in one C call, env reached through C callbacks) produces exactly the rollout of
+    the Python-driven loop: same env streams, same device noise streams, same bookkeeping."""
+    n, T, max_steps = 64, 24, 9
+    outs = []
+    for force_python in (False, True):
+        pi = _actor_critic(crux, ctx, seed=11)
+        env = crux.NativeHostLinQuad(n, seed=4, n_threads=2)
+        s = crux.Sampler(env, pi, max_steps=max_steps, required_columns=["return", "logprob", "advantage"], lam=0.95, seed=3)
+        s.force_python_loop = force_python
+        d1 = {k: v.clone() for k, v in s.steps_(None, Nsteps=n * T, explore=True, reset=True).items()}
+        d2 = {k: v.clone() for k, v in s.steps_(None, Nsteps=n * T, explore=True, reset=False).items()}  # continues the streams
+        outs.append((d1, d2, s.episode_length.copy(), host(s.cur).copy()))
+    for a, b in zip(outs[0][:2], outs[1][:2]):
+        for k in a:
+            assert torch.equal(a[k], b[k]), f"column {k} differs between the native and the Python rollout loop"
+    assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][3], outs[1][3])
+    ee = host(outs[0][0]["episode_end"]).reshape(T, n)
+    assert ee[-1].all() and 0 < ee[:-1].mean() < 0.5
