@@ -59,6 +59,8 @@ struct Env {
   float *sp = nullptr, *r = nullptr;
   uint8_t *done = nullptr;
   uint64_t job_tick = 0;
+  int job_e0 = 0, job_e1 = 0;
+  uint64_t last_step_tick = 0;
 };
 
 void s0_row(const Env &E, uint64_t tick, int64_t e, float *out) {
@@ -176,8 +178,9 @@ void worker(Env *E, int id) {
     }
     if (E->quit.load()) return;
     seen = E->gen.load(std::memory_order_acquire);
-    const int per = (E->n + E->n_threads - 1) / E->n_threads;
-    const int e0 = id * per, e1 = std::min(E->n, e0 + per);
+    const int cnt = E->job_e1 - E->job_e0;
+    const int per = (cnt + E->n_threads - 1) / E->n_threads;
+    const int e0 = E->job_e0 + id * per, e1 = std::min(E->job_e1, e0 + per);
     if (e0 < e1) step_range(*E, e0, e1);
     E->pending.fetch_sub(1, std::memory_order_acq_rel);
   }
@@ -226,7 +229,7 @@ void crux_hostenv_reset(void *h, const int32_t *idx, int n_idx, float *obs_out) 
     E->tick += 1;
   } else {
     // after a step: same stream position the device env uses for in-step resets (tick of that step + 2^32)
-    const uint64_t t = (E->tick - 1) + 0x100000000ULL;
+    const uint64_t t = E->last_step_tick + 0x100000000ULL;
     for (int q = 0; q < n_idx; ++q) {
       s0_row(*E, t, idx[q], &E->state[(size_t)idx[q] * S]);
       if (obs_out) memcpy(obs_out + (size_t)q * S, &E->state[(size_t)idx[q] * S], sizeof(float) * S);
@@ -234,21 +237,31 @@ void crux_hostenv_reset(void *h, const int32_t *idx, int n_idx, float *obs_out) 
   }
 }
 
-// @gen(:sp,:r)(mdp, s, a) + isterminal for every stream; the stream state advances to sp (the caller resets ended streams)
-void crux_hostenv_step(void *h, const float *a, float *sp, float *r, uint8_t *done) {
+// @gen(:sp,:r)(mdp, s, a) + isterminal for the streams [e0, e1) (pointers address the FULL arrays; rows e0..e1-1 are
+// read / written); the stream state advances to sp (the caller resets ended streams).  A vector step may be issued as several
+// consecutive ranges: the noise position (tick) advances when the range that ends at n_envs has been stepped.
+void crux_hostenv_step_range(void *h, int32_t e0, int32_t e1, const float *a, float *sp, float *r, uint8_t *done) {
   Env *E = (Env *)h;
-  E->a = a; E->sp = sp; E->r = r; E->done = done; E->job_tick = E->tick;
+  if (e0 < 0) e0 = 0;
+  if (e1 > E->n) e1 = E->n;
+  if (e0 >= e1) return;
+  E->a = a; E->sp = sp; E->r = r; E->done = done; E->job_tick = E->tick; E->job_e0 = e0; E->job_e1 = e1;
+  E->last_step_tick = E->tick;
   const int nt = E->n_threads;
   if (nt > 1) {
     E->pending.store(nt - 1, std::memory_order_release);
     E->gen.fetch_add(1, std::memory_order_acq_rel);
     E->cv.notify_all();
   }
-  const int per = (E->n + nt - 1) / nt;
-  step_range(*E, 0, std::min(E->n, per));
+  const int per = (e1 - e0 + nt - 1) / nt;
+  step_range(*E, e0, std::min(e1, e0 + per));
   while (E->pending.load(std::memory_order_acquire) > 0) CPU_PAUSE();
-  memcpy(E->state.data(), sp, sizeof(float) * (size_t)E->n * E->sdim);
-  E->tick += 1;
+  memcpy(E->state.data() + (size_t)e0 * E->sdim, sp + (size_t)e0 * E->sdim, sizeof(float) * (size_t)(e1 - e0) * E->sdim);
+  if (e1 == E->n) E->tick += 1;
+}
+
+void crux_hostenv_step(void *h, const float *a, float *sp, float *r, uint8_t *done) {
+  crux_hostenv_step_range(h, 0, ((Env *)h)->n, a, sp, r, done);
 }
 
 }  // extern "C"

@@ -245,7 +245,16 @@ int32_t crux_gaussian_entropy(crux_gaussian *p, const float *s, int64_t B, float
 }
 
 int32_t crux_rollout_step_fused(crux_gaussian *actor, crux_mlp *critic, const float *obs, int64_t N, const float *eps_in,
-                                uint64_t seed, uint64_t ctr, float *a_out, float *logp_out, float *v_out, int *handled);
+                                uint64_t seed, uint64_t ctr, float *a_out, float *logp_out, float *v_out, int *handled, int64_t row0);
+// rows [row0, row0 + N) of a larger vector step: device noise streams stay keyed by the absolute stream id
+int32_t crux_rollout_step_rows(crux_gaussian *actor, const float *obs, int64_t N, int64_t row0, uint64_t seed, uint64_t ctr, float *a_out,
+                               float *logp_out) {
+  int handled = 0;
+  int rc = crux_rollout_step_fused(actor, nullptr, obs, N, nullptr, seed, ctr, a_out, logp_out, nullptr, &handled, row0);
+  if (rc) return rc;
+  if (!handled) return crux_set_err(actor->ctx, CRUX_ERR_STATE, "crux_rollout_step_rows: only the fused policy shapes support split vector steps");
+  return CRUX_OK;
+}
 
 int32_t crux_rollout_step(crux_gaussian *actor, crux_mlp *critic, const float *obs, int64_t N, const float *eps_in,
                           uint64_t seed, uint64_t ctr, float *a_out, float *logp_out, float *v_out) {
@@ -255,7 +264,7 @@ int32_t crux_rollout_step(crux_gaussian *actor, crux_mlp *critic, const float *o
   if (N == 0) return CRUX_OK;
   CRUX_REQUIRE(ctx, obs && a_out, "crux_rollout_step: NULL pointer");
   int handled = 0;
-  int rc = crux_rollout_step_fused(actor, critic, obs, N, eps_in, seed, ctr, a_out, logp_out, v_out, &handled);
+  int rc = crux_rollout_step_fused(actor, critic, obs, N, eps_in, seed, ctr, a_out, logp_out, v_out, &handled, 0);
   if (rc || handled) return rc;
   rc = gaussian_head(actor, obs, N, 0, eps_in, nullptr, seed, ctr, a_out, logp_out);
   if (rc) return rc;

@@ -275,6 +275,7 @@ struct FwdArgs {
   const float *ls;           // mode 1: logΣ vector
   const float *eps_in;       // mode 1: injected noise or NULL
   uint64_t seed, ctr;
+  int64_t row0;              // mode 1: index of row 0 in the full vector step (noise streams are keyed by the absolute stream id)
 };
 
 // ---- small-batch variant pieces: 16-row tiles (4x more CTAs for a 4096-stream vector step), thread = (1 row, 4 cols)
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_forward_kernel(Fwd
         if (a.eps_in) e = a.eps_in[i * O + j];
         else {
           if ((j & 3) == 0) {
-            const Philox4 p = philox4x32_10(a.seed, a.ctr, (uint64_t)i * ((O + 3) / 4) + (j >> 2));
+            const Philox4 p = philox4x32_10(a.seed, a.ctr, (uint64_t)(a.row0 + i) * ((O + 3) / 4) + (j >> 2));
             box_muller(p.x, p.y, nrm[0], nrm[1]);
             box_muller(p.z, p.w, nrm[2], nrm[3]);
           }
@@ -798,7 +799,7 @@ int launch_forward(crux_ctx *ctx, FwdArgs &a, int nets) {
   if (cdiv(B, R) * nets < (int64_t)ctx->num_sms) {
     dim3 grid((unsigned)i64min(cdiv(B, R16), (int64_t)ctx->num_sms * 2), nets);
     fused_forward_kernel<R16><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
-  } else if (cdiv(B, RB) * nets >= (int64_t)ctx->num_sms && !getenv("CRUX_NO_RB")) {
+  } else if (cdiv(B, RB) * nets >= (int64_t)ctx->num_sms && getenv("CRUX_RB")) {  // measured slower than 2 x 64-row CTAs/SM (profiles/): opt-in
     dim3 grid((unsigned)i64min(cdiv(B, RB), (int64_t)ctx->num_sms), nets);
     fused_forward_kernel<RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
   } else {
@@ -827,8 +828,13 @@ int mlp_forward_fused(crux_mlp *mlp, const float *x, int64_t B, float *y, int *h
   return CRUX_OK;
 }
 
+bool fused_rows_supported(const crux_gaussian *actor) {
+  return !getenv("CRUX_NO_FUSED") && fusable(actor->mu) && !actor->head_mode && !actor->squashed && actor->adim == actor->mu->dims[3];
+}
+
 extern "C" int32_t crux_rollout_step_fused(crux_gaussian *actor, crux_mlp *critic, const float *obs, int64_t N, const float *eps_in,
-                                           uint64_t seed, uint64_t ctr, float *a_out, float *logp_out, float *v_out, int *handled) {
+                                           uint64_t seed, uint64_t ctr, float *a_out, float *logp_out, float *v_out, int *handled,
+                                           int64_t row0) {
   *handled = 0;
   if (getenv("CRUX_NO_FUSED")) return CRUX_OK;
   if (!fusable(actor->mu) || actor->head_mode || actor->squashed || actor->adim != actor->mu->dims[3]) return CRUX_OK;
@@ -839,7 +845,7 @@ extern "C" int32_t crux_rollout_step_fused(crux_gaussian *actor, crux_mlp *criti
   FwdArgs a;
   memset(&a, 0, sizeof(a));
   a.net[0] = describe(actor->mu); a.mode[0] = 1; a.y[0] = a_out; a.logp = logp_out; a.ls = actor->log_sigma; a.eps_in = eps_in;
-  a.seed = seed; a.ctr = ctr; a.x = obs; a.B = N;
+  a.seed = seed; a.ctr = ctr; a.x = obs; a.B = N; a.row0 = row0;
   if (with_critic) { a.net[1] = describe(critic); a.mode[1] = 0; a.y[1] = v_out; }
   rc = launch_forward(ctx, a, with_critic ? 2 : 1);
   if (rc) return rc;
@@ -852,7 +858,8 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
                            const float *adv, const float *ret, const int32_t *order, int64_t bm, const crux_ppo_hp *hp, float *rec,
                            int *ctl, int mb) {
   crux_ctx *ctx = mlp->ctx;
-  const bool big = cdiv(bm, RB) >= (int64_t)ctx->num_sms && !getenv("CRUX_NO_RB");   // 128-row tiles fill every SM at least once
+  // 128-row tiles (1 CTA/SM, 8x4 register tiles) measured SLOWER than 2 x 64-row CTAs per SM (occupancy halves; profiles/): opt-in
+  const bool big = cdiv(bm, RB) >= (int64_t)ctx->num_sms && getenv("CRUX_RB");
   const int grid = big ? (int)i64min(cdiv(bm, RB), (int64_t)ctx->num_sms) : (int)i64min(cdiv(bm, R), (int64_t)ctx->num_sms * 2);
   const int pstride = (int)((mlp->n_params + 16 + 31) / 32 * 32);
   const size_t need = (size_t)ctx->num_sms * 2 * pstride * sizeof(float);

@@ -128,7 +128,7 @@ class NativeHostLinQuad:
         """(step_fn, reset_fn, user) C pointers matching crux_env_step_fn / crux_env_reset_fn (include/crux_cuda.h): the
         rollout loop of ``crux_rollout_host`` calls the environment without going through Python."""
         L = self.lib()
-        return (C.cast(L.crux_hostenv_step, C.c_void_p), C.cast(L.crux_hostenv_reset, C.c_void_p), C.c_void_p(self.h))
+        return (C.cast(L.crux_hostenv_step_range, C.c_void_p), C.cast(L.crux_hostenv_reset, C.c_void_p), C.c_void_p(self.h))
 
     def step_into(self, a, sp, r, done):
         """a [N, act] f32, sp [N, obs] f32, r [N] f32, done [N] u8: contiguous numpy arrays (may be pinned memory)."""

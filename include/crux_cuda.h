@@ -150,12 +150,15 @@ int32_t crux_rollout_step(crux_gaussian *actor, crux_mlp *critic, const float *o
                           float *logp_out, float *v_out);
 /* The same hot path for a HOST environment: the whole steps! loop (sampler.jl:139-155) of T vector steps in one call.
  * The environment (the user's POMDPs.jl model) is reached through two callbacks, which a Julia host passes as @cfunction
- * pointers:  step  = @gen(:sp,:r)(mdp, s, a) + isterminal for all N streams (host arrays in pinned memory),
+ * pointers:  step  = @gen(:sp,:r)(mdp, s, a) + isterminal for the streams [e0, e1) (host arrays in pinned memory; the
+ *                    pointers address the full [N] arrays, rows e0..e1-1 are read / written),
  *            reset = rand(initialstate(mdp)) + convert_s for the listed streams (sampler.jl:31-43).
+ * With the fused policy shapes a vector step is issued as two half ranges so that the device forward of one half overlaps
+ * the host env step of the other; results do not depend on the split (noise streams are keyed by the stream id).
  * obs_pinned [N][sdim] (pinned host memory, in/out) holds the current observation of every stream (already tovec'ed);
  * episode_length [N] (host, in/out) is Sampler.episode_length.  Columns are device pointers to rows [T*N] (row t*N+e).
  * Exploration noise comes from the device Philox stream (seed, ctr0 + t). */
-typedef void (*crux_env_step_fn)(void *user, const float *a, float *sp, float *r, uint8_t *done);
+typedef void (*crux_env_step_fn)(void *user, int32_t e0, int32_t e1, const float *a, float *sp, float *r, uint8_t *done);
 typedef void (*crux_env_reset_fn)(void *user, const int32_t *idx, int32_t n_idx, float *obs_out);
 typedef struct crux_rollout_cols {
   float *s, *a, *sp, *r;

@@ -293,7 +293,7 @@ def test_solve_sac_runs(crux, ctx):
 def test_native_rollout_loop_equals_python_loop(crux, ctx):
     """crux_rollout_host (the steps! loop in one C call, env reached through C callbacks) produces exactly the rollout of
     the Python-driven loop: same env streams, same device noise streams, same bookkeeping."""
-    n, T, max_steps = 64, 24, 9
+    n, T, max_steps = 640, 12, 9   # >= 512 streams: the native loop leapfrogs two halves of the vector step
     outs = []
     for force_python in (False, True):
         pi = _actor_critic(crux, ctx, seed=11)
