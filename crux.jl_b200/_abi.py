@@ -60,6 +60,8 @@ _SIGS = {
     "crux_last_error": [_vp],
     "crux_ctx_launch_count": [_vp, C.POINTER(_i64)],
     "crux_ctx_check": [_vp],
+    "crux_ctx_timing_begin": [_vp],
+    "crux_ctx_timing_end": [_vp, _vp, _vp],
     "crux_dev_alloc": [_vp, C.c_size_t, _pp],
     "crux_dev_free": [_vp, _vp],
     "crux_pinned_alloc": [_vp, C.c_size_t, _pp],

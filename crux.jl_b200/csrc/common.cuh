@@ -26,6 +26,10 @@ struct crux_ctx {
   // generic scratch (grown on demand, stream-ordered reuse)
   void *scratch[8] = {nullptr};
   size_t scratch_bytes[8] = {0};
+  // opt-in per-kernel-family device timing (bench.py roofline): event pairs recorded around selected launches
+  bool timing = false;
+  std::vector<cudaEvent_t> t_start, t_stop;
+  std::vector<int> t_family;
   // multi-GPU
   int rank = 0, world = 1;
   void *nccl_comm = nullptr;
@@ -64,6 +68,21 @@ void *crux_scratch(crux_ctx *ctx, int slot, size_t bytes);  // nullptr on failur
       return crux_set_err((ctx), CRUX_ERR_CUDA, "%s:%d launch: %s", __FILE__, __LINE__,      \
                           cudaGetErrorString(e__));                                          \
   } while (0)
+
+// timing families (crux_ctx_timing_end)
+enum { CRUX_T_MINIBATCH = 0, CRUX_T_REDUCE = 1, CRUX_T_ADAM = 2, CRUX_T_FORWARD = 3, CRUX_T_GAE = 4, CRUX_T_ENV = 5, CRUX_T_FAMILIES = 8 };
+struct CruxTimed {  // RAII: records an event pair around a launch when timing is enabled
+  crux_ctx *ctx; int slot;
+  CruxTimed(crux_ctx *c, int family) : ctx(c), slot(-1) {
+    if (!c->timing) return;
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    c->t_start.push_back(a); c->t_stop.push_back(b); c->t_family.push_back(family);
+    slot = (int)c->t_start.size() - 1;
+    cudaEventRecord(a, c->stream);
+  }
+  ~CruxTimed() { if (slot >= 0) cudaEventRecord(ctx->t_stop[slot], ctx->stream); }
+};
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t i64min(int64_t a, int64_t b) { return a < b ? a : b; }

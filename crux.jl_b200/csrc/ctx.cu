@@ -114,6 +114,31 @@ int32_t crux_ctx_launch_count(crux_ctx *ctx, int64_t *out) {
   return CRUX_OK;
 }
 
+int32_t crux_ctx_timing_begin(crux_ctx *ctx) {
+  if (!ctx) return CRUX_ERR_INVALID;
+  for (auto e : ctx->t_start) cudaEventDestroy(e);
+  for (auto e : ctx->t_stop) cudaEventDestroy(e);
+  ctx->t_start.clear(); ctx->t_stop.clear(); ctx->t_family.clear();
+  ctx->timing = true;
+  return CRUX_OK;
+}
+
+int32_t crux_ctx_timing_end(crux_ctx *ctx, float *ms_out_host, int32_t *count_out_host) {
+  if (!ctx || !ms_out_host || !count_out_host) return CRUX_ERR_INVALID;
+  ctx->timing = false;
+  CRUX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int f = 0; f < CRUX_T_FAMILIES; ++f) { ms_out_host[f] = 0.f; count_out_host[f] = 0; }
+  for (size_t i = 0; i < ctx->t_start.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->t_start[i], ctx->t_stop[i]) == cudaSuccess) {
+      ms_out_host[ctx->t_family[i]] += ms; count_out_host[ctx->t_family[i]] += 1;
+    }
+    cudaEventDestroy(ctx->t_start[i]); cudaEventDestroy(ctx->t_stop[i]);
+  }
+  ctx->t_start.clear(); ctx->t_stop.clear(); ctx->t_family.clear();
+  return CRUX_OK;
+}
+
 int32_t crux_ctx_check(crux_ctx *ctx) {
   if (!ctx) return CRUX_ERR_INVALID;
   CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->flags_pinned, ctx->flags_dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));

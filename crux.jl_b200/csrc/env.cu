@@ -170,6 +170,7 @@ int32_t crux_linquad_step(crux_linquad *env, const float *obs, const float *a, f
   if (!env) return CRUX_ERR_INVALID;
   crux_ctx *ctx = env->ctx;
   CRUX_REQUIRE(ctx, obs && a && sp && r && done && episode_end && next_obs, "crux_linquad_step: NULL pointer");
+  CruxTimed timed(ctx, CRUX_T_ENV);
   linquad_step_kernel<<<(unsigned)cdiv(env->n_env * 8, 256), 256, 0, ctx->stream>>>(env->A, env->B, obs, a, env->n_env, env->sdim, env->adim,
                                                                                env->max_steps, env->seed, env->tick, force_end, sp, r,
                                                                                done, episode_end, next_obs, env->ep_len);

@@ -265,7 +265,8 @@ int32_t crux_fill_gae_returns(crux_ctx *ctx, const float *r, const uint8_t *done
   gae_returns_kernel<LL><<<grid, block, 0, ctx->stream>>>(r, done, episode_end, v_s, v_sp, T, N, gamma,  \
                                                           lambda, adv, ret, n_chunks, chunk_len, agg,    \
                                                           flags, ctx->flags_dev)
-  if (L == 4) GAE_LAUNCH(4); else GAE_LAUNCH(8);
+  { CruxTimed timed(ctx, CRUX_T_GAE);
+  if (L == 4) GAE_LAUNCH(4); else GAE_LAUNCH(8); }
 #undef GAE_LAUNCH
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;

@@ -796,6 +796,7 @@ int set_smem_attr(crux_ctx *ctx) {
 // forward launch: 16-row tiles when 64-row tiles cannot fill the GPU, 128-row tiles (1 CTA/SM) when they fill it at least once
 int launch_forward(crux_ctx *ctx, FwdArgs &a, int nets) {
   const int64_t B = a.B;
+  CruxTimed timed(ctx, CRUX_T_FORWARD);
   if (cdiv(B, R) * nets < (int64_t)ctx->num_sms) {
     dim3 grid((unsigned)i64min(cdiv(B, R16), (int64_t)ctx->num_sms * 2), nets);
     fused_forward_kernel<R16><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
@@ -872,6 +873,8 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   a.ls = head == 0 ? actor->log_sigma : nullptr;
   a.inv_bg = inv_bg; a.eps_clip = hp->eps_clip; a.lambda_p = hp->lambda_p; a.a2c = hp->a2c; a.partials = mlp->partials; a.pstride = pstride;
   a.n_params = (int)mlp->n_params; a.ctl = ctl; a.mb = mb;
+  {
+  CruxTimed timed(ctx, CRUX_T_MINIBATCH);
   if (big) {
     if (head == 0) fused_minibatch_kernel<0, RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
     else fused_minibatch_kernel<1, RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
@@ -879,12 +882,15 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
     if (head == 0) fused_minibatch_kernel<0, R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
     else fused_minibatch_kernel<1, R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
   }
+  }
   CRUX_LAUNCHED(ctx);
   const int n_out = (int)mlp->n_params + 16;
   const int rblocks = (n_out + 31) / 32;   // <= 1024 doubles of norm_part (n_params <= 6792)
   const float ls_shift = head == 0 ? -hp->lambda_e / (float)ctx->world : 0.f;
+  { CruxTimed timed(ctx, CRUX_T_REDUCE);
   reduce_fused_partials_kernel<<<rblocks, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
                                                                    ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb);
+  }
   CRUX_LAUNCHED(ctx);
   if (ctx->world > 1) { rc = grads_allreduce(ctx, mlp->grads, mlp->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
   AdamArgs g;
@@ -896,7 +902,8 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   g.lambda_p = hp->lambda_p; g.target_kl = hp->target_kl; g.a2c = hp->a2c; g.head = head; g.rec = rec; g.ctl = ctl; g.mb = mb;
   g.err_flags = ctx->flags_dev;
   if (ctx->world == 1) { g.norm_part = mlp->norm_part; g.n_norm_part = rblocks; }
-  fused_adam_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g);
+  { CruxTimed timed(ctx, CRUX_T_ADAM);
+  fused_adam_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g); }
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;
 }

@@ -65,6 +65,12 @@ int32_t crux_ctx_sync(crux_ctx *ctx);
 const char *crux_last_error(crux_ctx *ctx /* NULL: last error of a failed crux_ctx_create */);
 /* number of kernels this context has launched since creation (bench `gpu_launches`) */
 int32_t crux_ctx_launch_count(crux_ctx *ctx, int64_t *out);
+/* Opt-in device timing per kernel family (bench.py roofline): between begin and end every launch of the families below is
+ * bracketed by a CUDA event pair on the context stream; end synchronises and returns summed milliseconds and launch counts.
+ * families: 0 fused minibatch (forward+loss+backward), 1 partial reduction, 2 norm/record/Adam, 3 fused forward,
+ *           4 GAE/returns scan, 5 synthetic env step.  ms_out_host / count_out_host have 8 entries. */
+int32_t crux_ctx_timing_begin(crux_ctx *ctx);
+int32_t crux_ctx_timing_end(crux_ctx *ctx, float *ms_out_host, int32_t *count_out_host);
 /* sticky device-side error flag (NaN in gradients / advantages); reading synchronises. */
 int32_t crux_ctx_check(crux_ctx *ctx);
 
