@@ -135,6 +135,7 @@ _SIGS = {
     "crux_linquad_destroy": [_vp],
     "crux_linquad_reset": [_vp, _vp],
     "crux_linquad_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32],
+    "crux_linquad_rollout": [_vp, _vp, _i32, _i32, _vp, C.POINTER(RolloutCols), _u64, _u64],
     "crux_nccl_unique_id": [_vp],
     "crux_nccl_init": [_vp, _i32, _i32, _vp],
     "crux_nccl_allreduce_f32": [_vp, _vp, _i64],

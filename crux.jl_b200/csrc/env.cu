@@ -2,21 +2,7 @@
 // Not part of the reference: it stands in for a user's POMDPs.jl model so that the sampler hot path
 // (src/sampler.jl:71-137: gen -> isterminal -> write row -> terminate_episode!/reset) can be timed
 // without the host in the loop.  The CPU twin lives in crux.jl_b200/envs.py.
-#include "common.cuh"
-
-#define LQ_MAX_S 32
-#define LQ_MAX_A 16
-
-struct crux_linquad {
-  crux_ctx *ctx = nullptr;
-  int sdim = 0, adim = 0, max_steps = 0;
-  int64_t n_env = 0;
-  uint64_t seed = 0;
-  float *A = nullptr, *B = nullptr;  // device, row-major [sdim][sdim], [sdim][adim]
-  int32_t *ep_len = nullptr;         // per-env episode length (sampler.episode_length)
-  unsigned long long *tick = nullptr; // device: [0] global step counter -> Philox stream position, [1] finished-block counter
-                                     // (device-resident so a captured CUDA graph draws fresh noise on every replay)
-};
+#include "env.cuh"
 
 namespace {
 
@@ -73,7 +59,7 @@ linquad_step_kernel(const float *__restrict__ Am, const float *__restrict__ Bm, 
   for (int k = 0; k < sdim; ++k) s[k] = obs[ee * sdim + k];
   const int len = ep_len[ee] + 1;  // sampler.jl:130 (read by all 8 lanes BEFORE the full-mask shuffles; lane 0 writes after them)
   float a2 = 0.f;
-  for (int j = 0; j < adim; ++j) { const float a = act[ee * adim + j]; a2 += a * a; ta[j] = tanhf(a); }
+  for (int j = 0; j < adim; ++j) { const float a = act[ee * adim + j]; a2 = fmaf(a, a, a2); ta[j] = tanhf(a); }
   float sp[4] = {0.f, 0.f, 0.f, 0.f}, n2 = 0.f;
   const int k0 = 4 * q;
   if (k0 < sdim) {
@@ -86,9 +72,9 @@ linquad_step_kernel(const float *__restrict__ Am, const float *__restrict__ Bm, 
       float v = 0.f;
       for (int j = 0; j < sdim; ++j) v = fmaf(sA[kk * sdim + j], s[j], v);
       for (int j = 0; j < adim; ++j) v = fmaf(sB[kk * adim + j], ta[j], v);
-      v += 0.01f * xi[i];
+      v = fmaf(0.01f, xi[i], v);
       v = fminf(fmaxf(v, -10.f), 10.f);
-      sp[i] = v; n2 += v * v;
+      sp[i] = v; n2 = fmaf(v, v, n2);
     }
   }
   // |s'|^2 over the 8 lanes of the stream (fixed butterfly order); lane 0 holds s'_1

@@ -960,3 +960,198 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
   *handled = 1;
   return CRUX_OK;
 }
+
+// =================================================================================================== persistent device rollout
+// The whole `steps!` loop (sampler.jl:139-155) for a DEVICE environment in ONE launch: every CTA owns 16 env streams and
+// walks all T vector steps -- policy forward (fused_forward<16> building blocks, parameters staged once by TMA), Gaussian
+// sample + logprob, the LinQuad transition, episode bookkeeping and reset -- with the observation tile resident in shared
+// memory between steps.  Bit-identical to T x (crux_rollout_step + crux_linquad_step): same noise counters, same FMA order.
+#include "env.cuh"
+
+namespace {
+
+struct RolloutArgs {
+  NetDesc net;
+  const float *ls;
+  const float *A, *B;           // env matrices [sdim][sdim], [sdim][adim]
+  int64_t N; int T, adim, max_steps, force_end;
+  uint64_t seed_pi, ctr0;       // exploration noise: (seed_pi, ctr0 + t, stream)
+  uint64_t seed_env;            // env noise: (seed_env, tick0 + t, stream*16 + group)
+  unsigned long long *tick_dev; // [0] tick, [1] finished-block counter
+  int32_t *ep_len;
+  float *obs_io;                // [N][sdim] current observation of every stream (in: step 0, out: after step T-1)
+  float *s, *a, *sp, *r, *logp; uint8_t *done, *ee;   // rollout columns, rows [T*N]
+};
+
+__global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
+  using M = SmemMapT<R>;
+  extern __shared__ __align__(16) float sm[];
+  // the env state reuses regions of the carve-up that the 16-row forward does not touch
+  float *sA = sm + M::W2T;                       // [32*32] env A
+  float *sB = sm + M::W2T + LQ_MAX_S * LQ_MAX_S; // [32*16] env B
+  float *aT = sm + M::AT;                        // [8][LD16] sampled actions
+  float *taT = sm + M::AT + MAX_O * LD16;        // [8][LD16] tanh(a)
+  const NetDesc nd = g.net;
+  const int I = nd.I, O = nd.O, sdim = I, adim = g.adim;
+  const int t = threadIdx.x;
+  stage_params(sm, nd, M::MBAR);
+  float *spT = sm + M::H2T + H * LD16;           // [32][LD16] s': after the 16-row H2T tile ([64][LD16] = 1280 of the 4352 floats reserved)
+  int *s_len = reinterpret_cast<int *>(spT + LQ_MAX_S * LD16);  // [16] episode lengths
+  int *s_end = s_len + 16;                                      // [16] end flags of the current step
+  for (int i = t; i < sdim * sdim; i += NT) sA[i] = g.A[i];
+  for (int i = t; i < sdim * adim; i += NT) sB[i] = g.B[i];
+  const float *P = sm + M::P;
+  float *XT = sm + M::XT, *H1T = sm + M::H1T, *H2T = sm + M::H2T, *OT = sm + M::OT;
+  const int64_t e0 = (int64_t)blockIdx.x * R16;
+  const int r = t >> 4, d = t & 15;               // env row, dimension slot (dims d and d + 16)
+  const int64_t e = e0 + r;
+  const bool live = e < g.N;
+  const unsigned long long tick0 = *(volatile unsigned long long *)g.tick_dev;
+  // initial observation tile + episode lengths
+  for (int q = t; q < R16 * sdim; q += NT) {
+    const int rr = q / sdim, i = q - rr * sdim;
+    XT[i * LD16 + rr] = e0 + rr < g.N ? g.obs_io[(e0 + rr) * sdim + i] : 0.f;
+  }
+  if (t < R16) s_len[t] = e0 + t < g.N ? g.ep_len[e0 + t] : 0;
+  __syncthreads();
+
+  for (int step = 0; step < g.T; ++step) {
+    const int64_t row0 = (int64_t)step * g.N + e0;
+    // s rows of this step
+    for (int q = t; q < R16 * sdim; q += NT) {
+      const int rr = q / sdim, i = q - rr * sdim;
+      if (e0 + rr < g.N) g.s[(row0 + rr) * sdim + i] = XT[i * LD16 + rr];
+    }
+    // ---- policy forward + Gaussian head (identical to fused_forward_kernel<16>)
+    layer_fwd16(XT, I, P, P + off_b1(I), H1T, nd.act);
+    __syncthreads();
+    layer_fwd16(H1T, H, P + off_W2(I), P + off_b2(I), H2T, nd.act);
+    __syncthreads();
+    layer_out16(H2T, P + off_W3(I), P + off_b3(I, O), O, OT);
+    __syncthreads();
+    if (t < R16) {
+      const int rr = t;
+      const int64_t i = e0 + rr;   // absolute stream id == row index of the vector step
+      float logp = 0.f, nrm[4];
+      for (int j = 0; j < O; ++j) {
+        const float mu = OT[j * LD16 + rr];
+        const float ls = g.ls[j];
+        const float sigma = expf(ls);
+        const float var = sigma * sigma;
+        if ((j & 3) == 0) {
+          const Philox4 p = philox4x32_10(g.seed_pi, g.ctr0 + (uint64_t)step, (uint64_t)i * ((O + 3) / 4) + (j >> 2));
+          box_muller(p.x, p.y, nrm[0], nrm[1]);
+          box_muller(p.z, p.w, nrm[2], nrm[3]);
+        }
+        const float ev = nrm[j & 3];
+        const float act = ev * sigma + mu;
+        aT[j * LD16 + rr] = act;
+        if (i < g.N) g.a[(row0 + rr) * O + j] = act;
+        const float dd = act - mu;
+        logp += -(dd * dd) / (2.f * var) - LOG_SQRT_2PI - ls;
+      }
+      if (i < g.N && g.logp) g.logp[row0 + rr] = logp;
+    }
+    __syncthreads();
+    // ---- env transition (identical arithmetic to linquad_step_kernel)
+    if (d < adim) taT[d * LD16 + r] = tanhf(aT[d * LD16 + r]);
+    __syncthreads();
+    const unsigned long long tick = tick0 + (unsigned long long)step;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int kk = d + 16 * h;
+      if (kk < sdim) {
+        const Philox4 p = philox4x32_10(g.seed_env, tick, (uint64_t)(live ? e : 0) * 16 + (kk >> 2));
+        float xi[4];
+        box_muller(p.x, p.y, xi[0], xi[1]);
+        box_muller(p.z, p.w, xi[2], xi[3]);
+        float v = 0.f;
+        for (int j = 0; j < sdim; ++j) v = fmaf(sA[kk * sdim + j], XT[j * LD16 + r], v);
+        for (int j = 0; j < adim; ++j) v = fmaf(sB[kk * adim + j], taT[j * LD16 + r], v);
+        v = fmaf(0.01f, xi[kk & 3], v);
+        v = fminf(fmaxf(v, -10.f), 10.f);
+        spT[kk * LD16 + r] = v;
+      }
+    }
+    __syncthreads();
+    if (t < R16) {
+      const int rr = t;
+      // |s'|^2 in the exact order of linquad_step_kernel: 8 sequential 4-dim partials, then the xor-1/2/4 butterfly
+      float pq[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float n2 = 0.f;
+        for (int i = 0; i < 4 && 4 * q + i < sdim; ++i) { const float v = spT[(4 * q + i) * LD16 + rr]; n2 = fmaf(v, v, n2); }
+        pq[q] = n2;
+      }
+      const float n2 = ((pq[0] + pq[1]) + (pq[2] + pq[3])) + ((pq[4] + pq[5]) + (pq[6] + pq[7]));
+      float a2 = 0.f;
+      for (int j = 0; j < adim; ++j) { const float av = aT[j * LD16 + rr]; a2 = fmaf(av, av, a2); }
+      const float rew = 1.f - n2 / (float)sdim - 0.1f * a2 / (float)adim;
+      const bool dn = fabsf(spT[rr]) > 5.f;
+      const int len = s_len[rr] + 1;
+      const bool end = dn || len >= g.max_steps || (g.force_end && step == g.T - 1);
+      s_len[rr] = end ? 0 : len;
+      s_end[rr] = end ? 1 : 0;
+      if (e0 + rr < g.N) { g.r[row0 + rr] = rew; g.done[row0 + rr] = dn ? 1 : 0; g.ee[row0 + rr] = end ? 1 : 0; }
+    }
+    __syncthreads();
+    // ---- s' rows out; next observation tile: s', or a fresh initial state where the episode ended
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int kk = d + 16 * h;
+      if (kk < sdim) {
+        const float v = spT[kk * LD16 + r];
+        if (live) g.sp[(row0 + r) * sdim + kk] = v;
+        float nx = v;
+        if (s_end[r]) {
+          const Philox4 p = philox4x32_10(g.seed_env ^ 0x5851F42D4C957F2DULL, tick + 0x100000000ULL, (uint64_t)(live ? e : 0) * 16 + (kk >> 2));
+          const uint32_t u[4] = {p.x, p.y, p.z, p.w};
+          nx = (u32_to_unit_open(u[kk & 3]) * 2.f - 1.f) * 0.1f;
+        }
+        XT[kk * LD16 + r] = nx;
+      }
+    }
+    __syncthreads();
+  }
+  // current observation + episode lengths back to global
+  for (int q = t; q < R16 * sdim; q += NT) {
+    const int rr = q / sdim, i = q - rr * sdim;
+    if (e0 + rr < g.N) g.obs_io[(e0 + rr) * sdim + i] = XT[i * LD16 + rr];
+  }
+  if (t < R16 && e0 + t < g.N) g.ep_len[e0 + t] = s_len[t];
+  // the last block to finish advances the env tick by T (every block has read it by then)
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (t == 0) last = atomicAdd(g.tick_dev + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL;
+  __syncthreads();
+  if (last && t == 0) { g.tick_dev[0] += (unsigned long long)g.T; g.tick_dev[1] = 0ULL; __threadfence(); }
+}
+
+}  // namespace
+
+extern "C" int32_t crux_linquad_rollout(crux_linquad *env, crux_gaussian *actor, int32_t T, int32_t force_end_last, float *obs_io,
+                                        const crux_rollout_cols *cols, uint64_t seed, uint64_t ctr0) {
+  if (!env || !actor) return CRUX_ERR_INVALID;
+  crux_ctx *ctx = env->ctx;
+  CRUX_REQUIRE(ctx, T >= 1 && obs_io && cols, "crux_linquad_rollout: bad arguments");
+  CRUX_REQUIRE(ctx, cols->s && cols->a && cols->sp && cols->r && cols->done && cols->episode_end, "crux_linquad_rollout: NULL column");
+  CRUX_REQUIRE(ctx, fused_rows_supported(actor), "crux_linquad_rollout: needs a GaussianPolicy with a fusable I-64-64-O network and a logΣ vector");
+  CRUX_REQUIRE(ctx, actor->mu->dims[0] == env->sdim && actor->adim == env->adim && env->adim <= MAX_O, "crux_linquad_rollout: policy / env shapes differ");
+  int rc = set_smem_attr(ctx); if (rc) return rc;
+  static bool attr = false;
+  if (!attr) { CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(rollout_linquad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMapT<R>::BYTES)); attr = true; }
+  RolloutArgs g;
+  memset(&g, 0, sizeof(g));
+  g.net = describe(actor->mu); g.ls = actor->log_sigma; g.A = env->A; g.B = env->B; g.N = env->n_env; g.T = T; g.adim = env->adim;
+  g.max_steps = env->max_steps; g.force_end = force_end_last; g.seed_pi = seed; g.ctr0 = ctr0; g.seed_env = env->seed; g.tick_dev = env->tick;
+  g.ep_len = env->ep_len; g.obs_io = obs_io; g.s = cols->s; g.a = cols->a; g.sp = cols->sp; g.r = cols->r; g.logp = cols->logprob;
+  g.done = cols->done; g.ee = cols->episode_end;
+  {
+    CruxTimed timed(ctx, CRUX_T_ENV);
+    rollout_linquad_kernel<<<(unsigned)cdiv(env->n_env, R16), NT, SmemMapT<R>::BYTES, ctx->stream>>>(g);
+  }
+  CRUX_LAUNCHED(ctx);
+  return CRUX_OK;
+}

@@ -172,6 +172,15 @@ class DeviceLinQuad:
         self.ctx.check(self.ctx.lib.crux_linquad_step(self.h, ptr(obs), ptr(a), ptr(sp), ptr(r), ptr(done), ptr(episode_end),
                                                       ptr(next_obs), 1 if force_end else 0))
 
+    def rollout_into(self, actor_pi, T, force_end_last, obs_io, data, seed, ctr0):
+        """T vector steps (policy forward + sample + transition + bookkeeping) in one persistent launch."""
+        from . import _abi
+        lp = data.get("logprob")
+        cols = _abi.RolloutCols(data["s"].data_ptr(), data["a"].data_ptr(), data["sp"].data_ptr(), data["r"].data_ptr(), data["done"].data_ptr(),
+                                data["episode_end"].data_ptr(), lp.data_ptr() if lp is not None else None)
+        self.ctx.check(self.ctx.lib.crux_linquad_rollout(self.h, actor_pi.h, int(T), 1 if force_end_last else 0, ptr(obs_io), C.byref(cols),
+                                                         int(seed), int(ctr0)))
+
     def __del__(self):
         try:
             if getattr(self, "h", None) and self.ctx.h:

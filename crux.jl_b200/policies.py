@@ -121,6 +121,12 @@ class _MLP:
             pass
 
 
+def fusable(mlp):
+    """Shapes served by the fused kernels (csrc/ppo_fused.cu): Chain(Dense(I,64,act), Dense(64,64,act), Dense(64,O)), I <= 32, O <= 8."""
+    return (len(mlp.acts) == 3 and mlp.dims[1] == 64 and mlp.dims[2] == 64 and 1 <= mlp.dims[0] <= 32 and 1 <= mlp.dims[3] <= 8
+            and mlp.acts[0] == mlp.acts[1] and mlp.acts[0] in (tanh, relu) and mlp.acts[2] == identity)
+
+
 def _as_dev(ctx, x, dtype=torch.float32):
     if isinstance(x, torch.Tensor):
         t = x if x.device == ctx.device else x.to(ctx.device)

@@ -19,7 +19,7 @@ from . import _abi
 from .buffer import ExperienceBuffer, mdp_data, _TORCH
 from .device import ptr
 from .policies import (ActorCritic, ContinuousNetwork, DiscreteNetwork, GaussianPolicy, MixedPolicy, Policy, PolicyParams,
-                       action, actor, critic, exploration)
+                       action, actor, critic, exploration, fusable)
 from .spaces import ContinuousSpace, DiscreteSpace
 
 F32 = np.float32
@@ -185,6 +185,15 @@ class Sampler:
 
     def _rollout_device(self, data, T, explore, i, reset, noise):
         n, env = self.n, self.mdp
+        pe = self.agent.pi_explore
+        ap = actor(pe) if isinstance(pe, (GaussianPolicy, ActorCritic)) else None
+        if (explore and noise is None and isinstance(ap, GaussianPolicy) and not ap.squashed and ap.log_sigma is not None
+                and fusable(ap.mu.mlp) and ap.mu.mlp.dims[0] == env.obs_dim and ap.adim == env.act_dim and hasattr(env, "rollout_into")
+                and not getattr(self, "force_step_kernels", False)):
+            # the whole steps! loop in ONE persistent launch (crux_linquad_rollout): bit-identical to the per-step kernels below
+            env.rollout_into(ap, T, reset, self.cur, data, self.seed, self.noise_ctr)
+            self.noise_ctr += T
+            return
         s, a, sp, r = data["s"], data["a"], data["sp"], data["r"]
         done, ee, logp = data["done"], data["episode_end"], data.get("logprob")
         s[:n].copy_(self.cur)

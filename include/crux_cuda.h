@@ -316,6 +316,13 @@ int32_t crux_linquad_reset(crux_linquad *env, float *obs_out);
 int32_t crux_linquad_step(crux_linquad *env, const float *obs, const float *a, float *sp, float *r, uint8_t *done,
                           uint8_t *episode_end, float *next_obs, int32_t force_end /* last step of a rollout */);
 
+/* The whole steps! loop (sampler.jl:139-155) of T vector steps for the device env in ONE persistent launch: policy forward,
+ * Gaussian sample + logprob, transition, episode bookkeeping and reset, with the observation tile resident in shared memory.
+ * Bit-identical to T x (crux_rollout_step + crux_linquad_step).  obs_io [N][sdim] (device) is the current observation of every
+ * stream (in/out); columns are device rows [T*N]; noise = device Philox (seed, ctr0 + t). */
+int32_t crux_linquad_rollout(crux_linquad *env, crux_gaussian *actor, int32_t T, int32_t force_end_last, float *obs_io,
+                             const crux_rollout_cols *cols, uint64_t seed, uint64_t ctr0);
+
 /* ------------------------------------------------------------------ multi-GPU (one rank per GPU)
  * NCCL is resolved at run time (dlopen libnccl.so.2).  After crux_nccl_init every gradient produced by
  * crux_*_update / crux_*_train is summed over ranks before Adam and minibatch means use the global count. */

@@ -309,3 +309,27 @@ def test_native_rollout_loop_equals_python_loop(crux, ctx):
     assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][3], outs[1][3])
     ee = host(outs[0][0]["episode_end"]).reshape(T, n)
     assert ee[-1].all() and 0 < ee[:-1].mean() < 0.5
+
+
+def test_persistent_device_rollout_equals_step_kernels(crux, ctx):
+    """crux_linquad_rollout (T vector steps in one persistent launch) is bit-identical to T x (crux_rollout_step +
+    crux_linquad_step): same noise counters, same FMA order, same bookkeeping."""
+    n, T, max_steps = 1000, 20, 7   # not a multiple of the 16-stream CTA tile
+    outs = []
+    for force_steps in (False, True):
+        pi = _actor_critic(crux, ctx, seed=21)
+        env = crux.DeviceLinQuad(n, seed=17, max_steps=max_steps, ctx=ctx)
+        s = crux.Sampler(env, pi, max_steps=max_steps, required_columns=["return", "logprob", "advantage"], lam=0.95, seed=5)
+        s.force_step_kernels = force_steps
+        d1 = {k: v.clone() for k, v in s.steps_(None, Nsteps=n * T, explore=True, reset=True).items()}
+        d2 = {k: v.clone() for k, v in s.steps_(None, Nsteps=n * 3, explore=True, reset=False).items()}
+        outs.append((d1, d2, host(s.cur).copy()))
+    for a, b in zip(outs[0][:2], outs[1][:2]):
+        for k in a:
+            if k in ("logprob", "advantage", "return"):
+                assert_close(host(a[k]), host(b[k]), rtol=1e-6, atol=1e-6, what=k)
+            else:
+                assert torch.equal(a[k], b[k]), f"column {k} differs between the persistent and the per-step rollout"
+    assert np.array_equal(outs[0][2], outs[1][2])
+    ee = host(outs[0][0]["episode_end"]).reshape(T, n)
+    assert ee[-1].all() and ee[max_steps - 1].all() and not ee[0].any()
