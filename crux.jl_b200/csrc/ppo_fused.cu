@@ -628,6 +628,24 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
   }
 }
 
+// `train!` tail (training.jl:18-23) + the loss bookkeeping of the minibatch, one launch:
+//   gnorm = ||all grads||_2 (every CTA recomputes it, identical order -> identical value), NaN -> sticky error flag and no update,
+//   info record (block 0), KL early-stop vote (block 0), Flux Adam on this CTA's slice of the parameters.
+struct AdamArgs {
+  float *p, *g, *m, *v; int n;                       // network parameters
+  float *ls, *ls_g, *ls_m, *ls_v; int A;             // actor only: logΣ vector (A == 0 for a critic)
+  const float *sums;                                 // tail sums (after the optional all-reduce): obj, kl, clip, adv, ret, count
+  double eta, b1, b2, eps;
+  const int *step_dev;
+  float lambda_p, lambda_e, target_kl;
+  int a2c, head;                                     // head 0: actor (ppo/a2c), 1: critic (mse)
+  float *rec;                                        // info record of this minibatch
+  const double *norm_part; int n_norm_part;          // per-CTA sums of squares from the reduce kernel (NULL: recompute)
+  int *ctl; int mb;
+  unsigned int *err_flags;
+};
+__device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int n_blocks);
+
 // sum the per-CTA partials (double accumulation, fixed order: bit-reproducible) -> gradient vector + tail
 //   grads[p]                    p < n_params
 //   grads[n_params + j]         j < 8  : dL/dlogΣ_j           (tail_ls_grad)
@@ -640,7 +658,8 @@ constexpr int RW = 32;  // warps per reduce CTA
 __global__ void __launch_bounds__(RW * 32) reduce_fused_partials_kernel(const float *__restrict__ partials, int nparts, int pstride, int n_params,
                                                                        float *__restrict__ grads, float count, float ls_shift, int n_ls,
                                                                        double *__restrict__ norm_part, int *__restrict__ step_dev,
-                                                                       const int *__restrict__ ctl, int mb) {
+                                                                       const int *__restrict__ ctl, int mb, unsigned int *__restrict__ ticket,
+                                                                       AdamArgs adam, int fuse_adam) {
   if (stopped(ctl, mb)) return;
   __shared__ double sh[RW][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -674,44 +693,45 @@ __global__ void __launch_bounds__(RW * 32) reduce_fused_partials_kernel(const fl
     sq = warp_sum_d(sq);
     if (lane == 0) norm_part[blockIdx.x] = sq;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;
+  if (!fuse_adam) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;
+    return;
+  }
+  // single GPU: no all-reduce follows, so the LAST CTA to finish runs the norm / record / Adam tail right here (one launch less)
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+    if (last) { *ticket = 0u; *step_dev += 1; }
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  adam_body(adam, 0, 1);
 }
 
-// `train!` tail (training.jl:18-23) + the loss bookkeeping of the minibatch, one launch:
-//   gnorm = ||all grads||_2 (every CTA recomputes it, identical order -> identical value), NaN -> sticky error flag and no update,
-//   info record (block 0), KL early-stop vote (block 0), Flux Adam on this CTA's slice of the parameters.
-struct AdamArgs {
-  float *p, *g, *m, *v; int n;                       // network parameters
-  float *ls, *ls_g, *ls_m, *ls_v; int A;             // actor only: logΣ vector (A == 0 for a critic)
-  const float *sums;                                 // tail sums (after the optional all-reduce): obj, kl, clip, adv, ret, count
-  double eta, b1, b2, eps;
-  const int *step_dev;
-  float lambda_p, lambda_e, target_kl;
-  int a2c, head;                                     // head 0: actor (ppo/a2c), 1: critic (mse)
-  float *rec;                                        // info record of this minibatch
-  const double *norm_part; int n_norm_part;          // per-CTA sums of squares from the reduce kernel (NULL: recompute)
-  int *ctl; int mb;
-  unsigned int *err_flags;
-};
-__global__ void __launch_bounds__(256) fused_adam_kernel(AdamArgs a) {
-  if (stopped(a.ctl, a.mb)) return;
-  __shared__ double sh[8];
+// block_rank / n_blocks: the slice of the parameter vector this CTA updates (the norm and the record are computed by every CTA /
+// by CTA 0).  Gradients are read with ld.global.cg: they may have been written by other CTAs of the same launch.
+__device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int n_blocks) {
+  __shared__ double sh[32];
   __shared__ double s_n2, s_c1, s_c2;
+  const int nw = blockDim.x >> 5;
   // ---- gradient norm over (network grads, logΣ grads incl. the entropy term): from the reduce kernel's per-CTA sums of
   //      squares when nothing changed the gradient in between, else recomputed here (after an all-reduce)
   double s = 0.0;
   if (a.norm_part) {
-    for (int i = threadIdx.x; i < a.n_norm_part; i += blockDim.x) s += a.norm_part[i];
+    for (int i = threadIdx.x; i < a.n_norm_part; i += blockDim.x) s += __ldcg(a.norm_part + i);
   } else {
-    for (int i = threadIdx.x; i < a.n; i += blockDim.x) { const double v = (double)a.g[i]; s += v * v; }
-    if (threadIdx.x < a.A) { const double v = (double)a.ls_g[threadIdx.x]; s += v * v; }
+    for (int i = threadIdx.x; i < a.n; i += blockDim.x) { const double v = (double)__ldcg(a.g + i); s += v * v; }
+    if (threadIdx.x < a.A) { const double v = (double)__ldcg(a.ls_g + threadIdx.x); s += v * v; }
   }
   s = warp_sum_d(s);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int q = 0; q < 8; ++q) t += sh[q];
+    for (int q = 0; q < nw; ++q) t += sh[q];
     s_n2 = t;
     const int step = *a.step_dev;  // counts this step (incremented by the reduce kernel)
     s_c1 = 1.0 - pow(a.b1, (double)step);
@@ -720,24 +740,24 @@ __global__ void __launch_bounds__(256) fused_adam_kernel(AdamArgs a) {
   __syncthreads();
   const double n2 = s_n2;
   const bool bad = isnan(n2);
-  // ---- info record + early-stop vote (block 0, before any parameter changes)
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const float cnt = a.sums[5];
+  // ---- info record + early-stop vote (first CTA, before any parameter changes)
+  if (block_rank == 0 && threadIdx.x == 0) {
+    const float cnt = __ldcg(a.sums + 5);
     if (a.head == 0) {
       float sls = 0.f;
       for (int j = 0; j < a.A; ++j) sls += a.ls[j];
       const float entropy = 1.4189385332046727f + sls;          // policies.jl:348
-      const float p_loss = -(a.sums[0] / cnt);
+      const float p_loss = -(__ldcg(a.sums + 0) / cnt);
       a.rec[CRUX_PPO_LOSS] = a.lambda_p * p_loss + a.lambda_e * (-entropy);
       a.rec[CRUX_PPO_ENTROPY] = entropy;
-      const float kl = a.sums[1] / cnt;
+      const float kl = __ldcg(a.sums + 1) / cnt;
       a.rec[CRUX_PPO_KL] = kl;
-      a.rec[CRUX_PPO_CLIP_FRAC] = a.a2c ? 0.f : a.sums[2] / cnt;
-      a.rec[CRUX_PPO_AVG_ADV] = a.sums[3] / cnt;
-      a.rec[CRUX_PPO_AVG_RET] = a.sums[4] / cnt;
+      a.rec[CRUX_PPO_CLIP_FRAC] = a.a2c ? 0.f : __ldcg(a.sums + 2) / cnt;
+      a.rec[CRUX_PPO_AVG_ADV] = __ldcg(a.sums + 3) / cnt;
+      a.rec[CRUX_PPO_AVG_RET] = __ldcg(a.sums + 4) / cnt;
       if (a.ctl && kl > a.target_kl) a.ctl[1] = a.mb + 1;         // this minibatch is still applied; later ones are skipped
     } else {
-      a.rec[CRUX_PPO_LOSS] = a.sums[0] / cnt;
+      a.rec[CRUX_PPO_LOSS] = __ldcg(a.sums + 0) / cnt;
     }
     a.rec[CRUX_PPO_GRAD_NORM] = (float)sqrt(n2);
     a.rec[CRUX_PPO_VALID] = 1.f;
@@ -747,21 +767,26 @@ __global__ void __launch_bounds__(256) fused_adam_kernel(AdamArgs a) {
   __syncthreads();
   // ---- Flux Adam (float32 moments, Float64 scalars)
   const double c1 = s_c1, c2 = s_c2;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
-    const double g = (double)a.g[i];
+  for (int i = block_rank * blockDim.x + threadIdx.x; i < a.n; i += n_blocks * blockDim.x) {
+    const double g = (double)__ldcg(a.g + i);
     const float mt = (float)(a.b1 * (double)a.m[i] + (1.0 - a.b1) * g);
     const float vt = (float)(a.b2 * (double)a.v[i] + (1.0 - a.b2) * g * g);
     a.m[i] = mt; a.v[i] = vt;
     a.p[i] = a.p[i] - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
   }
-  if (blockIdx.x == 0 && threadIdx.x < a.A) {
+  if (block_rank == 0 && threadIdx.x < a.A) {
     const int i = threadIdx.x;
-    const double g = (double)a.ls_g[i];
+    const double g = (double)__ldcg(a.ls_g + i);
     const float mt = (float)(a.b1 * (double)a.ls_m[i] + (1.0 - a.b1) * g);
     const float vt = (float)(a.b2 * (double)a.ls_v[i] + (1.0 - a.b2) * g * g);
     a.ls_m[i] = mt; a.ls_v[i] = vt;
     a.ls[i] = a.ls[i] - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
   }
+}
+
+__global__ void __launch_bounds__(256) fused_adam_kernel(AdamArgs a) {
+  if (stopped(a.ctl, a.mb)) return;
+  adam_body(a, blockIdx.x, gridDim.x);
 }
 
 __global__ void fused_ctl_reset_kernel(int *ctl) { ctl[0] = 0; ctl[1] = 0; }
@@ -887,12 +912,6 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   const int n_out = (int)mlp->n_params + 16;
   const int rblocks = (n_out + 31) / 32;   // <= 1024 doubles of norm_part (n_params <= 6792)
   const float ls_shift = head == 0 ? -hp->lambda_e / (float)ctx->world : 0.f;
-  { CruxTimed timed(ctx, CRUX_T_REDUCE);
-  reduce_fused_partials_kernel<<<rblocks, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
-                                                                   ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb);
-  }
-  CRUX_LAUNCHED(ctx);
-  if (ctx->world > 1) { rc = grads_allreduce(ctx, mlp->grads, mlp->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
   AdamArgs g;
   memset(&g, 0, sizeof(g));
   g.p = mlp->params; g.g = mlp->grads; g.m = mlp->m; g.v = mlp->v; g.n = (int)mlp->n_params;
@@ -901,10 +920,20 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   g.sums = tail_sums(mlp); g.eta = mlp->eta; g.b1 = mlp->beta1; g.b2 = mlp->beta2; g.eps = mlp->eps; g.step_dev = mlp->step_dev;
   g.lambda_p = hp->lambda_p; g.target_kl = hp->target_kl; g.a2c = hp->a2c; g.head = head; g.rec = rec; g.ctl = ctl; g.mb = mb;
   g.err_flags = ctx->flags_dev;
-  if (ctx->world == 1) { g.norm_part = mlp->norm_part; g.n_norm_part = rblocks; }
-  { CruxTimed timed(ctx, CRUX_T_ADAM);
-  fused_adam_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g); }
+  const int fuse_adam = ctx->world == 1 ? 1 : 0;
+  if (fuse_adam) { g.norm_part = mlp->norm_part; g.n_norm_part = rblocks; }
+  { CruxTimed timed(ctx, CRUX_T_REDUCE);
+  reduce_fused_partials_kernel<<<rblocks, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
+                                                                   ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb,
+                                                                   ctx->flags_dev + 2, g, fuse_adam);
+  }
   CRUX_LAUNCHED(ctx);
+  if (!fuse_adam) {
+    rc = grads_allreduce(ctx, mlp->grads, mlp->n_params + CRUX_GRAD_TAIL); if (rc) return rc;
+    { CruxTimed timed(ctx, CRUX_T_ADAM);
+    fused_adam_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g); }
+    CRUX_LAUNCHED(ctx);
+  }
   return CRUX_OK;
 }
 
