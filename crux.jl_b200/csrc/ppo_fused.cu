@@ -920,8 +920,10 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   g.sums = tail_sums(mlp); g.eta = mlp->eta; g.b1 = mlp->beta1; g.b2 = mlp->beta2; g.eps = mlp->eps; g.step_dev = mlp->step_dev;
   g.lambda_p = hp->lambda_p; g.target_kl = hp->target_kl; g.a2c = hp->a2c; g.head = head; g.rec = rec; g.ctl = ctl; g.mb = mb;
   g.err_flags = ctx->flags_dev;
-  const int fuse_adam = ctx->world == 1 ? 1 : 0;
-  if (fuse_adam) { g.norm_part = mlp->norm_part; g.n_norm_part = rblocks; }
+  // Running the Adam tail in the last CTA of the reduce kernel saves a launch but serialises 5.7k double-precision updates on
+  // one SM: measured 20.5 us against 6.5 + 6.9 us for the two separate kernels (profiles/r1_notes.md) -> opt-in only.
+  const int fuse_adam = (ctx->world == 1 && getenv("CRUX_FUSE_ADAM")) ? 1 : 0;
+  if (ctx->world == 1) { g.norm_part = mlp->norm_part; g.n_norm_part = rblocks; }
   { CruxTimed timed(ctx, CRUX_T_REDUCE);
   reduce_fused_partials_kernel<<<rblocks, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
                                                                    ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb,
