@@ -39,7 +39,8 @@ struct crux_ctx {
   float *peer_recv_remote[16] = {nullptr};
   unsigned long long *peer_flags_remote[16] = {nullptr};
   int64_t peer_cap = 0;
-  unsigned long long peer_seq = 0;
+  unsigned long long *peer_seq_dev = nullptr;  // device-resident sequence number of the last completed peer exchange (local flags + 33):
+                                               // kept on the device so that minibatches skipped by the device-side early stop do not advance it
   bool peer_ready = false;
 };
 

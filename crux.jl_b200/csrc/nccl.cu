@@ -54,7 +54,8 @@ struct PeerPtrs { float *recv[16]; unsigned long long *flag[16]; };
 
 // each block pushes a slice of `src` into slot `rank` of every peer, then (last block) publishes the sequence number
 __global__ void peer_push_kernel(const float *__restrict__ src, int64_t n, PeerPtrs peers, int rank, int world, int64_t cap,
-                                 unsigned long long seq, unsigned long long *__restrict__ done_ctr) {
+                                 unsigned long long *__restrict__ seq_dev, unsigned long long *__restrict__ done_ctr) {
+  const unsigned long long seq = *(volatile unsigned long long *)seq_dev + 1ULL;  // read by every CTA before the last one advances it
   const int par = (int)(seq & 1ULL);
   for (int p = 0; p < world; ++p) {
     float *dst = peers.recv[p] + ((int64_t)par * 16 + rank) * cap;
@@ -72,11 +73,13 @@ __global__ void peer_push_kernel(const float *__restrict__ src, int64_t n, PeerP
       volatile unsigned long long *f = peers.flag[p] + par * 16 + rank;
       *f = seq;
     }
+    *seq_dev = seq;
     __threadfence_system();
   }
 }
 __global__ void peer_reduce_kernel(float *__restrict__ dst, int64_t n, const float *__restrict__ recv, volatile unsigned long long *flags,
-                                   int world, int64_t cap, unsigned long long seq) {
+                                   int world, int64_t cap, const unsigned long long *__restrict__ seq_dev) {
+  const unsigned long long seq = *(volatile const unsigned long long *)seq_dev;
   const int par = (int)(seq & 1ULL);
   if (threadIdx.x < world) {
     while (flags[par * 16 + threadIdx.x] < seq) { __nanosleep(100); }
@@ -170,7 +173,7 @@ int32_t crux_peer_init(crux_ctx *ctx, int32_t rank, int32_t world, const uint8_t
     }
     ctx->peer_flags_remote[p] = (unsigned long long *)((char *)ctx->peer_recv_remote[p] + (size_t)32 * ctx->peer_cap * sizeof(float));
   }
-  ctx->peer_seq = 0;
+  ctx->peer_seq_dev = ctx->peer_flags + 33;
   ctx->peer_ready = true;
   return CRUX_OK;
 }
@@ -179,11 +182,10 @@ int32_t crux_peer_allreduce(crux_ctx *ctx, float *buf, int64_t n) {
   CRUX_REQUIRE(ctx, ctx->peer_ready && n <= ctx->peer_cap, "crux_peer_allreduce: not initialised or vector too long");
   PeerPtrs pp;
   for (int p = 0; p < ctx->world; ++p) { pp.recv[p] = ctx->peer_recv_remote[p]; pp.flag[p] = ctx->peer_flags_remote[p]; }
-  const unsigned long long seq = ++ctx->peer_seq;
   const int blocks = (int)i64max(1, i64min(cdiv(n, 1024), 16));
-  peer_push_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, n, pp, ctx->rank, ctx->world, ctx->peer_cap, seq, ctx->peer_flags + 32);
+  peer_push_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, n, pp, ctx->rank, ctx->world, ctx->peer_cap, ctx->peer_seq_dev, ctx->peer_flags + 32);
   CRUX_LAUNCHED(ctx);
-  peer_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, n, ctx->peer_recv, ctx->peer_flags, ctx->world, ctx->peer_cap, seq);
+  peer_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, n, ctx->peer_recv, ctx->peer_flags, ctx->world, ctx->peer_cap, ctx->peer_seq_dev);
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;
 }

@@ -641,10 +641,19 @@ struct AdamArgs {
   int a2c, head;                                     // head 0: actor (ppo/a2c), 1: critic (mse)
   float *rec;                                        // info record of this minibatch
   const double *norm_part; int n_norm_part;          // per-CTA sums of squares from the reduce kernel (NULL: recompute)
+  // fused gradient all-reduce over NVLink peer memory: the gradient is the rank-ordered sum of the slots every rank's reduce
+  // kernel stored into THIS rank's receive buffer (double-buffered by the parity of the device-resident sequence number)
+  int peer, world; int64_t peer_cap;
+  const float *peer_recv; const unsigned long long *peer_flags; const unsigned long long *peer_seq_dev;
   int *ctl; int mb;
   unsigned int *err_flags;
 };
 __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int n_blocks);
+struct PeerOut {   // where the reduce kernel stores this rank's gradient for the fused all-reduce (enabled == 0: local only)
+  float *recv[16]; unsigned long long *flag[16];
+  int world, rank, enabled; int64_t cap;
+  unsigned long long *seq_dev;
+};
 
 // sum the per-CTA partials (double accumulation, fixed order: bit-reproducible) -> gradient vector + tail
 //   grads[p]                    p < n_params
@@ -659,8 +668,16 @@ __global__ void __launch_bounds__(RW * 32) reduce_fused_partials_kernel(const fl
                                                                        float *__restrict__ grads, float count, float ls_shift, int n_ls,
                                                                        double *__restrict__ norm_part, int *__restrict__ step_dev,
                                                                        const int *__restrict__ ctl, int mb, unsigned int *__restrict__ ticket,
-                                                                       AdamArgs adam, int fuse_adam) {
+                                                                       AdamArgs adam, int fuse_adam, PeerOut peer) {
   if (stopped(ctl, mb)) return;
+  unsigned long long pseq = 0ULL;
+  if (peer.enabled) pseq = *(volatile unsigned long long *)peer.seq_dev + 1ULL;   // every CTA reads it before the last one advances it
+  const int64_t pbase = ((int64_t)(pseq & 1ULL) * 16 + peer.rank) * peer.cap;
+  auto emit = [&](int idx, float v) {   // local gradient entry + (fused all-reduce) this rank's slot in every peer's receive buffer
+    grads[idx] = v;
+    if (peer.enabled)
+      for (int q = 0; q < peer.world; ++q) peer.recv[q][pbase + idx] = v;
+  };
   __shared__ double sh[RW][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int p = blockIdx.x * 32 + lane;
@@ -678,20 +695,41 @@ __global__ void __launch_bounds__(RW * 32) reduce_fused_partials_kernel(const fl
       double t = 0.0;
 #pragma unroll
       for (int q = 0; q < RW; ++q) t += sh[q][lane];
-      if (p < n_params) { grads[p] = (float)t; sq = (double)(float)t * (double)(float)t; }
+      if (p < n_params) { emit(p, (float)t); sq = (double)(float)t * (double)(float)t; }
       else if (p < n_params + 8) {
         const int j = p - n_params;
         const float g = (float)t + (j < n_ls ? ls_shift : 0.f);
-        grads[p] = g;
+        emit(p, g);
         if (j < n_ls) sq = (double)g * (double)g;
       } else {
         const int q = p - n_params - 8;
-        if (q < 5) grads[n_params + 64 + q] = (float)t;
-        else if (q == 5) grads[n_params + 64 + 5] = count;
+        if (q < 5) emit(n_params + 64 + q, (float)t);
+        else if (q == 5) emit(n_params + 64 + 5, count);
       }
     }
     sq = warp_sum_d(sq);
     if (lane == 0) norm_part[blockIdx.x] = sq;
+  }
+  if (peer.enabled) {
+    // fused all-reduce, sending side: when the LAST CTA of this kernel has seen every other CTA's stores, it raises this rank's
+    // arrival flag in every peer (the receiving side is the Adam kernel: it sums the slots while it reads the gradient)
+    __shared__ bool plast;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) plast = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (plast && threadIdx.x == 0) {
+      *ticket = 0u;
+      *step_dev += 1;
+      __threadfence_system();
+      for (int q = 0; q < peer.world; ++q) {
+        volatile unsigned long long *f = peer.flag[q] + (int)(pseq & 1ULL) * 16 + peer.rank;
+        *f = pseq;
+      }
+      *peer.seq_dev = pseq;
+      __threadfence_system();
+    }
+    return;
   }
   if (!fuse_adam) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;
@@ -717,14 +755,34 @@ __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int
   __shared__ double sh[32];
   __shared__ double s_n2, s_c1, s_c2;
   const int nw = blockDim.x >> 5;
+  const float *slot0 = nullptr;
+  if (a.peer) {   // wait until every rank's slice has landed in this rank's receive buffer
+    const unsigned long long seq = *(volatile const unsigned long long *)a.peer_seq_dev;
+    const int par = (int)(seq & 1ULL);
+    if ((int)threadIdx.x < a.world) {
+      const volatile unsigned long long *f = a.peer_flags + par * 16 + threadIdx.x;
+      while (*f < seq) { __nanosleep(64); }
+    }
+    __syncthreads();
+    __threadfence_system();
+    slot0 = a.peer_recv + (int64_t)par * 16 * a.peer_cap;
+  }
+  // gradient entry i (network grads, then the tail): local, or the rank-ordered sum of the peers' slots (identical on every rank)
+  auto G = [&](const float *local, int64_t i) -> float {
+    if (!slot0) return __ldcg(local);
+    float sum = 0.f;
+    for (int q = 0; q < a.world; ++q) sum += __ldcv(slot0 + (int64_t)q * a.peer_cap + i);
+    return sum;
+  };
+  const int64_t off_ls = a.n, off_sums = (int64_t)a.n + 64;
   // ---- gradient norm over (network grads, logΣ grads incl. the entropy term): from the reduce kernel's per-CTA sums of
   //      squares when nothing changed the gradient in between, else recomputed here (after an all-reduce)
   double s = 0.0;
   if (a.norm_part) {
     for (int i = threadIdx.x; i < a.n_norm_part; i += blockDim.x) s += __ldcg(a.norm_part + i);
   } else {
-    for (int i = threadIdx.x; i < a.n; i += blockDim.x) { const double v = (double)__ldcg(a.g + i); s += v * v; }
-    if (threadIdx.x < a.A) { const double v = (double)__ldcg(a.ls_g + threadIdx.x); s += v * v; }
+    for (int i = threadIdx.x; i < a.n; i += blockDim.x) { const double v = (double)G(a.g + i, i); s += v * v; }
+    if (threadIdx.x < a.A) { const double v = (double)G(a.ls_g + threadIdx.x, off_ls + threadIdx.x); s += v * v; }
   }
   s = warp_sum_d(s);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
@@ -742,22 +800,22 @@ __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int
   const bool bad = isnan(n2);
   // ---- info record + early-stop vote (first CTA, before any parameter changes)
   if (block_rank == 0 && threadIdx.x == 0) {
-    const float cnt = __ldcg(a.sums + 5);
+    const float cnt = G(a.sums + 5, off_sums + 5);
     if (a.head == 0) {
       float sls = 0.f;
       for (int j = 0; j < a.A; ++j) sls += a.ls[j];
       const float entropy = 1.4189385332046727f + sls;          // policies.jl:348
-      const float p_loss = -(__ldcg(a.sums + 0) / cnt);
+      const float p_loss = -(G(a.sums + 0, off_sums + 0) / cnt);
       a.rec[CRUX_PPO_LOSS] = a.lambda_p * p_loss + a.lambda_e * (-entropy);
       a.rec[CRUX_PPO_ENTROPY] = entropy;
-      const float kl = __ldcg(a.sums + 1) / cnt;
+      const float kl = G(a.sums + 1, off_sums + 1) / cnt;
       a.rec[CRUX_PPO_KL] = kl;
-      a.rec[CRUX_PPO_CLIP_FRAC] = a.a2c ? 0.f : __ldcg(a.sums + 2) / cnt;
-      a.rec[CRUX_PPO_AVG_ADV] = __ldcg(a.sums + 3) / cnt;
-      a.rec[CRUX_PPO_AVG_RET] = __ldcg(a.sums + 4) / cnt;
+      a.rec[CRUX_PPO_CLIP_FRAC] = a.a2c ? 0.f : G(a.sums + 2, off_sums + 2) / cnt;
+      a.rec[CRUX_PPO_AVG_ADV] = G(a.sums + 3, off_sums + 3) / cnt;
+      a.rec[CRUX_PPO_AVG_RET] = G(a.sums + 4, off_sums + 4) / cnt;
       if (a.ctl && kl > a.target_kl) a.ctl[1] = a.mb + 1;         // this minibatch is still applied; later ones are skipped
     } else {
-      a.rec[CRUX_PPO_LOSS] = __ldcg(a.sums + 0) / cnt;
+      a.rec[CRUX_PPO_LOSS] = G(a.sums + 0, off_sums + 0) / cnt;
     }
     a.rec[CRUX_PPO_GRAD_NORM] = (float)sqrt(n2);
     a.rec[CRUX_PPO_VALID] = 1.f;
@@ -768,7 +826,9 @@ __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int
   // ---- Flux Adam (float32 moments, Float64 scalars)
   const double c1 = s_c1, c2 = s_c2;
   for (int i = block_rank * blockDim.x + threadIdx.x; i < a.n; i += n_blocks * blockDim.x) {
-    const double g = (double)__ldcg(a.g + i);
+    const float gf = G(a.g + i, i);
+    if (slot0) a.g[i] = gf;   // keep the local gradient vector observable (crux_mlp_grads_ptr)
+    const double g = (double)gf;
     const float mt = (float)(a.b1 * (double)a.m[i] + (1.0 - a.b1) * g);
     const float vt = (float)(a.b2 * (double)a.v[i] + (1.0 - a.b2) * g * g);
     a.m[i] = mt; a.v[i] = vt;
@@ -776,7 +836,7 @@ __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int
   }
   if (block_rank == 0 && threadIdx.x < a.A) {
     const int i = threadIdx.x;
-    const double g = (double)__ldcg(a.ls_g + i);
+    const double g = (double)G(a.ls_g + i, off_ls + i);
     const float mt = (float)(a.b1 * (double)a.ls_m[i] + (1.0 - a.b1) * g);
     const float vt = (float)(a.b2 * (double)a.ls_v[i] + (1.0 - a.b2) * g * g);
     a.ls_m[i] = mt; a.ls_v[i] = vt;
@@ -924,14 +984,25 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   // one SM: measured 20.5 us against 6.5 + 6.9 us for the two separate kernels (profiles/r1_notes.md) -> opt-in only.
   const int fuse_adam = (ctx->world == 1 && getenv("CRUX_FUSE_ADAM")) ? 1 : 0;
   if (ctx->world == 1) { g.norm_part = mlp->norm_part; g.n_norm_part = rblocks; }
+  // multi-GPU: the gradient all-reduce is fused into these two kernels when the one-shot peer buffers are mapped (crux_peer_init):
+  // the reduce kernel stores its result straight into every peer's receive slot, the Adam kernel sums the slots as it reads.
+  PeerOut po;
+  memset(&po, 0, sizeof(po));
+  const bool use_peer = ctx->world > 1 && ctx->peer_ready && mlp->n_params + CRUX_GRAD_TAIL <= ctx->peer_cap && !getenv("CRUX_NO_PEER_FUSION");
+  if (use_peer) {
+    po.enabled = 1; po.world = ctx->world; po.rank = ctx->rank; po.cap = ctx->peer_cap; po.seq_dev = ctx->peer_seq_dev;
+    for (int q = 0; q < ctx->world; ++q) { po.recv[q] = ctx->peer_recv_remote[q]; po.flag[q] = ctx->peer_flags_remote[q]; }
+    g.peer = 1; g.world = ctx->world; g.peer_cap = ctx->peer_cap; g.peer_recv = ctx->peer_recv; g.peer_flags = ctx->peer_flags;
+    g.peer_seq_dev = ctx->peer_seq_dev;
+  }
   { CruxTimed timed(ctx, CRUX_T_REDUCE);
   reduce_fused_partials_kernel<<<rblocks, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
                                                                    ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb,
-                                                                   ctx->flags_dev + 2, g, fuse_adam);
+                                                                   ctx->flags_dev + 2, g, fuse_adam, po);
   }
   CRUX_LAUNCHED(ctx);
   if (!fuse_adam) {
-    rc = grads_allreduce(ctx, mlp->grads, mlp->n_params + CRUX_GRAD_TAIL); if (rc) return rc;
+    if (!use_peer) { rc = grads_allreduce(ctx, mlp->grads, mlp->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
     { CruxTimed timed(ctx, CRUX_T_ADAM);
     fused_adam_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g); }
     CRUX_LAUNCHED(ctx);

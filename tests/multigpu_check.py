@@ -72,30 +72,44 @@ def main():
             mb = {kk: v[idx] for kk, v in D.items()}
             o.train_step(cr.params(), lambda inf, mb=mb: o.value_mse_loss(cr, mb), opt_c, {})
     # device: every rank starts from the same parameters and sees only its shard
-    rng0 = np.random.default_rng(0)
-    mu0 = o.MLP([17, 64, 64, 6], [1, 1, 0], rng0); cr0 = o.MLP([17, 64, 64, 1], [1, 1, 0], rng0)
+    def ppo_check(tag):
+        rng0 = np.random.default_rng(0)
+        mu0 = o.MLP([17, 64, 64, 6], [1, 1, 0], rng0); cr0 = o.MLP([17, 64, 64, 1], [1, 1, 0], rng0)
 
-    def net(m):
-        return crux.ContinuousNetwork(crux.Chain(*[crux.Dense(m.dims[l], m.dims[l + 1], m.acts[l], m.W[l].detach().numpy(), m.b[l].detach().numpy())
-                                                   for l in range(3)]), ctx=ctx)
-    pol = crux.ActorCritic(crux.GaussianPolicy(net(mu0), ls), net(cr0))
-    pol.A.mu.mlp.set_adam(F32(3e-4)); pol.C.mlp.set_adam(F32(3e-4))
-    sh = slice(rank * n_loc, (rank + 1) * n_loc)
-    d = {k: dev(v[sh]) for k, v in D.items()}
-    hp = crux._abi.PPOHp(eps_clip=0.2, lambda_p=1.0, lambda_e=0.1, target_kl=math.inf, a2c=0, actor_epochs=epochs, actor_batch=ab,
-                         critic_epochs=epochs, critic_batch=ab, actor_max_batches=0, critic_max_batches=0)
-    oa = dev(np.stack(orders_a[rank]).astype(np.int32), torch.int32)
-    oc = dev(np.stack(orders_c[rank]).astype(np.int32), torch.int32)
-    ia = np.zeros((epochs * (n_loc // ab), 8), F32); ic = np.zeros_like(ia)
-    ctx.check(ctx.lib.crux_ppo_update(pol.A.h, pol.C.mlp.h, ptr(d["s"]), ptr(d["a"]), ptr(d["logprob"]), ptr(d["advantage"]), ptr(d["return"]),
-                                      n_loc, C.byref(hp), ptr(oa), ptr(oc), 0, ptr(ia), ptr(ic)))
-    for name, got, want in (("actor", pol.A.mu.mlp.get_flat(), mu.flat()), ("critic", pol.C.mlp.get_flat(), cr.flat())):
-        err = np.abs(got - want)
-        assert err.max() < 2 * 3e-4 * 8 + 2e-6, f"{name}: {err.max()}"
-        assert (err > 2e-6 + 1e-5 * np.abs(want)).mean() < 2e-3, f"{name}: {(err > 2e-6 + 1e-5 * np.abs(want)).sum()} coordinates off"
-        t = dev(got); gl = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(gl, t)
-        assert all(torch.equal(gl[0], g) for g in gl), f"{name}: replicas diverged"
+        def net(m):
+            return crux.ContinuousNetwork(crux.Chain(*[crux.Dense(m.dims[l], m.dims[l + 1], m.acts[l], m.W[l].detach().numpy(), m.b[l].detach().numpy())
+                                                       for l in range(3)]), ctx=ctx)
+        pol = crux.ActorCritic(crux.GaussianPolicy(net(mu0), ls), net(cr0))
+        pol.A.mu.mlp.set_adam(F32(3e-4)); pol.C.mlp.set_adam(F32(3e-4))
+        sh = slice(rank * n_loc, (rank + 1) * n_loc)
+        d = {k: dev(v[sh]) for k, v in D.items()}
+        hp = crux._abi.PPOHp(eps_clip=0.2, lambda_p=1.0, lambda_e=0.1, target_kl=math.inf, a2c=0, actor_epochs=epochs, actor_batch=ab,
+                             critic_epochs=epochs, critic_batch=ab, actor_max_batches=0, critic_max_batches=0)
+        oa = dev(np.stack(orders_a[rank]).astype(np.int32), torch.int32)
+        oc = dev(np.stack(orders_c[rank]).astype(np.int32), torch.int32)
+        ia = np.zeros((epochs * (n_loc // ab), 8), F32); ic = np.zeros_like(ia)
+        ctx.check(ctx.lib.crux_ppo_update(pol.A.h, pol.C.mlp.h, ptr(d["s"]), ptr(d["a"]), ptr(d["logprob"]), ptr(d["advantage"]), ptr(d["return"]),
+                                          n_loc, C.byref(hp), ptr(oa), ptr(oc), 0, ptr(ia), ptr(ic)))
+        assert ia[:, 7].all() and ic[:, 7].all(), f"{tag}: info records not all valid"
+        for name, got, want in (("actor", pol.A.mu.mlp.get_flat(), mu.flat()), ("critic", pol.C.mlp.get_flat(), cr.flat())):
+            err = np.abs(got - want)
+            assert err.max() < 2 * 3e-4 * 8 + 2e-6, f"{tag} {name}: {err.max()}"
+            assert (err > 2e-6 + 1e-5 * np.abs(want)).mean() < 2e-3, f"{tag} {name}: {(err > 2e-6 + 1e-5 * np.abs(want)).sum()} coordinates off"
+            t = dev(got); gl = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(gl, t)
+            assert all(torch.equal(gl[0], g) for g in gl), f"{tag} {name}: replicas diverged"
+        # early stop must be taken identically on every rank (the KL comes from the all-reduced sums)
+        hp2 = crux._abi.PPOHp(eps_clip=0.2, lambda_p=1.0, lambda_e=0.1, target_kl=1e-9, a2c=0, actor_epochs=epochs, actor_batch=ab,
+                              critic_epochs=0, critic_batch=ab, actor_max_batches=0, critic_max_batches=0)
+        ctx.check(ctx.lib.crux_ppo_update(pol.A.h, pol.C.mlp.h, ptr(d["s"]), ptr(d["a"]), ptr(d["logprob"]), ptr(d["advantage"]), ptr(d["return"]),
+                                          n_loc, C.byref(hp2), ptr(oa), ptr(oc), 0, ptr(ia), ptr(ic)))
+        v = torch.tensor(ia[:, 7].copy(), device=ctx.device); gl = [torch.empty_like(v) for _ in range(world)]
+        dist.all_gather(gl, v)
+        assert all(torch.equal(gl[0], g) for g in gl) and ia[0, 7] == 1 and ia[-1, 7] == 0, f"{tag}: early stop diverged {ia[:, 7]}"
+        if rank == 0:
+            print(f"ppo update parity OK ({tag})")
+
+    ppo_check("nccl all-reduce")
 
     # ---- global whitening: every rank whitens its shard with the all-reduced moments
     x = np.random.default_rng(5).standard_normal(4000).astype(F32) * 3 + 1
@@ -114,6 +128,9 @@ def main():
     ctx.check(ctx.lib.crux_peer_init(ctx.h, rank, world, allh))
     dist.barrier()
     allreduce_check("peer", 50)
+    ppo_check("fused peer all-reduce")      # reduce kernel stores into the peers' slots, Adam kernel sums them
+    ppo_check("fused peer all-reduce, 2nd") # after early-stopped (skipped) exchanges: the device sequence numbers stayed in step
+    allreduce_check("peer after ppo", 5)
     # timing of the two paths for the 44 KB gradient payload
     for tag in ("peer",):
         t = dev(np.ones(11213, F32))
