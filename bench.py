@@ -114,7 +114,7 @@ def run_ours(args):
     ctx = crux.Context(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        ctx.init_distributed(rank, world, peer_floats=16384)   # one-shot peer buffers: the gradient all-reduce is fused into the update kernels
+        ctx.init_distributed(rank, world)
     dN = N_ENVS * HORIZON
     hbm_peak, peak_src = peaks()
 

@@ -248,6 +248,17 @@ class ExperienceBuffer:
             out[k] = dst
         return out
 
+    def shuffle_(self, perm=None):
+        """``shuffle!(b)`` :118-124: permutes every column in place (``perm`` 1-based injects ``shuffle(1:length(b))``).  The
+        update kernels never need this (an epoch is an index order consumed by their gather); it exists for API parity."""
+        n = len(self)
+        perm = np.random.permutation(n) + 1 if perm is None else np.asarray(perm, dtype=np.int64)
+        assert sorted(perm.tolist()) == list(range(1, n + 1)), "shuffle!: not a permutation"
+        mb = self.minibatch(perm)
+        for k, v in mb.items():
+            self._cols[k][:n].copy_(v)
+        return self
+
     def isprioritized(self):
         return self.priority_params is not None
 

@@ -19,6 +19,8 @@ struct crux_ctx {
   int num_sms = CRUX_NUM_SMS_DEFAULT;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t side_stream = nullptr;   // concurrent critic epochs of the fused PPO update (single GPU)
+  cudaEvent_t side_fork = nullptr, side_done = nullptr;
   std::string err;
   int64_t launches = 0;
   unsigned int *flags_dev = nullptr;   // sticky device error flags

@@ -68,6 +68,9 @@ int32_t crux_ctx_create(int32_t device, void *stream, crux_ctx **out) {
     if (e != cudaSuccess) { delete ctx; return crux_set_err(nullptr, CRUX_ERR_CUDA, "stream: %s", cudaGetErrorString(e)); }
     ctx->own_stream = true;
   }
+  cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming);
   cudaMalloc((void **)&ctx->flags_dev, sizeof(unsigned int) * 4);
   cudaMemset(ctx->flags_dev, 0, sizeof(unsigned int) * 4);
   cudaMallocHost((void **)&ctx->flags_pinned, sizeof(unsigned int) * 4);
@@ -84,6 +87,9 @@ int32_t crux_ctx_destroy(crux_ctx *ctx) {
   if (ctx->flags_pinned) cudaFreeHost(ctx->flags_pinned);
   if (ctx->peer_recv) cudaFree(ctx->peer_recv);
   if (ctx->peer_flags) cudaFree(ctx->peer_flags);
+  if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+  if (ctx->side_fork) cudaEventDestroy(ctx->side_fork);
+  if (ctx->side_done) cudaEventDestroy(ctx->side_done);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CRUX_OK;

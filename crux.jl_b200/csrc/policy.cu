@@ -181,6 +181,7 @@ int32_t crux_gaussian_destroy(crux_gaussian *p) {
   if (p->log_sigma) cudaFree(p->log_sigma);
   if (p->mb) cudaFree(p->mb);
   if (p->order) cudaFree(p->order);
+  if (p->order2) cudaFree(p->order2);
   if (p->info_actor) cudaFree(p->info_actor);
   if (p->info_critic) cudaFree(p->info_critic);
   if (p->ctl) cudaFree(p->ctl);

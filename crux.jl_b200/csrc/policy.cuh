@@ -18,8 +18,10 @@ struct crux_gaussian {
   // PPO workspace
   float *mb = nullptr;          // gathered minibatch columns
   size_t mb_bytes = 0;
-  int32_t *order = nullptr;     // device-generated permutations
+  int32_t *order = nullptr;     // device-generated permutations (actor epochs)
   size_t order_bytes = 0;
+  int32_t *order2 = nullptr;    // ... critic epochs (they may run concurrently on the side stream)
+  size_t order2_bytes = 0;
   float *info_actor = nullptr, *info_critic = nullptr;
   size_t info_actor_bytes = 0, info_critic_bytes = 0;
   int *ctl = nullptr;           // [0]=skip (actor early stop), [1]=pending stop

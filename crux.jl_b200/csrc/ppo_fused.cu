@@ -988,7 +988,9 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   // the reduce kernel stores its result straight into every peer's receive slot, the Adam kernel sums the slots as it reads.
   PeerOut po;
   memset(&po, 0, sizeof(po));
-  const bool use_peer = ctx->world > 1 && ctx->peer_ready && mlp->n_params + CRUX_GRAD_TAIL <= ctx->peer_cap && !getenv("CRUX_NO_PEER_FUSION");
+  // Measured on 2 x B200 (profiles/r1_notes.md): the fence-based fused exchange costs 22 + 28 us per minibatch against
+  // 10 + 17 (NCCL LL all-reduce) + 9 us -> opt-in (CRUX_PEER_FUSION=1) until it is rebuilt on flag-in-data (LL) stores.
+  const bool use_peer = ctx->world > 1 && ctx->peer_ready && mlp->n_params + CRUX_GRAD_TAIL <= ctx->peer_cap && getenv("CRUX_PEER_FUSION");
   if (use_peer) {
     po.enabled = 1; po.world = ctx->world; po.rank = ctx->rank; po.cap = ctx->peer_cap; po.seq_dev = ctx->peer_seq_dev;
     for (int q = 0; q < ctx->world; ++q) { po.recv[q] = ctx->peer_recv_remote[q]; po.flag[q] = ctx->peer_flags_remote[q]; }
@@ -1030,9 +1032,14 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
   CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(actor->info_critic, 0, ic, ctx->stream));
   if (!order_actor || (nmb_c && !order_critic)) {
     rc = ppo_ensure_bytes(ctx, (void **)&actor->order, &actor->order_bytes, (size_t)n * sizeof(int32_t)); if (rc) return rc;
+    rc = ppo_ensure_bytes(ctx, (void **)&actor->order2, &actor->order2_bytes, (size_t)n * sizeof(int32_t)); if (rc) return rc;
   }
   fused_ctl_reset_kernel<<<1, 1, 0, ctx->stream>>>(actor->ctl);
   CRUX_LAUNCHED(ctx);
+  if (ctx->side_stream) {   // fork point for the concurrent critic epochs: the side stream sees the rollout / whitening / memsets above
+    CRUX_CHECK_CUDA(ctx, cudaEventRecord(ctx->side_fork, ctx->stream));
+    CRUX_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_fork, 0));
+  }
   int64_t total = 0;
   const int64_t maxb_a = hp->actor_max_batches > 0 ? hp->actor_max_batches : INT64_MAX;
   for (int e = 0; e < hp->actor_epochs && total < maxb_a; ++e) {
@@ -1046,18 +1053,34 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
       if (rc) return rc;
     }
   }
+  // The critic epochs depend only on the buffer (not on the actor), so on one GPU they are enqueued on a side stream and run
+  // CONCURRENTLY with the actor epochs: the small reduce / Adam launches of one network hide behind the minibatch kernel of the
+  // other.  Results are exactly those of the sequential order (separate parameters, optimisers, scratch buffers and flags).
+  // With several ranks the exchanges must stay ordered on one stream.
+  cudaStream_t main_stream = ctx->stream;
+  const bool side = ctx->world == 1 && nmb_c > 0 && hp->critic_epochs > 0 && !ctx->timing && !getenv("CRUX_NO_SIDE_STREAM") && ctx->side_stream;
+  if (side) ctx->stream = ctx->side_stream;   // every launch helper below enqueues on ctx->stream
   total = 0;
   const int64_t maxb_c = hp->critic_max_batches > 0 ? hp->critic_max_batches : INT64_MAX;
   for (int e = 0; e < hp->critic_epochs && nmb_c && total < maxb_c; ++e) {
     const int32_t *order;
     if (order_critic) order = order_critic + (int64_t)e * n;
-    else { rc = ppo_fill_order(ctx, actor->order, n, seed ^ 0xC2B2AE3D27D4EB4FULL, (uint32_t)e); if (rc) return rc; order = actor->order; }
+    else {
+      rc = ppo_fill_order(ctx, actor->order2, n, seed ^ 0xC2B2AE3D27D4EB4FULL, (uint32_t)e);
+      if (rc) { ctx->stream = main_stream; return rc; }
+      order = actor->order2;
+    }
     for (int64_t mbi = 0; mbi < nmb_c && total < maxb_c; ++mbi, ++total) {
       const int64_t off = mbi * hp->critic_batch, bm = i64min(hp->critic_batch, n - off);
       float *rec = actor->info_critic + ((int64_t)e * nmb_c + mbi) * CRUX_PPO_INFO_STRIDE;
       rc = fused_minibatch(actor, critic, 1, s, nullptr, nullptr, nullptr, ret, order + off, bm, hp, rec, nullptr, (int)total);
-      if (rc) return rc;
+      if (rc) { ctx->stream = main_stream; return rc; }
     }
+  }
+  if (side) {   // join: everything after the update (info readback, the next rollout) sees both networks updated
+    ctx->stream = main_stream;
+    CRUX_CHECK_CUDA(ctx, cudaEventRecord(ctx->side_done, ctx->side_stream));
+    CRUX_CHECK_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->side_done, 0));
   }
   *handled = 1;
   return CRUX_OK;

@@ -46,6 +46,7 @@ class Sampler:
         self.cur = self.ctx.empty((self.n, self.sdim))   # current observation of every stream (device)
         self._pinned = None
         self._scratch = {}
+        self._carry = np.zeros(self.n, dtype=bool)
         self.reset_()
 
     # ---- reset_sampler! (sampler.jl:31-43) for every stream
@@ -59,6 +60,7 @@ class Sampler:
             self._pinned["obs"][...] = o
             self.ctx.h2d(self.cur, self._pinned["obs"])
         self.episode_length[:] = 0
+        self._carry = np.zeros(self.n, dtype=bool)
 
     def _tovec(self, o):
         """tovec(o, S) spaces.jl:24-25 for a ContinuousSpace: (o - μ)/σ."""
@@ -306,6 +308,48 @@ class Sampler:
         ctx.check(ctx.lib.crux_fill_gae_returns(ctx.h, ptr(data["r"]), ptr(data["done"]), ptr(data["episode_end"]), ptr(vs), ptr(vsp),
                                                 T, n, float(self.gamma), float(0.0 if math.isnan(float(self.lam)) else self.lam),
                                                 ptr(adv), ptr(ret)))
+
+    # ---- episodes! (sampler.jl:175-200): whole episodes only, each one contiguous in the returned columns
+    def episodes_(self, buffer=None, Neps=1, explore=False, i=0, cb=None, return_episodes=False):
+        """Resets every stream, then collects ``Neps`` complete episodes (in stream-major order of completion within chunks of
+        ``max_steps`` vector steps).  Returns the columns (episodes concatenated); with ``return_episodes`` also the 1-based
+        inclusive (start, end) pairs like ``episodes(data)``."""
+        self.reset_()
+        n, T = self.n, self.max_steps
+        picked, pairs, total = [], [], 0
+        cols = None
+        while len(pairs) < Neps:
+            data = {k: v.clone() for k, v in self.steps_(None, Nsteps=n * T, explore=explore, i=i, reset=False).items()}
+            ee = data["episode_end"].reshape(T, n).cpu().numpy().astype(bool)
+            idx = []
+            for e in range(n):
+                start = 0
+                for end in np.flatnonzero(ee[:, e]):
+                    if len(pairs) >= Neps:
+                        break
+                    # an episode that began in a previous chunk is incomplete here: skip a first segment that does not start at a reset
+                    if start == 0 and cols is not None and self._carry[e]:
+                        start = end + 1
+                        continue
+                    rows = np.arange(start, end + 1) * n + e
+                    idx.append(rows)
+                    pairs.append((total + 1, total + len(rows)))
+                    total += len(rows)
+                    start = end + 1
+            self._carry = ~ee[-1]            # streams whose episode continues into the next chunk
+            if idx:
+                sel = torch.as_tensor(np.concatenate(idx), device=self.ctx.device)
+                part = {k: v.index_select(0, sel) for k, v in data.items()}
+                cols = part if cols is None or not picked else {k: torch.cat([cols[k], part[k]]) for k in part}
+                picked.append(True)
+            elif cols is None:
+                cols = {k: v[:0] for k, v in data.items()}
+            i += n * T
+        if cb is not None:
+            cb(cols)
+        if buffer is not None:
+            buffer.push_(cols)
+        return (cols, pairs) if return_episodes else cols
 
     # ---- evaluation helpers (sampler.jl:206-251): mean undiscounted return of greedy episodes on a host env
     def undiscounted_return(self, Neps=10):

@@ -333,3 +333,27 @@ def test_persistent_device_rollout_equals_step_kernels(crux, ctx):
     assert np.array_equal(outs[0][2], outs[1][2])
     ee = host(outs[0][0]["episode_end"]).reshape(T, n)
     assert ee[-1].all() and ee[max_steps - 1].all() and not ee[0].any()
+
+
+def test_episodes_and_shuffle(crux, ctx):
+    # episodes! (sampler.jl:175-200; test/gym/sampler_tests.jl:32-56,94-100) and shuffle! (experience_buffer.jl:118-124)
+    n, max_steps = 4, 6
+    pi = _actor_critic(crux, ctx, seed=2)
+    env = crux.HostLinQuad(n, seed=3)
+    s = crux.Sampler(env, pi, max_steps=max_steps, required_columns=["return", "t"])
+    buf = crux.ExperienceBuffer(crux.ContinuousSpace(17), crux.ContinuousSpace(6), 500, ["return", "t"], ctx=ctx)
+    data, eps = s.episodes_(buf, Neps=7, explore=True, return_episodes=True)
+    assert len(eps) == 7 and eps[0][0] == 1 and eps[-1][1] == data["s"].shape[0] == len(buf)
+    ee = host(data["episode_end"])[:, 0].astype(bool)
+    t = host(data["t"])[:, 0]
+    for a, b in eps:                       # every episode is contiguous, starts at t == 1, ends at its only episode_end flag
+        assert t[a - 1] == 1 and ee[b - 1] and not ee[a - 1:b - 1].any() and b - a + 1 <= max_steps
+        assert np.array_equal(t[a - 1:b], np.arange(1, b - a + 2))
+        sp, s_ = host(data["sp"])[a - 1:b - 1], host(data["s"])[a:b]
+        assert np.array_equal(sp, s_)      # rows chain inside an episode
+    assert buf.episodes() == eps           # episodes(buffer) == episodes from the sampler (test/gym/sampler_tests.jl:94-100)
+    before = {k: host(buf[k]).copy() for k in buf.keys()}
+    perm = np.random.default_rng(0).permutation(len(buf)) + 1
+    buf.shuffle_(perm)
+    for k in buf.keys():
+        assert np.array_equal(host(buf[k]), before[k][perm - 1])
