@@ -28,6 +28,10 @@ struct crux_ctx {
   // generic scratch (grown on demand, stream-ordered reuse)
   void *scratch[8] = {nullptr};
   size_t scratch_bytes[8] = {0};
+  // TMA GAE path (gae_tma.cu): epoch-tagged carry flags + a never-reset work counter in scratch slot 7
+  void *gae_scratch_seen = nullptr;
+  unsigned int gae_epoch = 0, gae_ctr_base = 0;
+  size_t gae_flag_cap = 0;
   // opt-in per-kernel-family device timing (bench.py roofline): event pairs recorded around selected launches
   bool timing = false;
   std::vector<cudaEvent_t> t_start, t_stop;

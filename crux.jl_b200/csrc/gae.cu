@@ -228,6 +228,10 @@ __global__ void normalize_kernel(const float *__restrict__ x, int64_t n, float m
 
 }  // namespace
 
+// gae_tma.cu: TMA-fed streaming scan for large rollouts (*handled = 0 when the shape is not eligible)
+int gae_tma_launch(crux_ctx *ctx, const float *r, const uint8_t *done, const uint8_t *ee, const float *vs, const float *vsp, int64_t T, int64_t N,
+                   float gamma, float lambda, float *adv, float *ret, int *handled);
+
 extern "C" {
 
 int32_t crux_fill_gae_returns(crux_ctx *ctx, const float *r, const uint8_t *done, const uint8_t *episode_end,
@@ -238,6 +242,11 @@ int32_t crux_fill_gae_returns(crux_ctx *ctx, const float *r, const uint8_t *done
   if (T == 0 || N == 0) return CRUX_OK;
   CRUX_REQUIRE(ctx, r && done && episode_end && v_s && v_sp, "crux_fill_gae_returns: NULL input column");
   CRUX_REQUIRE(ctx, adv || ret, "crux_fill_gae_returns: both outputs NULL");
+  {
+    int handled = 0;
+    const int rc = gae_tma_launch(ctx, r, done, episode_end, v_s, v_sp, T, N, gamma, lambda, adv, ret, &handled);
+    if (rc || handled) return rc;
+  }
   const int64_t tiles = cdiv(N, 32);
   // steps per thread L, warps per CTA W -> chunk of W*L steps
   int L, W;

@@ -56,7 +56,8 @@ if os.path.exists(lp):
     for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append(f"| `{k}` | {c} | {v:.1f} | {v / c:.2f} | {100 * v / tot:.1f}% |")
     out.append("")
-for name, title in (("prof_minibatch", "fused_minibatch_kernel (dominant kernel of the step)"), ("prof_gae", "gae_returns_kernel at [2048, 16384] (738 MB)"),
+for name, title in (("prof_minibatch", "fused_minibatch_kernel (dominant kernel of the step)"), ("prof_gae_tma", "gae_tma_kernel at [2048, 16384] (738 MB): TMA-fed streaming scan, the kernel crux_fill_gae_returns runs for N >= 8192"),
+                    ("prof_gae", "gae_returns_kernel at [2048, 16384] (738 MB): register-resident scan (narrow / short rollouts; CRUX_GAE=scan)"),
                     ("prof_forward", "fused_forward_kernel")):
     rep = os.path.join(G, name + ".ncu-rep")
     if not os.path.exists(rep):
@@ -70,7 +71,7 @@ for name, title in (("prof_minibatch", "fused_minibatch_kernel (dominant kernel 
     out.append("")
 # dram traffic per launch of the captured kernels (bench.py reports it as roofline.traffic)
 traffic = {}
-for name, key in (("prof_minibatch", "fused_minibatch_kernel"), ("prof_gae", "gae_returns_kernel")):
+for name, key in (("prof_minibatch", "fused_minibatch_kernel"), ("prof_gae", "gae_returns_kernel"), ("prof_gae_tma", "gae_tma_kernel")):
     rep = os.path.join(G, name + ".ncu-rep")
     if os.path.exists(rep):
         m = metrics(rep, ["dram__bytes_read.sum", "dram__bytes_write.sum"])

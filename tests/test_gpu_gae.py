@@ -116,6 +116,60 @@ def test_full_size_properties(ctx):
     assert np.array_equal(adv2, 2 * adv) and np.array_equal(ret2, 2 * ret)
 
 
+# ---- the TMA-fed streaming scan (gae_tma.cu): forced with CRUX_GAE=tma, segment hand-off exercised through CRUX_GAE_CFG
+@pytest.fixture
+def gae_env(monkeypatch):
+    def set_(mode, cfg=None):
+        monkeypatch.setenv("CRUX_GAE", mode)
+        if cfg:
+            monkeypatch.setenv("CRUX_GAE_CFG", cfg)
+        else:
+            monkeypatch.delenv("CRUX_GAE_CFG", raising=False)
+    return set_
+
+
+@pytest.mark.parametrize("T,N,cfg", [(1, 16, None), (5, 48, None), (64, 128, None), (100, 144, "16,2,1,2"), (257, 272, "16,3,2,2"),
+                                     (300, 4112, "32,2,1,1"), (1000, 1040, "32,4,3,2"), (1024, 4096, None), (2049, 160, "16,4,5,2"),
+                                     (513, 16400, None)])
+def test_tma_path_against_oracle(ctx, gae_env, T, N, cfg):
+    r, done, ee, vs, vsp = _inputs(T, N, seed=T * 7 + N)
+    gae_env("tma", cfg)
+    l0 = ctx.launch_count()
+    adv, ret = _run(ctx, r, done, ee, vs, vsp, 0.99, 0.95)
+    assert ctx.launch_count() - l0 == 1
+    a0, r0 = c_oracle.gae_returns(r, done, ee, vs, vsp, 0.99, 0.95)
+    assert_close(adv, a0, rtol=1e-5, atol=2e-5, what=f"tma advantage [{T},{N}] cfg={cfg}")
+    assert_close(ret, r0, rtol=1e-5, atol=2e-5, what=f"tma return [{T},{N}] cfg={cfg}")
+    # the streaming scan IS the sequential recurrence: identical bits for every tiling / segmentation
+    gae_env("tma", "32,2,1,1")
+    adv2, ret2 = _run(ctx, r, done, ee, vs, vsp, 0.99, 0.95)
+    assert np.array_equal(adv, adv2) and np.array_equal(ret, ret2)
+    # and within tolerance of the register-resident scan kernel
+    gae_env("scan")
+    adv3, ret3 = _run(ctx, r, done, ee, vs, vsp, 0.99, 0.95)
+    assert_close(adv, adv3, rtol=1e-5, atol=2e-5); assert_close(ret, ret3, rtol=1e-5, atol=2e-5)
+
+
+def test_tma_path_single_output_nan_and_fallback(ctx, crux, gae_env):
+    r, done, ee, vs, vsp = _inputs(200, 256, seed=3)
+    a0, r0 = c_oracle.gae_returns(r, done, ee, vs, vsp, 0.9, 0.8)
+    gae_env("tma", "16,3,2,2")
+    adv, _ = _run(ctx, r, done, ee, vs, vsp, 0.9, 0.8, want_ret=False)
+    _, ret = _run(ctx, r, done, ee, vs, vsp, 0.9, 0.8, want_adv=False)
+    assert_close(adv, a0, atol=2e-5); assert_close(ret, r0, atol=2e-5)
+    r[17, 33] = np.nan
+    d = [dev(ctx, x) for x in (r, done, ee, vs, vsp)]
+    out = ctx.empty((200, 256))
+    ctx.check(ctx.lib.crux_fill_gae_returns(ctx.h, p(d[0]), p(d[1]), p(d[2]), p(d[3]), p(d[4]), 200, 256, 0.9, 0.9, p(out), None))
+    with pytest.raises(crux.NaNError):
+        ctx.check_flags()
+    # N not a multiple of 16: not TMA-encodable (u8 row pitch), the scan kernel takes over silently
+    r, done, ee, vs, vsp = _inputs(130, 100, seed=4)
+    adv, ret = _run(ctx, r, done, ee, vs, vsp, 0.99, 0.95)
+    a0, r0 = c_oracle.gae_returns(r, done, ee, vs, vsp, 0.99, 0.95)
+    assert_close(adv, a0, rtol=1e-5, atol=2e-5); assert_close(ret, r0, rtol=1e-5, atol=2e-5)
+
+
 def test_nan_advantage_flag(ctx, crux):
     r, done, ee, vs, vsp = _inputs(16, 8, seed=1)
     r[3, 2] = np.nan
