@@ -48,8 +48,9 @@ template <int RT>
 struct SmemMapT {
   static constexpr int LD = RT + 4;
   static constexpr int P = 0;                       // raw params
-  static constexpr int W2T = P + P_SMEM;            // [64][64]  W2T[j][k] = W2[k][j]
-  static constexpr int W3T = W2T + H * H;           // [8][64]   W3T[o][k] = W3[k][o]
+  static constexpr int W2T = P + P_SMEM;            // [64][64]  W2T[j][k] = W2[k][j]   (tensor-core variant: B fragments of W2^T, see build_w2_fragments)
+  static constexpr int W2F = W2T + H * H;           // [64][64]  tensor-core variant: B fragments of W2
+  static constexpr int W3T = W2F + H * H;           // [8][64]   W3T[o][k] = W3[k][o]
   static constexpr int XT = W3T + MAX_O * H;        // [32][LD]
   static constexpr int H1T = XT + MAX_I * LD;       // [64][LD]
   static constexpr int H2T = H1T + H * LD;          // [64][LD]
@@ -64,7 +65,7 @@ struct SmemMapT {
   static constexpr int TOTAL = MBAR + 2;
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
   static_assert(MBAR % 2 == 0, "mbarrier must be 8-byte aligned");
-  static_assert(W2T % 4 == 0 && XT % 4 == 0 && H1T % 4 == 0 && OT % 4 == 0 && AT % 4 == 0, "16-byte alignment");
+  static_assert(W2T % 4 == 0 && W2F % 4 == 0 && XT % 4 == 0 && H1T % 4 == 0 && OT % 4 == 0 && AT % 4 == 0, "16-byte alignment");
 };
 using SmemMap = SmemMapT<R>;   // offsets that do not depend on the tile height (P, W2T, W3T) are shared by all variants
 constexpr size_t SMEM_BYTES = SmemMapT<R>::BYTES;
@@ -252,6 +253,84 @@ __device__ __forceinline__ float dot4(const float4 &a, const float4 &b, float ac
   return acc;
 }
 
+// ---- tensor-core path for the three 64x64 GEMMs of a 64-row tile (layer-2 forward, layer-2 data backward, dW2) ---------------
+// 3xTF32 split accumulation on mma.sync.m16n8k8: x = hi + lo with hi = rna_tf32(x); acc += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi keeps
+// fp32-level accuracy (measured ~1e-6 relative, experiments/tcgen05_tf32_test.cu) where a single TF32 pass gives ~1e-3.
+// tcgen05 was evaluated for these GEMMs (experiments/tcgen05_layouts_test.cu): with tf32 operands only K-major shared-memory
+// tiles are accepted without the 128B/32B-base swizzle, so the weight-gradient GEMM (contraction over rows) needs a second,
+// transposed hi/lo copy of every activation -- that does not fit next to the row-major copies at M = 128 rows, and M = 64
+// leaves half of the epilogue lanes idle.  The warp-level MMA reads the existing transposed tiles directly.
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], float b0, float b1) {
+  uint32_t bh0, bl0, bh1, bl1;
+  split_tf32(b0, bh0, bl0); split_tf32(b1, bh1, bl1);
+  mma_tf32(c, al, bh0, bh1);   // small terms first
+  mma_tf32(c, ah, bl0, bl1);
+  mma_tf32(c, ah, bh0, bh1);
+}
+// B fragments of the two weight operands, one float2 per (k-step, n-tile, lane): b0 = B[8ks + t][8nt + g], b1 = B[8ks + t + 4][8nt + g]
+//   W2F: B = W2   (layer-2 forward,       C[row][j] = sum_k h1[row][k] W2[k][j])
+//   W2T: B = W2^T (layer-2 data backward, C[row][k] = sum_j dz2[row][j] W2[k][j])
+__device__ __forceinline__ void build_w2_fragments(float *sm, int I) {
+  const float *W2 = sm + SmemMap::P + off_W2(I);
+  float2 *wf = reinterpret_cast<float2 *>(sm + SmemMap::W2F), *wt = reinterpret_cast<float2 *>(sm + SmemMap::W2T);
+  for (int e = threadIdx.x; e < 8 * 8 * 32; e += NT) {
+    const int lane = e & 31, nt = (e >> 5) & 7, ks = e >> 8, g = lane >> 2, t = lane & 3;
+    wf[e] = make_float2(W2[(8 * ks + t) * H + 8 * nt + g], W2[(8 * ks + t + 4) * H + 8 * nt + g]);
+    wt[e] = make_float2(W2[(8 * nt + g) * H + 8 * ks + t], W2[(8 * nt + g) * H + 8 * ks + t + 4]);
+  }
+}
+// acc[q][.] = C[rows 16*(w&3) + {g, g+8}][cols 32*(w>>2) + 8q + {2t, 2t+1}] = sum_{k<64} A^T[k][row] * B[k][col]   (64-row tile, 8 warps)
+__device__ __forceinline__ void gemm_rows_mma(const float *__restrict__ AT, const float2 *__restrict__ WF, float (&acc)[4][4]) {
+  constexpr int LD = R + 4;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int r0 = 16 * (w & 3), wn = w >> 2;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[q][c] = 0.f;
+  const float *ap = AT + t * LD + r0 + g;
+  const float2 *bp = WF + (4 * wn) * 32 + lane;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    uint32_t ah[4], al[4];
+    split_tf32(ap[(8 * ks) * LD], ah[0], al[0]);
+    split_tf32(ap[(8 * ks) * LD + 8], ah[1], al[1]);
+    split_tf32(ap[(8 * ks + 4) * LD], ah[2], al[2]);
+    split_tf32(ap[(8 * ks + 4) * LD + 8], ah[3], al[3]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 b = bp[(ks * 8 + q) * 32];
+      mma3(acc[q], ah, al, b.x, b.y);
+    }
+  }
+}
+// dW[k][j] += sum_{row<64} A^T[k][row] * D^T[j][row];  acc[q][.] = dW[16*(w&3) + {g, g+8}][32*(w>>2) + 8q + {2t, 2t+1}]
+__device__ __forceinline__ void gemm_wgrad_mma(const float *__restrict__ AT, const float *__restrict__ DT, float (&acc)[4][4]) {
+  constexpr int LD = R + 4;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const float *ap = AT + (16 * (w & 3) + g) * LD + t;
+  const float *dp = DT + (32 * (w >> 2) + g) * LD + t;
+#pragma unroll
+  for (int ks = 0; ks < R / 8; ++ks) {
+    uint32_t ah[4], al[4];
+    split_tf32(ap[8 * ks], ah[0], al[0]);
+    split_tf32(ap[8 * LD + 8 * ks], ah[1], al[1]);
+    split_tf32(ap[8 * ks + 4], ah[2], al[2]);
+    split_tf32(ap[8 * LD + 8 * ks + 4], ah[3], al[3]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mma3(acc[q], ah, al, dp[(8 * q) * LD + 8 * ks], dp[(8 * q) * LD + 8 * ks + 4]);
+  }
+}
+
 // ---- tile loads --------------------------------------------------------------------------------------------------------------
 // x^T[i][r] = x[row(r)][i]; rows beyond n are zero.  idx (shared) holds the source row or -1.
 template <int RT>
@@ -408,8 +487,11 @@ __device__ __forceinline__ bool stopped(const int *ctl, int mb) { return ctl && 
 // RT = 64 : 2 CTAs per SM, 4x4 register tiles (small and medium minibatches).
 // RT = 128: 1 CTA per SM, 8x4 register tiles in the forward / data-backward GEMMs: a third fewer shared-memory wavefronts
 //           per FFMA (the 64-row variant is shared-memory-bandwidth bound, profiles/).
-template <int HEAD, int RT>
+// TC = 1 : the three 64x64 GEMMs of a tile (layer-2 forward, layer-2 data backward, dW2) run on the tensor cores (3xTF32 split
+//          accumulation, mma.sync m16n8k8), 64-row tiles only.  TC = 0 is the all-FFMA kernel (CRUX_NO_MMA=1, and the 128-row variant).
+template <int HEAD, int RT, int TC = 0>
 __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(MbArgs a) {
+  static_assert(!TC || RT == R, "the tensor-core path is written for 64-row tiles");
   if (stopped(a.ctl, a.mb)) return;
   using M = SmemMapT<RT>;
   constexpr int LD = M::LD;
@@ -419,6 +501,9 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
   const int t = threadIdx.x;
   stage_params(sm, nd, M::MBAR);
   build_transposes(sm, I, O);
+  if (TC) { __syncthreads(); build_w2_fragments(sm, I); }   // overwrites the plain W2^T copy (unused on this path) with fragment order
+  // tensor-core fragment coordinates of this thread (TC path): rows / k 16*(w&3) + {g, g+8}, columns 32*(w>>2) + 8q + {2t, 2t+1}
+  const int fg = (t & 31) >> 2, ft = t & 3, fr0 = 16 * ((t >> 5) & 3), fc0 = 32 * (t >> 7);
   int *sidx = reinterpret_cast<int *>(sm + M::IDX);
   const float *P = sm + M::P;
   float *XT = sm + M::XT, *H1T = sm + M::H1T, *H2T = sm + M::H2T, *OT = sm + M::OT, *AT = sm + M::AT;
@@ -464,7 +549,20 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
     // ---------------- forward
     layer_fwd<RT>(XT, I, P, P + off_b1(I), H1T, act);
     __syncthreads();
-    layer_fwd<RT>(H1T, H, P + off_W2(I), P + off_b2(I), H2T, act);
+    if (TC) {
+      float c[4][4];
+      gemm_rows_mma(H1T, reinterpret_cast<const float2 *>(sm + M::W2F), c);
+      const float *b2 = P + off_b2(I);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = fc0 + 8 * q + 2 * ft + (e & 1), r = fr0 + fg + 8 * (e >> 1);
+          H2T[j * LD + r] = act_fused(act, c[q][e] + b2[j]);
+        }
+    } else {
+      layer_fwd<RT>(H1T, H, P + off_W2(I), P + off_b2(I), H2T, act);
+    }
     __syncthreads();
     layer_out<RT>(H2T, P + off_W3(I), P + off_b3(I, O), O, OT);
     __syncthreads();
@@ -534,18 +632,22 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
     layer_bwd_data<RT>(OT, O, sm + M::W3T, H2T, act);
     __syncthreads();
     // ---------------- dW2 += h1^T dz2 ; db2
+    if (TC) {
+      gemm_wgrad_mma(H1T, H2T, acc2);
+    } else {
 #pragma unroll 2
-    for (int r4 = 0; r4 < RT / 4; ++r4) {
-      float4 hv[4], zv[4];
+      for (int r4 = 0; r4 < RT / 4; ++r4) {
+        float4 hv[4], zv[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        hv[q] = *reinterpret_cast<const float4 *>(H1T + (kg + 16 * q) * LD + 4 * r4);
-        zv[q] = *reinterpret_cast<const float4 *>(H2T + (jg + 16 * q) * LD + 4 * r4);
+        for (int q = 0; q < 4; ++q) {
+          hv[q] = *reinterpret_cast<const float4 *>(H1T + (kg + 16 * q) * LD + 4 * r4);
+          zv[q] = *reinterpret_cast<const float4 *>(H2T + (jg + 16 * q) * LD + 4 * r4);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc2[i][j] = dot4(hv[i], zv[j], acc2[i][j]);
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc2[i][j] = dot4(hv[i], zv[j], acc2[i][j]);
     }
     if (t < 64) {  // db2[t]
       for (int r4 = 0; r4 < RT / 4; ++r4) {
@@ -555,7 +657,20 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
     }
     __syncthreads();
     // ---------------- dz1^T in place over h1^T
-    layer_bwd_data<RT>(H2T, H, sm + M::W2T, H1T, act);
+    if (TC) {
+      float c[4][4];
+      gemm_rows_mma(H2T, reinterpret_cast<const float2 *>(sm + M::W2T), c);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = fc0 + 8 * q + 2 * ft + (e & 1), r = fr0 + fg + 8 * (e >> 1);
+          float *p = H1T + k * LD + r;
+          *p = c[q][e] * act_bwd_from_out(act, *p);
+        }
+    } else {
+      layer_bwd_data<RT>(H2T, H, sm + M::W2T, H1T, act);
+    }
     __syncthreads();
     // ---------------- dW1 += x^T dz1 ; db1
 #pragma unroll 2
@@ -590,10 +705,17 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
 #pragma unroll
       for (int j = 0; j < 4; ++j) out[ii * H + jg + 16 * j] = acc1[i][j];
   }
+  if (TC) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[off_W2(I) + (kg + 16 * i) * H + jg + 16 * j] = acc2[i][j];
+      for (int e = 0; e < 4; ++e) out[off_W2(I) + (fr0 + fg + 8 * (e >> 1)) * H + fc0 + 8 * q + 2 * ft + (e & 1)] = acc2[q][e];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[off_W2(I) + (kg + 16 * i) * H + jg + 16 * j] = acc2[i][j];
+  }
   {
     const int k = t & 63, og = t >> 6;
     if (og < O) out[off_W3(I) + k * O + og] = acc3[0];
@@ -871,6 +993,8 @@ int set_smem_attr(crux_ctx *ctx) {
   SET_ATTR(fused_forward_kernel<RB>, SmemMapT<RB>::BYTES);
   SET_ATTR((fused_minibatch_kernel<0, R>), SmemMapT<R>::BYTES);
   SET_ATTR((fused_minibatch_kernel<1, R>), SmemMapT<R>::BYTES);
+  SET_ATTR((fused_minibatch_kernel<0, R, 1>), SmemMapT<R>::BYTES);
+  SET_ATTR((fused_minibatch_kernel<1, R, 1>), SmemMapT<R>::BYTES);
   SET_ATTR((fused_minibatch_kernel<0, RB>), SmemMapT<RB>::BYTES);
   SET_ATTR((fused_minibatch_kernel<1, RB>), SmemMapT<RB>::BYTES);
 #undef SET_ATTR
@@ -963,9 +1087,12 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   if (big) {
     if (head == 0) fused_minibatch_kernel<0, RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
     else fused_minibatch_kernel<1, RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
-  } else {
+  } else if (getenv("CRUX_NO_MMA")) {   // all-FFMA variant (A/B reference for the tensor-core path)
     if (head == 0) fused_minibatch_kernel<0, R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
     else fused_minibatch_kernel<1, R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
+  } else {
+    if (head == 0) fused_minibatch_kernel<0, R, 1><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
+    else fused_minibatch_kernel<1, R, 1><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
   }
   }
   CRUX_LAUNCHED(ctx);

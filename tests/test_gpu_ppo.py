@@ -205,3 +205,32 @@ def test_fused_path_equals_generic_engine(ctx, crux):
     assert_params_close(f[2], g[2], 3e-4, 6, what="actor params fused vs generic")
     assert_params_close(f[3], g[3], 3e-4, 2, what="critic params fused vs generic")
     assert_close(f[4], g[4], rtol=1e-5, atol=1e-6, what="forward fused vs generic")
+
+
+def test_tensor_core_path_equals_ffma_path(ctx, crux):
+    """The 3xTF32 tensor-core GEMMs of the fused minibatch kernel (default) against its all-FFMA variant (CRUX_NO_MMA=1):
+    fp32-level agreement on the loss records, the gradient norm and the updated parameters, on a ragged minibatch."""
+    import os
+    n = 5000  # not a multiple of the 64-row tile
+    results = []
+    for no_mma in ("", "1"):
+        if no_mma:
+            os.environ["CRUX_NO_MMA"] = "1"
+        else:
+            os.environ.pop("CRUX_NO_MMA", None)
+        try:
+            rng, pi, cr, handles, D = _setup(ctx, crux, n, seed=99)
+            hp = _hp(crux, actor_batch=2048, critic_batch=2500, actor_epochs=2, critic_epochs=2)
+            oa = _orders(rng, n, 2); oc = _orders(rng, n, 2, start=oa[-1])
+            ia, ic = _run(ctx, crux, handles, D, hp, oa, oc, n)
+            results.append((ia.copy(), ic.copy(), mlp_params(ctx, handles[0]).copy(), mlp_params(ctx, handles[1]).copy()))
+        finally:
+            os.environ.pop("CRUX_NO_MMA", None)
+    tc, ff = results
+    A = crux._abi
+    assert_close(tc[0][:, A.PPO_LOSS], ff[0][:, A.PPO_LOSS], rtol=2e-5, atol=1e-6, what="actor loss tc vs ffma")
+    assert_close(tc[0][:, A.PPO_GRAD_NORM], ff[0][:, A.PPO_GRAD_NORM], rtol=2e-5, what="actor grad norm tc vs ffma")
+    assert_close(tc[1][:, A.PPO_LOSS], ff[1][:, A.PPO_LOSS], rtol=2e-5, what="critic loss tc vs ffma")
+    assert_close(tc[1][:, A.PPO_GRAD_NORM], ff[1][:, A.PPO_GRAD_NORM], rtol=2e-5, what="critic grad norm tc vs ffma")
+    assert_params_close(tc[2], ff[2], 3e-4, 6, what="actor params tc vs ffma")
+    assert_params_close(tc[3], ff[3], 3e-4, 4, what="critic params tc vs ffma")
