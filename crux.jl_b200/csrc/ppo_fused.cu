@@ -48,9 +48,8 @@ template <int RT>
 struct SmemMapT {
   static constexpr int LD = RT + 4;
   static constexpr int P = 0;                       // raw params
-  static constexpr int W2T = P + P_SMEM;            // [64][64]  W2T[j][k] = W2[k][j]   (tensor-core variant: B fragments of W2^T, see build_w2_fragments)
-  static constexpr int W2F = W2T + H * H;           // [64][64]  tensor-core variant: B fragments of W2
-  static constexpr int W3T = W2F + H * H;           // [8][64]   W3T[o][k] = W3[k][o]
+  static constexpr int W2T = P + P_SMEM;            // [64][64]  W2T[j][k] = W2[k][j]
+  static constexpr int W3T = W2T + H * H;           // [8][64]   W3T[o][k] = W3[k][o]
   static constexpr int XT = W3T + MAX_O * H;        // [32][LD]
   static constexpr int H1T = XT + MAX_I * LD;       // [64][LD]
   static constexpr int H2T = H1T + H * LD;          // [64][LD]
@@ -65,7 +64,7 @@ struct SmemMapT {
   static constexpr int TOTAL = MBAR + 2;
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
   static_assert(MBAR % 2 == 0, "mbarrier must be 8-byte aligned");
-  static_assert(W2T % 4 == 0 && W2F % 4 == 0 && XT % 4 == 0 && H1T % 4 == 0 && OT % 4 == 0 && AT % 4 == 0, "16-byte alignment");
+  static_assert(W2T % 4 == 0 && XT % 4 == 0 && H1T % 4 == 0 && OT % 4 == 0 && AT % 4 == 0, "16-byte alignment");
 };
 using SmemMap = SmemMapT<R>;   // offsets that do not depend on the tile height (P, W2T, W3T) are shared by all variants
 constexpr size_t SMEM_BYTES = SmemMapT<R>::BYTES;
@@ -253,15 +252,19 @@ __device__ __forceinline__ float dot4(const float4 &a, const float4 &b, float ac
   return acc;
 }
 
-// ---- tensor-core path for the three 64x64 GEMMs of a 64-row tile (layer-2 forward, layer-2 data backward, dW2) ---------------
+// ---- tensor-core building blocks (fused_minibatch_tc_kernel) -----------------------------------------------------------------
 // 3xTF32 split accumulation on mma.sync.m16n8k8: x = hi + lo with hi = rna_tf32(x); acc += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi keeps
 // fp32-level accuracy (measured ~1e-6 relative, experiments/tcgen05_tf32_test.cu) where a single TF32 pass gives ~1e-3.
 // tcgen05 was evaluated for these GEMMs (experiments/tcgen05_layouts_test.cu): with tf32 operands only K-major shared-memory
-// tiles are accepted without the 128B/32B-base swizzle, so the weight-gradient GEMM (contraction over rows) needs a second,
-// transposed hi/lo copy of every activation -- that does not fit next to the row-major copies at M = 128 rows, and M = 64
-// leaves half of the epilogue lanes idle.  The warp-level MMA reads the existing transposed tiles directly.
+// tiles are accepted without the 128B/32B-base swizzle, so the weight-gradient GEMMs (contraction over rows) would need a
+// second, transposed hi/lo copy of every activation -- that does not fit next to the row-major copies at M = 128 rows, and M = 64
+// leaves half of the epilogue lanes idle.  The warp-level MMA reads the transposed activation tiles [feature][row] directly,
+// both as A^T (contraction over features) and as A / B (contraction over rows).
+// hi = x rounded to tf32 (10 explicit mantissa bits), nearest with ties away -- the value cvt.rna.tf32.f32 returns for every finite
+// x, in two integer instructions (on sm_100a the cvt itself expands to five: add, |x| < inf test, select, mask, ...);
+// lo = x - hi is exact.  Inf stays Inf (lo = NaN propagates like the FFMA kernel's Inf - Inf would).
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -276,49 +279,45 @@ __device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], con
   mma_tf32(c, ah, bl0, bl1);
   mma_tf32(c, ah, bh0, bh1);
 }
-// B fragments of the two weight operands, one float2 per (k-step, n-tile, lane): b0 = B[8ks + t][8nt + g], b1 = B[8ks + t + 4][8nt + g]
-//   W2F: B = W2   (layer-2 forward,       C[row][j] = sum_k h1[row][k] W2[k][j])
-//   W2T: B = W2^T (layer-2 data backward, C[row][k] = sum_j dz2[row][j] W2[k][j])
-__device__ __forceinline__ void build_w2_fragments(float *sm, int I) {
-  const float *W2 = sm + SmemMap::P + off_W2(I);
-  float2 *wf = reinterpret_cast<float2 *>(sm + SmemMap::W2F), *wt = reinterpret_cast<float2 *>(sm + SmemMap::W2T);
-  for (int e = threadIdx.x; e < 8 * 8 * 32; e += NT) {
-    const int lane = e & 31, nt = (e >> 5) & 7, ks = e >> 8, g = lane >> 2, t = lane & 3;
-    wf[e] = make_float2(W2[(8 * ks + t) * H + 8 * nt + g], W2[(8 * ks + t + 4) * H + 8 * nt + g]);
-    wt[e] = make_float2(W2[(8 * nt + g) * H + 8 * ks + t], W2[(8 * nt + g) * H + 8 * ks + t + 4]);
-  }
-}
-// acc[q][.] = C[rows 16*(w&3) + {g, g+8}][cols 32*(w>>2) + 8q + {2t, 2t+1}] = sum_{k<64} A^T[k][row] * B[k][col]   (64-row tile, 8 warps)
-__device__ __forceinline__ void gemm_rows_mma(const float *__restrict__ AT, const float2 *__restrict__ WF, float (&acc)[4][4]) {
+// Fragment coordinates of a lane: g = lane / 4, tq = lane % 4.
+//   A (16x8)  a0 = A[g][tq]       a1 = A[g+8][tq]      a2 = A[g][tq+4]   a3 = A[g+8][tq+4]
+//   B (8x8)   b0 = B[tq][g]       b1 = B[tq+4][g]
+//   C (16x8)  c0 = C[g][2tq]      c1 = C[g][2tq+1]     c2 = C[g+8][2tq]  c3 = C[g+8][2tq+1]
+// Weight operands are kept in shared memory in B-fragment order, one float2 {b0, b1} per (k-step, n-tile, lane).
+//
+// acc[q] = C[rows r0 + {g, g+8}][n-tile q] = sum over `ks_n` k-steps of A^T[k][row] * B[k][col]; A^T = transposed activation tile
+// [k][LD], bp = fragment base of this warp's first n-tile (lane included), ks_stride = float2 per k-step.
+template <int NQ>
+__device__ __forceinline__ void mma_rows(const float *__restrict__ AT, int ks_n, int r0, const float2 *__restrict__ bp, int ks_stride,
+                                         float (&acc)[NQ][4]) {
   constexpr int LD = R + 4;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const int r0 = 16 * (w & 3), wn = w >> 2;
+  const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < NQ; ++q)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[q][c] = 0.f;
-  const float *ap = AT + t * LD + r0 + g;
-  const float2 *bp = WF + (4 * wn) * 32 + lane;
-#pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
+  const float *ap = AT + tq * LD + r0 + g;
+#pragma unroll 4
+  for (int ks = 0; ks < ks_n; ++ks) {
     uint32_t ah[4], al[4];
     split_tf32(ap[(8 * ks) * LD], ah[0], al[0]);
     split_tf32(ap[(8 * ks) * LD + 8], ah[1], al[1]);
     split_tf32(ap[(8 * ks + 4) * LD], ah[2], al[2]);
     split_tf32(ap[(8 * ks + 4) * LD + 8], ah[3], al[3]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 b = bp[(ks * 8 + q) * 32];
+    for (int q = 0; q < NQ; ++q) {
+      const float2 b = bp[ks * ks_stride + q * 32];
       mma3(acc[q], ah, al, b.x, b.y);
     }
   }
 }
-// dW[k][j] += sum_{row<64} A^T[k][row] * D^T[j][row];  acc[q][.] = dW[16*(w&3) + {g, g+8}][32*(w>>2) + 8q + {2t, 2t+1}]
-__device__ __forceinline__ void gemm_wgrad_mma(const float *__restrict__ AT, const float *__restrict__ DT, float (&acc)[4][4]) {
+// acc[q] += dW[m0 + {g, g+8}][n0 + 8q + {2tq, 2tq+1}] = sum_{row<64} A^T[m][row] * D^T[n][row]   (both operands are transposed tiles)
+template <int NQ>
+__device__ __forceinline__ void mma_wgrad(const float *__restrict__ AT, int m0, const float *__restrict__ DT, int n0, float (&acc)[NQ][4]) {
   constexpr int LD = R + 4;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const float *ap = AT + (16 * (w & 3) + g) * LD + t;
-  const float *dp = DT + (32 * (w >> 2) + g) * LD + t;
+  const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  const float *ap = AT + (m0 + g) * LD + tq;
+  const float *dp = DT + (n0 + g) * LD + tq;
 #pragma unroll
   for (int ks = 0; ks < R / 8; ++ks) {
     uint32_t ah[4], al[4];
@@ -327,7 +326,7 @@ __device__ __forceinline__ void gemm_wgrad_mma(const float *__restrict__ AT, con
     split_tf32(ap[8 * ks + 4], ah[2], al[2]);
     split_tf32(ap[8 * LD + 8 * ks + 4], ah[3], al[3]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) mma3(acc[q], ah, al, dp[(8 * q) * LD + 8 * ks], dp[(8 * q) * LD + 8 * ks + 4]);
+    for (int q = 0; q < NQ; ++q) mma3(acc[q], ah, al, dp[(8 * q) * LD + 8 * ks], dp[(8 * q) * LD + 8 * ks + 4]);
   }
 }
 
@@ -487,11 +486,9 @@ __device__ __forceinline__ bool stopped(const int *ctl, int mb) { return ctl && 
 // RT = 64 : 2 CTAs per SM, 4x4 register tiles (small and medium minibatches).
 // RT = 128: 1 CTA per SM, 8x4 register tiles in the forward / data-backward GEMMs: a third fewer shared-memory wavefronts
 //           per FFMA (the 64-row variant is shared-memory-bandwidth bound, profiles/).
-// TC = 1 : the three 64x64 GEMMs of a tile (layer-2 forward, layer-2 data backward, dW2) run on the tensor cores (3xTF32 split
-//          accumulation, mma.sync m16n8k8), 64-row tiles only.  TC = 0 is the all-FFMA kernel (CRUX_NO_MMA=1, and the 128-row variant).
-template <int HEAD, int RT, int TC = 0>
+// The all-FFMA kernel: the A/B reference of the tensor-core kernel below (CRUX_NO_MMA=1) and the 128-row variant (CRUX_RB=1).
+template <int HEAD, int RT>
 __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(MbArgs a) {
-  static_assert(!TC || RT == R, "the tensor-core path is written for 64-row tiles");
   if (stopped(a.ctl, a.mb)) return;
   using M = SmemMapT<RT>;
   constexpr int LD = M::LD;
@@ -501,9 +498,6 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
   const int t = threadIdx.x;
   stage_params(sm, nd, M::MBAR);
   build_transposes(sm, I, O);
-  if (TC) { __syncthreads(); build_w2_fragments(sm, I); }   // overwrites the plain W2^T copy (unused on this path) with fragment order
-  // tensor-core fragment coordinates of this thread (TC path): rows / k 16*(w&3) + {g, g+8}, columns 32*(w>>2) + 8q + {2t, 2t+1}
-  const int fg = (t & 31) >> 2, ft = t & 3, fr0 = 16 * ((t >> 5) & 3), fc0 = 32 * (t >> 7);
   int *sidx = reinterpret_cast<int *>(sm + M::IDX);
   const float *P = sm + M::P;
   float *XT = sm + M::XT, *H1T = sm + M::H1T, *H2T = sm + M::H2T, *OT = sm + M::OT, *AT = sm + M::AT;
@@ -549,20 +543,7 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
     // ---------------- forward
     layer_fwd<RT>(XT, I, P, P + off_b1(I), H1T, act);
     __syncthreads();
-    if (TC) {
-      float c[4][4];
-      gemm_rows_mma(H1T, reinterpret_cast<const float2 *>(sm + M::W2F), c);
-      const float *b2 = P + off_b2(I);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = fc0 + 8 * q + 2 * ft + (e & 1), r = fr0 + fg + 8 * (e >> 1);
-          H2T[j * LD + r] = act_fused(act, c[q][e] + b2[j]);
-        }
-    } else {
-      layer_fwd<RT>(H1T, H, P + off_W2(I), P + off_b2(I), H2T, act);
-    }
+    layer_fwd<RT>(H1T, H, P + off_W2(I), P + off_b2(I), H2T, act);
     __syncthreads();
     layer_out<RT>(H2T, P + off_W3(I), P + off_b3(I, O), O, OT);
     __syncthreads();
@@ -632,22 +613,18 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
     layer_bwd_data<RT>(OT, O, sm + M::W3T, H2T, act);
     __syncthreads();
     // ---------------- dW2 += h1^T dz2 ; db2
-    if (TC) {
-      gemm_wgrad_mma(H1T, H2T, acc2);
-    } else {
 #pragma unroll 2
-      for (int r4 = 0; r4 < RT / 4; ++r4) {
-        float4 hv[4], zv[4];
+    for (int r4 = 0; r4 < RT / 4; ++r4) {
+      float4 hv[4], zv[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          hv[q] = *reinterpret_cast<const float4 *>(H1T + (kg + 16 * q) * LD + 4 * r4);
-          zv[q] = *reinterpret_cast<const float4 *>(H2T + (jg + 16 * q) * LD + 4 * r4);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc2[i][j] = dot4(hv[i], zv[j], acc2[i][j]);
+      for (int q = 0; q < 4; ++q) {
+        hv[q] = *reinterpret_cast<const float4 *>(H1T + (kg + 16 * q) * LD + 4 * r4);
+        zv[q] = *reinterpret_cast<const float4 *>(H2T + (jg + 16 * q) * LD + 4 * r4);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc2[i][j] = dot4(hv[i], zv[j], acc2[i][j]);
     }
     if (t < 64) {  // db2[t]
       for (int r4 = 0; r4 < RT / 4; ++r4) {
@@ -657,20 +634,7 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
     }
     __syncthreads();
     // ---------------- dz1^T in place over h1^T
-    if (TC) {
-      float c[4][4];
-      gemm_rows_mma(H2T, reinterpret_cast<const float2 *>(sm + M::W2T), c);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = fc0 + 8 * q + 2 * ft + (e & 1), r = fr0 + fg + 8 * (e >> 1);
-          float *p = H1T + k * LD + r;
-          *p = c[q][e] * act_bwd_from_out(act, *p);
-        }
-    } else {
-      layer_bwd_data<RT>(H2T, H, sm + M::W2T, H1T, act);
-    }
+    layer_bwd_data<RT>(H2T, H, sm + M::W2T, H1T, act);
     __syncthreads();
     // ---------------- dW1 += x^T dz1 ; db1
 #pragma unroll 2
@@ -705,17 +669,10 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
 #pragma unroll
       for (int j = 0; j < 4; ++j) out[ii * H + jg + 16 * j] = acc1[i][j];
   }
-  if (TC) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) out[off_W2(I) + (fr0 + fg + 8 * (e >> 1)) * H + fc0 + 8 * q + 2 * ft + (e & 1)] = acc2[q][e];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) out[off_W2(I) + (kg + 16 * i) * H + jg + 16 * j] = acc2[i][j];
-  }
+    for (int j = 0; j < 4; ++j) out[off_W2(I) + (kg + 16 * i) * H + jg + 16 * j] = acc2[i][j];
   {
     const int k = t & 63, og = t >> 6;
     if (og < O) out[off_W3(I) + k * O + og] = acc3[0];
@@ -746,6 +703,313 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
     if (src < 5 || src >= 8)
 #pragma unroll
       for (int w = 0; w < RT / 32; ++w) v += red[w * 24 + src];
+    out[a.n_params + t] = v;
+  }
+}
+
+// =================================================================================================== tensor-core minibatch kernel
+// Same contract as fused_minibatch_kernel<HEAD, 64> (same partials layout, same head arithmetic), with EVERY GEMM of the tile on
+// the tensor cores (3xTF32 split accumulation, mma.sync m16n8k8; 8 warps, warp (wm, wn) = (w & 3, w >> 2)):
+//   layer 1      z1[64 x 64]  = x[64 x I]    W1          K = I padded to a multiple of 8 (zero rows)      mma_rows<4>
+//   layer 2      z2[64 x 64]  = h1           W2          K = 64                                           mma_rows<4>
+//   output       o [64 x 8]   = h2           W3          N = O padded to 8 (zero columns), warps 0..3     mma_rows<1>
+//   dz2          [64 x 64]    = dOut[64 x 8] W3^T        K = 8 (one k-step)                               mma_rows<4>
+//   dz1          [64 x 64]    = dz2          W2^T        K = 64                                           mma_rows<4>
+//   dW3 [64 x 8]  += h2^T dOut   (warps 0..3)   dW2 [64 x 64] += h1^T dz2   dW1 [32 x 64] += x^T dz1      mma_wgrad<1/4/2>
+// Weight operands live in shared memory in B-fragment order (built once per CTA; W2's fragments replace W2 inside the staged
+// parameter vector, in place).  Activations stay transposed [feature][row]; bias gradients and the loss head are the FFMA code.
+struct TcMap {
+  static constexpr int LD = R + 4;
+  static constexpr int P = 0;                        // raw parameter vector (TMA destination); W2's slot is rewritten as B fragments of W2
+  static constexpr int W2T = P + P_SMEM;             // [8 ks][8 nt][32] float2 : B fragments of W2^T
+  static constexpr int W1F = W2T + H * H;            // [4 ks][8 nt][32] float2 : B fragments of W1 (rows >= I are zero)
+  static constexpr int W3F = W1F + 4 * 8 * 32 * 2;   // [8 ks][32] float2       : B fragments of W3 (columns >= O are zero)
+  static constexpr int W3TF = W3F + 8 * 32 * 2;      // [8 nt][32] float2       : B fragments of W3^T (k = o < 8; o >= O zero)
+  static constexpr int XT = W3TF + 8 * 32 * 2;       // [32][LD]  rows >= I stay zero
+  static constexpr int H1T = XT + MAX_I * LD;        // [64][LD]
+  static constexpr int H2T = H1T + H * LD;           // [64][LD]
+  static constexpr int OT = H2T + H * LD;            // [8][LD]   outputs, then dL/dout; rows >= O stay zero
+  static constexpr int AT = OT + MAX_O * LD;         // [8][LD]   stored actions
+  static constexpr int LP = AT + MAX_O * LD;
+  static constexpr int ADV = LP + LD;
+  static constexpr int RET = ADV + LD;
+  static constexpr int IDX = RET + LD;               // [R] ints
+  static constexpr int RED = IDX + R;
+  static constexpr int MBAR = RED + 8 * 24;
+  static constexpr int TOTAL = MBAR + 2;
+  static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
+  static_assert(MBAR % 2 == 0 && W2T % 2 == 0 && W1F % 2 == 0 && W3F % 2 == 0 && W3TF % 2 == 0, "8-byte alignment");
+};
+
+template <int HEAD>
+__global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
+  if (stopped(a.ctl, a.mb)) return;
+  using M = TcMap;
+  constexpr int LD = M::LD;
+  extern __shared__ __align__(16) float sm[];
+  const NetDesc nd = a.net;
+  const int I = nd.I, O = nd.O, act = nd.act;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5, g = lane >> 2, tq = lane & 3;
+  const int r0 = 16 * (w & 3), wn = w >> 2;
+  float *XT = sm + M::XT, *H1T = sm + M::H1T, *H2T = sm + M::H2T, *OT = sm + M::OT, *AT = sm + M::AT;
+  int *sidx = reinterpret_cast<int *>(sm + M::IDX);
+  // zero the padding rows the GEMMs read (x^T rows >= I, out^T rows >= O) while the parameters are in flight
+  for (int e = t; e < MAX_I * LD; e += NT) XT[e] = 0.f;
+  for (int e = t; e < MAX_O * LD; e += NT) OT[e] = 0.f;
+  stage_params(sm, nd, M::MBAR);   // ends with every thread having observed the TMA completion
+  const float *P = sm + M::P;
+  {  // ---- weight operands in B-fragment order
+    float *W2 = sm + M::P + off_W2(I);
+    const float *W1 = P, *W3 = P + off_W3(I);
+    float2 f2[8], t2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {   // entry e = (ks, nt, lane')
+      const int e = t + u * NT, l = e & 31, nt = (e >> 5) & 7, ks = e >> 8, gg = l >> 2, tt = l & 3;
+      f2[u] = make_float2(W2[(8 * ks + tt) * H + 8 * nt + gg], W2[(8 * ks + tt + 4) * H + 8 * nt + gg]);       // B = W2
+      t2[u] = make_float2(W2[(8 * nt + gg) * H + 8 * ks + tt], W2[(8 * nt + gg) * H + 8 * ks + tt + 4]);       // B = W2^T
+    }
+    float2 *w1f = reinterpret_cast<float2 *>(sm + M::W1F);
+    for (int e = t; e < 4 * 8 * 32; e += NT) {
+      const int l = e & 31, nt = (e >> 5) & 7, ks = e >> 8, gg = l >> 2, tt = l & 3;
+      const int i0 = 8 * ks + tt, i1 = i0 + 4, j = 8 * nt + gg;
+      w1f[e] = make_float2(i0 < I ? W1[i0 * H + j] : 0.f, i1 < I ? W1[i1 * H + j] : 0.f);
+    }
+    {
+      const int l = t & 31, q = t >> 5, gg = l >> 2, tt = l & 3;   // 256 entries each
+      float2 *w3f = reinterpret_cast<float2 *>(sm + M::W3F), *w3t = reinterpret_cast<float2 *>(sm + M::W3TF);
+      w3f[t] = make_float2(gg < O ? W3[(8 * q + tt) * O + gg] : 0.f, gg < O ? W3[(8 * q + tt + 4) * O + gg] : 0.f);           // B[k][o] = W3[k][o], ks = q
+      w3t[t] = make_float2(tt < O ? W3[(8 * q + gg) * O + tt] : 0.f, tt + 4 < O ? W3[(8 * q + gg) * O + tt + 4] : 0.f);       // B[o][k] = W3[k][o], nt = q
+    }
+    __syncthreads();   // every thread holds its W2 values: the slot can be rewritten
+    float2 *w2f = reinterpret_cast<float2 *>(W2), *w2t = reinterpret_cast<float2 *>(sm + M::W2T);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { w2f[t + u * NT] = f2[u]; w2t[t + u * NT] = t2[u]; }
+  }
+  const float2 *W2F = reinterpret_cast<const float2 *>(sm + M::P + off_W2(I)), *W2TF = reinterpret_cast<const float2 *>(sm + M::W2T);
+  const float2 *W1F = reinterpret_cast<const float2 *>(sm + M::W1F), *W3F = reinterpret_cast<const float2 *>(sm + M::W3F);
+  const float2 *W3TF = reinterpret_cast<const float2 *>(sm + M::W3TF);
+  const int ks1 = (I + 7) >> 3;
+  const uint32_t inv_I = (65536u + (uint32_t)I - 1u) / (uint32_t)I, inv_O = (65536u + (uint32_t)O - 1u) / (uint32_t)O;   // exact e / I for e < 2176
+
+  // per-CTA gradient accumulators (registers, live across all tiles), in C-fragment layout
+  float acc2[4][4], acc1[2][4], acc3[1][4], accb = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { acc2[q][e] = 0.f; if (q < 2) acc1[q][e] = 0.f; if (q < 1) acc3[q][e] = 0.f; }
+  float s_obj = 0.f, s_kl = 0.f, s_clip = 0.f, s_adv = 0.f, s_ret = 0.f, dls[MAX_O];
+#pragma unroll
+  for (int j = 0; j < MAX_O; ++j) dls[j] = 0.f;
+
+  const int64_t n_tiles = (a.bm + R - 1) / R;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();   // the previous tile (and the fragment build) is done with every buffer
+    if (t < R) {
+      const int64_t row = tile * R + t;
+      sidx[t] = row < a.bm ? (a.order ? a.order[row] : (int)row) : -1;
+    }
+    __syncthreads();
+    for (int e = t; e < R * I; e += NT) {
+      const int r = (int)(((uint32_t)e * inv_I) >> 16), i = e - r * I;
+      const int row = sidx[r];
+      XT[i * LD + r] = row >= 0 ? __ldg(a.s + (int64_t)row * I + i) : 0.f;
+    }
+    if (HEAD == 0) {
+      for (int e = t; e < R * O; e += NT) {
+        const int r = (int)(((uint32_t)e * inv_O) >> 16), o = e - r * O;
+        const int row = sidx[r];
+        AT[o * LD + r] = row >= 0 ? __ldg(a.act + (int64_t)row * O + o) : 0.f;
+      }
+      if (t < R) {
+        const int row = sidx[t];
+        sm[M::LP + t] = row >= 0 ? a.logp_old[row] : 0.f;
+        sm[M::ADV + t] = row >= 0 ? a.adv[row] : 0.f;
+        sm[M::RET + t] = (row >= 0 && a.ret) ? a.ret[row] : 0.f;
+      }
+    } else if (t < R) {
+      const int row = sidx[t];
+      sm[M::RET + t] = row >= 0 ? a.ret[row] : 0.f;
+    }
+    __syncthreads();
+    // ---------------- layer 1
+    {
+      float c[4][4];
+      mma_rows<4>(XT, ks1, r0, W1F + (4 * wn) * 32 + lane, 8 * 32, c);
+      const float *b1 = P + off_b1(I);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 32 * wn + 8 * q + 2 * tq + (e & 1), r = r0 + g + 8 * (e >> 1);
+          H1T[j * LD + r] = act_fused(act, c[q][e] + b1[j]);
+        }
+    }
+    __syncthreads();
+    // ---------------- layer 2
+    {
+      float c[4][4];
+      mma_rows<4>(H1T, 8, r0, W2F + (4 * wn) * 32 + lane, 8 * 32, c);
+      const float *b2 = P + off_b2(I);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 32 * wn + 8 * q + 2 * tq + (e & 1), r = r0 + g + 8 * (e >> 1);
+          H2T[j * LD + r] = act_fused(act, c[q][e] + b2[j]);
+        }
+    }
+    __syncthreads();
+    // ---------------- output layer (warps 0..3: one 16-row m-tile each, a single n-tile of 8 outputs)
+    if (w < 4) {
+      float c[1][4];
+      mma_rows<1>(H2T, 8, r0, W3F + lane, 32, c);
+      const float *b3 = P + off_b3(I, O);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int o = 2 * tq + (e & 1), r = r0 + g + 8 * (e >> 1);
+        if (o < O) OT[o * LD + r] = c[0][e] + b3[o];
+      }
+    }
+    __syncthreads();
+    // ---------------- loss head: dL/dout (scaled by 1/B_global) replaces out^T      (identical to fused_minibatch_kernel)
+    if (t < R) {
+      const bool live = sidx[t] >= 0;
+      if (HEAD == 0) {
+        float logp = 0.f;
+        for (int j = 0; j < O; ++j) {
+          const float sg = expf(a.ls[j]);
+          const float d = AT[j * LD + t] - OT[j * LD + t];
+          logp += -(d * d) / (2.f * (sg * sg)) - LOG_SQRT_2PI - a.ls[j];
+        }
+        const float Ai = sm[M::ADV + t], old = sm[M::LP + t];
+        float dlogp = 0.f;
+        if (live) {
+          if (a.a2c) {
+            s_obj += logp * Ai;
+            dlogp = -a.lambda_p * a.inv_bg * Ai;
+          } else {
+            const float rt = expf(logp - old);
+            const float lo = 1.f - a.eps_clip, hi = 1.f + a.eps_clip;
+            const float x = rt * Ai, y = fminf(fmaxf(rt, lo), hi) * Ai;
+            const bool first = !(y < x);  // min(x, y) keeps x on ties
+            s_obj += first ? x : y;
+            dlogp = first ? -a.lambda_p * a.inv_bg * x : 0.f;
+            s_clip += (rt > hi || rt < lo) ? 1.f : 0.f;
+          }
+          s_kl += old - logp; s_adv += Ai; s_ret += sm[M::RET + t];
+        }
+        for (int j = 0; j < O; ++j) {
+          const float sg = expf(a.ls[j]);
+          const float var = sg * sg;
+          const float d = AT[j * LD + t] - OT[j * LD + t];
+          OT[j * LD + t] = dlogp * d / var;
+          dls[j] += dlogp * (d * d / var - 1.f);
+        }
+      } else {
+        const float d = OT[t] - sm[M::RET + t];
+        if (live) s_obj += d * d;
+        OT[t] = live ? 2.f * d * a.inv_bg : 0.f;
+      }
+    }
+    __syncthreads();
+    // ---------------- dW3 += h2^T dOut (warps 0..3) ; db3 ; dz2 = (dOut W3^T) .* act'(h2), accumulated in registers first
+    {
+      if (w < 4) mma_wgrad<1>(H2T, r0, OT, 0, acc3);
+      if (t >= 128 && t < 128 + O) {
+        const int o = t - 128;
+        for (int r4 = 0; r4 < R / 4; ++r4) {
+          const float4 d = *reinterpret_cast<const float4 *>(OT + o * LD + 4 * r4);
+          accb += (d.x + d.y) + (d.z + d.w);
+        }
+      }
+      float c[4][4];
+      mma_rows<4>(OT, 1, r0, W3TF + (4 * wn) * 32 + lane, 0, c);
+      __syncthreads();   // dW3 has read h2^T
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = 32 * wn + 8 * q + 2 * tq + (e & 1), r = r0 + g + 8 * (e >> 1);
+          float *p = H2T + k * LD + r;
+          *p = c[q][e] * act_bwd_from_out(act, *p);
+        }
+    }
+    __syncthreads();
+    // ---------------- dW2 += h1^T dz2 ; db2 ; dz1 = (dz2 W2^T) .* act'(h1), accumulated in registers first
+    {
+      mma_wgrad<4>(H1T, r0, H2T, 32 * wn, acc2);
+      if (t < 64) {
+        for (int r4 = 0; r4 < R / 4; ++r4) {
+          const float4 d = *reinterpret_cast<const float4 *>(H2T + t * LD + 4 * r4);
+          accb += (d.x + d.y) + (d.z + d.w);
+        }
+      }
+      float c[4][4];
+      mma_rows<4>(H2T, 8, r0, W2TF + (4 * wn) * 32 + lane, 8 * 32, c);
+      __syncthreads();   // dW2 has read h1^T
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = 32 * wn + 8 * q + 2 * tq + (e & 1), r = r0 + g + 8 * (e >> 1);
+          float *p = H1T + k * LD + r;
+          *p = c[q][e] * act_bwd_from_out(act, *p);
+        }
+    }
+    __syncthreads();
+    // ---------------- dW1 += x^T dz1 (M = 32 input rows: warp = m-tile w & 1, n-tiles 2 (w >> 1) + {0, 1}) ; db1
+    mma_wgrad<2>(XT, 16 * (w & 1), H1T, 16 * (w >> 1), acc1);
+    if (t >= 64 && t < 128) {
+      for (int r4 = 0; r4 < R / 4; ++r4) {
+        const float4 d = *reinterpret_cast<const float4 *>(H1T + (t - 64) * LD + 4 * r4);
+        accb += (d.x + d.y) + (d.z + d.w);
+      }
+    }
+  }
+
+  // ---------------- publish this CTA's partial gradient (same layout as fused_minibatch_kernel)
+  float *out = a.partials + (int64_t)blockIdx.x * a.pstride;
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = 16 * (w & 1) + g + 8 * (e >> 1), j = 16 * (w >> 1) + 8 * q + 2 * tq + (e & 1);
+      if (i < I) out[i * H + j] = acc1[q][e];
+    }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[off_W2(I) + (r0 + g + 8 * (e >> 1)) * H + 32 * wn + 8 * q + 2 * tq + (e & 1)] = acc2[q][e];
+  if (w < 4) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = r0 + g + 8 * (e >> 1), o = 2 * tq + (e & 1);
+      if (o < O) out[off_W3(I) + k * O + o] = acc3[0][e];
+    }
+  }
+  if (t < 64) out[off_b2(I) + t] = accb;
+  else if (t < 128) out[off_b1(I) + (t - 64)] = accb;
+  else if (t < 128 + O) out[off_b3(I, O) + (t - 128)] = accb;
+  // head sums: threads 0..R-1 = the first two warps
+  __syncthreads();
+  float *red = sm + M::RED;
+  if (t < R) {
+    float v;
+    v = warp_sum(s_obj); if (lane == 0) red[w * 24 + 0] = v;
+    v = warp_sum(s_kl); if (lane == 0) red[w * 24 + 1] = v;
+    v = warp_sum(s_clip); if (lane == 0) red[w * 24 + 2] = v;
+    v = warp_sum(s_adv); if (lane == 0) red[w * 24 + 3] = v;
+    v = warp_sum(s_ret); if (lane == 0) red[w * 24 + 4] = v;
+#pragma unroll
+    for (int j = 0; j < MAX_O; ++j) { v = warp_sum(dls[j]); if (lane == 0) red[w * 24 + 8 + j] = v; }
+  }
+  __syncthreads();
+  if (t < 16) {
+    const int src = t < 8 ? 8 + t : t - 8;
+    float v = 0.f;
+    if (src < 5 || src >= 8)
+#pragma unroll
+      for (int ww = 0; ww < R / 32; ++ww) v += red[ww * 24 + src];
     out[a.n_params + t] = v;
   }
 }
@@ -993,8 +1257,8 @@ int set_smem_attr(crux_ctx *ctx) {
   SET_ATTR(fused_forward_kernel<RB>, SmemMapT<RB>::BYTES);
   SET_ATTR((fused_minibatch_kernel<0, R>), SmemMapT<R>::BYTES);
   SET_ATTR((fused_minibatch_kernel<1, R>), SmemMapT<R>::BYTES);
-  SET_ATTR((fused_minibatch_kernel<0, R, 1>), SmemMapT<R>::BYTES);
-  SET_ATTR((fused_minibatch_kernel<1, R, 1>), SmemMapT<R>::BYTES);
+  SET_ATTR(fused_minibatch_tc_kernel<0>, TcMap::BYTES);
+  SET_ATTR(fused_minibatch_tc_kernel<1>, TcMap::BYTES);
   SET_ATTR((fused_minibatch_kernel<0, RB>), SmemMapT<RB>::BYTES);
   SET_ATTR((fused_minibatch_kernel<1, RB>), SmemMapT<RB>::BYTES);
 #undef SET_ATTR
@@ -1091,8 +1355,8 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
     if (head == 0) fused_minibatch_kernel<0, R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
     else fused_minibatch_kernel<1, R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
   } else {
-    if (head == 0) fused_minibatch_kernel<0, R, 1><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
-    else fused_minibatch_kernel<1, R, 1><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
+    if (head == 0) fused_minibatch_tc_kernel<0><<<grid, NT, TcMap::BYTES, ctx->stream>>>(a);
+    else fused_minibatch_tc_kernel<1><<<grid, NT, TcMap::BYTES, ctx->stream>>>(a);
   }
   }
   CRUX_LAUNCHED(ctx);
