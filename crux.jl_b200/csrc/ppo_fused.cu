@@ -733,13 +733,23 @@ struct TcMap {
   static constexpr int LP = AT + MAX_O * LD;
   static constexpr int ADV = LP + LD;
   static constexpr int RET = ADV + LD;
-  static constexpr int IDX = RET + LD;               // [R] ints
-  static constexpr int RED = IDX + R;
-  static constexpr int MBAR = RED + 8 * 24;
+  static constexpr int IDX = RET + LD;               // [R] ints: source rows of the current tile (-1: padding row)
+  static constexpr int IDX2 = IDX + R;               // [R] ints: source rows of this CTA's next tile
+  static constexpr int RED = IDX2 + R;
+  static constexpr int LSC = RED + 8 * 24;           // [8] logΣ_j, [8] σ_j²  (actor head constants)
+  static constexpr int MBAR = LSC + 16;
   static constexpr int TOTAL = MBAR + 2;
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
   static_assert(MBAR % 2 == 0 && W2T % 2 == 0 && W1F % 2 == 0 && W3F % 2 == 0 && W3TF % 2 == 0, "8-byte alignment");
+  // gather staging of the NEXT tile (cp.async, row-major) lives in the h2^T region while that is dead (after dz1 of the current tile,
+  // before layer 2 of the next one): x [R][I] | actions [R][O] | logprob, advantage, return [R] each
+  static constexpr int SX = H2T, SA = SX + R * MAX_I, SH = SA + R * MAX_O;
+  static_assert(SH + 3 * R <= OT, "gather staging must fit in the h2^T region");
 };
+__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src, bool valid) {
+  const int nbytes = valid ? 4 : 0;   // 0 source bytes: the destination is zero-filled, nothing is read
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(nbytes) : "memory");
+}
 
 template <int HEAD>
 __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
@@ -753,9 +763,44 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
   const int r0 = 16 * (w & 3), wn = w >> 2;
   float *XT = sm + M::XT, *H1T = sm + M::H1T, *H2T = sm + M::H2T, *OT = sm + M::OT, *AT = sm + M::AT;
   int *sidx = reinterpret_cast<int *>(sm + M::IDX);
-  // zero the padding rows the GEMMs read (x^T rows >= I, out^T rows >= O) while the parameters are in flight
+  int *sidx2 = reinterpret_cast<int *>(sm + M::IDX2);
+  const uint32_t inv_I = (65536u + (uint32_t)I - 1u) / (uint32_t)I, inv_O = (65536u + (uint32_t)O - 1u) / (uint32_t)O;   // exact e / I for e < 2176
+  // asynchronous gather of the rows listed in sidx2 into the staging area (no registers held, no wait here)
+  auto issue_gather = [&]() {
+    for (int e = t; e < R * I; e += NT) {
+      const int r = (int)(((uint32_t)e * inv_I) >> 16), i = e - r * I;
+      const int row = sidx2[r];
+      cp_async4(sm + M::SX + e, a.s + (row >= 0 ? (int64_t)row * I + i : 0), row >= 0);
+    }
+    if (HEAD == 0)
+      for (int e = t; e < R * O; e += NT) {
+        const int r = (int)(((uint32_t)e * inv_O) >> 16), o = e - r * O;
+        const int row = sidx2[r];
+        cp_async4(sm + M::SA + e, a.act + (row >= 0 ? (int64_t)row * O + o : 0), row >= 0);
+      }
+    if (t < R) {
+      const int row = sidx2[t];
+      if (HEAD == 0) {
+        cp_async4(sm + M::SH + t, a.logp_old + (row >= 0 ? row : 0), row >= 0);
+        cp_async4(sm + M::SH + R + t, a.adv + (row >= 0 ? row : 0), row >= 0);
+      }
+      const bool has_ret = a.ret != nullptr;
+      cp_async4(sm + M::SH + 2 * R + t, has_ret ? a.ret + (row >= 0 ? row : 0) : a.s, has_ret && row >= 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int64_t n_tiles = (a.bm + R - 1) / R;
+  auto tile_row = [&](int64_t tile) -> int {   // source row of this thread's row in `tile` (t < R)
+    const int64_t row = tile * R + t;
+    return (tile < n_tiles && row < a.bm) ? (a.order ? a.order[row] : (int)row) : -1;
+  };
+  // the first tile's rows start streaming in while the parameters are staged and the weight fragments are built;
+  // zero the padding rows the GEMMs read (x^T rows >= I, out^T rows >= O)
+  if (t < R) sidx2[t] = tile_row(blockIdx.x);
   for (int e = t; e < MAX_I * LD; e += NT) XT[e] = 0.f;
   for (int e = t; e < MAX_O * LD; e += NT) OT[e] = 0.f;
+  __syncthreads();
+  issue_gather();
   stage_params(sm, nd, M::MBAR);   // ends with every thread having observed the TMA completion
   const float *P = sm + M::P;
   {  // ---- weight operands in B-fragment order
@@ -789,7 +834,6 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
   const float2 *W1F = reinterpret_cast<const float2 *>(sm + M::W1F), *W3F = reinterpret_cast<const float2 *>(sm + M::W3F);
   const float2 *W3TF = reinterpret_cast<const float2 *>(sm + M::W3TF);
   const int ks1 = (I + 7) >> 3;
-  const uint32_t inv_I = (65536u + (uint32_t)I - 1u) / (uint32_t)I, inv_O = (65536u + (uint32_t)O - 1u) / (uint32_t)O;   // exact e / I for e < 2176
 
   // per-CTA gradient accumulators (registers, live across all tiles), in C-fragment layout
   float acc2[4][4], acc1[2][4], acc3[1][4], accb = 0.f;
@@ -797,39 +841,30 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
   for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int e = 0; e < 4; ++e) { acc2[q][e] = 0.f; if (q < 2) acc1[q][e] = 0.f; if (q < 1) acc3[q][e] = 0.f; }
-  float s_obj = 0.f, s_kl = 0.f, s_clip = 0.f, s_adv = 0.f, s_ret = 0.f, dls[MAX_O];
-#pragma unroll
-  for (int j = 0; j < MAX_O; ++j) dls[j] = 0.f;
+  // head sums: rows on the tq == 0 lanes of warps 0..3; dL/dlogΣ of the outputs {2tq, 2tq+1} on every lane of warps 0..3
+  float s_obj = 0.f, s_kl = 0.f, s_clip = 0.f, s_adv = 0.f, s_ret = 0.f, dls[2] = {0.f, 0.f};
+  if (HEAD == 0 && t < O) {
+    const float ls = a.ls[t], sg = expf(ls);
+    sm[M::LSC + t] = ls; sm[M::LSC + 8 + t] = sg * sg;
+  }
 
-  const int64_t n_tiles = (a.bm + R - 1) / R;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    __syncthreads();   // the previous tile (and the fragment build) is done with every buffer
-    if (t < R) {
-      const int64_t row = tile * R + t;
-      sidx[t] = row < a.bm ? (a.order ? a.order[row] : (int)row) : -1;
-    }
-    __syncthreads();
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();   // this tile's staged rows are visible to everybody; the previous tile is done with every other buffer
+    // next tile's source rows: requested now, stored to shared memory after layer 1 (the load latency hides behind it)
+    const int nidx = t < R ? tile_row(tile + gridDim.x) : -1;
     for (int e = t; e < R * I; e += NT) {
       const int r = (int)(((uint32_t)e * inv_I) >> 16), i = e - r * I;
-      const int row = sidx[r];
-      XT[i * LD + r] = row >= 0 ? __ldg(a.s + (int64_t)row * I + i) : 0.f;
+      XT[i * LD + r] = sm[M::SX + e];
     }
     if (HEAD == 0) {
       for (int e = t; e < R * O; e += NT) {
         const int r = (int)(((uint32_t)e * inv_O) >> 16), o = e - r * O;
-        const int row = sidx[r];
-        AT[o * LD + r] = row >= 0 ? __ldg(a.act + (int64_t)row * O + o) : 0.f;
+        AT[o * LD + r] = sm[M::SA + e];
       }
-      if (t < R) {
-        const int row = sidx[t];
-        sm[M::LP + t] = row >= 0 ? a.logp_old[row] : 0.f;
-        sm[M::ADV + t] = row >= 0 ? a.adv[row] : 0.f;
-        sm[M::RET + t] = (row >= 0 && a.ret) ? a.ret[row] : 0.f;
-      }
-    } else if (t < R) {
-      const int row = sidx[t];
-      sm[M::RET + t] = row >= 0 ? a.ret[row] : 0.f;
+      if (t < R) { sm[M::LP + t] = sm[M::SH + t]; sm[M::ADV + t] = sm[M::SH + R + t]; }
     }
+    if (t < R) { sm[M::RET + t] = sm[M::SH + 2 * R + t]; sidx[t] = sidx2[t]; }
     __syncthreads();
     // ---------------- layer 1
     {
@@ -843,6 +878,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
           const int j = 32 * wn + 8 * q + 2 * tq + (e & 1), r = r0 + g + 8 * (e >> 1);
           H1T[j * LD + r] = act_fused(act, c[q][e] + b1[j]);
         }
+      if (t < R) sidx2[t] = nidx;
     }
     __syncthreads();
     // ---------------- layer 2
@@ -859,56 +895,63 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
         }
     }
     __syncthreads();
-    // ---------------- output layer (warps 0..3: one 16-row m-tile each, a single n-tile of 8 outputs)
+    // ---------------- output layer + loss head on warps 0..3: one 16-row m-tile each, a single n-tile of 8 outputs.  The C fragment
+    //                  puts the outputs {2tq, 2tq+1} of rows g and g+8 in lane (g, tq): the four lanes of a row hold its whole output
+    //                  vector, so ppo_loss / a2c_loss / mse and dL/dout (scaled by 1/B_global) are evaluated straight from the
+    //                  accumulators (two shuffles per row for logpdf) and only dL/dout goes to shared memory (out^T).
     if (w < 4) {
       float c[1][4];
       mma_rows<1>(H2T, 8, r0, W3F + lane, 32, c);
       const float *b3 = P + off_b3(I, O);
+      const float *lsc = sm + M::LSC;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int o = 2 * tq + (e & 1), r = r0 + g + 8 * (e >> 1);
-        if (o < O) OT[o * LD + r] = c[0][e] + b3[o];
-      }
-    }
-    __syncthreads();
-    // ---------------- loss head: dL/dout (scaled by 1/B_global) replaces out^T      (identical to fused_minibatch_kernel)
-    if (t < R) {
-      const bool live = sidx[t] >= 0;
-      if (HEAD == 0) {
-        float logp = 0.f;
-        for (int j = 0; j < O; ++j) {
-          const float sg = expf(a.ls[j]);
-          const float d = AT[j * LD + t] - OT[j * LD + t];
-          logp += -(d * d) / (2.f * (sg * sg)) - LOG_SQRT_2PI - a.ls[j];
-        }
-        const float Ai = sm[M::ADV + t], old = sm[M::LP + t];
-        float dlogp = 0.f;
-        if (live) {
-          if (a.a2c) {
-            s_obj += logp * Ai;
-            dlogp = -a.lambda_p * a.inv_bg * Ai;
-          } else {
-            const float rt = expf(logp - old);
-            const float lo = 1.f - a.eps_clip, hi = 1.f + a.eps_clip;
-            const float x = rt * Ai, y = fminf(fmaxf(rt, lo), hi) * Ai;
-            const bool first = !(y < x);  // min(x, y) keeps x on ties
-            s_obj += first ? x : y;
-            dlogp = first ? -a.lambda_p * a.inv_bg * x : 0.f;
-            s_clip += (rt > hi || rt < lo) ? 1.f : 0.f;
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = r0 + g + 8 * rr;
+        const bool live = sidx[row] >= 0;
+        if (HEAD == 0) {
+          float d[2] = {0.f, 0.f}, part = 0.f;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int o = 2 * tq + u;
+            if (o < O) {
+              d[u] = AT[o * LD + row] - (c[0][2 * rr + u] + b3[o]);
+              part += -(d[u] * d[u]) / (2.f * lsc[8 + o]) - LOG_SQRT_2PI - lsc[o];
+            }
           }
-          s_kl += old - logp; s_adv += Ai; s_ret += sm[M::RET + t];
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          const float logp = part + __shfl_xor_sync(0xffffffffu, part, 2);
+          const float Ai = sm[M::ADV + row], old = sm[M::LP + row];
+          float dlogp = 0.f;
+          if (live) {
+            float obj, clip = 0.f;
+            if (a.a2c) {
+              obj = logp * Ai;
+              dlogp = -a.lambda_p * a.inv_bg * Ai;
+            } else {
+              const float rt = expf(logp - old);
+              const float lo = 1.f - a.eps_clip, hi = 1.f + a.eps_clip;
+              const float x = rt * Ai, y = fminf(fmaxf(rt, lo), hi) * Ai;
+              const bool first = !(y < x);  // min(x, y) keeps x on ties
+              obj = first ? x : y;
+              dlogp = first ? -a.lambda_p * a.inv_bg * x : 0.f;
+              clip = (rt > hi || rt < lo) ? 1.f : 0.f;
+            }
+            if (tq == 0) { s_obj += obj; s_clip += clip; s_kl += old - logp; s_adv += Ai; s_ret += sm[M::RET + row]; }   // once per row
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int o = 2 * tq + u;
+            if (o < O) {
+              const float var = lsc[8 + o];
+              OT[o * LD + row] = dlogp * d[u] / var;
+              dls[u] += dlogp * (d[u] * d[u] / var - 1.f);
+            }
+          }
+        } else if (tq == 0) {   // critic: a single output, held by the tq == 0 lane of the row
+          const float d = (c[0][2 * rr] + b3[0]) - sm[M::RET + row];
+          if (live) s_obj += d * d;
+          OT[row] = live ? 2.f * d * a.inv_bg : 0.f;
         }
-        for (int j = 0; j < O; ++j) {
-          const float sg = expf(a.ls[j]);
-          const float var = sg * sg;
-          const float d = AT[j * LD + t] - OT[j * LD + t];
-          OT[j * LD + t] = dlogp * d / var;
-          dls[j] += dlogp * (d * d / var - 1.f);
-        }
-      } else {
-        const float d = OT[t] - sm[M::RET + t];
-        if (live) s_obj += d * d;
-        OT[t] = live ? 2.f * d * a.inv_bg : 0.f;
       }
     }
     __syncthreads();
@@ -958,6 +1001,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
     }
     __syncthreads();
     // ---------------- dW1 += x^T dz1 (M = 32 input rows: warp = m-tile w & 1, n-tiles 2 (w >> 1) + {0, 1}) ; db1
+    if (tile + gridDim.x < n_tiles) issue_gather();   // h2^T is dead until layer 2 of the next tile: stream the next rows into it
     mma_wgrad<2>(XT, 16 * (w & 1), H1T, 16 * (w >> 1), acc1);
     if (t >= 64 && t < 128) {
       for (int r4 = 0; r4 < R / 4; ++r4) {
@@ -990,10 +1034,10 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
   if (t < 64) out[off_b2(I) + t] = accb;
   else if (t < 128) out[off_b1(I) + (t - 64)] = accb;
   else if (t < 128 + O) out[off_b3(I, O) + (t - 128)] = accb;
-  // head sums: threads 0..R-1 = the first two warps
+  // head sums live in warps 0..3
   __syncthreads();
   float *red = sm + M::RED;
-  if (t < R) {
+  if (w < 4) {
     float v;
     v = warp_sum(s_obj); if (lane == 0) red[w * 24 + 0] = v;
     v = warp_sum(s_kl); if (lane == 0) red[w * 24 + 1] = v;
@@ -1001,15 +1045,20 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
     v = warp_sum(s_adv); if (lane == 0) red[w * 24 + 3] = v;
     v = warp_sum(s_ret); if (lane == 0) red[w * 24 + 4] = v;
 #pragma unroll
-    for (int j = 0; j < MAX_O; ++j) { v = warp_sum(dls[j]); if (lane == 0) red[w * 24 + 8 + j] = v; }
+    for (int u = 0; u < 2; ++u) {   // sum over the rows (g) of the warp: lanes g == 0 end up with output 2tq + u
+      v = dls[u];
+      v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (g == 0) red[w * 24 + 8 + 2 * tq + u] = v;
+    }
   }
   __syncthreads();
   if (t < 16) {
+    // tail layout: [n_params .. +8) = dlogΣ, [n_params+8 .. +16) = obj, kl, clip, adv, ret, 0, 0, 0
     const int src = t < 8 ? 8 + t : t - 8;
     float v = 0.f;
     if (src < 5 || src >= 8)
 #pragma unroll
-      for (int ww = 0; ww < R / 32; ++ww) v += red[ww * 24 + src];
+      for (int ww = 0; ww < 4; ++ww) v += red[ww * 24 + src];
     out[a.n_params + t] = v;
   }
 }
