@@ -250,7 +250,7 @@ def phase_breakdown(crux, ctx, S, env, torch):
     flops_launch = MB * ((fwd_a + bwd_a) + (fwd_c + bwd_c)) / 2.0                      # average of the actor and the critic launch
     mb_ms = fam_ms[0] / max(1, fam_n[0])
     tf = flops_launch / (mb_ms * 1e-3) / 1e12
-    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal fp32 SIMT FFMA peak at max clock (MEASURED_PEAKS has no fp32 figure)
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal fp32 SIMT FFMA peak at max clock (what the all-FFMA variant is bounded by)
     share = fam_ms[0] / 2.0 / acc.sum()
     traffic = None
     try:
@@ -258,12 +258,26 @@ def phase_breakdown(crux, ctx, S, env, torch):
             traffic = json.load(f).get("fused_minibatch_kernel")
     except Exception:
         pass
-    roof = {"kernel": "fused_minibatch_kernel (gather + forward + loss + backward of one 32768-row minibatch; avg of actor and critic launches)",
-            "bound": "fp32-simt", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak, "traffic": traffic,
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        tensor_peak, tensor_src = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"])), "measured dense bf16, sustained (MEASURED_PEAKS.json; the kernel is timed inside a long step)"
+    except Exception:
+        tensor_peak, tensor_src = 1500.0, "fallback (B200_PROFILING.md)"
+    legacy_tf32 = 278.0  # measured on this pool's B200: mma.sync.m16n8k8 tf32 issue rate, experiments/mma_sync_tf32_rate.cu
+    roof = {"kernel": "fused_minibatch_tc_kernel (gather + forward + loss + backward of one 32768-row minibatch; avg of actor and critic launches)",
+            "bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak, "traffic": traffic,
             "flops_per_launch": flops_launch, "ms_per_launch": mb_ms, "launches_per_step": int(fam_n[0]) // 2, "share_of_step": share,
-            "note": "fp32 FFMA path: the 1e-5 parity bar excludes TF32/BF16 MMA, so this kernel is bounded by the fp32 SIMT pipe, not by "
-                    "HBM or the tensor pipe; peak is the NOMINAL 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no fp32 figure). "
-                    "Against the measured bf16 tensor peak the same number is %.4f." % (tf / 1637.1)}
+            "peak_source": tensor_src,
+            "tensor_passes_per_flop": 3, "tensor_tflops_issued": 3 * tf, "legacy_mma_tf32_peak_measured": legacy_tf32,
+            "frac_of_legacy_mma_tf32_peak": 3 * tf / legacy_tf32, "frac_of_fp32_simt_nominal": tf / fp32_peak,
+            "note": "`achieved` counts ALGORITHMIC fp32 FLOPs (2*MAC of the layer shapes, forward + both backward GEMMs). Every GEMM runs on "
+                    "the tensor cores as 3xTF32 split accumulation (hi*hi + hi*lo + lo*hi, fp32-level accuracy for the 1e-5 parity bar), so the "
+                    "tensor pipe issues 3x that. The instruction is the warp-level mma.sync.m16n8k8 (measured ceiling on B200 %.0f TFLOP/s tf32, "
+                    "experiments/mma_sync_tf32_rate.cu), not tcgen05: tf32 MN-major smem operands need the 128B/32B-base swizzle "
+                    "(experiments/tcgen05_layouts_test.cu) and the duplicated hi/lo transposed tiles do not fit at M=128 (DESIGN.md 3). The kernel is "
+                    "issue/latency bound (ncu: issue slots ~33%% busy, barrier + scoreboard stalls), far from any pipe roofline; the all-FFMA "
+                    "variant (CRUX_NO_MMA=1) measured 58.3 us per launch against %.1f us here." % (legacy_tf32, mb_ms * 1e3)}
     return {"phases_ms": {"rollout": acc[0], "values+gae": acc[1], "whiten": acc[2], "update": acc[3]}, "roofline": roof, "kernels": fam}
 
 

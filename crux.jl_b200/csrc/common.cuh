@@ -39,6 +39,7 @@ struct crux_ctx {
   // multi-GPU
   int rank = 0, world = 1;
   void *nccl_comm = nullptr;
+  void *nccl_comm_side = nullptr;       // second communicator (ncclCommSplit): collectives enqueued on side_stream (concurrent critic epochs)
   // peer (IPC) all-reduce state
   float *peer_recv = nullptr;            // [world][peer_cap] receive slots (local)
   unsigned long long *peer_flags = nullptr; // [world] arrival sequence numbers (local)

@@ -20,6 +20,7 @@ typedef int (*fn_getuid)(nccl_uid *);
 typedef int (*fn_initrank)(nccl_comm_t *, int, nccl_uid, int);
 typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t);
 typedef int (*fn_destroy)(nccl_comm_t);
+typedef int (*fn_split)(nccl_comm_t, int, int, nccl_comm_t *, void *);
 typedef const char *(*fn_errstr)(int);
 
 struct NcclApi {
@@ -28,6 +29,7 @@ struct NcclApi {
   fn_initrank init_rank = nullptr;
   fn_allreduce all_reduce = nullptr;
   fn_destroy destroy = nullptr;
+  fn_split split = nullptr;
   fn_errstr err = nullptr;
   std::string why;
 } g_nccl;
@@ -44,6 +46,7 @@ bool load_nccl() {
   g_nccl.init_rank = (fn_initrank)dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.all_reduce = (fn_allreduce)dlsym(g_nccl.lib, "ncclAllReduce");
   g_nccl.destroy = (fn_destroy)dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.split = (fn_split)dlsym(g_nccl.lib, "ncclCommSplit");   // NCCL >= 2.18; optional
   g_nccl.err = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
   if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.all_reduce) { g_nccl.why = "libnccl is missing symbols"; g_nccl.lib = nullptr; return false; }
   return true;
@@ -119,6 +122,12 @@ int32_t crux_nccl_init(crux_ctx *ctx, int32_t rank, int32_t world, const uint8_t
   const int rc = g_nccl.init_rank(&comm, world, id, rank);
   if (rc != 0) return crux_set_err(ctx, CRUX_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.err ? g_nccl.err(rc) : "error");
   ctx->nccl_comm = comm; ctx->rank = rank; ctx->world = world;
+  // A duplicate communicator for the side stream: the critic epochs of the fused PPO update then keep running concurrently with the
+  // actor epochs on several GPUs too (each communicator sees its own collectives in the same order on every rank).
+  if (world > 1 && g_nccl.split && !getenv("CRUX_NO_SIDE_COMM")) {
+    nccl_comm_t side = nullptr;
+    if (g_nccl.split(comm, 0, rank, &side, nullptr) == 0) ctx->nccl_comm_side = side;
+  }
   return CRUX_OK;
 }
 
@@ -129,7 +138,8 @@ int32_t crux_nccl_allreduce_f32(crux_ctx *ctx, float *buf, int64_t n) {
   if (ctx->world <= 1 || n <= 0) return CRUX_OK;
   if (ctx->peer_ready && n <= ctx->peer_cap) return crux_peer_allreduce(ctx, buf, n);
   CRUX_REQUIRE(ctx, ctx->nccl_comm, "crux_nccl_allreduce_f32: NCCL not initialised");
-  const int rc = g_nccl.all_reduce(buf, buf, (size_t)n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, (nccl_comm_t)ctx->nccl_comm, ctx->stream);
+  nccl_comm_t comm = (ctx->stream == ctx->side_stream && ctx->nccl_comm_side) ? (nccl_comm_t)ctx->nccl_comm_side : (nccl_comm_t)ctx->nccl_comm;
+  const int rc = g_nccl.all_reduce(buf, buf, (size_t)n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, ctx->stream);
   if (rc != 0) return crux_set_err(ctx, CRUX_ERR_NCCL, "ncclAllReduce: %s", g_nccl.err ? g_nccl.err(rc) : "error");
   return CRUX_OK;
 }

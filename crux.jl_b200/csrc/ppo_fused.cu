@@ -1063,6 +1063,115 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
   }
 }
 
+// =================================================================================================== tensor-core forward kernel
+// value(π, s) over a whole rollout column (the two critic passes that feed the GAE scan, policies.jl:94-98) on the building blocks of
+// fused_minibatch_tc_kernel: contiguous 64-row tiles streamed in with 16-byte cp.async one tile ahead (staging = the W2^T slot, which
+// a forward pass does not need), three MMA layers, outputs written straight from the accumulators.
+struct FwdTcArgs { NetDesc net; const float *x; int64_t B; float *y; };
+
+template <int DUMMY>
+__global__ void __launch_bounds__(NT, 2) fused_forward_tc_kernel(FwdTcArgs a) {
+  using M = TcMap;
+  constexpr int LD = M::LD;
+  extern __shared__ __align__(16) float sm[];
+  const NetDesc nd = a.net;
+  const int I = nd.I, O = nd.O, act = nd.act;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5, g = lane >> 2, tq = lane & 3;
+  const int r0 = 16 * (w & 3), wn = w >> 2;
+  float *XT = sm + M::XT, *H1T = sm + M::H1T, *H2T = sm + M::H2T, *ST = sm + M::W2T;
+  const int64_t n_tiles = (a.B + R - 1) / R;
+  const int chunks = R * I / 4;   // 16-byte chunks of one tile (R * I is a multiple of 4)
+  auto issue_tile = [&](int64_t tile) {
+    const int64_t f0 = tile * R * I, f_end = a.B * I;   // first float of the tile, end of the column
+    for (int c = t; c < chunks; c += NT) {
+      const int64_t f = f0 + 4 * c;
+      const int64_t left = f_end - f;
+      const int nbytes = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(ST + 4 * c)), "l"(a.x + (nbytes ? f : 0)), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int e = t; e < MAX_I * LD; e += NT) XT[e] = 0.f;
+  issue_tile(blockIdx.x);
+  stage_params(sm, nd, M::MBAR);
+  const float *P = sm + M::P;
+  {  // weight operands in B-fragment order (W2's fragments replace W2 inside the staged parameter vector)
+    float *W2 = sm + M::P + off_W2(I);
+    const float *W1 = P, *W3 = P + off_W3(I);
+    float2 f2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = t + u * NT, l = e & 31, nt = (e >> 5) & 7, ks = e >> 8, gg = l >> 2, tt = l & 3;
+      f2[u] = make_float2(W2[(8 * ks + tt) * H + 8 * nt + gg], W2[(8 * ks + tt + 4) * H + 8 * nt + gg]);
+    }
+    float2 *w1f = reinterpret_cast<float2 *>(sm + M::W1F);
+    for (int e = t; e < 4 * 8 * 32; e += NT) {
+      const int l = e & 31, nt = (e >> 5) & 7, ks = e >> 8, gg = l >> 2, tt = l & 3;
+      const int i0 = 8 * ks + tt, i1 = i0 + 4, j = 8 * nt + gg;
+      w1f[e] = make_float2(i0 < I ? W1[i0 * H + j] : 0.f, i1 < I ? W1[i1 * H + j] : 0.f);
+    }
+    {
+      const int l = t & 31, q = t >> 5, gg = l >> 2, tt = l & 3;
+      reinterpret_cast<float2 *>(sm + M::W3F)[t] = make_float2(gg < O ? W3[(8 * q + tt) * O + gg] : 0.f, gg < O ? W3[(8 * q + tt + 4) * O + gg] : 0.f);
+    }
+    __syncthreads();
+    float2 *w2f = reinterpret_cast<float2 *>(W2);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w2f[t + u * NT] = f2[u];
+  }
+  const float2 *W2F = reinterpret_cast<const float2 *>(sm + M::P + off_W2(I));
+  const float2 *W1F = reinterpret_cast<const float2 *>(sm + M::W1F), *W3F = reinterpret_cast<const float2 *>(sm + M::W3F);
+  const int ks1 = (I + 7) >> 3;
+  const uint32_t inv_I = (65536u + (uint32_t)I - 1u) / (uint32_t)I;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    for (int e = t; e < R * I; e += NT) {
+      const int r = (int)(((uint32_t)e * inv_I) >> 16), i = e - r * I;
+      XT[i * LD + r] = ST[e];
+    }
+    __syncthreads();
+    if (tile + gridDim.x < n_tiles) issue_tile(tile + gridDim.x);
+    {
+      float c[4][4];
+      mma_rows<4>(XT, ks1, r0, W1F + (4 * wn) * 32 + lane, 8 * 32, c);
+      const float *b1 = P + off_b1(I);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 32 * wn + 8 * q + 2 * tq + (e & 1), r = r0 + g + 8 * (e >> 1);
+          H1T[j * LD + r] = act_fused(act, c[q][e] + b1[j]);
+        }
+    }
+    __syncthreads();
+    {
+      float c[4][4];
+      mma_rows<4>(H1T, 8, r0, W2F + (4 * wn) * 32 + lane, 8 * 32, c);
+      const float *b2 = P + off_b2(I);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 32 * wn + 8 * q + 2 * tq + (e & 1), r = r0 + g + 8 * (e >> 1);
+          H2T[j * LD + r] = act_fused(act, c[q][e] + b2[j]);
+        }
+    }
+    __syncthreads();
+    if (w < 4) {
+      float c[1][4];
+      mma_rows<1>(H2T, 8, r0, W3F + lane, 32, c);
+      const float *b3 = P + off_b3(I, O);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int o = 2 * tq + (e & 1);
+        const int64_t row = tile * R + r0 + g + 8 * (e >> 1);
+        if (o < O && row < a.B) a.y[row * O + o] = c[0][e] + b3[o];
+      }
+    }
+  }
+}
+
 // `train!` tail (training.jl:18-23) + the loss bookkeeping of the minibatch, one launch:
 //   gnorm = ||all grads||_2 (every CTA recomputes it, identical order -> identical value), NaN -> sticky error flag and no update,
 //   info record (block 0), KL early-stop vote (block 0), Flux Adam on this CTA's slice of the parameters.
@@ -1306,6 +1415,7 @@ int set_smem_attr(crux_ctx *ctx) {
   SET_ATTR(fused_forward_kernel<RB>, SmemMapT<RB>::BYTES);
   SET_ATTR((fused_minibatch_kernel<0, R>), SmemMapT<R>::BYTES);
   SET_ATTR((fused_minibatch_kernel<1, R>), SmemMapT<R>::BYTES);
+  SET_ATTR(fused_forward_tc_kernel<0>, TcMap::BYTES);
   SET_ATTR(fused_minibatch_tc_kernel<0>, TcMap::BYTES);
   SET_ATTR(fused_minibatch_tc_kernel<1>, TcMap::BYTES);
   SET_ATTR((fused_minibatch_kernel<0, RB>), SmemMapT<RB>::BYTES);
@@ -1342,6 +1452,18 @@ int mlp_forward_fused(crux_mlp *mlp, const float *x, int64_t B, float *y, int *h
   if (!fusable(mlp) || getenv("CRUX_NO_FUSED")) return CRUX_OK;
   crux_ctx *ctx = mlp->ctx;
   int rc = set_smem_attr(ctx); if (rc) return rc;
+  // whole-column passes (at least one 64-row tile per resident CTA) run on the tensor cores; small batches keep the FFMA tiles
+  if (cdiv(B, R) >= (int64_t)ctx->num_sms * 2 && ((uintptr_t)x & 15) == 0 && !getenv("CRUX_NO_MMA")) {
+    FwdTcArgs f;
+    f.net = describe(mlp); f.x = x; f.B = B; f.y = y;
+    {
+      CruxTimed timed(ctx, CRUX_T_FORWARD);
+      fused_forward_tc_kernel<0><<<(unsigned)i64min(cdiv(B, R), (int64_t)ctx->num_sms * 2), NT, TcMap::BYTES, ctx->stream>>>(f);
+    }
+    CRUX_LAUNCHED(ctx);
+    *handled = 1;
+    return CRUX_OK;
+  }
   FwdArgs a;
   memset(&a, 0, sizeof(a));
   a.net[0] = describe(mlp); a.mode[0] = 0; a.x = x; a.B = B; a.y[0] = y;
@@ -1493,12 +1615,14 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
       if (rc) return rc;
     }
   }
-  // The critic epochs depend only on the buffer (not on the actor), so on one GPU they are enqueued on a side stream and run
-  // CONCURRENTLY with the actor epochs: the small reduce / Adam launches of one network hide behind the minibatch kernel of the
+  // The critic epochs depend only on the buffer (not on the actor), so they are enqueued on a side stream and run CONCURRENTLY
+  // with the actor epochs: the small reduce / all-reduce / Adam launches of one network hide behind the minibatch kernel of the
   // other.  Results are exactly those of the sequential order (separate parameters, optimisers, scratch buffers and flags).
-  // With several ranks the exchanges must stay ordered on one stream.
   cudaStream_t main_stream = ctx->stream;
-  const bool side = ctx->world == 1 && nmb_c > 0 && hp->critic_epochs > 0 && !ctx->timing && !getenv("CRUX_NO_SIDE_STREAM") && ctx->side_stream;
+  // With several ranks the critic's gradient all-reduces go through the second communicator (nccl.cu); the single-buffered peer
+  // exchange cannot run two sequences at once.
+  const bool side = (ctx->world == 1 || (ctx->nccl_comm_side && !ctx->peer_ready)) && nmb_c > 0 && hp->critic_epochs > 0 && !ctx->timing &&
+                    !getenv("CRUX_NO_SIDE_STREAM") && ctx->side_stream;
   if (side) ctx->stream = ctx->side_stream;   // every launch helper below enqueues on ctx->stream
   total = 0;
   const int64_t maxb_c = hp->critic_max_batches > 0 ? hp->critic_max_batches : INT64_MAX;
