@@ -84,6 +84,7 @@ _SIGS = {
     "crux_mlp_set_adam": [_vp, _f64, _f64, _f64, _f64],
     "crux_mlp_forward": [_vp, _vp, _i64, _vp],
     "crux_mlp_forward_sa": [_vp, _vp, _i32, _vp, _i32, _i64, _vp],
+    "crux_value_next": [_vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "crux_mlp_copy": [_vp, _vp],
     "crux_mlp_polyak": [_vp, _vp, _f32],
     "crux_mlp_train_mse": [_vp, _vp, _vp, _i64, _vp],

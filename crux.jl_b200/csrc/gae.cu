@@ -172,9 +172,11 @@ __global__ void moments_kernel(const float *__restrict__ x, int64_t n, double *_
 }
 // stats[0]=sum, stats[1]=sumsq, stats[2]=count (float for the NCCL sum; exact below 2^24 per rank... use double pairs)
 __global__ void moments_final_kernel(const double *__restrict__ part, int nparts, int64_t n, float *__restrict__ stats3) {
+  // one warp, fixed order: lane l sums partials l, l+32, ... then a butterfly (deterministic for a given nparts)
+  double s = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += 32) { s += part[2 * i]; s2 += part[2 * i + 1]; }
+  s = warp_sum_d(s); s2 = warp_sum_d(s2);
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0, s2 = 0.0;
-    for (int i = 0; i < nparts; ++i) { s += part[2 * i]; s2 += part[2 * i + 1]; }
     // shift-free f32 triple is too lossy for the variance: keep hi/lo splits of the doubles
     float sh = (float)s, sl = (float)(s - (double)sh);
     float qh = (float)s2, ql = (float)(s2 - (double)qh);

@@ -440,6 +440,7 @@ int32_t crux_mlp_create(crux_ctx *ctx, int32_t n_layers, const int32_t *dims, co
 int32_t crux_mlp_destroy(crux_mlp *m) {
   if (!m) return CRUX_OK;
   cudaStreamSynchronize(m->ctx->stream);
+  if (m->frag) cudaFree(m->frag);
   cudaFree(m->params); cudaFree(m->grads); cudaFree(m->m); cudaFree(m->v); cudaFree(m->step_dev); cudaFree(m->norm_part);
   for (int l = 0; l <= CRUX_MAX_LAYERS; ++l) { if (m->act[l]) cudaFree(m->act[l]); if (m->dz[l]) cudaFree(m->dz[l]); }
   if (m->partials) cudaFree(m->partials);
@@ -493,6 +494,18 @@ int32_t crux_mlp_forward(crux_mlp *m, const float *x, int64_t B, float *y) {
   const int rc = mlp_forward_fused(m, x, B, y, &handled);
   if (rc || handled) return rc;
   return mlp_forward_out(m, x, B, y);
+}
+
+int32_t crux_value_next(crux_mlp *m, const float *sp, const float *s, const float *v_s, int64_t T, int64_t N, float *v_sp) {
+  if (!m) return CRUX_ERR_INVALID;
+  CRUX_REQUIRE(m->ctx, T >= 0 && N >= 0, "crux_value_next: negative shape");
+  if (T == 0 || N == 0) return CRUX_OK;
+  CRUX_REQUIRE(m->ctx, sp && s && v_s && v_sp, "crux_value_next: NULL pointer");
+  CRUX_REQUIRE(m->ctx, m->dims[m->n_layers] == 1, "crux_value_next: needs a value network (one output)");
+  int handled = 0;
+  const int rc = mlp_value_next_fused(m, sp, s, v_s, T, N, v_sp, &handled);
+  if (rc || handled) return rc;
+  return mlp_forward_out(m, sp, T * N, v_sp);
 }
 
 int32_t crux_mlp_forward_sa(crux_mlp *m, const float *s, int32_t sdim, const float *a, int32_t adim, int64_t B, float *y) {

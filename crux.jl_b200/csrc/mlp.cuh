@@ -23,6 +23,10 @@ struct crux_mlp {
   float *partials = nullptr;                      // split-batch weight-gradient partials
   size_t partials_bytes = 0;
   double *norm_part = nullptr;                    // grad-norm partial sums (1024 doubles)
+  // tensor-core PPO update (ppo_fused.cu): the weights in MMA B-fragment order + biases, rebuilt at the start of every
+  // crux_ppo_update and kept in step with `params` by the fused Adam kernel for the rest of that update
+  float *frag = nullptr;
+  size_t frag_bytes = 0;
 };
 
 int mlp_ensure_workspace(crux_mlp *mlp, int64_t B);
@@ -50,3 +54,4 @@ int grads_allreduce(crux_ctx *ctx, float *g, int64_t n);
 // ---- fused fast path (ppo_fused.cu): Chain(Dense(I,64,act), Dense(64,64,act), Dense(64,O)), I <= 32, O <= 8
 // value(π, s) in one launch; *handled == 0 -> the caller runs the generic engine.
 int mlp_forward_fused(crux_mlp *mlp, const float *x, int64_t B, float *y, int *handled);
+int mlp_value_next_fused(crux_mlp *mlp, const float *sp, const float *s, const float *v_s, int64_t T, int64_t N, float *v_sp, int *handled);

@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_minibatch_kernel(M
 //   dW3 [64 x 8]  += h2^T dOut   (warps 0..3)   dW2 [64 x 64] += h1^T dz2   dW1 [32 x 64] += x^T dz1      mma_wgrad<1/4/2>
 // Weight operands live in shared memory in B-fragment order (built once per CTA; W2's fragments replace W2 inside the staged
 // parameter vector, in place).  Activations stay transposed [feature][row]; bias gradients and the loss head are the FFMA code.
-struct TcMap {
+struct TcMapP {   // tensor-core FORWARD kernel: raw parameters staged, fragments built in the kernel
   static constexpr int LD = R + 4;
   static constexpr int P = 0;                        // raw parameter vector (TMA destination); W2's slot is rewritten as B fragments of W2
   static constexpr int W2T = P + P_SMEM;             // [8 ks][8 nt][32] float2 : B fragments of W2^T
@@ -746,6 +746,95 @@ struct TcMap {
   static constexpr int SX = H2T, SA = SX + R * MAX_I, SH = SA + R * MAX_O;
   static_assert(SH + 3 * R <= OT, "gather staging must fit in the h2^T region");
 };
+// Fragment buffer of a network (global memory, crux_mlp::frag): everything the tensor-core minibatch kernel needs from the
+// parameters, in the order it is staged into shared memory with ONE TMA bulk copy.  Built by build_frag_kernel at the start of a
+// PPO update, then kept in step with `params` by the fused Adam kernel (frag_scatter).
+struct Frag {
+  static constexpr int W2F = 0;                    // [8 ks][8 nt][32] float2 : B fragments of W2      (b0 = B[8ks+t][8nt+g], b1 = B[8ks+t+4][8nt+g])
+  static constexpr int W2T = W2F + H * H;          // [8 ks][8 nt][32] float2 : B fragments of W2^T
+  static constexpr int W1F = W2T + H * H;          // [4 ks][8 nt][32] float2 : B fragments of W1      (rows >= I zero)
+  static constexpr int W3F = W1F + 4 * 8 * 32 * 2; // [8 ks][32] float2       : B fragments of W3      (columns >= O zero)
+  static constexpr int W3TF = W3F + 8 * 32 * 2;    // [8 nt][32] float2       : B fragments of W3^T    (k = o < 8; o >= O zero)
+  static constexpr int B1 = W3TF + 8 * 32 * 2;     // [64]
+  static constexpr int B2 = B1 + H;                // [64]
+  static constexpr int B3 = B2 + H;                // [8]
+  static constexpr int TOTAL = B3 + MAX_O;         // 11400 floats = 45600 bytes (a multiple of 16)
+  static_assert((TOTAL * 4) % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+};
+// position of B[k][n] inside a fragment array with `nts` n-tiles per k-step
+__host__ __device__ __forceinline__ int frag_pos(int k, int n, int nts) {
+  return 2 * ((((k >> 3) * nts + (n >> 3)) * 32) + (n & 7) * 4 + (k & 3)) + ((k >> 2) & 1);
+}
+// parameter i of the flat vector (Flux order W1 b1 W2 b2 W3 b3) -> its copies in the fragment buffer
+__device__ __forceinline__ void frag_scatter(float *__restrict__ frag, int I, int O, int i, float v) {
+  if (i < I * H) { frag[Frag::W1F + frag_pos(i / H, i % H, 8)] = v; return; }          // W1[ii][j]: B = W1
+  i -= I * H;
+  if (i < H) { frag[Frag::B1 + i] = v; return; }
+  i -= H;
+  if (i < H * H) {
+    const int k = i / H, j = i % H;
+    frag[Frag::W2F + frag_pos(k, j, 8)] = v;                                             // B = W2   : B[k][j]
+    frag[Frag::W2T + frag_pos(j, k, 8)] = v;                                             // B = W2^T : B[j][k]
+    return;
+  }
+  i -= H * H;
+  if (i < H) { frag[Frag::B2 + i] = v; return; }
+  i -= H;
+  if (i < H * O) {
+    const int k = i / O, o = i % O;
+    frag[Frag::W3F + frag_pos(k, o, 1)] = v;                                             // B = W3   : B[k][o], a single n-tile
+    frag[Frag::W3TF + frag_pos(o, k, 8)] = v;                                            // B = W3^T : B[o][k], a single k-step
+    return;
+  }
+  i -= H * O;
+  if (i < O) frag[Frag::B3 + i] = v;
+}
+// one thread per fragment-buffer entry (gather form; padding entries are written as zeros)
+__global__ void build_frag_kernel(const float *__restrict__ params, float *__restrict__ frag, int I, int O) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Frag::TOTAL) return;
+  const float *W1 = params, *b1 = W1 + I * H, *W2 = b1 + H, *b2 = W2 + H * H, *W3 = b2 + H, *b3 = W3 + H * O;
+  float v = 0.f;
+  if (e < Frag::B1) {
+    const int base = e < Frag::W2T ? Frag::W2F : e < Frag::W1F ? Frag::W2T : e < Frag::W3F ? Frag::W1F : e < Frag::W3TF ? Frag::W3F : Frag::W3TF;
+    const int nts = base == Frag::W3F ? 1 : 8;
+    const int idx = e - base, half = idx & 1, f = idx >> 1, lane = f & 31, blk = f >> 5, nt = blk % nts, ks = blk / nts;
+    const int k = 8 * ks + (lane & 3) + 4 * half, n = 8 * nt + (lane >> 2);   // the entry holds B[k][n]
+    if (base == Frag::W2F) v = W2[k * H + n];
+    else if (base == Frag::W2T) v = W2[n * H + k];
+    else if (base == Frag::W1F) v = k < I ? W1[k * H + n] : 0.f;
+    else if (base == Frag::W3F) v = n < O ? W3[k * O + n] : 0.f;          // B[k][o]
+    else v = k < O ? W3[n * O + k] : 0.f;                                  // B[o][k] = W3[k][o]
+  } else if (e < Frag::B2) v = b1[e - Frag::B1];
+  else if (e < Frag::B3) v = b2[e - Frag::B2];
+  else v = e - Frag::B3 < O ? b3[e - Frag::B3] : 0.f;
+  frag[e] = v;
+}
+
+struct TcMap {
+  static constexpr int LD = R + 4;
+  static constexpr int FR = 0;                       // the staged fragment buffer (Frag layout)
+  static constexpr int XT = FR + Frag::TOTAL;        // [32][LD]  rows >= I stay zero
+  static constexpr int H1T = XT + MAX_I * LD;        // [64][LD]
+  static constexpr int H2T = H1T + H * LD;           // [64][LD]
+  static constexpr int OT = H2T + H * LD;            // [8][LD]   outputs, then dL/dout; rows >= O stay zero
+  static constexpr int AT = OT + MAX_O * LD;         // [8][LD]   stored actions
+  static constexpr int LP = AT + MAX_O * LD;
+  static constexpr int ADV = LP + LD;
+  static constexpr int RET = ADV + LD;
+  static constexpr int IDX = RET + LD;               // [R] ints: source rows of the current tile (-1: padding row)
+  static constexpr int IDX2 = IDX + R;               // [R] ints: source rows of this CTA's next tile
+  static constexpr int RED = IDX2 + R;
+  static constexpr int LSC = RED + 8 * 24;           // [8] logΣ_j, [8] σ_j²  (actor head constants)
+  static constexpr int MBAR = LSC + 16;
+  static constexpr int TOTAL = MBAR + 2;
+  static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
+  static_assert(MBAR % 2 == 0 && XT % 4 == 0, "alignment");
+  // gather staging of the NEXT tile (cp.async, row-major) lives in the h2^T region while that is dead (after dz1 of the current tile,
+  // before layer 2 of the next one): x [R][I] | actions [R][O] | logprob, advantage, return [R] each
+  static constexpr int SX = H2T, SA = SX + R * MAX_I, SH = SA + R * MAX_O;
+  static_assert(SH + 3 * R <= OT, "gather staging must fit in the h2^T region");
+};
 __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src, bool valid) {
   const int nbytes = valid ? 4 : 0;   // 0 source bytes: the destination is zero-filled, nothing is read
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(nbytes) : "memory");
@@ -753,7 +842,7 @@ __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src, boo
 
 template <int HEAD>
 __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
-  if (stopped(a.ctl, a.mb)) return;
+  const int stop_at = a.ctl ? a.ctl[1] : 0;   // requested now, tested after the prologue (a dependent global load off the critical path)
   using M = TcMap;
   constexpr int LD = M::LD;
   extern __shared__ __align__(16) float sm[];
@@ -801,38 +890,15 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
   for (int e = t; e < MAX_O * LD; e += NT) OT[e] = 0.f;
   __syncthreads();
   issue_gather();
-  stage_params(sm, nd, M::MBAR);   // ends with every thread having observed the TMA completion
-  const float *P = sm + M::P;
-  {  // ---- weight operands in B-fragment order
-    float *W2 = sm + M::P + off_W2(I);
-    const float *W1 = P, *W3 = P + off_W3(I);
-    float2 f2[8], t2[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {   // entry e = (ks, nt, lane')
-      const int e = t + u * NT, l = e & 31, nt = (e >> 5) & 7, ks = e >> 8, gg = l >> 2, tt = l & 3;
-      f2[u] = make_float2(W2[(8 * ks + tt) * H + 8 * nt + gg], W2[(8 * ks + tt + 4) * H + 8 * nt + gg]);       // B = W2
-      t2[u] = make_float2(W2[(8 * nt + gg) * H + 8 * ks + tt], W2[(8 * nt + gg) * H + 8 * ks + tt + 4]);       // B = W2^T
-    }
-    float2 *w1f = reinterpret_cast<float2 *>(sm + M::W1F);
-    for (int e = t; e < 4 * 8 * 32; e += NT) {
-      const int l = e & 31, nt = (e >> 5) & 7, ks = e >> 8, gg = l >> 2, tt = l & 3;
-      const int i0 = 8 * ks + tt, i1 = i0 + 4, j = 8 * nt + gg;
-      w1f[e] = make_float2(i0 < I ? W1[i0 * H + j] : 0.f, i1 < I ? W1[i1 * H + j] : 0.f);
-    }
-    {
-      const int l = t & 31, q = t >> 5, gg = l >> 2, tt = l & 3;   // 256 entries each
-      float2 *w3f = reinterpret_cast<float2 *>(sm + M::W3F), *w3t = reinterpret_cast<float2 *>(sm + M::W3TF);
-      w3f[t] = make_float2(gg < O ? W3[(8 * q + tt) * O + gg] : 0.f, gg < O ? W3[(8 * q + tt + 4) * O + gg] : 0.f);           // B[k][o] = W3[k][o], ks = q
-      w3t[t] = make_float2(tt < O ? W3[(8 * q + gg) * O + tt] : 0.f, tt + 4 < O ? W3[(8 * q + gg) * O + tt + 4] : 0.f);       // B[o][k] = W3[k][o], nt = q
-    }
-    __syncthreads();   // every thread holds its W2 values: the slot can be rewritten
-    float2 *w2f = reinterpret_cast<float2 *>(W2), *w2t = reinterpret_cast<float2 *>(sm + M::W2T);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { w2f[t + u * NT] = f2[u]; w2t[t + u * NT] = t2[u]; }
+  stage_params(sm, nd, M::MBAR);   // nd.params = the network's fragment buffer (Frag layout): weights arrive in B-fragment order
+  const float *FRs = sm + M::FR;
+  const float2 *W2F = reinterpret_cast<const float2 *>(FRs + Frag::W2F), *W2TF = reinterpret_cast<const float2 *>(FRs + Frag::W2T);
+  const float2 *W1F = reinterpret_cast<const float2 *>(FRs + Frag::W1F), *W3F = reinterpret_cast<const float2 *>(FRs + Frag::W3F);
+  const float2 *W3TF = reinterpret_cast<const float2 *>(FRs + Frag::W3TF);
+  if (stop_at != 0 && stop_at <= a.mb) {   // an EARLIER minibatch raised the KL stop flag (rl/ppo.jl:59): nothing to do
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    return;
   }
-  const float2 *W2F = reinterpret_cast<const float2 *>(sm + M::P + off_W2(I)), *W2TF = reinterpret_cast<const float2 *>(sm + M::W2T);
-  const float2 *W1F = reinterpret_cast<const float2 *>(sm + M::W1F), *W3F = reinterpret_cast<const float2 *>(sm + M::W3F);
-  const float2 *W3TF = reinterpret_cast<const float2 *>(sm + M::W3TF);
   const int ks1 = (I + 7) >> 3;
 
   // per-CTA gradient accumulators (registers, live across all tiles), in C-fragment layout
@@ -870,7 +936,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
     {
       float c[4][4];
       mma_rows<4>(XT, ks1, r0, W1F + (4 * wn) * 32 + lane, 8 * 32, c);
-      const float *b1 = P + off_b1(I);
+      const float *b1 = FRs + Frag::B1;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -885,7 +951,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
     {
       float c[4][4];
       mma_rows<4>(H1T, 8, r0, W2F + (4 * wn) * 32 + lane, 8 * 32, c);
-      const float *b2 = P + off_b2(I);
+      const float *b2 = FRs + Frag::B2;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -902,7 +968,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
     if (w < 4) {
       float c[1][4];
       mma_rows<1>(H2T, 8, r0, W3F + lane, 32, c);
-      const float *b3 = P + off_b3(I, O);
+      const float *b3 = FRs + Frag::B3;
       const float *lsc = sm + M::LSC;
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
@@ -1067,11 +1133,17 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
 // value(π, s) over a whole rollout column (the two critic passes that feed the GAE scan, policies.jl:94-98) on the building blocks of
 // fused_minibatch_tc_kernel: contiguous 64-row tiles streamed in with 16-byte cp.async one tile ahead (staging = the W2^T slot, which
 // a forward pass does not need), three MMA layers, outputs written straight from the accumulators.
-struct FwdTcArgs { NetDesc net; const float *x; int64_t B; float *y; };
+struct FwdTcArgs {
+  NetDesc net; const float *x; int64_t B; float *y;
+  // value(V, sp) over a [T][N] rollout (crux_value_next): x = sp, x_alt = s + N rows, y_alt = V(s) + N rows.  A tile whose rows all
+  // satisfy sp[row] == s[row + N] bit for bit (every transition that is not followed by a reset) copies V(s)[row + N] instead of
+  // running the network; alt_rows = number of rows that have a successor row (B - N).  NULL x_alt: plain forward.
+  const float *x_alt; const float *y_alt; int64_t alt_rows;
+};
 
 template <int DUMMY>
 __global__ void __launch_bounds__(NT, 2) fused_forward_tc_kernel(FwdTcArgs a) {
-  using M = TcMap;
+  using M = TcMapP;
   constexpr int LD = M::LD;
   extern __shared__ __align__(16) float sm[];
   const NetDesc nd = a.net;
@@ -1081,13 +1153,16 @@ __global__ void __launch_bounds__(NT, 2) fused_forward_tc_kernel(FwdTcArgs a) {
   float *XT = sm + M::XT, *H1T = sm + M::H1T, *H2T = sm + M::H2T, *ST = sm + M::W2T;
   const int64_t n_tiles = (a.B + R - 1) / R;
   const int chunks = R * I / 4;   // 16-byte chunks of one tile (R * I is a multiple of 4)
+  auto has_alt = [&](int64_t tile) { return a.x_alt != nullptr && (tile + 1) * R <= a.alt_rows; };   // every row of the tile has a successor row
   auto issue_tile = [&](int64_t tile) {
     const int64_t f0 = tile * R * I, f_end = a.B * I;   // first float of the tile, end of the column
+    const bool alt = has_alt(tile);
     for (int c = t; c < chunks; c += NT) {
       const int64_t f = f0 + 4 * c;
       const int64_t left = f_end - f;
       const int nbytes = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(ST + 4 * c)), "l"(a.x + (nbytes ? f : 0)), "r"(nbytes) : "memory");
+      if (alt) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 16;" ::"r"(smem_u32(ST + R * MAX_I + 4 * c)), "l"(a.x_alt + f) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -1126,6 +1201,18 @@ __global__ void __launch_bounds__(NT, 2) fused_forward_tc_kernel(FwdTcArgs a) {
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
+    bool same = has_alt(tile);
+    if (same) {   // bitwise comparison of the staged sp tile with the staged s[t+1] tile
+      int diff = 0;
+      for (int e = t; e < R * I; e += NT) diff |= __float_as_int(ST[e]) != __float_as_int(ST[R * MAX_I + e]);
+      same = __syncthreads_or(diff) == 0;
+    }
+    if (same) {   // uniform for the CTA
+      if (t < R) a.y[tile * R + t] = a.y_alt[tile * R + t];   // O == 1 on this path (checked by the launcher)
+      __syncthreads();   // the staging area is free again
+      if (tile + gridDim.x < n_tiles) issue_tile(tile + gridDim.x);
+      continue;
+    }
     for (int e = t; e < R * I; e += NT) {
       const int r = (int)(((uint32_t)e * inv_I) >> 16), i = e - r * I;
       XT[i * LD + r] = ST[e];
@@ -1191,6 +1278,7 @@ struct AdamArgs {
   const float *peer_recv; const unsigned long long *peer_flags; const unsigned long long *peer_seq_dev;
   int *ctl; int mb;
   unsigned int *err_flags;
+  float *frag; int fI, fO;                           // fragment buffer of the network (NULL: none) and its input / output widths
 };
 __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int n_blocks);
 struct PeerOut {   // where the reduce kernel stores this rank's gradient for the fused all-reduce (enabled == 0: local only)
@@ -1376,7 +1464,9 @@ __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int
     const float mt = (float)(a.b1 * (double)a.m[i] + (1.0 - a.b1) * g);
     const float vt = (float)(a.b2 * (double)a.v[i] + (1.0 - a.b2) * g * g);
     a.m[i] = mt; a.v[i] = vt;
-    a.p[i] = a.p[i] - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
+    const float pn = a.p[i] - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
+    a.p[i] = pn;
+    if (a.frag) frag_scatter(a.frag, a.fI, a.fO, i, pn);   // the next minibatch kernel stages the weights in B-fragment order
   }
   if (block_rank == 0 && threadIdx.x < a.A) {
     const int i = threadIdx.x;
@@ -1415,7 +1505,7 @@ int set_smem_attr(crux_ctx *ctx) {
   SET_ATTR(fused_forward_kernel<RB>, SmemMapT<RB>::BYTES);
   SET_ATTR((fused_minibatch_kernel<0, R>), SmemMapT<R>::BYTES);
   SET_ATTR((fused_minibatch_kernel<1, R>), SmemMapT<R>::BYTES);
-  SET_ATTR(fused_forward_tc_kernel<0>, TcMap::BYTES);
+  SET_ATTR(fused_forward_tc_kernel<0>, TcMapP::BYTES);
   SET_ATTR(fused_minibatch_tc_kernel<0>, TcMap::BYTES);
   SET_ATTR(fused_minibatch_tc_kernel<1>, TcMap::BYTES);
   SET_ATTR((fused_minibatch_kernel<0, RB>), SmemMapT<RB>::BYTES);
@@ -1447,7 +1537,7 @@ int launch_forward(crux_ctx *ctx, FwdArgs &a, int nets) {
 
 // ------------------------------------------------------------------------------------------------ entry points (internal)
 // value(π, s) fast path for crux_mlp_forward
-int mlp_forward_fused(crux_mlp *mlp, const float *x, int64_t B, float *y, int *handled) {
+static int forward_fused_impl(crux_mlp *mlp, const float *x, int64_t B, float *y, const float *x_alt, const float *y_alt, int64_t alt_rows, int *handled) {
   *handled = 0;
   if (!fusable(mlp) || getenv("CRUX_NO_FUSED")) return CRUX_OK;
   crux_ctx *ctx = mlp->ctx;
@@ -1455,10 +1545,12 @@ int mlp_forward_fused(crux_mlp *mlp, const float *x, int64_t B, float *y, int *h
   // whole-column passes (at least one 64-row tile per resident CTA) run on the tensor cores; small batches keep the FFMA tiles
   if (cdiv(B, R) >= (int64_t)ctx->num_sms * 2 && ((uintptr_t)x & 15) == 0 && !getenv("CRUX_NO_MMA")) {
     FwdTcArgs f;
+    memset(&f, 0, sizeof(f));
     f.net = describe(mlp); f.x = x; f.B = B; f.y = y;
+    if (x_alt && y_alt && mlp->dims[3] == 1 && ((uintptr_t)x_alt & 15) == 0 && !getenv("CRUX_NO_VALUE_REUSE")) { f.x_alt = x_alt; f.y_alt = y_alt; f.alt_rows = alt_rows; }
     {
       CruxTimed timed(ctx, CRUX_T_FORWARD);
-      fused_forward_tc_kernel<0><<<(unsigned)i64min(cdiv(B, R), (int64_t)ctx->num_sms * 2), NT, TcMap::BYTES, ctx->stream>>>(f);
+      fused_forward_tc_kernel<0><<<(unsigned)i64min(cdiv(B, R), (int64_t)ctx->num_sms * 2), NT, TcMapP::BYTES, ctx->stream>>>(f);
     }
     CRUX_LAUNCHED(ctx);
     *handled = 1;
@@ -1471,6 +1563,14 @@ int mlp_forward_fused(crux_mlp *mlp, const float *x, int64_t B, float *y, int *h
   if (rc) return rc;
   *handled = 1;
   return CRUX_OK;
+}
+int mlp_forward_fused(crux_mlp *mlp, const float *x, int64_t B, float *y, int *handled) {
+  return forward_fused_impl(mlp, x, B, y, nullptr, nullptr, 0, handled);
+}
+// value(V, sp) over a [T][N] rollout given V(s): see FwdTcArgs.  *handled == 0 -> the caller runs a plain forward.
+int mlp_value_next_fused(crux_mlp *mlp, const float *sp, const float *s, const float *v_s, int64_t T, int64_t N, float *v_sp, int *handled) {
+  const int I = mlp->dims[0];
+  return forward_fused_impl(mlp, sp, T * N, v_sp, T > 1 ? s + N * I : nullptr, T > 1 ? v_s + N : nullptr, (T - 1) * N, handled);
 }
 
 bool fused_rows_supported(const crux_gaussian *actor) {
@@ -1517,12 +1617,14 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   a.ls = head == 0 ? actor->log_sigma : nullptr;
   a.inv_bg = inv_bg; a.eps_clip = hp->eps_clip; a.lambda_p = hp->lambda_p; a.a2c = hp->a2c; a.partials = mlp->partials; a.pstride = pstride;
   a.n_params = (int)mlp->n_params; a.ctl = ctl; a.mb = mb;
+  const bool tc = !big && !getenv("CRUX_NO_MMA") && mlp->frag;   // tensor-core kernel: stages the fragment buffer instead of the raw parameters
+  if (tc) { a.net.params = mlp->frag; a.net.bytes16 = (uint32_t)(Frag::TOTAL * sizeof(float)); }
   {
   CruxTimed timed(ctx, CRUX_T_MINIBATCH);
   if (big) {
     if (head == 0) fused_minibatch_kernel<0, RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
     else fused_minibatch_kernel<1, RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
-  } else if (getenv("CRUX_NO_MMA")) {   // all-FFMA variant (A/B reference for the tensor-core path)
+  } else if (!tc) {   // all-FFMA variant (CRUX_NO_MMA=1: A/B reference for the tensor-core path)
     if (head == 0) fused_minibatch_kernel<0, R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
     else fused_minibatch_kernel<1, R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
   } else {
@@ -1542,6 +1644,7 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   g.sums = tail_sums(mlp); g.eta = mlp->eta; g.b1 = mlp->beta1; g.b2 = mlp->beta2; g.eps = mlp->eps; g.step_dev = mlp->step_dev;
   g.lambda_p = hp->lambda_p; g.target_kl = hp->target_kl; g.a2c = hp->a2c; g.head = head; g.rec = rec; g.ctl = ctl; g.mb = mb;
   g.err_flags = ctx->flags_dev;
+  if (tc) { g.frag = mlp->frag; g.fI = mlp->dims[0]; g.fO = mlp->dims[3]; }
   // Running the Adam tail in the last CTA of the reduce kernel saves a launch but serialises 5.7k double-precision updates on
   // one SM: measured 20.5 us against 6.5 + 6.9 us for the two separate kernels (profiles/r1_notes.md) -> opt-in only.
   const int fuse_adam = (ctx->world == 1 && getenv("CRUX_FUSE_ADAM")) ? 1 : 0;
@@ -1598,6 +1701,15 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
   }
   fused_ctl_reset_kernel<<<1, 1, 0, ctx->stream>>>(actor->ctl);
   CRUX_LAUNCHED(ctx);
+  if (!getenv("CRUX_NO_MMA")) {   // weights in MMA B-fragment order for the tensor-core minibatch kernel (kept current by the fused Adam kernel)
+    crux_mlp *nets[2] = {mu, critic};
+    for (crux_mlp *m : nets) {
+      if (!m) continue;
+      rc = ppo_ensure_bytes(ctx, (void **)&m->frag, &m->frag_bytes, Frag::TOTAL * sizeof(float)); if (rc) return rc;
+      build_frag_kernel<<<(Frag::TOTAL + 255) / 256, 256, 0, ctx->stream>>>(m->params, m->frag, m->dims[0], m->dims[3]);
+      CRUX_LAUNCHED(ctx);
+    }
+  }
   if (ctx->side_stream) {   // fork point for the concurrent critic epochs: the side stream sees the rollout / whitening / memsets above
     CRUX_CHECK_CUDA(ctx, cudaEventRecord(ctx->side_fork, ctx->stream));
     CRUX_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_fork, 0));
@@ -1718,32 +1830,36 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
     __syncthreads();
     layer_out16(H2T, P + off_W3(I), P + off_b3(I, O), O, OT);
     __syncthreads();
-    if (t < R16) {
-      const int rr = t;
+    // Gaussian head, one thread per (stream, action dimension): same noise counters and the same arithmetic per value as the
+    // per-step kernel (which walks the dimensions sequentially in one thread); the logpdf terms are summed in that order below.
+    float *lterm = spT;   // [8][LD16] scratch: s'^T is not written before the transition phase
+    if (t < 8 * R16) {
+      const int rr = t >> 3, j = t & 7;
       const int64_t i = e0 + rr;   // absolute stream id == row index of the vector step
-      float logp = 0.f, nrm[4];
-      for (int j = 0; j < O; ++j) {
+      if (j < O) {
         const float mu = OT[j * LD16 + rr];
         const float ls = g.ls[j];
         const float sigma = expf(ls);
         const float var = sigma * sigma;
-        if ((j & 3) == 0) {
-          const Philox4 p = philox4x32_10(g.seed_pi, g.ctr0 + (uint64_t)step, (uint64_t)i * ((O + 3) / 4) + (j >> 2));
-          box_muller(p.x, p.y, nrm[0], nrm[1]);
-          box_muller(p.z, p.w, nrm[2], nrm[3]);
-        }
-        const float ev = nrm[j & 3];
+        const Philox4 p = philox4x32_10(g.seed_pi, g.ctr0 + (uint64_t)step, (uint64_t)i * ((O + 3) / 4) + (j >> 2));
+        float n0, n1;
+        if ((j & 2) == 0) box_muller(p.x, p.y, n0, n1); else box_muller(p.z, p.w, n0, n1);
+        const float ev = (j & 1) ? n1 : n0;
         const float act = ev * sigma + mu;
         aT[j * LD16 + rr] = act;
         if (i < g.N) g.a[(row0 + rr) * O + j] = act;
         const float dd = act - mu;
-        logp += -(dd * dd) / (2.f * var) - LOG_SQRT_2PI - ls;
+        lterm[j * LD16 + rr] = -(dd * dd) / (2.f * var) - LOG_SQRT_2PI - ls;
       }
-      if (i < g.N && g.logp) g.logp[row0 + rr] = logp;
     }
     __syncthreads();
     // ---- env transition (identical arithmetic to linquad_step_kernel)
     if (d < adim) taT[d * LD16 + r] = tanhf(aT[d * LD16 + r]);
+    if (t < R16 && g.logp) {
+      float logp = 0.f;
+      for (int j = 0; j < O; ++j) logp += lterm[j * LD16 + t];
+      if (e0 + t < g.N) g.logp[row0 + t] = logp;
+    }
     __syncthreads();
     const unsigned long long tick = tick0 + (unsigned long long)step;
 #pragma unroll
@@ -1751,28 +1867,30 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
       const int kk = d + 16 * h;
       if (kk < sdim) {
         const Philox4 p = philox4x32_10(g.seed_env, tick, (uint64_t)(live ? e : 0) * 16 + (kk >> 2));
-        float xi[4];
-        box_muller(p.x, p.y, xi[0], xi[1]);
-        box_muller(p.z, p.w, xi[2], xi[3]);
+        float x0, x1;   // only the Box-Muller pair that holds this dimension's normal
+        if ((kk & 2) == 0) box_muller(p.x, p.y, x0, x1); else box_muller(p.z, p.w, x0, x1);
         float v = 0.f;
         for (int j = 0; j < sdim; ++j) v = fmaf(sA[kk * sdim + j], XT[j * LD16 + r], v);
         for (int j = 0; j < adim; ++j) v = fmaf(sB[kk * adim + j], taT[j * LD16 + r], v);
-        v = fmaf(0.01f, xi[kk & 3], v);
+        v = fmaf(0.01f, (kk & 1) ? x1 : x0, v);
         v = fminf(fmaxf(v, -10.f), 10.f);
         spT[kk * LD16 + r] = v;
       }
     }
+    // |s'|^2 in the exact order of linquad_step_kernel: 8 sequential 4-dim partials (one lane each: every dimension of a stream was
+    // written by this warp), combined below like the xor-1/2/4 butterfly.  tanh(a)^T is dead: it holds the partials.
+    __syncwarp();
+    if (d < 8) {
+      float n2 = 0.f;
+      for (int i = 0; i < 4 && 4 * d + i < sdim; ++i) { const float v = spT[(4 * d + i) * LD16 + r]; n2 = fmaf(v, v, n2); }
+      taT[d * LD16 + r] = n2;
+    }
     __syncthreads();
     if (t < R16) {
       const int rr = t;
-      // |s'|^2 in the exact order of linquad_step_kernel: 8 sequential 4-dim partials, then the xor-1/2/4 butterfly
       float pq[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float n2 = 0.f;
-        for (int i = 0; i < 4 && 4 * q + i < sdim; ++i) { const float v = spT[(4 * q + i) * LD16 + rr]; n2 = fmaf(v, v, n2); }
-        pq[q] = n2;
-      }
+      for (int q = 0; q < 8; ++q) pq[q] = taT[q * LD16 + rr];
       const float n2 = ((pq[0] + pq[1]) + (pq[2] + pq[3])) + ((pq[4] + pq[5]) + (pq[6] + pq[7]));
       float a2 = 0.f;
       for (int j = 0; j < adim; ++j) { const float av = aT[j * LD16 + rr]; a2 = fmaf(av, av, a2); }

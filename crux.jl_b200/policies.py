@@ -105,6 +105,11 @@ class _MLP:
         self.ctx.check(self.ctx.lib.crux_mlp_forward(self.h, ptr(x), B, ptr(out)))
         return out
 
+    def value_next(self, sp, s, v_s, T, N, out):
+        """value(V, sp) over a [T][N] rollout given v_s = value(V, s): rows whose sp equals the next step's s bit for bit reuse v_s."""
+        self.ctx.check(self.ctx.lib.crux_value_next(self.h, ptr(sp), ptr(s), ptr(v_s), T, N, ptr(out)))
+        return out
+
     def forward_sa(self, s, a):
         s, a = _as_dev(self.ctx, s), _as_dev(self.ctx, a)
         B = s.shape[0]

@@ -302,7 +302,9 @@ class Sampler:
             assert isinstance(V, ContinuousNetwork) and not math.isnan(float(self.lam)), "GAE needs a critic and λ"
             vs, vsp = self._tmp("v_s", (T * n, 1)), self._tmp("v_sp", (T * n, 1))
             V.mlp.forward(data["s"], out=vs)      # value(V, s_i) for every row
-            V.mlp.forward(data["sp"], out=vsp)    # value(V, sp_i): the stored next observation (pre-reset at boundaries)
+            # value(V, sp_i): the stored next observation (pre-reset at boundaries); wherever sp_i is bitwise the next step's s the
+            # kernel reuses V(s) of that row instead of evaluating the network again
+            V.mlp.value_next(data["sp"], data["s"], vs, T, n, out=vsp)
         else:
             vs = vsp = data["r"]  # unused by the kernel when adv is NULL
         ctx.check(ctx.lib.crux_fill_gae_returns(ctx.h, ptr(data["r"]), ptr(data["done"]), ptr(data["episode_end"]), ptr(vs), ptr(vsp),

@@ -103,6 +103,10 @@ int32_t crux_mlp_grads_ptr(crux_mlp *mlp, float **dev_out);   /* gradient of the
 int32_t crux_mlp_set_adam(crux_mlp *mlp, double eta, double beta1, double beta2, double eps);
 /* value(π, s)  policies.jl:94,120 */
 int32_t crux_mlp_forward(crux_mlp *mlp, const float *x, int64_t B, float *y);
+/* value(V, sp_i) for every row of a [T][N] rollout (the second value call of fill_gae!, sampler.jl:268), given v_s = value(V, s):
+ * wherever sp[t][e] equals s[t+1][e] bit for bit (every transition that is not followed by a reset) the result is v_s[t+1][e] --
+ * identical to evaluating the network on the same input -- and only the remaining tiles run the network. */
+int32_t crux_value_next(crux_mlp *mlp, const float *sp, const float *s, const float *v_s, int64_t T, int64_t N, float *v_sp);
 /* value(π, s, a) = network(vcat(s, a))  policies.jl:96 */
 int32_t crux_mlp_forward_sa(crux_mlp *mlp, const float *s, int32_t sdim, const float *a, int32_t adim,
                             int64_t B, float *y);

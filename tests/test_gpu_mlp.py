@@ -112,3 +112,48 @@ def test_bad_arguments(ctx):
     assert lib.crux_mlp_create(ctx.h, 1, (C.c_int32 * 2)(3, 0), (C.c_int32 * 1)(0), C.byref(h)) == 1
     assert lib.crux_mlp_create(ctx.h, 1, (C.c_int32 * 2)(3, 2), (C.c_int32 * 1)(9), C.byref(h)) == 1
     assert b"activation" in lib.crux_last_error(ctx.h)
+
+
+def test_whole_column_forward_and_value_next(ctx):
+    """Tensor-core forward kernel (whole rollout columns) against the oracle, and crux_value_next: V(sp) over a [T][N] rollout reuses
+    V(s)[t+1] wherever sp[t] == s[t+1] bit for bit and evaluates the network elsewhere (resets, last step, perturbed rows)."""
+    import os
+    rng = np.random.default_rng(5)
+    T, N, I = 40, 512, 17   # 20480 rows >= 2 x 148 tiles of 64: the tensor-core path
+    ref = o.MLP([I, 64, 64, 1], [1, 1, 0], rng)
+    h = make_mlp(ctx, ref.dims, ref.acts, ref.flat())
+    s = rng.standard_normal((T, N, I)).astype(F32)
+    sp = np.empty_like(s)
+    sp[:-1] = s[1:]
+    sp[-1] = rng.standard_normal((N, I)).astype(F32)
+    reset = rng.random((T, N)) < 0.01             # transitions followed by a reset: sp differs from the next s
+    sp[reset] = rng.standard_normal((int(reset.sum()), I)).astype(F32)
+    sp[7, 100, 3] = np.nextafter(sp[7, 100, 3], F32(10))   # a one-ulp difference must be noticed
+    B = T * N
+    sd, spd = dev(ctx, s.reshape(B, I)), dev(ctx, sp.reshape(B, I))
+    vs, vsp, vsp_plain = ctx.empty((B, 1)), ctx.empty((B, 1)), ctx.empty((B, 1))
+    ctx.check(ctx.lib.crux_mlp_forward(h, p(sd), B, p(vs)))
+    ctx.check(ctx.lib.crux_value_next(h, p(spd), p(sd), p(vs), T, N, p(vsp)))
+    ctx.check(ctx.lib.crux_mlp_forward(h, p(spd), B, p(vsp_plain)))
+    want_s = ref(s.reshape(B, I)).detach().numpy()
+    want_sp = ref(sp.reshape(B, I)).detach().numpy()
+    assert_close(host(vs), want_s, rtol=1e-5, atol=2e-6, what="V(s), tensor-core forward")
+    assert_close(host(vsp_plain), want_sp, rtol=1e-5, atol=2e-6, what="V(sp), plain forward")
+    assert_close(host(vsp), want_sp, rtol=1e-5, atol=2e-6, what="V(sp), value_next")
+    # tiles without any reset are copies of V(s)[t+1]: bitwise
+    v, vn = host(vs).reshape(T, N), host(vsp).reshape(T, N)
+    same_tile = ~(reset | (np.arange(T)[:, None] == T - 1)).reshape(-1, 64).any(axis=1)
+    same_tile[(7 * N + 100) // 64] = False
+    rows = np.repeat(same_tile, 64).reshape(T, N)
+    assert rows.sum() > 0.3 * T * N
+    shifted = np.roll(v, -1, axis=0)
+    assert np.array_equal(vn[rows], shifted[rows])
+    # and the FFMA fallback agrees
+    os.environ["CRUX_NO_MMA"] = "1"
+    try:
+        v2 = ctx.empty((B, 1))
+        ctx.check(ctx.lib.crux_value_next(h, p(spd), p(sd), p(vs), T, N, p(v2)))
+        assert_close(host(v2), want_sp, rtol=1e-5, atol=2e-6, what="V(sp), FFMA path")
+    finally:
+        os.environ.pop("CRUX_NO_MMA", None)
+    ctx.check(ctx.lib.crux_mlp_destroy(h))
