@@ -354,6 +354,10 @@ struct FwdArgs {
   const float *eps_in;       // mode 1: injected noise or NULL
   uint64_t seed, ctr;
   int64_t row0;              // mode 1: index of row 0 in the full vector step (noise streams are keyed by the absolute stream id)
+  // host-environment rollouts (crux_rollout_host): x may be PINNED HOST memory read over PCIe by the kernel itself (no H2D copy
+  // call); x_copy receives the rows on the device (the s column of the rollout) and y2 (pinned host) a second copy of the actions
+  float *x_copy;
+  float *y2;
 };
 
 // ---- small-batch variant pieces: 16-row tiles (4x more CTAs for a 4096-stream vector step), thread = (1 row, 4 cols)
@@ -417,7 +421,16 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_forward_kernel(Fwd
       for (int e = threadIdx.x; e < RT * I; e += NT) {
         const int r = e / I, i = e - r * I;
         const int row = sidx[r];
-        sm[M::XT + i * LDT + r] = row >= 0 ? __ldg(a.x + (int64_t)row * I + i) : 0.f;
+        float v = 0.f;
+        if (row >= 0) {
+          if (a.x_copy) {   // x is pinned host memory written by the host since the last launch: bypass every cache
+            v = __ldcv(a.x + (int64_t)row * I + i);
+            if (which == 0) a.x_copy[(int64_t)row * I + i] = v;
+          } else {
+            v = __ldg(a.x + (int64_t)row * I + i);
+          }
+        }
+        sm[M::XT + i * LDT + r] = v;
       }
       __syncthreads();
       layer_fwd16(sm + M::XT, I, P, P + off_b1(I), sm + M::H1T, nd.act);
@@ -456,6 +469,7 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_forward_kernel(Fwd
         }
         const float act = e * sigma + mu;
         a.y[which][i * O + j] = act;
+        if (a.y2) a.y2[i * O + j] = act;
         const float d = act - mu;
         logp += -(d * d) / (2.f * var) - LOG_SQRT_2PI - ls;
       }
@@ -1519,7 +1533,7 @@ int set_smem_attr(crux_ctx *ctx) {
 int launch_forward(crux_ctx *ctx, FwdArgs &a, int nets) {
   const int64_t B = a.B;
   CruxTimed timed(ctx, CRUX_T_FORWARD);
-  if (cdiv(B, R) * nets < (int64_t)ctx->num_sms) {
+  if (cdiv(B, R) * nets < (int64_t)ctx->num_sms || a.x_copy) {   // (the mapped-input form is implemented by the 16-row variant)
     dim3 grid((unsigned)i64min(cdiv(B, R16), (int64_t)ctx->num_sms * 2), nets);
     fused_forward_kernel<R16><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
   } else if (cdiv(B, RB) * nets >= (int64_t)ctx->num_sms && getenv("CRUX_RB")) {  // measured slower than 2 x 64-row CTAs/SM (profiles/): opt-in
@@ -1596,6 +1610,23 @@ extern "C" int32_t crux_rollout_step_fused(crux_gaussian *actor, crux_mlp *criti
   if (rc) return rc;
   *handled = 1;
   return CRUX_OK;
+}
+
+// rows [row0, row0 + N) of a vector step whose observations sit in PINNED HOST memory: the kernel reads them over PCIe, stores them
+// into the device column s_dev, and writes the actions both to the device column and to pinned host memory -- one launch, no copy
+// calls (crux_rollout_host).  Same arithmetic and noise streams as crux_rollout_step_rows.
+extern "C" int32_t crux_rollout_step_rows_mapped(crux_gaussian *actor, const float *obs_pinned, int64_t N, int64_t row0, uint64_t seed, uint64_t ctr,
+                                                 float *s_dev, float *a_dev, float *a_pinned, float *logp_dev) {
+  if (!actor) return CRUX_ERR_INVALID;
+  crux_ctx *ctx = actor->ctx;
+  CRUX_REQUIRE(ctx, fused_rows_supported(actor), "crux_rollout_step_rows_mapped: only the fused policy shapes support split vector steps");
+  CRUX_REQUIRE(ctx, obs_pinned && s_dev && a_dev && a_pinned && N >= 1, "crux_rollout_step_rows_mapped: bad arguments");
+  int rc = set_smem_attr(ctx); if (rc) return rc;
+  FwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.net[0] = describe(actor->mu); a.mode[0] = 1; a.y[0] = a_dev; a.y2 = a_pinned; a.logp = logp_dev; a.ls = actor->log_sigma;
+  a.seed = seed; a.ctr = ctr; a.x = obs_pinned; a.x_copy = s_dev; a.B = N; a.row0 = row0;
+  return launch_forward(ctx, a, 1);
 }
 
 // one minibatch = 3 launches: fused forward/loss/backward -> partial reduction (+ step count) -> [all-reduce] -> norm/record/Adam

@@ -5,45 +5,48 @@
 // episode bookkeeping) stays on this side of the ABI, so no interpreter sits between two vector steps.
 //
 // The N streams are split into two halves that leapfrog: while the host steps the env streams of one half, the device runs the
-// policy forward (and the copies) of the other half.  Per half g and vector step t, all on the context stream:
-//     obs_g (pinned) --H2D--> s[t] rows of g      fused_forward (a, logprob rows of g)      a rows --D2H--> pinned      event E_g
-//     wait E_g    step callback(g) -> sp, r, done (pinned)    episode_end = done | len >= max_steps | (reset_at_end & last step)
-//     reset callback for ended streams -> next obs_g      sp, r, done, episode_end rows of g --H2D--> row t
+// policy forward of the other half.  Per half g and vector step t, all on the context stream:
+//     ONE launch: the forward kernel reads obs_g straight from pinned host memory (PCIe), stores it as the s[t] rows of g, computes
+//                 a / logprob and writes the actions to the device column AND to pinned host memory        event E_g
+//     wait E_g    step callback(g) -> sp, r, done (pinned, full-rollout staging)    episode_end = done | len >= max_steps | forced
+//     reset callback for ended streams -> next obs_g
+// The transition columns (sp, r, done, episode_end) are not needed on the device before the rollout ends: they are uploaded in
+// chunks of UPLOAD_STEPS whole vector steps (4 copy calls per chunk instead of 8 per vector step).
 // Exploration noise is keyed by (seed, ctr0 + t, absolute stream id): the result does not depend on the split.
 #include "policy.cuh"
 #include <vector>
 
-extern "C" int32_t crux_rollout_step_rows(crux_gaussian *actor, const float *obs, int64_t N, int64_t row0, uint64_t seed, uint64_t ctr,
-                                          float *a_out, float *logp_out);
+extern "C" int32_t crux_rollout_step_rows_mapped(crux_gaussian *actor, const float *obs_pinned, int64_t N, int64_t row0, uint64_t seed, uint64_t ctr,
+                                                 float *s_dev, float *a_dev, float *a_pinned, float *logp_dev);
 bool fused_rows_supported(const crux_gaussian *actor);
 
 struct HostRolloutStage {
   float *a = nullptr, *sp = nullptr, *r = nullptr, *robs = nullptr;
   uint8_t *done = nullptr, *ee = nullptr;
-  int64_t N = 0; int sdim = 0, adim = 0;
+  int64_t N = 0, T = 0; int sdim = 0, adim = 0;   // a: [N][adim]; sp, r, done, ee: [T][N] (full rollout)
   cudaEvent_t ev[2] = {nullptr, nullptr};
   std::vector<int32_t> idx;
 };
 
 static HostRolloutStage g_stage;  // one staging set per process (contexts are one per process / GPU)
 
-static int ensure_stage(crux_ctx *ctx, int64_t N, int sdim, int adim) {
+static int ensure_stage(crux_ctx *ctx, int64_t N, int64_t T, int sdim, int adim) {
   HostRolloutStage &S = g_stage;
-  if (S.N >= N && S.sdim == sdim && S.adim == adim) return CRUX_OK;
+  if (S.N == N && S.T >= T && S.sdim == sdim && S.adim == adim) return CRUX_OK;
   CRUX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (S.a) { cudaFreeHost(S.a); cudaFreeHost(S.sp); cudaFreeHost(S.r); cudaFreeHost(S.robs); cudaFreeHost(S.done); cudaFreeHost(S.ee); }
   cudaEvent_t e0 = S.ev[0], e1 = S.ev[1];
   S = HostRolloutStage();
   S.ev[0] = e0; S.ev[1] = e1;
   CRUX_CHECK_CUDA(ctx, cudaMallocHost((void **)&S.a, (size_t)N * adim * sizeof(float)));
-  CRUX_CHECK_CUDA(ctx, cudaMallocHost((void **)&S.sp, (size_t)N * sdim * sizeof(float)));
+  CRUX_CHECK_CUDA(ctx, cudaMallocHost((void **)&S.sp, (size_t)T * N * sdim * sizeof(float)));
   CRUX_CHECK_CUDA(ctx, cudaMallocHost((void **)&S.robs, (size_t)N * sdim * sizeof(float)));
-  CRUX_CHECK_CUDA(ctx, cudaMallocHost((void **)&S.r, (size_t)N * sizeof(float)));
-  CRUX_CHECK_CUDA(ctx, cudaMallocHost((void **)&S.done, (size_t)N));
-  CRUX_CHECK_CUDA(ctx, cudaMallocHost((void **)&S.ee, (size_t)N));
+  CRUX_CHECK_CUDA(ctx, cudaMallocHost((void **)&S.r, (size_t)T * N * sizeof(float)));
+  CRUX_CHECK_CUDA(ctx, cudaMallocHost((void **)&S.done, (size_t)T * N));
+  CRUX_CHECK_CUDA(ctx, cudaMallocHost((void **)&S.ee, (size_t)T * N));
   for (int g = 0; g < 2; ++g)
     if (!S.ev[g]) CRUX_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&S.ev[g], cudaEventDisableTiming));
-  S.N = N; S.sdim = sdim; S.adim = adim;
+  S.N = N; S.T = T; S.sdim = sdim; S.adim = adim;
   S.idx.reserve((size_t)N);
   return CRUX_OK;
 }
@@ -57,7 +60,7 @@ extern "C" int32_t crux_rollout_host(crux_gaussian *actor, int64_t N, int32_t T,
   CRUX_REQUIRE(ctx, step && reset && obs_pinned && episode_length && cols, "crux_rollout_host: NULL argument");
   CRUX_REQUIRE(ctx, cols->s && cols->a && cols->sp && cols->r && cols->done && cols->episode_end, "crux_rollout_host: NULL column");
   const int sdim = actor->mu->dims[0], adim = actor->adim;
-  int rc = ensure_stage(ctx, N, sdim, adim);
+  int rc = ensure_stage(ctx, N, T, sdim, adim);
   if (rc) return rc;
   HostRolloutStage &S = g_stage;
   cudaStream_t st = ctx->stream;
@@ -65,39 +68,52 @@ extern "C" int32_t crux_rollout_host(crux_gaussian *actor, int64_t N, int32_t T,
   const int G = (fused_rows_supported(actor) && N >= 512) ? 2 : 1;
   const int64_t lo[2] = {0, G == 2 ? N / 2 : N}, hi[2] = {G == 2 ? N / 2 : N, N};
 
+  constexpr int UPLOAD_STEPS = 8;
+  const bool mapped = G == 2;   // the fused policy shapes: the kernel does its own PCIe reads / writes
   auto enqueue_forward = [&](int g, int t) -> int {  // obs_g -> s[t]; policy forward; action back to the host; event
     const int64_t row = (int64_t)t * N + lo[g], n = hi[g] - lo[g];
     float *s_t = cols->s + row * sdim, *a_t = cols->a + row * adim;
-    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(s_t, obs_pinned + lo[g] * sdim, (size_t)n * sdim * sizeof(float), cudaMemcpyHostToDevice, st));
     float *lp = cols->logprob ? cols->logprob + row : nullptr;
-    int rc2 = G == 2 ? crux_rollout_step_rows(actor, s_t, n, lo[g], seed, ctr0 + (uint64_t)t, a_t, lp)
-                     : crux_rollout_step(actor, nullptr, s_t, n, nullptr, seed, ctr0 + (uint64_t)t, a_t, lp, nullptr);
-    if (rc2) return rc2;
-    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(S.a + lo[g] * adim, a_t, (size_t)n * adim * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (mapped) {
+      int rc2 = crux_rollout_step_rows_mapped(actor, obs_pinned + lo[g] * sdim, n, lo[g], seed, ctr0 + (uint64_t)t, s_t, a_t, S.a + lo[g] * adim, lp);
+      if (rc2) return rc2;
+    } else {
+      CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(s_t, obs_pinned + lo[g] * sdim, (size_t)n * sdim * sizeof(float), cudaMemcpyHostToDevice, st));
+      int rc2 = crux_rollout_step(actor, nullptr, s_t, n, nullptr, seed, ctr0 + (uint64_t)t, a_t, lp, nullptr);
+      if (rc2) return rc2;
+      CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(S.a + lo[g] * adim, a_t, (size_t)n * adim * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
     CRUX_CHECK_CUDA(ctx, cudaEventRecord(S.ev[g], st));
+    return CRUX_OK;
+  };
+  auto upload = [&](int t0, int t1) -> int {   // transition columns of the vector steps [t0, t1): contiguous rows in the [T][N] layout
+    const int64_t row = (int64_t)t0 * N, n = (int64_t)(t1 - t0) * N;
+    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(cols->sp + row * sdim, S.sp + row * sdim, (size_t)n * sdim * sizeof(float), cudaMemcpyHostToDevice, st));
+    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(cols->r + row, S.r + row, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
+    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(cols->done + row, S.done + row, (size_t)n, cudaMemcpyHostToDevice, st));
+    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(cols->episode_end + row, S.ee + row, (size_t)n, cudaMemcpyHostToDevice, st));
     return CRUX_OK;
   };
 
   for (int g = 0; g < G; ++g) { rc = enqueue_forward(g, 0); if (rc) return rc; }
+  int uploaded = 0;
   for (int t = 0; t < T; ++t) {
     const bool force = reset_at_end && t == T - 1;                                                     // steps!(reset=true) :148
+    float *sp_t = S.sp + (size_t)t * N * sdim, *r_t = S.r + (size_t)t * N;
+    uint8_t *done_t = S.done + (size_t)t * N, *ee_t = S.ee + (size_t)t * N;
     for (int g = 0; g < G; ++g) {
-      const int64_t e0 = lo[g], e1 = hi[g], n = e1 - e0, row = (int64_t)t * N + e0;
-      CRUX_CHECK_CUDA(ctx, cudaEventSynchronize(S.ev[g]));   // actions of half g are on the host; its earlier H2Ds are done too
-      step(user, (int32_t)e0, (int32_t)e1, S.a, S.sp, S.r, S.done);                                    // @gen(:sp,:r), isterminal
+      const int64_t e0 = lo[g], e1 = hi[g], n = e1 - e0;
+      CRUX_CHECK_CUDA(ctx, cudaEventSynchronize(S.ev[g]));   // actions of half g are on the host (and obs_g has been read)
+      step(user, (int32_t)e0, (int32_t)e1, S.a, sp_t, r_t, done_t);                                    // @gen(:sp,:r), isterminal
       S.idx.clear();
       for (int64_t e = e0; e < e1; ++e) {
         const int32_t len = ++episode_length[e];                                                       // sampler.jl:130
-        const bool end = S.done[e] || len >= max_steps || force;
-        S.ee[e] = end ? 1 : 0;
+        const bool end = done_t[e] || len >= max_steps || force;
+        ee_t[e] = end ? 1 : 0;
         if (end) { S.idx.push_back((int32_t)e); episode_length[e] = 0; }
       }
-      CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(cols->sp + row * sdim, S.sp + e0 * sdim, (size_t)n * sdim * sizeof(float), cudaMemcpyHostToDevice, st));
-      CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(cols->r + row, S.r + e0, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
-      CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(cols->done + row, S.done + e0, (size_t)n, cudaMemcpyHostToDevice, st));
-      CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(cols->episode_end + row, S.ee + e0, (size_t)n, cudaMemcpyHostToDevice, st));
       // next observation: sp, or a fresh initial state where the episode ended (terminate_episode! -> reset_sampler!)
-      memcpy(obs_pinned + e0 * sdim, S.sp + e0 * sdim, (size_t)n * sdim * sizeof(float));
+      memcpy(obs_pinned + e0 * sdim, sp_t + e0 * sdim, (size_t)n * sdim * sizeof(float));
       if (!S.idx.empty()) {
         reset(user, S.idx.data(), (int32_t)S.idx.size(), S.robs);
         for (size_t q = 0; q < S.idx.size(); ++q) memcpy(obs_pinned + (size_t)S.idx[q] * sdim, S.robs + q * sdim, sizeof(float) * sdim);
@@ -105,6 +121,7 @@ extern "C" int32_t crux_rollout_host(crux_gaussian *actor, int64_t N, int32_t T,
       // the forward of this half for the next vector step runs on the device while the host steps the other half
       if (t + 1 < T) { rc = enqueue_forward(g, t + 1); if (rc) return rc; }
     }
+    if (t + 1 - uploaded >= UPLOAD_STEPS || t + 1 == T) { rc = upload(uploaded, t + 1); if (rc) return rc; uploaded = t + 1; }
   }
   CRUX_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
   return CRUX_OK;
