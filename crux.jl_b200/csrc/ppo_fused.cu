@@ -1636,7 +1636,11 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   crux_ctx *ctx = mlp->ctx;
   // 128-row tiles (1 CTA/SM, 8x4 register tiles) measured SLOWER than 2 x 64-row CTAs per SM (occupancy halves; profiles/): opt-in
   const bool big = cdiv(bm, RB) >= (int64_t)ctx->num_sms && getenv("CRUX_RB");
-  const int grid = big ? (int)i64min(cdiv(bm, RB), (int64_t)ctx->num_sms) : (int)i64min(cdiv(bm, R), (int64_t)ctx->num_sms * 2);
+  // CRUX_MB_RESERVE_SMS=k leaves k SMs out of the grid (for the concurrent reduce / all-reduce / Adam tail of the other network).
+  // Measured on 2 x B200 with k = 0, 4, 8, 16: no effect (128 M env-steps/s each) -- the tail is not waiting for SMs -- so 0 it is.
+  static const int reserve_env = getenv("CRUX_MB_RESERVE_SMS") ? atoi(getenv("CRUX_MB_RESERVE_SMS")) : 0;
+  const int sms = (int)i64max(1, ctx->num_sms - (reserve_env > 0 ? reserve_env : 0));
+  const int grid = big ? (int)i64min(cdiv(bm, RB), (int64_t)ctx->num_sms) : (int)i64min(cdiv(bm, R), (int64_t)sms * 2);
   const int pstride = (int)((mlp->n_params + 16 + 31) / 32 * 32);
   const size_t need = (size_t)ctx->num_sms * 2 * pstride * sizeof(float);
   int rc = ppo_ensure_bytes(ctx, (void **)&mlp->partials, &mlp->partials_bytes, need);
