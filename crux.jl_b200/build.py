@@ -60,14 +60,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 HOST_LIB = os.path.join(LIBDIR, "libcrux_hostenv.so")
 HOST_LIB_AVX2 = os.path.join(LIBDIR, "libcrux_hostenv_avx2.so")
+HOST_LIB_AVX512 = os.path.join(LIBDIR, "libcrux_hostenv_avx512.so")
 
 
 def build_host(force: bool = False) -> str:
-    """g++ builds of the host-side synthetic env stepper (no CUDA): a baseline x86-64 variant that runs anywhere and an
-    AVX2+FMA variant (libmvec-vectorised) that envs.py selects when /proc/cpuinfo advertises avx2 and fma."""
+    """g++ builds of the host-side synthetic env stepper (no CUDA): a baseline x86-64 variant that runs anywhere, an AVX2+FMA
+    variant and an AVX-512 variant (libmvec-vectorised); envs.py selects the widest one /proc/cpuinfo advertises."""
     src = os.path.join(CSRC, "host", "linquad_host.cpp")
     cxx = os.environ.get("CXX", "g++")
-    for out, extra in ((HOST_LIB, []), (HOST_LIB_AVX2, ["-mavx2", "-mfma"])):
+    for out, extra in ((HOST_LIB, []), (HOST_LIB_AVX2, ["-mavx2", "-mfma"]),
+                       (HOST_LIB_AVX512, ["-mavx512f", "-mavx512dq", "-mavx512vl", "-mavx512bw", "-mfma", "-mprefer-vector-width=512"])):
         if force or _stale(out, [src]):
             r = subprocess.run([cxx, "-O3", "-ffast-math", "-fopenmp-simd", "-std=c++17", "-fPIC", "-shared", "-pthread", *extra, src, "-o", out, "-lm"],
                                capture_output=True, text=True)

@@ -15,6 +15,8 @@
 // Exploration noise is keyed by (seed, ctr0 + t, absolute stream id): the result does not depend on the split.
 #include "policy.cuh"
 #include <vector>
+#include <chrono>
+#include <stdlib.h>
 
 extern "C" int32_t crux_rollout_step_rows_mapped(crux_gaussian *actor, const float *obs_pinned, int64_t N, int64_t row0, uint64_t seed, uint64_t ctr,
                                                  float *s_dev, float *a_dev, float *a_pinned, float *logp_dev);
@@ -95,6 +97,10 @@ extern "C" int32_t crux_rollout_host(crux_gaussian *actor, int64_t N, int32_t T,
     return CRUX_OK;
   };
 
+  // CRUX_ROLLOUT_PROFILE=1: host wall-clock split of the loop (printed to stderr at the end of the call)
+  static const bool prof = getenv("CRUX_ROLLOUT_PROFILE") != nullptr;
+  double t_wait = 0, t_step = 0, t_book = 0, t_enq = 0;
+  auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (int g = 0; g < G; ++g) { rc = enqueue_forward(g, 0); if (rc) return rc; }
   int uploaded = 0;
   for (int t = 0; t < T; ++t) {
@@ -103,8 +109,11 @@ extern "C" int32_t crux_rollout_host(crux_gaussian *actor, int64_t N, int32_t T,
     uint8_t *done_t = S.done + (size_t)t * N, *ee_t = S.ee + (size_t)t * N;
     for (int g = 0; g < G; ++g) {
       const int64_t e0 = lo[g], e1 = hi[g], n = e1 - e0;
+      const double q0 = prof ? now() : 0;
       CRUX_CHECK_CUDA(ctx, cudaEventSynchronize(S.ev[g]));   // actions of half g are on the host (and obs_g has been read)
+      const double q1 = prof ? now() : 0;
       step(user, (int32_t)e0, (int32_t)e1, S.a, sp_t, r_t, done_t);                                    // @gen(:sp,:r), isterminal
+      const double q2 = prof ? now() : 0;
       S.idx.clear();
       for (int64_t e = e0; e < e1; ++e) {
         const int32_t len = ++episode_length[e];                                                       // sampler.jl:130
@@ -119,10 +128,14 @@ extern "C" int32_t crux_rollout_host(crux_gaussian *actor, int64_t N, int32_t T,
         for (size_t q = 0; q < S.idx.size(); ++q) memcpy(obs_pinned + (size_t)S.idx[q] * sdim, S.robs + q * sdim, sizeof(float) * sdim);
       }
       // the forward of this half for the next vector step runs on the device while the host steps the other half
+      const double q3 = prof ? now() : 0;
       if (t + 1 < T) { rc = enqueue_forward(g, t + 1); if (rc) return rc; }
+      if (prof) { const double q4 = now(); t_wait += q1 - q0; t_step += q2 - q1; t_book += q3 - q2; t_enq += q4 - q3; }
     }
     if (t + 1 - uploaded >= UPLOAD_STEPS || t + 1 == T) { rc = upload(uploaded, t + 1); if (rc) return rc; uploaded = t + 1; }
   }
   CRUX_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+  if (prof) fprintf(stderr, "crux_rollout_host: T=%d N=%lld  wait %.0f us  env step %.0f us  bookkeeping+memcpy %.0f us  enqueue %.0f us\n", (int)T,
+                    (long long)N, t_wait, t_step, t_book, t_enq);
   return CRUX_OK;
 }

@@ -83,11 +83,17 @@ class NativeHostLinQuad:
             import os
             libdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
             path = os.path.join(libdir, "libcrux_hostenv.so")
-            try:  # the AVX2+FMA build (libmvec-vectorised) when the CPU has it
+            try:  # the widest libmvec-vectorised build the CPU supports (CRUX_HOSTENV_ISA=baseline|avx2|avx512 overrides)
                 flags = open("/proc/cpuinfo").read()
-                fast = os.path.join(libdir, "libcrux_hostenv_avx2.so")
-                if " avx2" in flags and " fma" in flags and os.path.exists(fast) and not os.environ.get("CRUX_HOSTENV_BASELINE"):
-                    path = fast
+                want = os.environ.get("CRUX_HOSTENV_ISA", "baseline" if os.environ.get("CRUX_HOSTENV_BASELINE") else "")
+                fast2 = os.path.join(libdir, "libcrux_hostenv_avx2.so")
+                fast5 = os.path.join(libdir, "libcrux_hostenv_avx512.so")
+                has5 = all(f" {f}" in flags for f in ("avx512f", "avx512dq", "avx512vl", "avx512bw")) and " fma" in flags
+                has2 = " avx2" in flags and " fma" in flags
+                if want in ("", "avx512") and has5 and os.path.exists(fast5):
+                    path = fast5
+                elif want in ("", "avx2", "avx512") and has2 and os.path.exists(fast2):
+                    path = fast2
             except OSError:
                 pass
             if not os.path.exists(path):

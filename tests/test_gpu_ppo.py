@@ -234,3 +234,38 @@ def test_tensor_core_path_equals_ffma_path(ctx, crux):
     assert_close(tc[1][:, A.PPO_GRAD_NORM], ff[1][:, A.PPO_GRAD_NORM], rtol=2e-5, what="critic grad norm tc vs ffma")
     assert_params_close(tc[2], ff[2], 3e-4, 6, what="actor params tc vs ffma")
     assert_params_close(tc[3], ff[3], 3e-4, 4, what="critic params tc vs ffma")
+
+
+def test_full_size_update_properties(ctx, crux):
+    """BASELINE config[1] update shape (131 072 rows, minibatches of 32 768, actor then critic) through crux_ppo_update:
+    (1) bit-reproducible: two runs from the same parameters give identical parameters and info records (fixed-order partial
+        reductions, no atomics); (2) the tensor-core kernel and the all-FFMA kernel agree to fp32 accuracy at this size;
+    (3) the first minibatch's loss is the oracle's ppo_loss on those rows."""
+    import os
+    n, mb = 131072, 32768
+    out = {}
+    for tag, env in (("tc1", ""), ("tc2", ""), ("ffma", "1")):
+        if env:
+            os.environ["CRUX_NO_MMA"] = env
+        try:
+            rng, pi, cr, handles, D = _setup(ctx, crux, n, seed=123)
+            hp = _hp(crux, actor_batch=mb, critic_batch=mb, actor_epochs=1, critic_epochs=1, lambda_e=0.0)
+            oa = _orders(rng, n, 1); oc = _orders(rng, n, 1, start=oa[-1])
+            ia, ic = _run(ctx, crux, handles, D, hp, oa, oc, n)
+            out[tag] = (ia.copy(), ic.copy(), mlp_params(ctx, handles[0]).copy(), mlp_params(ctx, handles[1]).copy())
+            if tag == "tc1":
+                idx = oa[0][:mb]
+                mbD = {k: v[idx] for k, v in D.items()}
+                info = {}
+                want = float(o.ppo_loss(pi, {"eps": F32(0.2), "lp": F32(1), "le": F32(0.0)}, mbD, info))
+                assert_close(ia[0, crux._abi.PPO_LOSS], want, rtol=2e-5, atol=1e-6, what="first minibatch ppo_loss at full size")
+        finally:
+            os.environ.pop("CRUX_NO_MMA", None)
+    for k in range(4):
+        assert np.array_equal(out["tc1"][k], out["tc2"][k]), "the update is not bit-reproducible"
+    A = crux._abi
+    assert_close(out["tc1"][0][:, A.PPO_LOSS], out["ffma"][0][:, A.PPO_LOSS], rtol=2e-5, atol=1e-6, what="actor loss tc vs ffma (full size)")
+    assert_close(out["tc1"][0][:, A.PPO_GRAD_NORM], out["ffma"][0][:, A.PPO_GRAD_NORM], rtol=5e-5, what="actor grad norm tc vs ffma (full size)")
+    assert_close(out["tc1"][1][:, A.PPO_LOSS], out["ffma"][1][:, A.PPO_LOSS], rtol=2e-5, what="critic loss tc vs ffma (full size)")
+    assert_params_close(out["tc1"][2], out["ffma"][2], 3e-4, 4, what="actor params tc vs ffma (full size)")
+    assert_params_close(out["tc1"][3], out["ffma"][3], 3e-4, 4, what="critic params tc vs ffma (full size)")
