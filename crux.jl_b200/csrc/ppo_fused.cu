@@ -1143,6 +1143,8 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
   }
 }
 
+#include "fwd_tc5.cuh"
+
 // =================================================================================================== tensor-core forward kernel
 // value(π, s) over a whole rollout column (the two critic passes that feed the GAE scan, policies.jl:94-98) on the building blocks of
 // fused_minibatch_tc_kernel: contiguous 64-row tiles streamed in with 16-byte cp.async one tile ahead (staging = the W2^T slot, which
@@ -1556,6 +1558,22 @@ static int forward_fused_impl(crux_mlp *mlp, const float *x, int64_t B, float *y
   if (!fusable(mlp) || getenv("CRUX_NO_FUSED")) return CRUX_OK;
   crux_ctx *ctx = mlp->ctx;
   int rc = set_smem_attr(ctx); if (rc) return rc;
+  // whole-column plain forwards: tcgen05 + TMEM kernel (fwd_tc5.cuh), one 128-row tile per SM and round
+  static const char *tc5_env = getenv("CRUX_FWD_TC5");
+  if (!x_alt && tc5_env && tc5_env[0] == '1' && mlp->dims[0] <= tc5::KX && mlp->dims[3] <= 8 && cdiv(B, tc5::TR) >= (int64_t)ctx->num_sms &&
+      ((uintptr_t)x & 15) == 0 && !getenv("CRUX_NO_MMA")) {
+    static bool attr = false;
+    if (!attr) { CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(tc5::forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5::Map::TOTAL)); attr = true; }
+    tc5::Args f;
+    f.net = describe(mlp); f.x = x; f.B = B; f.y = y;
+    {
+      CruxTimed timed(ctx, CRUX_T_FORWARD);
+      tc5::forward_kernel<<<(unsigned)i64min(cdiv(B, tc5::TR), (int64_t)ctx->num_sms), NT, tc5::Map::TOTAL, ctx->stream>>>(f);
+    }
+    CRUX_LAUNCHED(ctx);
+    *handled = 1;
+    return CRUX_OK;
+  }
   // whole-column passes (at least one 64-row tile per resident CTA) run on the tensor cores; small batches keep the FFMA tiles
   if (cdiv(B, R) >= (int64_t)ctx->num_sms * 2 && ((uintptr_t)x & 15) == 0 && !getenv("CRUX_NO_MMA")) {
     FwdTcArgs f;
