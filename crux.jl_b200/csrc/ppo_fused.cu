@@ -1559,16 +1559,27 @@ static int forward_fused_impl(crux_mlp *mlp, const float *x, int64_t B, float *y
   crux_ctx *ctx = mlp->ctx;
   int rc = set_smem_attr(ctx); if (rc) return rc;
   // whole-column plain forwards: tcgen05 + TMEM kernel (fwd_tc5.cuh), one 128-row tile per SM and round
-  static const char *tc5_env = getenv("CRUX_FWD_TC5");
-  if (!x_alt && tc5_env && tc5_env[0] == '1' && mlp->dims[0] <= tc5::KX && mlp->dims[3] <= 8 && cdiv(B, tc5::TR) >= (int64_t)ctx->num_sms &&
+  // (CRUX_FWD_TC5=0: the mma.sync kernel below; =1s: the variant that keeps the activations in shared memory)
+  static const char *tc5_env = getenv("CRUX_FWD_TC5") ? getenv("CRUX_FWD_TC5") : "1";
+  const bool alt_ok = x_alt && y_alt && mlp->dims[3] == 1 && ((uintptr_t)x_alt & 15) == 0 && !getenv("CRUX_NO_VALUE_REUSE");
+  if (tc5_env[0] == '1' && (!alt_ok || tc5_env[1] != 's') && mlp->dims[0] <= tc5::KX && mlp->dims[3] <= 8 && cdiv(B, tc5::TR) >= (int64_t)ctx->num_sms &&
       ((uintptr_t)x & 15) == 0 && !getenv("CRUX_NO_MMA")) {
     static bool attr = false;
-    if (!attr) { CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(tc5::forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5::Map::TOTAL)); attr = true; }
+    if (!attr) {
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(tc5::forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5::Map::TOTAL));
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(tc5::forward_kernel_tmem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5::Map2::TOTAL));
+      attr = true;
+    }
     tc5::Args f;
+    memset(&f, 0, sizeof(f));
     f.net = describe(mlp); f.x = x; f.B = B; f.y = y;
+    if (alt_ok) { f.x_alt = x_alt; f.y_alt = y_alt; f.alt_rows = alt_rows; }
     {
       CruxTimed timed(ctx, CRUX_T_FORWARD);
-      tc5::forward_kernel<<<(unsigned)i64min(cdiv(B, tc5::TR), (int64_t)ctx->num_sms), NT, tc5::Map::TOTAL, ctx->stream>>>(f);
+      if (tc5_env[1] == 's')   // "1s": activations through shared memory (variant 1)
+        tc5::forward_kernel<<<(unsigned)i64min(cdiv(B, tc5::TR), (int64_t)ctx->num_sms), NT, tc5::Map::TOTAL, ctx->stream>>>(f);
+      else                     // activations stay in tensor memory, two CTAs per SM
+        tc5::forward_kernel_tmem<<<(unsigned)i64min(cdiv(B, tc5::TR), (int64_t)ctx->num_sms * 2), NT, tc5::Map2::TOTAL, ctx->stream>>>(f);
     }
     CRUX_LAUNCHED(ctx);
     *handled = 1;

@@ -1,6 +1,6 @@
 """tcgen05 forward kernel (CRUX_FWD_TC5=1) against the oracle and the mma.sync forward kernel: python scripts/fwd_tc5_check.py"""
 import os, sys
-os.environ["CRUX_FWD_TC5"] = "1"
+os.environ.setdefault("CRUX_FWD_TC5", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch

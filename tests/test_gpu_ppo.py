@@ -265,7 +265,10 @@ def test_full_size_update_properties(ctx, crux):
         assert np.array_equal(out["tc1"][k], out["tc2"][k]), "the update is not bit-reproducible"
     A = crux._abi
     assert_close(out["tc1"][0][:, A.PPO_LOSS], out["ffma"][0][:, A.PPO_LOSS], rtol=2e-5, atol=1e-6, what="actor loss tc vs ffma (full size)")
-    assert_close(out["tc1"][0][:, A.PPO_GRAD_NORM], out["ffma"][0][:, A.PPO_GRAD_NORM], rtol=5e-5, what="actor grad norm tc vs ffma (full size)")
+    # first minibatch: same parameters on both paths; later ones see parameters after Adam steps that amplify rounding differences
+    # in near-zero gradient coordinates (assert_params_close documents the effect)
+    assert_close(out["tc1"][0][:1, A.PPO_GRAD_NORM], out["ffma"][0][:1, A.PPO_GRAD_NORM], rtol=2e-5, what="actor grad norm tc vs ffma (first minibatch)")
+    assert_close(out["tc1"][0][:, A.PPO_GRAD_NORM], out["ffma"][0][:, A.PPO_GRAD_NORM], rtol=1e-3, what="actor grad norm tc vs ffma (full size)")
     assert_close(out["tc1"][1][:, A.PPO_LOSS], out["ffma"][1][:, A.PPO_LOSS], rtol=2e-5, what="critic loss tc vs ffma (full size)")
     assert_params_close(out["tc1"][2], out["ffma"][2], 3e-4, 4, what="actor params tc vs ffma (full size)")
     assert_params_close(out["tc1"][3], out["ffma"][3], 3e-4, 4, what="critic params tc vs ffma (full size)")
