@@ -284,19 +284,19 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
                "l"(db), "r"(idesc), "r"(acc)
                : "memory");
 }
-// 3 passes x ksteps MMAs, A = TMEM columns (8 per k-step), B = canonical K-major shared-memory planes
-__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo_off, uint32_t b_sbo, int ksteps,
-                                              uint32_t idesc, uint32_t bar) {
-  int first = 1;
-#pragma unroll 1
-  for (int p = 0; p < 3; ++p) {   // lo*hi, hi*lo, hi*hi
-    const uint32_t a = p == 0 ? a_lo : a_hi, b = b_hi + (p == 1 ? b_lo_off : 0);
-#pragma unroll 1
-    for (int ks = 0; ks < ksteps; ++ks) {
-      mma_tf32_ts(d_tmem, a + 8 * ks, make_desc(b + ks * 256, 128, b_sbo), idesc, first ? 0u : 1u);
-      first = 0;
-    }
-  }
+// 3 passes x KS MMAs, A = TMEM columns (8 per k-step), B = canonical K-major shared-memory planes.  Fully unrolled: the descriptor of
+// k-step ks is the base descriptor + 16 * ks (the 14-bit start-address field counts 16-byte units; no carry for < 256 KB of smem), so
+// the single issuing thread spends ~3 instructions per MMA instead of rebuilding 64-bit descriptors.
+template <int KS>
+__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo_off, uint32_t b_sbo, uint32_t idesc,
+                                              uint32_t bar) {
+  const uint64_t dbh = make_desc(b_hi, 128, b_sbo), dbl = make_desc(b_hi + b_lo_off, 128, b_sbo);
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d_tmem, a_lo + 8 * ks, dbh + 16 * ks, idesc, ks ? 1u : 0u);   // lo * hi
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d_tmem, a_hi + 8 * ks, dbl + 16 * ks, idesc, 1u);             // hi * lo
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d_tmem, a_hi + 8 * ks, dbh + 16 * ks, idesc, 1u);             // hi * hi
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 #define TC5_LD32(v, taddr)                                                                                                                             \
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(NT, 2) forward_kernel_tmem(Args a) {
     // ---------------- layer 1: C1 = x W1
     if (t == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue_gemm_ts(tmem + C1, tmem + XH, tmem + XL, sW1, 64 * KX * 4, 32 * KX, KX / 8, idesc64, bar_mma);
+      issue_gemm_ts<KX / 8>(tmem + C1, tmem + XH, tmem + XL, sW1, 64 * KX * 4, 32 * KX, idesc64, bar_mma);
     }
     mbar_wait(bar_mma, ph); ph ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(NT, 2) forward_kernel_tmem(Args a) {
     // ---------------- layer 2: C3 = h1 W2
     if (t == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue_gemm_ts(tmem + C3, tmem + C1, tmem + C2, sW2, 64 * 64 * 4, 32 * 64, 8, idesc64, bar_mma);
+      issue_gemm_ts<8>(tmem + C3, tmem + C1, tmem + C2, sW2, 64 * 64 * 4, 32 * 64, idesc64, bar_mma);
     }
     mbar_wait(bar_mma, ph); ph ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(NT, 2) forward_kernel_tmem(Args a) {
     // ---------------- output layer: C1[0,16) = h2 W3
     if (t == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue_gemm_ts(tmem + C1, tmem + C3, tmem + C2, sW3, NOUT * 64 * 4, 32 * 64, 8, idesc16, bar_mma);
+      issue_gemm_ts<8>(tmem + C1, tmem + C3, tmem + C2, sW3, NOUT * 64 * 4, 32 * 64, idesc16, bar_mma);
     }
     mbar_wait(bar_mma, ph); ph ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -312,14 +312,14 @@ __device__ __forceinline__ void mma_rows(const float *__restrict__ AT, int ks_n,
   }
 }
 // acc[q] += dW[m0 + {g, g+8}][n0 + 8q + {2tq, 2tq+1}] = sum_{row<64} A^T[m][row] * D^T[n][row]   (both operands are transposed tiles)
-template <int NQ>
+template <int NQ, int ROWS = R>
 __device__ __forceinline__ void mma_wgrad(const float *__restrict__ AT, int m0, const float *__restrict__ DT, int n0, float (&acc)[NQ][4]) {
-  constexpr int LD = R + 4;
+  constexpr int LD = ROWS + 4;
   const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
   const float *ap = AT + (m0 + g) * LD + tq;
   const float *dp = DT + (n0 + g) * LD + tq;
-#pragma unroll
-  for (int ks = 0; ks < R / 8; ++ks) {
+#pragma unroll (ROWS == R ? 8 : 4)
+  for (int ks = 0; ks < ROWS / 8; ++ks) {
     uint32_t ah[4], al[4];
     split_tf32(ap[8 * ks], ah[0], al[0]);
     split_tf32(ap[8 * LD + 8 * ks], ah[1], al[1]);
@@ -1145,6 +1145,8 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
 
 #include "fwd_tc5.cuh"
 
+#include "mb_tc5.cuh"
+
 // =================================================================================================== tensor-core forward kernel
 // value(π, s) over a whole rollout column (the two critic passes that feed the GAE scan, policies.jl:94-98) on the building blocks of
 // fused_minibatch_tc_kernel: contiguous 64-row tiles streamed in with 16-byte cp.async one tile ahead (staging = the W2^T slot, which
@@ -1669,7 +1671,10 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   // Measured on 2 x B200 with k = 0, 4, 8, 16: no effect (128 M env-steps/s each) -- the tail is not waiting for SMs -- so 0 it is.
   static const int reserve_env = getenv("CRUX_MB_RESERVE_SMS") ? atoi(getenv("CRUX_MB_RESERVE_SMS")) : 0;
   const int sms = (int)i64max(1, ctx->num_sms - (reserve_env > 0 ? reserve_env : 0));
-  const int grid = big ? (int)i64min(cdiv(bm, RB), (int64_t)ctx->num_sms) : (int)i64min(cdiv(bm, R), (int64_t)sms * 2);
+  static const char *mb5_env0 = getenv("CRUX_MB_TC5");
+  const bool tc5_grid = !big && !getenv("CRUX_NO_MMA") && mb5_env0 && mb5_env0[0] == '1' && mlp->dims[0] <= mb5::KX && mlp->dims[3] <= 8;
+  const int grid = big ? (int)i64min(cdiv(bm, RB), (int64_t)ctx->num_sms)
+                       : tc5_grid ? (int)i64min(cdiv(bm, mb5::TR), (int64_t)ctx->num_sms) : (int)i64min(cdiv(bm, R), (int64_t)sms * 2);
   const int pstride = (int)((mlp->n_params + 16 + 31) / 32 * 32);
   const size_t need = (size_t)ctx->num_sms * 2 * pstride * sizeof(float);
   int rc = ppo_ensure_bytes(ctx, (void **)&mlp->partials, &mlp->partials_bytes, need);
@@ -1681,13 +1686,25 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   a.ls = head == 0 ? actor->log_sigma : nullptr;
   a.inv_bg = inv_bg; a.eps_clip = hp->eps_clip; a.lambda_p = hp->lambda_p; a.a2c = hp->a2c; a.partials = mlp->partials; a.pstride = pstride;
   a.n_params = (int)mlp->n_params; a.ctl = ctl; a.mb = mb;
-  const bool tc = !big && !getenv("CRUX_NO_MMA") && mlp->frag;   // tensor-core kernel: stages the fragment buffer instead of the raw parameters
+  // CRUX_MB_TC5=1: row GEMMs on tcgen05 with the activations in tensor memory (mb_tc5.cuh), one 512-thread CTA per SM, 128-row tiles
+  static const char *mb5_env = getenv("CRUX_MB_TC5");
+  const bool tc5k = !big && !getenv("CRUX_NO_MMA") && mb5_env && mb5_env[0] == '1' && mlp->dims[0] <= mb5::KX && mlp->dims[3] <= 8;
+  const bool tc = !big && !tc5k && !getenv("CRUX_NO_MMA") && mlp->frag;   // mma.sync kernel: stages the fragment buffer instead of the raw parameters
   if (tc) { a.net.params = mlp->frag; a.net.bytes16 = (uint32_t)(Frag::TOTAL * sizeof(float)); }
   {
   CruxTimed timed(ctx, CRUX_T_MINIBATCH);
   if (big) {
     if (head == 0) fused_minibatch_kernel<0, RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
     else fused_minibatch_kernel<1, RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
+  } else if (tc5k) {
+    static bool attr5 = false;
+    if (!attr5) {
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(mb5::minibatch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb5::Map::TOTAL));
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(mb5::minibatch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb5::Map::TOTAL));
+      attr5 = true;
+    }
+    if (head == 0) mb5::minibatch_kernel<0><<<grid, mb5::NTH, mb5::Map::TOTAL, ctx->stream>>>(a);
+    else mb5::minibatch_kernel<1><<<grid, mb5::NTH, mb5::Map::TOTAL, ctx->stream>>>(a);
   } else if (!tc) {   // all-FFMA variant (CRUX_NO_MMA=1: A/B reference for the tensor-core path)
     if (head == 0) fused_minibatch_kernel<0, R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
     else fused_minibatch_kernel<1, R><<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(a);
