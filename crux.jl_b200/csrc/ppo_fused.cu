@@ -1314,7 +1314,10 @@ struct PeerOut {   // where the reduce kernel stores this rank's gradient for th
 // (scaled by 1/world so that the all-reduce sum restores it).  Each CTA also emits the sum of squares of its 32 finished
 // gradient entries (used by the Adam kernel when there is no all-reduce in between).  Block 0 counts the optimiser step.
 constexpr int RW = 32;  // warps per reduce CTA
-__global__ void __launch_bounds__(RW * 32) reduce_fused_partials_kernel(const float *__restrict__ partials, int nparts, int pstride, int n_params,
+// FUSE = 1 (opt-in CRUX_FUSE_ADAM) compiles the Adam tail into the kernel; the default instantiation stays at 32 registers so that
+// two 1024-thread CTAs share an SM (with the tail inlined it needs 60 and the 179-CTA grid runs in two waves: 14 us instead of 9).
+template <int FUSE>
+__global__ void __launch_bounds__(RW * 32, FUSE ? 1 : 2) reduce_fused_partials_kernel(const float *__restrict__ partials, int nparts, int pstride, int n_params,
                                                                        float *__restrict__ grads, float count, float ls_shift, int n_ls,
                                                                        double *__restrict__ norm_part, int *__restrict__ step_dev,
                                                                        const int *__restrict__ ctl, int mb, unsigned int *__restrict__ ticket,
@@ -1381,7 +1384,7 @@ __global__ void __launch_bounds__(RW * 32) reduce_fused_partials_kernel(const fl
     }
     return;
   }
-  if (!fuse_adam) {
+  if (!FUSE || !fuse_adam) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;
     return;
   }
@@ -1744,9 +1747,14 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
     g.peer_seq_dev = ctx->peer_seq_dev;
   }
   { CruxTimed timed(ctx, CRUX_T_REDUCE);
-  reduce_fused_partials_kernel<<<rblocks, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
-                                                                   ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb,
-                                                                   ctx->flags_dev + 2, g, fuse_adam, po);
+  if (fuse_adam)
+    reduce_fused_partials_kernel<1><<<rblocks, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
+                                                                        ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb,
+                                                                        ctx->flags_dev + 2, g, fuse_adam, po);
+  else
+    reduce_fused_partials_kernel<0><<<rblocks, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
+                                                                        ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb,
+                                                                        ctx->flags_dev + 2, g, fuse_adam, po);
   }
   CRUX_LAUNCHED(ctx);
   if (!fuse_adam) {

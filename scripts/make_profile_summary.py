@@ -39,7 +39,8 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_th
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
@@ -58,6 +59,9 @@ if os.path.exists(lp):
     out.append("")
 for name, title in (("prof_minibatch", "fused_minibatch_kernel (dominant kernel of the step)"), ("prof_gae_tma", "gae_tma_kernel at [2048, 16384] (738 MB): TMA-fed streaming scan, the kernel crux_fill_gae_returns runs for N >= 8192"),
                     ("prof_gae", "gae_returns_kernel at [2048, 16384] (738 MB): register-resident scan (narrow / short rollouts; CRUX_GAE=scan)"),
+                    ("prof_fwd_tc5", "tc5::forward_kernel_tmem: value(V, s) over 131072 rows on tcgen05, activations resident in tensor memory"),
+                    ("prof_mb5", "mb5::minibatch_kernel (opt-in CRUX_MB_TC5=1): PPO minibatch with the row GEMMs on tcgen05 / TMEM"),
+                    ("prof_rollout", "rollout_linquad_kernel: T = 32 vector steps of 4096 env streams in one persistent launch"),
                     ("prof_forward", "fused_forward_kernel")):
     rep = os.path.join(G, name + ".ncu-rep")
     if not os.path.exists(rep):
