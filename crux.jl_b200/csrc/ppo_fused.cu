@@ -1333,35 +1333,41 @@ __global__ void __launch_bounds__(RW * 32, FUSE ? 1 : 2) reduce_fused_partials_k
   };
   __shared__ double sh[RW][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int p = blockIdx.x * 32 + lane;
-  double s = 0.0;
-  if (p < n_params + 16) {
-    const float *src = partials + p;
-#pragma unroll 10
-    for (int c = w; c < nparts; c += RW) s += (double)__ldcg(src + (int64_t)c * pstride);
-  }
-  sh[w][lane] = s;
-  __syncthreads();
-  if (w == 0) {
-    double sq = 0.0;
+  // groups of 32 entries, grid-strided: the grid may be much smaller than the number of groups (several ranks: the kernel runs on
+  // the few SMs the concurrent minibatch kernel of the other network leaves free); results do not depend on the grid size
+  const int n_groups = (n_params + 16 + 31) / 32;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int p = grp * 32 + lane;
+    double s = 0.0;
     if (p < n_params + 16) {
-      double t = 0.0;
-#pragma unroll
-      for (int q = 0; q < RW; ++q) t += sh[q][lane];
-      if (p < n_params) { emit(p, (float)t); sq = (double)(float)t * (double)(float)t; }
-      else if (p < n_params + 8) {
-        const int j = p - n_params;
-        const float g = (float)t + (j < n_ls ? ls_shift : 0.f);
-        emit(p, g);
-        if (j < n_ls) sq = (double)g * (double)g;
-      } else {
-        const int q = p - n_params - 8;
-        if (q < 5) emit(n_params + 64 + q, (float)t);
-        else if (q == 5) emit(n_params + 64 + 5, count);
-      }
+      const float *src = partials + p;
+#pragma unroll 10
+      for (int c = w; c < nparts; c += RW) s += (double)__ldcg(src + (int64_t)c * pstride);
     }
-    sq = warp_sum_d(sq);
-    if (lane == 0) norm_part[blockIdx.x] = sq;
+    sh[w][lane] = s;
+    __syncthreads();
+    if (w == 0) {
+      double sq = 0.0;
+      if (p < n_params + 16) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < RW; ++q) t += sh[q][lane];
+        if (p < n_params) { emit(p, (float)t); sq = (double)(float)t * (double)(float)t; }
+        else if (p < n_params + 8) {
+          const int j = p - n_params;
+          const float g = (float)t + (j < n_ls ? ls_shift : 0.f);
+          emit(p, g);
+          if (j < n_ls) sq = (double)g * (double)g;
+        } else {
+          const int q = p - n_params - 8;
+          if (q < 5) emit(n_params + 64 + q, (float)t);
+          else if (q == 5) emit(n_params + 64 + 5, count);
+        }
+      }
+      sq = warp_sum_d(sq);
+      if (lane == 0) norm_part[grp] = sq;
+    }
+    __syncthreads();   // sh is reused by the next group
   }
   if (peer.enabled) {
     // fused all-reduce, sending side: when the LAST CTA of this kernel has seen every other CTA's stores, it raises this rank's
@@ -1670,10 +1676,12 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   crux_ctx *ctx = mlp->ctx;
   // 128-row tiles (1 CTA/SM, 8x4 register tiles) measured SLOWER than 2 x 64-row CTAs per SM (occupancy halves; profiles/): opt-in
   const bool big = cdiv(bm, RB) >= (int64_t)ctx->num_sms && getenv("CRUX_RB");
-  // CRUX_MB_RESERVE_SMS=k leaves k SMs out of the grid (for the concurrent reduce / all-reduce / Adam tail of the other network).
-  // Measured on 2 x B200 with k = 0, 4, 8, 16: no effect (128 M env-steps/s each) -- the tail is not waiting for SMs -- so 0 it is.
+  // CRUX_MB_RESERVE_SMS=k leaves k SMs out of this kernel's grid and runs the tail's reduce kernel on 2k CTAs (for the concurrent
+  // reduce / all-reduce / Adam tail of the other network on several ranks).  Measured on 2 x B200: k = 0: 132 M env-steps/s,
+  // k = 4: 81 M, k = 8: 109 M, k = 16: 127 M -- the reduction needs its full grid more than it needs to start early -- so 0 it is.
   static const int reserve_env = getenv("CRUX_MB_RESERVE_SMS") ? atoi(getenv("CRUX_MB_RESERVE_SMS")) : 0;
-  const int sms = (int)i64max(1, ctx->num_sms - (reserve_env > 0 ? reserve_env : 0));
+  const int reserve = reserve_env > 0 ? reserve_env : 0;
+  const int sms = (int)i64max(1, ctx->num_sms - reserve);
   static const char *mb5_env0 = getenv("CRUX_MB_TC5");
   const bool tc5_grid = !big && !getenv("CRUX_NO_MMA") && mb5_env0 && mb5_env0[0] == '1' && mlp->dims[0] <= mb5::KX && mlp->dims[3] <= 8;
   const int grid = big ? (int)i64min(cdiv(bm, RB), (int64_t)ctx->num_sms)
@@ -1719,6 +1727,7 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   CRUX_LAUNCHED(ctx);
   const int n_out = (int)mlp->n_params + 16;
   const int rblocks = (n_out + 31) / 32;   // <= 1024 doubles of norm_part (n_params <= 6792)
+  const int rgrid = reserve > 0 ? (int)i64min(rblocks, 2 * reserve) : rblocks;   // two 1024-thread CTAs per reserved SM
   const float ls_shift = head == 0 ? -hp->lambda_e / (float)ctx->world : 0.f;
   AdamArgs g;
   memset(&g, 0, sizeof(g));
@@ -1748,11 +1757,11 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   }
   { CruxTimed timed(ctx, CRUX_T_REDUCE);
   if (fuse_adam)
-    reduce_fused_partials_kernel<1><<<rblocks, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
+    reduce_fused_partials_kernel<1><<<rgrid, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
                                                                         ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb,
                                                                         ctx->flags_dev + 2, g, fuse_adam, po);
   else
-    reduce_fused_partials_kernel<0><<<rblocks, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
+    reduce_fused_partials_kernel<0><<<rgrid, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
                                                                         ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb,
                                                                         ctx->flags_dev + 2, g, fuse_adam, po);
   }
