@@ -20,8 +20,8 @@
 //   carry never leaves the registers; between segments it crosses global memory once per stream (value + release flag, acquired
 //   by the chain warp that starts the earlier segment).  An item is only waited on by items taken later from the counter, i.e.
 //   by CTAs that were resident after its owner: deadlock-free for any residency.
-//   The sequential chain is the critical resource: N/64 chain warps, ~21 instructions per time step each, so the path is used
-//   for wide rollouts (N >= 8192); narrow ones stay on the time-parallel scan of gae.cu.
+//   The sequential chains are the critical resource (one chain warp per 64 streams): the path is used for rollouts wider than
+//   4096 streams (64-stream tiles up to 64 x SM-count streams, 128-stream tiles above); narrow ones stay on the time-parallel scan of gae.cu.
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -29,11 +29,11 @@
 
 namespace {
 
-constexpr int TS = 128;            // streams per tile
-constexpr int NCW = 2;             // chain warps (64 streams each, 2 per lane)
+// streams per tile TS = 64 * NCW, NCW = chain warps (64 streams each, 2 per lane): 128-stream tiles for wide rollouts, 64-stream
+// tiles (twice as many sequential chains / CTAs) for narrower ones
 constexpr int NPW = 2;             // prep warps
-constexpr int W_LOAD = 0, W_CHAIN = 1, W_PREP = W_CHAIN + NCW, W_STORE = W_PREP + NPW;
-constexpr int NTHREADS = 32 * (W_STORE + 1);
+constexpr int W_LOAD = 0, W_CHAIN = 1;   // then NCW chain warps, NPW prep warps, the storer warp
+constexpr int n_threads(int ncw) { return 32 * (1 + ncw + NPW + 1); }
 constexpr int MAX_STAGES = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,7 +94,7 @@ struct TmaArgs {
 
 // stage layout (bytes): r [CS][TS] f32 (-> returns) | V(s) [CS][TS] f32 (-> delta -> advantages) | V(sp) [CS][TS] f32 |
 //                       done [CS][TS] u8 | episode_end [CS][TS] u8
-template <int CS>
+template <int CS, int TS>
 struct StageMap {
   static constexpr int F = CS * TS * 4, B = CS * TS;
   static constexpr int R = 0, VS = F, VSP = 2 * F, DN = 3 * F, EE = 3 * F + B;
@@ -102,12 +102,13 @@ struct StageMap {
   static_assert(BYTES % 128 == 0, "TMA boxes must stay 128-byte aligned");
 };
 
-template <int CS>
-__global__ void __launch_bounds__(NTHREADS) gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_vs,
+template <int CS, int NCW>
+__global__ void __launch_bounds__(n_threads(NCW)) gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_vs,
                                                            const __grid_constant__ CUtensorMap tm_vsp, const __grid_constant__ CUtensorMap tm_dn,
                                                            const __grid_constant__ CUtensorMap tm_ee, const __grid_constant__ CUtensorMap tm_adv,
                                                            const __grid_constant__ CUtensorMap tm_ret, const TmaArgs a) {
-  using SM = StageMap<CS>;
+  constexpr int TS = 64 * NCW, W_PREP = W_CHAIN + NCW, W_STORE = W_PREP + NPW;
+  using SM = StageMap<CS, TS>;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], prep_bar[MAX_STAGES], chain_bar[MAX_STAGES], empty_bar[MAX_STAGES];
   __shared__ int4 meta[MAX_STAGES];   // x: tile (-1: no more work), y: chunk, z: segment, w: bit0 latest chunk of the segment, bit1 earliest
@@ -159,34 +160,34 @@ __global__ void __launch_bounds__(NTHREADS) gae_tma_kernel(const __grid_constant
     // ================================================================ prep warps: delta = (r + (1-done) gamma V(sp)) - V(s), in place over V(s)
     const int pw = w - W_PREP;
     const float gamma = a.gamma;
-    constexpr int ROWS = CS / NPW, PB = 4;   // rows per prep warp, rows per batch (all loads of a batch are issued before its math)
+    constexpr int PER = CS * TS / 4 / (NPW * 32), PB = 4;   // float4 elements per lane (the stage arrays are dense: flat indexing)
+    static_assert(PER % PB == 0, "prep batches");
     int s = 0; uint32_t ph = 0;
     for (;;) {
       mbar_wait(smem_u32(&full_bar[s]), ph);
       const bool stop = meta[s].x < 0;
       if (!stop) {
-        unsigned char *st = smem + (size_t)s * SM::BYTES + 16 * lane;
+        unsigned char *st = smem + (size_t)s * SM::BYTES;
+        float4 *pr = reinterpret_cast<float4 *>(st + SM::R), *pv = reinterpret_cast<float4 *>(st + SM::VS), *pp = reinterpret_cast<float4 *>(st + SM::VSP);
+        const uchar4 *pdn = reinterpret_cast<const uchar4 *>(st + SM::DN);
 #pragma unroll
-        for (int b = 0; b < ROWS; b += PB) {
+        for (int b = 0; b < PER; b += PB) {
           float4 r4[PB], va[PB], vb[PB];
           uchar4 dn[PB];
 #pragma unroll
           for (int j = 0; j < PB; ++j) {
-            const int i = pw * ROWS + b + j;
-            r4[j] = *reinterpret_cast<const float4 *>(st + SM::R + i * TS * 4);
-            va[j] = *reinterpret_cast<const float4 *>(st + SM::VS + i * TS * 4);
-            vb[j] = *reinterpret_cast<const float4 *>(st + SM::VSP + i * TS * 4);
-            dn[j] = *reinterpret_cast<const uchar4 *>(smem + (size_t)s * SM::BYTES + SM::DN + i * TS + 4 * lane);
+            const int f = (pw * PER + b + j) * 32 + lane;
+            r4[j] = pr[f]; va[j] = pv[f]; vb[j] = pp[f]; dn[j] = pdn[f];
           }
 #pragma unroll
           for (int j = 0; j < PB; ++j) {
-            const int i = pw * ROWS + b + j;
+            const int f = (pw * PER + b + j) * 32 + lane;
             float4 d;
             d.x = (r4[j].x + (dn[j].x ? 0.f : gamma) * vb[j].x) - va[j].x;
             d.y = (r4[j].y + (dn[j].y ? 0.f : gamma) * vb[j].y) - va[j].y;
             d.z = (r4[j].z + (dn[j].z ? 0.f : gamma) * vb[j].z) - va[j].z;
             d.w = (r4[j].w + (dn[j].w ? 0.f : gamma) * vb[j].w) - va[j].w;
-            *reinterpret_cast<float4 *>(st + SM::VS + i * TS * 4) = d;
+            pv[f] = d;
           }
         }
       }
@@ -306,10 +307,10 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 
-bool make_map(CUtensorMap *m, const void *base, bool is_u8, int64_t T, int64_t N, int cs) {
+bool make_map(CUtensorMap *m, const void *base, bool is_u8, int64_t T, int64_t N, int cs, int ts) {
   const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)T};
   const cuuint64_t strides[1] = {(cuuint64_t)N * (is_u8 ? 1 : 4)};
-  const cuuint32_t box[2] = {(cuuint32_t)TS, (cuuint32_t)cs};
+  const cuuint32_t box[2] = {(cuuint32_t)ts, (cuuint32_t)cs};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode_fn()(m, is_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box,
                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -320,18 +321,21 @@ bool make_map(CUtensorMap *m, const void *base, bool is_u8, int64_t T, int64_t N
 }  // namespace
 
 // Returns CRUX_OK with *handled = 0 when the shape is not eligible (the register-resident scan of gae.cu runs instead).
-// Eligibility: T >= 64, N >= 8192 and a multiple of 16 (TMA row pitch of the u8 columns), 16-byte aligned columns, TMA encode available.
+// Eligibility: T >= 64, N > 4096 and a multiple of 16 (TMA row pitch of the u8 columns), 16-byte aligned columns, TMA encode available.
 // CRUX_GAE=scan forces the gae.cu kernel, CRUX_GAE=tma forces this one for any eligible T >= 1;
-// CRUX_GAE_CFG="CS,STAGES,SEG_CHUNKS,CTAS_PER_SM" overrides the tuning (tests use it to exercise the segment hand-off).
+// CRUX_GAE_CFG="CS,STAGES,SEG_CHUNKS,CTAS_PER_SM,CHAIN_WARPS" overrides the tuning (0 = default; tests use it to exercise the
+// segment hand-off and both tile widths).
 int gae_tma_launch(crux_ctx *ctx, const float *r, const uint8_t *done, const uint8_t *ee, const float *vs, const float *vsp, int64_t T, int64_t N,
                    float gamma, float lambda, float *adv, float *ret, int *handled) {
   *handled = 0;
   const char *mode = getenv("CRUX_GAE");
   if (mode && !strcmp(mode, "scan")) return CRUX_OK;
   const bool forced = mode && !strcmp(mode, "tma");
-  // narrow or short rollouts stay on the time-parallel scan: this path has N/64 sequential chains and needs >= ~128 tiles to fill the GPU
-  if (!forced && (T < 64 || N < 8192)) return CRUX_OK;
-  if (N % 16 != 0 || N >= ((int64_t)1 << 31) - TS || T >= ((int64_t)1 << 31) - 64) return CRUX_OK;
+  // every tile is one sequential chain: 64-stream tiles (twice the chains) above N = 4096 while each tile gets its own SM, else 128;
+  // narrower or short rollouts stay on the time-parallel scan of gae.cu (measured cross-overs, profiles/r1_gae_sweep.log:
+  // [2048,8192] 5.4 TB/s with 64-stream tiles against 4.0 with 128 and 3.2 for the scan; [2048,4096] a tie at 3.0)
+  if (!forced && (T < 64 || N <= 4096)) return CRUX_OK;
+  if (N % 16 != 0 || N >= ((int64_t)1 << 31) - 128 || T >= ((int64_t)1 << 31) - 64) return CRUX_OK;
   const uintptr_t al = (uintptr_t)r | (uintptr_t)done | (uintptr_t)ee | (uintptr_t)vs | (uintptr_t)vsp | (uintptr_t)adv | (uintptr_t)ret;
   if (al & 15) return CRUX_OK;
   if (!encode_fn()) return CRUX_OK;
@@ -342,14 +346,18 @@ int gae_tma_launch(crux_ctx *ctx, const float *r, const uint8_t *done, const uin
 
   // measured best on B200 (profiles/r1_gae_sweep.log): 16-step stages, 4 stages loading + 2 draining per CTA, one CTA per SM;
   // with more tiles than SMs two smaller CTAs per SM so that every tile still is a single segment
+  // 64-stream tiles while every tile still gets its own SM (N <= 64 x SMs = 9472 on B200), 128-stream tiles beyond
+  int ncw = cdiv(N, 64) <= (int64_t)ctx->num_sms ? 1 : 2, cs = 0, stages = 0, seg_chunks = 0, per_sm = 0;
+  if (const char *cfg = getenv("CRUX_GAE_CFG")) sscanf(cfg, "%d,%d,%d,%d,%d", &cs, &stages, &seg_chunks, &per_sm, &ncw);
+  if (ncw != 1 && ncw != 2) ncw = 2;
+  const int TS = 64 * ncw;
   const int tiles_ = (int)cdiv(N, TS);
-  int cs = 16, stages = tiles_ > ctx->num_sms ? 4 : 6, seg_chunks = 0, per_sm = tiles_ > ctx->num_sms ? 2 : 1;
-  if (const char *cfg = getenv("CRUX_GAE_CFG")) sscanf(cfg, "%d,%d,%d,%d", &cs, &stages, &seg_chunks, &per_sm);
-  if (cs != 16 && cs != 32) cs = 16;
+  if (cs != 16 && cs != 32) cs = ncw == 2 ? 16 : 32;                      // 28 KB stages either way
+  if (stages <= 0) stages = tiles_ > ctx->num_sms ? 4 : 6;
+  if (per_sm <= 0) per_sm = tiles_ > ctx->num_sms ? 2 : 1;
   if (stages < 3) stages = 3;   // the storer keeps two stages in flight
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (per_sm < 1) per_sm = 1;
-  const size_t stage_bytes = cs == 16 ? StageMap<16>::BYTES : StageMap<32>::BYTES;
+  const size_t stage_bytes = (size_t)cs * TS * 14;
   while (stages > 3 && stages * stage_bytes > 226 * 1024) --stages;   // 227 KB per CTA minus the static barriers
   const int n_chunks = (int)cdiv(T, cs);
   const int tiles = (int)cdiv(N, TS);
@@ -375,9 +383,9 @@ int gae_tma_launch(crux_ctx *ctx, const float *r, const uint8_t *done, const uin
   // scratch slot 7 belongs to this path and survives between launches: [counter + flags: flag_cap words][carry records].
   // The flag region keeps a fixed capacity so that carry bits of one launch can never be read as flags by a later one.
   size_t flag_cap = ctx->gae_flag_cap ? ctx->gae_flag_cap : 4096;
-  while (flag_cap < (size_t)n_items64 * NCW + 4) flag_cap *= 2;
+  while (flag_cap < (size_t)n_items64 * ncw + 4) flag_cap *= 2;
   const size_t flag_al = flag_cap * sizeof(unsigned int);
-  const size_t carry_bytes = (size_t)n_items64 * NCW * 32 * sizeof(float4);
+  const size_t carry_bytes = (size_t)n_items64 * ncw * 32 * sizeof(float4);
   char *p = (char *)crux_scratch(ctx, 7, flag_al + carry_bytes);
   if (!p) return CRUX_ERR_OOM;
   if (p != ctx->gae_scratch_seen || flag_cap != ctx->gae_flag_cap || ctx->gae_epoch == 0xFFFFFFFFu) {   // fresh / regrown block or epoch wrap
@@ -394,19 +402,20 @@ int gae_tma_launch(crux_ctx *ctx, const float *r, const uint8_t *done, const uin
   CUtensorMap m[7];
   const void *cols[7] = {r, vs, vsp, done, ee, adv ? adv : ret, ret ? ret : adv};
   for (int i = 0; i < 7; ++i)
-    if (!make_map(&m[i], cols[i], i == 3 || i == 4, T, N, cs)) return CRUX_OK;   // not encodable (exotic pitch): fall back to the scan kernel
+    if (!make_map(&m[i], cols[i], i == 3 || i == 4, T, N, cs, TS)) return CRUX_OK;   // not encodable (exotic pitch): fall back to the scan kernel
 
   const size_t smem = (size_t)stages * stage_bytes;
   const int grid = (int)i64min(n_items64, (int64_t)G_max);
   {
     CruxTimed timed(ctx, CRUX_T_GAE);
-    if (cs == 16) {
-      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(gae_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gae_tma_kernel<16><<<grid, NTHREADS, smem, ctx->stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], a);
-    } else {
-      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(gae_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gae_tma_kernel<32><<<grid, NTHREADS, smem, ctx->stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], a);
-    }
+#define GAE_TMA_LAUNCH(CS_, NCW_)                                                                                                              \
+  do {                                                                                                                                         \
+    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(gae_tma_kernel<CS_, NCW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    gae_tma_kernel<CS_, NCW_><<<grid, n_threads(NCW_), smem, ctx->stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], a);                      \
+  } while (0)
+    if (ncw == 2) { if (cs == 16) GAE_TMA_LAUNCH(16, 2); else GAE_TMA_LAUNCH(32, 2); }
+    else          { if (cs == 16) GAE_TMA_LAUNCH(16, 1); else GAE_TMA_LAUNCH(32, 1); }
+#undef GAE_TMA_LAUNCH
   }
   CRUX_LAUNCHED(ctx);
   ctx->gae_ctr_base += (unsigned int)n_items64 + (unsigned int)grid;   // every CTA takes exactly one index past the end

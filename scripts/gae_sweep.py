@@ -15,7 +15,7 @@ for T, N in shapes:
     ee = done.clone(); ee[999::1000] = 1; ee[-1] = 1
     adv, ret = torch.empty_like(r), torch.empty_like(r)
     run = lambda: ctx.check(ctx.lib.crux_fill_gae_returns(ctx.h, ptr(r), ptr(done), ptr(ee), ptr(vs), ptr(vsp), T, N, 0.99, 0.95, ptr(adv), ptr(ret)))
-    cfgs = [("scan", None), ("tma", None)]
+    cfgs = [("scan", None), ("tma", None), ("tma", "0,0,0,0,1"), ("tma", "0,0,0,0,2")]
     if T >= 64:
         for cs, st, seg, per in itertools.product((16, 32), (3, 4, 6, 7, 8), (0, 16), (1, 2)):
             if st * cs * 128 * 14 * per > 226 * 1024 or os.environ.get("SWEEP_DEFAULT_ONLY"):

@@ -130,7 +130,9 @@ def gae_env(monkeypatch):
 
 @pytest.mark.parametrize("T,N,cfg", [(1, 16, None), (5, 48, None), (64, 128, None), (100, 144, "16,2,1,2"), (257, 272, "16,3,2,2"),
                                      (300, 4112, "32,2,1,1"), (1000, 1040, "32,4,3,2"), (1024, 4096, None), (2049, 160, "16,4,5,2"),
-                                     (513, 16400, None)])
+                                     (513, 16400, None),
+                                     # 64-stream tiles (fifth field = chain warps) and explicit 128-stream tiles on a narrow rollout
+                                     (300, 4112, "32,3,1,1,1"), (257, 272, "16,3,2,2,1"), (1024, 4096, "16,6,0,1,2"), (700, 3088, "0,0,0,0,1")])
 def test_tma_path_against_oracle(ctx, gae_env, T, N, cfg):
     r, done, ee, vs, vsp = _inputs(T, N, seed=T * 7 + N)
     gae_env("tma", cfg)
@@ -141,7 +143,7 @@ def test_tma_path_against_oracle(ctx, gae_env, T, N, cfg):
     assert_close(adv, a0, rtol=1e-5, atol=2e-5, what=f"tma advantage [{T},{N}] cfg={cfg}")
     assert_close(ret, r0, rtol=1e-5, atol=2e-5, what=f"tma return [{T},{N}] cfg={cfg}")
     # the streaming scan IS the sequential recurrence: identical bits for every tiling / segmentation
-    gae_env("tma", "32,2,1,1")
+    gae_env("tma", "32,2,1,1,2")
     adv2, ret2 = _run(ctx, r, done, ee, vs, vsp, 0.99, 0.95)
     assert np.array_equal(adv, adv2) and np.array_equal(ret, ret2)
     # and within tolerance of the register-resident scan kernel
