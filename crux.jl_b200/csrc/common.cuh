@@ -49,6 +49,10 @@ struct crux_ctx {
   unsigned long long *peer_seq_dev = nullptr;  // device-resident sequence number of the last completed peer exchange (local flags + 33):
                                                // kept on the device so that minibatches skipped by the device-side early stop do not advance it
   bool peer_ready = false;
+  // LL (flag-in-data) gradient exchange fused into the reduce / Adam kernels: [2 networks][2 parities][16 ranks][peer_cap] 8-byte
+  // words {float bits, sequence number} in every rank's peer allocation; device-resident per-network sequence numbers / tickets
+  unsigned long long *peer_ll = nullptr;
+  unsigned long long *peer_ll_remote[16] = {nullptr};
 };
 
 int crux_set_err(crux_ctx *ctx, int code, const char *fmt, ...);

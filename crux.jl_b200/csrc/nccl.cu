@@ -153,10 +153,13 @@ int32_t crux_peer_handle(crux_ctx *ctx, uint8_t *handle_out_host, int64_t max_fl
   if (!ctx->peer_recv) {
     ctx->peer_cap = (max_floats + 31) / 32 * 32;
     // one allocation: [2 parities][16 ranks][cap] floats, then [2][16] flags + [1] block counter
-    const size_t bytes = (size_t)32 * ctx->peer_cap * sizeof(float) + 64 * sizeof(unsigned long long);
+    // ... then the LL region of the fused gradient exchange: [2 networks][2 parities][16 ranks][cap] 8-byte words
+    const size_t base_bytes = (size_t)32 * ctx->peer_cap * sizeof(float) + 64 * sizeof(unsigned long long);
+    const size_t bytes = base_bytes + (size_t)64 * ctx->peer_cap * sizeof(unsigned long long);
     CRUX_CHECK_CUDA(ctx, cudaMalloc((void **)&ctx->peer_recv, bytes));
     CRUX_CHECK_CUDA(ctx, cudaMemset(ctx->peer_recv, 0, bytes));
     ctx->peer_flags = (unsigned long long *)((char *)ctx->peer_recv + (size_t)32 * ctx->peer_cap * sizeof(float));
+    ctx->peer_ll = (unsigned long long *)((char *)ctx->peer_recv + base_bytes);
   }
   cudaIpcMemHandle_t h;
   CRUX_CHECK_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->peer_recv));
@@ -182,6 +185,7 @@ int32_t crux_peer_init(crux_ctx *ctx, int32_t rank, int32_t world, const uint8_t
       ctx->peer_recv_remote[p] = (float *)ptr;
     }
     ctx->peer_flags_remote[p] = (unsigned long long *)((char *)ctx->peer_recv_remote[p] + (size_t)32 * ctx->peer_cap * sizeof(float));
+    ctx->peer_ll_remote[p] = (unsigned long long *)((char *)ctx->peer_recv_remote[p] + (size_t)32 * ctx->peer_cap * sizeof(float) + 64 * sizeof(unsigned long long));
   }
   ctx->peer_seq_dev = ctx->peer_flags + 33;
   ctx->peer_ready = true;

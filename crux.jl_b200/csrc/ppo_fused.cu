@@ -1290,19 +1290,20 @@ struct AdamArgs {
   int a2c, head;                                     // head 0: actor (ppo/a2c), 1: critic (mse)
   float *rec;                                        // info record of this minibatch
   const double *norm_part; int n_norm_part;          // per-CTA sums of squares from the reduce kernel (NULL: recompute)
-  // fused gradient all-reduce over NVLink peer memory: the gradient is the rank-ordered sum of the slots every rank's reduce
-  // kernel stored into THIS rank's receive buffer (double-buffered by the parity of the device-resident sequence number)
+  // fused gradient all-reduce over NVLink peer memory (LL protocol): the gradient is the rank-ordered sum of the 8-byte words
+  // {value, sequence number} every rank's reduce kernel stored into THIS rank's receive region of this network (double-buffered by
+  // the parity of the device-resident sequence number); the last CTA of the Adam kernel advances the sequence number
   int peer, world; int64_t peer_cap;
-  const float *peer_recv; const unsigned long long *peer_flags; const unsigned long long *peer_seq_dev;
+  const unsigned long long *ll_recv; unsigned long long *ll_seq; unsigned int *ll_ticket;
   int *ctl; int mb;
   unsigned int *err_flags;
   float *frag; int fI, fO;                           // fragment buffer of the network (NULL: none) and its input / output widths
 };
 __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int n_blocks);
 struct PeerOut {   // where the reduce kernel stores this rank's gradient for the fused all-reduce (enabled == 0: local only)
-  float *recv[16]; unsigned long long *flag[16];
+  unsigned long long *ll[16];          // every rank's LL region of this network: [2 parities][16 ranks][cap] words
   int world, rank, enabled; int64_t cap;
-  unsigned long long *seq_dev;
+  const unsigned long long *seq_dev;   // sequence number of the last completed exchange of this network
 };
 
 // sum the per-CTA partials (double accumulation, fixed order: bit-reproducible) -> gradient vector + tail
@@ -1324,12 +1325,14 @@ __global__ void __launch_bounds__(RW * 32, FUSE ? 1 : 2) reduce_fused_partials_k
                                                                        AdamArgs adam, int fuse_adam, PeerOut peer) {
   if (stopped(ctl, mb)) return;
   unsigned long long pseq = 0ULL;
-  if (peer.enabled) pseq = *(volatile unsigned long long *)peer.seq_dev + 1ULL;   // every CTA reads it before the last one advances it
+  if (peer.enabled) pseq = *(volatile const unsigned long long *)peer.seq_dev + 1ULL;   // advanced by the Adam kernel that consumes this exchange
   const int64_t pbase = ((int64_t)(pseq & 1ULL) * 16 + peer.rank) * peer.cap;
-  auto emit = [&](int idx, float v) {   // local gradient entry + (fused all-reduce) this rank's slot in every peer's receive buffer
+  auto emit = [&](int idx, float v) {   // local gradient entry + (fused all-reduce) one {value, sequence} word in every rank's receive region
     grads[idx] = v;
-    if (peer.enabled)
-      for (int q = 0; q < peer.world; ++q) peer.recv[q][pbase + idx] = v;
+    if (peer.enabled) {
+      const unsigned long long word = ((unsigned long long)(unsigned int)pseq << 32) | (unsigned long long)__float_as_uint(v);
+      for (int q = 0; q < peer.world; ++q) *(volatile unsigned long long *)(peer.ll[q] + pbase + idx) = word;   // single 8-byte store: no fence, no flag
+    }
   };
   __shared__ double sh[RW][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1369,27 +1372,6 @@ __global__ void __launch_bounds__(RW * 32, FUSE ? 1 : 2) reduce_fused_partials_k
     }
     __syncthreads();   // sh is reused by the next group
   }
-  if (peer.enabled) {
-    // fused all-reduce, sending side: when the LAST CTA of this kernel has seen every other CTA's stores, it raises this rank's
-    // arrival flag in every peer (the receiving side is the Adam kernel: it sums the slots while it reads the gradient)
-    __shared__ bool plast;
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) plast = atomicAdd(ticket, 1u) == gridDim.x - 1u;
-    __syncthreads();
-    if (plast && threadIdx.x == 0) {
-      *ticket = 0u;
-      *step_dev += 1;
-      __threadfence_system();
-      for (int q = 0; q < peer.world; ++q) {
-        volatile unsigned long long *f = peer.flag[q] + (int)(pseq & 1ULL) * 16 + peer.rank;
-        *f = pseq;
-      }
-      *peer.seq_dev = pseq;
-      __threadfence_system();
-    }
-    return;
-  }
   if (!FUSE || !fuse_adam) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;
     return;
@@ -1414,23 +1396,24 @@ __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int
   __shared__ double sh[32];
   __shared__ double s_n2, s_c1, s_c2;
   const int nw = blockDim.x >> 5;
-  const float *slot0 = nullptr;
-  if (a.peer) {   // wait until every rank's slice has landed in this rank's receive buffer
-    const unsigned long long seq = *(volatile const unsigned long long *)a.peer_seq_dev;
-    const int par = (int)(seq & 1ULL);
-    if ((int)threadIdx.x < a.world) {
-      const volatile unsigned long long *f = a.peer_flags + par * 16 + threadIdx.x;
-      while (*f < seq) { __nanosleep(64); }
-    }
-    __syncthreads();
-    __threadfence_system();
-    slot0 = a.peer_recv + (int64_t)par * 16 * a.peer_cap;
+  const unsigned long long *slot0 = nullptr;
+  unsigned int seq32 = 0u;
+  if (a.peer) {
+    const unsigned long long seq = *(volatile const unsigned long long *)a.ll_seq + 1ULL;   // the exchange the reduce kernels just sent
+    seq32 = (unsigned int)seq;
+    slot0 = a.ll_recv + (int64_t)(seq & 1ULL) * 16 * a.peer_cap;
   }
-  // gradient entry i (network grads, then the tail): local, or the rank-ordered sum of the peers' slots (identical on every rank)
+  // gradient entry i (network grads, then the tail): local, or the rank-ordered sum of the ranks' words (identical on every rank);
+  // a word is valid once its upper half carries this exchange's sequence number
   auto G = [&](const float *local, int64_t i) -> float {
     if (!slot0) return __ldcg(local);
     float sum = 0.f;
-    for (int q = 0; q < a.world; ++q) sum += __ldcv(slot0 + (int64_t)q * a.peer_cap + i);
+    for (int q = 0; q < a.world; ++q) {
+      const volatile unsigned long long *p = slot0 + (int64_t)q * a.peer_cap + i;
+      unsigned long long x = *p;
+      while ((unsigned int)(x >> 32) != seq32) x = *p;
+      sum += __uint_as_float((unsigned int)x);
+    }
     return sum;
   };
   const int64_t off_ls = a.n, off_sums = (int64_t)a.n + 64;
@@ -1508,6 +1491,13 @@ __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int
 __global__ void __launch_bounds__(256) fused_adam_kernel(AdamArgs a) {
   if (stopped(a.ctl, a.mb)) return;
   adam_body(a, blockIdx.x, gridDim.x);
+  if (a.peer) {   // the LAST CTA (every other one has read the sequence number long ago) closes this network's exchange
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(a.ll_ticket, 1u) == gridDim.x - 1u) {
+      *a.ll_ticket = 0u;
+      *a.ll_seq = *a.ll_seq + 1ULL;
+    }
+  }
 }
 
 __global__ void fused_ctl_reset_kernel(int *ctl) { ctl[0] = 0; ctl[1] = 0; }
@@ -1742,18 +1732,20 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   // one SM: measured 20.5 us against 6.5 + 6.9 us for the two separate kernels (profiles/r1_notes.md) -> opt-in only.
   const int fuse_adam = (ctx->world == 1 && getenv("CRUX_FUSE_ADAM")) ? 1 : 0;
   if (ctx->world == 1) { g.norm_part = mlp->norm_part; g.n_norm_part = rblocks; }
-  // multi-GPU: the gradient all-reduce is fused into these two kernels when the one-shot peer buffers are mapped (crux_peer_init):
-  // the reduce kernel stores its result straight into every peer's receive slot, the Adam kernel sums the slots as it reads.
+  // multi-GPU: when the peer buffers are mapped (crux_peer_init) the gradient all-reduce is fused into these two kernels with the LL
+  // (flag-in-data) protocol: the reduce kernel stores every entry as one 8-byte {value, sequence} word straight into every rank's
+  // receive region over NVLink, the Adam kernel spins on the words as it sums them -- no fences, no flag round trip, no NCCL launch.
+  // Each network (head) has its own region and sequence number, so the actor and critic exchanges can be in flight concurrently.
+  // (The first, fence-based version of this fusion measured 22 + 28 us per minibatch against 10 + 17 (NCCL) + 9 us.)
   PeerOut po;
   memset(&po, 0, sizeof(po));
-  // Measured on 2 x B200 (profiles/r1_notes.md): the fence-based fused exchange costs 22 + 28 us per minibatch against
-  // 10 + 17 (NCCL LL all-reduce) + 9 us -> opt-in (CRUX_PEER_FUSION=1) until it is rebuilt on flag-in-data (LL) stores.
-  const bool use_peer = ctx->world > 1 && ctx->peer_ready && mlp->n_params + CRUX_GRAD_TAIL <= ctx->peer_cap && getenv("CRUX_PEER_FUSION");
+  const bool use_peer = ctx->world > 1 && ctx->peer_ready && ctx->peer_ll && mlp->n_params + CRUX_GRAD_TAIL <= ctx->peer_cap && !getenv("CRUX_NO_PEER_LL");
   if (use_peer) {
-    po.enabled = 1; po.world = ctx->world; po.rank = ctx->rank; po.cap = ctx->peer_cap; po.seq_dev = ctx->peer_seq_dev;
-    for (int q = 0; q < ctx->world; ++q) { po.recv[q] = ctx->peer_recv_remote[q]; po.flag[q] = ctx->peer_flags_remote[q]; }
-    g.peer = 1; g.world = ctx->world; g.peer_cap = ctx->peer_cap; g.peer_recv = ctx->peer_recv; g.peer_flags = ctx->peer_flags;
-    g.peer_seq_dev = ctx->peer_seq_dev;
+    const int64_t net_off = (int64_t)head * 32 * ctx->peer_cap;   // [network][parity][rank][cap]
+    po.enabled = 1; po.world = ctx->world; po.rank = ctx->rank; po.cap = ctx->peer_cap; po.seq_dev = ctx->peer_flags + 40 + head;
+    for (int q = 0; q < ctx->world; ++q) po.ll[q] = ctx->peer_ll_remote[q] + net_off;
+    g.peer = 1; g.world = ctx->world; g.peer_cap = ctx->peer_cap; g.ll_recv = ctx->peer_ll + net_off;
+    g.ll_seq = ctx->peer_flags + 40 + head; g.ll_ticket = reinterpret_cast<unsigned int *>(ctx->peer_flags + 48 + head);
   }
   { CruxTimed timed(ctx, CRUX_T_REDUCE);
   if (fuse_adam)
@@ -1829,9 +1821,10 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
   // with the actor epochs: the small reduce / all-reduce / Adam launches of one network hide behind the minibatch kernel of the
   // other.  Results are exactly those of the sequential order (separate parameters, optimisers, scratch buffers and flags).
   cudaStream_t main_stream = ctx->stream;
-  // With several ranks the critic's gradient all-reduces go through the second communicator (nccl.cu); the single-buffered peer
-  // exchange cannot run two sequences at once.
-  const bool side = (ctx->world == 1 || (ctx->nccl_comm_side && !ctx->peer_ready)) && nmb_c > 0 && hp->critic_epochs > 0 && !ctx->timing &&
+  // With several ranks the critic's gradient exchange uses its own LL region (or, without peer buffers, the second NCCL
+  // communicator of nccl.cu).
+  const bool ll = ctx->peer_ready && ctx->peer_ll && !getenv("CRUX_NO_PEER_LL");   // per-network exchange regions: safe to run both at once
+  const bool side = (ctx->world == 1 || ll || (ctx->nccl_comm_side && !ctx->peer_ready)) && nmb_c > 0 && hp->critic_epochs > 0 && !ctx->timing &&
                     !getenv("CRUX_NO_SIDE_STREAM") && ctx->side_stream;
   if (side) ctx->stream = ctx->side_stream;   // every launch helper below enqueues on ctx->stream
   total = 0;

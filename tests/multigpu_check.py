@@ -25,7 +25,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = crux.Context(local)
-    ctx.init_distributed(rank, world)
+    ctx.init_distributed(rank, world)   # NCCL only first; the peer buffers are mapped further down
     dev = lambda x, dt=None: ctx.to_device(x, dt)
 
     def allreduce_check(tag, iters):
@@ -128,8 +128,12 @@ def main():
     ctx.check(ctx.lib.crux_peer_init(ctx.h, rank, world, allh))
     dist.barrier()
     allreduce_check("peer", 50)
-    ppo_check("fused peer all-reduce")      # reduce kernel stores into the peers' slots, Adam kernel sums them
-    ppo_check("fused peer all-reduce, 2nd") # after early-stopped (skipped) exchanges: the device sequence numbers stayed in step
+    ppo_check("fused LL peer exchange")      # reduce kernel stores {value, seq} words into every rank's region, Adam kernel sums them
+    ppo_check("fused LL peer exchange, 2nd") # after early-stopped (skipped) exchanges: the device sequence numbers stayed in step
+    os.environ["CRUX_NO_PEER_LL"] = "1"
+    ppo_check("one-shot peer all-reduce between reduce and Adam")
+    os.environ.pop("CRUX_NO_PEER_LL")
+    ppo_check("fused LL peer exchange, 3rd")
     allreduce_check("peer after ppo", 5)
     # timing of the two paths for the 44 KB gradient payload
     for tag in ("peer",):
