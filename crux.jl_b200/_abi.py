@@ -97,6 +97,10 @@ _SIGS = {
     "crux_gaussian_entropy": [_vp, _vp, _i64, _vp],
     "crux_discrete_argmax": [_vp, _vp, _i64, _i32, _vp],
     "crux_discrete_explore": [_vp, _vp, _i64, _i32, _vp, _u64, _u64, _vp, _vp],
+    "crux_discrete_explore_t": [_vp, _vp, _i64, _i32, _f32, _vp, _u64, _u64, _vp, _vp],
+    "crux_discrete_logpdf_t": [_vp, _vp, _vp, _i64, _i32, _f32, _vp],
+    "crux_discrete_entropy_t": [_vp, _vp, _i64, _i32, _f32, _vp],
+    "crux_softq_target": [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _vp],
     "crux_discrete_logpdf": [_vp, _vp, _vp, _i64, _i32, _vp],
     "crux_discrete_entropy": [_vp, _vp, _i64, _i32, _vp],
     "crux_discrete_eps_greedy": [_vp, _vp, _i64, _i32, _f64, _vp, _u64, _u64, _vp, _vp, _vp],
@@ -105,6 +109,11 @@ _SIGS = {
     "crux_normalize_obs": [_vp, _vp, _i64, _f32, _f32, _vp],
     "crux_fill_gae_returns": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _vp, _vp],
     "crux_whiten": [_vp, _vp, _i64],
+    "crux_noise_explore": [_vp, _vp, _i64, _i32, _f32, _f32, _f32, _vp, _i32, _vp, _i32, _vp, _u64, _u64],
+    "crux_ddpg_create": [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _pp],
+    "crux_ddpg_destroy": [_vp],
+    "crux_ddpg_train": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _i32, _f32, _f32, _f32, _vp, _i32, _vp, _i32, _vp, _u64, _u64, _i32, _i32,
+                        _vp, _vp],
     "crux_dqn_target": [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp],
     "crux_sac_target": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp],
     "crux_td_error": [_vp, _vp, _vp, _i64, _vp],

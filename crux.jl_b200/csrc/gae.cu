@@ -203,6 +203,18 @@ __global__ void dqn_target_kernel(const float *__restrict__ r, const uint8_t *__
   for (int a = 1; a < nA; ++a) m = fmaxf(m, q[i * nA + a]);
   y[i] = r[i] + (gamma * (1.0f - (float)done[i])) * m;  // rl/dqn.jl:5 (left-to-right)
 }
+// softq_target rl/softq.jl:13-17 with soft_value :8: α .* logsumexp(Q⁻(sp) ./ α) (NNlib logsumexp: max + log(Σ exp(x - max)))
+__global__ void softq_target_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done,
+                                    const float *__restrict__ q, int64_t B, int nA, float gamma, float alpha, float *__restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  float m = q[i * nA] / alpha;
+  for (int a = 1; a < nA; ++a) m = fmaxf(m, q[i * nA + a] / alpha);
+  float s = 0.f;
+  for (int a = 0; a < nA; ++a) s += expf(q[i * nA + a] / alpha - m);
+  const float v = alpha * (m + logf(s));
+  y[i] = r[i] + (gamma * (1.0f - (float)done[i])) * v;
+}
 __global__ void sac_target_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done,
                                   const float *__restrict__ q1, const float *__restrict__ q2,
                                   const float *__restrict__ logp, int64_t B, float gamma,
@@ -315,6 +327,16 @@ int32_t crux_dqn_target(crux_ctx *ctx, const float *r, const uint8_t *done, cons
   CRUX_REQUIRE(ctx, B >= 0 && nA >= 1, "crux_dqn_target: bad shape");
   if (B == 0) return CRUX_OK;
   dqn_target_kernel<<<(unsigned)cdiv(B, 256), 256, 0, ctx->stream>>>(r, done, q_sp, B, nA, gamma, y);
+  CRUX_LAUNCHED(ctx);
+  return CRUX_OK;
+}
+
+int32_t crux_softq_target(crux_ctx *ctx, const float *r, const uint8_t *done, const float *q_sp, int64_t B,
+                          int32_t nA, float gamma, float alpha, float *y) {
+  if (!ctx) return CRUX_ERR_INVALID;
+  CRUX_REQUIRE(ctx, B >= 0 && nA >= 1 && alpha > 0.f, "crux_softq_target: bad shape or temperature");
+  if (B == 0) return CRUX_OK;
+  softq_target_kernel<<<(unsigned)cdiv(B, 256), 256, 0, ctx->stream>>>(r, done, q_sp, B, nA, gamma, alpha, y);
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;
 }

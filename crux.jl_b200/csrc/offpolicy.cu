@@ -1,5 +1,6 @@
-// Off-policy updates (src/model_free/off_policy.jl:66-111): the DQN critic step (td_loss, utils.jl:76-87)
-// and one SAC value_training epoch (rl/sac.jl:4-52): target -> temperature -> double-Q critic -> actor -> polyak.
+// Off-policy updates (src/model_free/off_policy.jl:66-111): the DQN critic step (td_loss, utils.jl:76-87),
+// one SAC value_training epoch (rl/sac.jl:4-52): target -> temperature -> double-Q critic -> actor -> polyak,
+// and one DDPG / TD3 epoch (rl/ddpg.jl:6-25, rl/td3.jl:4-12): (smoothed) target -> critic(s) -> deterministic actor -> polyak.
 #include "policy.cuh"
 
 namespace {
@@ -186,6 +187,87 @@ __global__ void sac_actor_bwd_head_kernel(const float *__restrict__ net, const f
   }
 }
 
+// ---- DDPG / TD3 -----------------------------------------------------------------------------------------
+// exploration(::GaussianNoiseExplorationPolicy) policies.jl:510-514 on an action batch that action(π_on, s) already filled:
+//   a = clamp(a + clamp(randn * σ(i), ϵ_min, ϵ_max), a_min, a_max); a_min / a_max broadcast when they have one entry.
+struct NoiseBounds { float lo[32], hi[32]; int n_lo, n_hi; };
+__global__ void noise_clamp_kernel(float *__restrict__ a, int64_t B, int A, float sigma, float eps_min, float eps_max, NoiseBounds nb,
+                                   const float *__restrict__ eps_in, uint64_t seed, uint64_t ctr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  float nrm[4];
+  for (int j = 0; j < A; ++j) {
+    float e;
+    if (eps_in) e = eps_in[i * A + j];
+    else {
+      if ((j & 3) == 0) {
+        const Philox4 p = philox4x32_10(seed, ctr, (uint64_t)i * ((A + 3) / 4) + (j >> 2));
+        box_muller(p.x, p.y, nrm[0], nrm[1]);
+        box_muller(p.z, p.w, nrm[2], nrm[3]);
+      }
+      e = nrm[j & 3];
+    }
+    const float n = fminf(fmaxf(e * sigma, eps_min), eps_max);
+    const float lo = nb.lo[nb.n_lo == 1 ? 0 : j], hi = nb.hi[nb.n_hi == 1 ? 0 : j];
+    a[i * A + j] = fminf(fmaxf(a[i * A + j] + n, lo), hi);
+  }
+}
+// ddpg_target rl/ddpg.jl:6-8 / td3_target rl/td3.jl:4-7: y = r + γ(1-done)·Q⁻(sp, a') or ·min(Q1⁻, Q2⁻)(sp, a')
+__global__ void ddpg_target_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done, const float *__restrict__ q1,
+                                   const float *__restrict__ q2, int64_t B, float gamma, float *__restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const float q = q2 ? fminf(q1[i], q2[i]) : q1[i];
+  y[i] = r[i] + (gamma * (1.0f - (float)done[i])) * q;
+}
+// td_loss utils.jl:76-87 on a ContinuousNetwork critic: mse(Q(s,a), y); part[b] = {sum e, sum q}
+__global__ void q_mse_head_kernel(const float *__restrict__ q, const float *__restrict__ y, int64_t B, float inv_b, float *__restrict__ dq,
+                                  double *__restrict__ part) {
+  __shared__ double sh[32];
+  double e = 0.0, sq = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = q[i] - y[i];
+    e += (double)(d * d); sq += (double)q[i];
+    dq[i] = 2.f * d * inv_b;
+  }
+  double r;
+  r = block_sum_d(e, sh); if (threadIdx.x == 0) part[2 * blockIdx.x] = r;
+  r = block_sum_d(sq, sh); if (threadIdx.x == 0) part[2 * blockIdx.x + 1] = r;
+}
+__global__ void q_mse_record_kernel(const double *__restrict__ part, int nb, int64_t B, float *__restrict__ info) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < nb; ++i) { a += part[2 * i]; b += part[2 * i + 1]; }
+    info[1] = (float)(a / (double)B);
+    info[6] = (float)(b / (double)B);
+  }
+}
+// ddpg_actor_loss rl/ddpg.jl:25 / td3_actor_loss rl/td3.jl:12: -mean(Q(s, μ(s))): dL/dQ = -1/B; part[b] = sum q
+__global__ void ddpg_actor_seed_kernel(const float *__restrict__ q, int64_t B, float inv_b, float *__restrict__ dq, double *__restrict__ part) {
+  __shared__ double sh[32];
+  double sq = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+    sq += (double)q[i];
+    dq[i] = -inv_b;
+  }
+  const double r = block_sum_d(sq, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = r;
+}
+__global__ void ddpg_actor_record_kernel(const double *__restrict__ part, int nb, int64_t B, float *__restrict__ info) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0;
+    for (int i = 0; i < nb; ++i) a += part[i];
+    info[3] = (float)(-(a / (double)B));
+  }
+}
+// dL/da = the action columns of dL/dvcat(s, a)
+__global__ void slice_action_grad_kernel(const float *__restrict__ dcat, int sdim, int A, int64_t B, float *__restrict__ da) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B * A; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / A; const int j = (int)(i % A);
+    da[i] = dcat[b * (sdim + A) + sdim + j];
+  }
+}
+
 __global__ void concat2_kernel(const float *__restrict__ s, int sd, const float *__restrict__ a, int ad, int64_t B, float *__restrict__ out) {
   const int d = sd + ad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B * d; i += (int64_t)gridDim.x * blockDim.x) {
@@ -206,6 +288,17 @@ struct crux_sac_state {
   int *alpha_step = nullptr;
   float *info = nullptr;        // device [8]
   float *ws = nullptr;          // workspace
+  size_t ws_bytes = 0;
+  double *part = nullptr;
+};
+
+struct crux_ddpg_state {
+  crux_ctx *ctx = nullptr;
+  crux_mlp *actor = nullptr, *actor_t = nullptr;
+  crux_mlp *q1 = nullptr, *q2 = nullptr, *q1t = nullptr, *q2t = nullptr;   // q2 == nullptr: DDPG (one critic)
+  float tau = 0.005f;
+  float *info = nullptr;        // device [8]
+  float *ws = nullptr;
   size_t ws_bytes = 0;
   double *part = nullptr;
 };
@@ -380,6 +473,160 @@ int32_t crux_sac_train(crux_sac_state *st, const float *s, const float *a, const
   // 5. target_update (off_policy.jl:100): polyak τ on the critics (the actor copy inside π⁻ is never read)
   rc = crux_mlp_polyak(st->q1t, st->q1, st->tau); if (rc) return rc;
   rc = crux_mlp_polyak(st->q2t, st->q2, st->tau); if (rc) return rc;
+
+  if (info_out_host) {
+    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(info_out_host, st->info, 8 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return crux_ctx_check(ctx);
+  }
+  return CRUX_OK;
+}
+
+static int fill_bounds(crux_ctx *ctx, NoiseBounds &nb, const float *a_min, int32_t n_min, const float *a_max, int32_t n_max, int A) {
+  if ((n_min != 0 && n_min != 1 && n_min != A) || (n_max != 0 && n_max != 1 && n_max != A) || A > 32)
+    return crux_set_err(ctx, CRUX_ERR_INVALID, "noise bounds: a_min / a_max need 0, 1 or adim entries (adim <= 32)");
+  nb.n_lo = n_min ? n_min : 1; nb.n_hi = n_max ? n_max : 1;
+  nb.lo[0] = -INFINITY; nb.hi[0] = INFINITY;
+  for (int j = 0; j < n_min; ++j) nb.lo[j] = a_min[j];
+  for (int j = 0; j < n_max; ++j) nb.hi[j] = a_max[j];
+  return CRUX_OK;
+}
+
+int32_t crux_noise_explore(crux_ctx *ctx, float *a, int64_t B, int32_t A, float sigma, float eps_min, float eps_max, const float *a_min,
+                           int32_t n_min, const float *a_max, int32_t n_max, const float *eps_in, uint64_t seed, uint64_t ctr) {
+  if (!ctx) return CRUX_ERR_INVALID;
+  CRUX_REQUIRE(ctx, a && B >= 0 && A >= 1, "crux_noise_explore: bad arguments");
+  NoiseBounds nb;
+  int rc = fill_bounds(ctx, nb, a_min, n_min, a_max, n_max, A); if (rc) return rc;
+  if (B == 0) return CRUX_OK;
+  noise_clamp_kernel<<<(unsigned)cdiv(B, 128), 128, 0, ctx->stream>>>(a, B, A, sigma, eps_min, eps_max, nb, eps_in, seed, ctr);
+  CRUX_LAUNCHED(ctx);
+  return CRUX_OK;
+}
+
+int32_t crux_ddpg_create(crux_mlp *actor, crux_mlp *actor_target, crux_mlp *q1, crux_mlp *q1_target, crux_mlp *q2, crux_mlp *q2_target,
+                         float tau, crux_ddpg_state **out) {
+  if (!actor) return CRUX_ERR_INVALID;
+  crux_ctx *ctx = actor->ctx;
+  CRUX_REQUIRE(ctx, actor_target && q1 && q1_target && out && ((q2 == nullptr) == (q2_target == nullptr)), "crux_ddpg_create: NULL argument");
+  const int sdim = actor->dims[0], A = actor->dims[actor->n_layers];
+  CRUX_REQUIRE(ctx, q1->dims[0] == sdim + A && q1->dims[q1->n_layers] == 1 && (!q2 || (q2->dims[0] == sdim + A && q2->dims[q2->n_layers] == 1)),
+               "crux_ddpg_create: critics must map vcat(s,a) -> 1");
+  CRUX_REQUIRE(ctx, actor->n_params == actor_target->n_params && q1->n_params == q1_target->n_params && (!q2 || q2->n_params == q2_target->n_params),
+               "crux_ddpg_create: target shape mismatch");
+  crux_ddpg_state *st = new crux_ddpg_state();
+  st->ctx = ctx; st->actor = actor; st->actor_t = actor_target; st->q1 = q1; st->q1t = q1_target; st->q2 = q2; st->q2t = q2_target; st->tau = tau;
+  if (cudaMalloc((void **)&st->info, 8 * sizeof(float)) != cudaSuccess || cudaMalloc((void **)&st->part, 4096 * sizeof(double)) != cudaSuccess) {
+    crux_ddpg_destroy(st);
+    return crux_set_err(ctx, CRUX_ERR_OOM, "crux_ddpg_create: cudaMalloc");
+  }
+  cudaMemsetAsync(st->info, 0, 8 * sizeof(float), ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  *out = st;
+  return CRUX_OK;
+}
+
+int32_t crux_ddpg_destroy(crux_ddpg_state *st) {
+  if (!st) return CRUX_OK;
+  cudaStreamSynchronize(st->ctx->stream);
+  if (st->info) cudaFree(st->info);
+  if (st->ws) cudaFree(st->ws);
+  if (st->part) cudaFree(st->part);
+  delete st;
+  return CRUX_OK;
+}
+
+int32_t crux_ddpg_train(crux_ddpg_state *st, const float *s, const float *a, const float *sp, const float *r, const uint8_t *done, int64_t B,
+                        float gamma, int32_t smooth, float sigma, float eps_min, float eps_max, const float *a_min, int32_t n_min,
+                        const float *a_max, int32_t n_max, const float *eps_smooth, uint64_t seed, uint64_t ctr, int32_t train_critic,
+                        int32_t train_actor, float *y_out, float *info_out_host) {
+  if (!st) return CRUX_ERR_INVALID;
+  crux_ctx *ctx = st->ctx;
+  CRUX_REQUIRE(ctx, B >= 1 && s && a && sp && r && done, "crux_ddpg_train: bad arguments");
+  crux_mlp *act = st->actor;
+  const int sdim = act->dims[0], La = act->n_layers, A = act->dims[La], ld = sdim + A;
+  NoiseBounds nb;
+  int rc = fill_bounds(ctx, nb, a_min, n_min, a_max, n_max, A); if (rc) return rc;
+  // workspace: ap[B][A], cat[B][ld], q1v[B], q2v[B], y[B], dq1[B], dq2[B], da[B][A]
+  const size_t nfl = (size_t)B * (A + ld + 5 + A);
+  if (st->ws_bytes < nfl * sizeof(float)) {
+    CRUX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (st->ws) cudaFree(st->ws);
+    st->ws = nullptr; st->ws_bytes = 0;
+    if (cudaMalloc((void **)&st->ws, nfl * sizeof(float) * 5 / 4) != cudaSuccess) return crux_set_err(ctx, CRUX_ERR_OOM, "crux_ddpg_train: workspace");
+    st->ws_bytes = nfl * sizeof(float) * 5 / 4;
+  }
+  float *ap = st->ws, *cat = ap + (size_t)B * A, *q1v = cat + (size_t)B * ld, *q2v = q1v + B, *y = q2v + B, *dq1 = y + B, *dq2 = dq1 + B,
+        *da = dq2 + B;
+  const unsigned rb = (unsigned)cdiv(B, 128);
+  const unsigned eb = (unsigned)i64min(cdiv(B * ld, 256), (int64_t)ctx->num_sms * 8);
+  const int nb_ = (int)i64min(cdiv(B, 256), 256);
+  const float inv_b = 1.0f / (float)B;
+
+  // 1. target (off_policy.jl:80): a' = action(π⁻, sp) [+ clipped smoothing noise, then the action clamp], y from the TARGET critic(s)
+  rc = mlp_forward_out(st->actor_t, sp, B, ap); if (rc) return rc;
+  if (smooth) {
+    noise_clamp_kernel<<<rb, 128, 0, ctx->stream>>>(ap, B, A, sigma, eps_min, eps_max, nb, eps_smooth, seed, ctr);
+    CRUX_LAUNCHED(ctx);
+  }
+  concat2_kernel<<<eb, 256, 0, ctx->stream>>>(sp, sdim, ap, A, B, cat);
+  CRUX_LAUNCHED(ctx);
+  rc = mlp_forward_out(st->q1t, cat, B, q1v); if (rc) return rc;
+  if (st->q2) { rc = mlp_forward_out(st->q2t, cat, B, q2v); if (rc) return rc; }
+  ddpg_target_kernel<<<(unsigned)cdiv(B, 256), 256, 0, ctx->stream>>>(r, done, q1v, st->q2 ? q2v : nullptr, B, gamma, y);
+  CRUX_LAUNCHED(ctx);
+  if (y_out) CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(y_out, y, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+
+  // 2. critic step (off_policy.jl:91-93): td_loss on one critic (DDPG) or double_Q_loss with one optimiser over (Q1, Q2) (TD3)
+  if (train_critic) {
+    concat2_kernel<<<eb, 256, 0, ctx->stream>>>(s, sdim, a, A, B, cat);
+    CRUX_LAUNCHED(ctx);
+    rc = mlp_forward_keep(st->q1, cat, B, nullptr); if (rc) return rc;
+    if (st->q2) {
+      rc = mlp_forward_keep(st->q2, cat, B, nullptr); if (rc) return rc;
+      sac_critic_head_kernel<<<nb_, 256, 0, ctx->stream>>>(st->q1->act[st->q1->n_layers], st->q2->act[st->q2->n_layers], y, B, inv_b, dq1, dq2,
+                                                          st->part);
+      CRUX_LAUNCHED(ctx);
+      sac_critic_record_kernel<<<1, 32, 0, ctx->stream>>>(st->part, nb_, B, st->info);
+      CRUX_LAUNCHED(ctx);
+      rc = mlp_backward(st->q1, cat, B, dq1, false, false, true, nullptr); if (rc) return rc;
+      rc = mlp_backward(st->q2, cat, B, dq2, false, false, true, nullptr); if (rc) return rc;
+      AdamSegs segs;
+      segs.n = 2;
+      segs.s[0] = AdamSeg{st->q1->params, st->q1->grads, st->q1->m, st->q1->v, st->q1->n_params};
+      segs.s[1] = AdamSeg{st->q2->params, st->q2->grads, st->q2->m, st->q2->v, st->q2->n_params};
+      rc = adam_step_segments(ctx, segs, st->q1->eta, st->q1->beta1, st->q1->beta2, st->q1->eps, st->q1->step_dev, st->info + 2, nullptr,
+                              st->q1->norm_part);
+      if (rc) return rc;
+    } else {
+      q_mse_head_kernel<<<nb_, 256, 0, ctx->stream>>>(st->q1->act[st->q1->n_layers], y, B, inv_b, dq1, st->part);
+      CRUX_LAUNCHED(ctx);
+      q_mse_record_kernel<<<1, 32, 0, ctx->stream>>>(st->part, nb_, B, st->info);
+      CRUX_LAUNCHED(ctx);
+      rc = mlp_backward(st->q1, cat, B, dq1, false, false, true, nullptr); if (rc) return rc;
+      rc = mlp_adam_step(st->q1, st->info + 2, nullptr); if (rc) return rc;
+    }
+  }
+
+  // 3. actor step (off_policy.jl:96-101): -mean(Q1(s, μ(s))) through the (already updated, frozen) first critic, then the target update
+  if (train_actor) {
+    rc = mlp_forward_keep(act, s, B, nullptr); if (rc) return rc;
+    concat2_kernel<<<eb, 256, 0, ctx->stream>>>(s, sdim, act->act[La], A, B, cat);
+    CRUX_LAUNCHED(ctx);
+    rc = mlp_forward_keep(st->q1, cat, B, nullptr); if (rc) return rc;
+    ddpg_actor_seed_kernel<<<nb_, 256, 0, ctx->stream>>>(st->q1->act[st->q1->n_layers], B, inv_b, dq1, st->part);
+    CRUX_LAUNCHED(ctx);
+    ddpg_actor_record_kernel<<<1, 32, 0, ctx->stream>>>(st->part, nb_, B, st->info);
+    CRUX_LAUNCHED(ctx);
+    rc = mlp_backward(st->q1, cat, B, dq1, true, false, false, nullptr); if (rc) return rc;
+    slice_action_grad_kernel<<<(unsigned)i64min(cdiv(B * A, 256), (int64_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(st->q1->dz[0], sdim, A, B, da);
+    CRUX_LAUNCHED(ctx);
+    rc = mlp_backward(act, s, B, da, false, false, true, nullptr); if (rc) return rc;
+    rc = mlp_adam_step(act, st->info + 4, nullptr); if (rc) return rc;
+    // target_update(π⁻, π) = polyak_average!(π⁻, π, τ) over every parameter of the policy (off_policy.jl:55,100)
+    rc = crux_mlp_polyak(st->actor_t, act, st->tau); if (rc) return rc;
+    rc = crux_mlp_polyak(st->q1t, st->q1, st->tau); if (rc) return rc;
+    if (st->q2) { rc = crux_mlp_polyak(st->q2t, st->q2, st->tau); if (rc) return rc; }
+  }
 
   if (info_out_host) {
     CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(info_out_host, st->info, 8 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));

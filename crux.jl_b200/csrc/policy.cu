@@ -76,11 +76,13 @@ __global__ void gaussian_entropy_kernel(const float *__restrict__ net, int ld, c
 }
 
 // ---------------------------------------------------------------- discrete
-__device__ __forceinline__ void softmax_row(const float *q, int nA, float *p) {  // NNlib softmax (max-subtracted)
-  float m = q[0];
-  for (int a = 1; a < nA; ++a) m = fmaxf(m, q[a]);
+// NNlib softmax (max-subtracted) of value(π, s) ./ α: α = 1 is the default logit_conversion (policies.jl:108), any other α the
+// SoftQ one (rl/softq.jl:48).  x / 1.f == x bit for bit.
+__device__ __forceinline__ void softmax_row(const float *q, int nA, float alpha, float *p) {
+  float m = q[0] / alpha;
+  for (int a = 1; a < nA; ++a) m = fmaxf(m, q[a] / alpha);
   float s = 0.f;
-  for (int a = 0; a < nA; ++a) { p[a] = expf(q[a] - m); s += p[a]; }
+  for (int a = 0; a < nA; ++a) { p[a] = expf(q[a] / alpha - m); s += p[a]; }
   for (int a = 0; a < nA; ++a) p[a] /= s;
 }
 #define MAX_NA 64
@@ -91,12 +93,12 @@ __global__ void discrete_argmax_kernel(const float *__restrict__ q, int64_t B, i
   for (int a = 1; a < nA; ++a) { const float v = q[i * nA + a]; if (v > bv) { bv = v; best = a; } }
   out[i] = best;
 }
-__global__ void discrete_explore_kernel(const float *__restrict__ q, int64_t B, int nA, const double *__restrict__ u_in,
+__global__ void discrete_explore_kernel(const float *__restrict__ q, int64_t B, int nA, float alpha, const double *__restrict__ u_in,
                                         uint64_t seed, uint64_t ctr, int32_t *__restrict__ a_idx, float *__restrict__ logp) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   float p[MAX_NA];
-  softmax_row(q + i * nA, nA, p);
+  softmax_row(q + i * nA, nA, alpha, p);
   double u;
   if (u_in) u = u_in[i];
   else { const Philox4 r = philox4x32_10(seed, ctr, (uint64_t)i); u = u64_to_unit(r.x, r.y); }
@@ -106,21 +108,21 @@ __global__ void discrete_explore_kernel(const float *__restrict__ q, int64_t B, 
   a_idx[i] = k;
   if (logp) logp[i] = logf(p[k]);  // categorical_logpdf :135
 }
-__global__ void discrete_logpdf_kernel(const float *__restrict__ q, const float *__restrict__ oh, int64_t B, int nA,
+__global__ void discrete_logpdf_kernel(const float *__restrict__ q, const float *__restrict__ oh, int64_t B, int nA, float alpha,
                                        float *__restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   float p[MAX_NA];
-  softmax_row(q + i * nA, nA, p);
+  softmax_row(q + i * nA, nA, alpha, p);
   float s = 0.f;
   for (int a = 0; a < nA; ++a) s += p[a] * oh[i * nA + a];
   out[i] = logf(s);
 }
-__global__ void discrete_entropy_kernel(const float *__restrict__ q, int64_t B, int nA, float *__restrict__ out) {
+__global__ void discrete_entropy_kernel(const float *__restrict__ q, int64_t B, int nA, float alpha, float *__restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   float p[MAX_NA];
-  softmax_row(q + i * nA, nA, p);
+  softmax_row(q + i * nA, nA, alpha, p);
   float s = 0.f;
   for (int a = 0; a < nA; ++a) s += p[a] * logf(p[a] + 1.1920929e-07f);  // eps(Float32) :154
   out[i] = -s;
@@ -287,30 +289,43 @@ int32_t crux_discrete_argmax(crux_ctx *ctx, const float *q, int64_t B, int32_t n
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;
 }
-int32_t crux_discrete_explore(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, const double *u_in, uint64_t seed,
-                              uint64_t ctr, int32_t *a_idx, float *logp) {
+int32_t crux_discrete_explore_t(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, float alpha, const double *u_in, uint64_t seed,
+                                uint64_t ctr, int32_t *a_idx, float *logp) {
   if (!ctx) return CRUX_ERR_INVALID;
   DISCRETE_GUARD(ctx, nA);
+  CRUX_REQUIRE(ctx, alpha > 0.f, "crux_discrete_explore: temperature must be positive");
   if (B <= 0) return CRUX_OK;
-  discrete_explore_kernel<<<(unsigned)cdiv(B, 128), 128, 0, ctx->stream>>>(q, B, nA, u_in, seed, ctr, a_idx, logp);
+  discrete_explore_kernel<<<(unsigned)cdiv(B, 128), 128, 0, ctx->stream>>>(q, B, nA, alpha, u_in, seed, ctr, a_idx, logp);
+  CRUX_LAUNCHED(ctx);
+  return CRUX_OK;
+}
+int32_t crux_discrete_explore(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, const double *u_in, uint64_t seed,
+                              uint64_t ctr, int32_t *a_idx, float *logp) {
+  return crux_discrete_explore_t(ctx, q, B, nA, 1.f, u_in, seed, ctr, a_idx, logp);
+}
+int32_t crux_discrete_logpdf_t(crux_ctx *ctx, const float *q, const float *a_onehot, int64_t B, int32_t nA, float alpha, float *out) {
+  if (!ctx) return CRUX_ERR_INVALID;
+  DISCRETE_GUARD(ctx, nA);
+  CRUX_REQUIRE(ctx, alpha > 0.f, "crux_discrete_logpdf: temperature must be positive");
+  if (B <= 0) return CRUX_OK;
+  discrete_logpdf_kernel<<<(unsigned)cdiv(B, 128), 128, 0, ctx->stream>>>(q, a_onehot, B, nA, alpha, out);
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;
 }
 int32_t crux_discrete_logpdf(crux_ctx *ctx, const float *q, const float *a_onehot, int64_t B, int32_t nA, float *out) {
+  return crux_discrete_logpdf_t(ctx, q, a_onehot, B, nA, 1.f, out);
+}
+int32_t crux_discrete_entropy_t(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, float alpha, float *out) {
   if (!ctx) return CRUX_ERR_INVALID;
   DISCRETE_GUARD(ctx, nA);
+  CRUX_REQUIRE(ctx, alpha > 0.f, "crux_discrete_entropy: temperature must be positive");
   if (B <= 0) return CRUX_OK;
-  discrete_logpdf_kernel<<<(unsigned)cdiv(B, 128), 128, 0, ctx->stream>>>(q, a_onehot, B, nA, out);
+  discrete_entropy_kernel<<<(unsigned)cdiv(B, 128), 128, 0, ctx->stream>>>(q, B, nA, alpha, out);
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;
 }
 int32_t crux_discrete_entropy(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, float *out) {
-  if (!ctx) return CRUX_ERR_INVALID;
-  DISCRETE_GUARD(ctx, nA);
-  if (B <= 0) return CRUX_OK;
-  discrete_entropy_kernel<<<(unsigned)cdiv(B, 128), 128, 0, ctx->stream>>>(q, B, nA, out);
-  CRUX_LAUNCHED(ctx);
-  return CRUX_OK;
+  return crux_discrete_entropy_t(ctx, q, B, nA, 1.f, out);
 }
 int32_t crux_discrete_eps_greedy(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, double eps, const double *u_in,
                                  uint64_t seed, uint64_t ctr, int32_t *a_idx, float *a_onehot, float *logp) {

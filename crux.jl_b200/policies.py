@@ -158,12 +158,14 @@ class ContinuousNetwork(NetworkPolicy):
 class DiscreteNetwork(NetworkPolicy):
     """policies.jl:104-157.  Actions cross as one-hot rows (``a_oh``)."""
 
-    def __init__(self, network, outputs, always_stochastic=False, ctx=None):
+    def __init__(self, network, outputs, always_stochastic=False, ctx=None, temperature=1.0):
         self.network = network
         self.mlp = _MLP(network, ctx)
         self.ctx = self.mlp.ctx
         self.outputs = list(outputs)
         self.always_stochastic = always_stochastic
+        # logit_conversion = (π, s) -> softmax(value(π, s) ./ α): α = 1 is the default (policies.jl:108), SoftQ sets its α (rl/softq.jl:48)
+        self.temperature = float(np.float32(temperature))
         self.device = self.ctx.device
         assert network.layers[-1].out == len(self.outputs)
 
@@ -301,7 +303,7 @@ def exploration(pi, s, eps=None, seed=0, ctr=0, **_):
         B, nA = q.shape
         u = None if eps is None else _as_dev(ctx, np.asarray(eps, dtype=np.float64).reshape(-1, 1), torch.float64)
         idx, lp = ctx.empty((B,), torch.int32), ctx.empty((B, 1))
-        ctx.check(ctx.lib.crux_discrete_explore(ctx.h, ptr(q), B, nA, ptr(u), seed, ctr, ptr(idx), ptr(lp)))
+        ctx.check(ctx.lib.crux_discrete_explore_t(ctx.h, ptr(q), B, nA, pi.temperature, ptr(u), seed, ctr, ptr(idx), ptr(lp)))
         return idx, lp
     raise TypeError(f"exploration: unsupported policy {type(pi).__name__}")
 
@@ -318,7 +320,7 @@ def logpdf(pi, s, a):
         return out
     if isinstance(pi, DiscreteNetwork):
         q = pi.mlp.forward(s)
-        ctx.check(ctx.lib.crux_discrete_logpdf(ctx.h, ptr(q), ptr(a), q.shape[0], q.shape[1], ptr(out)))
+        ctx.check(ctx.lib.crux_discrete_logpdf_t(ctx.h, ptr(q), ptr(a), q.shape[0], q.shape[1], pi.temperature, ptr(out)))
         return out
     raise TypeError(f"logpdf: unsupported policy {type(pi).__name__}")
 
@@ -339,7 +341,7 @@ def entropy(pi, s):
     if isinstance(pi, DiscreteNetwork):
         q = pi.mlp.forward(s)
         out = ctx.empty((B, 1))
-        ctx.check(ctx.lib.crux_discrete_entropy(ctx.h, ptr(q), B, q.shape[1], ptr(out)))
+        ctx.check(ctx.lib.crux_discrete_entropy_t(ctx.h, ptr(q), B, q.shape[1], pi.temperature, ptr(out)))
         return out
     raise TypeError(f"entropy: unsupported policy {type(pi).__name__}")
 
@@ -391,7 +393,7 @@ def deepcopy(pi):
     if isinstance(pi, GaussianPolicy):
         return GaussianPolicy(deepcopy(pi.mu), pi.log_sigma.cpu().numpy(), pi.always_stochastic)
     if isinstance(pi, DiscreteNetwork):
-        return DiscreteNetwork(chain_of(pi.mlp), pi.outputs, pi.always_stochastic, pi.ctx)
+        return DiscreteNetwork(chain_of(pi.mlp), pi.outputs, pi.always_stochastic, pi.ctx, pi.temperature)
     if isinstance(pi, ContinuousNetwork):
         return ContinuousNetwork(chain_of(pi.mlp), pi.output_dim, pi.ctx)
     raise TypeError(type(pi))
@@ -463,13 +465,20 @@ class GaussianNoiseExplorationPolicy(Policy):
         self.sigma = sigma if callable(sigma) else (lambda i, s=sigma: s)
         self.a_min, self.a_max, self.eps_min, self.eps_max = a_min, a_max, eps_min, eps_max
 
+    def bounds(self):
+        """(a_min, a_max) as float32 host vectors, or None for an unbounded side (n = 0 across the ABI)."""
+        f = lambda v, inf: None if np.all(np.asarray(v, dtype=np.float64) == inf) else np.ascontiguousarray(np.atleast_1d(v), dtype=np.float32)
+        return f(self.a_min, -math.inf), f(self.a_max, math.inf)
+
     def exploration(self, s, pi_on, i, eps=None, seed=0, ctr=0):
-        a = action(pi_on, s)
-        e = torch.randn(a.shape, device=a.device) if eps is None else _as_dev(pi_on.ctx, eps)
-        noise = torch.clamp(e * float(self.sigma(i)), self.eps_min, self.eps_max)
-        amin = torch.as_tensor(self.a_min, device=a.device, dtype=torch.float32)
-        amax = torch.as_tensor(self.a_max, device=a.device, dtype=torch.float32)
-        return torch.minimum(torch.maximum(a + noise, amin), amax), float("nan")
+        ctx = pi_on.ctx
+        a = action(pi_on, s).contiguous().clone()   # the noise is applied in place, never on the network's own output buffer
+        B, A = a.shape
+        e = None if eps is None else _as_dev(ctx, np.ascontiguousarray(eps, dtype=np.float32))
+        lo, hi = self.bounds()
+        ctx.check(ctx.lib.crux_noise_explore(ctx.h, ptr(a), B, A, float(np.float32(self.sigma(i))), float(self.eps_min), float(self.eps_max),
+                                             ptr(lo), 0 if lo is None else lo.size, ptr(hi), 0 if hi is None else hi.size, ptr(e), seed, ctr))
+        return a, float("nan")
 
 
 class FirstExplorePolicy(Policy):

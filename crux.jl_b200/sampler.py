@@ -116,7 +116,7 @@ class Sampler:
                 if logp_out is not None:
                     logp_out.copy_(lp.reshape(logp_out.shape))
                 return idx
-            a, lp = pe.exploration(obs, pi, i, **({"eps": noise} if noise is not None else {}))
+            a, lp = pe.exploration(obs, pi, i, seed=self.seed, ctr=ctr, **({"eps": noise} if noise is not None else {}))
             a_out.copy_(a.reshape(a_out.shape))
             if logp_out is not None:
                 logp_out.fill_(float("nan") if isinstance(lp, float) else 0.0)

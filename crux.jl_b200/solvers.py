@@ -90,7 +90,7 @@ class OnPolicySolver:
 
     def __init__(self, agent, S, N=1000, dN=200, max_steps=100, log=None, i=0, a_opt=None, c_opt=None, P=None,
                  post_sample_callback=None, post_batch_callback=None, lam_gae=0.95, required_columns=(), a2c=False, seed=0,
-                 interaction_storage=None):
+                 interaction_storage=None, weight_column="advantage"):
         self.agent = agent if isinstance(agent, PolicyParams) else PolicyParams(agent)
         self.S, self.N, self.dN, self.max_steps, self.log, self.i = S, int(N), int(dN), int(max_steps), log, int(i)
         self.a_opt, self.c_opt, self.P = a_opt, c_opt, dict(P or {})
@@ -99,9 +99,14 @@ class OnPolicySolver:
         self.interaction_storage = interaction_storage
         self.update_count = 0
         pi = self.agent.pi
-        assert isinstance(pi, ActorCritic) and isinstance(pi.A, GaussianPolicy) and not pi.A.squashed and isinstance(pi.C, ContinuousNetwork), \
-            "the fused on-policy update supports ActorCritic(GaussianPolicy(μ, logΣ vector), ContinuousNetwork) (rl/ppo.jl examples)"
-        _set_adam(pi.A.mu.mlp, a_opt.optimizer)
+        self.weight_column = weight_column
+        A = pi.A if isinstance(pi, ActorCritic) else pi
+        assert isinstance(A, GaussianPolicy) and not A.squashed, \
+            "the fused on-policy update supports GaussianPolicy(μ, logΣ vector) actors (rl/ppo.jl, rl/reinforce.jl examples)"
+        assert c_opt is None or (isinstance(pi, ActorCritic) and isinstance(pi.C, ContinuousNetwork)), \
+            "a critic optimiser needs ActorCritic(GaussianPolicy, ContinuousNetwork)"
+        self._actor = A
+        _set_adam(A.mu.mlp, a_opt.optimizer)
         if c_opt is not None:
             _set_adam(pi.C.mlp, c_opt.optimizer)
         self.buffer = None
@@ -130,9 +135,9 @@ class OnPolicySolver:
         self.update_count += 1
         self._hp_last, self._n_last = hp, n
         self._keep = (oa, oc)
-        ctx.check(ctx.lib.crux_ppo_update_async(pi.A.h, pi.C.mlp.h if self.c_opt is not None else None, ptr(D["s"]), ptr(D["a"]),
-                                                ptr(D["logprob"]), ptr(D["advantage"]), ptr(D["return"]), n, C.byref(hp), ptr(oa), ptr(oc),
-                                                self.seed * 1000003 + self.update_count))
+        ctx.check(ctx.lib.crux_ppo_update_async(self._actor.h, pi.C.mlp.h if self.c_opt is not None else None, ptr(D["s"]), ptr(D["a"]),
+                                                ptr(D["logprob"]), ptr(D[self.weight_column]), ptr(D["return"]), n, C.byref(hp), ptr(oa),
+                                                ptr(oc), self.seed * 1000003 + self.update_count))
         return self.training_info  # lazily evaluated: reading it synchronises
 
     def training_info(self):
@@ -141,7 +146,7 @@ class OnPolicySolver:
         pi, ctx = self.agent.pi, self.agent.pi.ctx
         hp, n = self._hp_last, self._n_last
         pa, pc = C.c_void_p(), C.c_void_p()
-        ctx.check(ctx.lib.crux_ppo_info_ptrs(pi.A.h, C.byref(pa), C.byref(pc)))
+        ctx.check(ctx.lib.crux_ppo_info_ptrs(self._actor.h, C.byref(pa), C.byref(pc)))
         nmb_a, nmb_c = -(-n // hp.actor_batch), -(-n // hp.critic_batch)
         ia = view(pa.value, (max(1, hp.actor_epochs * nmb_a), 8), _abi.F32, ctx.device).cpu().numpy()
         ctx.check_flags()
@@ -190,6 +195,16 @@ def A2C(pi, S, lp=1.0, le=0.1, a_opt=None, c_opt=None, log=None, required_column
     cols = list(dict.fromkeys(list(required_columns) + ["return", "logprob", "advantage"]))
     return OnPolicySolver(PolicyParams(pi), S, P={"lp": F32(lp), "le": F32(le)}, a_opt=a, c_opt=c, a2c=True,
                           post_sample_callback=_whiten_advantage, required_columns=cols, log=log, **kw)
+
+
+def REINFORCE(pi, S, a_opt=None, log=None, required_columns=(), **kw):
+    """``REINFORCE(;π, a_opt, ...)`` rl/reinforce.jl:27-39: ``reinforce_loss = -mean(logpdf(π, s, a) .* return)`` (:4-13), early
+    stop at KL > 0.015, no critic.  It is the a2c_loss kernel head with the ``return`` column as the per-row weight, λp = 1 and
+    λe = 0, so no kernel is specific to it."""
+    a = TrainingParams(loss="reinforce_loss", name="actor_", target_kl=0.015, **(a_opt or {}))
+    cols = list(dict.fromkeys(list(required_columns) + ["return", "logprob"]))
+    return OnPolicySolver(PolicyParams(pi), S, P={"lp": F32(1.0), "le": F32(0.0)}, a_opt=a, c_opt=None, a2c=True,
+                          weight_column="return", required_columns=cols, log=log, **kw)
 
 
 def _solve_on_policy(S, mdp):
@@ -257,8 +272,20 @@ class OffPolicySolver:
         self.train_count = 0
         self.last_info = {}
         self._sac = None
-        if kind == "dqn":
+        self._ddpg = None
+        if kind in ("dqn", "softq"):
             _set_adam(agent.pi.mlp, c_opt.optimizer)
+        elif kind in ("ddpg", "td3"):
+            pi, tg = agent.pi, agent.pi_target
+            twin = isinstance(pi.C, DoubleNetwork)
+            crit, crit_t = ([pi.C.N1, pi.C.N2], [tg.C.N1, tg.C.N2]) if twin else ([pi.C], [tg.C])
+            _set_adam(pi.A.mlp, a_opt.optimizer)
+            for c in crit:
+                _set_adam(c.mlp, c_opt.optimizer)
+            st = C.c_void_p()
+            ctx.check(ctx.lib.crux_ddpg_create(pi.A.mlp.h, tg.A.mlp.h, crit[0].mlp.h, crit_t[0].mlp.h, crit[1].mlp.h if twin else None,
+                                               crit_t[1].mlp.h if twin else None, self.tau, C.byref(st)))
+            self._ddpg = st
         else:
             pi = agent.pi
             _set_adam(pi.A.mu.mlp, a_opt.optimizer)
@@ -280,12 +307,16 @@ class OffPolicySolver:
             self.train_count += 1
             rand_(D, self.buffer, i=self.i, draws=None if draws is None else [draws[epoch]], seed=self.seed, ctr=2 * self.train_count)
             s, a, sp, r, dn = D.column("s"), D.column("a"), D.column("sp"), D.column("r"), D.column("done")
-            if self.kind == "dqn":
+            if self.kind in ("dqn", "softq"):
                 pi, tgt = self.agent.pi, self.agent.pi_target
                 nA = len(pi.outputs)
                 y = ctx.empty((B,))
                 q_sp = tgt.mlp.forward(sp)
-                ctx.check(lib.crux_dqn_target(ctx.h, ptr(r), ptr(dn), ptr(q_sp), B, nA, float(gamma), ptr(y)))     # rl/dqn.jl:4-6
+                if self.kind == "dqn":
+                    ctx.check(lib.crux_dqn_target(ctx.h, ptr(r), ptr(dn), ptr(q_sp), B, nA, float(gamma), ptr(y)))  # rl/dqn.jl:4-6
+                else:
+                    ctx.check(lib.crux_softq_target(ctx.h, ptr(r), ptr(dn), ptr(q_sp), B, nA, float(gamma), float(self.P["alpha"]),
+                                                    ptr(y)))                                                          # rl/softq.jl:13-17
                 if self.buffer.isprioritized():                                                                       # off_policy.jl:83
                     q = pi.mlp.forward(s)
                     qsa, td = ctx.empty((B,)), ctx.empty((B,))
@@ -295,11 +326,22 @@ class OffPolicySolver:
                 w = D.column("weight") if (self.weighted_loss and "weight" in D.schema) else None
                 if epoch % self.c_opt.update_every == 0:
                     ctx.check(lib.crux_dqn_train(pi.mlp.h, ptr(s), ptr(a), ptr(y), ptr(w), B, None))                 # off_policy.jl:91-93
+            elif self.kind in ("ddpg", "td3"):
+                sm = self.P.get("pi_smooth")                      # None: plain ddpg_target (rl/ddpg.jl:6-8)
+                e = None if noise is None else ctx.to_device(noise[epoch], torch.float32)
+                lo, hi = sm.bounds() if sm is not None else (None, None)
+                do_c = epoch % self.c_opt.update_every == 0       # off_policy.jl:91
+                do_a = epoch % self.a_opt.update_every == 0       # off_policy.jl:96 (TD3's delayed actor = a_opt.update_every 2)
+                ctx.check(lib.crux_ddpg_train(self._ddpg, ptr(s), ptr(a), ptr(sp), ptr(r), ptr(dn), B, float(gamma), 0 if sm is None else 1,
+                                              0.0 if sm is None else float(F32(sm.sigma(self.i))), -math.inf if sm is None else float(sm.eps_min),
+                                              math.inf if sm is None else float(sm.eps_max), ptr(lo), 0 if lo is None else lo.size, ptr(hi),
+                                              0 if hi is None else hi.size, ptr(e), self.seed, 3 * self.train_count, 1 if do_c else 0,
+                                              1 if do_a else 0, None, None))
             else:
                 e = (None, None, None) if noise is None else [ctx.to_device(x, torch.float32) for x in noise[epoch]]
                 ctx.check(lib.crux_sac_train(self._sac, ptr(s), ptr(a), ptr(sp), ptr(r), ptr(dn), B, float(gamma), ptr(e[0]), ptr(e[1]), ptr(e[2]),
                                              self.seed, 3 * self.train_count, None, None))
-        if self.kind == "dqn":  # no separate actor: target update after the epoch loop (off_policy.jl:108)
+        if self.kind in ("dqn", "softq"):  # no separate actor: target update after the epoch loop (off_policy.jl:108)
             polyak_average_(self.agent.pi_target, self.agent.pi, self.tau)
         return infos
 
@@ -308,6 +350,9 @@ class OffPolicySolver:
             if self._sac is not None and self.agent.pi.ctx.h:
                 self.agent.pi.ctx.lib.crux_sac_destroy(self._sac)
                 self._sac = None
+            if self._ddpg is not None and self.agent.pi.ctx.h:
+                self.agent.pi.ctx.lib.crux_ddpg_destroy(self._ddpg)
+                self._ddpg = None
         except Exception:
             pass
 
@@ -322,6 +367,17 @@ def DQN(pi, S, N, dN=4, pi_explore=None, c_opt=None, log=None, **kw):
     return OffPolicySolver(agent, S, N=N, dN=dN, c_opt=c, kind="dqn", log=log, **kw)
 
 
+def SoftQ(pi, S, N, dN=4, c_opt=None, log=None, alpha=1.0, **kw):
+    """``SoftQ(;π::DiscreteNetwork, N, ΔN=4, c_opt, α=1f0, ...)`` rl/softq.jl:36-58: the policy becomes always-stochastic with
+    ``softmax(value(π, s) ./ α)`` logits (:47-48), the target is ``r + γ(1-done)·α·logsumexp(Q⁻(sp)/α)`` (:8,13-17), the critic
+    trains with td_loss like DQN (default ``c_opt = (;epochs=4)`` :26)."""
+    assert isinstance(pi, DiscreteNetwork)
+    pi.always_stochastic, pi.temperature = True, float(F32(alpha))
+    c = TrainingParams(**{"loss": "td_loss", "name": "critic_", **({"epochs": 4} if c_opt is None else c_opt)})
+    agent = PolicyParams(pi, pi_target=deepcopy(pi))
+    return OffPolicySolver(agent, S, N=N, dN=dN, c_opt=c, kind="softq", P={"alpha": F32(alpha)}, log=log, **kw)
+
+
 def SAC(pi, S, N=1000, dN=50, SAC_alpha=1.0, SAC_H_target=None, pi_explore=None, SAC_alpha_opt=None, a_opt=None, c_opt=None,
         log=None, **kw):
     """``SAC(;π::ActorCritic{_, DoubleNetwork}, ΔN=50, SAC_α=1f0, SAC_H_target=-dim(A), π_explore=GaussianNoiseExplorationPolicy(0.1f0), ...)``
@@ -334,6 +390,30 @@ def SAC(pi, S, N=1000, dN=50, SAC_alpha=1.0, SAC_H_target=None, pi_explore=None,
     agent = PolicyParams(pi, pi_explore=pi_explore or GaussianNoiseExplorationPolicy(F32(0.1)), pi_target=deepcopy(pi))
     P = {"SAC_log_alpha": F32(math.log(SAC_alpha)), "SAC_H_target": H, "alpha_eta": t.optimizer.eta}
     return OffPolicySolver(agent, S, N=N, dN=dN, a_opt=a, c_opt=c, P=P, kind="sac", log=log, **kw)
+
+
+def DDPG(pi, S, N=1000, dN=50, pi_explore=None, a_opt=None, c_opt=None, pi_smooth=None, smoothed_target=False, log=None, **kw):
+    """``DDPG(;π::ActorCritic, ΔN=50, π_explore=GaussianNoiseExplorationPolicy(0.1f0), a_loss=ddpg_actor_loss, c_loss=td_loss(),
+    target_fn=ddpg_target, π_smooth=GaussianNoiseExplorationPolicy(0.1f0, ϵ_min=-0.5f0, ϵ_max=0.5f0), ...)`` rl/ddpg.jl:45-67.
+    ``smoothed_target=True`` selects ``smoothed_ddpg_target`` (:14-17) as ``target_fn``."""
+    assert isinstance(pi, ActorCritic) and isinstance(pi.A, ContinuousNetwork) and isinstance(pi.C, ContinuousNetwork)
+    sm = pi_smooth or GaussianNoiseExplorationPolicy(F32(0.1), eps_min=-0.5, eps_max=0.5)
+    a = TrainingParams(**{"loss": "ddpg_actor_loss", "name": "actor_", **(a_opt or {})})
+    c = TrainingParams(**{"loss": "td_loss", "name": "critic_", "epochs": dN, **(c_opt or {})})
+    agent = PolicyParams(pi, pi_explore=pi_explore or GaussianNoiseExplorationPolicy(F32(0.1)), pi_target=deepcopy(pi))
+    return OffPolicySolver(agent, S, N=N, dN=dN, a_opt=a, c_opt=c, P={"pi_smooth": sm if smoothed_target else None}, kind="ddpg", log=log, **kw)
+
+
+def TD3(pi, S, N=1000, dN=50, pi_smooth=None, pi_explore=None, a_opt=None, c_opt=None, log=None, **kw):
+    """``TD3(;π, ΔN=50, π_smooth=GaussianNoiseExplorationPolicy(0.1f0, ϵ_min=-0.5f0, ϵ_max=0.5f0),
+    π_explore=GaussianNoiseExplorationPolicy(0.1f0), a_loss=td3_actor_loss, c_loss=double_Q_loss(), target_fn=td3_target, ...)``
+    rl/td3.jl:34-57; the delayed actor of the paper is ``a_opt=(;update_every=2)`` (training.jl:7, off_policy.jl:96; default 1)."""
+    assert isinstance(pi, ActorCritic) and isinstance(pi.A, ContinuousNetwork) and isinstance(pi.C, DoubleNetwork)
+    sm = pi_smooth or GaussianNoiseExplorationPolicy(F32(0.1), eps_min=-0.5, eps_max=0.5)
+    a = TrainingParams(**{"loss": "td3_actor_loss", "name": "actor_", **(a_opt or {})})
+    c = TrainingParams(**{"loss": "double_Q_loss", "name": "critic_", "epochs": dN, **(c_opt or {})})
+    agent = PolicyParams(pi, pi_explore=pi_explore or GaussianNoiseExplorationPolicy(F32(0.1)), pi_target=deepcopy(pi))
+    return OffPolicySolver(agent, S, N=N, dN=dN, a_opt=a, c_opt=c, P={"pi_smooth": sm}, kind="td3", log=log, **kw)
 
 
 def _solve_off_policy(S, mdp):

@@ -145,6 +145,13 @@ int32_t crux_discrete_explore(crux_ctx *ctx, const float *q, int64_t B, int32_t 
 /* logpdf :144-150 (a one-hot [B][nA] float) and entropy :152-155 */
 int32_t crux_discrete_logpdf(crux_ctx *ctx, const float *q, const float *a_onehot, int64_t B, int32_t nA, float *out);
 int32_t crux_discrete_entropy(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, float *out);
+/* The same three with logit_conversion = softmax(value(π, s) ./ α), the conversion SoftQ installs (rl/softq.jl:48);
+ * α = 1 is the default conversion (policies.jl:108) and bit-identical to the entry points above. */
+int32_t crux_discrete_explore_t(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, float alpha, const double *u_in,
+                                uint64_t seed, uint64_t ctr, int32_t *a_idx, float *logp);
+int32_t crux_discrete_logpdf_t(crux_ctx *ctx, const float *q, const float *a_onehot, int64_t B, int32_t nA, float alpha,
+                               float *out);
+int32_t crux_discrete_entropy_t(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, float alpha, float *out);
 /* ϵ-greedy exploration(::MixedPolicy) :474-494 over B env streams: with prob eps a uniform action
  * (u_in[2B]: [coin, pick] pairs, NULL => Philox) else argmax; writes index, one-hot row and logprob. */
 int32_t crux_discrete_eps_greedy(crux_ctx *ctx, const float *q, int64_t B, int32_t nA, double eps,
@@ -193,6 +200,9 @@ int32_t crux_whiten(crux_ctx *ctx, float *x, int64_t n);
 /* dqn_target rl/dqn.jl:4-6 : y = r + γ(1-done)·max_a Q⁻(sp) */
 int32_t crux_dqn_target(crux_ctx *ctx, const float *r, const uint8_t *done, const float *q_sp, int64_t B,
                         int32_t nA, float gamma, float *y);
+/* softq_target rl/softq.jl:13-17 : y = r + γ(1-done)·soft_value(sp), soft_value = α·logsumexp(Q⁻(sp)/α) (:8) */
+int32_t crux_softq_target(crux_ctx *ctx, const float *r, const uint8_t *done, const float *q_sp, int64_t B,
+                          int32_t nA, float gamma, float alpha, float *y);
 /* sac_target rl/sac.jl:4-9 : y = r + γ(1-done)(min(Q1⁻,Q2⁻) - e^{logα}·logp) */
 int32_t crux_sac_target(crux_ctx *ctx, const float *r, const uint8_t *done, const float *q1, const float *q2,
                         const float *logp, int64_t B, float gamma, const float *log_alpha_dev, float *y);
@@ -256,6 +266,31 @@ int32_t crux_sac_train(crux_sac_state *st, const float *s, const float *a, const
                        const uint8_t *done, int64_t B, float gamma, const float *eps_target,
                        const float *eps_temp, const float *eps_actor, uint64_t seed, uint64_t ctr,
                        float *y_out /* nullable [B] */, float *info_out_host /* nullable */);
+
+/* exploration(::GaussianNoiseExplorationPolicy) policies.jl:499-514 applied in place to a = action(π_on, s) [B][A]:
+ * a = clamp(a + clamp(randn·σ(i), ϵ_min, ϵ_max), a_min, a_max).  a_min / a_max: host vectors of n_min / n_max entries
+ * (0 => unbounded, 1 => broadcast, A => per dimension).  eps_in [B][A] nullable => Philox. */
+int32_t crux_noise_explore(crux_ctx *ctx, float *a, int64_t B, int32_t A, float sigma, float eps_min, float eps_max,
+                           const float *a_min, int32_t n_min, const float *a_max, int32_t n_max,
+                           const float *eps_in, uint64_t seed, uint64_t ctr);
+
+/* One DDPG / TD3 value_training epoch (off_policy.jl:66-111) on a sampled minibatch:
+ *   target  ddpg_target rl/ddpg.jl:6-8, smoothed_ddpg_target :14-17 (smooth = 1), td3_target rl/td3.jl:4-7 (two critics):
+ *           a' = action(π⁻, sp) [clamp(a' + clamp(σ·ε, ϵ_min, ϵ_max), a_min, a_max)], y = r + γ(1-done)·min_k Q_k⁻(sp, a')
+ *   critic  td_loss (utils.jl:76-87) or double_Q_loss (:89-96), skipped when train_critic == 0 (c_opt.update_every)
+ *   actor   ddpg_actor_loss rl/ddpg.jl:25 / td3_actor_loss rl/td3.jl:12: -mean(Q1(s, μ(s))), then polyak τ of the whole π⁻
+ *           (actor and critics, off_policy.jl:55,100); both skipped when train_actor == 0 (a_opt.update_every)
+ * q2 / q2_target NULL => DDPG.  info_out_host[0..7] = -, critic_loss, critic_grad_norm, actor_loss, actor_grad_norm, -, Q1avg, Q2avg */
+typedef struct crux_ddpg_state crux_ddpg_state;
+int32_t crux_ddpg_create(crux_mlp *actor, crux_mlp *actor_target, crux_mlp *q1, crux_mlp *q1_target,
+                         crux_mlp *q2 /* nullable */, crux_mlp *q2_target /* nullable */, float tau, crux_ddpg_state **out);
+int32_t crux_ddpg_destroy(crux_ddpg_state *st);
+int32_t crux_ddpg_train(crux_ddpg_state *st, const float *s, const float *a, const float *sp, const float *r,
+                        const uint8_t *done, int64_t B, float gamma, int32_t smooth, float sigma, float eps_min,
+                        float eps_max, const float *a_min, int32_t n_min, const float *a_max, int32_t n_max,
+                        const float *eps_smooth /* nullable [B][A] */, uint64_t seed, uint64_t ctr,
+                        int32_t train_critic, int32_t train_actor, float *y_out /* nullable [B] */,
+                        float *info_out_host /* nullable */);
 
 /* ------------------------------------------------------------------ ExperienceBuffer (src/experience_buffer.jl)
  * Device-resident structure-of-arrays ring buffer.  Column ids are caller-chosen small integers

@@ -638,6 +638,17 @@ def a2c_loss(pi, P, D, info=None):
     return float(P["lp"]) * p_loss + float(P["le"]) * e_loss
 
 
+def reinforce_loss(pi, P, D, info=None):
+    """rl/reinforce.jl:4-13: ``-mean(logpdf(π, s, a) .* return)``; info: entropy, kl."""
+    info = {} if info is None else info
+    new_probs = pi.logpdf(D["s"], D["a"])
+    R = torch.as_tensor(D["return"], dtype=torch.float32).reshape(-1, 1)
+    with torch.no_grad():
+        info["entropy"] = float(torch.mean(torch.as_tensor(pi.entropy(D["s"]))))
+        info["kl"] = float(torch.mean(torch.as_tensor(D["logprob"], dtype=torch.float32).reshape(-1, 1) - new_probs))
+    return -torch.mean(new_probs * R)
+
+
 def value_mse_loss(V, D):
     """PPO/A2C critic loss ``Flux.mse(value(π, D[:s]), D[:return])`` (ppo.jl:60, a2c.jl:47)."""
     ret = torch.as_tensor(D["return"], dtype=torch.float32).reshape(-1, 1)
@@ -663,6 +674,25 @@ def dqn_target(q_target_sp, r, done, gamma):
     return (r + float(F32(gamma)) * nd * torch.max(q, dim=1, keepdim=True).values).detach()
 
 
+def soft_value(q, alpha=1.0):
+    """rl/softq.jl:8: ``α .* logsumexp(value(π, s) ./ α, dims=1)`` (NNlib logsumexp = max + log Σ exp(x - max))."""
+    x = torch.as_tensor(q, dtype=torch.float32) / float(F32(alpha))
+    m = torch.max(x, dim=1, keepdim=True).values
+    return float(F32(alpha)) * (m + torch.log(torch.sum(torch.exp(x - m), dim=1, keepdim=True)))
+
+
+def softq_target(q_target_sp, r, done, gamma, alpha=1.0):
+    """rl/softq.jl:13-17."""
+    r = torch.as_tensor(r, dtype=torch.float32).reshape(-1, 1)
+    nd = 1.0 - torch.as_tensor(np.asarray(done, dtype=F32)).reshape(-1, 1)
+    return (r + float(F32(gamma)) * nd * soft_value(q_target_sp, alpha)).detach()
+
+
+def softq_logits(q, alpha=1.0):
+    """The logit_conversion SoftQ installs: ``softmax(value(π, s) ./ α)`` (rl/softq.jl:48)."""
+    return torch.softmax(torch.as_tensor(q, dtype=torch.float32) / float(F32(alpha)), dim=1)
+
+
 def td_error(q_sa, y):
     """utils.jl:112."""
     return torch.abs(q_sa - torch.as_tensor(y, dtype=torch.float32).reshape(-1, 1)).detach()
@@ -678,6 +708,38 @@ def sac_target(actor, q1_t, q2_t, D, gamma, log_alpha, eps):
         r = torch.as_tensor(D["r"], dtype=torch.float32).reshape(-1, 1)
         nd = 1.0 - torch.as_tensor(np.asarray(D["done"], dtype=F32)).reshape(-1, 1)
         return r + float(F32(gamma)) * nd * (qmin - math.exp(float(log_alpha)) * logp)
+
+
+def gaussian_noise_exploration(a, eps, sigma, eps_min=-math.inf, eps_max=math.inf, a_min=-math.inf, a_max=math.inf):
+    """``exploration(::GaussianNoiseExplorationPolicy)`` policies.jl:510-514 on a = action(π_on, s):
+    ``clamp.(a .+ clamp.(randn .* σ(i), ϵ_min, ϵ_max), a_min, a_max)``."""
+    a = torch.as_tensor(a, dtype=torch.float32)
+    n = torch.clamp(torch.as_tensor(eps, dtype=torch.float32) * float(F32(sigma)), float(eps_min), float(eps_max))
+    lo = torch.as_tensor(np.asarray(a_min, dtype=F32)).reshape(1, -1)
+    hi = torch.as_tensor(np.asarray(a_max, dtype=F32)).reshape(1, -1)
+    return torch.minimum(torch.maximum(a + n, lo), hi)
+
+
+def ddpg_target(actor_t, critics_t, D, gamma, smooth=None):
+    """rl/ddpg.jl:6-8 (one critic, no noise), smoothed_ddpg_target :14-17, td3_target rl/td3.jl:4-7 (min over two critics).
+    ``smooth`` = dict(eps, sigma, eps_min, eps_max, a_min, a_max) or None; networks are the TARGET copies (off_policy.jl:80)."""
+    with torch.no_grad():
+        ap = actor_t(D["sp"])
+        if smooth is not None:
+            ap = gaussian_noise_exploration(ap, **smooth)
+        x = torch.cat([torch.as_tensor(D["sp"], dtype=torch.float32), ap], dim=1)
+        q = critics_t[0](x)
+        for c in critics_t[1:]:
+            q = torch.minimum(q, c(x))
+        r = torch.as_tensor(D["r"], dtype=torch.float32).reshape(-1, 1)
+        nd = 1.0 - torch.as_tensor(np.asarray(D["done"], dtype=F32)).reshape(-1, 1)
+        return r + float(F32(gamma)) * nd * q
+
+
+def ddpg_actor_loss(actor, q1, D):
+    """rl/ddpg.jl:25 / td3_actor_loss rl/td3.jl:12: ``-mean(value(Q1, s, action(π, s)))``."""
+    s = torch.as_tensor(D["s"], dtype=torch.float32)
+    return -torch.mean(q1(torch.cat([s, actor(D["s"])], dim=1)))
 
 
 def sac_actor_loss(actor, q1, q2, D, log_alpha, eps, info=None):

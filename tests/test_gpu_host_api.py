@@ -229,6 +229,19 @@ def test_solve_ppo_and_a2c_run(crux, ctx, device_env):
         assert S.i == 6 * n * T
 
 
+def test_solve_reinforce_runs_without_a_critic(crux, ctx):
+    """rl/reinforce.jl:27-39: a bare GaussianPolicy, columns return + logprob only (no value passes, no advantage)."""
+    n, T = 64, 8
+    pi = _actor_critic(crux, ctx, seed=6).A
+    before = pi.mu.mlp.get_flat().copy()
+    S = crux.REINFORCE(pi, crux.ContinuousSpace(17), a_opt=dict(epochs=2, batch_size=128), N=2 * n * T, dN=n * T, max_steps=50)
+    out = crux.solve(S, crux.DeviceLinQuad(n, seed=2, max_steps=50, ctx=ctx))
+    assert out is pi and S.i == 2 * n * T and "advantage" not in S.buffer.schema
+    info = S.training_info()
+    assert np.isfinite(info["actor_loss"]) and info["actor_batches_trained"] >= 1 and "critic_loss" not in info
+    assert not np.array_equal(before, pi.mu.mlp.get_flat())
+
+
 # ------------------------------------------------------------------------------------------------ DQN / SAC
 def test_dqn_value_training_matches_oracle(crux, ctx):
     """value_training (off_policy.jl:66-111) for DQN with injected sample ids: dqn_target -> td_loss train! x epochs -> polyak."""
@@ -255,6 +268,42 @@ def test_dqn_value_training_matches_oracle(crux, ctx):
     assert_params_close(S.agent.pi_target.mlp.get_flat(), qt.flat(), 3e-4, 4, what="target Q")
 
 
+def test_softq_value_training_matches_oracle(crux, ctx):
+    """rl/softq.jl:36-58 through value_training (off_policy.jl:66-111): soft target -> td_loss train! x epochs -> polyak; the
+    policy itself turns always-stochastic with softmax(Q/α) logits."""
+    rng = np.random.default_rng(1)
+    chain = crux.Chain(crux.Dense(2, 8, crux.relu, rng=rng), crux.Dense(8, 4, rng=rng))
+    pi = crux.DiscreteNetwork(chain, [0, 1, 2, 3], ctx=ctx)
+    alpha = F32(0.5)
+    S = crux.SoftQ(pi, crux.ContinuousSpace(2), N=1000, dN=4, c_opt=dict(batch_size=32, epochs=3), alpha=alpha, buffer_size=200)
+    assert pi.always_stochastic and pi.temperature == 0.5 and S.agent.pi_target.temperature == 0.5
+    nb = 150
+    d = {"s": rng.standard_normal((nb, 2)).astype(F32), "a": np.eye(4, dtype=F32)[rng.integers(0, 4, nb)], "sp": rng.standard_normal((nb, 2)).astype(F32),
+         "r": rng.standard_normal((nb, 1)).astype(F32), "done": (rng.random((nb, 1)) < 0.2)}
+    S.buffer.push_(d)
+    q = _oracle_mlp(pi.mlp); qt = _oracle_mlp(S.agent.pi_target.mlp)
+    refnet = o.DiscreteNetwork(q, range(4))
+    opt = o.Adam(F32(3e-4))
+    draws = [rng.integers(1, nb + 1, 32) for _ in range(3)]
+    for ids in draws:
+        mb = {k: v[ids - 1] for k, v in d.items()}
+        y = o.softq_target(qt(mb["sp"]).detach(), mb["r"], mb["done"], F32(0.95), alpha)
+        o.train_step(q.params(), lambda inf: o.td_loss(refnet.value(mb["s"], mb["a"]), y, None, inf), opt, {})
+    o.polyak_average(qt.params(), q.params(), 0.005)
+    Dmb = crux.buffer_like(S.buffer, capacity=32)
+    S.value_training(Dmb, F32(0.95), draws=draws)
+    assert_params_close(pi.mlp.get_flat(), q.flat(), 3e-4, 3, what="online Q")
+    assert_params_close(S.agent.pi_target.mlp.get_flat(), qt.flat(), 3e-4, 3, what="target Q")
+    # action(π, s) samples from softmax(Q/α) once always_stochastic is set (policies.jl:124)
+    s1 = np.tile(np.array([[0.3, -0.2]], F32), (40000, 1))
+    ps = o.softq_logits(q(s1[:1]).detach(), alpha).numpy()[0]
+    freq = np.bincount(host(crux.action(pi, s1)), minlength=4) / 40000
+    assert np.allclose(freq, ps, atol=1.5e-2)
+    S2 = crux.SoftQ(pi, crux.ContinuousSpace(2), N=400, alpha=alpha, buffer_size=500, buffer_init=200)
+    assert crux.solve(S2, crux.SimpleGridWorld(4, seed=0)) is pi and S2.i >= 400 and np.isfinite(pi.mlp.get_flat()).all()
+    assert np.isfinite(host(S2.buffer["logprob"])[:len(S2.buffer)]).all() if "logprob" in S2.buffer.schema else True
+
+
 def test_solve_dqn_gridworld_readme_example(crux, ctx):
     # README.md:72-82 / test/readme.jl (N reduced): DQN(π=DiscreteNetwork(Chain(Dense(2,8,relu), Dense(8,4)), actions), S, N)
     rng = np.random.default_rng(0)
@@ -273,6 +322,37 @@ def test_solve_dqn_gridworld_readme_example(crux, ctx):
     crux.solve(S2, env)
     pr = host(S2.buffer.priorities())[:len(S2.buffer)]
     assert np.all(pr > 0) and pr.std() > 0
+
+
+@pytest.mark.parametrize("kind", ["ddpg", "ddpg_smooth", "td3"])
+def test_solve_ddpg_td3_run(crux, ctx, kind):
+    """rl/ddpg.jl:45-67, rl/td3.jl:34-57 through solve(): Gaussian-noise exploration on a deterministic actor, value_training with
+    the (smoothed) target, the delayed TD3 actor and the polyak of the whole target policy."""
+    rng = np.random.default_rng(0)
+    D = crux.Dense
+    obs, act, hid = 17, 6, 32
+    A = crux.ContinuousNetwork(crux.Chain(D(obs, hid, crux.relu, rng=rng), D(hid, hid, crux.relu, rng=rng), D(hid, act, crux.tanh, rng=rng)), ctx=ctx)
+    Q = lambda: crux.ContinuousNetwork(crux.Chain(D(obs + act, hid, crux.relu, rng=rng), D(hid, hid, crux.relu, rng=rng), D(hid, 1, rng=rng)), ctx=ctx)
+    pi = crux.ActorCritic(A, crux.DoubleNetwork(Q(), Q()) if kind == "td3" else Q())
+    before_a, before_t = A.mlp.get_flat().copy(), None
+    n = 16
+    opt = dict(batch_size=64)
+    expl = crux.GaussianNoiseExplorationPolicy(F32(0.2), a_min=-1.0, a_max=1.0)
+    if kind == "td3":
+        S = crux.TD3(pi, crux.ContinuousSpace(obs), N=40 * n, dN=2 * n, a_opt=dict(opt, update_every=2), c_opt=dict(opt, epochs=4),
+                     pi_explore=expl, buffer_size=2000, buffer_init=128)
+    else:
+        S = crux.DDPG(pi, crux.ContinuousSpace(obs), N=40 * n, dN=2 * n, a_opt=dict(opt), c_opt=dict(opt, epochs=4), pi_explore=expl,
+                      smoothed_target=(kind == "ddpg_smooth"), buffer_size=2000, buffer_init=128)
+    before_t = S.agent.pi_target.A.mlp.get_flat().copy()
+    out = crux.solve(S, crux.HostLinQuad(n, seed=3))
+    assert out is pi and S.i >= 40 * n
+    a = host(S.buffer["a"])[:len(S.buffer)]
+    assert np.all(np.abs(a) <= 1.0) and a.std() > 0.05                       # clamp(π(s) + noise, a_min, a_max)
+    after_a, after_t = A.mlp.get_flat(), S.agent.pi_target.A.mlp.get_flat()
+    assert np.isfinite(after_a).all() and not np.array_equal(before_a, after_a)
+    assert not np.array_equal(before_t, after_t)                             # the actor copy inside π⁻ follows by polyak
+    assert np.abs(after_t - before_t).max() < np.abs(after_a - before_a).max()
 
 
 def test_solve_sac_runs(crux, ctx):

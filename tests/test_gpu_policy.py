@@ -180,6 +180,40 @@ def test_discrete_network(ctx):
     assert ctx.lib.crux_discrete_argmax(ctx.h, p(q), B, 65, p(idx)) == 1
 
 
+@pytest.mark.parametrize("alpha", [1.0, 0.3, 2.5])
+def test_softq_logits_target_and_sampling(ctx, alpha):
+    """rl/softq.jl:8,13-17,47-48: soft_value = α·logsumexp(Q/α); logits = softmax(Q/α) drive exploration, logpdf and entropy."""
+    rng = np.random.default_rng(5)
+    B, nA = 600, 5
+    q = (3 * rng.standard_normal((B, nA))).astype(F32)
+    r = rng.standard_normal(B).astype(F32); done = (rng.random(B) < 0.3).astype(np.uint8)
+    qd = dev(ctx, q)
+    y = ctx.empty((B,))
+    ctx.check(ctx.lib.crux_softq_target(ctx.h, p(dev(ctx, r)), p(dev(ctx, done)), p(qd), B, nA, 0.97, alpha, p(y)))
+    assert_close(host(y), o.softq_target(q, r, done, 0.97, alpha).numpy()[:, 0], rtol=1e-5, atol=1e-6, what="softq target")
+    ps = o.softq_logits(q, alpha).numpy()
+    u = rng.random(B)
+    idx = torch.empty(B, dtype=torch.int32, device=ctx.device); lp = ctx.empty((B,))
+    ctx.check(ctx.lib.crux_discrete_explore_t(ctx.h, p(qd), B, nA, alpha, p(dev(ctx, u)), 0, 0, p(idx), p(lp)))
+    cdf = np.cumsum(ps.astype(np.float64), axis=1)
+    want = np.minimum((cdf < u[:, None]).sum(1), nA - 1)
+    got = host(idx)
+    edge = np.abs(np.take_along_axis(cdf, np.minimum(got, want)[:, None], 1)[:, 0] - u) < 1e-6   # draws on a CDF step: either side
+    assert np.array_equal(got[~edge], want[~edge]) and edge.sum() <= 2
+    assert_close(host(lp), np.log(ps[np.arange(B), got]), rtol=1e-5, atol=1e-6, what="logprob")
+    oh = np.eye(nA, dtype=F32)[rng.integers(0, nA, B)]
+    out = ctx.empty((B,))
+    ctx.check(ctx.lib.crux_discrete_logpdf_t(ctx.h, p(qd), p(dev(ctx, oh)), B, nA, alpha, p(out)))
+    assert_close(host(out), np.log((ps * oh).sum(1)), rtol=1e-5, atol=1e-6, what="logpdf")
+    ctx.check(ctx.lib.crux_discrete_entropy_t(ctx.h, p(qd), B, nA, alpha, p(out)))
+    assert_close(host(out), -(ps * np.log(ps + np.finfo(F32).eps)).sum(1), rtol=1e-5, atol=1e-6, what="entropy")
+    if alpha == 1.0:   # α = 1 is the default conversion, bit for bit
+        out1 = ctx.empty((B,))
+        ctx.check(ctx.lib.crux_discrete_entropy(ctx.h, p(qd), B, nA, p(out1)))
+        assert np.array_equal(host(out), host(out1))
+    assert ctx.lib.crux_softq_target(ctx.h, p(dev(ctx, r)), p(dev(ctx, done)), p(qd), B, nA, 0.97, 0.0, p(y)) != 0
+
+
 def test_eps_greedy(ctx):
     # exploration(::MixedPolicy) policies.jl:474-494
     rng = np.random.default_rng(1)

@@ -149,6 +149,30 @@ def test_a2c_loss_and_max_batches(ctx, crux):
     assert_params_close(mlp_params(ctx, handles[1]), cr.flat(), 3e-4, 1)
 
 
+def test_reinforce_loss_is_the_a2c_head_weighted_by_returns(ctx, crux):
+    """rl/reinforce.jl:4-13 ``-mean(logpdf .* return)`` with the early stop at KL > 0.015 (:36): the a2c kernel head with the
+    ``return`` column as the per-row weight, λp = 1, λe = 0 and no critic -- what ``crux_b200.REINFORCE`` launches."""
+    n, ab = 768, 256
+    rng, pi, cr, handles, D = _setup(ctx, crux, n, seed=17)
+    D["return"] = (D["return"] * F32(4)).astype(F32)
+    hp = _hp(crux, a2c=1, actor_batch=ab, actor_epochs=4, critic_epochs=0, lambda_p=1.0, lambda_e=0.0, target_kl=0.015)
+    oa = _orders(rng, n, 4)
+    ra = _oracle_train(pi.params(), lambda mb, inf: o.reinforce_loss(pi, {}, mb, inf), o.Adam(F32(3e-4)), D, oa, ab,
+                       stop=lambda info: info["kl"] > 0.015)
+    d = dict(D); d["advantage"] = D["return"]
+    hm, hc, h = handles
+    ia, _ = _run(ctx, crux, (hm, None, h), d, hp, oa, None, n)
+    A = crux._abi
+    valid = ia[:, A.PPO_VALID]
+    assert valid[:len(ra)].all() and not valid[len(ra):].any()
+    for k, rec in enumerate(ra):
+        assert_close(ia[k, A.PPO_LOSS], rec["loss"], rtol=1e-4, atol=1e-5, what=f"reinforce loss {k}")
+        assert_close(ia[k, A.PPO_KL], rec["kl"], rtol=1e-3, atol=2e-6, what=f"kl {k}")
+        assert_close(ia[k, A.PPO_ENTROPY], rec["entropy"], rtol=1e-5, what="entropy")
+        assert_close(ia[k, A.PPO_GRAD_NORM], rec["grad_norm"], rtol=1e-3, what="grad_norm")
+    assert_params_close(mlp_params(ctx, hm), pi.mu.flat(), 3e-4, len(ra), what="actor params")
+
+
 def test_device_permutation_is_a_permutation_and_trains(ctx, crux):
     """order == NULL: device-generated shuffles.  Each epoch must visit every row exactly once (checked through a
     critic whose target equals a per-row id-free constant is not observable; instead check determinism + change)."""

@@ -243,3 +243,26 @@ def test_adam_first_step_is_eta_sign():
     p.grad = torch.tensor([0.5, -0.25, 0.0])
     o.Adam(eta=1e-3).step([p])
     assert np.allclose(p.detach().numpy(), [1 - 1e-3, -2 + 1e-3, 3.0], atol=1e-8)
+
+
+def test_soft_value_and_reinforce_restatements():
+    # rl/softq.jl:8: α·logsumexp(Q/α) -> max(Q) as α -> 0, >= max(Q) always, = log Σ exp Q at α = 1 (float64 cross-check)
+    import torch
+    rng = np.random.default_rng(3)
+    q = (2 * rng.standard_normal((50, 6))).astype(F32)
+    v1 = o.soft_value(q, 1.0).numpy()[:, 0]
+    assert np.allclose(v1, np.log(np.exp(q.astype(np.float64)).sum(1)), rtol=1e-6)
+    v0 = o.soft_value(q, 1e-2).numpy()[:, 0]
+    assert np.allclose(v0, q.max(1), atol=0.05) and np.all(v0 >= q.max(1) - 1e-6)
+    assert np.allclose(o.softq_logits(q, 0.5).sum(1).numpy(), 1.0, atol=1e-6)
+    y = o.softq_target(q, np.ones(50, F32), np.ones(50, bool), 0.9, 0.5).numpy()[:, 0]
+    assert np.array_equal(y, np.ones(50, F32))            # done rows never bootstrap
+    # rl/reinforce.jl:4-13 == a2c_loss (rl/a2c.jl:4-16) with the return column as the weight, λp = 1, λe = 0
+    mu = o.MLP([3, 8, 2], [o.ACT_TANH, o.ACT_IDENTITY], rng)
+    pi = o.GaussianPolicy(mu, np.full(2, -0.5, F32))
+    D = {"s": rng.standard_normal((32, 3)).astype(F32), "a": rng.standard_normal((32, 2)).astype(F32),
+         "logprob": rng.standard_normal((32, 1)).astype(F32), "return": rng.standard_normal((32, 1)).astype(F32)}
+    i1, i2 = {}, {}
+    l1 = o.reinforce_loss(pi, {}, D, i1)
+    l2 = o.a2c_loss(pi, {"lp": F32(1), "le": F32(0)}, dict(D, advantage=D["return"]), i2)
+    assert torch.equal(l1, l2) and i1["kl"] == i2["kl"] and i1["entropy"] == i2["entropy"]
