@@ -353,9 +353,46 @@ class Sampler:
             buffer.push_(cols)
         return (cols, pairs) if return_episodes else cols
 
-    # ---- evaluation helpers (sampler.jl:206-251): mean undiscounted return of greedy episodes on a host env
-    def undiscounted_return(self, Neps=10):
-        assert not self.on_device, "evaluation rollouts use a host environment"
+    # ---- metrics (sampler.jl:203-251).  Per-episode sums run on the device: the concatenated episodes are ONE stream of the
+    # returns scan (crux_fill_gae_returns with adv = NULL), cut by the episode_end flags; the value at an episode's first row is
+    # Σ_t γ^t x_t of that episode (γ = 1: the plain sum).
+    def episode_sums(self, data, pairs, key="r", gamma=1.0):
+        """``[metric_by_key(data, start, stop; key) for (start, stop) in episodes]`` (:206,212) for γ = 1 and
+        ``discounted_return(data, start, stop, γ)`` (:221-227) otherwise -> float32 tensor ``[len(pairs)]``."""
+        ctx = self.ctx
+        x = data[key].reshape(-1).to(torch.float32).contiguous()
+        T = x.shape[0]
+        if T == 0 or not pairs:
+            return ctx.empty((0,))
+        out = ctx.empty((T,))
+        ee, dn = data["episode_end"].reshape(-1).contiguous(), data["done"].reshape(-1).contiguous()
+        ctx.check(ctx.lib.crux_fill_gae_returns(ctx.h, ptr(x), ptr(dn), ptr(ee), ptr(x), ptr(x), T, 1, float(gamma), 0.0, None, ptr(out)))
+        first = torch.as_tensor([p[0] - 1 for p in pairs], device=ctx.device)
+        return out.index_select(0, first)
+
+    def metrics_by_key(self, keys, Neps=100, **kw):
+        """``metrics_by_key(s::Sampler; keys, Neps)`` (:208-219): ``sum(data[key]) / Neps`` over ``Neps`` fresh episodes."""
+        data, pairs = self.episodes_(Neps=Neps, return_episodes=True, **kw)
+        return [float(self.episode_sums(data, pairs, k).sum().item()) / Neps for k in keys]
+
+    def metric_by_key(self, key, Neps=100, **kw):
+        return self.metrics_by_key([key], Neps=Neps, **kw)[0]
+
+    def discounted_return(self, Neps=100, **kw):
+        """``discounted_return(s::Sampler; Neps)`` (:229-232): mean over episodes of Σ γ^t r_t."""
+        data, pairs = self.episodes_(Neps=Neps, return_episodes=True, **kw)
+        return float(self.episode_sums(data, pairs, "r", float(self.gamma)).mean().item())
+
+    def failure(self, threshold=0.0, Neps=100, **kw):
+        """``failure(s::Sampler; threshold, Neps)`` (:235-240): fraction of episodes whose undiscounted return is below the threshold."""
+        data, pairs = self.episodes_(Neps=Neps, return_episodes=True, **kw)
+        return float((self.episode_sums(data, pairs, "r") < threshold).to(torch.float32).mean().item())
+
+    def undiscounted_return(self, Neps=10, **kw):
+        """``undiscounted_return(s::Sampler; Neps)`` (:216): on a device env through ``episodes_`` + the device scan; on a host env
+        the batched greedy loop below (episodes counted in finishing order)."""
+        if self.on_device:
+            return self.metric_by_key("r", Neps=Neps, **kw)
         self.reset_()
         total = np.zeros(self.n)
         finished = []

@@ -659,7 +659,7 @@ def td_loss(q_sa, y, weight=None, info=None, name="Qavg"):
     """utils.jl:76-87 with Q(s,a) already evaluated; ``weighted_mean`` utils.jl:47."""
     y = torch.as_tensor(y, dtype=torch.float32).reshape(-1, 1)
     if info is not None:
-        info[name] = float(torch.mean(q_sa))
+        info[name] = float(torch.mean(q_sa).detach())
     e = (q_sa - y) ** 2
     if weight is None:
         return torch.mean(e)

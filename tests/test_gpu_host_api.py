@@ -437,3 +437,28 @@ def test_episodes_and_shuffle(crux, ctx):
     buf.shuffle_(perm)
     for k in buf.keys():
         assert np.array_equal(host(buf[k]), before[k][perm - 1])
+
+
+@pytest.mark.parametrize("device_env", [False, True])
+def test_episode_metrics_on_device(crux, ctx, device_env):
+    """sampler.jl:203-240: undiscounted / discounted return, metric_by_key and failure over episodes!, with the per-episode sums
+    computed by the returns scan on the device (one stream cut at episode_end)."""
+    n, max_steps = 8, 12
+    pi = _actor_critic(crux, ctx, seed=5)
+    env = crux.DeviceLinQuad(n, seed=4, max_steps=max_steps, ctx=ctx) if device_env else crux.HostLinQuad(n, seed=4)
+    s = crux.Sampler(env, pi, max_steps=max_steps)
+    data, eps = s.episodes_(Neps=19, explore=True, return_episodes=True)
+    r = host(data["r"])[:, 0].astype(np.float64)
+    g = float(s.gamma)
+    und = np.array([r[a - 1:b].sum() for a, b in eps])
+    dis = np.array([o.discounted_return(r[a - 1:b].astype(F32), F32(g)) for a, b in eps])
+    assert_close(host(s.episode_sums(data, eps, "r")), und, rtol=1e-5, atol=1e-5, what="undiscounted sums")
+    assert_close(host(s.episode_sums(data, eps, "r", g)), dis, rtol=1e-5, atol=1e-5, what="discounted sums")
+    assert s.episode_sums(data, [], "r").shape[0] == 0
+    # the sampler-level metrics draw fresh (greedy) episodes: deterministic given the env seed, finite, consistent with each other
+    u = s.undiscounted_return(Neps=10)
+    d = s.discounted_return(Neps=10)
+    assert np.isfinite(u) and np.isfinite(d)
+    assert s.failure(threshold=1e9, Neps=5) == 1.0 and s.failure(threshold=-1e9, Neps=5) == 0.0
+    m = s.metrics_by_key(["r", "done"], Neps=6)
+    assert np.isfinite(m[0]) and 0.0 <= m[1] <= 1.0      # at most one terminal transition per episode
