@@ -17,5 +17,5 @@ from .buffer import (ExperienceBuffer, PriorityParams, buffer_like, mdp_data, pr
                      uniform_sample_)
 from .envs import DeviceLinQuad, HostLinQuad, NativeHostLinQuad, SimpleGridWorld, linquad_matrices  # noqa: F401
 from .sampler import Sampler, fill_gae_, fill_returns_, steps_  # noqa: F401
-from .solvers import (A2C, DDPG, DQN, PPO, REINFORCE, SAC, TD3, Adam, SoftQ, LoggerParams, OffPolicySolver, OnPolicySolver, TrainingParams,  # noqa: F401
+from .solvers import (A2C, DDPG, DQN, PPO, LagrangePPO, REINFORCE, SAC, TD3, Adam, SoftQ, LoggerParams, OffPolicySolver, OnPolicySolver, TrainingParams,  # noqa: F401
                       log_undiscounted_return, solve)

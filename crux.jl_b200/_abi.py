@@ -37,6 +37,12 @@ class PPOHp(C.Structure):
                 ("actor_max_batches", C.c_int64), ("critic_max_batches", C.c_int64)]
 
 
+class LagrangeHp(C.Structure):
+    _fields_ = [("target_cost", C.c_float), ("penalty_max", C.c_float), ("Ki_max", C.c_float), ("Ki", C.c_float), ("Kp", C.c_float),
+                ("Kd", C.c_float), ("ema_alpha", C.c_double), ("cost_epochs", C.c_int32), ("cost_batch", C.c_int64),
+                ("cost_max_batches", C.c_int64)]
+
+
 class RolloutCols(C.Structure):
     _fields_ = [("s", C.c_void_p), ("a", C.c_void_p), ("sp", C.c_void_p), ("r", C.c_void_p), ("done", C.c_void_p),
                 ("episode_end", C.c_void_p), ("logprob", C.c_void_p)]
@@ -121,6 +127,8 @@ _SIGS = {
     "crux_ppo_update": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(PPOHp), _vp, _vp, _u64, _vp, _vp],
     "crux_ppo_update_async": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(PPOHp), _vp, _vp, _u64],
     "crux_ppo_info_ptrs": [_vp, _pp, _pp],
+    "crux_lagrange_ppo_update": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(PPOHp), C.POINTER(LagrangeHp),
+                                 _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp],
     "crux_dqn_train": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "crux_sac_create": [_vp, _vp, _vp, _vp, _vp, _f32, _f32, _f64, _f32, _pp],
     "crux_sac_destroy": [_vp],

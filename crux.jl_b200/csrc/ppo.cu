@@ -42,7 +42,7 @@ __global__ void advance_kernel(int *__restrict__ ctl, float *__restrict__ rec) {
 __global__ void reset_ctl_kernel(int *__restrict__ ctl) { ctl[0] = 0; ctl[1] = 0; }
 
 // gather a minibatch: dst columns [bm][d] <- src[idx[i]][d]
-struct GatherCols { const float *src[5]; float *dst[5]; int dim[5]; int n; };
+struct GatherCols { const float *src[6]; float *dst[6]; int dim[6]; int n; };
 __global__ void gather_cols_kernel(GatherCols g, const int32_t *__restrict__ idx, int64_t bm, const int *__restrict__ skip) {
   if (skip && *skip) return;
   const int c = blockIdx.y;
@@ -57,16 +57,20 @@ __global__ void gather_cols_kernel(GatherCols g, const int32_t *__restrict__ idx
 
 // ppo_loss / a2c_loss head (rl/ppo.jl:4-21, rl/a2c.jl:4-16) for a state-independent-logΣ GaussianPolicy.
 // One thread per sample.  Writes dL/dmu and block partial sums:
-//  part[b][0..6] = sum surr|logp*A, sum (old-new), clip count, sum adv, sum ret, 0, 0 ; part[b][8+j] = d/dlogΣ_j
+//  part[b][0..7] = sum surr|logp*A, sum (old-new), clip count, sum adv, sum ret, 0, sum cost surrogate, 0 ; part[b][8+j] = d/dlogΣ_j
 #define HEAD_STRIDE (8 + CRUX_MAX_ADIM)
 __global__ void __launch_bounds__(128)
 ppo_head_kernel(const float *__restrict__ mu, const float *__restrict__ a, const float *__restrict__ old_logp,
                 const float *__restrict__ adv, const float *__restrict__ ret, const float *__restrict__ ls, int A,
                 int64_t bm, float inv_bg, float eps_clip, float lambda_p, int a2c, float *__restrict__ dmu,
-                double *__restrict__ part, const int *__restrict__ skip) {
+                double *__restrict__ part, const int *__restrict__ skip, const float *__restrict__ cadv,
+                const float *__restrict__ penalty) {
   if (skip && *skip) return;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  float s_obj = 0.f, s_kl = 0.f, s_clip = 0.f, s_adv = 0.f, s_ret = 0.f;
+  float s_obj = 0.f, s_kl = 0.f, s_clip = 0.f, s_adv = 0.f, s_ret = 0.f, s_cobj = 0.f;
+  // lagrange_ppo_loss rl/ppo.jl:70-131: (λp·p_loss + λe·e_loss + penalty·mean(max(r·Ac, clamp(r)·Ac))) / (1 + penalty)
+  const float pen = penalty ? penalty[0] : 0.f;
+  const float lscale = 1.f / (1.f + pen);
   float dls[CRUX_MAX_ADIM];
 #pragma unroll 8
   for (int j = 0; j < CRUX_MAX_ADIM; ++j) dls[j] = 0.f;
@@ -90,6 +94,15 @@ ppo_head_kernel(const float *__restrict__ mu, const float *__restrict__ a, const
       s_obj = first ? x : y;
       dlogp = first ? -lambda_p * inv_bg * x : 0.f;  // the clamped branch is only taken outside [lo, hi]: zero slope
       s_clip = (r > hi || r < lo) ? 1.f : 0.f;
+      if (cadv) {
+        const float Ac = cadv[i];
+        const float xc = r * Ac, yc = fminf(fmaxf(r, lo), hi) * Ac;
+        const bool takex = xc > yc;                 // max(x, y): the clamped branch on ties (same slope inside [lo, hi])
+        s_cobj = takex ? xc : yc;
+        const bool inside = r >= lo && r <= hi;
+        dlogp += pen * inv_bg * ((takex || inside) ? xc : 0.f);
+        dlogp *= lscale;
+      }
     }
     s_kl = old - logp; s_adv = Ai; s_ret = ret ? ret[i] : 0.f;
     for (int j = 0; j < A; ++j) {
@@ -109,10 +122,11 @@ ppo_head_kernel(const float *__restrict__ mu, const float *__restrict__ a, const
   v = warp_sum_d((double)s_clip); if (lane == 0) sh[w][2] = v;
   v = warp_sum_d((double)s_adv); if (lane == 0) sh[w][3] = v;
   v = warp_sum_d((double)s_ret); if (lane == 0) sh[w][4] = v;
+  v = warp_sum_d((double)s_cobj); if (lane == 0) sh[w][6] = v;
   for (int j = 0; j < A; ++j) { v = warp_sum_d((double)dls[j]); if (lane == 0) sh[w][8 + j] = v; }
   __syncthreads();
   for (int k = threadIdx.x; k < 8 + A; k += blockDim.x) {
-    if (k >= 5 && k < 8) { part[(int64_t)blockIdx.x * HEAD_STRIDE + k] = 0.0; continue; }
+    if (k == 5 || k == 7) { part[(int64_t)blockIdx.x * HEAD_STRIDE + k] = 0.0; continue; }
     part[(int64_t)blockIdx.x * HEAD_STRIDE + k] = sh[0][k] + sh[1][k] + sh[2][k] + sh[3][k];
   }
 }
@@ -125,7 +139,7 @@ __global__ void ppo_finalize_kernel(const double *__restrict__ part, int nblocks
   if (k >= 8 + A) return;
   double s = 0.0;
   for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * HEAD_STRIDE + k];
-  if (k < 5) sums[k] = (float)s;
+  if (k < 5 || k == 6) sums[k] = (float)s;
   else if (k == 5) sums[5] = (float)bm;
   else if (k >= 8) ls_grad[k - 8] = (float)s;  // entropy term added after the all-reduce (record kernel)
   (void)lambda_e;
@@ -134,7 +148,8 @@ __global__ void ppo_finalize_kernel(const double *__restrict__ part, int nblocks
 // after the (optional) all-reduce: info record, entropy gradient, early-stop vote.  One thread.
 __global__ void ppo_record_kernel(const float *__restrict__ sums, float *__restrict__ ls_grad, const float *__restrict__ ls,
                                   int A, float lambda_p, float lambda_e, float target_kl, int a2c, int world,
-                                  float *__restrict__ rec, int *__restrict__ ctl) {
+                                  float *__restrict__ rec, int *__restrict__ ctl, const float *__restrict__ penalty,
+                                  float *__restrict__ lrec) {
   if (ctl[0]) return;
   const float cnt = sums[5];
   float sls = 0.f;
@@ -142,6 +157,13 @@ __global__ void ppo_record_kernel(const float *__restrict__ sums, float *__restr
   const float entropy = ENT_CONST + sls;     // policies.jl:348
   const float p_loss = -(sums[0] / cnt);
   const float e_loss = -entropy;
+  if (penalty) {                             // lagrange_ppo_loss rl/ppo.jl:108-131
+    const float pen = penalty[0];
+    const float cost_loss = pen * (sums[6] / cnt);
+    rec[CRUX_PPO_LOSS] = (lambda_p * p_loss + lambda_e * e_loss + cost_loss) / (1.f + pen);
+    lrec[5] = lambda_p * p_loss; lrec[6] = cost_loss;
+    lambda_e = lambda_e / (1.f + pen);       // the entropy term's share of the gradient below
+  } else
   rec[CRUX_PPO_LOSS] = lambda_p * p_loss + lambda_e * e_loss;
   rec[CRUX_PPO_ENTROPY] = entropy;
   const float kl = sums[1] / cnt;
@@ -153,6 +175,37 @@ __global__ void ppo_record_kernel(const float *__restrict__ sums, float *__restr
   for (int j = 0; j < A; ++j) ls_grad[j] += -lambda_e;
   if (kl > target_kl) ctl[1] = 1;  // rl/ppo.jl:59 checked after this minibatch's update (training.jl:46)
   (void)world;
+}
+
+// The PID penalty update inside lagrange_ppo_loss (rl/ppo.jl:79-106), once per loss evaluation = once per minibatch:
+//   Jc = sum(cost) / sum(episode_end) over the minibatch rows; Δ = Jc - target; I = clamp(I + Ki Δ, 0, Ki_max);
+//   smooth_Δ, smooth_Jc: EMA with the Float64 α rounded to the Float32 state; ∂ = max(0, smooth_Jc - Jc_prev);
+//   penalty = clamp(Kp smooth_Δ + I + Kd ∂, 0, penalty_max).   state = {I, smooth_Δ, smooth_Jc, Jc_prev}, one block.
+struct LagrangePid { float target_cost, penalty_max, Ki_max, Ki, Kp, Kd; double ema_alpha; };
+__global__ void lagrange_pid_kernel(const float *__restrict__ cost, const uint8_t *__restrict__ episode_end, const int32_t *__restrict__ idx,
+                                    int64_t bm, LagrangePid h, float *__restrict__ state, float *__restrict__ penalty,
+                                    float *__restrict__ lrec, const int *__restrict__ skip) {
+  if (skip && *skip) return;
+  __shared__ double sh[2][32];
+  double c = 0.0, e = 0.0;
+  for (int64_t i = threadIdx.x; i < bm; i += blockDim.x) { const int64_t r = idx[i]; c += (double)cost[r]; e += (double)episode_end[r]; }
+  c = warp_sum_d(c); e = warp_sum_d(e);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = c; sh[1][threadIdx.x >> 5] = e; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    c = 0.0; e = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { c += sh[0][w]; e += sh[1][w]; }
+    const float Jc = (float)c / (float)e;
+    const float d = Jc - h.target_cost;
+    const float I = fminf(fmaxf(state[0] + h.Ki * d, 0.f), h.Ki_max);
+    const float sd = (float)(h.ema_alpha * (double)state[1] + (1.0 - h.ema_alpha) * (double)d);
+    const float sj = (float)(h.ema_alpha * (double)state[2] + (1.0 - h.ema_alpha) * (double)Jc);
+    const float der = fmaxf(0.f, sj - state[3]);
+    state[0] = I; state[1] = sd; state[2] = sj; state[3] = sj;
+    const float pen = fminf(fmaxf(h.Kp * sd + I + h.Kd * der, 0.f), h.penalty_max);
+    penalty[0] = pen;
+    lrec[0] = pen; lrec[1] = Jc; lrec[2] = h.Kp * sd; lrec[3] = der; lrec[4] = I; lrec[7] = 1.f;
+  }
 }
 
 // critic: mse head, dz = 2 (V - R) / Bg, block partial sums of squared error
@@ -208,9 +261,68 @@ int ppo_fill_order(crux_ctx *ctx, int32_t *out, int64_t n, uint64_t seed, uint32
 }
 int ppo_ensure_bytes(crux_ctx *ctx, void **p, size_t *have, size_t need) { return ensure_bytes(ctx, p, have, need); }
 
+// LagrangePPO (rl/ppo.jl:133-214): the cost critic Vc, the :cost / :cost_advantage / :cost_return columns and the PID state
+struct LagrangeArgs {
+  crux_mlp *cost_critic;
+  const float *cost, *cost_adv, *cost_ret;
+  const uint8_t *episode_end;
+  LagrangePid pid;
+  float *state;                 // device float[5]: I, smooth_Δ, smooth_Jc, Jc_prev, penalty (persists across updates)
+  int cost_epochs; int64_t cost_batch, cost_max_batches;
+  const int32_t *order_cost;
+  float *info_l, *info_cost;    // device records, CRUX_PPO_INFO_STRIDE floats per minibatch
+};
+
+// batch_train!(V, opt, 𝒫, 𝒟) with Flux.mse(value(V, s), target) (ppo.jl:60, :208): the critic and the cost critic
+static int value_epochs(crux_gaussian *actor, crux_mlp *net, const float *s, const float *target, int64_t n, int epochs, int64_t batch,
+                        int64_t max_batches, const int32_t *order_in, uint64_t seed, int half_bits, float *mb_s, float *mb_ret, float *info) {
+  crux_ctx *ctx = actor->ctx;
+  const int sdim = net->dims[0];
+  const int64_t nmb = cdiv(n, batch);
+  int64_t total = 0;
+  const int64_t maxb = max_batches > 0 ? max_batches : INT64_MAX;
+  int rc;
+  for (int e = 0; e < epochs && total < maxb; ++e) {
+    const int32_t *order;
+    if (order_in) order = order_in + (int64_t)e * n;
+    else {
+      perm_fill_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(actor->order, n, half_bits, seed, (uint32_t)e);
+      CRUX_LAUNCHED(ctx);
+      order = actor->order;
+    }
+    const int Lc = net->n_layers;
+    for (int64_t mbi = 0; mbi < nmb && total < maxb; ++mbi, ++total) {
+      const int64_t off = mbi * batch, bm = i64min(batch, n - off);
+      float *rec = info + ((int64_t)e * nmb + mbi) * CRUX_PPO_INFO_STRIDE;
+      const float inv_bg = 1.0f / ((float)bm * (float)ctx->world);
+      {
+        GatherCols g;
+        g.n = 2;
+        g.src[0] = s; g.dst[0] = mb_s; g.dim[0] = sdim;
+        g.src[1] = target; g.dst[1] = mb_ret; g.dim[1] = 1;
+        dim3 gg((unsigned)i64min(cdiv(bm * sdim, 256), 1024), 2);
+        gather_cols_kernel<<<gg, 256, 0, ctx->stream>>>(g, order + off, bm, nullptr);
+        CRUX_LAUNCHED(ctx);
+        rc = mlp_forward_keep(net, mb_s, bm, nullptr); if (rc) return rc;
+        const int hb = (int)i64min(cdiv(bm, 256), 512);
+        critic_head_kernel<<<hb, 256, 0, ctx->stream>>>(net->act[Lc], mb_ret, bm, inv_bg, net->dz[Lc], actor->partials);
+        CRUX_LAUNCHED(ctx);
+        critic_finalize_kernel<<<1, 32, 0, ctx->stream>>>(actor->partials, hb, bm, tail_sums(net));
+        CRUX_LAUNCHED(ctx);
+        rc = mlp_backward(net, mb_s, bm, net->dz[Lc], false, false, true, nullptr); if (rc) return rc;
+      }
+      if (ctx->world > 1) { rc = grads_allreduce(ctx, net->grads, net->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
+      critic_record_kernel<<<1, 1, 0, ctx->stream>>>(tail_sums(net), rec);
+      CRUX_LAUNCHED(ctx);
+      rc = mlp_adam_step(net, rec + CRUX_PPO_GRAD_NORM, nullptr); if (rc) return rc;
+    }
+  }
+  return CRUX_OK;
+}
+
 static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *s, const float *a, const float *logprob,
                            const float *advantage, const float *ret, int64_t n, const crux_ppo_hp *hp,
-                           const int32_t *order_actor, const int32_t *order_critic, uint64_t seed) {
+                           const int32_t *order_actor, const int32_t *order_critic, uint64_t seed, const LagrangeArgs *lg = nullptr) {
   crux_ctx *ctx = actor->ctx;
   CRUX_REQUIRE(ctx, hp, "crux_ppo_update: NULL hyper-parameters");
   CRUX_REQUIRE(ctx, n >= 1, "crux_ppo_update: empty buffer");
@@ -228,14 +340,15 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
     CRUX_REQUIRE(ctx, critic->dims[0] == sdim && critic->dims[critic->n_layers] == 1, "crux_ppo_update: critic shape");
   }
   int rc;
-  {
+  if (!lg) {   // the fused kernels cover ppo_loss / a2c_loss / mse; lagrange_ppo_loss runs on the layer-by-layer engine below
     int handled = 0;
     rc = ppo_update_fused(actor, nmb_c ? critic : nullptr, s, a, logprob, advantage, ret, n, hp, order_actor, order_critic, seed, &handled);
     if (rc || handled) return rc;
   }
   // workspaces
-  const int64_t bmax = i64max(i64min(n, hp->actor_batch), nmb_c ? i64min(n, hp->critic_batch) : 0);
-  const size_t mb_floats = (size_t)bmax * (sdim + A + 3);
+  const int64_t bmax = i64max(i64max(i64min(n, hp->actor_batch), nmb_c ? i64min(n, hp->critic_batch) : 0),
+                              (lg && lg->cost_epochs > 0) ? i64min(n, lg->cost_batch) : 0);
+  const size_t mb_floats = (size_t)bmax * (sdim + A + 4);
   rc = ensure_bytes(ctx, (void **)&actor->mb, &actor->mb_bytes, mb_floats * sizeof(float)); if (rc) return rc;
   const size_t ia = (size_t)i64max(1, hp->actor_epochs * nmb_a) * CRUX_PPO_INFO_STRIDE * sizeof(float);
   const size_t ic = (size_t)i64max(1, (int64_t)hp->critic_epochs * nmb_c) * CRUX_PPO_INFO_STRIDE * sizeof(float);
@@ -248,11 +361,12 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
   }
   rc = mlp_ensure_workspace(mu, bmax); if (rc) return rc;
   if (nmb_c) { rc = mlp_ensure_workspace(critic, bmax); if (rc) return rc; }
+  if (lg && lg->cost_epochs > 0) { rc = mlp_ensure_workspace(lg->cost_critic, bmax); if (rc) return rc; }
   int half_bits = 1;
   while ((1ll << (2 * half_bits)) < n) ++half_bits;
 
   float *mb_s = actor->mb, *mb_a = mb_s + (size_t)bmax * sdim, *mb_lp = mb_a + (size_t)bmax * A, *mb_adv = mb_lp + bmax,
-        *mb_ret = mb_adv + bmax;
+        *mb_ret = mb_adv + bmax, *mb_cadv = mb_ret + bmax;
   int *skip = actor->ctl;
   reset_ctl_kernel<<<1, 1, 0, ctx->stream>>>(actor->ctl);
   CRUX_LAUNCHED(ctx);
@@ -284,16 +398,23 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
         g.src[2] = logprob; g.dst[2] = mb_lp; g.dim[2] = 1;
         g.src[3] = advantage; g.dst[3] = mb_adv; g.dim[3] = 1;
         g.src[4] = ret ? ret : advantage; g.dst[4] = mb_ret; g.dim[4] = 1;
-        dim3 gg((unsigned)i64min(cdiv(bm * sdim, 256), 1024), 5);
+        if (lg) { g.n = 6; g.src[5] = lg->cost_adv; g.dst[5] = mb_cadv; g.dim[5] = 1; }
+        dim3 gg((unsigned)i64min(cdiv(bm * sdim, 256), 1024), g.n);
         gather_cols_kernel<<<gg, 256, 0, ctx->stream>>>(g, order + off, bm, skip);
         CRUX_LAUNCHED(ctx);
+        if (lg) {   // the PID step of the loss evaluation (rl/ppo.jl:79-106) on this minibatch's rows
+          lagrange_pid_kernel<<<1, 1024, 0, ctx->stream>>>(lg->cost, lg->episode_end, order + off, bm, lg->pid, lg->state, lg->state + 4,
+                                                         lg->info_l + ((int64_t)e * nmb_a + mbi) * CRUX_PPO_INFO_STRIDE, skip);
+          CRUX_LAUNCHED(ctx);
+        }
         rc = mlp_forward_keep(mu, mb_s, bm, skip); if (rc) return rc;
         const int hb = (int)cdiv(bm, 128);
         // head partials live in scratch slot 4 (hb blocks x HEAD_STRIDE doubles)
         double *part = (double *)crux_scratch(ctx, 4, (size_t)hb * HEAD_STRIDE * sizeof(double));
         if (!part) return CRUX_ERR_OOM;
         ppo_head_kernel<<<hb, 128, 0, ctx->stream>>>(mu->act[L], mb_a, mb_lp, mb_adv, ret ? mb_ret : nullptr, actor->log_sigma, A, bm,
-                                                     inv_bg, hp->eps_clip, hp->lambda_p, hp->a2c, mu->dz[L], part, skip);
+                                                     inv_bg, hp->eps_clip, hp->lambda_p, hp->a2c, mu->dz[L], part, skip,
+                                                     lg ? mb_cadv : nullptr, lg ? lg->state + 4 : nullptr);
         CRUX_LAUNCHED(ctx);
         ppo_finalize_kernel<<<1, 128, 0, ctx->stream>>>(part, hb, A, bm, hp->lambda_e, tail_ls_grad(mu), tail_sums(mu), skip);
         CRUX_LAUNCHED(ctx);
@@ -301,7 +422,8 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
       }
       if (ctx->world > 1) { rc = grads_allreduce(ctx, mu->grads, mu->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
       ppo_record_kernel<<<1, 1, 0, ctx->stream>>>(tail_sums(mu), tail_ls_grad(mu), actor->log_sigma, A, hp->lambda_p, hp->lambda_e,
-                                                  hp->target_kl, hp->a2c, ctx->world, rec, actor->ctl);
+                                                  hp->target_kl, hp->a2c, ctx->world, rec, actor->ctl, lg ? lg->state + 4 : nullptr,
+                                                  lg ? lg->info_l + ((int64_t)e * nmb_a + mbi) * CRUX_PPO_INFO_STRIDE : nullptr);
       CRUX_LAUNCHED(ctx);
       AdamSegs segs;
       segs.n = 2;
@@ -315,42 +437,16 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
   (void)inv_world;
 
   // ---------------- critic: batch_train!(critic(π), c_opt, 𝒫, 𝒟)  on_policy.jl:68-70
-  total = 0;
-  const int64_t maxb_c = hp->critic_max_batches > 0 ? hp->critic_max_batches : INT64_MAX;
-  for (int e = 0; e < hp->critic_epochs && nmb_c && total < maxb_c; ++e) {
-    const int32_t *order;
-    if (order_critic) order = order_critic + (int64_t)e * n;
-    else {
-      perm_fill_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(actor->order, n, half_bits, seed ^ 0xC2B2AE3D27D4EB4FULL, (uint32_t)e);
-      CRUX_LAUNCHED(ctx);
-      order = actor->order;
-    }
-    const int Lc = critic->n_layers;
-    for (int64_t mbi = 0; mbi < nmb_c && total < maxb_c; ++mbi, ++total) {
-      const int64_t off = mbi * hp->critic_batch, bm = i64min(hp->critic_batch, n - off);
-      float *rec = actor->info_critic + ((int64_t)e * nmb_c + mbi) * CRUX_PPO_INFO_STRIDE;
-      const float inv_bg = 1.0f / ((float)bm * (float)ctx->world);
-      {
-        GatherCols g;
-        g.n = 2;
-        g.src[0] = s; g.dst[0] = mb_s; g.dim[0] = sdim;
-        g.src[1] = ret; g.dst[1] = mb_ret; g.dim[1] = 1;
-        dim3 gg((unsigned)i64min(cdiv(bm * sdim, 256), 1024), 2);
-        gather_cols_kernel<<<gg, 256, 0, ctx->stream>>>(g, order + off, bm, nullptr);
-        CRUX_LAUNCHED(ctx);
-        rc = mlp_forward_keep(critic, mb_s, bm, nullptr); if (rc) return rc;
-        const int hb = (int)i64min(cdiv(bm, 256), 512);
-        critic_head_kernel<<<hb, 256, 0, ctx->stream>>>(critic->act[Lc], mb_ret, bm, inv_bg, critic->dz[Lc], actor->partials);
-        CRUX_LAUNCHED(ctx);
-        critic_finalize_kernel<<<1, 32, 0, ctx->stream>>>(actor->partials, hb, bm, tail_sums(critic));
-        CRUX_LAUNCHED(ctx);
-        rc = mlp_backward(critic, mb_s, bm, critic->dz[Lc], false, false, true, nullptr); if (rc) return rc;
-      }
-      if (ctx->world > 1) { rc = grads_allreduce(ctx, critic->grads, critic->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
-      critic_record_kernel<<<1, 1, 0, ctx->stream>>>(tail_sums(critic), rec);
-      CRUX_LAUNCHED(ctx);
-      rc = mlp_adam_step(critic, rec + CRUX_PPO_GRAD_NORM, nullptr); if (rc) return rc;
-    }
+  if (nmb_c) {
+    rc = value_epochs(actor, critic, s, ret, n, hp->critic_epochs, hp->critic_batch, hp->critic_max_batches, order_critic,
+                      seed ^ 0xC2B2AE3D27D4EB4FULL, half_bits, mb_s, mb_ret, actor->info_critic);
+    if (rc) return rc;
+  }
+  // ---------------- cost critic: batch_train!(𝒮.Vc, cost_opt, 𝒫, 𝒟)  on_policy.jl:73-75 with mse(Vc(s), cost_return) (ppo.jl:208)
+  if (lg && lg->cost_epochs > 0) {
+    rc = value_epochs(actor, lg->cost_critic, s, lg->cost_ret, n, lg->cost_epochs, lg->cost_batch, lg->cost_max_batches, lg->order_cost,
+                      seed ^ 0x9E3779B97F4A7C15ULL, half_bits, mb_s, mb_ret, lg->info_cost);
+    if (rc) return rc;
   }
   return CRUX_OK;
 }
@@ -362,6 +458,53 @@ int32_t crux_ppo_update_async(crux_gaussian *actor, crux_mlp *critic, const floa
                               const int32_t *order_actor, const int32_t *order_critic, uint64_t seed) {
   if (!actor) return CRUX_ERR_INVALID;
   return ppo_update_impl(actor, critic, s, a, logprob, advantage, ret, n, hp, order_actor, order_critic, seed);
+}
+
+int32_t crux_lagrange_ppo_update(crux_gaussian *actor, crux_mlp *critic, crux_mlp *cost_critic, const float *s, const float *a,
+                                 const float *logprob, const float *advantage, const float *ret, const float *cost,
+                                 const float *cost_advantage, const float *cost_return, const uint8_t *episode_end, int64_t n,
+                                 const crux_ppo_hp *hp, const crux_lagrange_hp *lhp, float *pid_state_dev, const int32_t *order_actor,
+                                 const int32_t *order_critic, const int32_t *order_cost, uint64_t seed, float *info_actor_host,
+                                 float *info_critic_host, float *info_lagrange_host, float *info_cost_host) {
+  if (!actor) return CRUX_ERR_INVALID;
+  crux_ctx *ctx = actor->ctx;
+  CRUX_REQUIRE(ctx, hp && lhp && cost && cost_advantage && episode_end && pid_state_dev && n >= 1, "crux_lagrange_ppo_update: NULL argument");
+  CRUX_REQUIRE(ctx, !hp->a2c, "crux_lagrange_ppo_update: the Lagrange loss extends ppo_loss");
+  CRUX_REQUIRE(ctx, ctx->world == 1, "crux_lagrange_ppo_update: the PID cost estimate is not all-reduced (single rank only)");
+  const int64_t nmb_a = cdiv(n, hp->actor_batch);
+  const bool train_cost = cost_critic && lhp->cost_epochs > 0;
+  if (train_cost) {
+    CRUX_REQUIRE(ctx, cost_return && lhp->cost_batch >= 1, "crux_lagrange_ppo_update: cost critic training needs :cost_return and a batch size");
+    CRUX_REQUIRE(ctx, cost_critic->dims[0] == actor->mu->dims[0] && cost_critic->dims[cost_critic->n_layers] == 1,
+                 "crux_lagrange_ppo_update: cost critic shape");
+  }
+  const int64_t nmb_k = train_cost ? cdiv(n, lhp->cost_batch) : 0;
+  const size_t il = (size_t)i64max(1, hp->actor_epochs * nmb_a) * CRUX_PPO_INFO_STRIDE * sizeof(float);
+  const size_t ik = (size_t)i64max(1, (int64_t)lhp->cost_epochs * nmb_k) * CRUX_PPO_INFO_STRIDE * sizeof(float);
+  float *info = (float *)crux_scratch(ctx, 5, il + ik);
+  if (!info) return CRUX_ERR_OOM;
+  CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(info, 0, il + ik, ctx->stream));
+  LagrangeArgs lg;
+  lg.cost_critic = cost_critic; lg.cost = cost; lg.cost_adv = cost_advantage; lg.cost_ret = cost_return; lg.episode_end = episode_end;
+  lg.pid = LagrangePid{lhp->target_cost, lhp->penalty_max, lhp->Ki_max, lhp->Ki, lhp->Kp, lhp->Kd, lhp->ema_alpha};
+  lg.state = pid_state_dev;
+  lg.cost_epochs = train_cost ? lhp->cost_epochs : 0; lg.cost_batch = lhp->cost_batch; lg.cost_max_batches = lhp->cost_max_batches;
+  lg.order_cost = order_cost;
+  lg.info_l = info; lg.info_cost = (float *)((char *)info + il);
+  int rc = ppo_update_impl(actor, critic, s, a, logprob, advantage, ret, n, hp, order_actor, order_critic, seed, &lg);
+  if (rc) return rc;
+  const int64_t nmb_c = (critic && hp->critic_epochs > 0) ? cdiv(n, hp->critic_batch) : 0;
+  if (info_actor_host && hp->actor_epochs > 0)
+    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(info_actor_host, actor->info_actor, il, cudaMemcpyDeviceToHost, ctx->stream));
+  if (info_lagrange_host && hp->actor_epochs > 0)
+    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(info_lagrange_host, lg.info_l, il, cudaMemcpyDeviceToHost, ctx->stream));
+  if (info_critic_host && nmb_c)
+    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(info_critic_host, actor->info_critic,
+                                         (size_t)hp->critic_epochs * nmb_c * CRUX_PPO_INFO_STRIDE * sizeof(float),
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+  if (info_cost_host && nmb_k)
+    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(info_cost_host, lg.info_cost, ik, cudaMemcpyDeviceToHost, ctx->stream));
+  return crux_ctx_check(ctx);
 }
 
 int32_t crux_ppo_info_ptrs(crux_gaussian *actor, float **info_actor_dev, float **info_critic_dev) {

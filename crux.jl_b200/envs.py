@@ -39,8 +39,12 @@ class HostLinQuad:
     terminal if |s'_1| > 5; s0 ~ U(-0.1, 0.1)^S; γ = 0.99."""
     on_device = False
 
-    def __init__(self, n_envs, obs_dim=17, act_dim=6, seed=0, gamma=0.99):
+    def __init__(self, n_envs, obs_dim=17, act_dim=6, seed=0, gamma=0.99, cost_threshold=None):
         self.n_envs, self.obs_dim, self.act_dim = int(n_envs), obs_dim, act_dim
+        # optional safety signal like the reference's safety-gym envs (sampler.jl:76-78,114): info["cost"] = 1 when |s'_2| exceeds
+        # the threshold; read by the Sampler when the rollout has a :cost column (LagrangePPO)
+        self.cost_threshold = cost_threshold
+        self.last_info = {}
         self.A, self.B = linquad_matrices(obs_dim, act_dim, 0)
         self.AT, self.BT = np.ascontiguousarray(self.A.T), np.ascontiguousarray(self.B.T)
         self.gamma = F32(gamma)
@@ -67,6 +71,8 @@ class HostLinQuad:
         r = (F32(1) - np.einsum("ij,ij->i", sp, sp) / F32(self.obs_dim) - F32(0.1) * np.einsum("ij,ij->i", a, a) / F32(self.act_dim)).astype(F32)
         done = np.abs(sp[:, 0]) > F32(5)
         self.state = sp
+        if self.cost_threshold is not None:
+            self.last_info = {"cost": (np.abs(sp[:, 1]) > F32(self.cost_threshold)).astype(F32)}
         return sp, r, done
 
 

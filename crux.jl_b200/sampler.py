@@ -28,8 +28,9 @@ F32 = np.float32
 class Sampler:
     """sampler.jl:1-22.  ``mdp`` is a vectorised environment (crux.jl_b200/envs.py protocol)."""
 
-    def __init__(self, mdp, agent, S=None, max_steps=100, required_columns=(), lam=float("nan"), gamma=None, seed=0):
+    def __init__(self, mdp, agent, S=None, max_steps=100, required_columns=(), lam=float("nan"), gamma=None, seed=0, Vc=None):
         self.mdp = mdp
+        self.Vc = Vc                # value network of the cost (sampler.jl:16-18), LagrangePPO only
         self.agent = agent if isinstance(agent, PolicyParams) else PolicyParams(agent)
         self.ctx = self.agent.pi.ctx
         self.n = int(mdp.n_envs)
@@ -157,6 +158,7 @@ class Sampler:
         logp = data.get("logprob")
         discrete = isinstance(self.agent.space, DiscreteSpace)
         if self.on_device:
+            assert "cost" not in data, "the device env reports no cost: LagrangePPO rollouts use a host env with last_info['cost']"
             self._rollout_device(data, T, explore, i, reset, noise)
         elif self._can_rollout_native(explore, noise, data, discrete):
             self._rollout_host_native(data, T, reset)
@@ -165,6 +167,8 @@ class Sampler:
         # terminate_episode! bookkeeping for all closed ranges at once (sampler.jl:56-57)
         if "advantage" in data or "return" in data:
             self.fill_gae_returns_(data, T)
+        if "cost_advantage" in data or "cost_return" in data:   # sampler.jl:64-66: the same scans with source = :cost and Vc
+            self.fill_gae_returns_(data, T, source="cost", adv_key="cost_advantage", ret_key="cost_return", V=self.Vc)
         if cb is not None:
             cb(data)
         if store is not None:
@@ -234,6 +238,8 @@ class Sampler:
                 P["r"][...] = rn
                 dn = np.asarray(dn, dtype=bool)
                 P["done"][...] = dn
+            if "cost" in data:                                                # sampler.jl:76-78,114: info["cost"] of the env step
+                data["cost"][rows].copy_(torch.from_numpy(np.asarray(env.last_info["cost"], dtype=np.float32).reshape(n, 1)))
             if tcol is not None:
                 P["t"][...] = self.episode_length + 1
             self.episode_length += 1                                          # sampler.jl:130
@@ -266,7 +272,8 @@ class Sampler:
         return (explore and noise is None and not discrete and hasattr(self.mdp, "c_callbacks") and not self._needs_tovec()
                 and not getattr(self, "force_python_loop", False)
                 and isinstance(actor(pe), GaussianPolicy) and (pe is self.agent.pi or isinstance(pe, (GaussianPolicy, ActorCritic)))
-                and not actor(pe).squashed and actor(pe).log_sigma is not None and "t" not in data and "i" not in data)
+                and not actor(pe).squashed and actor(pe).log_sigma is not None and "t" not in data and "i" not in data
+                and "cost" not in data)
 
     def _rollout_host_native(self, data, T, reset):
         import ctypes as C
@@ -293,12 +300,12 @@ class Sampler:
         return bool(np.any(np.asarray(mu) != 0) or np.any(np.asarray(sg) != 1))
 
     # ---- fill_gae! / fill_returns! (sampler.jl:255-281) for every episode range of every stream
-    def fill_gae_returns_(self, data, T):
+    def fill_gae_returns_(self, data, T, source="r", adv_key="advantage", ret_key="return", V=None):
         ctx, n = self.ctx, self.n
-        adv, ret = data.get("advantage"), data.get("return")
+        adv, ret = data.get(adv_key), data.get(ret_key)
         vs = vsp = None
         if adv is not None:
-            V = critic(self.agent.pi)
+            V = critic(self.agent.pi) if V is None else V
             assert isinstance(V, ContinuousNetwork) and not math.isnan(float(self.lam)), "GAE needs a critic and λ"
             vs, vsp = self._tmp("v_s", (T * n, 1)), self._tmp("v_sp", (T * n, 1))
             V.mlp.forward(data["s"], out=vs)      # value(V, s_i) for every row
@@ -306,8 +313,8 @@ class Sampler:
             # kernel reuses V(s) of that row instead of evaluating the network again
             V.mlp.value_next(data["sp"], data["s"], vs, T, n, out=vsp)
         else:
-            vs = vsp = data["r"]  # unused by the kernel when adv is NULL
-        ctx.check(ctx.lib.crux_fill_gae_returns(ctx.h, ptr(data["r"]), ptr(data["done"]), ptr(data["episode_end"]), ptr(vs), ptr(vsp),
+            vs = vsp = data[source]  # unused by the kernel when adv is NULL
+        ctx.check(ctx.lib.crux_fill_gae_returns(ctx.h, ptr(data[source]), ptr(data["done"]), ptr(data["episode_end"]), ptr(vs), ptr(vsp),
                                                 T, n, float(self.gamma), float(0.0 if math.isnan(float(self.lam)) else self.lam),
                                                 ptr(adv), ptr(ret)))
 

@@ -90,7 +90,7 @@ class OnPolicySolver:
 
     def __init__(self, agent, S, N=1000, dN=200, max_steps=100, log=None, i=0, a_opt=None, c_opt=None, P=None,
                  post_sample_callback=None, post_batch_callback=None, lam_gae=0.95, required_columns=(), a2c=False, seed=0,
-                 interaction_storage=None, weight_column="advantage"):
+                 interaction_storage=None, weight_column="advantage", Vc=None, cost_opt=None):
         self.agent = agent if isinstance(agent, PolicyParams) else PolicyParams(agent)
         self.S, self.N, self.dN, self.max_steps, self.log, self.i = S, int(N), int(dN), int(max_steps), log, int(i)
         self.a_opt, self.c_opt, self.P = a_opt, c_opt, dict(P or {})
@@ -100,6 +100,12 @@ class OnPolicySolver:
         self.update_count = 0
         pi = self.agent.pi
         self.weight_column = weight_column
+        self.Vc, self.cost_opt = Vc, cost_opt     # on_policy.jl:51-53: parameters specific to cost constraints
+        self._pid_state = None
+        if Vc is not None:
+            assert isinstance(Vc, ContinuousNetwork) and cost_opt is not None
+            _set_adam(Vc.mlp, cost_opt.optimizer)
+            self._pid_state = pi.ctx.zeros((5,))  # I, smooth_Δ, smooth_Jc, Jc_prev, penalty (the 1-element arrays of 𝒫, ppo.jl:190-201)
         A = pi.A if isinstance(pi, ActorCritic) else pi
         assert isinstance(A, GaussianPolicy) and not A.squashed, \
             "the fused on-policy update supports GaussianPolicy(μ, logΣ vector) actors (rl/ppo.jl, rl/reinforce.jl examples)"
@@ -135,14 +141,50 @@ class OnPolicySolver:
         self.update_count += 1
         self._hp_last, self._n_last = hp, n
         self._keep = (oa, oc)
+        if self.Vc is not None:
+            return self._lagrange_training(D, hp, oa, oc, None if orders is None or len(orders) < 3 else orders[2])
         ctx.check(ctx.lib.crux_ppo_update_async(self._actor.h, pi.C.mlp.h if self.c_opt is not None else None, ptr(D["s"]), ptr(D["a"]),
                                                 ptr(D["logprob"]), ptr(D[self.weight_column]), ptr(D["return"]), n, C.byref(hp), ptr(oa),
                                                 ptr(oc), self.seed * 1000003 + self.update_count))
         return self.training_info  # lazily evaluated: reading it synchronises
 
+    def _lagrange_training(self, D, hp, oa, oc, ok):
+        """policy_gradient_training (on_policy.jl:56-78) for LagrangePPO: actor with lagrange_ppo_loss, critic, cost critic."""
+        pi, ctx, P, k = self.agent.pi, self.agent.pi.ctx, self.P, self.cost_opt
+        n = len(D)
+        lhp = _abi.LagrangeHp(target_cost=float(P["target_cost"]), penalty_max=float(P["penalty_max"]), Ki_max=float(P["Ki_max"]),
+                              Ki=float(P["Ki"]), Kp=float(P["Kp"]), Kd=float(P["Kd"]), ema_alpha=float(P["ema_alpha"]), cost_epochs=k.epochs,
+                              cost_batch=k.batch_size, cost_max_batches=0 if math.isinf(k.max_batches) else int(k.max_batches))
+        okd = None if ok is None else ctx.to_device(np.ascontiguousarray(ok, dtype=np.int32), torch.int32)
+        nmb_a, nmb_c, nmb_k = -(-n // hp.actor_batch), -(-n // hp.critic_batch), -(-n // k.batch_size)
+        ia, il = np.zeros((max(1, hp.actor_epochs * nmb_a), 8), F32), np.zeros((max(1, hp.actor_epochs * nmb_a), 8), F32)
+        ic, ik = np.zeros((max(1, hp.critic_epochs * nmb_c), 8), F32), np.zeros((max(1, k.epochs * nmb_k), 8), F32)
+        ctx.check(ctx.lib.crux_lagrange_ppo_update(self._actor.h, pi.C.mlp.h, self.Vc.mlp.h, ptr(D["s"]), ptr(D["a"]), ptr(D["logprob"]),
+                                                   ptr(D["advantage"]), ptr(D["return"]), ptr(D["cost"]), ptr(D["cost_advantage"]),
+                                                   ptr(D["cost_return"]), ptr(D["episode_end"]), n, C.byref(hp), C.byref(lhp),
+                                                   ptr(self._pid_state), ptr(oa), ptr(oc), ptr(okd), self.seed * 1000003 + self.update_count,
+                                                   ptr(ia), ptr(ic), ptr(il), ptr(ik)))
+        valid = np.flatnonzero(ia[:, _abi.PPO_VALID] > 0)
+        info = {"actor_batches_trained": int(len(valid))}
+        if len(valid):
+            last, ll = ia[valid[-1]], il[valid[-1]]
+            info.update({"actor_loss": float(last[_abi.PPO_LOSS]), "actor_grad_norm": float(last[_abi.PPO_GRAD_NORM]),
+                         "entropy": float(last[_abi.PPO_ENTROPY]), "kl": float(last[_abi.PPO_KL]), "clip_fraction": float(last[_abi.PPO_CLIP_FRAC]),
+                         "avg_advantage": float(last[_abi.PPO_AVG_ADV]), "avg_return": float(last[_abi.PPO_AVG_RET]),
+                         "penalty": float(ll[0]), "cur_cost": float(ll[1]), "prop_term": float(ll[2]), "deriv_term": float(ll[3]),
+                         "integral term": float(ll[4]), "p_loss": float(ll[5]), "cost_loss": float(ll[6])})
+        for name, rec in (("critic_", ic), ("cost_critic_", ik)):
+            v = np.flatnonzero(rec[:, _abi.PPO_VALID] > 0)
+            if len(v):
+                info.update({name + "loss": float(rec[v[-1], _abi.PPO_LOSS]), name + "grad_norm": float(rec[v[-1], _abi.PPO_GRAD_NORM])})
+        self.last_info = info
+        return lambda: info
+
     def training_info(self):
         """Aggregated info of the last update.  ``batch_train!`` pushes the SAME dict for every minibatch
         (training.jl:43), so the reference's aggregates equal the last trained minibatch's values."""
+        if self.Vc is not None:
+            return self.last_info
         pi, ctx = self.agent.pi, self.agent.pi.ctx
         hp, n = self._hp_last, self._n_last
         pa, pc = C.c_void_p(), C.c_void_p()
@@ -197,6 +239,29 @@ def A2C(pi, S, lp=1.0, le=0.1, a_opt=None, c_opt=None, log=None, required_column
                           post_sample_callback=_whiten_advantage, required_columns=cols, log=log, **kw)
 
 
+def _record_avgr(D, info=None, **_):
+    """post_sample_callback of LagrangePPO (ppo.jl:181-183): info[:avg_r] = sum(r) / sum(episode_end)."""
+    if info is not None:
+        info["avg_r"] = float(D["r"].sum().item()) / max(float(D["episode_end"].sum().item()), 1.0)
+
+
+def LagrangePPO(pi, Vc, S, eps=0.2, lp=1.0, le=0.1, lam_gae=0.95, target_kl=0.012, target_cost=0.025, penalty_scale=1.0,
+                penalty_max=math.inf, Ki_max=10.0, Ki=1e-3, Kp=1, Kd=0, ema_alpha=0.95, a_opt=None, c_opt=None, cost_opt=None, log=None,
+                required_columns=(), **kw):
+    """``LagrangePPO(;π::ActorCritic, Vc::ContinuousNetwork, ϵ, λp, λe, λ_gae, target_kl, target_cost, penalty_max, Ki_max, Ki, Kp,
+    Kd, ema_α, a_opt, c_opt, cost_opt, ...)`` rl/ppo.jl:133-214: PPO whose actor loss adds a PID-weighted clipped cost-advantage
+    surrogate (``lagrange_ppo_loss`` :70-131), plus a cost critic trained on ``cost_return``.  The rollout needs a host env that
+    reports ``last_info["cost"]`` (sampler.jl:76-78,114); ``penalty_scale`` is carried but unused, as in the reference (:112)."""
+    a = TrainingParams(loss="lagrange_ppo_loss", name="actor_", target_kl=target_kl, **(a_opt or {}))
+    c = TrainingParams(loss="mse", name="critic_", **(c_opt or {}))
+    k = TrainingParams(loss="mse", name="cost_critic_", **(cost_opt or {}))
+    cols = list(dict.fromkeys(list(required_columns) + ["return", "advantage", "logprob", "cost_advantage", "cost", "cost_return"]))
+    P = {"eps": F32(eps), "lp": F32(lp), "le": F32(le), "target_cost": F32(target_cost), "penalty_scale": F32(penalty_scale),
+         "penalty_max": F32(penalty_max), "Ki_max": F32(Ki_max), "Ki": F32(Ki), "Kp": Kp, "Kd": Kd, "ema_alpha": float(ema_alpha)}
+    return OnPolicySolver(PolicyParams(pi), S, P=P, a_opt=a, c_opt=c, Vc=Vc, cost_opt=k, lam_gae=lam_gae, post_batch_callback=_whiten_advantage,
+                          post_sample_callback=_record_avgr, required_columns=cols, log=log, **kw)
+
+
 def REINFORCE(pi, S, a_opt=None, log=None, required_columns=(), **kw):
     """``REINFORCE(;π, a_opt, ...)`` rl/reinforce.jl:27-39: ``reinforce_loss = -mean(logpdf(π, s, a) .* return)`` (:4-13), early
     stop at KL > 0.015, no critic.  It is the a2c_loss kernel head with the ``return`` column as the per-row weight, λp = 1 and
@@ -213,7 +278,8 @@ def _solve_on_policy(S, mdp):
     if S.buffer is None:
         S.buffer = ExperienceBuffer(S.S, S.agent.space, S.dN, S.required_columns, ctx=pi.ctx)
     if S.sampler is None or S.sampler.mdp is not mdp:
-        S.sampler = Sampler(mdp, S.agent, S=S.S, required_columns=S.required_columns, lam=S.lam_gae, max_steps=S.max_steps, seed=S.seed)
+        S.sampler = Sampler(mdp, S.agent, S=S.S, required_columns=S.required_columns, lam=S.lam_gae, max_steps=S.max_steps, seed=S.seed,
+                            Vc=S.Vc)
     D, s = S.buffer, S.sampler
     if S.log is not None and S.log.sampler is None:
         S.log.sampler = s

@@ -246,6 +246,33 @@ int32_t crux_ppo_update_async(crux_gaussian *actor, crux_mlp *critic, const floa
                               uint64_t seed);
 int32_t crux_ppo_info_ptrs(crux_gaussian *actor, float **info_actor_dev, float **info_critic_dev);
 
+/* LagrangePPO (rl/ppo.jl:133-214): policy_gradient_training (on_policy.jl:56-78) with lagrange_ppo_loss (ppo.jl:70-131) for the
+ * actor, mse(V(s), return) for the critic and mse(Vc(s), cost_return) for the cost critic (:207-208), in that order.
+ * The loss evaluates a PID controller on the minibatch's average episode cost sum(cost)/sum(episode_end) (:79-106) ONCE per
+ * minibatch and scales the clipped cost-advantage surrogate with the resulting penalty:
+ *   loss = (λp·p_loss + λe·e_loss + penalty·mean(max(r·Ac, clamp(r, 1-ϵ, 1+ϵ)·Ac))) / (1 + penalty).
+ * pid_state_dev: device float[5] = {I, smooth_Δ, smooth_Jc, Jc_prev, penalty}, zero-initialised by the caller, persists
+ * across updates (the reference keeps them in 𝒫).  Runs on the layer-by-layer engine (the fused kernels cover ppo/a2c/mse).
+ * info_lagrange_host [actor minibatches][8] = penalty, cur_cost, prop_term, deriv_term, integral term, λp·p_loss, cost_loss, valid;
+ * info_cost_host [cost minibatches][8] like info_critic_host.  Single rank only. */
+typedef struct crux_lagrange_hp {
+  float target_cost;  /* 𝒫[:target_cost] ppo.jl:146 */
+  float penalty_max;  /* Inf32 */
+  float Ki_max, Ki, Kp, Kd;
+  double ema_alpha;   /* Float64 0.95 in the reference */
+  int32_t cost_epochs;
+  int64_t cost_batch;
+  int64_t cost_max_batches; /* 0 = Inf */
+} crux_lagrange_hp;
+int32_t crux_lagrange_ppo_update(crux_gaussian *actor, crux_mlp *critic, crux_mlp *cost_critic, const float *s,
+                                 const float *a, const float *logprob, const float *advantage, const float *ret,
+                                 const float *cost, const float *cost_advantage, const float *cost_return,
+                                 const uint8_t *episode_end, int64_t n, const crux_ppo_hp *hp,
+                                 const crux_lagrange_hp *lhp, float *pid_state_dev, const int32_t *order_actor,
+                                 const int32_t *order_critic, const int32_t *order_cost, uint64_t seed,
+                                 float *info_actor_host, float *info_critic_host, float *info_lagrange_host,
+                                 float *info_cost_host);
+
 /* One DQN critic `train!` (off_policy.jl:91-93 with td_loss utils.jl:76-87 on a DiscreteNetwork):
  * loss = agg((Σ Q(s)·a_onehot - y)²), agg = mean or weighted_mean(weight) (utils.jl:47).
  * info_out_host[0..2] = loss, grad_norm, Qavg (synchronises; NULL skips the readback). */

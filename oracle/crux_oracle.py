@@ -638,6 +638,49 @@ def a2c_loss(pi, P, D, info=None):
     return float(P["lp"]) * p_loss + float(P["le"]) * e_loss
 
 
+def lagrange_params(eps=0.2, lp=1.0, le=0.1, target_cost=0.025, penalty_max=math.inf, Ki_max=10.0, Ki=1e-3, Kp=1, Kd=0, ema_alpha=0.95):
+    """The 𝒫 NamedTuple of ``LagrangePPO`` (rl/ppo.jl:185-202): Float32 scalars and 1-element Float32 state arrays;
+    ``ema_α`` stays Float64 like the reference's literal ``0.95``."""
+    return {"eps": F32(eps), "lp": F32(lp), "le": F32(le), "target_cost": F32(target_cost), "penalty_max": F32(penalty_max),
+            "Ki_max": F32(Ki_max), "Ki": F32(Ki), "Kp": Kp, "Kd": Kd, "ema_alpha": float(ema_alpha),
+            "I": F32(0), "Jc_prev": F32(0), "smooth_D": F32(0), "smooth_Jc": F32(0)}
+
+
+def lagrange_ppo_loss(pi, P, D, info=None):
+    """rl/ppo.jl:70-131.  The PID penalty update (:79-106) runs inside the loss, once per evaluation, and mutates ``P``."""
+    info = {} if info is None else info
+    new_probs = pi.logpdf(D["s"], D["a"])
+    old = torch.as_tensor(D["logprob"], dtype=torch.float32).reshape(-1, 1)
+    r = torch.exp(new_probs - old)
+    A = torch.as_tensor(D["advantage"], dtype=torch.float32).reshape(-1, 1)
+    Ac = torch.as_tensor(D["cost_advantage"], dtype=torch.float32).reshape(-1, 1)
+    lo, hi = float(F32(1) - F32(P["eps"])), float(F32(1) + F32(P["eps"]))
+    p_loss = -torch.mean(torch.minimum(r * A, torch.clamp(r, lo, hi) * A))
+    e_loss = -torch.mean(torch.as_tensor(pi.entropy(D["s"])))
+    # ---- penalty (ignore_derivatives block)
+    Jc = F32(np.sum(np.asarray(D["cost"], dtype=F32), dtype=np.float64)) / F32(np.sum(np.asarray(D["episode_end"]).astype(np.int64)))
+    d = F32(Jc - P["target_cost"])
+    P["I"] = F32(min(max(F32(P["I"] + P["Ki"] * d), F32(0)), P["Ki_max"]))
+    al = P["ema_alpha"]
+    P["smooth_D"] = F32(al * float(P["smooth_D"]) + (1.0 - al) * float(d))
+    P["smooth_Jc"] = F32(al * float(P["smooth_Jc"]) + (1.0 - al) * float(Jc))
+    der = F32(max(F32(0), F32(P["smooth_Jc"] - P["Jc_prev"])))
+    P["Jc_prev"] = P["smooth_Jc"]
+    penalty = F32(min(max(F32(F32(P["Kp"]) * P["smooth_D"] + P["I"] + F32(P["Kd"]) * der), F32(0)), P["penalty_max"]))
+    info.update({"penalty": float(penalty), "cur_cost": float(Jc), "prop_term": float(F32(P["Kp"]) * P["smooth_D"]),
+                 "deriv_term": float(der), "integral term": float(P["I"])})
+    cost_loss = float(penalty) * torch.mean(torch.maximum(r * Ac, torch.clamp(r, lo, hi) * Ac))
+    with torch.no_grad():
+        info["entropy"] = float(-e_loss)
+        info["kl"] = float(torch.mean(old - new_probs))
+        info["clip_fraction"] = float(torch.sum((r > hi) | (r < lo))) / r.numel()
+        info["p_loss"] = float(float(P["lp"]) * p_loss)
+        info["cost_loss"] = float(cost_loss)
+        info["avg_advantage"] = float(torch.mean(A))
+        info["avg_return"] = float(np.mean(np.asarray(D["return"], dtype=F32)))
+    return (float(P["lp"]) * p_loss + float(P["le"]) * e_loss + cost_loss) / (1.0 + float(penalty))
+
+
 def reinforce_loss(pi, P, D, info=None):
     """rl/reinforce.jl:4-13: ``-mean(logpdf(π, s, a) .* return)``; info: entropy, kl."""
     info = {} if info is None else info

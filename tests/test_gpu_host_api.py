@@ -242,6 +242,39 @@ def test_solve_reinforce_runs_without_a_critic(crux, ctx):
     assert not np.array_equal(before, pi.mu.mlp.get_flat())
 
 
+def test_solve_lagrange_ppo_runs(crux, ctx):
+    """rl/ppo.jl:133-214 through solve(): :cost from the env's info, cost GAE / returns with Vc (sampler.jl:64-66), the PID penalty
+    and the cost critic."""
+    n, T = 32, 8
+    pi = _actor_critic(crux, ctx, seed=8)
+    rng = np.random.default_rng(9)
+    D = crux.Dense
+    Vc = crux.ContinuousNetwork(crux.Chain(D(17, 64, crux.tanh, rng=rng), D(64, 64, crux.tanh, rng=rng), D(64, 1, rng=rng)), ctx=ctx)
+    before_vc = Vc.mlp.get_flat().copy()
+    opt = dict(epochs=2, batch_size=128)
+    S = crux.LagrangePPO(pi, Vc, crux.ContinuousSpace(17), a_opt=dict(opt), c_opt=dict(opt), cost_opt=dict(opt), N=3 * n * T, dN=n * T,
+                         max_steps=50, target_cost=0.0, Ki=0.5)
+    env = crux.HostLinQuad(n, seed=1, cost_threshold=0.05)
+    assert crux.solve(S, env) is pi and S.i == 3 * n * T
+    info = S.training_info()
+    for k in ("actor_loss", "critic_loss", "cost_critic_loss", "penalty", "cur_cost", "integral term", "p_loss", "cost_loss"):
+        assert np.isfinite(info[k]), k
+    assert info["cur_cost"] > 0 and info["penalty"] > 0          # costs occur, the integral term has wound up
+    cost = host(S.buffer["cost"])[:, 0]
+    assert set(np.unique(cost)) <= {0.0, 1.0} and cost.sum() > 0
+    # cost_return is the discounted cost-to-go inside each episode range: check the recurrence on the stored rollout
+    cr, ee = host(S.buffer["cost_return"])[:, 0].reshape(T, n), host(S.buffer["episode_end"])[:, 0].reshape(T, n).astype(bool)
+    c2 = cost.reshape(T, n)
+    want = np.zeros((T, n), F32); acc = np.zeros(n, F32)
+    for t in range(T - 1, -1, -1):
+        acc = np.where(ee[t], F32(0), acc)
+        acc = (c2[t] + F32(0.99) * acc).astype(F32)
+        want[t] = acc
+    assert_close(cr, want, rtol=1e-5, atol=1e-6, what="cost_return")
+    assert np.abs(host(S.buffer["cost_advantage"])).sum() > 0
+    assert not np.array_equal(before_vc, Vc.mlp.get_flat())
+
+
 # ------------------------------------------------------------------------------------------------ DQN / SAC
 def test_dqn_value_training_matches_oracle(crux, ctx):
     """value_training (off_policy.jl:66-111) for DQN with injected sample ids: dqn_target -> td_loss train! x epochs -> polyak."""

@@ -173,6 +173,56 @@ def test_reinforce_loss_is_the_a2c_head_weighted_by_returns(ctx, crux):
     assert_params_close(mlp_params(ctx, hm), pi.mu.flat(), 3e-4, len(ra), what="actor params")
 
 
+def test_lagrange_ppo_update_matches_oracle(ctx, crux):
+    """LagrangePPO (rl/ppo.jl:70-214): the PID penalty evaluated once per minibatch on sum(cost)/sum(episode_end), the clipped
+    cost-advantage surrogate, the (1 + penalty) normalisation, then the critic and the cost critic on cost_return."""
+    n, ab, cb = 1024, 256, 512
+    rng, pi, cr, handles, D = _setup(ctx, crux, n, seed=23)
+    hm, hc, h = handles
+    vc = o.MLP([17, 64, 64, 1], [o.ACT_TANH, o.ACT_TANH, o.ACT_IDENTITY], rng)
+    hk = make_mlp(ctx, vc.dims, vc.acts, vc.flat())
+    ctx.check(ctx.lib.crux_mlp_set_adam(hk, float(F32(3e-4)), 0.9, 0.999, 1e-8))
+    D["cost"] = (rng.random(n) < 0.3).astype(F32) * rng.random(n).astype(F32)
+    D["cost_advantage"] = rng.standard_normal(n).astype(F32)
+    D["cost_return"] = rng.standard_normal(n).astype(F32)
+    D["episode_end"] = (rng.random(n) < 0.1)
+    hp = _hp(crux, actor_batch=ab, actor_epochs=3, critic_epochs=1, critic_batch=cb)
+    lhp = crux._abi.LagrangeHp(target_cost=0.025, penalty_max=math.inf, Ki_max=10.0, Ki=0.05, Kp=1.0, Kd=0.5, ema_alpha=0.95,
+                               cost_epochs=2, cost_batch=cb, cost_max_batches=0)
+    oa = _orders(rng, n, 3); oc = _orders(rng, n, 1, start=oa[-1]); ok = _orders(rng, n, 2, start=oc[-1])
+    P = o.lagrange_params(eps=0.2, lp=1.0, le=0.1, target_cost=0.025, Ki=0.05, Kp=1, Kd=0.5)
+    ra = _oracle_train(pi.params(), lambda mb, inf: o.lagrange_ppo_loss(pi, P, mb, inf), o.Adam(F32(3e-4)), D, oa, ab)
+    rc_ = _oracle_train(cr.params(), lambda mb, inf: o.value_mse_loss(cr, mb), o.Adam(F32(3e-4)), D, oc, cb)
+    rk = _oracle_train(vc.params(), lambda mb, inf: o.value_mse_loss(vc, dict(mb, **{"return": mb["cost_return"]})), o.Adam(F32(3e-4)), D, ok, cb)
+    d = {k: dev(ctx, v.astype(np.uint8) if v.dtype == bool else v) for k, v in D.items()}
+    state = dev(ctx, np.zeros(5, F32))
+    ia = np.zeros((len(ra), 8), F32); il = np.zeros((len(ra), 8), F32); ic = np.zeros((len(rc_), 8), F32); ik = np.zeros((len(rk), 8), F32)
+    ctx.check(ctx.lib.crux_lagrange_ppo_update(h, hc, hk, p(d["s"]), p(d["a"]), p(d["logprob"]), p(d["advantage"]), p(d["return"]), p(d["cost"]),
+                                               p(d["cost_advantage"]), p(d["cost_return"]), p(d["episode_end"]), n, C.byref(hp), C.byref(lhp),
+                                               p(state), p(dev(ctx, oa)), p(dev(ctx, oc)), p(dev(ctx, ok)), 42, p(ia), p(ic), p(il), p(ik)))
+    A = crux._abi
+    assert any(rec["penalty"] > 0 for rec in ra), "the test must exercise a non-zero penalty"
+    for k, rec in enumerate(ra):
+        assert ia[k, A.PPO_VALID] == 1.0 and il[k, 7] == 1.0
+        want = [rec["penalty"], rec["cur_cost"], rec["prop_term"], rec["deriv_term"], rec["integral term"], rec["p_loss"], rec["cost_loss"]]
+        assert_close(il[k, :7], want, rtol=2e-4, atol=2e-6, what=f"lagrange info mb {k}")
+        assert_close(ia[k, A.PPO_LOSS], rec["loss"], rtol=1e-4, atol=1e-5, what=f"actor loss mb {k}")
+        assert_close(ia[k, A.PPO_KL], rec["kl"], rtol=1e-3, atol=2e-6, what=f"kl mb {k}")
+        assert_close(ia[k, A.PPO_GRAD_NORM], rec["grad_norm"], rtol=1e-3, what=f"grad_norm mb {k}")
+    for k, rec in enumerate(rc_):
+        assert_close(ic[k, A.PPO_LOSS], rec["loss"], rtol=1e-4, what=f"critic loss mb {k}")
+    for k, rec in enumerate(rk):
+        assert_close(ik[k, A.PPO_LOSS], rec["loss"], rtol=1e-4, what=f"cost critic loss mb {k}")
+    assert_params_close(mlp_params(ctx, hm), pi.mu.flat(), 3e-4, len(ra), what="actor params")
+    assert_params_close(mlp_params(ctx, hc), cr.flat(), 3e-4, len(rc_), what="critic params")
+    assert_params_close(mlp_params(ctx, hk), vc.flat(), 3e-4, len(rk), what="cost critic params")
+    st = host(state)
+    assert_close(st, [P["I"], P["smooth_D"], P["smooth_Jc"], P["Jc_prev"], ra[-1]["penalty"]], rtol=2e-4, atol=2e-6, what="PID state")
+    lsp = C.c_void_p(); ctx.check(ctx.lib.crux_gaussian_log_sigma_ptr(h, C.byref(lsp)))
+    ls = np.empty(6, F32); ctx.check(ctx.lib.crux_memcpy_d2h(ctx.h, p(ls), lsp, 24)); ctx.sync()
+    assert_close(ls, pi.log_sigma.detach().numpy(), rtol=1e-5, atol=2e-6, what="logΣ")
+
+
 def test_device_permutation_is_a_permutation_and_trains(ctx, crux):
     """order == NULL: device-generated shuffles.  Each epoch must visit every row exactly once (checked through a
     critic whose target equals a per-row id-free constant is not observable; instead check determinism + change)."""

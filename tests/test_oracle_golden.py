@@ -266,3 +266,35 @@ def test_soft_value_and_reinforce_restatements():
     l1 = o.reinforce_loss(pi, {}, D, i1)
     l2 = o.a2c_loss(pi, {"lp": F32(1), "le": F32(0)}, dict(D, advantage=D["return"]), i2)
     assert torch.equal(l1, l2) and i1["kl"] == i2["kl"] and i1["entropy"] == i2["entropy"]
+
+
+def test_lagrange_ppo_loss_restatement():
+    # rl/ppo.jl:70-131: with a zero penalty the loss IS ppo_loss; the PID terms follow the hand-computed recurrences
+    import torch
+    rng = np.random.default_rng(4)
+    mu = o.MLP([3, 8, 2], [o.ACT_TANH, o.ACT_IDENTITY], rng)
+    pi = o.GaussianPolicy(mu, np.full(2, -0.5, F32))
+    n = 64
+    D = {"s": rng.standard_normal((n, 3)).astype(F32), "a": rng.standard_normal((n, 2)).astype(F32),
+         "logprob": (-3 + 0.1 * rng.standard_normal(n)).astype(F32), "advantage": rng.standard_normal(n).astype(F32),
+         "return": rng.standard_normal(n).astype(F32), "cost_advantage": rng.standard_normal(n).astype(F32),
+         "cost": (rng.random(n) < 0.5).astype(F32), "episode_end": rng.random(n) < 0.2}
+    P0 = o.lagrange_params(target_cost=1e6)                       # Δ << 0: I clamps at 0, Kp·smooth_Δ < 0 -> penalty 0
+    i0, i1 = {}, {}
+    l0 = o.lagrange_ppo_loss(pi, P0, D, i0)
+    l1 = o.ppo_loss(pi, P0, D, i1)
+    assert i0["penalty"] == 0.0 and torch.allclose(l0, l1, rtol=0, atol=1e-7) and i0["kl"] == i1["kl"]
+    P = o.lagrange_params(target_cost=0.025, Ki=0.1, Kp=2, Kd=1)
+    Jc = D["cost"].sum() / D["episode_end"].sum()
+    info = {}
+    o.lagrange_ppo_loss(pi, P, D, info)
+    d = Jc - 0.025
+    want_I, want_sd, want_sj = 0.1 * d, 0.05 * d, 0.05 * Jc
+    want_pen = 2 * want_sd + want_I + 1 * max(0.0, want_sj - 0.0)
+    assert np.isclose(info["cur_cost"], Jc, rtol=1e-6) and np.isclose(info["integral term"], want_I, rtol=1e-5)
+    assert np.isclose(info["prop_term"], 2 * want_sd, rtol=1e-5) and np.isclose(info["deriv_term"], want_sj, rtol=1e-5)
+    assert np.isclose(info["penalty"], want_pen, rtol=1e-5) and np.isclose(float(P["Jc_prev"]), want_sj, rtol=1e-5)
+    info2 = {}
+    l2 = o.lagrange_ppo_loss(pi, P, D, info2)                     # second evaluation: the state carries over
+    assert np.isclose(info2["integral term"], 2 * want_I, rtol=1e-5) and info2["penalty"] > info["penalty"]
+    assert np.isclose(float(l2), (info2["p_loss"] + 0.1 * -info2["entropy"] + info2["cost_loss"]) / (1 + info2["penalty"]), rtol=1e-5)
