@@ -358,6 +358,10 @@ struct FwdArgs {
   // call); x_copy receives the rows on the device (the s column of the rollout) and y2 (pinned host) a second copy of the actions
   float *x_copy;
   float *y2;
+  // rows whose x_flag byte (pinned host) is set read their input from x_reset instead of x: the next observation of a stream is
+  // its s' row of the previous vector step unless the episode ended there, in which case it is the freshly reset state
+  const uint8_t *x_flag;
+  const float *x_reset;
 };
 
 // ---- small-batch variant pieces: 16-row tiles (4x more CTAs for a 4096-stream vector step), thread = (1 row, 4 cols)
@@ -425,6 +429,7 @@ __global__ void __launch_bounds__(NT, RT == RB ? 1 : 2) fused_forward_kernel(Fwd
         if (row >= 0) {
           if (a.x_copy) {   // x is pinned host memory written by the host since the last launch: bypass every cache
             v = __ldcv(a.x + (int64_t)row * I + i);
+            if (a.x_flag && __ldcv(a.x_flag + row)) v = __ldcv(a.x_reset + (int64_t)row * I + i);
             if (which == 0) a.x_copy[(int64_t)row * I + i] = v;
           } else {
             v = __ldg(a.x + (int64_t)row * I + i);
@@ -1646,7 +1651,8 @@ extern "C" int32_t crux_rollout_step_fused(crux_gaussian *actor, crux_mlp *criti
 // into the device column s_dev, and writes the actions both to the device column and to pinned host memory -- one launch, no copy
 // calls (crux_rollout_host).  Same arithmetic and noise streams as crux_rollout_step_rows.
 extern "C" int32_t crux_rollout_step_rows_mapped(crux_gaussian *actor, const float *obs_pinned, int64_t N, int64_t row0, uint64_t seed, uint64_t ctr,
-                                                 float *s_dev, float *a_dev, float *a_pinned, float *logp_dev) {
+                                                 float *s_dev, float *a_dev, float *a_pinned, float *logp_dev, const uint8_t *reset_flag_pinned,
+                                                 const float *reset_obs_pinned) {
   if (!actor) return CRUX_ERR_INVALID;
   crux_ctx *ctx = actor->ctx;
   CRUX_REQUIRE(ctx, fused_rows_supported(actor), "crux_rollout_step_rows_mapped: only the fused policy shapes support split vector steps");
@@ -1656,6 +1662,7 @@ extern "C" int32_t crux_rollout_step_rows_mapped(crux_gaussian *actor, const flo
   memset(&a, 0, sizeof(a));
   a.net[0] = describe(actor->mu); a.mode[0] = 1; a.y[0] = a_dev; a.y2 = a_pinned; a.logp = logp_dev; a.ls = actor->log_sigma;
   a.seed = seed; a.ctr = ctr; a.x = obs_pinned; a.x_copy = s_dev; a.B = N; a.row0 = row0;
+  a.x_flag = reset_flag_pinned; a.x_reset = reset_obs_pinned;
   return launch_forward(ctx, a, 1);
 }
 

@@ -19,7 +19,8 @@
 #include <stdlib.h>
 
 extern "C" int32_t crux_rollout_step_rows_mapped(crux_gaussian *actor, const float *obs_pinned, int64_t N, int64_t row0, uint64_t seed, uint64_t ctr,
-                                                 float *s_dev, float *a_dev, float *a_pinned, float *logp_dev);
+                                                 float *s_dev, float *a_dev, float *a_pinned, float *logp_dev, const uint8_t *reset_flag_pinned,
+                                                 const float *reset_obs_pinned);
 bool fused_rows_supported(const crux_gaussian *actor);
 
 struct HostRolloutStage {
@@ -72,12 +73,24 @@ extern "C" int32_t crux_rollout_host(crux_gaussian *actor, int64_t N, int32_t T,
 
   constexpr int UPLOAD_STEPS = 8;
   const bool mapped = G == 2;   // the fused policy shapes: the kernel does its own PCIe reads / writes
+  // The host copies s' into the observation buffer the next forward reads (one memcpy per half step, ~0.2 ms per rollout).  Letting the
+  // kernel read the s' rows where the env's worker threads left them (CRUX_ROLLOUT_DIRECT=1: staging rows + an episode_end flag per
+  // row selecting the reset state) measured 30x SLOWER on the PCIe side (8.0 ms instead of 0.26 ms of event waits per 32-step
+  // rollout, scripts/e2e_ab.py): those lines sit modified in 16 different cores' caches and every device read snoops them out one
+  // by one, while the copy leaves one core's streaming stores behind.
+  static const bool copy_obs = getenv("CRUX_ROLLOUT_DIRECT") == nullptr;
   auto enqueue_forward = [&](int g, int t) -> int {  // obs_g -> s[t]; policy forward; action back to the host; event
     const int64_t row = (int64_t)t * N + lo[g], n = hi[g] - lo[g];
     float *s_t = cols->s + row * sdim, *a_t = cols->a + row * adim;
     float *lp = cols->logprob ? cols->logprob + row : nullptr;
     if (mapped) {
-      int rc2 = crux_rollout_step_rows_mapped(actor, obs_pinned + lo[g] * sdim, n, lo[g], seed, ctr0 + (uint64_t)t, s_t, a_t, S.a + lo[g] * adim, lp);
+      // step 0 reads the current observations; every later step reads the s' rows the env wrote for the previous vector step straight
+      // from the rollout staging, except the streams whose episode ended there (episode_end flag): those read the reset state
+      const bool direct = t > 0 && !copy_obs;
+      const float *x = direct ? S.sp + ((size_t)(t - 1) * N + lo[g]) * sdim : obs_pinned + lo[g] * sdim;
+      const uint8_t *flag = direct ? S.ee + (size_t)(t - 1) * N + lo[g] : nullptr;
+      int rc2 = crux_rollout_step_rows_mapped(actor, x, n, lo[g], seed, ctr0 + (uint64_t)t, s_t, a_t, S.a + lo[g] * adim, lp, flag,
+                                              obs_pinned + lo[g] * sdim);
       if (rc2) return rc2;
     } else {
       CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(s_t, obs_pinned + lo[g] * sdim, (size_t)n * sdim * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -121,8 +134,9 @@ extern "C" int32_t crux_rollout_host(crux_gaussian *actor, int64_t N, int32_t T,
         ee_t[e] = end ? 1 : 0;
         if (end) { S.idx.push_back((int32_t)e); episode_length[e] = 0; }
       }
-      // next observation: sp, or a fresh initial state where the episode ended (terminate_episode! -> reset_sampler!)
-      memcpy(obs_pinned + e0 * sdim, sp_t + e0 * sdim, (size_t)n * sdim * sizeof(float));
+      // next observation: sp, or a fresh initial state where the episode ended (terminate_episode! -> reset_sampler!).  With the
+      // mapped forward the kernel picks sp / reset rows itself; obs_pinned is brought up to date once, after the last vector step
+      if (!mapped || copy_obs || t + 1 == T) memcpy(obs_pinned + e0 * sdim, sp_t + e0 * sdim, (size_t)n * sdim * sizeof(float));
       if (!S.idx.empty()) {
         reset(user, S.idx.data(), (int32_t)S.idx.size(), S.robs);
         for (size_t q = 0; q < S.idx.size(); ++q) memcpy(obs_pinned + (size_t)S.idx[q] * sdim, S.robs + q * sdim, sizeof(float) * sdim);
