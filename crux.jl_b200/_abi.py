@@ -159,6 +159,7 @@ _SIGS = {
     "crux_nccl_allreduce_f32": [_vp, _vp, _i64],
     "crux_peer_handle": [_vp, _vp, _i64],
     "crux_peer_init": [_vp, _i32, _i32, _vp],
+    "crux_peer_disable": [_vp],
 }
 _RESTYPE = {"crux_last_error": C.c_char_p}
 

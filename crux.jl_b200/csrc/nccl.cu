@@ -192,6 +192,14 @@ int32_t crux_peer_init(crux_ctx *ctx, int32_t rank, int32_t world, const uint8_t
   return CRUX_OK;
 }
 
+// Turns the peer paths off again (the mapped buffers stay allocated): every rank must call it when ANY rank failed to map its
+// peers, so that all of them fall back to NCCL together.
+int32_t crux_peer_disable(crux_ctx *ctx) {
+  if (!ctx) return CRUX_ERR_INVALID;
+  ctx->peer_ready = false;
+  return CRUX_OK;
+}
+
 int32_t crux_peer_allreduce(crux_ctx *ctx, float *buf, int64_t n) {
   CRUX_REQUIRE(ctx, ctx->peer_ready && n <= ctx->peer_cap, "crux_peer_allreduce: not initialised or vector too long");
   PeerPtrs pp;

@@ -1336,7 +1336,9 @@ __global__ void __launch_bounds__(RW * 32, FUSE ? 1 : 2) reduce_fused_partials_k
     grads[idx] = v;
     if (peer.enabled) {
       const unsigned long long word = ((unsigned long long)(unsigned int)pseq << 32) | (unsigned long long)__float_as_uint(v);
-      for (int q = 0; q < peer.world; ++q) *(volatile unsigned long long *)(peer.ll[q] + pbase + idx) = word;   // single 8-byte store: no fence, no flag
+      // single 8-byte stores: no fence, no flag.  (Parking the words in shared memory and letting warp q store to rank q measured
+      // slower: 15.0 us against 13.4 us per launch on 2 GPUs.)
+      for (int q = 0; q < peer.world; ++q) *(volatile unsigned long long *)(peer.ll[q] + pbase + idx) = word;
     }
   };
   __shared__ double sh[RW][33];
@@ -1502,6 +1504,118 @@ __global__ void __launch_bounds__(256) fused_adam_kernel(AdamArgs a) {
       *a.ll_ticket = 0u;
       *a.ll_seq = *a.ll_seq + 1ULL;
     }
+  }
+}
+
+// The Adam kernel of the fused LL gradient exchange: thread i owns gradient entry i from the first poll to the parameter update.
+//   1. poll the `world` 8-byte {value, sequence} words of entry i (all loads in flight at once, re-polled until each carries this
+//      exchange's sequence number) and sum them in rank order -> g_i, identical on every rank
+//   2. ||g||^2: block sums of squares (double, fixed order) -> norm_slots[block]; the last block to arrive publishes the exchange's
+//      sequence number in `ready`, every block spins on it and adds the slots in block order (the CTAs of this small grid become
+//      co-resident as the concurrent minibatch kernel retires CTAs; they wait for nothing but each other)
+//   3. record / KL vote (block 0), Flux Adam on entry i, fragment scatter; block 0 closes the exchange (sequence number + 1)
+// against adam_body's LL path (every CTA polling the whole vector for the norm): 27.9 us -> see profiles/r1_notes.md.
+__global__ void __launch_bounds__(256) fused_adam_ll_kernel(AdamArgs a, double *__restrict__ norm_slots, unsigned int *__restrict__ ticket,
+                                                            unsigned long long *__restrict__ ready) {
+  if (stopped(a.ctl, a.mb)) return;
+  __shared__ double sh[8];
+  __shared__ double s_n2, s_c1, s_c2;
+  __shared__ float s_tail[16];   // [0..8) dlogΣ, [8..14) obj, kl, clip, adv, ret, count
+  const int tid = threadIdx.x;
+  const unsigned long long seq = *(volatile const unsigned long long *)a.ll_seq + 1ULL;   // the exchange the reduce kernels just sent
+  const unsigned int seq32 = (unsigned int)seq;
+  const unsigned long long *slot0 = a.ll_recv + (int64_t)(seq & 1ULL) * 16 * a.peer_cap;
+  auto poll = [&](int64_t idx) -> float {
+    float sum = 0.f;
+    for (int base = 0; base < a.world; base += 8) {
+      unsigned long long w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (base + u < a.world) w[u] = *(const volatile unsigned long long *)(slot0 + (int64_t)(base + u) * a.peer_cap + idx);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (base + u < a.world) {
+          while ((unsigned int)(w[u] >> 32) != seq32) w[u] = *(const volatile unsigned long long *)(slot0 + (int64_t)(base + u) * a.peer_cap + idx);
+          sum += __uint_as_float((unsigned int)w[u]);
+        }
+    }
+    return sum;
+  };
+  const int i = blockIdx.x * 256 + tid;
+  const int64_t off_ls = a.n, off_sums = (int64_t)a.n + 64;
+  const float gf = i < a.n ? poll(i) : 0.f;
+  double sq = (double)gf * (double)gf;
+  if (blockIdx.x == 0) {
+    if (tid < a.A) { const float g = poll(off_ls + tid); s_tail[tid] = g; sq += (double)g * (double)g; }
+    else if (tid >= 32 && tid < 38) s_tail[8 + tid - 32] = poll(off_sums + (tid - 32));
+  }
+  sq = warp_sum_d(sq);
+  if ((tid & 31) == 0) sh[tid >> 5] = sq;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int q = 0; q < 8; ++q) t += sh[q];
+    norm_slots[blockIdx.x] = t;
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
+      *ticket = 0u;
+      __threadfence();
+      *(volatile unsigned long long *)ready = seq;
+    }
+    while (*(volatile unsigned long long *)ready != seq) { }
+    __threadfence();
+    t = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(norm_slots + b);
+    s_n2 = t;
+    const int step = *a.step_dev;  // counts this step (incremented by the reduce kernel)
+    s_c1 = 1.0 - pow(a.b1, (double)step);
+    s_c2 = 1.0 - pow(a.b2, (double)step);
+  }
+  __syncthreads();
+  const double n2 = s_n2;
+  const bool bad = isnan(n2);
+  if (blockIdx.x == 0 && tid == 0) {
+    // every block has read the sequence number and all of its words (it published its slot afterwards): close the exchange
+    *(volatile unsigned long long *)a.ll_seq = seq;
+    const float cnt = s_tail[8 + 5];
+    if (a.head == 0) {
+      float sls = 0.f;
+      for (int j = 0; j < a.A; ++j) sls += a.ls[j];
+      const float entropy = 1.4189385332046727f + sls;          // policies.jl:348
+      const float p_loss = -(s_tail[8 + 0] / cnt);
+      a.rec[CRUX_PPO_LOSS] = a.lambda_p * p_loss + a.lambda_e * (-entropy);
+      a.rec[CRUX_PPO_ENTROPY] = entropy;
+      const float kl = s_tail[8 + 1] / cnt;
+      a.rec[CRUX_PPO_KL] = kl;
+      a.rec[CRUX_PPO_CLIP_FRAC] = a.a2c ? 0.f : s_tail[8 + 2] / cnt;
+      a.rec[CRUX_PPO_AVG_ADV] = s_tail[8 + 3] / cnt;
+      a.rec[CRUX_PPO_AVG_RET] = s_tail[8 + 4] / cnt;
+      if (a.ctl && kl > a.target_kl) a.ctl[1] = a.mb + 1;         // this minibatch is still applied; later ones are skipped
+    } else {
+      a.rec[CRUX_PPO_LOSS] = s_tail[8 + 0] / cnt;
+    }
+    a.rec[CRUX_PPO_GRAD_NORM] = (float)sqrt(n2);
+    a.rec[CRUX_PPO_VALID] = 1.f;
+    if (bad) atomicOr(a.err_flags, CRUX_FLAG_NAN);                // training.jl:20: error before Flux.update!
+  }
+  if (bad) return;
+  const double c1 = s_c1, c2 = s_c2;
+  if (i < a.n) {
+    a.g[i] = gf;   // keep the local gradient vector observable (crux_mlp_grads_ptr)
+    const double g = (double)gf;
+    const float mt = (float)(a.b1 * (double)a.m[i] + (1.0 - a.b1) * g);
+    const float vt = (float)(a.b2 * (double)a.v[i] + (1.0 - a.b2) * g * g);
+    a.m[i] = mt; a.v[i] = vt;
+    const float pn = a.p[i] - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
+    a.p[i] = pn;
+    if (a.frag) frag_scatter(a.frag, a.fI, a.fO, i, pn);
+  }
+  if (blockIdx.x == 0 && tid < a.A) {
+    const double g = (double)s_tail[tid];
+    const float mt = (float)(a.b1 * (double)a.ls_m[tid] + (1.0 - a.b1) * g);
+    const float vt = (float)(a.b2 * (double)a.ls_v[tid] + (1.0 - a.b2) * g * g);
+    a.ls_m[tid] = mt; a.ls_v[tid] = vt;
+    a.ls[tid] = a.ls[tid] - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
   }
 }
 
@@ -1768,7 +1882,12 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   if (!fuse_adam) {
     if (!use_peer) { rc = grads_allreduce(ctx, mlp->grads, mlp->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
     { CruxTimed timed(ctx, CRUX_T_ADAM);
-    fused_adam_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g); }
+    static const bool ll_old = getenv("CRUX_LL_ADAM_V1") != nullptr;   // A/B: every CTA polls the whole vector (adam_body)
+    if (use_peer && !ll_old)
+      fused_adam_ll_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g, mlp->norm_part, reinterpret_cast<unsigned int *>(ctx->peer_flags + 48 + head),
+                                                                       ctx->peer_flags + 56 + head);
+    else
+      fused_adam_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g); }
     CRUX_LAUNCHED(ctx);
   }
   return CRUX_OK;

@@ -398,6 +398,8 @@ int32_t crux_nccl_allreduce_f32(crux_ctx *ctx, float *buf, int64_t n); /* in-pla
 /* one-shot peer all-reduce over NVLink (CUDA IPC): exchange handles through the host. */
 int32_t crux_peer_handle(crux_ctx *ctx, uint8_t *handle_out_host /* 64 bytes */, int64_t max_floats);
 int32_t crux_peer_init(crux_ctx *ctx, int32_t rank, int32_t world, const uint8_t *handles_host /* world*64 */);
+/* back to NCCL for every exchange: call on ALL ranks when any rank's crux_peer_handle / crux_peer_init failed */
+int32_t crux_peer_disable(crux_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = crux.Context(local)
-    ctx.init_distributed(rank, world)   # NCCL only first; the peer buffers are mapped further down
+    ctx.init_distributed(rank, world, peer_floats=0)   # NCCL only first; the peer buffers are mapped further down
     dev = lambda x, dt=None: ctx.to_device(x, dt)
 
     def allreduce_check(tag, iters):
@@ -118,7 +118,6 @@ def main():
     assert np.allclose(t.cpu().numpy(), o.whiten(x)[rank::world], rtol=1e-4, atol=1e-5), "whiten"
 
     # ---- one-shot peer all-reduce over NVLink (CUDA IPC), many back-to-back calls (double-buffer race check)
-    ctx.init_distributed(rank, world, peer_floats=16384) if False else None
     hb = (C.c_uint8 * 64)()
     ctx.check(ctx.lib.crux_peer_handle(ctx.h, hb, 16384))
     handles = [None] * world
