@@ -387,7 +387,8 @@ int32_t crux_sac_train(crux_sac_state *st, const float *s, const float *a, const
   if (!st) return CRUX_ERR_INVALID;
   crux_ctx *ctx = st->ctx;
   CRUX_REQUIRE(ctx, B >= 1 && s && a && sp && r && done, "crux_sac_train: bad arguments");
-  CRUX_REQUIRE(ctx, ctx->world == 1 || true, "");
+  CRUX_REQUIRE(ctx, ctx->world == 1, "crux_sac_train: single rank only (the three optimisers' gradients and the temperature mean are not all-reduced; "
+                                     "run replicas with separate contexts instead)");
   crux_gaussian *pol = st->actor;
   crux_mlp *net = pol->mu;
   const int sdim = net->dims[0], A = pol->adim, ld = sdim + A, La = net->n_layers;
@@ -542,6 +543,7 @@ int32_t crux_ddpg_train(crux_ddpg_state *st, const float *s, const float *a, con
   if (!st) return CRUX_ERR_INVALID;
   crux_ctx *ctx = st->ctx;
   CRUX_REQUIRE(ctx, B >= 1 && s && a && sp && r && done, "crux_ddpg_train: bad arguments");
+  CRUX_REQUIRE(ctx, ctx->world == 1, "crux_ddpg_train: single rank only (gradients are not all-reduced; run replicas with separate contexts instead)");
   crux_mlp *act = st->actor;
   const int sdim = act->dims[0], La = act->n_layers, A = act->dims[La], ld = sdim + A;
   NoiseBounds nb;
