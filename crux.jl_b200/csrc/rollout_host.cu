@@ -128,11 +128,22 @@ extern "C" int32_t crux_rollout_host(crux_gaussian *actor, int64_t N, int32_t T,
       step(user, (int32_t)e0, (int32_t)e1, S.a, sp_t, r_t, done_t);                                    // @gen(:sp,:r), isterminal
       const double q2 = prof ? now() : 0;
       S.idx.clear();
-      for (int64_t e = e0; e < e1; ++e) {
-        const int32_t len = ++episode_length[e];                                                       // sampler.jl:130
-        const bool end = done_t[e] || len >= max_steps || force;
-        ee_t[e] = end ? 1 : 0;
-        if (end) { S.idx.push_back((int32_t)e); episode_length[e] = 0; }
+      {   // branch-free pass (vectorises); the index list of ended streams is only built when there is one
+        int32_t *len_p = episode_length + e0;
+        const uint8_t *dn_p = done_t + e0;
+        uint8_t *ee_p = ee_t + e0;
+        const int32_t ms = max_steps, f = force ? 1 : 0;
+        int any = 0;
+        for (int64_t q = 0; q < n; ++q) {
+          const int32_t len = len_p[q] + 1;                                                            // sampler.jl:130
+          const int32_t end = (dn_p[q] != 0) | (len >= ms) | f;
+          ee_p[q] = (uint8_t)end;
+          len_p[q] = end ? 0 : len;
+          any |= end;
+        }
+        if (any)
+          for (int64_t e = e0; e < e1; ++e)
+            if (ee_t[e]) S.idx.push_back((int32_t)e);
       }
       // next observation: sp, or a fresh initial state where the episode ended (terminate_episode! -> reset_sampler!).  With the
       // mapped forward the kernel picks sp / reset rows itself; obs_pinned is brought up to date once, after the last vector step
