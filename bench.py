@@ -312,7 +312,7 @@ def gae_roofline(crux, ctx, torch, hbm_peak, peak_src, T=2048, N=16384, reps=10)
             traffic = json.load(f).get("gae_tma_kernel")
     except Exception:
         pass
-    return {"kernel": "gae_tma_kernel (TMA-fed streaming scan; crux_fill_gae_returns for rollouts wider than 4096 streams)", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+    return {"kernel": "gae_tma_kernel (TMA-fed streaming scan; crux_fill_gae_returns for rollouts wider than 2048 streams)", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
             "traffic": traffic, "shape": [T, N], "bytes_per_launch": nbytes, "ms_per_launch": ms, "peak_source": peak_src}
 
 

@@ -20,8 +20,11 @@
 //   carry never leaves the registers; between segments it crosses global memory once per stream (value + release flag, acquired
 //   by the chain warp that starts the earlier segment).  An item is only waited on by items taken later from the counter, i.e.
 //   by CTAs that were resident after its owner: deadlock-free for any residency.
-//   The sequential chains are the critical resource (one chain warp per 64 streams): the path is used for rollouts wider than
-//   4096 streams (64-stream tiles up to 64 x SM-count streams, 128-stream tiles above); narrow ones stay on the time-parallel scan of gae.cu.
+//   The sequential chains are the critical resource (one chain warp per tile column group): the tile is as narrow as it can be while
+//   every tile still gets its own SM -- 32-stream tiles (one stream per chain lane) up to 32 x SM-count streams, 64-stream tiles up
+//   to 64 x SM-count, 128-stream tiles above.  The path is used for rollouts wider than 2048 streams and at least 64 steps long;
+//   narrower or shorter ones stay on the time-parallel scan of gae.cu (profiles/r1_gae_sweep.log: [1024,4096] 3.6 TB/s against
+//   2.65 for the scan, [2048,4096] 4.5 against 3.1, [2048,2560] 2.9 against 2.75).
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -102,12 +105,12 @@ struct StageMap {
   static_assert(BYTES % 128 == 0, "TMA boxes must stay 128-byte aligned");
 };
 
-template <int CS, int NCW>
+template <int CS, int NCW, int SPL>
 __global__ void __launch_bounds__(n_threads(NCW)) gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_vs,
                                                            const __grid_constant__ CUtensorMap tm_vsp, const __grid_constant__ CUtensorMap tm_dn,
                                                            const __grid_constant__ CUtensorMap tm_ee, const __grid_constant__ CUtensorMap tm_adv,
                                                            const __grid_constant__ CUtensorMap tm_ret, const TmaArgs a) {
-  constexpr int TS = 64 * NCW, W_PREP = W_CHAIN + NCW, W_STORE = W_PREP + NPW;
+  constexpr int TS = 32 * SPL * NCW, W_PREP = W_CHAIN + NCW, W_STORE = W_PREP + NPW;   // SPL = streams per chain lane (2, or 1 for 32-stream tiles)
   using SM = StageMap<CS, TS>;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], prep_bar[MAX_STAGES], chain_bar[MAX_STAGES], empty_bar[MAX_STAGES];
@@ -200,12 +203,12 @@ __global__ void __launch_bounds__(n_threads(NCW)) gae_tma_kernel(const __grid_co
   }
 
   if (w >= W_CHAIN && w < W_CHAIN + NCW) {
-    // ================================================================ chain warps: lane = streams 64*cw + 2*lane + {0, 1} of the tile
+    // ================================================================ chain warps: lane = streams (32*cw + lane) * SPL + {0, SPL-1} of the tile
     const int cw = w - W_CHAIN;
     const float gamma = a.gamma, cl = a.lambda * a.gamma;
     float A0 = 0.f, R0 = 0.f, A1 = 0.f, R1 = 0.f;
     bool bad = false;
-    const int col = 64 * cw + 2 * lane;
+    const int col = SPL * (32 * cw + lane);
     int s = 0; uint32_t ph = 0;
     for (;;) {
       mbar_wait(smem_u32(&prep_bar[s]), ph);
@@ -216,14 +219,6 @@ __global__ void __launch_bounds__(n_threads(NCW)) gae_tma_kernel(const __grid_co
       }
       const int tile = m.x, seg = m.z;
       unsigned char *st = smem + (size_t)s * SM::BYTES;
-      float2 *pr = reinterpret_cast<float2 *>(st + SM::R + col * 4);     // r     -> returns
-      float2 *pd = reinterpret_cast<float2 *>(st + SM::VS + col * 4);    // delta -> advantages
-      const uchar2 *pe = reinterpret_cast<const uchar2 *>(st + SM::EE + col);
-      // the whole stage into registers first (independent shared-memory loads), then the dependent FMA chain, then the stores
-      float2 r2[CS], d2[CS];
-      uchar2 e2[CS];
-#pragma unroll
-      for (int i = 0; i < CS; ++i) { r2[i] = pr[i * (TS / 2)]; d2[i] = pd[i * (TS / 2)]; e2[i] = pe[i * (TS / 2)]; }
       if (m.w & 1) {   // carry into the latest chunk of this segment: zero at the end of the rollout, else published by the later segment
         A0 = R0 = A1 = R1 = 0.f;
         if (seg + 1 < a.n_segs) {
@@ -234,19 +229,48 @@ __global__ void __launch_bounds__(n_threads(NCW)) gae_tma_kernel(const __grid_co
           A0 = cin.x; R0 = cin.y; A1 = cin.z; R1 = cin.w;
         }
       }
+      if constexpr (SPL == 2) {
+        float2 *pr = reinterpret_cast<float2 *>(st + SM::R + col * 4);     // r     -> returns
+        float2 *pd = reinterpret_cast<float2 *>(st + SM::VS + col * 4);    // delta -> advantages
+        const uchar2 *pe = reinterpret_cast<const uchar2 *>(st + SM::EE + col);
+        // the whole stage into registers first (independent shared-memory loads), then the dependent FMA chain, then the stores
+        float2 r2[CS], d2[CS];
+        uchar2 e2[CS];
 #pragma unroll
-      for (int i = CS - 1; i >= 0; --i) {
-        // an episode end cuts the trace: A = delta, R = r (select AFTER the FMA so that a NaN/Inf never crosses an episode boundary)
-        const float a0 = fmaf(cl, A0, d2[i].x), a1 = fmaf(cl, A1, d2[i].y);
-        const float q0 = fmaf(gamma, R0, r2[i].x), q1 = fmaf(gamma, R1, r2[i].y);
-        A0 = e2[i].x ? d2[i].x : a0; A1 = e2[i].y ? d2[i].y : a1;
-        R0 = e2[i].x ? r2[i].x : q0; R1 = e2[i].y ? r2[i].y : q1;
-        d2[i] = make_float2(A0, A1);
-        r2[i] = make_float2(R0, R1);
-        bad |= (A0 != A0) | (A1 != A1);
+        for (int i = 0; i < CS; ++i) { r2[i] = pr[i * (TS / 2)]; d2[i] = pd[i * (TS / 2)]; e2[i] = pe[i * (TS / 2)]; }
+#pragma unroll
+        for (int i = CS - 1; i >= 0; --i) {
+          // an episode end cuts the trace: A = delta, R = r (select AFTER the FMA so that a NaN/Inf never crosses an episode boundary)
+          const float a0 = fmaf(cl, A0, d2[i].x), a1 = fmaf(cl, A1, d2[i].y);
+          const float q0 = fmaf(gamma, R0, r2[i].x), q1 = fmaf(gamma, R1, r2[i].y);
+          A0 = e2[i].x ? d2[i].x : a0; A1 = e2[i].y ? d2[i].y : a1;
+          R0 = e2[i].x ? r2[i].x : q0; R1 = e2[i].y ? r2[i].y : q1;
+          d2[i] = make_float2(A0, A1);
+          r2[i] = make_float2(R0, R1);
+          bad |= (A0 != A0) | (A1 != A1);
+        }
+#pragma unroll
+        for (int i = 0; i < CS; ++i) { pd[i * (TS / 2)] = d2[i]; pr[i * (TS / 2)] = r2[i]; }
+      } else {   // one stream per lane: 32-stream tiles, twice as many sequential chains for a rollout of the same width
+        float *pr = reinterpret_cast<float *>(st + SM::R + col * 4);
+        float *pd = reinterpret_cast<float *>(st + SM::VS + col * 4);
+        const unsigned char *pe = st + SM::EE + col;
+        float r1[CS], d1[CS];
+        unsigned char e1[CS];
+#pragma unroll
+        for (int i = 0; i < CS; ++i) { r1[i] = pr[i * TS]; d1[i] = pd[i * TS]; e1[i] = pe[i * TS]; }
+#pragma unroll
+        for (int i = CS - 1; i >= 0; --i) {
+          const float a0 = fmaf(cl, A0, d1[i]);
+          const float q0 = fmaf(gamma, R0, r1[i]);
+          A0 = e1[i] ? d1[i] : a0;
+          R0 = e1[i] ? r1[i] : q0;
+          d1[i] = A0; r1[i] = R0;
+          bad |= (A0 != A0);
+        }
+#pragma unroll
+        for (int i = 0; i < CS; ++i) { pd[i * TS] = d1[i]; pr[i * TS] = r1[i]; }
       }
-#pragma unroll
-      for (int i = 0; i < CS; ++i) { pd[i * (TS / 2)] = d2[i]; pr[i * (TS / 2)] = r2[i]; }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the TMA store (async proxy) reads what this thread wrote
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&chain_bar[s]));
@@ -321,9 +345,9 @@ bool make_map(CUtensorMap *m, const void *base, bool is_u8, int64_t T, int64_t N
 }  // namespace
 
 // Returns CRUX_OK with *handled = 0 when the shape is not eligible (the register-resident scan of gae.cu runs instead).
-// Eligibility: T >= 64, N > 4096 and a multiple of 16 (TMA row pitch of the u8 columns), 16-byte aligned columns, TMA encode available.
+// Eligibility: T >= 64, N > 2048 and a multiple of 16 (TMA row pitch of the u8 columns), 16-byte aligned columns, TMA encode available.
 // CRUX_GAE=scan forces the gae.cu kernel, CRUX_GAE=tma forces this one for any eligible T >= 1;
-// CRUX_GAE_CFG="CS,STAGES,SEG_CHUNKS,CTAS_PER_SM,CHAIN_WARPS" overrides the tuning (0 = default; tests use it to exercise the
+// CRUX_GAE_CFG="CS,STAGES,SEG_CHUNKS,CTAS_PER_SM,CHAIN_WARPS,STREAMS_PER_LANE" overrides the tuning (0 = default; tests use it to exercise the
 // segment hand-off and both tile widths).
 int gae_tma_launch(crux_ctx *ctx, const float *r, const uint8_t *done, const uint8_t *ee, const float *vs, const float *vsp, int64_t T, int64_t N,
                    float gamma, float lambda, float *adv, float *ret, int *handled) {
@@ -331,10 +355,11 @@ int gae_tma_launch(crux_ctx *ctx, const float *r, const uint8_t *done, const uin
   const char *mode = getenv("CRUX_GAE");
   if (mode && !strcmp(mode, "scan")) return CRUX_OK;
   const bool forced = mode && !strcmp(mode, "tma");
-  // every tile is one sequential chain: 64-stream tiles (twice the chains) above N = 4096 while each tile gets its own SM, else 128;
-  // narrower or short rollouts stay on the time-parallel scan of gae.cu (measured cross-overs, profiles/r1_gae_sweep.log:
-  // [2048,8192] 5.4 TB/s with 64-stream tiles against 4.0 with 128 and 3.2 for the scan; [2048,4096] a tie at 3.0)
-  if (!forced && (T < 64 || N <= 4096)) return CRUX_OK;
+  // every tile is one sequential chain: the narrowest tile that still leaves one tile per SM (32, 64 or 128 streams); rollouts of at
+  // most 2048 streams or fewer than 64 steps stay on the time-parallel scan of gae.cu (measured cross-overs, profiles/r1_gae_sweep.log:
+  // [2048,8192] 5.4 TB/s with 64-stream tiles against 4.0 with 128 and 3.2 for the scan; [2048,4096] 4.5 with 32-stream tiles against
+  // 3.5 with 64 and 3.1 for the scan)
+  if (!forced && (T < 64 || N <= 2048)) return CRUX_OK;
   if (N % 16 != 0 || N >= ((int64_t)1 << 31) - 128 || T >= ((int64_t)1 << 31) - 64) return CRUX_OK;
   const uintptr_t al = (uintptr_t)r | (uintptr_t)done | (uintptr_t)ee | (uintptr_t)vs | (uintptr_t)vsp | (uintptr_t)adv | (uintptr_t)ret;
   if (al & 15) return CRUX_OK;
@@ -347,13 +372,18 @@ int gae_tma_launch(crux_ctx *ctx, const float *r, const uint8_t *done, const uin
   // measured best on B200 (profiles/r1_gae_sweep.log): 16-step stages, 4 stages loading + 2 draining per CTA, one CTA per SM;
   // with more tiles than SMs two smaller CTAs per SM so that every tile still is a single segment
   // 64-stream tiles while every tile still gets its own SM (N <= 64 x SMs = 9472 on B200), 128-stream tiles beyond
+  // ... and 32-stream tiles (one stream per chain lane) while even those all get their own SM (N <= 32 x SMs = 4736)
   int ncw = cdiv(N, 64) <= (int64_t)ctx->num_sms ? 1 : 2, cs = 0, stages = 0, seg_chunks = 0, per_sm = 0;
-  if (const char *cfg = getenv("CRUX_GAE_CFG")) sscanf(cfg, "%d,%d,%d,%d,%d", &cs, &stages, &seg_chunks, &per_sm, &ncw);
+  int spl = cdiv(N, 32) <= (int64_t)ctx->num_sms ? 1 : 2;
+  if (const char *cfg = getenv("CRUX_GAE_CFG")) sscanf(cfg, "%d,%d,%d,%d,%d,%d", &cs, &stages, &seg_chunks, &per_sm, &ncw, &spl);
   if (ncw != 1 && ncw != 2) ncw = 2;
-  const int TS = 64 * ncw;
+  if (spl != 1 && spl != 2) spl = 2;
+  if (spl == 1) ncw = 1;
+  const int TS = 32 * spl * ncw;
   const int tiles_ = (int)cdiv(N, TS);
-  if (cs != 16 && cs != 32) cs = ncw == 2 ? 16 : 32;                      // 28 KB stages either way
-  if (stages <= 0) stages = tiles_ > ctx->num_sms ? 4 : 6;
+  if (spl == 1) { if (cs != 32 && cs != 64) cs = 64; }                    // 28 KB stages at 64 steps
+  else if (cs != 16 && cs != 32) cs = ncw == 2 ? 16 : 32;                 // 28 KB stages either way
+  if (stages <= 0) stages = tiles_ > ctx->num_sms ? 4 : (spl == 1 ? 7 : 6);
   if (per_sm <= 0) per_sm = tiles_ > ctx->num_sms ? 2 : 1;
   if (stages < 3) stages = 3;   // the storer keeps two stages in flight
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -408,13 +438,14 @@ int gae_tma_launch(crux_ctx *ctx, const float *r, const uint8_t *done, const uin
   const int grid = (int)i64min(n_items64, (int64_t)G_max);
   {
     CruxTimed timed(ctx, CRUX_T_GAE);
-#define GAE_TMA_LAUNCH(CS_, NCW_)                                                                                                              \
+#define GAE_TMA_LAUNCH(CS_, NCW_, SPL_)                                                                                                        \
   do {                                                                                                                                         \
-    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(gae_tma_kernel<CS_, NCW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
-    gae_tma_kernel<CS_, NCW_><<<grid, n_threads(NCW_), smem, ctx->stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], a);                      \
+    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(gae_tma_kernel<CS_, NCW_, SPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    gae_tma_kernel<CS_, NCW_, SPL_><<<grid, n_threads(NCW_), smem, ctx->stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], a);                \
   } while (0)
-    if (ncw == 2) { if (cs == 16) GAE_TMA_LAUNCH(16, 2); else GAE_TMA_LAUNCH(32, 2); }
-    else          { if (cs == 16) GAE_TMA_LAUNCH(16, 1); else GAE_TMA_LAUNCH(32, 1); }
+    if (spl == 1)      { if (cs == 32) GAE_TMA_LAUNCH(32, 1, 1); else GAE_TMA_LAUNCH(64, 1, 1); }
+    else if (ncw == 2) { if (cs == 16) GAE_TMA_LAUNCH(16, 2, 2); else GAE_TMA_LAUNCH(32, 2, 2); }
+    else               { if (cs == 16) GAE_TMA_LAUNCH(16, 1, 2); else GAE_TMA_LAUNCH(32, 1, 2); }
 #undef GAE_TMA_LAUNCH
   }
   CRUX_LAUNCHED(ctx);

@@ -16,7 +16,10 @@ for T, N in shapes:
     adv, ret = torch.empty_like(r), torch.empty_like(r)
     run = lambda: ctx.check(ctx.lib.crux_fill_gae_returns(ctx.h, ptr(r), ptr(done), ptr(ee), ptr(vs), ptr(vsp), T, N, 0.99, 0.95, ptr(adv), ptr(ret)))
     cfgs = [("scan", None), ("tma", None), ("tma", "0,0,0,0,1"), ("tma", "0,0,0,0,2")]
-    if T >= 64:
+    if os.environ.get("SWEEP_SPL"):   # tile widths on narrow rollouts: 32-stream tiles (6th field 1) against 64-stream tiles and the scan
+        cfgs = [("scan", None), ("tma", None), ("tma", "0,0,0,0,1,2"), ("tma", "32,6,0,1,1,1"), ("tma", "32,8,0,1,1,1"), ("tma", "64,4,0,1,1,1"),
+                ("tma", "64,6,0,1,1,1"), ("tma", "64,7,0,1,1,1"), ("tma", "32,6,0,2,1,1"), ("tma", "64,3,0,2,1,1")]
+    elif T >= 64:
         for cs, st, seg, per in itertools.product((16, 32), (3, 4, 6, 7, 8), (0, 16), (1, 2)):
             if st * cs * 128 * 14 * per > 226 * 1024 or os.environ.get("SWEEP_DEFAULT_ONLY"):
                 continue

@@ -132,7 +132,10 @@ def gae_env(monkeypatch):
                                      (300, 4112, "32,2,1,1"), (1000, 1040, "32,4,3,2"), (1024, 4096, None), (2049, 160, "16,4,5,2"),
                                      (513, 16400, None),
                                      # 64-stream tiles (fifth field = chain warps) and explicit 128-stream tiles on a narrow rollout
-                                     (300, 4112, "32,3,1,1,1"), (257, 272, "16,3,2,2,1"), (1024, 4096, "16,6,0,1,2"), (700, 3088, "0,0,0,0,1")])
+                                     (300, 4112, "32,3,1,1,1,2"), (257, 272, "16,3,2,2,1,2"), (1024, 4096, "16,6,0,1,2,2"), (700, 3088, "0,0,0,0,1,2"),
+                                     # 32-stream tiles (sixth field = streams per chain lane; the default up to 32 x SM-count streams)
+                                     (300, 4112, "32,3,2,1,1,1"), (1000, 1040, "64,3,3,2,1,1"), (2049, 160, "32,4,5,2,1,1"), (1024, 4096, "0,0,0,0,0,1"),
+                                     (129, 4736, None)])
 def test_tma_path_against_oracle(ctx, gae_env, T, N, cfg):
     r, done, ee, vs, vsp = _inputs(T, N, seed=T * 7 + N)
     gae_env("tma", cfg)
@@ -143,7 +146,7 @@ def test_tma_path_against_oracle(ctx, gae_env, T, N, cfg):
     assert_close(adv, a0, rtol=1e-5, atol=2e-5, what=f"tma advantage [{T},{N}] cfg={cfg}")
     assert_close(ret, r0, rtol=1e-5, atol=2e-5, what=f"tma return [{T},{N}] cfg={cfg}")
     # the streaming scan IS the sequential recurrence: identical bits for every tiling / segmentation
-    gae_env("tma", "32,2,1,1,2")
+    gae_env("tma", "32,2,1,1,2,2")
     adv2, ret2 = _run(ctx, r, done, ee, vs, vsp, 0.99, 0.95)
     assert np.array_equal(adv, adv2) and np.array_equal(ret, ret2)
     # and within tolerance of the register-resident scan kernel
@@ -155,7 +158,7 @@ def test_tma_path_against_oracle(ctx, gae_env, T, N, cfg):
 def test_tma_path_single_output_nan_and_fallback(ctx, crux, gae_env):
     r, done, ee, vs, vsp = _inputs(200, 256, seed=3)
     a0, r0 = c_oracle.gae_returns(r, done, ee, vs, vsp, 0.9, 0.8)
-    gae_env("tma", "16,3,2,2")
+    gae_env("tma", "16,3,2,2,0,2")
     adv, _ = _run(ctx, r, done, ee, vs, vsp, 0.9, 0.8, want_ret=False)
     _, ret = _run(ctx, r, done, ee, vs, vsp, 0.9, 0.8, want_adv=False)
     assert_close(adv, a0, atol=2e-5); assert_close(ret, r0, atol=2e-5)
