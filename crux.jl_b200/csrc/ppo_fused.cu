@@ -2050,23 +2050,29 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
     // Gaussian head, one thread per (stream, action dimension): same noise counters and the same arithmetic per value as the
     // per-step kernel (which walks the dimensions sequentially in one thread); the logpdf terms are summed in that order below.
     float *lterm = spT;   // [8][LD16] scratch: s'^T is not written before the transition phase
-    if (t < 8 * R16) {
-      const int rr = t >> 3, j = t & 7;
+    if (t < 4 * R16) {   // lane (stream, action-dimension pair): one Philox block + one Box-Muller yield both normals of the pair
+      const int rr = t >> 2, j0 = 2 * (t & 3);
       const int64_t i = e0 + rr;   // absolute stream id == row index of the vector step
-      if (j < O) {
-        const float mu = OT[j * LD16 + rr];
-        const float ls = g.ls[j];
-        const float sigma = expf(ls);
-        const float var = sigma * sigma;
-        const Philox4 p = philox4x32_10(g.seed_pi, g.ctr0 + (uint64_t)step, (uint64_t)i * ((O + 3) / 4) + (j >> 2));
+      if (j0 < O) {
+        const Philox4 p = philox4x32_10(g.seed_pi, g.ctr0 + (uint64_t)step, (uint64_t)i * ((O + 3) / 4) + (j0 >> 2));
         float n0, n1;
-        if ((j & 2) == 0) box_muller(p.x, p.y, n0, n1); else box_muller(p.z, p.w, n0, n1);
-        const float ev = (j & 1) ? n1 : n0;
-        const float act = ev * sigma + mu;
-        aT[j * LD16 + rr] = act;
-        if (i < g.N) g.a[(row0 + rr) * O + j] = act;
-        const float dd = act - mu;
-        lterm[j * LD16 + rr] = -(dd * dd) / (2.f * var) - LOG_SQRT_2PI - ls;
+        if ((j0 & 2) == 0) box_muller(p.x, p.y, n0, n1); else box_muller(p.z, p.w, n0, n1);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = j0 + u;
+          if (j < O) {
+            const float mu = OT[j * LD16 + rr];
+            const float ls = g.ls[j];
+            const float sigma = expf(ls);
+            const float var = sigma * sigma;
+            const float ev = u ? n1 : n0;
+            const float act = ev * sigma + mu;
+            aT[j * LD16 + rr] = act;
+            if (i < g.N) g.a[(row0 + rr) * O + j] = act;
+            const float dd = act - mu;
+            lterm[j * LD16 + rr] = -(dd * dd) / (2.f * var) - LOG_SQRT_2PI - ls;
+          }
+        }
       }
     }
     __syncthreads();
@@ -2079,19 +2085,26 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
     }
     __syncthreads();
     const unsigned long long tick = tick0 + (unsigned long long)step;
+    {
+      // lane (r, d) owns the dimension PAIR (2d, 2d + 1): both normals come from one Box-Muller of one Philox block, so a stream costs
+      // ceil(sdim / 2) Philox + Box-Muller evaluations in ONE pass instead of sdim in two (same counters, same arithmetic per value)
+      const int k0 = 2 * d;
+      if (k0 < sdim) {
+        const Philox4 p = philox4x32_10(g.seed_env, tick, (uint64_t)(live ? e : 0) * 16 + (k0 >> 2));
+        float x0, x1;
+        if ((k0 & 2) == 0) box_muller(p.x, p.y, x0, x1); else box_muller(p.z, p.w, x0, x1);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int kk = d + 16 * h;
-      if (kk < sdim) {
-        const Philox4 p = philox4x32_10(g.seed_env, tick, (uint64_t)(live ? e : 0) * 16 + (kk >> 2));
-        float x0, x1;   // only the Box-Muller pair that holds this dimension's normal
-        if ((kk & 2) == 0) box_muller(p.x, p.y, x0, x1); else box_muller(p.z, p.w, x0, x1);
-        float v = 0.f;
-        for (int j = 0; j < sdim; ++j) v = fmaf(sA[kk * sdim + j], XT[j * LD16 + r], v);
-        for (int j = 0; j < adim; ++j) v = fmaf(sB[kk * adim + j], taT[j * LD16 + r], v);
-        v = fmaf(0.01f, (kk & 1) ? x1 : x0, v);
-        v = fminf(fmaxf(v, -10.f), 10.f);
-        spT[kk * LD16 + r] = v;
+        for (int u = 0; u < 2; ++u) {
+          const int kk = k0 + u;
+          if (kk < sdim) {
+            float v = 0.f;
+            for (int j = 0; j < sdim; ++j) v = fmaf(sA[kk * sdim + j], XT[j * LD16 + r], v);
+            for (int j = 0; j < adim; ++j) v = fmaf(sB[kk * adim + j], taT[j * LD16 + r], v);
+            v = fmaf(0.01f, u ? x1 : x0, v);
+            v = fminf(fmaxf(v, -10.f), 10.f);
+            spT[kk * LD16 + r] = v;
+          }
+        }
       }
     }
     // |s'|^2 in the exact order of linquad_step_kernel: 8 sequential 4-dim partials (one lane each: every dimension of a stream was
