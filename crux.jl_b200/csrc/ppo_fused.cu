@@ -2033,26 +2033,37 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
   if (t < R16) s_len[t] = e0 + t < g.N ? g.ep_len[e0 + t] : 0;
   __syncthreads();
 
+  // Every phase of a vector step uses the same mapping -- lane (r, d) = (t >> 4, t & 15): env stream r of the tile, slot d -- and only
+  // touches columns [*][r] of the shared-memory tiles, so a stream's whole step (forward, head, transition, bookkeeping) lives in
+  // ONE half-warp: the phases are ordered by __syncwarp() and the T-step loop needs no block barrier at all.  (It had eight per step,
+  // 21 % of the stall samples; removing them moved the launch from 255 to 253.5 us only: the warps wait on shared-memory loads of
+  // the two 64-wide layers and on the dependent FMA chains instead -- profiles/r1_notes.md.)  Arithmetic per value is unchanged.
   for (int step = 0; step < g.T; ++step) {
     const int64_t row0 = (int64_t)step * g.N + e0;
-    // s rows of this step
-    for (int q = t; q < R16 * sdim; q += NT) {
-      const int rr = q / sdim, i = q - rr * sdim;
-      if (e0 + rr < g.N) g.s[(row0 + rr) * sdim + i] = XT[i * LD16 + rr];
+    // s row of this step
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int kk = d + 16 * h;
+      if (kk < sdim && live) g.s[(row0 + r) * sdim + kk] = XT[kk * LD16 + r];
     }
-    // ---- policy forward + Gaussian head (identical to fused_forward_kernel<16>)
+    // ---- policy forward + Gaussian head (identical to fused_forward_kernel<16>): thread (r, jg) computes 4 outputs of stream r
     layer_fwd16(XT, I, P, P + off_b1(I), H1T, nd.act);
-    __syncthreads();
+    __syncwarp();
     layer_fwd16(H1T, H, P + off_W2(I), P + off_b2(I), H2T, nd.act);
-    __syncthreads();
-    layer_out16(H2T, P + off_W3(I), P + off_b3(I, O), O, OT);
-    __syncthreads();
-    // Gaussian head, one thread per (stream, action dimension): same noise counters and the same arithmetic per value as the
-    // per-step kernel (which walks the dimensions sequentially in one thread); the logpdf terms are summed in that order below.
-    float *lterm = spT;   // [8][LD16] scratch: s'^T is not written before the transition phase
-    if (t < 4 * R16) {   // lane (stream, action-dimension pair): one Philox block + one Box-Muller yield both normals of the pair
-      const int rr = t >> 2, j0 = 2 * (t & 3);
-      const int64_t i = e0 + rr;   // absolute stream id == row index of the vector step
+    __syncwarp();
+    if (d < O) {   // output layer: lane (r, o)
+      const float *W3 = P + off_W3(I);
+      float a0 = P[off_b3(I, O) + d];
+#pragma unroll 8
+      for (int k = 0; k < H; ++k) a0 = fmaf(H2T[k * LD16 + r], W3[k * O + d], a0);
+      OT[d * LD16 + r] = a0;
+    }
+    __syncwarp();
+    // Gaussian head, lane (stream, action-dimension pair): one Philox block + one Box-Muller yield both normals of the pair; same noise
+    // counters and the same arithmetic per value as the per-step kernel; the logpdf terms replace mu in OT and are summed in order below
+    {
+      const int j0 = 2 * d;
+      const int64_t i = e0 + r;   // absolute stream id == row index of the vector step
       if (j0 < O) {
         const Philox4 p = philox4x32_10(g.seed_pi, g.ctr0 + (uint64_t)step, (uint64_t)i * ((O + 3) / 4) + (j0 >> 2));
         float n0, n1;
@@ -2061,29 +2072,29 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
         for (int u = 0; u < 2; ++u) {
           const int j = j0 + u;
           if (j < O) {
-            const float mu = OT[j * LD16 + rr];
+            const float mu = OT[j * LD16 + r];
             const float ls = g.ls[j];
             const float sigma = expf(ls);
             const float var = sigma * sigma;
             const float ev = u ? n1 : n0;
             const float act = ev * sigma + mu;
-            aT[j * LD16 + rr] = act;
-            if (i < g.N) g.a[(row0 + rr) * O + j] = act;
+            aT[j * LD16 + r] = act;
+            if (live) g.a[(row0 + r) * O + j] = act;
             const float dd = act - mu;
-            lterm[j * LD16 + rr] = -(dd * dd) / (2.f * var) - LOG_SQRT_2PI - ls;
+            OT[j * LD16 + r] = -(dd * dd) / (2.f * var) - LOG_SQRT_2PI - ls;
           }
         }
       }
     }
-    __syncthreads();
+    __syncwarp();
     // ---- env transition (identical arithmetic to linquad_step_kernel)
     if (d < adim) taT[d * LD16 + r] = tanhf(aT[d * LD16 + r]);
-    if (t < R16 && g.logp) {
+    if (d == 15 && g.logp) {
       float logp = 0.f;
-      for (int j = 0; j < O; ++j) logp += lterm[j * LD16 + t];
-      if (e0 + t < g.N) g.logp[row0 + t] = logp;
+      for (int j = 0; j < O; ++j) logp += OT[j * LD16 + r];
+      if (live) g.logp[row0 + r] = logp;
     }
-    __syncthreads();
+    __syncwarp();
     const unsigned long long tick = tick0 + (unsigned long long)step;
     {
       // lane (r, d) owns the dimension PAIR (2d, 2d + 1): both normals come from one Box-Muller of one Philox block, so a stream costs
@@ -2098,8 +2109,11 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
           const int kk = k0 + u;
           if (kk < sdim) {
             float v = 0.f;
-            for (int j = 0; j < sdim; ++j) v = fmaf(sA[kk * sdim + j], XT[j * LD16 + r], v);
-            for (int j = 0; j < adim; ++j) v = fmaf(sB[kk * adim + j], taT[j * LD16 + r], v);
+            const float *ar = sA + kk * sdim, *br = sB + kk * adim;
+#pragma unroll 4
+            for (int j = 0; j < sdim; ++j) v = fmaf(ar[j], XT[j * LD16 + r], v);
+#pragma unroll 2
+            for (int j = 0; j < adim; ++j) v = fmaf(br[j], taT[j * LD16 + r], v);
             v = fmaf(0.01f, u ? x1 : x0, v);
             v = fminf(fmaxf(v, -10.f), 10.f);
             spT[kk * LD16 + r] = v;
@@ -2107,32 +2121,31 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
         }
       }
     }
-    // |s'|^2 in the exact order of linquad_step_kernel: 8 sequential 4-dim partials (one lane each: every dimension of a stream was
-    // written by this warp), combined below like the xor-1/2/4 butterfly.  tanh(a)^T is dead: it holds the partials.
+    // |s'|^2 in the exact order of linquad_step_kernel: 8 sequential 4-dim partials (one lane each), combined below like the
+    // xor-1/2/4 butterfly.  tanh(a)^T is dead: it holds the partials.
     __syncwarp();
     if (d < 8) {
       float n2 = 0.f;
       for (int i = 0; i < 4 && 4 * d + i < sdim; ++i) { const float v = spT[(4 * d + i) * LD16 + r]; n2 = fmaf(v, v, n2); }
       taT[d * LD16 + r] = n2;
     }
-    __syncthreads();
-    if (t < R16) {
-      const int rr = t;
+    __syncwarp();
+    if (d == 0) {   // reward, termination and episode bookkeeping of stream r
       float pq[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) pq[q] = taT[q * LD16 + rr];
+      for (int q = 0; q < 8; ++q) pq[q] = taT[q * LD16 + r];
       const float n2 = ((pq[0] + pq[1]) + (pq[2] + pq[3])) + ((pq[4] + pq[5]) + (pq[6] + pq[7]));
       float a2 = 0.f;
-      for (int j = 0; j < adim; ++j) { const float av = aT[j * LD16 + rr]; a2 = fmaf(av, av, a2); }
+      for (int j = 0; j < adim; ++j) { const float av = aT[j * LD16 + r]; a2 = fmaf(av, av, a2); }
       const float rew = 1.f - n2 / (float)sdim - 0.1f * a2 / (float)adim;
-      const bool dn = fabsf(spT[rr]) > 5.f;
-      const int len = s_len[rr] + 1;
+      const bool dn = fabsf(spT[r]) > 5.f;
+      const int len = s_len[r] + 1;
       const bool end = dn || len >= g.max_steps || (g.force_end && step == g.T - 1);
-      s_len[rr] = end ? 0 : len;
-      s_end[rr] = end ? 1 : 0;
-      if (e0 + rr < g.N) { g.r[row0 + rr] = rew; g.done[row0 + rr] = dn ? 1 : 0; g.ee[row0 + rr] = end ? 1 : 0; }
+      s_len[r] = end ? 0 : len;
+      s_end[r] = end ? 1 : 0;
+      if (live) { g.r[row0 + r] = rew; g.done[row0 + r] = dn ? 1 : 0; g.ee[row0 + r] = end ? 1 : 0; }
     }
-    __syncthreads();
+    __syncwarp();
     // ---- s' rows out; next observation tile: s', or a fresh initial state where the episode ended
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -2149,8 +2162,9 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
         XT[kk * LD16 + r] = nx;
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
+  __syncthreads();
   // current observation + episode lengths back to global
   for (int q = t; q < R16 * sdim; q += NT) {
     const int rr = q / sdim, i = q - rr * sdim;
