@@ -1993,6 +1993,7 @@ struct RolloutArgs {
   const float *ls;
   const float *A, *B;           // env matrices [sdim][sdim], [sdim][adim]
   int64_t N; int T, adim, max_steps, force_end;
+  int rows;                     // env streams per CTA (<= 16): chosen so that the CTAs spread evenly over 2 x SM-count slots
   uint64_t seed_pi, ctr0;       // exploration noise: (seed_pi, ctr0 + t, stream)
   uint64_t seed_env;            // env noise: (seed_env, tick0 + t, stream*16 + group)
   unsigned long long *tick_dev; // [0] tick, [1] finished-block counter
@@ -2020,17 +2021,18 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
   for (int i = t; i < sdim * adim; i += NT) sB[i] = g.B[i];
   const float *P = sm + M::P;
   float *XT = sm + M::XT, *H1T = sm + M::H1T, *H2T = sm + M::H2T, *OT = sm + M::OT;
-  const int64_t e0 = (int64_t)blockIdx.x * R16;
+  const int rows = g.rows;
+  const int64_t e0 = (int64_t)blockIdx.x * rows;
   const int r = t >> 4, d = t & 15;               // env row, dimension slot (dims d and d + 16)
   const int64_t e = e0 + r;
-  const bool live = e < g.N;
+  const bool live = r < rows && e < g.N;
   const unsigned long long tick0 = *(volatile unsigned long long *)g.tick_dev;
   // initial observation tile + episode lengths
   for (int q = t; q < R16 * sdim; q += NT) {
     const int rr = q / sdim, i = q - rr * sdim;
-    XT[i * LD16 + rr] = e0 + rr < g.N ? g.obs_io[(e0 + rr) * sdim + i] : 0.f;
+    XT[i * LD16 + rr] = (rr < rows && e0 + rr < g.N) ? g.obs_io[(e0 + rr) * sdim + i] : 0.f;
   }
-  if (t < R16) s_len[t] = e0 + t < g.N ? g.ep_len[e0 + t] : 0;
+  if (t < R16) s_len[t] = (t < rows && e0 + t < g.N) ? g.ep_len[e0 + t] : 0;
   __syncthreads();
 
   // Every phase of a vector step uses the same mapping -- lane (r, d) = (t >> 4, t & 15): env stream r of the tile, slot d -- and only
@@ -2038,7 +2040,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
   // ONE half-warp: the phases are ordered by __syncwarp() and the T-step loop needs no block barrier at all.  (It had eight per step,
   // 21 % of the stall samples; removing them moved the launch from 255 to 253.5 us only: the warps wait on shared-memory loads of
   // the two 64-wide layers and on the dependent FMA chains instead -- profiles/r1_notes.md.)  Arithmetic per value is unchanged.
-  for (int step = 0; step < g.T; ++step) {
+  const int n_steps = (t >> 5) * 2 < rows ? g.T : 0;   // a warp whose two streams are both beyond the tile's rows has nothing to do
+  for (int step = 0; step < n_steps; ++step) {
     const int64_t row0 = (int64_t)step * g.N + e0;
     // s row of this step
 #pragma unroll
@@ -2168,9 +2171,9 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
   // current observation + episode lengths back to global
   for (int q = t; q < R16 * sdim; q += NT) {
     const int rr = q / sdim, i = q - rr * sdim;
-    if (e0 + rr < g.N) g.obs_io[(e0 + rr) * sdim + i] = XT[i * LD16 + rr];
+    if (rr < rows && e0 + rr < g.N) g.obs_io[(e0 + rr) * sdim + i] = XT[i * LD16 + rr];
   }
-  if (t < R16 && e0 + t < g.N) g.ep_len[e0 + t] = s_len[t];
+  if (t < rows && e0 + t < g.N) g.ep_len[e0 + t] = s_len[t];
   // the last block to finish advances the env tick by T (every block has read it by then)
   __shared__ bool last;
   __threadfence();
@@ -2199,9 +2202,12 @@ extern "C" int32_t crux_linquad_rollout(crux_linquad *env, crux_gaussian *actor,
   g.max_steps = env->max_steps; g.force_end = force_end_last; g.seed_pi = seed; g.ctr0 = ctr0; g.seed_env = env->seed; g.tick_dev = env->tick;
   g.ep_len = env->ep_len; g.obs_io = obs_io; g.s = cols->s; g.a = cols->a; g.sp = cols->sp; g.r = cols->r; g.logp = cols->logprob;
   g.done = cols->done; g.ee = cols->episode_end;
+  // streams per CTA: 16 would give cdiv(N, 16) CTAs, e.g. 256 for 4096 streams = two CTAs on 108 SMs and one on 40; taking
+  // ceil(N / (2 x SMs)) streams (14 -> 293 CTAs) loads every SM alike (the idle half-warps of a tile cost nothing)
+  g.rows = (int)i64max(1, i64min(R16, cdiv(env->n_env, (int64_t)2 * ctx->num_sms)));
   {
     CruxTimed timed(ctx, CRUX_T_ENV);
-    rollout_linquad_kernel<<<(unsigned)cdiv(env->n_env, R16), NT, SmemMapT<R>::BYTES, ctx->stream>>>(g);
+    rollout_linquad_kernel<<<(unsigned)cdiv(env->n_env, g.rows), NT, SmemMapT<R>::BYTES, ctx->stream>>>(g);
   }
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;
