@@ -76,9 +76,10 @@ extern "C" int32_t crux_rollout_host(crux_gaussian *actor, int64_t N, int32_t T,
   // The host copies s' into the observation buffer the next forward reads (one memcpy per half step, ~0.2 ms per rollout).  Letting the
   // kernel read the s' rows where the env's worker threads left them (CRUX_ROLLOUT_DIRECT=1: staging rows + an episode_end flag per
   // row selecting the reset state) measured 30x SLOWER on the PCIe side (8.0 ms instead of 0.26 ms of event waits per 32-step
-  // rollout, scripts/e2e_ab.py).  Not root-caused: the rows are then read from a rotating 9 MB staging buffer (new pages for the
-  // I/O translation every step) whose lines were last written by 16 different cores, while the copy leaves 278 KB that one core
-  // wrote and the device reads again and again.
+  // rollout, scripts/e2e_ab.py).  A second experiment had the env write into a ONE-step pinned buffer reused every step (the kernel
+  // also stored the rows as the sp column, no upload): still 4.9 ms of waits.  So most of the cost is the device reading lines that
+  // were last written by the env's 16 worker cores (the rest: a rotating 9 MB buffer instead of 278 KB); the main thread's copy
+  // gathers them through one core first and the device then reads 278 KB that one core wrote.
   static const bool copy_obs = getenv("CRUX_ROLLOUT_DIRECT") == nullptr;
   auto enqueue_forward = [&](int g, int t) -> int {  // obs_g -> s[t]; policy forward; action back to the host; event
     const int64_t row = (int64_t)t * N + lo[g], n = hi[g] - lo[g];
