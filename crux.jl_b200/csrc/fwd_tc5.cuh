@@ -43,6 +43,11 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t da, uint64
                "l"(db), "r"(idesc), "r"(acc)
                : "memory");
 }
+__device__ __forceinline__ bool elect_one() {   // one lane of a converged warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void split(float x, float &hi, float &lo) {
   hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   lo = x - hi;
@@ -216,9 +221,10 @@ __global__ void __launch_bounds__(NT, 1) forward_kernel(Args a) {
     __syncthreads();
     if (tile + gridDim.x < n_tiles) issue_tile(tile + gridDim.x);   // the staging area has been consumed
     // ---------------- layer 1
-    if (t == 0) {
+    if (w == 0) {   // warp-uniform branch + elect.sync: under `if (t == 0)` nvcc wraps every MMA in an election loop (96 instead of 24-48 cycles each)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue_gemm(tmem + 0, sXA, TR * KX * 4, 32 * KX, sW1, 64 * KX * 4, 32 * KX, KX / 8, idesc64, bar_mma);
+      if (elect_one()) issue_gemm(tmem + 0, sXA, TR * KX * 4, 32 * KX, sW1, 64 * KX * 4, 32 * KX, KX / 8, idesc64, bar_mma);
+      __syncwarp();
     }
     mbar_wait(bar_mma, ph); ph ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -227,9 +233,10 @@ __global__ void __launch_bounds__(NT, 1) forward_kernel(Args a) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     // ---------------- layer 2
-    if (t == 0) {
+    if (w == 0) {   // warp-uniform branch + elect.sync: under `if (t == 0)` nvcc wraps every MMA in an election loop (96 instead of 24-48 cycles each)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue_gemm(tmem + 64, sHA, TR * 64 * 4, 32 * 64, sW2, 64 * 64 * 4, 32 * 64, 8, idesc64, bar_mma);
+      if (elect_one()) issue_gemm(tmem + 64, sHA, TR * 64 * 4, 32 * 64, sW2, 64 * 64 * 4, 32 * 64, 8, idesc64, bar_mma);
+      __syncwarp();
     }
     mbar_wait(bar_mma, ph); ph ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -238,9 +245,10 @@ __global__ void __launch_bounds__(NT, 1) forward_kernel(Args a) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     // ---------------- output layer
-    if (t == 0) {
+    if (w == 0) {   // warp-uniform branch + elect.sync: under `if (t == 0)` nvcc wraps every MMA in an election loop (96 instead of 24-48 cycles each)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue_gemm(tmem + 128, sHB, TR * 64 * 4, 32 * 64, sW3, NOUT * 64 * 4, 32 * 64, 8, idesc16, bar_mma);
+      if (elect_one()) issue_gemm(tmem + 128, sHB, TR * 64 * 4, 32 * 64, sW3, NOUT * 64 * 4, 32 * 64, 8, idesc16, bar_mma);
+      __syncwarp();
     }
     mbar_wait(bar_mma, ph); ph ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -457,9 +465,10 @@ __global__ void __launch_bounds__(NT, 2) forward_kernel_tmem(Args a) {
     __syncthreads();
     if (tile + gridDim.x < n_tiles) issue_tile(tile + gridDim.x);
     // ---------------- layer 1: C1 = x W1
-    if (t == 0) {
+    if (w == 0) {   // warp-uniform branch + elect.sync: under `if (t == 0)` nvcc wraps every MMA in an election loop (96 instead of 24-48 cycles each)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue_gemm_ts<KX / 8>(tmem + C1, tmem + XH, tmem + XL, sW1, 64 * KX * 4, 32 * KX, idesc64, bar_mma);
+      if (elect_one()) issue_gemm_ts<KX / 8>(tmem + C1, tmem + XH, tmem + XL, sW1, 64 * KX * 4, 32 * KX, idesc64, bar_mma);
+      __syncwarp();
     }
     mbar_wait(bar_mma, ph); ph ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -467,9 +476,10 @@ __global__ void __launch_bounds__(NT, 2) forward_kernel_tmem(Args a) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     // ---------------- layer 2: C3 = h1 W2
-    if (t == 0) {
+    if (w == 0) {   // warp-uniform branch + elect.sync: under `if (t == 0)` nvcc wraps every MMA in an election loop (96 instead of 24-48 cycles each)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue_gemm_ts<8>(tmem + C3, tmem + C1, tmem + C2, sW2, 64 * 64 * 4, 32 * 64, idesc64, bar_mma);
+      if (elect_one()) issue_gemm_ts<8>(tmem + C3, tmem + C1, tmem + C2, sW2, 64 * 64 * 4, 32 * 64, idesc64, bar_mma);
+      __syncwarp();
     }
     mbar_wait(bar_mma, ph); ph ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -477,9 +487,10 @@ __global__ void __launch_bounds__(NT, 2) forward_kernel_tmem(Args a) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     // ---------------- output layer: C1[0,16) = h2 W3
-    if (t == 0) {
+    if (w == 0) {   // warp-uniform branch + elect.sync: under `if (t == 0)` nvcc wraps every MMA in an election loop (96 instead of 24-48 cycles each)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue_gemm_ts<8>(tmem + C1, tmem + C3, tmem + C2, sW3, NOUT * 64 * 4, 32 * 64, idesc16, bar_mma);
+      if (elect_one()) issue_gemm_ts<8>(tmem + C1, tmem + C3, tmem + C2, sW3, NOUT * 64 * 4, 32 * 64, idesc16, bar_mma);
+      __syncwarp();
     }
     mbar_wait(bar_mma, ph); ph ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -205,9 +205,10 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
     }
     MB5_HANDOFF();
     // ---------------- layer 1
-    if (t == 0) {
+    if (w == 0) {   // warp-uniform branch + elect.sync: under `if (t == 0)` nvcc wraps every MMA in an election loop (96 instead of 24-48 cycles each)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tc5::issue_gemm_ts<KX / 8>(tmem + C1, tmem + XH, tmem + XL, sW1, 64 * KX * 4, 32 * KX, idesc64, bar_mma);
+      if (tc5::elect_one()) tc5::issue_gemm_ts<KX / 8>(tmem + C1, tmem + XH, tmem + XL, sW1, 64 * KX * 4, 32 * KX, idesc64, bar_mma);
+      __syncwarp();
     }
     MB5_WAIT_MMA();
     {
@@ -228,9 +229,10 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
     }
     MB5_HANDOFF();
     // ---------------- layer 2
-    if (t == 0) {
+    if (w == 0) {   // warp-uniform branch + elect.sync: under `if (t == 0)` nvcc wraps every MMA in an election loop (96 instead of 24-48 cycles each)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tc5::issue_gemm_ts<8>(tmem + C3, tmem + C1, tmem + C2, sW2F, 64 * 64 * 4, 32 * 64, idesc64, bar_mma);
+      if (tc5::elect_one()) tc5::issue_gemm_ts<8>(tmem + C3, tmem + C1, tmem + C2, sW2F, 64 * 64 * 4, 32 * 64, idesc64, bar_mma);
+      __syncwarp();
     }
     MB5_WAIT_MMA();
     {
@@ -251,9 +253,10 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
     }
     MB5_HANDOFF();
     // ---------------- output layer + loss head (thread = row, warps 0..3)
-    if (t == 0) {
+    if (w == 0) {   // warp-uniform branch + elect.sync: under `if (t == 0)` nvcc wraps every MMA in an election loop (96 instead of 24-48 cycles each)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tc5::issue_gemm_ts<8>(tmem + C1, tmem + C3, tmem + C2, sW3F, NOUT * 64 * 4, 32 * 64, idesc16, bar_mma);
+      if (tc5::elect_one()) tc5::issue_gemm_ts<8>(tmem + C1, tmem + C3, tmem + C2, sW3F, NOUT * 64 * 4, 32 * 64, idesc16, bar_mma);
+      __syncwarp();
     }
     MB5_WAIT_MMA();
     if (w < 4) {
@@ -346,9 +349,10 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
     }
     MB5_HANDOFF();
     // ---------------- dh1 = dz2 W2^T (tcgen05)   ||   dW2 += h1^T dz2, db2 (warp-level MMA)
-    if (t == 0) {
+    if (w == 0) {   // warp-uniform branch + elect.sync: under `if (t == 0)` nvcc wraps every MMA in an election loop (96 instead of 24-48 cycles each)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tc5::issue_gemm_ts<8>(tmem + C3, tmem + C1, tmem + C2, sW2B, 64 * 64 * 4, 32 * 64, idesc64, bar_mma);
+      if (tc5::elect_one()) tc5::issue_gemm_ts<8>(tmem + C3, tmem + C1, tmem + C2, sW2B, 64 * 64 * 4, 32 * 64, idesc64, bar_mma);
+      __syncwarp();
     }
     mma_wgrad<2, TR>(H1T, 16 * (w & 3), H2T, 16 * (w >> 2), acc2);
     if (t < 64) {

@@ -1151,6 +1151,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
 #include "fwd_tc5.cuh"
 
 #include "mb_tc5.cuh"
+#include "mb_t5.cuh"
 
 // =================================================================================================== tensor-core forward kernel
 // value(π, s) over a whole rollout column (the two critic passes that feed the GAE scan, policies.jl:94-98) on the building blocks of
@@ -1780,6 +1781,18 @@ extern "C" int32_t crux_rollout_step_rows_mapped(crux_gaussian *actor, const flo
   return launch_forward(ctx, a, 1);
 }
 
+// CRUX_MB_KERNEL selects the minibatch kernel: "t5" (default: all GEMMs on tcgen05, mb_t5.cuh), "mma" (warp-level mma.sync 3xTF32),
+// "tc5" (= CRUX_MB_TC5=1: row GEMMs on tcgen05, weight gradients on mma.sync), "ffma" (= CRUX_NO_MMA=1)
+static const char *mb_kernel_env() { const char *env = getenv("CRUX_MB_KERNEL"); return env ? env : ""; }   // read per call: tests switch kernels
+static bool no_mma() { return getenv("CRUX_NO_MMA") != nullptr || strcmp(mb_kernel_env(), "ffma") == 0; }
+static const char *mb5_selected() { return strcmp(mb_kernel_env(), "tc5") == 0 ? "1" : getenv("CRUX_MB_TC5"); }
+static bool minibatch_kernel_is_t5(const crux_mlp *mlp) {
+  const char *mb5_env = mb5_selected();
+  if (no_mma() || (mb5_env && mb5_env[0] == '1')) return false;
+  if (mb_kernel_env()[0] && strcmp(mb_kernel_env(), "t5") != 0) return false;
+  return mlp->dims[0] <= mb6::KX && mlp->dims[3] <= 8;
+}
+
 // one minibatch = 3 launches: fused forward/loss/backward -> partial reduction (+ step count) -> [all-reduce] -> norm/record/Adam
 static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const float *s, const float *act, const float *logp_old,
                            const float *adv, const float *ret, const int32_t *order, int64_t bm, const crux_ppo_hp *hp, float *rec,
@@ -1793,9 +1806,11 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   static const int reserve_env = getenv("CRUX_MB_RESERVE_SMS") ? atoi(getenv("CRUX_MB_RESERVE_SMS")) : 0;
   const int reserve = reserve_env > 0 ? reserve_env : 0;
   const int sms = (int)i64max(1, ctx->num_sms - reserve);
-  static const char *mb5_env0 = getenv("CRUX_MB_TC5");
-  const bool tc5_grid = !big && !getenv("CRUX_NO_MMA") && mb5_env0 && mb5_env0[0] == '1' && mlp->dims[0] <= mb5::KX && mlp->dims[3] <= 8;
+  const char *mb5_env0 = mb5_selected();
+  const bool tc5_grid = !big && !no_mma() && mb5_env0 && mb5_env0[0] == '1' && mlp->dims[0] <= mb5::KX && mlp->dims[3] <= 8;
+  const bool t5k = minibatch_kernel_is_t5(mlp) && !big;
   const int grid = big ? (int)i64min(cdiv(bm, RB), (int64_t)ctx->num_sms)
+                       : t5k ? (int)i64min(cdiv(bm, mb6::TRW), (int64_t)ctx->num_sms)
                        : tc5_grid ? (int)i64min(cdiv(bm, mb5::TR), (int64_t)ctx->num_sms) : (int)i64min(cdiv(bm, R), (int64_t)sms * 2);
   const int pstride = (int)((mlp->n_params + 16 + 31) / 32 * 32);
   const size_t need = (size_t)ctx->num_sms * 2 * pstride * sizeof(float);
@@ -1809,15 +1824,24 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   a.inv_bg = inv_bg; a.eps_clip = hp->eps_clip; a.lambda_p = hp->lambda_p; a.a2c = hp->a2c; a.partials = mlp->partials; a.pstride = pstride;
   a.n_params = (int)mlp->n_params; a.ctl = ctl; a.mb = mb;
   // CRUX_MB_TC5=1: row GEMMs on tcgen05 with the activations in tensor memory (mb_tc5.cuh), one 512-thread CTA per SM, 128-row tiles
-  static const char *mb5_env = getenv("CRUX_MB_TC5");
-  const bool tc5k = !big && !getenv("CRUX_NO_MMA") && mb5_env && mb5_env[0] == '1' && mlp->dims[0] <= mb5::KX && mlp->dims[3] <= 8;
-  const bool tc = !big && !tc5k && !getenv("CRUX_NO_MMA") && mlp->frag;   // mma.sync kernel: stages the fragment buffer instead of the raw parameters
+  const char *mb5_env = mb5_selected();
+  const bool tc5k = !big && !no_mma() && mb5_env && mb5_env[0] == '1' && mlp->dims[0] <= mb5::KX && mlp->dims[3] <= 8;
+  const bool tc = !big && !tc5k && !t5k && !no_mma() && mlp->frag;   // mma.sync kernel: stages the fragment buffer instead of the raw parameters
   if (tc) { a.net.params = mlp->frag; a.net.bytes16 = (uint32_t)(Frag::TOTAL * sizeof(float)); }
   {
   CruxTimed timed(ctx, CRUX_T_MINIBATCH);
   if (big) {
     if (head == 0) fused_minibatch_kernel<0, RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
     else fused_minibatch_kernel<1, RB><<<grid, NT, SmemMapT<RB>::BYTES, ctx->stream>>>(a);
+  } else if (t5k) {   // default: every GEMM on tcgen05, features on the TMEM lanes (mb_t5.cuh), one 256-thread CTA per SM, 64-row tiles
+    static bool attr6 = false;
+    if (!attr6) {
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(mb6::minibatch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb6::Map::TOTAL));
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(mb6::minibatch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb6::Map::TOTAL));
+      attr6 = true;
+    }
+    if (head == 0) mb6::minibatch_kernel<0><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
+    else mb6::minibatch_kernel<1><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
   } else if (tc5k) {
     static bool attr5 = false;
     if (!attr5) {
@@ -1917,7 +1941,7 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
   }
   fused_ctl_reset_kernel<<<1, 1, 0, ctx->stream>>>(actor->ctl);
   CRUX_LAUNCHED(ctx);
-  if (!getenv("CRUX_NO_MMA")) {   // weights in MMA B-fragment order for the tensor-core minibatch kernel (kept current by the fused Adam kernel)
+  if (!no_mma() && !minibatch_kernel_is_t5(mu)) {   // weights in MMA B-fragment order for the mma.sync minibatch kernel (kept current by the fused Adam kernel)
     crux_mlp *nets[2] = {mu, critic};
     for (crux_mlp *m : nets) {
       if (!m) continue;
