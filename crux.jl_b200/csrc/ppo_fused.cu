@@ -497,6 +497,8 @@ struct MbArgs {
   int n_params;
   const int *ctl;   // ctl[1] = 1 + index of the minibatch after which training stopped (0: not stopped); NULL: never skip
   int mb;           // index of this minibatch in the update
+  const float *planes;   // mb_t5.cuh: the network's weight planes (crux_mlp::frag in plane mode)
+  long long *prof;       // CRUX_MB6_PROF=1: clock64 at the phase boundaries of CTA 0 (development aid)
 };
 // a minibatch is skipped when an EARLIER minibatch raised the stop flag (rl/ppo.jl:59 via training.jl:46,49)
 __device__ __forceinline__ bool stopped(const int *ctl, int mb) { return ctl && ctl[1] != 0 && ctl[1] <= mb; }
@@ -1304,6 +1306,7 @@ struct AdamArgs {
   int *ctl; int mb;
   unsigned int *err_flags;
   float *frag; int fI, fO;                           // fragment buffer of the network (NULL: none) and its input / output widths
+  int frag_mode;                                     // 0: MMA B-fragment order (mma.sync kernel), 1: tcgen05 hi/lo weight planes (mb_t5.cuh)
 };
 __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int n_blocks);
 struct PeerOut {   // where the reduce kernel stores this rank's gradient for the fused all-reduce (enabled == 0: local only)
@@ -1484,7 +1487,7 @@ __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int
     a.m[i] = mt; a.v[i] = vt;
     const float pn = a.p[i] - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
     a.p[i] = pn;
-    if (a.frag) frag_scatter(a.frag, a.fI, a.fO, i, pn);   // the next minibatch kernel stages the weights in B-fragment order
+    if (a.frag) { if (a.frag_mode) mb6::plane_scatter(a.frag, a.fI, a.fO, i, pn); else frag_scatter(a.frag, a.fI, a.fO, i, pn); }   // what the next minibatch kernel stages
   }
   if (block_rank == 0 && threadIdx.x < a.A) {
     const int i = threadIdx.x;
@@ -1609,7 +1612,7 @@ __global__ void __launch_bounds__(256) fused_adam_ll_kernel(AdamArgs a, double *
     a.m[i] = mt; a.v[i] = vt;
     const float pn = a.p[i] - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
     a.p[i] = pn;
-    if (a.frag) frag_scatter(a.frag, a.fI, a.fO, i, pn);
+    if (a.frag) { if (a.frag_mode) mb6::plane_scatter(a.frag, a.fI, a.fO, i, pn); else frag_scatter(a.frag, a.fI, a.fO, i, pn); }
   }
   if (blockIdx.x == 0 && tid < a.A) {
     const double g = (double)s_tail[tid];
@@ -1828,6 +1831,7 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   const bool tc5k = !big && !no_mma() && mb5_env && mb5_env[0] == '1' && mlp->dims[0] <= mb5::KX && mlp->dims[3] <= 8;
   const bool tc = !big && !tc5k && !t5k && !no_mma() && mlp->frag;   // mma.sync kernel: stages the fragment buffer instead of the raw parameters
   if (tc) { a.net.params = mlp->frag; a.net.bytes16 = (uint32_t)(Frag::TOTAL * sizeof(float)); }
+  if (t5k) a.planes = mlp->frag;
   {
   CruxTimed timed(ctx, CRUX_T_MINIBATCH);
   if (big) {
@@ -1840,8 +1844,22 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
       CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(mb6::minibatch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb6::Map::TOTAL));
       attr6 = true;
     }
+    static long long *prof_dev = nullptr;
+    if (getenv("CRUX_MB6_PROF")) {
+      if (!prof_dev) CRUX_CHECK_CUDA(ctx, cudaMalloc(&prof_dev, 64 * sizeof(long long)));
+      CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(prof_dev, 0, 64 * sizeof(long long), ctx->stream));
+      a.prof = prof_dev;
+    }
     if (head == 0) mb6::minibatch_kernel<0><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
     else mb6::minibatch_kernel<1><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
+    if (a.prof) {
+      long long h[64];
+      CRUX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      CRUX_CHECK_CUDA(ctx, cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+      fprintf(stderr, "mb6 prof head=%d bm=%lld:", head, (long long)bm);
+      for (int k = 1; k < 64 && h[k]; ++k) fprintf(stderr, " %lld", h[k] - h[k - 1]);
+      fprintf(stderr, "\n");
+    }
   } else if (tc5k) {
     static bool attr5 = false;
     if (!attr5) {
@@ -1872,7 +1890,7 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   g.sums = tail_sums(mlp); g.eta = mlp->eta; g.b1 = mlp->beta1; g.b2 = mlp->beta2; g.eps = mlp->eps; g.step_dev = mlp->step_dev;
   g.lambda_p = hp->lambda_p; g.target_kl = hp->target_kl; g.a2c = hp->a2c; g.head = head; g.rec = rec; g.ctl = ctl; g.mb = mb;
   g.err_flags = ctx->flags_dev;
-  if (tc) { g.frag = mlp->frag; g.fI = mlp->dims[0]; g.fO = mlp->dims[3]; }
+  if (tc || t5k) { g.frag = mlp->frag; g.fI = mlp->dims[0]; g.fO = mlp->dims[3]; g.frag_mode = t5k ? 1 : 0; }
   // Running the Adam tail in the last CTA of the reduce kernel saves a launch but serialises 5.7k double-precision updates on
   // one SM: measured 20.5 us against 6.5 + 6.9 us for the two separate kernels (profiles/r1_notes.md) -> opt-in only.
   const int fuse_adam = (ctx->world == 1 && getenv("CRUX_FUSE_ADAM")) ? 1 : 0;
@@ -1941,12 +1959,20 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
   }
   fused_ctl_reset_kernel<<<1, 1, 0, ctx->stream>>>(actor->ctl);
   CRUX_LAUNCHED(ctx);
-  if (!no_mma() && !minibatch_kernel_is_t5(mu)) {   // weights in MMA B-fragment order for the mma.sync minibatch kernel (kept current by the fused Adam kernel)
+  if (!no_mma()) {   // weights in the order the minibatch kernel stages them with one TMA bulk copy (kept current by the fused Adam kernels):
+                     // tcgen05 hi/lo planes (mb_t5.cuh) or MMA B-fragment order (mma.sync kernel)
     crux_mlp *nets[2] = {mu, critic};
     for (crux_mlp *m : nets) {
       if (!m) continue;
-      rc = ppo_ensure_bytes(ctx, (void **)&m->frag, &m->frag_bytes, Frag::TOTAL * sizeof(float)); if (rc) return rc;
-      build_frag_kernel<<<(Frag::TOTAL + 255) / 256, 256, 0, ctx->stream>>>(m->params, m->frag, m->dims[0], m->dims[3]);
+      const bool t5 = minibatch_kernel_is_t5(m);
+      const size_t bytes = t5 ? (size_t)mb6::Map::PLANES : Frag::TOTAL * sizeof(float);
+      rc = ppo_ensure_bytes(ctx, (void **)&m->frag, &m->frag_bytes, bytes > Frag::TOTAL * sizeof(float) ? bytes : Frag::TOTAL * sizeof(float)); if (rc) return rc;
+      if (t5) {
+        CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(m->frag, 0, mb6::Map::PLANES, ctx->stream));
+        mb6::build_planes_kernel<<<((int)m->n_params + 255) / 256, 256, 0, ctx->stream>>>(m->params, m->frag, m->dims[0], m->dims[3], (int)m->n_params);
+      } else {
+        build_frag_kernel<<<(Frag::TOTAL + 255) / 256, 256, 0, ctx->stream>>>(m->params, m->frag, m->dims[0], m->dims[3]);
+      }
       CRUX_LAUNCHED(ctx);
     }
   }
