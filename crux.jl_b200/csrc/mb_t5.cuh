@@ -32,10 +32,11 @@
 
 namespace mb6 {
 
-constexpr int TRW = 64, NR = 32, KX = tc5::KX;
-// warp roles: 16 epilogue warps (TMEM quarter q, column group ch of 8 rows) | 1 MMA issuer | 2 loaders (gather + hi/lo split of the next tile)
-constexpr int NEW = 16, NLW = 2, NTE = NEW * 32, W_ISSUE = NEW, W_LOAD = NEW + 1, NTH = (NEW + 1 + NLW) * 32;
-constexpr int NB_READY = 1, NB_EPI = 2;   // named barriers: epilogue -> issuer hand-off (arrive / sync), epilogue-only sync
+constexpr int NR = 32, KX = tc5::KX;   // a tile = one 32-row atom
+// Two independent pipelines ("groups", g = 0 / 1) share a CTA and the weight planes; group g owns the TMEM data-path half dp = 16 g.
+// warps [0, 16): epilogue (8 per group: TMEM quarter q, column half ch) | 16, 17: MMA issuer of group 0 / 1 | 18, 19: loader of group 0 / 1
+constexpr int NEW = 8, NTE = NEW * 32, W_ISSUE = 2 * NEW, W_LOAD = 2 * NEW + 2, NTH = (2 * NEW + 4) * 32, NGT = (NEW + 2) * 32;
+constexpr int NB_READY = 1, NB_PRO = 3, NB_EPI = 5;   // named barriers (+ g): epilogue -> issuer hand-off, cooperative first load, epilogue-only
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t ZA = 0, H1L = 32, ZB = 64, H2L = 96, ZC = 128, ZD = 160, D1L = 192, OUTC = 224, DW2C = 256, DW1C = 320, DW3C = 352;
 constexpr int ACT_LBO = 144, ACT_SBO = 2320;   // padded K-major tile: the [row][feature] stores of a warp hit 32 distinct banks
@@ -47,30 +48,29 @@ struct Map {   // bytes; every operand is a pair of planes hi | lo
   static constexpr int W3B = W2TA + 2 * 64 * 64 * 4;             // B [8 o][64 k]    = W3(o,k)
   static constexpr int W3TA = W3B + 2 * 8 * 64 * 4;              // A [64 k][8 o]    = W3(o,k)
   static constexpr int PLANES = W3TA + 2 * 64 * 8 * 4;           // bytes of the weight planes = crux_mlp::frag in plane mode (one TMA bulk copy)
-  // input tile, DOUBLE-BUFFERED (the loader warps prepare tile n+1 while tile n runs): S hi|lo, S^T hi|lo
-  static constexpr int S = PLANES;                               // B [64 rows][24]
-  static constexpr int S_PLANE = TRW * KX * 4;
-  static constexpr int ST = S + 2 * S_PLANE;                     // B per atom [24 i][32 rows]; plane = 2 atoms x 3072
-  static constexpr int ST_ATOM = 3 * 1024, ST_PLANE = 2 * ST_ATOM;
-  static constexpr int IN_BUF = 2 * S_PLANE + 2 * ST_PLANE;      // bytes of one input buffer (S + S^T)
-  static constexpr int ACT = S + 2 * IN_BUF;                     // [64 rows][64] padded
-  static constexpr int ACT_PLANE = 8 * ACT_SBO;
-  static constexpr int DZT = ACT + 2 * ACT_PLANE;                // B per atom [64 o][32 rows]
-  static constexpr int DZT_ATOM = 8 * 1024, DZT_PLANE = 2 * DZT_ATOM;
-  static constexpr int DO = DZT + 2 * DZT_PLANE;                 // B [64 rows][8]
-  static constexpr int DO_PLANE = 8 * 256;
-  static constexpr int DOT = DO + 2 * DO_PLANE;                  // B per atom [8 o][32 rows]
-  static constexpr int DOT_ATOM = 1024, DOT_PLANE = 2 * DOT_ATOM;
-  static constexpr int SX = DOT + 2 * DOT_PLANE;                 // gather staging: x [64][I <= 24] (loader-private, single)
-  static constexpr int SA = SX + TRW * KX * 4;                   // head inputs, DOUBLE-BUFFERED: actions [64][O <= 8]
-  static constexpr int SH = SA + TRW * 8 * 4;                    //                 logprob | advantage | return [64] each
-  static constexpr int IDX = SH + 3 * TRW * 4;                   //                 [64] ints: source rows (-1: padding)
-  static constexpr int HEAD_BUF = TRW * 8 * 4 + 3 * TRW * 4 + TRW * 4;
-  static constexpr int BIAS = SA + 2 * HEAD_BUF;                 // b3[8] | logΣ[8] | 1/σ²[8]
-  static constexpr int RED = BIAS + 24 * 4;                      // [4 ch][64] db1 | [4 ch][64] db2 | [4][24] head scratch
-  static constexpr int BAR = RED + (4 * 64 * 2 + 4 * 24) * 4;
-  static constexpr int TOTAL = BAR + 64;   // bar_mma, bar_par, bar_g[2], bar_free[2], tmem slot
+  // per group g and buffer b (the loader prepares tile n+1 while tile n runs): S hi|lo [32 rows][24] (B of L1), S^T hi|lo [24][32 rows] (B of dW1)
+  static constexpr int S = PLANES;
+  static constexpr int S_PLANE = NR * KX * 4, ST_PLANE = 3 * 1024;
+  static constexpr int IN_BUF = 2 * S_PLANE + 2 * ST_PLANE;      // bytes of one input buffer; buffer (g, b) at S + (2 g + b) IN_BUF
+  static constexpr int ACT = S + 4 * IN_BUF;                     // per group [32 rows][64] padded, hi | lo (L3 reads 64 rows: the tail is don't-care)
+  static constexpr int ACT_PLANE = 4 * ACT_SBO, ACT_G = 2 * ACT_PLANE;
+  static constexpr int DZT = ACT + 2 * ACT_G;                    // per group B [64 o][32 rows] hi | lo   (L3's 64-row read of group 1's lo plane ends inside it)
+  static constexpr int DZT_PLANE = 8 * 1024, DZT_G = 2 * DZT_PLANE;
+  static constexpr int DO = DZT + 2 * DZT_G;                     // per group B [32 rows][8] hi | lo
+  static constexpr int DO_PLANE = 4 * 256, DO_G = 2 * DO_PLANE;
+  static constexpr int DOT = DO + 2 * DO_G;                      // per group B [8 o][32 rows] hi | lo
+  static constexpr int DOT_PLANE = 1024, DOT_G = 2 * DOT_PLANE;
+  static constexpr int SX = DOT + 2 * DOT_G;                     // per group gather staging: x [32][I <= 24] (loader-private)
+  static constexpr int SX_G = NR * KX * 4;
+  static constexpr int SA = SX + 2 * SX_G;                       // per (g, b) head inputs: actions [32][8] | logprob, advantage, return [32] each | rows [32] ints
+  static constexpr int HEAD_BUF = NR * 8 * 4 + 3 * NR * 4 + NR * 4;
+  static constexpr int BIAS = SA + 4 * HEAD_BUF;                 // b3[8] | logΣ[8] | 1/σ²[8]
+  static constexpr int RED = BIAS + 24 * 4;                      // per group: [2 ch][64] db1 | [2 ch][64] db2 | [2][24] head scratch
+  static constexpr int RED_G = (2 * 64 * 2 + 2 * 24) * 4;
+  static constexpr int BAR = RED + 2 * RED_G;                    // bar_par | per group: bar_mma, bar_g[2], bar_free[2] | tmem slot
+  static constexpr int TOTAL = BAR + 128;
   static_assert(ACT % 16 == 0 && DZT % 16 == 0 && DO % 16 == 0 && SX % 16 == 0 && BAR % 8 == 0, "alignment");
+  static_assert(TOTAL <= 232448, "shared memory");
 };
 
 __device__ __forceinline__ int canon(int row, int k, int K) { return (row >> 3) * (32 * K) + (k >> 2) * 128 + (row & 7) * 16 + (k & 3) * 4; }
@@ -151,37 +151,104 @@ __device__ __forceinline__ void commit(uint32_t bar) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])                                           \
                : "r"(taddr)                                                                                                                               \
                : "memory")
+// 16 data-path lanes x 256 bit, twice: thread t of the warp holds lanes t/4 (v0 v1 | v4 v5) and t/4 + 8 (v2 v3 | v6 v7), columns
+// 2 (t%4) + {0, 1} (v0..v3) and 8 + 2 (t%4) + {0, 1} (v4..v7) of the 16 lanes x 16 columns at taddr -- all 32 threads work on ONE atom
+#define MB6_LDX2(v, taddr)                                                                                                                               \
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                                                           \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])                                           \
+               : "r"(taddr)                                                                                                                               \
+               : "memory")
+#define MB6_STX2(taddr, v)                                                                                                                               \
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),   \
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])                                                                                               \
+               : "memory")
 #define MB6_WAIT_LD() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 #define MB6_WAIT_ST() asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory")
+// gather + hi/lo split of one 32-row tile of group g into input buffer b, by the `NL` threads lt = 0 .. NL-1 (sync() orders them)
+template <int HEAD, class Sync>
+__device__ __forceinline__ void load_tile(unsigned char *smb, const MbArgs &a, int I, int O, int g, int b, int64_t atile, int lt, int NL, Sync sync) {
+  float *SXp = reinterpret_cast<float *>(smb + Map::SX + g * Map::SX_G);
+  float *SAp = reinterpret_cast<float *>(smb + Map::SA + (2 * g + b) * Map::HEAD_BUF), *SHp = SAp + NR * 8;
+  int *sidx = reinterpret_cast<int *>(SHp + 3 * NR);
+  const uint32_t inv_I = (65536u + (uint32_t)I - 1u) / (uint32_t)I, inv_O = (65536u + (uint32_t)O - 1u) / (uint32_t)O;
+  for (int r = lt; r < NR; r += NL) {
+    const int64_t row = atile * NR + r;
+    sidx[r] = row < a.bm ? (a.order ? a.order[row] : (int)row) : -1;
+  }
+  sync();
+  for (int e = lt; e < NR * I; e += NL) {
+    const int r = (int)(((uint32_t)e * inv_I) >> 16), i = e - r * I;
+    const int row = sidx[r];
+    cp_async4(SXp + e, a.s + (row >= 0 ? (int64_t)row * I + i : 0), row >= 0);
+  }
+  if (HEAD == 0)
+    for (int e = lt; e < NR * O; e += NL) {
+      const int r = (int)(((uint32_t)e * inv_O) >> 16), o = e - r * O;
+      const int row = sidx[r];
+      cp_async4(SAp + e, a.act + (row >= 0 ? (int64_t)row * O + o : 0), row >= 0);
+    }
+  for (int r = lt; r < NR; r += NL) {
+    const int row = sidx[r];
+    if (HEAD == 0) {
+      cp_async4(SHp + r, a.logp_old + (row >= 0 ? row : 0), row >= 0);
+      cp_async4(SHp + NR + r, a.adv + (row >= 0 ? row : 0), row >= 0);
+    }
+    const bool has_ret = a.ret != nullptr;
+    cp_async4(SHp + 2 * NR + r, has_ret ? a.ret + (row >= 0 ? row : 0) : a.s, has_ret && row >= 0);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  sync();
+  unsigned char *Sb = smb + Map::S + (2 * g + b) * Map::IN_BUF, *STb = Sb + 2 * Map::S_PLANE;
+  for (int e = lt; e < NR * I; e += NL) {   // x -> S [row][24] (B of L1) and S^T [24][32 rows] (B of dW1), hi/lo
+    const int r = (int)(((uint32_t)e * inv_I) >> 16), i = e - r * I;
+    float hi, lo;
+    tc5::split(SXp[e], hi, lo);
+    const int o1 = canon(r, i, KX), o2 = canon(i, r, NR);
+    *reinterpret_cast<float *>(Sb + o1) = hi;
+    *reinterpret_cast<float *>(Sb + Map::S_PLANE + o1) = lo;
+    *reinterpret_cast<float *>(STb + o2) = hi;
+    *reinterpret_cast<float *>(STb + Map::ST_PLANE + o2) = lo;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 template <int HEAD>
 __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
   extern __shared__ __align__(1024) unsigned char smb[];
   const NetDesc nd = a.net;
   const int I = nd.I, O = nd.O, act = nd.act;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  // group of this warp and its index inside the group's 320 threads (epilogue 0..255 | issuer 256..287 | loader 288..319)
+  const int g = w < 2 * NEW ? w / NEW : (w - 2 * NEW) & 1;
+  const int gt = w < 2 * NEW ? t - g * NTE : (w < W_LOAD ? NTE + lane : NTE + 32 + lane);
   int prof_n = 0;
 #define MB6_STAMP() do { if (a.prof && blockIdx.x == 0 && t == 0 && prof_n < 64) a.prof[prof_n++] = clock64(); } while (0)
   MB6_STAMP();
   const int stop_at = a.ctl ? a.ctl[1] : 0;
-  const uint32_t bar_mma = smem_u32(smb + Map::BAR), bar_par = smem_u32(smb + Map::BAR + 8);
-  const uint32_t bar_g = smem_u32(smb + Map::BAR + 16), bar_free = smem_u32(smb + Map::BAR + 32);   // [2] each
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + Map::BAR + 48);
+  const uint32_t bar_par = smem_u32(smb + Map::BAR);
+  const uint32_t bar_mma = smem_u32(smb + Map::BAR + 8 + 40 * g), bar_g = bar_mma + 8, bar_free = bar_mma + 24;   // bar_g[2], bar_free[2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + Map::BAR + 96);
   float *bias = reinterpret_cast<float *>(smb + Map::BIAS);   // b3[8] | logΣ[8] | 1/σ²[8]
-  const int64_t n_tiles = (a.bm + TRW - 1) / TRW;
+  const int64_t n_tiles = (a.bm + NR - 1) / NR;
+  const int64_t tile0 = 2 * (int64_t)blockIdx.x + g, tstride = 2 * (int64_t)gridDim.x;   // this group's tiles: tile0, tile0 + tstride, ...
 
   // ---- prologue (all warps): barriers, weight planes (ONE TMA bulk copy), TMEM, zero the K padding of the input buffers
   if (t == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_mma), "r"(1) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_par), "r"(1) : "memory");
-    for (int b = 0; b < 2; ++b) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_g + 8 * b), "r"(NLW * 32) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_free + 8 * b), "r"(1) : "memory");
+    for (int gg = 0; gg < 2; ++gg) {
+      const uint32_t bm_ = smem_u32(smb + Map::BAR + 8 + 40 * gg);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bm_), "r"(1) : "memory");
+      for (int b = 0; b < 2; ++b) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bm_ + 8 + 8 * b), "r"(32) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bm_ + 24 + 8 * b), "r"(1) : "memory");
+      }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  for (int e = t; e < 2 * Map::IN_BUF / 4; e += NTH) reinterpret_cast<float *>(smb + Map::S)[e] = 0.f;   // K padding stays zero
-  for (int e = t; e < (2 * Map::DO_PLANE + 2 * Map::DOT_PLANE) / 4; e += NTH) reinterpret_cast<float *>(smb + Map::DO)[e] = 0.f;
+  for (int e = t; e < 4 * Map::IN_BUF / 4; e += NTH) reinterpret_cast<float *>(smb + Map::S)[e] = 0.f;   // K padding stays zero
+  for (int e = t; e < (2 * Map::DO_G + 2 * Map::DOT_G) / 4; e += NTH) reinterpret_cast<float *>(smb + Map::DO)[e] = 0.f;
   __syncthreads();
   if (t == 0) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_par), "r"((uint32_t)Map::PLANES) : "memory");
@@ -195,75 +262,38 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
   }
   if (t < 8) bias[t] = t < O ? __ldg(nd.params + off_b3(I, O) + t) : 0.f;
   if (HEAD == 0 && t >= 32 && t < 40) { const int j = t - 32; const float ls = j < O ? a.ls[j] : 0.f, sg = expf(ls); bias[8 + j] = ls; bias[16 + j] = 1.0f / (sg * sg); }
+  // the group's first tile is loaded by ALL of its 320 threads (the loader warp alone would put ~2 us in front of the first GEMM)
+  const bool skip = stop_at != 0 && stop_at <= a.mb;   // an EARLIER minibatch raised the KL stop flag (rl/ppo.jl:59): nothing to do
+  if (!skip && tile0 < n_tiles) {
+    load_tile<HEAD>(smb, a, I, O, g, 0, tile0, gt, NGT, [&]() { asm volatile("bar.sync %0, %1;" ::"r"(NB_PRO + g), "n"(NGT) : "memory"); });
+    asm volatile("bar.sync %0, %1;" ::"r"(NB_PRO + g), "n"(NGT) : "memory");
+    if (w >= W_LOAD) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_g) : "memory");   // buffer 0 of this group is ready
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  if (stop_at != 0 && stop_at <= a.mb) {   // an EARLIER minibatch raised the KL stop flag (rl/ppo.jl:59): nothing to do
+  if (skip) {
     tc5::mbar_wait(bar_par, 0);
     __syncthreads();
     if (w == W_ISSUE) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     return;
   }
   MB6_STAMP();   // end of the prologue
+  const uint32_t tm_g = tmem + ((uint32_t)(16 * g) << 16);   // this group's data-path half
 
   if (w >= W_LOAD) {
-    // =========================================================== LOADER warps: gather + hi/lo split of this CTA's tiles, one tile ahead
-    const int lt = t - W_LOAD * 32;                 // 0 .. NLW*32-1
-    constexpr int NL = NLW * 32;
-    float *SXp = reinterpret_cast<float *>(smb + Map::SX);
-    const uint32_t inv_I = (65536u + (uint32_t)I - 1u) / (uint32_t)I, inv_O = (65536u + (uint32_t)O - 1u) / (uint32_t)O;
-    int k = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+    // =========================================================== LOADER warp of group g: one tile ahead of the pipeline
+    int k = 1;
+    for (int64_t tile = tile0 + tstride; tile < n_tiles; tile += tstride, ++k) {
       const int b = k & 1;
       if (k >= 2) tc5::mbar_wait(bar_free + 8 * b, (uint32_t)(((k >> 1) - 1) & 1));   // dW1 of the tile that used this buffer has completed
-      float *SAp = reinterpret_cast<float *>(smb + Map::SA + b * Map::HEAD_BUF), *SHp = SAp + TRW * 8;
-      int *sidx = reinterpret_cast<int *>(SHp + 3 * TRW);
-      for (int r = lt; r < TRW; r += NL) {
-        const int64_t row = tile * TRW + r;
-        sidx[r] = row < a.bm ? (a.order ? a.order[row] : (int)row) : -1;
-      }
-      asm volatile("bar.sync %0, %1;" ::"n"(3), "n"(NL) : "memory");   // sidx complete (loader warps only)
-      for (int e = lt; e < TRW * I; e += NL) {
-        const int r = (int)(((uint32_t)e * inv_I) >> 16), i = e - r * I;
-        const int row = sidx[r];
-        cp_async4(SXp + e, a.s + (row >= 0 ? (int64_t)row * I + i : 0), row >= 0);
-      }
-      if (HEAD == 0)
-        for (int e = lt; e < TRW * O; e += NL) {
-          const int r = (int)(((uint32_t)e * inv_O) >> 16), o = e - r * O;
-          const int row = sidx[r];
-          cp_async4(SAp + e, a.act + (row >= 0 ? (int64_t)row * O + o : 0), row >= 0);
-        }
-      for (int r = lt; r < TRW; r += NL) {
-        const int row = sidx[r];
-        if (HEAD == 0) {
-          cp_async4(SHp + r, a.logp_old + (row >= 0 ? row : 0), row >= 0);
-          cp_async4(SHp + TRW + r, a.adv + (row >= 0 ? row : 0), row >= 0);
-        }
-        const bool has_ret = a.ret != nullptr;
-        cp_async4(SHp + 2 * TRW + r, has_ret ? a.ret + (row >= 0 ? row : 0) : a.s, has_ret && row >= 0);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      asm volatile("bar.sync %0, %1;" ::"n"(3), "n"(NL) : "memory");   // every loader thread's rows have landed
-      unsigned char *Sb = smb + Map::S + b * Map::IN_BUF, *STb = Sb + 2 * Map::S_PLANE;
-      for (int e = lt; e < TRW * I; e += NL) {   // x -> S [row][24] (B of L1) and S^T [atom][24][32 rows] (B of dW1), hi/lo
-        const int r = (int)(((uint32_t)e * inv_I) >> 16), i = e - r * I;
-        float hi, lo;
-        tc5::split(SXp[e], hi, lo);
-        const int o1 = canon(r, i, KX), o2 = (r >> 5) * Map::ST_ATOM + canon(i, r & 31, NR);
-        *reinterpret_cast<float *>(Sb + o1) = hi;
-        *reinterpret_cast<float *>(Sb + Map::S_PLANE + o1) = lo;
-        *reinterpret_cast<float *>(STb + o2) = hi;
-        *reinterpret_cast<float *>(STb + Map::ST_PLANE + o2) = lo;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      load_tile<HEAD>(smb, a, I, O, g, b, tile, lane, 32, [&]() { __syncwarp(); });
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_g + 8 * b) : "memory");
     }
-  } else if (w == W_ISSUE) {
-    // =========================================================== MMA ISSUER warp (one elected lane issues; the warp stays converged)
+  } else if (w >= W_ISSUE) {
+    // =========================================================== MMA ISSUER warp of group g (one elected lane issues; the warp stays converged)
     tc5::mbar_wait(bar_par, 0);   // weight planes have landed
     const uint32_t sb = smem_u32(smb);
     const uint64_t dW1A = tc5::make_desc(sb + Map::W1A, 128, 32 * KX), dW1A_lo = tc5::make_desc(sb + Map::W1A + 64 * KX * 4, 128, 32 * KX);
@@ -271,94 +301,78 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
     const uint64_t dW2TA = tc5::make_desc(sb + Map::W2TA, 128, 32 * 64), dW2TA_lo = tc5::make_desc(sb + Map::W2TA + 64 * 64 * 4, 128, 32 * 64);
     const uint64_t dW3B = tc5::make_desc(sb + Map::W3B, 128, 32 * 64), dW3B_lo = tc5::make_desc(sb + Map::W3B + 8 * 64 * 4, 128, 32 * 64);
     const uint64_t dW3TA = tc5::make_desc(sb + Map::W3TA, 128, 32 * 8), dW3TA_lo = tc5::make_desc(sb + Map::W3TA + 64 * 8 * 4, 128, 32 * 8);
-    const uint64_t dACT = tc5::make_desc(sb + Map::ACT, ACT_LBO, ACT_SBO), dACT_lo = tc5::make_desc(sb + Map::ACT + Map::ACT_PLANE, ACT_LBO, ACT_SBO);
-    const uint64_t dDZT = tc5::make_desc(sb + Map::DZT, 128, 32 * NR), dDZT_lo = tc5::make_desc(sb + Map::DZT + Map::DZT_PLANE, 128, 32 * NR);
-    const uint64_t dDO = tc5::make_desc(sb + Map::DO, 128, 32 * 8), dDO_lo = tc5::make_desc(sb + Map::DO + Map::DO_PLANE, 128, 32 * 8);
-    const uint64_t dDOT = tc5::make_desc(sb + Map::DOT, 128, 32 * NR), dDOT_lo = tc5::make_desc(sb + Map::DOT + Map::DOT_PLANE, 128, 32 * NR);
+    const uint64_t dACT = tc5::make_desc(sb + Map::ACT + g * Map::ACT_G, ACT_LBO, ACT_SBO), dACT_lo = dACT + (uint64_t)(Map::ACT_PLANE >> 4);
+    const uint64_t dDZT = tc5::make_desc(sb + Map::DZT + g * Map::DZT_G, 128, 32 * NR), dDZT_lo = dDZT + (uint64_t)(Map::DZT_PLANE >> 4);
+    const uint64_t dDO = tc5::make_desc(sb + Map::DO + g * Map::DO_G, 128, 32 * 8), dDO_lo = dDO + (uint64_t)(Map::DO_PLANE >> 4);
+    const uint64_t dDOT = tc5::make_desc(sb + Map::DOT + g * Map::DOT_G, 128, 32 * NR), dDOT_lo = dDOT + (uint64_t)(Map::DOT_PLANE >> 4);
     constexpr uint32_t ADV = 16, ADV_ACT = (2 * ACT_LBO) >> 4;           // one k-step = two core matrices along K
-    constexpr uint32_t S_ATOM = (4 * 32 * KX) >> 4, ACT_ATOM = (4 * ACT_SBO) >> 4, DO_ATOM = (4 * 32 * 8) >> 4;   // rows 32.. of a [64 rows][K] tile
     const uint32_t id32 = tc5::make_idesc(64, 32), id8 = tc5::make_idesc(64, 8), id64 = tc5::make_idesc(64, 64), id24 = tc5::make_idesc(64, 24);
-    uint32_t first = 0;   // 0 on this CTA's first tile: the dW accumulators are overwritten, then accumulated
+    uint32_t first = 0;   // 0 on this group's first tile: the dW accumulators are overwritten, then accumulated
     int k = 0;
 #define MB6_WAIT_READY()                                                       \
-    asm volatile("bar.sync %0, %1;" ::"n"(NB_READY), "n"(NTE + 32) : "memory");  \
+    asm volatile("bar.sync %0, %1;" ::"r"(NB_READY + g), "n"(NTE + 32) : "memory");  \
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory")
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+    for (int64_t tile = tile0; tile < n_tiles; tile += tstride, ++k) {
       const int b = k & 1;
-      const uint64_t dS = tc5::make_desc(sb + Map::S + b * Map::IN_BUF, 128, 32 * KX), dS_lo = dS + (uint64_t)(Map::S_PLANE >> 4);
-      const uint64_t dST = tc5::make_desc(sb + Map::S + b * Map::IN_BUF + 2 * Map::S_PLANE, 128, 32 * NR), dST_lo = dST + (uint64_t)(Map::ST_PLANE >> 4);
-      tc5::mbar_wait(bar_g + 8 * b, (uint32_t)((k >> 1) & 1));   // the loaders have prepared S / S^T of this tile
+      const uint64_t dS = tc5::make_desc(sb + Map::S + (2 * g + b) * Map::IN_BUF, 128, 32 * KX), dS_lo = dS + (uint64_t)(Map::S_PLANE >> 4);
+      const uint64_t dST = tc5::make_desc(sb + Map::S + (2 * g + b) * Map::IN_BUF + 2 * Map::S_PLANE, 128, 32 * NR), dST_lo = dST + (uint64_t)(Map::ST_PLANE >> 4);
+      tc5::mbar_wait(bar_g + 8 * b, (uint32_t)((k >> 1) & 1));   // S / S^T of this tile are ready
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (elect_one()) {   // L1: ZA[atom] = W1 S^T
-#pragma unroll
-        for (uint32_t at = 0; at < 2; ++at)
-          gemm_ss<KX / 8>(tmem + ((16u * at) << 16) + ZA, dW1A, dW1A_lo, ADV, dS + at * S_ATOM, dS_lo + at * S_ATOM, ADV, id32, 0u);
+      if (elect_one()) {   // L1: ZA = W1 S^T
+        gemm_ss<KX / 8>(tm_g + ZA, dW1A, dW1A_lo, ADV, dS, dS_lo, ADV, id32, 0u);
         commit(bar_mma);
       }
       __syncwarp();
       MB6_WAIT_READY();    // E1 done
-      if (elect_one()) {   // L2: ZB[atom] = W2 h1
-#pragma unroll
-        for (uint32_t at = 0; at < 2; ++at)
-          gemm_ss<8>(tmem + ((16u * at) << 16) + ZB, dW2A, dW2A_lo, ADV, dACT + at * ACT_ATOM, dACT_lo + at * ACT_ATOM, ADV_ACT, id32, 0u);
+      if (elect_one()) {   // L2: ZB = W2 h1
+        gemm_ss<8>(tm_g + ZB, dW2A, dW2A_lo, ADV, dACT, dACT_lo, ADV_ACT, id32, 0u);
         commit(bar_mma);
       }
       __syncwarp();
       MB6_WAIT_READY();    // E2 done
-      if (elect_one()) {   // L3 (rows on the lanes): OUT[64 rows][8] = h2 W3^T
-        gemm_ss<8>(tmem + OUTC, dACT, dACT_lo, ADV_ACT, dW3B, dW3B_lo, ADV, id8, 0u);
+      if (elect_one()) {   // L3 (rows on the lanes, M = 64: rows 32.. of the A operand are don't-care): OUT[rows][8] = h2 W3^T
+        gemm_ss<8>(tm_g + OUTC, dACT, dACT_lo, ADV_ACT, dW3B, dW3B_lo, ADV, id8, 0u);
         commit(bar_mma);
       }
       __syncwarp();
       MB6_WAIT_READY();    // head done
-      if (elect_one()) {   // G4: ZC[atom] = W3^T dOut^T, then (under E3) dW3^T[atom] += h2^T dOut
-#pragma unroll
-        for (uint32_t at = 0; at < 2; ++at)
-          gemm_ss<1>(tmem + ((16u * at) << 16) + ZC, dW3TA, dW3TA_lo, ADV, dDO + at * DO_ATOM, dDO_lo + at * DO_ATOM, ADV, id32, 0u);
+      if (elect_one()) {   // G4: ZC = W3^T dOut^T, then (under E3) dW3^T += h2^T dOut
+        gemm_ss<1>(tm_g + ZC, dW3TA, dW3TA_lo, ADV, dDO, dDO_lo, ADV, id32, 0u);
         commit(bar_mma);
-#pragma unroll
-        for (uint32_t at = 0; at < 2; ++at) {
-          const uint32_t dp = tmem + ((16u * at) << 16);
-          gemm_ts<NR / 8>(dp + DW3C, dp + ZB, dp + H2L, dDOT + at * (Map::DOT_ATOM >> 4), dDOT_lo + at * (Map::DOT_ATOM >> 4), ADV, id8, first);
-        }
+        gemm_ts<NR / 8>(tm_g + DW3C, tm_g + ZB, tm_g + H2L, dDOT, dDOT_lo, ADV, id8, first);
       }
       __syncwarp();
       MB6_WAIT_READY();    // E3 done
-      if (elect_one()) {   // G5: ZD[atom] = W2^T dz2, then (under E4) dW2^T[atom] += h1^T dz2
-#pragma unroll
-        for (uint32_t at = 0; at < 2; ++at)
-          gemm_ss<8>(tmem + ((16u * at) << 16) + ZD, dW2TA, dW2TA_lo, ADV, dACT + at * ACT_ATOM, dACT_lo + at * ACT_ATOM, ADV_ACT, id32, 0u);
+      if (elect_one()) {   // G5: ZD = W2^T dz2, then (under E4) dW2^T += h1^T dz2
+        gemm_ss<8>(tm_g + ZD, dW2TA, dW2TA_lo, ADV, dACT, dACT_lo, ADV_ACT, id32, 0u);
         commit(bar_mma);
-#pragma unroll
-        for (uint32_t at = 0; at < 2; ++at) {
-          const uint32_t dp = tmem + ((16u * at) << 16);
-          gemm_ts<NR / 8>(dp + DW2C, dp + ZA, dp + H1L, dDZT + at * (Map::DZT_ATOM >> 4), dDZT_lo + at * (Map::DZT_ATOM >> 4), ADV, id64, first);
-        }
+        gemm_ts<NR / 8>(tm_g + DW2C, tm_g + ZA, tm_g + H1L, dDZT, dDZT_lo, ADV, id64, first);
       }
       __syncwarp();
       MB6_WAIT_READY();    // E4 done
-      if (elect_one()) {   // G6: dW1[atom] += dz1^T S; its completion frees this tile's input buffer for the loaders
-#pragma unroll
-        for (uint32_t at = 0; at < 2; ++at) {
-          const uint32_t dp = tmem + ((16u * at) << 16);
-          gemm_ts<NR / 8>(dp + DW1C, dp + ZD, dp + D1L, dST + at * (Map::ST_ATOM >> 4), dST_lo + at * (Map::ST_ATOM >> 4), ADV, id24, first);
-        }
+      if (elect_one()) {   // G6: dW1 += dz1^T S; its completion frees this tile's input buffer for the loader
+        gemm_ts<NR / 8>(tm_g + DW1C, tm_g + ZD, tm_g + D1L, dST, dST_lo, ADV, id24, first);
         commit(bar_free + 8 * b);
       }
       __syncwarp();
       first = 1u;
     }
-    if (elect_one()) commit(bar_mma);   // every weight-gradient MMA has completed: the epilogue warps read the accumulators
+    if (elect_one()) commit(bar_mma);   // every weight-gradient MMA of this group has completed: its epilogue warps read the accumulators
     __syncwarp();
 #undef MB6_WAIT_READY
   } else {
-    // =========================================================== EPILOGUE warps
-    const int q = w & 3, ch = w >> 2, atom = lane >> 4, f = 16 * q + (lane & 15);   // owner of feature f, atom rows [8ch, 8ch + 8)
-    const float b1f = __ldg(nd.params + off_b1(I) + f), b2f = __ldg(nd.params + off_b2(I) + f);
-    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-    const uint32_t c0 = 8 * ch;                     // this thread's columns (rows of its atom) inside a 32-column block
+    // =========================================================== EPILOGUE warps of group g
+    // warp (q, ch) owns TMEM lanes [32q + 16g, +16) x columns [16ch, +16); thread: features fa, fa + 8, rows c0 + 8 rep + rr + {0, 1}
+    const int we = w - g * NEW, q = we & 3, ch = we >> 2;
+    const int fa = 16 * q + (lane >> 2), rr = 2 * (lane & 3), c0 = 16 * ch;
+    const float b1a = __ldg(nd.params + off_b1(I) + fa), b1b = __ldg(nd.params + off_b1(I) + fa + 8);
+    const float b2a = __ldg(nd.params + off_b2(I) + fa), b2b = __ldg(nd.params + off_b2(I) + fa + 8);
+    const uint32_t quad_addr = tmem + ((uint32_t)(32 * q) << 16);           // 32x32b accesses (head, publication)
+    const uint32_t atom_addr = tm_g + ((uint32_t)(32 * q) << 16) + c0;      // 16x256b accesses of this warp's 16 lanes x 16 columns
+    unsigned char *act_a = smb + Map::ACT + g * Map::ACT_G + canon_act(c0 + rr, fa);   // (row c0 + rr, feature fa); fa + 8: + 2 LBO; rows + 8: + SBO
+    unsigned char *dzt_a = smb + Map::DZT + g * Map::DZT_G + canon(fa, c0 + rr, NR);   // (feature fa, row c0 + rr); fa + 8: + 1024; rows + 8: + 256
     uint32_t ph = 0;
-    float db1 = 0.f, db2 = 0.f;                     // bias gradients of feature f over this thread's rows
+    float db1a = 0.f, db1b = 0.f, db2a = 0.f, db2b = 0.f;   // bias gradients of features fa, fa + 8 over this thread's rows
     float s_obj = 0.f, s_kl = 0.f, s_clip = 0.f, s_adv = 0.f, s_ret = 0.f, dls[MAX_O], db3[MAX_O];
 #pragma unroll
     for (int j = 0; j < MAX_O; ++j) { dls[j] = 0.f; db3[j] = 0.f; }
@@ -367,50 +381,51 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
 #define MB6_READY()                                                     \
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        \
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");    \
-    asm volatile("bar.arrive %0, %1;" ::"n"(NB_READY), "n"(NTE + 32) : "memory")
+    asm volatile("bar.arrive %0, %1;" ::"r"(NB_READY + g), "n"(NTE + 32) : "memory")
 #define MB6_WAIT_MMA()                                                  \
     tc5::mbar_wait(bar_mma, ph); ph ^= 1;                               \
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory")
-#define MB6_HIDDEN_EPILOGUE(ZCOL, LCOL, BIASF)                                                                           \
+    // element e of the 8 a thread holds: feature fa + 8 ((e >> 1) & 1), row c0 + 8 (e >> 2) + rr + (e & 1)
+#define MB6_ACT_OFF(e) (((e) >> 2) * ACT_SBO + (((e) >> 1) & 1) * 2 * ACT_LBO + ((e) & 1) * 16)
+#define MB6_HIDDEN_EPILOGUE(ZCOL, LCOL, BA, BB)                                                                          \
     {                                                                                                                    \
       uint32_t v[8], l[8];                                                                                               \
-      MB6_LD8(v, lane_addr + ZCOL + c0);                                                                                 \
+      MB6_LDX2(v, atom_addr + ZCOL);                                                                                     \
       MB6_WAIT_LD();                                                                                                     \
-      unsigned char *ap = smb + Map::ACT + canon_act(32 * atom + (int)c0, f);   /* c0 is a multiple of 8: one 8-row group */ \
-      _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                                                    \
+      _Pragma("unroll") for (int e = 0; e < 8; ++e) {                                                                    \
         float hi, lo;                                                                                                    \
-        tc5::split(act_fused(act, __uint_as_float(v[j]) + BIASF), hi, lo);                                               \
-        v[j] = __float_as_uint(hi); l[j] = __float_as_uint(lo);                                                          \
-        *reinterpret_cast<float *>(ap + 16 * j) = hi;                                                                    \
-        *reinterpret_cast<float *>(ap + Map::ACT_PLANE + 16 * j) = lo;                                                   \
+        tc5::split(act_fused(act, __uint_as_float(v[e]) + (((e >> 1) & 1) ? BB : BA)), hi, lo);                          \
+        v[e] = __float_as_uint(hi); l[e] = __float_as_uint(lo);                                                          \
+        *reinterpret_cast<float *>(act_a + MB6_ACT_OFF(e)) = hi;                                                         \
+        *reinterpret_cast<float *>(act_a + Map::ACT_PLANE + MB6_ACT_OFF(e)) = lo;                                        \
       }                                                                                                                  \
-      MB6_ST8(lane_addr + ZCOL + c0, v);                                                                                 \
-      MB6_ST8(lane_addr + LCOL + c0, l);                                                                                 \
+      MB6_STX2(atom_addr + ZCOL, v);                                                                                     \
+      MB6_STX2(atom_addr + LCOL, l);                                                                                     \
       MB6_WAIT_ST();                                                                                                     \
     }
     int k = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+    for (int64_t tile = tile0; tile < n_tiles; tile += tstride, ++k) {
       const int b = k & 1;
       any = true;
       MB6_WAIT_MMA();
       MB6_STAMP();   // L1 done
-      MB6_HIDDEN_EPILOGUE(ZA, H1L, b1f)
+      MB6_HIDDEN_EPILOGUE(ZA, H1L, b1a, b1b)
       MB6_READY();
       MB6_WAIT_MMA();
       MB6_STAMP();   // E1 + L2 done
-      MB6_HIDDEN_EPILOGUE(ZB, H2L, b2f)
+      MB6_HIDDEN_EPILOGUE(ZB, H2L, b2a, b2b)
       MB6_READY();
       MB6_WAIT_MMA();
       MB6_STAMP();   // E2 + L3 done
-      if (w < 4) {   // loss head (thread = row: 16 lanes of warps 0..3)
-        const float *SAp = reinterpret_cast<const float *>(smb + Map::SA + b * Map::HEAD_BUF), *SHp = SAp + TRW * 8;
-        const int *sidx = reinterpret_cast<const int *>(SHp + 3 * TRW);
-        tc5::mbar_wait(bar_g + 8 * b, (uint32_t)((k >> 1) & 1));   // (long complete) the loaders' cp.async data of this tile is visible
+      if (ch == 0 && q < 2) {   // loss head (thread = row: the group's 16 lanes of warps q = 0, 1)
+        const float *SAp = reinterpret_cast<const float *>(smb + Map::SA + (2 * g + b) * Map::HEAD_BUF), *SHp = SAp + NR * 8;
+        const int *sidx = reinterpret_cast<const int *>(SHp + 3 * NR);
+        tc5::mbar_wait(bar_g + 8 * b, (uint32_t)((k >> 1) & 1));   // (long complete) the cp.async data of this tile is visible
         uint32_t v[8];
-        MB6_LD8(v, lane_addr + OUTC);
+        MB6_LD8(v, quad_addr + OUTC);
         MB6_WAIT_LD();
-        if (lane < 16) {
-          const int row = 16 * q + lane;
+        if ((lane >> 4) == g) {
+          const int row = 16 * q + (lane & 15);
           const bool live = sidx[row] >= 0;
           float dout[8];
 #pragma unroll
@@ -423,7 +438,7 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
                 d[j] = SAp[row * O + j] - (__uint_as_float(v[j]) + bias[j]);
                 logp += -(d[j] * d[j]) * (0.5f * bias[16 + j]) - LOG_SQRT_2PI - bias[8 + j];
               }
-            const float Ai = SHp[TRW + row], old = SHp[row];
+            const float Ai = SHp[NR + row], old = SHp[row];
             float dlogp = 0.f;
             if (live) {
               if (a.a2c) {
@@ -438,7 +453,7 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
                 dlogp = firstb ? -a.lambda_p * a.inv_bg * x : 0.f;
                 s_clip += (rt > hi || rt < lo) ? 1.f : 0.f;
               }
-              s_kl += old - logp; s_adv += Ai; s_ret += SHp[2 * TRW + row];
+              s_kl += old - logp; s_adv += Ai; s_ret += SHp[2 * NR + row];
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -448,20 +463,20 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
                 dls[j] += dlogp * (d[j] * d[j] * ivar - 1.f);
               }
           } else {
-            const float d = (__uint_as_float(v[0]) + bias[0]) - SHp[2 * TRW + row];
+            const float d = (__uint_as_float(v[0]) + bias[0]) - SHp[2 * NR + row];
             if (live) s_obj += d * d;
             dout[0] = live ? 2.f * d * a.inv_bg : 0.f;
           }
-          // dOut -> DO [row][8] (B of G4) and DO^T [atom][8][rows] (B of dW3), hi/lo
+          // dOut -> DO [row][8] (B of G4) and DO^T [8][rows] (B of dW3), hi/lo
           float hi8[8], lo8[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) { db3[j] += dout[j]; tc5::split(dout[j], hi8[j], lo8[j]); }
-          unsigned char *p = smb + Map::DO + canon(row, 0, 8);
+          unsigned char *p = smb + Map::DO + g * Map::DO_G + canon(row, 0, 8);
           *reinterpret_cast<float4 *>(p) = make_float4(hi8[0], hi8[1], hi8[2], hi8[3]);
           *reinterpret_cast<float4 *>(p + 128) = make_float4(hi8[4], hi8[5], hi8[6], hi8[7]);
           *reinterpret_cast<float4 *>(p + Map::DO_PLANE) = make_float4(lo8[0], lo8[1], lo8[2], lo8[3]);
           *reinterpret_cast<float4 *>(p + Map::DO_PLANE + 128) = make_float4(lo8[4], lo8[5], lo8[6], lo8[7]);
-          unsigned char *pt = smb + Map::DOT + (row >> 5) * Map::DOT_ATOM + canon(0, row & 31, NR);
+          unsigned char *pt = smb + Map::DOT + g * Map::DOT_G + canon(0, row, NR);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             *reinterpret_cast<float *>(pt + 16 * j) = hi8[j];
@@ -472,28 +487,27 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
       MB6_READY();
       MB6_WAIT_MMA();
       MB6_STAMP();   // head + G4 (dh2) done
-      {   // E3: dz2 = dh2 .* act'(h2)
+      {   // E3: dz2 = dh2 .* act'(h2): [row][feature] -> ACT (B of G5), [feature][rows] -> DZ^T (B of dW2)
         uint32_t v[8], hh[8], ll[8];
-        MB6_LD8(v, lane_addr + ZC + c0);
-        MB6_LD8(hh, lane_addr + ZB + c0);
-        MB6_LD8(ll, lane_addr + H2L + c0);
+        MB6_LDX2(v, atom_addr + ZC);
+        MB6_LDX2(hh, atom_addr + ZB);
+        MB6_LDX2(ll, atom_addr + H2L);
         MB6_WAIT_LD();
-        unsigned char *ap = smb + Map::ACT + canon_act(32 * atom + (int)c0, f);
-        unsigned char *zp = smb + Map::DZT + atom * Map::DZT_ATOM + canon(f, (int)c0, NR);
         float hi8[8], lo8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float h2 = __uint_as_float(hh[j]) + __uint_as_float(ll[j]);
-          const float dz = __uint_as_float(v[j]) * act_bwd_from_out(act, h2);
-          db2 += dz;
-          tc5::split(dz, hi8[j], lo8[j]);
-          *reinterpret_cast<float *>(ap + 16 * j) = hi8[j];
-          *reinterpret_cast<float *>(ap + Map::ACT_PLANE + 16 * j) = lo8[j];
+        for (int e = 0; e < 8; ++e) {
+          const float h2 = __uint_as_float(hh[e]) + __uint_as_float(ll[e]);
+          const float dz = __uint_as_float(v[e]) * act_bwd_from_out(act, h2);
+          if ((e >> 1) & 1) db2b += dz; else db2a += dz;
+          tc5::split(dz, hi8[e], lo8[e]);
+          *reinterpret_cast<float *>(act_a + MB6_ACT_OFF(e)) = hi8[e];
+          *reinterpret_cast<float *>(act_a + Map::ACT_PLANE + MB6_ACT_OFF(e)) = lo8[e];
         }
 #pragma unroll
-        for (int g4 = 0; g4 < 2; ++g4) {   // 4 consecutive rows = one 16-byte chunk of a core-matrix row; next chunk along K is 128 B away
-          *reinterpret_cast<float4 *>(zp + 128 * g4) = make_float4(hi8[4 * g4], hi8[4 * g4 + 1], hi8[4 * g4 + 2], hi8[4 * g4 + 3]);
-          *reinterpret_cast<float4 *>(zp + Map::DZT_PLANE + 128 * g4) = make_float4(lo8[4 * g4], lo8[4 * g4 + 1], lo8[4 * g4 + 2], lo8[4 * g4 + 3]);
+        for (int pr = 0; pr < 4; ++pr) {   // pairs (e, e + 1) = rows (r, r + 1) of one feature: 8 contiguous bytes of a core-matrix row
+          const int off = ((pr >> 1) * 256) + ((pr & 1) * 1024);   // rows + 8: two chunks along K (256 B); feature + 8: next 8-feature group
+          *reinterpret_cast<float2 *>(dzt_a + off) = make_float2(hi8[2 * pr], hi8[2 * pr + 1]);
+          *reinterpret_cast<float2 *>(dzt_a + Map::DZT_PLANE + off) = make_float2(lo8[2 * pr], lo8[2 * pr + 1]);
         }
       }
       MB6_READY();
@@ -501,111 +515,111 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
       MB6_STAMP();   // E3 + G5 (dh1) done
       {   // E4: dz1 = dh1 .* act'(h1): hi -> ZD, lo -> D1L (A of dW1)
         uint32_t v[8], hh[8], ll[8];
-        MB6_LD8(v, lane_addr + ZD + c0);
-        MB6_LD8(hh, lane_addr + ZA + c0);
-        MB6_LD8(ll, lane_addr + H1L + c0);
+        MB6_LDX2(v, atom_addr + ZD);
+        MB6_LDX2(hh, atom_addr + ZA);
+        MB6_LDX2(ll, atom_addr + H1L);
         MB6_WAIT_LD();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float h1 = __uint_as_float(hh[j]) + __uint_as_float(ll[j]);
-          const float dz = __uint_as_float(v[j]) * act_bwd_from_out(act, h1);
-          db1 += dz;
+        for (int e = 0; e < 8; ++e) {
+          const float h1 = __uint_as_float(hh[e]) + __uint_as_float(ll[e]);
+          const float dz = __uint_as_float(v[e]) * act_bwd_from_out(act, h1);
+          if ((e >> 1) & 1) db1b += dz; else db1a += dz;
           float hi, lo;
           tc5::split(dz, hi, lo);
-          v[j] = __float_as_uint(hi); ll[j] = __float_as_uint(lo);
+          v[e] = __float_as_uint(hi); ll[e] = __float_as_uint(lo);
         }
-        MB6_ST8(lane_addr + ZD + c0, v);
-        MB6_ST8(lane_addr + D1L + c0, ll);
+        MB6_STX2(atom_addr + ZD, v);
+        MB6_STX2(atom_addr + D1L, ll);
         MB6_WAIT_ST();
       }
       MB6_READY();
       MB6_STAMP();   // E4 done
     }
-    MB6_WAIT_MMA();   // the issuer's final commit: all weight-gradient MMAs have completed
+    MB6_WAIT_MMA();   // the issuer's final commit: all weight-gradient MMAs of this group have completed
     MB6_STAMP();
 
-    // ---------------- publish this CTA's partial gradient (layout of fused_minibatch_kernel); the two atoms' accumulators are summed here
-    float *out = a.partials + (int64_t)blockIdx.x * a.pstride;
-    if (!any) {   // no tile (cannot happen with grid <= n_tiles, kept for safety): publish zeros
-      for (int e = t; e < a.n_params + 16; e += NTE) out[e] = 0.f;
+    // ---------------- publish this GROUP's partial gradient (layout of fused_minibatch_kernel): partial row 2 blockIdx + g.
+    // 32x32b accesses of the whole quarter; the lanes of this group's data-path half hold its accumulators (lane -> feature 16 q + lane % 16)
+    float *out = a.partials + (2 * (int64_t)blockIdx.x + g) * a.pstride;
+    const bool mine = (lane >> 4) == g;
+    const int f = 16 * q + (lane & 15);
+    if (!any) {   // this group had no tile (odd tile count): publish zeros
+      for (int e = t - g * NTE; e < a.n_params + 16; e += NTE) out[e] = 0.f;
     } else {
-      {   // dW2^T [i = f lanes][o columns]: this warp's quarter of the columns, 16 contiguous floats per thread
-        uint32_t v[16];
-        MB6_LD16(v, lane_addr + DW2C + 16 * ch);
+      {   // dW2^T [i = f lanes][o columns]: this warp's half of the columns, 32 contiguous floats per thread
+        uint32_t v[16], v2[16];
+        MB6_LD16(v, quad_addr + DW2C + 32 * ch);
+        MB6_LD16(v2, quad_addr + DW2C + 32 * ch + 16);
         MB6_WAIT_LD();
-        float x[16];
+        if (mine) {
+          float4 *dst = reinterpret_cast<float4 *>(out + off_W2(I) + f * H + 32 * ch);   // off_W2 = 64 (I + 1), pstride % 32 == 0: 16-byte aligned
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { x[j] = __uint_as_float(v[j]); x[j] += __shfl_xor_sync(0xffffffffu, x[j], 16); }
-        if (lane < 16) {
-          float4 *dst = reinterpret_cast<float4 *>(out + off_W2(I) + f * H + 16 * ch);   // off_W2 = 64 (I + 1), pstride % 32 == 0: 16-byte aligned
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            dst[j4] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]), __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
+            dst[4 + j4] = make_float4(__uint_as_float(v2[4 * j4]), __uint_as_float(v2[4 * j4 + 1]), __uint_as_float(v2[4 * j4 + 2]), __uint_as_float(v2[4 * j4 + 3]));
+          }
         }
       }
       if (ch == 0) {   // dW1 [o = f lanes][i columns]
         uint32_t v[16], v2[8];
-        MB6_LD16(v, lane_addr + DW1C);
-        MB6_LD8(v2, lane_addr + DW1C + 16);
+        MB6_LD16(v, quad_addr + DW1C);
+        MB6_LD8(v2, quad_addr + DW1C + 16);
         MB6_WAIT_LD();
+        if (mine) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = __uint_as_float(v[j]);
-          x += __shfl_xor_sync(0xffffffffu, x, 16);
-          if (lane < 16 && j < I) out[j * H + f] = x;
-        }
+          for (int j = 0; j < 16; ++j) if (j < I) out[j * H + f] = __uint_as_float(v[j]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float x = __uint_as_float(v2[j]);
-          x += __shfl_xor_sync(0xffffffffu, x, 16);
-          if (lane < 16 && 16 + j < I) out[(16 + j) * H + f] = x;
+          for (int j = 0; j < 8; ++j) if (16 + j < I) out[(16 + j) * H + f] = __uint_as_float(v2[j]);
         }
-      } else if (ch == 1) {         // dW3^T [k = f lanes][o columns]
+      } else {         // dW3^T [k = f lanes][o columns]
         uint32_t v[8];
-        MB6_LD8(v, lane_addr + DW3C);
+        MB6_LD8(v, quad_addr + DW3C);
         MB6_WAIT_LD();
+        if (mine) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float x = __uint_as_float(v[j]);
-          x += __shfl_xor_sync(0xffffffffu, x, 16);
-          if (lane < 16 && j < O) out[off_W3(I) + f * O + j] = x;
+          for (int j = 0; j < 8; ++j) if (j < O) out[off_W3(I) + f * O + j] = __uint_as_float(v[j]);
         }
       }
     }
-    float *red = reinterpret_cast<float *>(smb + Map::RED);   // [4 ch][64] db1 | [4 ch][64] db2 | [4][24] head
-    db1 += __shfl_xor_sync(0xffffffffu, db1, 16);
-    db2 += __shfl_xor_sync(0xffffffffu, db2, 16);
-    if (lane < 16) { red[ch * 64 + f] = db1; red[256 + ch * 64 + f] = db2; }
-    float *hred = red + 512;
-    if (w < 4) {   // head sums: rows live in lanes 0..15 of warps 0..3 (the other lanes hold zeros)
+    float *red = reinterpret_cast<float *>(smb + Map::RED + g * Map::RED_G);   // [2 ch][64] db1 | [2 ch][64] db2 | [2][24] head
+    // a feature's rows are spread over the 4 lanes with the same lane / 4 (and over the two column halves ch)
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      db1a += __shfl_xor_sync(0xffffffffu, db1a, o); db1b += __shfl_xor_sync(0xffffffffu, db1b, o);
+      db2a += __shfl_xor_sync(0xffffffffu, db2a, o); db2b += __shfl_xor_sync(0xffffffffu, db2b, o);
+    }
+    if ((lane & 3) == 0) { red[ch * 64 + fa] = db1a; red[ch * 64 + fa + 8] = db1b; red[128 + ch * 64 + fa] = db2a; red[128 + ch * 64 + fa + 8] = db2b; }
+    float *hred = red + 256;
+    if (ch == 0 && q < 2) {   // head sums: this group's rows live in 16 lanes of warps q = 0, 1 (the other lanes hold zeros)
       float v;
-      v = warp_sum(s_obj); if (lane == 0) hred[w * 24 + 0] = v;
-      v = warp_sum(s_kl); if (lane == 0) hred[w * 24 + 1] = v;
-      v = warp_sum(s_clip); if (lane == 0) hred[w * 24 + 2] = v;
-      v = warp_sum(s_adv); if (lane == 0) hred[w * 24 + 3] = v;
-      v = warp_sum(s_ret); if (lane == 0) hred[w * 24 + 4] = v;
+      v = warp_sum(s_obj); if (lane == 0) hred[q * 24 + 0] = v;
+      v = warp_sum(s_kl); if (lane == 0) hred[q * 24 + 1] = v;
+      v = warp_sum(s_clip); if (lane == 0) hred[q * 24 + 2] = v;
+      v = warp_sum(s_adv); if (lane == 0) hred[q * 24 + 3] = v;
+      v = warp_sum(s_ret); if (lane == 0) hred[q * 24 + 4] = v;
 #pragma unroll
       for (int j = 0; j < MAX_O; ++j) {
-        v = warp_sum(dls[j]); if (lane == 0) hred[w * 24 + 8 + j] = v;
-        v = warp_sum(db3[j]); if (lane == 0) hred[w * 24 + 16 + j] = v;
+        v = warp_sum(dls[j]); if (lane == 0) hred[q * 24 + 8 + j] = v;
+        v = warp_sum(db3[j]); if (lane == 0) hred[q * 24 + 16 + j] = v;
       }
     }
-    asm volatile("bar.sync %0, %1;" ::"n"(NB_EPI), "n"(NTE) : "memory");
-    if (t < 64) out[off_b1(I) + t] = (red[t] + red[64 + t]) + (red[128 + t] + red[192 + t]);
-    else if (t < 128) { const int j = t - 64; out[off_b2(I) + j] = (red[256 + j] + red[320 + j]) + (red[384 + j] + red[448 + j]); }
-    else if (t < 128 + O) { const int o = t - 128; out[off_b3(I, O) + o] = (hred[16 + o] + hred[24 + 16 + o]) + (hred[48 + 16 + o] + hred[72 + 16 + o]); }
-    else if (t >= 160 && t < 176) {
+    asm volatile("bar.sync %0, %1;" ::"r"(NB_EPI + g), "n"(NTE) : "memory");
+    const int te = t - g * NTE;
+    if (te < 64) out[off_b1(I) + te] = red[te] + red[64 + te];
+    else if (te < 128) { const int j = te - 64; out[off_b2(I) + j] = red[128 + j] + red[192 + j]; }
+    else if (te < 128 + O) { const int o = te - 128; out[off_b3(I, O) + o] = hred[16 + o] + hred[24 + 16 + o]; }
+    else if (te >= 160 && te < 176) {
       // tail layout: [n_params .. +8) = dlogΣ, [n_params+8 .. +16) = obj, kl, clip, adv, ret, 0, 0, 0
-      const int kk = t - 160, src = kk < 8 ? 8 + kk : kk - 8;
+      const int kk = te - 160, src = kk < 8 ? 8 + kk : kk - 8;
       float v = 0.f;
-      if (src < 5 || (src >= 8 && src < 16))
-#pragma unroll
-        for (int ww = 0; ww < 4; ++ww) v += hred[ww * 24 + src];
+      if (src < 5 || (src >= 8 && src < 16)) v = hred[src] + hred[24 + src];
       out[a.n_params + kk] = v;
     }
     MB6_STAMP();   // partial gradient published
 #undef MB6_READY
 #undef MB6_WAIT_MMA
 #undef MB6_HIDDEN_EPILOGUE
+#undef MB6_ACT_OFF
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -617,6 +631,8 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
 #undef MB6_ST16
 #undef MB6_ST8
 #undef MB6_LD8
+#undef MB6_LDX2
+#undef MB6_STX2
 #undef MB6_WAIT_LD
 #undef MB6_WAIT_ST
 

@@ -1813,7 +1813,7 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   const bool tc5_grid = !big && !no_mma() && mb5_env0 && mb5_env0[0] == '1' && mlp->dims[0] <= mb5::KX && mlp->dims[3] <= 8;
   const bool t5k = minibatch_kernel_is_t5(mlp) && !big;
   const int grid = big ? (int)i64min(cdiv(bm, RB), (int64_t)ctx->num_sms)
-                       : t5k ? (int)i64min(cdiv(bm, mb6::TRW), (int64_t)ctx->num_sms)
+                       : t5k ? (int)i64min(cdiv(cdiv(bm, mb6::NR), 2), (int64_t)ctx->num_sms)
                        : tc5_grid ? (int)i64min(cdiv(bm, mb5::TR), (int64_t)ctx->num_sms) : (int)i64min(cdiv(bm, R), (int64_t)sms * 2);
   const int pstride = (int)((mlp->n_params + 16 + 31) / 32 * 32);
   const size_t need = (size_t)ctx->num_sms * 2 * pstride * sizeof(float);
@@ -1878,6 +1878,7 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   }
   }
   CRUX_LAUNCHED(ctx);
+  const int nparts = t5k ? 2 * grid : grid;   // mb_t5.cuh: each CTA runs two pipelines, each publishes its own partial
   const int n_out = (int)mlp->n_params + 16;
   const int rblocks = (n_out + 31) / 32;   // <= 1024 doubles of norm_part (n_params <= 6792)
   const int rgrid = reserve > 0 ? (int)i64min(rblocks, 2 * reserve) : rblocks;   // two 1024-thread CTAs per reserved SM
@@ -1912,11 +1913,11 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   }
   { CruxTimed timed(ctx, CRUX_T_REDUCE);
   if (fuse_adam)
-    reduce_fused_partials_kernel<1><<<rgrid, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
+    reduce_fused_partials_kernel<1><<<rgrid, RW * 32, 0, ctx->stream>>>(mlp->partials, nparts, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
                                                                         ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb,
                                                                         ctx->flags_dev + 2, g, fuse_adam, po);
   else
-    reduce_fused_partials_kernel<0><<<rgrid, RW * 32, 0, ctx->stream>>>(mlp->partials, grid, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
+    reduce_fused_partials_kernel<0><<<rgrid, RW * 32, 0, ctx->stream>>>(mlp->partials, nparts, pstride, (int)mlp->n_params, mlp->grads, (float)bm,
                                                                         ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, ctl, mb,
                                                                         ctx->flags_dev + 2, g, fuse_adam, po);
   }

