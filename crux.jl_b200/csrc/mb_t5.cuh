@@ -23,8 +23,8 @@
 //   L1  ZA  = W1 S^T                  E1  h1 = act(ZA + b1): hi -> ZA, lo -> H1L (A of dW2), [row][feature] hi/lo -> ACT (B of L2)
 //   L2  ZB  = W2 h1                   E2  h2: hi -> ZB, lo -> H2L (A of dW3), ACT
 //   L3  OUT[rows][8] = h2 W3^T        (row-major form: A = ACT, B = W3 [8][64])      head: loss terms, dOut -> DO [row][8], DO^T [8][rows]
-//   G4  ZC  = W3^T dOut^T  ||  dW3^T += h2^T dOut       E3  dz2 = ZC .* act'(h2): ACT (B of G5), DZ^T [feature][rows] (B of dW2); db2
-//   G5  ZD  = W2^T dz2     ||  dW2^T += h1^T dz2        E4  dz1 = ZD .* act'(h1): hi -> ZD, lo -> D1L (A of dW1); db1
+//                                     E3  dh2 = dOut W3 (K <= 8: FP32 pipe), dz2 = dh2 .* act'(h2): ACT (B of G5), DZ^T [feature][rows] (B of dW2); db2
+//   G5  ZD  = W2^T dz2     ||  dW3^T += h2^T dOut, dW2^T += h1^T dz2        E4  dz1 = ZD .* act'(h1): hi -> ZD, lo -> D1L (A of dW1); db1
 //   G6  dW1 += dz1^T S                                   (completion awaited at the top of the next tile)
 // 3xTF32 everywhere (lo*hi + hi*lo + hi*hi, fp32-level accuracy), same partial-gradient layout and head arithmetic as
 // fused_minibatch_tc_kernel.  Included by ppo_fused.cu after mb_tc5.cuh.
@@ -38,16 +38,18 @@ constexpr int NR = 32, KX = tc5::KX;   // a tile = one 32-row atom
 constexpr int NEW = 8, NTE = NEW * 32, W_ISSUE = 2 * NEW, W_LOAD = 2 * NEW + 2, NTH = (2 * NEW + 4) * 32, NGT = (NEW + 2) * 32;
 constexpr int NB_READY = 1, NB_PRO = 3, NB_EPI = 5;   // named barriers (+ g): epilogue -> issuer hand-off, cooperative first load, epilogue-only
 constexpr int TMEM_COLS = 512;
-constexpr uint32_t ZA = 0, H1L = 32, ZB = 64, H2L = 96, ZC = 128, ZD = 160, D1L = 192, OUTC = 224, DW2C = 256, DW1C = 320, DW3C = 352;
+// TMEM columns (all 512; a group uses the data-path half dp = 16 g of every block, the weight blocks are replicated in both halves):
+//   ZA  z1 -> h1 hi | H1L h1 lo | ZB z2 -> h2 hi | H2L h2 lo, later dz1 lo (D1L) | ZC L3's output (8 columns), later dh1 -> dz1 hi (ZD)
+//   DW2C / DW1C / DW3C weight-gradient accumulators | W2A / W2TA: W2 and W2^T as hi | lo A operands (A from tensor memory costs 16 cycles
+//   per MMA against 24 from shared memory and takes 2 KB per MMA off the shared-memory pipe: experiments/tc5_probe5.cu)
+constexpr uint32_t ZA = 0, H1L = 32, ZB = 64, H2L = 96, D1L = H2L, ZC = 128, ZD = ZC, OUTC = ZC, DW2C = 160, DW1C = 224, DW3C = 248;
+constexpr uint32_t W2A_HI = 256, W2A_LO = 320, W2TA_HI = 384, W2TA_LO = 448;
 constexpr int ACT_LBO = 144, ACT_SBO = 2320;   // padded K-major tile: the [row][feature] stores of a warp hit 32 distinct banks
 
 struct Map {   // bytes; every operand is a pair of planes hi | lo
-  static constexpr int W1A = 0;                                  // A [64 j][24 i]
-  static constexpr int W2A = W1A + 2 * 64 * KX * 4;              // A [64 j][64 k]   = W2(j,k)
-  static constexpr int W2TA = W2A + 2 * 64 * 64 * 4;             // A [64 k][64 j]   = W2(j,k)
-  static constexpr int W3B = W2TA + 2 * 64 * 64 * 4;             // B [8 o][64 k]    = W3(o,k)
-  static constexpr int W3TA = W3B + 2 * 8 * 64 * 4;              // A [64 k][8 o]    = W3(o,k)
-  static constexpr int PLANES = W3TA + 2 * 64 * 8 * 4;           // bytes of the weight planes = crux_mlp::frag in plane mode (one TMA bulk copy)
+  static constexpr int W1A = 0;                                  // A [64 j][24 i]   = W1(j,i)
+  static constexpr int W3B = W1A + 2 * 64 * KX * 4;              // B [8 o][64 k]    = W3(o,k)
+  static constexpr int PLANES = W3B + 2 * 8 * 64 * 4;            // bytes of the weight planes = crux_mlp::frag in plane mode (one TMA bulk copy)
   // per group g and buffer b (the loader prepares tile n+1 while tile n runs): S hi|lo [32 rows][24] (B of L1), S^T hi|lo [24][32 rows] (B of dW1)
   static constexpr int S = PLANES;
   static constexpr int S_PLANE = NR * KX * 4, ST_PLANE = 3 * 1024;
@@ -56,8 +58,8 @@ struct Map {   // bytes; every operand is a pair of planes hi | lo
   static constexpr int ACT_PLANE = 4 * ACT_SBO, ACT_G = 2 * ACT_PLANE;
   static constexpr int DZT = ACT + 2 * ACT_G;                    // per group B [64 o][32 rows] hi | lo   (L3's 64-row read of group 1's lo plane ends inside it)
   static constexpr int DZT_PLANE = 8 * 1024, DZT_G = 2 * DZT_PLANE;
-  static constexpr int DO = DZT + 2 * DZT_G;                     // per group B [32 rows][8] hi | lo
-  static constexpr int DO_PLANE = 4 * 256, DO_G = 2 * DO_PLANE;
+  static constexpr int DO = DZT + 2 * DZT_G;                     // per group fp32 dOut [32 rows][8] (read back by E3: dh2 = dOut W3 on the FP32 pipe, K <= 8)
+  static constexpr int DO_G = NR * 8 * 4;
   static constexpr int DOT = DO + 2 * DO_G;                      // per group B [8 o][32 rows] hi | lo
   static constexpr int DOT_PLANE = 1024, DOT_G = 2 * DOT_PLANE;
   static constexpr int SX = DOT + 2 * DOT_G;                     // per group gather staging: x [32][I <= 24] (loader-private)
@@ -79,7 +81,7 @@ using tc5::elect_one;
 
 // Weight planes in GLOBAL memory (crux_mlp::frag, Map::PLANES bytes, same offsets as the shared-memory map): built once at the start
 // of an update (build_planes_kernel) and kept current by the Adam kernels, which scatter every updated parameter into its plane
-// positions -- the minibatch kernel stages them with ONE TMA bulk copy instead of rebuilding 10.7 k hi/lo pairs per CTA and launch.
+// positions -- the minibatch kernel stages them with ONE TMA bulk copy.  (W1 as the A operand of L1, W3 as the B operand of L3.)
 __device__ __forceinline__ void plane_put(unsigned char *planes, int base, int plane_bytes, int off, float v) {
   float hi, lo;
   tc5::split(v, hi, lo);
@@ -89,18 +91,10 @@ __device__ __forceinline__ void plane_put(unsigned char *planes, int base, int p
 __device__ __forceinline__ void plane_scatter(float *planes_f, int I, int O, int i, float v) {   // i = index in the flat parameter vector
   unsigned char *pl = reinterpret_cast<unsigned char *>(planes_f);
   if (i < I * H) { const int in = i >> 6, j = i & 63; plane_put(pl, Map::W1A, 64 * KX * 4, canon(j, in, KX), v); return; }
-  const int e2 = i - off_W2(I);
-  if (e2 >= 0 && e2 < H * H) {
-    const int k = e2 >> 6, j = e2 & 63;   // flat W2[k*64 + j] = W2(out j, in k)
-    plane_put(pl, Map::W2A, 64 * 64 * 4, canon(j, k, 64), v);
-    plane_put(pl, Map::W2TA, 64 * 64 * 4, canon(k, j, 64), v);
-    return;
-  }
-  const int e3 = i - off_W3(I);
+  const int e3 = i - off_W3(I);   // (W2 and W2^T are loaded into tensor memory from the parameter vector by every CTA)
   if (e3 >= 0 && e3 < H * O) {
     const int k = e3 / O, o = e3 - k * O;
     plane_put(pl, Map::W3B, 8 * 64 * 4, canon(o, k, 64), v);
-    plane_put(pl, Map::W3TA, 64 * 8 * 4, canon(k, o, 8), v);
   }
 }
 __global__ void build_planes_kernel(const float *__restrict__ params, float *__restrict__ planes, int I, int O, int n_params) {
@@ -213,32 +207,48 @@ __device__ __forceinline__ void load_tile(unsigned char *smb, const MbArgs &a, i
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-template <int HEAD>
+// tanh_fast of ppo_fused.cu (1 - 2 / (exp(2x) + 1) on the SFU) without the denormal-range fix-up of __expf: branch-free, so that the
+// 8 independent element chains of an epilogue thread interleave (with the activation as a RUN-TIME switch every element was a
+// branch and the MUFU latencies added up: ~100 cycles per element, measured as ~1000-cycle epilogues)
+__device__ __forceinline__ float tanh_t5(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((2.0f * x) * 1.4426950216293334961f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
+template <int ACT> __device__ __forceinline__ float actf(float z) { return ACT == CRUX_ACT_TANH ? tanh_t5(z) : fmaxf(z, 0.0f); }
+template <int ACT> __device__ __forceinline__ float dactf(float y) { return ACT == CRUX_ACT_TANH ? fmaf(-y, y, 1.0f) : (y > 0.0f ? 1.0f : 0.0f); }
+
+template <int HEAD, int ACT>
 __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
   extern __shared__ __align__(1024) unsigned char smb[];
   const NetDesc nd = a.net;
-  const int I = nd.I, O = nd.O, act = nd.act;
+  const int I = nd.I, O = nd.O;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   // group of this warp and its index inside the group's 320 threads (epilogue 0..255 | issuer 256..287 | loader 288..319)
   const int g = w < 2 * NEW ? w / NEW : (w - 2 * NEW) & 1;
   const int gt = w < 2 * NEW ? t - g * NTE : (w < W_LOAD ? NTE + lane : NTE + 32 + lane);
   int prof_n = 0;
 #define MB6_STAMP() do { if (a.prof && blockIdx.x == 0 && t == 0 && prof_n < 64) a.prof[prof_n++] = clock64(); } while (0)
+#define MB6_ISTAMP() do { if (a.prof && blockIdx.x == 0 && w == W_ISSUE && lane == 0 && prof_n < 64) a.prof[64 + prof_n++] = clock64(); } while (0)
   MB6_STAMP();
   const int stop_at = a.ctl ? a.ctl[1] : 0;
   const uint32_t bar_par = smem_u32(smb + Map::BAR);
-  const uint32_t bar_mma = smem_u32(smb + Map::BAR + 8 + 40 * g), bar_g = bar_mma + 8, bar_free = bar_mma + 24;   // bar_g[2], bar_free[2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + Map::BAR + 96);
+  const uint32_t bar_mma = smem_u32(smb + Map::BAR + 8 + 48 * g), bar_g = bar_mma + 8, bar_free = bar_mma + 24, bar_dw3 = bar_mma + 40;   // bar_g[2], bar_free[2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + Map::BAR + 112);
+  int *pipe_token = reinterpret_cast<int *>(smb + Map::BAR + 116);   // tensor-pipe token shared by the two issuer warps
   float *bias = reinterpret_cast<float *>(smb + Map::BIAS);   // b3[8] | logΣ[8] | 1/σ²[8]
   const int64_t n_tiles = (a.bm + NR - 1) / NR;
   const int64_t tile0 = 2 * (int64_t)blockIdx.x + g, tstride = 2 * (int64_t)gridDim.x;   // this group's tiles: tile0, tile0 + tstride, ...
 
   // ---- prologue (all warps): barriers, weight planes (ONE TMA bulk copy), TMEM, zero the K padding of the input buffers
   if (t == 0) {
+    *pipe_token = 0;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_par), "r"(1) : "memory");
     for (int gg = 0; gg < 2; ++gg) {
-      const uint32_t bm_ = smem_u32(smb + Map::BAR + 8 + 40 * gg);
+      const uint32_t bm_ = smem_u32(smb + Map::BAR + 8 + 48 * gg);
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bm_), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bm_ + 40), "r"(1) : "memory");
       for (int b = 0; b < 2; ++b) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bm_ + 8 + 8 * b), "r"(32) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bm_ + 24 + 8 * b), "r"(1) : "memory");
@@ -247,39 +257,66 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  if (w == W_ISSUE) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   for (int e = t; e < 4 * Map::IN_BUF / 4; e += NTH) reinterpret_cast<float *>(smb + Map::S)[e] = 0.f;   // K padding stays zero
-  for (int e = t; e < (2 * Map::DO_G + 2 * Map::DOT_G) / 4; e += NTH) reinterpret_cast<float *>(smb + Map::DO)[e] = 0.f;
+  for (int e = t; e < (2 * Map::DO_G + 2 * Map::DOT_G) / 4; e += NTH) reinterpret_cast<float *>(smb + Map::DO)[e] = 0.f;   // outputs >= O stay zero
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const bool skip = stop_at != 0 && stop_at <= a.mb;   // an EARLIER minibatch raised the KL stop flag (rl/ppo.jl:59): nothing to do
   if (t == 0) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_par), "r"((uint32_t)Map::PLANES) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smb)), "l"(a.planes),
                  "r"((uint32_t)Map::PLANES), "r"(bar_par)
                  : "memory");
   }
-  if (w == W_ISSUE) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
   if (t < 8) bias[t] = t < O ? __ldg(nd.params + off_b3(I, O) + t) : 0.f;
   if (HEAD == 0 && t >= 32 && t < 40) { const int j = t - 32; const float ls = j < O ? a.ls[j] : 0.f, sg = expf(ls); bias[8 + j] = ls; bias[16 + j] = 1.0f / (sg * sg); }
-  // the group's first tile is loaded by ALL of its 320 threads (the loader warp alone would put ~2 us in front of the first GEMM)
-  const bool skip = stop_at != 0 && stop_at <= a.mb;   // an EARLIER minibatch raised the KL stop flag (rl/ppo.jl:59): nothing to do
-  if (!skip && tile0 < n_tiles) {
-    load_tile<HEAD>(smb, a, I, O, g, 0, tile0, gt, NGT, [&]() { asm volatile("bar.sync %0, %1;" ::"r"(NB_PRO + g), "n"(NGT) : "memory"); });
-    asm volatile("bar.sync %0, %1;" ::"r"(NB_PRO + g), "n"(NGT) : "memory");
-    if (w >= W_LOAD) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_g) : "memory");   // buffer 0 of this group is ready
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = *tmem_slot;
   if (skip) {
     tc5::mbar_wait(bar_par, 0);
     __syncthreads();
     if (w == W_ISSUE) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     return;
   }
+  if (w >= 2 * NEW) {
+    // the group's FIRST tile is loaded by its issuer + loader warps (64 threads) while the epilogue warps fill tensor memory with W2
+    if (tile0 < n_tiles) {
+      load_tile<HEAD>(smb, a, I, O, g, 0, tile0, gt - NTE, 64, [&]() { asm volatile("bar.sync %0, %1;" ::"r"(NB_PRO + g), "n"(64) : "memory"); });
+      asm volatile("bar.sync %0, %1;" ::"r"(NB_PRO + g), "n"(64) : "memory");
+      if (w >= W_LOAD) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_g) : "memory");   // buffer 0 of this group is ready
+    }
+  } else {   // W2 (A of L2) and W2^T (A of G5) -> tensor memory, hi | lo, replicated in both data-path halves:
+    // warp (quarter wq, part) owns lanes [32 wq, +32) (feature m = 16 wq + lane % 16 in either half) x 32 of the 128 K-columns
+    const int wq = w & 3, part = w >> 2, m = 16 * wq + (lane & 15);
+    const float *W2p = nd.params + off_W2(I);   // flat W2[k * 64 + j] = W2(out j, in k)
+    uint32_t hi[32], lo[32];
+    if (part < 2) {            // W2A[m = j][k]: k = 32 part .. + 31
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { float h, l; tc5::split(__ldg(W2p + (32 * part + c) * H + m), h, l); hi[c] = __float_as_uint(h); lo[c] = __float_as_uint(l); }
+    } else {                   // W2TA[m = k][j]: j = 32 (part - 2) .. + 31
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(W2p + m * H + 32 * (part - 2)) + c4);
+        float h, l;
+        tc5::split(x.x, h, l); hi[4 * c4] = __float_as_uint(h); lo[4 * c4] = __float_as_uint(l);
+        tc5::split(x.y, h, l); hi[4 * c4 + 1] = __float_as_uint(h); lo[4 * c4 + 1] = __float_as_uint(l);
+        tc5::split(x.z, h, l); hi[4 * c4 + 2] = __float_as_uint(h); lo[4 * c4 + 2] = __float_as_uint(l);
+        tc5::split(x.w, h, l); hi[4 * c4 + 3] = __float_as_uint(h); lo[4 * c4 + 3] = __float_as_uint(l);
+      }
+    }
+    const uint32_t dst = tmem + ((uint32_t)(32 * wq) << 16) + (part < 2 ? W2A_HI + 32 * part : W2TA_HI + 32 * (part - 2));
+    TC5_ST32(dst, hi);
+    TC5_ST32(dst + 64, lo);   // the lo block follows the hi block
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   MB6_STAMP();   // end of the prologue
   const uint32_t tm_g = tmem + ((uint32_t)(16 * g) << 16);   // this group's data-path half
 
@@ -297,65 +334,88 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
     tc5::mbar_wait(bar_par, 0);   // weight planes have landed
     const uint32_t sb = smem_u32(smb);
     const uint64_t dW1A = tc5::make_desc(sb + Map::W1A, 128, 32 * KX), dW1A_lo = tc5::make_desc(sb + Map::W1A + 64 * KX * 4, 128, 32 * KX);
-    const uint64_t dW2A = tc5::make_desc(sb + Map::W2A, 128, 32 * 64), dW2A_lo = tc5::make_desc(sb + Map::W2A + 64 * 64 * 4, 128, 32 * 64);
-    const uint64_t dW2TA = tc5::make_desc(sb + Map::W2TA, 128, 32 * 64), dW2TA_lo = tc5::make_desc(sb + Map::W2TA + 64 * 64 * 4, 128, 32 * 64);
     const uint64_t dW3B = tc5::make_desc(sb + Map::W3B, 128, 32 * 64), dW3B_lo = tc5::make_desc(sb + Map::W3B + 8 * 64 * 4, 128, 32 * 64);
-    const uint64_t dW3TA = tc5::make_desc(sb + Map::W3TA, 128, 32 * 8), dW3TA_lo = tc5::make_desc(sb + Map::W3TA + 64 * 8 * 4, 128, 32 * 8);
     const uint64_t dACT = tc5::make_desc(sb + Map::ACT + g * Map::ACT_G, ACT_LBO, ACT_SBO), dACT_lo = dACT + (uint64_t)(Map::ACT_PLANE >> 4);
     const uint64_t dDZT = tc5::make_desc(sb + Map::DZT + g * Map::DZT_G, 128, 32 * NR), dDZT_lo = dDZT + (uint64_t)(Map::DZT_PLANE >> 4);
-    const uint64_t dDO = tc5::make_desc(sb + Map::DO + g * Map::DO_G, 128, 32 * 8), dDO_lo = dDO + (uint64_t)(Map::DO_PLANE >> 4);
     const uint64_t dDOT = tc5::make_desc(sb + Map::DOT + g * Map::DOT_G, 128, 32 * NR), dDOT_lo = dDOT + (uint64_t)(Map::DOT_PLANE >> 4);
     constexpr uint32_t ADV = 16, ADV_ACT = (2 * ACT_LBO) >> 4;           // one k-step = two core matrices along K
     const uint32_t id32 = tc5::make_idesc(64, 32), id8 = tc5::make_idesc(64, 8), id64 = tc5::make_idesc(64, 64), id24 = tc5::make_idesc(64, 24);
     uint32_t first = 0;   // 0 on this group's first tile: the dW accumulators are overwritten, then accumulated
     int k = 0;
+    // The tensor pipe executes the two groups' MMAs strictly interleaved when both issue at once (measured: 53 instead of 24 cycles per
+    // MMA for BOTH chains), which keeps the two pipelines phase-locked: both wait for their GEMMs, then both run their epilogues.  A
+    // chain is therefore issued under a token: the first collision serialises the two chains and from then on one group's GEMM runs
+    // under the other group's epilogue.  (The issue loop is back-pressured by the pipe, so holding the token while issuing = owning it.)
+    auto pipe_acquire = [&]() { while (atomicCAS(pipe_token, 0, 1) != 0) { } };
+    auto pipe_release = [&]() { atomicExch(pipe_token, 0); };
 #define MB6_WAIT_READY()                                                       \
     asm volatile("bar.sync %0, %1;" ::"r"(NB_READY + g), "n"(NTE + 32) : "memory");  \
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory")
-    for (int64_t tile = tile0; tile < n_tiles; tile += tstride, ++k) {
-      const int b = k & 1;
-      const uint64_t dS = tc5::make_desc(sb + Map::S + (2 * g + b) * Map::IN_BUF, 128, 32 * KX), dS_lo = dS + (uint64_t)(Map::S_PLANE >> 4);
-      const uint64_t dST = tc5::make_desc(sb + Map::S + (2 * g + b) * Map::IN_BUF + 2 * Map::S_PLANE, 128, 32 * NR), dST_lo = dST + (uint64_t)(Map::ST_PLANE >> 4);
-      tc5::mbar_wait(bar_g + 8 * b, (uint32_t)((k >> 1) & 1));   // S / S^T of this tile are ready
+    auto in_desc = [&](int bb, uint64_t &dS, uint64_t &dS_lo, uint64_t &dST, uint64_t &dST_lo) {
+      dS = tc5::make_desc(sb + Map::S + (2 * g + bb) * Map::IN_BUF, 128, 32 * KX); dS_lo = dS + (uint64_t)(Map::S_PLANE >> 4);
+      dST = tc5::make_desc(sb + Map::S + (2 * g + bb) * Map::IN_BUF + 2 * Map::S_PLANE, 128, 32 * NR); dST_lo = dST + (uint64_t)(Map::ST_PLANE >> 4);
+    };
+    auto issue_L1 = [&](int kk) {   // L1 of this group's kk-th tile: ZA = W1 S^T (waits for the loader's buffer)
+      uint64_t dS, dS_lo, dST, dST_lo;
+      in_desc(kk & 1, dS, dS_lo, dST, dST_lo);
+      tc5::mbar_wait(bar_g + 8 * (kk & 1), (uint32_t)((kk >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (elect_one()) {   // L1: ZA = W1 S^T
+      if (elect_one()) {
+        pipe_acquire();
         gemm_ss<KX / 8>(tm_g + ZA, dW1A, dW1A_lo, ADV, dS, dS_lo, ADV, id32, 0u);
         commit(bar_mma);
+        pipe_release();
       }
       __syncwarp();
+    };
+    if (tile0 < n_tiles) issue_L1(0);
+    for (int64_t tile = tile0; tile < n_tiles; tile += tstride, ++k) {
+      const int b = k & 1;
+      uint64_t dS, dS_lo, dST, dST_lo;
+      in_desc(b, dS, dS_lo, dST, dST_lo);
       MB6_WAIT_READY();    // E1 done
+      MB6_ISTAMP();
       if (elect_one()) {   // L2: ZB = W2 h1
-        gemm_ss<8>(tm_g + ZB, dW2A, dW2A_lo, ADV, dACT, dACT_lo, ADV_ACT, id32, 0u);
+        pipe_acquire();
+        gemm_ts<8>(tm_g + ZB, tm_g + W2A_HI, tm_g + W2A_LO, dACT, dACT_lo, ADV_ACT, id32, 0u);
         commit(bar_mma);
+        pipe_release();
       }
       __syncwarp();
+      MB6_ISTAMP();
       MB6_WAIT_READY();    // E2 done
+      MB6_ISTAMP();
       if (elect_one()) {   // L3 (rows on the lanes, M = 64: rows 32.. of the A operand are don't-care): OUT[rows][8] = h2 W3^T
+        pipe_acquire();
         gemm_ss<8>(tm_g + OUTC, dACT, dACT_lo, ADV_ACT, dW3B, dW3B_lo, ADV, id8, 0u);
         commit(bar_mma);
+        pipe_release();
       }
       __syncwarp();
-      MB6_WAIT_READY();    // head done
-      if (elect_one()) {   // G4: ZC = W3^T dOut^T, then (under E3) dW3^T += h2^T dOut
-        gemm_ss<1>(tm_g + ZC, dW3TA, dW3TA_lo, ADV, dDO, dDO_lo, ADV, id32, 0u);
+      MB6_ISTAMP();
+      MB6_WAIT_READY();    // head + E3 done (dh2 = dOut W3 has K <= 8: FP32 pipe inside E3, no GEMM round trip)
+      if (elect_one()) {   // G5: ZD = W2^T dz2, then (under E4) dW3^T += h2^T dOut, dW2^T += h1^T dz2
+        pipe_acquire();
+        gemm_ts<8>(tm_g + ZD, tm_g + W2TA_HI, tm_g + W2TA_LO, dACT, dACT_lo, ADV_ACT, id32, 0u);
         commit(bar_mma);
+        pipe_release();   // the other group's critical chain may go first
+        pipe_acquire();
         gemm_ts<NR / 8>(tm_g + DW3C, tm_g + ZB, tm_g + H2L, dDOT, dDOT_lo, ADV, id8, first);
-      }
-      __syncwarp();
-      MB6_WAIT_READY();    // E3 done
-      if (elect_one()) {   // G5: ZD = W2^T dz2, then (under E4) dW2^T += h1^T dz2
-        gemm_ss<8>(tm_g + ZD, dW2TA, dW2TA_lo, ADV, dACT, dACT_lo, ADV_ACT, id32, 0u);
-        commit(bar_mma);
+        commit(bar_dw3);  // h2 lo has been read: E4 may store dz1 lo over it
         gemm_ts<NR / 8>(tm_g + DW2C, tm_g + ZA, tm_g + H1L, dDZT, dDZT_lo, ADV, id64, first);
+        pipe_release();
       }
       __syncwarp();
       MB6_WAIT_READY();    // E4 done
       if (elect_one()) {   // G6: dW1 += dz1^T S; its completion frees this tile's input buffer for the loader
+        pipe_acquire();
         gemm_ts<NR / 8>(tm_g + DW1C, tm_g + ZD, tm_g + D1L, dST, dST_lo, ADV, id24, first);
         commit(bar_free + 8 * b);
+        pipe_release();
       }
       __syncwarp();
       first = 1u;
+      if (tile + tstride < n_tiles) issue_L1(k + 1);   // the next tile's L1 runs behind dW1: its round trip is off the critical path
     }
     if (elect_one()) commit(bar_mma);   // every weight-gradient MMA of this group has completed: its epilogue warps read the accumulators
     __syncwarp();
@@ -367,6 +427,12 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
     const int fa = 16 * q + (lane >> 2), rr = 2 * (lane & 3), c0 = 16 * ch;
     const float b1a = __ldg(nd.params + off_b1(I) + fa), b1b = __ldg(nd.params + off_b1(I) + fa + 8);
     const float b2a = __ldg(nd.params + off_b2(I) + fa), b2b = __ldg(nd.params + off_b2(I) + fa + 8);
+    float w3a[MAX_O], w3b[MAX_O];   // W3(o, fa), W3(o, fa + 8): dh2 = dOut W3 in E3
+#pragma unroll
+    for (int o = 0; o < MAX_O; ++o) {
+      w3a[o] = o < O ? __ldg(nd.params + off_W3(I) + fa * O + o) : 0.f;
+      w3b[o] = o < O ? __ldg(nd.params + off_W3(I) + (fa + 8) * O + o) : 0.f;
+    }
     const uint32_t quad_addr = tmem + ((uint32_t)(32 * q) << 16);           // 32x32b accesses (head, publication)
     const uint32_t atom_addr = tm_g + ((uint32_t)(32 * q) << 16) + c0;      // 16x256b accesses of this warp's 16 lanes x 16 columns
     unsigned char *act_a = smb + Map::ACT + g * Map::ACT_G + canon_act(c0 + rr, fa);   // (row c0 + rr, feature fa); fa + 8: + 2 LBO; rows + 8: + SBO
@@ -394,7 +460,7 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
       MB6_WAIT_LD();                                                                                                     \
       _Pragma("unroll") for (int e = 0; e < 8; ++e) {                                                                    \
         float hi, lo;                                                                                                    \
-        tc5::split(act_fused(act, __uint_as_float(v[e]) + (((e >> 1) & 1) ? BB : BA)), hi, lo);                          \
+        tc5::split(actf<ACT>(__uint_as_float(v[e]) + (((e >> 1) & 1) ? BB : BA)), hi, lo);                          \
         v[e] = __float_as_uint(hi); l[e] = __float_as_uint(lo);                                                          \
         *reinterpret_cast<float *>(act_a + MB6_ACT_OFF(e)) = hi;                                                         \
         *reinterpret_cast<float *>(act_a + Map::ACT_PLANE + MB6_ACT_OFF(e)) = lo;                                        \
@@ -467,15 +533,13 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
             if (live) s_obj += d * d;
             dout[0] = live ? 2.f * d * a.inv_bg : 0.f;
           }
-          // dOut -> DO [row][8] (B of G4) and DO^T [8][rows] (B of dW3), hi/lo
+          // dOut -> fp32 rows [row][8] (E3) and DO^T [8][rows] hi/lo (B of dW3)
           float hi8[8], lo8[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) { db3[j] += dout[j]; tc5::split(dout[j], hi8[j], lo8[j]); }
-          unsigned char *p = smb + Map::DO + g * Map::DO_G + canon(row, 0, 8);
-          *reinterpret_cast<float4 *>(p) = make_float4(hi8[0], hi8[1], hi8[2], hi8[3]);
-          *reinterpret_cast<float4 *>(p + 128) = make_float4(hi8[4], hi8[5], hi8[6], hi8[7]);
-          *reinterpret_cast<float4 *>(p + Map::DO_PLANE) = make_float4(lo8[0], lo8[1], lo8[2], lo8[3]);
-          *reinterpret_cast<float4 *>(p + Map::DO_PLANE + 128) = make_float4(lo8[4], lo8[5], lo8[6], lo8[7]);
+          float4 *p = reinterpret_cast<float4 *>(smb + Map::DO + g * Map::DO_G + row * 32);
+          p[0] = make_float4(dout[0], dout[1], dout[2], dout[3]);
+          p[1] = make_float4(dout[4], dout[5], dout[6], dout[7]);
           unsigned char *pt = smb + Map::DOT + g * Map::DOT_G + canon(0, row, NR);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -484,20 +548,37 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
           }
         }
       }
-      MB6_READY();
-      MB6_WAIT_MMA();
-      MB6_STAMP();   // head + G4 (dh2) done
-      {   // E3: dz2 = dh2 .* act'(h2): [row][feature] -> ACT (B of G5), [feature][rows] -> DZ^T (B of dW2)
-        uint32_t v[8], hh[8], ll[8];
-        MB6_LDX2(v, atom_addr + ZC);
+      asm volatile("bar.sync %0, %1;" ::"r"(NB_EPI + g), "n"(NTE) : "memory");   // dOut rows of this tile are in shared memory
+      MB6_STAMP();   // head done
+      {   // E3: dh2 = dOut W3 (K <= 8, FP32 pipe), dz2 = dh2 .* act'(h2): [row][feature] -> ACT (B of G5), [feature][rows] -> DZ^T (B of dW2)
+        uint32_t hh[8], ll[8];
         MB6_LDX2(hh, atom_addr + ZB);
         MB6_LDX2(ll, atom_addr + H2L);
+        float v[8];
+        const float *dop = reinterpret_cast<const float *>(smb + Map::DO + g * Map::DO_G) + (c0 + rr) * 8;
+#pragma unroll
+        for (int rp = 0; rp < 4; ++rp) {   // this thread's 4 rows: c0 + 8 (rp >> 1) + rr + (rp & 1)  -> elements e = 4 (rp >> 1) + (rp & 1) (+ 2 for fa + 8)
+          const float4 d0 = *reinterpret_cast<const float4 *>(dop + ((rp >> 1) * 8 + (rp & 1)) * 8);
+          float xa = d0.x * w3a[0], xb = d0.x * w3b[0];
+          if (HEAD == 0) {
+            const float4 d1 = *reinterpret_cast<const float4 *>(dop + ((rp >> 1) * 8 + (rp & 1)) * 8 + 4);
+            xa = fmaf(d0.y, w3a[1], xa); xb = fmaf(d0.y, w3b[1], xb);
+            xa = fmaf(d0.z, w3a[2], xa); xb = fmaf(d0.z, w3b[2], xb);
+            xa = fmaf(d0.w, w3a[3], xa); xb = fmaf(d0.w, w3b[3], xb);
+            xa = fmaf(d1.x, w3a[4], xa); xb = fmaf(d1.x, w3b[4], xb);
+            xa = fmaf(d1.y, w3a[5], xa); xb = fmaf(d1.y, w3b[5], xb);
+            xa = fmaf(d1.z, w3a[6], xa); xb = fmaf(d1.z, w3b[6], xb);
+            xa = fmaf(d1.w, w3a[7], xa); xb = fmaf(d1.w, w3b[7], xb);
+          }
+          v[4 * (rp >> 1) + (rp & 1)] = xa;
+          v[4 * (rp >> 1) + (rp & 1) + 2] = xb;
+        }
         MB6_WAIT_LD();
         float hi8[8], lo8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float h2 = __uint_as_float(hh[e]) + __uint_as_float(ll[e]);
-          const float dz = __uint_as_float(v[e]) * act_bwd_from_out(act, h2);
+          const float dz = v[e] * dactf<ACT>(h2);
           if ((e >> 1) & 1) db2b += dz; else db2a += dz;
           tc5::split(dz, hi8[e], lo8[e]);
           *reinterpret_cast<float *>(act_a + MB6_ACT_OFF(e)) = hi8[e];
@@ -522,13 +603,15 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float h1 = __uint_as_float(hh[e]) + __uint_as_float(ll[e]);
-          const float dz = __uint_as_float(v[e]) * act_bwd_from_out(act, h1);
+          const float dz = __uint_as_float(v[e]) * dactf<ACT>(h1);
           if ((e >> 1) & 1) db1b += dz; else db1a += dz;
           float hi, lo;
           tc5::split(dz, hi, lo);
           v[e] = __float_as_uint(hi); ll[e] = __float_as_uint(lo);
         }
         MB6_STX2(atom_addr + ZD, v);
+        tc5::mbar_wait(bar_dw3, (uint32_t)(k & 1));   // dW3 (12 MMAs, issued right behind G5) has read h2 lo: D1L shares its columns
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         MB6_STX2(atom_addr + D1L, ll);
         MB6_WAIT_ST();
       }
@@ -625,6 +708,7 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
   __syncthreads();
   if (w == W_ISSUE) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 #undef MB6_STAMP
+#undef MB6_ISTAMP
 }
 
 #undef MB6_LD16

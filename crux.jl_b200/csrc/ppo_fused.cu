@@ -1840,24 +1840,33 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   } else if (t5k) {   // default: every GEMM on tcgen05, features on the TMEM lanes (mb_t5.cuh), one 256-thread CTA per SM, 64-row tiles
     static bool attr6 = false;
     if (!attr6) {
-      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(mb6::minibatch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb6::Map::TOTAL));
-      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(mb6::minibatch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb6::Map::TOTAL));
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute((mb6::minibatch_kernel<0, CRUX_ACT_TANH>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb6::Map::TOTAL));
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute((mb6::minibatch_kernel<1, CRUX_ACT_TANH>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb6::Map::TOTAL));
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute((mb6::minibatch_kernel<0, CRUX_ACT_RELU>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb6::Map::TOTAL));
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute((mb6::minibatch_kernel<1, CRUX_ACT_RELU>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb6::Map::TOTAL));
       attr6 = true;
     }
     static long long *prof_dev = nullptr;
     if (getenv("CRUX_MB6_PROF")) {
-      if (!prof_dev) CRUX_CHECK_CUDA(ctx, cudaMalloc(&prof_dev, 64 * sizeof(long long)));
-      CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(prof_dev, 0, 64 * sizeof(long long), ctx->stream));
+      if (!prof_dev) CRUX_CHECK_CUDA(ctx, cudaMalloc(&prof_dev, 128 * sizeof(long long)));
+      CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(prof_dev, 0, 128 * sizeof(long long), ctx->stream));
       a.prof = prof_dev;
     }
-    if (head == 0) mb6::minibatch_kernel<0><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
-    else mb6::minibatch_kernel<1><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
+    const bool tanh_act = mlp->acts[0] == CRUX_ACT_TANH;   // the activation is a compile-time parameter: branch-free epilogues
+    if (head == 0 && tanh_act) mb6::minibatch_kernel<0, CRUX_ACT_TANH><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
+    else if (head == 0) mb6::minibatch_kernel<0, CRUX_ACT_RELU><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
+    else if (tanh_act) mb6::minibatch_kernel<1, CRUX_ACT_TANH><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
+    else mb6::minibatch_kernel<1, CRUX_ACT_RELU><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
     if (a.prof) {
-      long long h[64];
+      long long h[128];
       CRUX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       CRUX_CHECK_CUDA(ctx, cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
       fprintf(stderr, "mb6 prof head=%d bm=%lld:", head, (long long)bm);
       for (int k = 1; k < 64 && h[k]; ++k) fprintf(stderr, " %lld", h[k] - h[k - 1]);
+      fprintf(stderr, "\nmb6 abs E:");
+      for (int k = 0; k < 64 && h[k]; ++k) fprintf(stderr, " %lld", h[k] - h[0]);
+      fprintf(stderr, "\nmb6 abs I:");
+      for (int k = 64; k < 128 && h[k]; ++k) fprintf(stderr, " %lld", h[k] - h[0]);
       fprintf(stderr, "\n");
     }
   } else if (tc5k) {
