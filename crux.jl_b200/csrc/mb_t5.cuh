@@ -45,6 +45,7 @@ constexpr int TMEM_COLS = 512;
 constexpr uint32_t ZA = 0, H1L = 32, ZB = 64, H2L = 96, D1L = H2L, ZC = 128, ZD = ZC, OUTC = ZC, DW2C = 160, DW1C = 224, DW3C = 248;
 constexpr uint32_t W2A_HI = 256, W2A_LO = 320, W2TA_HI = 384, W2TA_LO = 448;
 constexpr int ACT_LBO = 144, ACT_SBO = 2320;   // padded K-major tile: the [row][feature] stores of a warp hit 32 distinct banks
+constexpr int STG_SPLIT = 4 * ACT_SBO * 2 / 4;   // floats of a group's ACT buffer: the first piece of its staged partial gradient (the rest: its DZ^T buffer)
 
 struct Map {   // bytes; every operand is a pair of planes hi | lo
   static constexpr int W1A = 0;                                  // A [64 j][24 i]   = W1(j,i)
@@ -219,8 +220,10 @@ __device__ __forceinline__ float tanh_t5(float x) {
 template <int ACT> __device__ __forceinline__ float actf(float z) { return ACT == CRUX_ACT_TANH ? tanh_t5(z) : fmaxf(z, 0.0f); }
 template <int ACT> __device__ __forceinline__ float dactf(float y) { return ACT == CRUX_ACT_TANH ? fmaf(-y, y, 1.0f) : (y > 0.0f ? 1.0f : 0.0f); }
 
+// 80 registers per thread: 640 x 80 leaves 14 k registers (and 70 KB of shared memory) on the SM for the 256-thread CTAs of the OTHER
+// network's update tail (reduce_adam_kernel), which would otherwise wait for this kernel to drain
 template <int HEAD, int ACT>
-__global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
+__global__ void __maxnreg__(80) minibatch_kernel(MbArgs a) {
   extern __shared__ __align__(1024) unsigned char smb[];
   const NetDesc nd = a.net;
   const int I = nd.I, O = nd.O;
@@ -232,6 +235,7 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
 #define MB6_STAMP() do { if (a.prof && blockIdx.x == 0 && t == 0 && prof_n < 64) a.prof[prof_n++] = clock64(); } while (0)
 #define MB6_ISTAMP() do { if (a.prof && blockIdx.x == 0 && w == W_ISSUE && lane == 0 && prof_n < 64) a.prof[64 + prof_n++] = clock64(); } while (0)
   MB6_STAMP();
+  if (a.trace && t == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); a.trace[2 * blockIdx.x] = gt_; }
   const int stop_at = a.ctl ? a.ctl[1] : 0;
   const uint32_t bar_par = smem_u32(smb + Map::BAR);
   const uint32_t bar_mma = smem_u32(smb + Map::BAR + 8 + 48 * g), bar_g = bar_mma + 8, bar_free = bar_mma + 24, bar_dw3 = bar_mma + 40;   // bar_g[2], bar_free[2]
@@ -623,11 +627,14 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
 
     // ---------------- publish this GROUP's partial gradient (layout of fused_minibatch_kernel): partial row 2 blockIdx + g.
     // 32x32b accesses of the whole quarter; the lanes of this group's data-path half hold its accumulators (lane -> feature 16 q + lane % 16)
-    float *out = a.partials + (2 * (int64_t)blockIdx.x + g) * a.pstride;
+    // The partial is staged in this group's own (now dead) ACT and DZ^T buffers; after the CTA-wide barrier below all threads add the two
+    // groups' vectors and store ONE coalesced row per CTA (half the rows for the reduction that follows, no strided global stores).
+    float *stg_a = reinterpret_cast<float *>(smb + Map::ACT + g * Map::ACT_G), *stg_b = reinterpret_cast<float *>(smb + Map::DZT + g * Map::DZT_G) - STG_SPLIT;
+#define out(idx) (*((idx) < STG_SPLIT ? stg_a + (idx) : stg_b + (idx)))
     const bool mine = (lane >> 4) == g;
     const int f = 16 * q + (lane & 15);
     if (!any) {   // this group had no tile (odd tile count): publish zeros
-      for (int e = t - g * NTE; e < a.n_params + 16; e += NTE) out[e] = 0.f;
+      for (int e = t - g * NTE; e < a.n_params + 16; e += NTE) out(e) = 0.f;
     } else {
       {   // dW2^T [i = f lanes][o columns]: this warp's half of the columns, 32 contiguous floats per thread
         uint32_t v[16], v2[16];
@@ -635,11 +642,11 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
         MB6_LD16(v2, quad_addr + DW2C + 32 * ch + 16);
         MB6_WAIT_LD();
         if (mine) {
-          float4 *dst = reinterpret_cast<float4 *>(out + off_W2(I) + f * H + 32 * ch);   // off_W2 = 64 (I + 1), pstride % 32 == 0: 16-byte aligned
+          const int base = off_W2(I) + f * H + 32 * ch;   // multiple of 4, like STG_SPLIT: a float4 never straddles the two staging pieces
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            dst[j4] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]), __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
-            dst[4 + j4] = make_float4(__uint_as_float(v2[4 * j4]), __uint_as_float(v2[4 * j4 + 1]), __uint_as_float(v2[4 * j4 + 2]), __uint_as_float(v2[4 * j4 + 3]));
+            *reinterpret_cast<float4 *>(&out(base + 4 * j4)) = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]), __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
+            *reinterpret_cast<float4 *>(&out(base + 16 + 4 * j4)) = make_float4(__uint_as_float(v2[4 * j4]), __uint_as_float(v2[4 * j4 + 1]), __uint_as_float(v2[4 * j4 + 2]), __uint_as_float(v2[4 * j4 + 3]));
           }
         }
       }
@@ -650,9 +657,9 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
         MB6_WAIT_LD();
         if (mine) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (j < I) out[j * H + f] = __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j) if (j < I) out(j * H + f) = __uint_as_float(v[j]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) if (16 + j < I) out[(16 + j) * H + f] = __uint_as_float(v2[j]);
+          for (int j = 0; j < 8; ++j) if (16 + j < I) out((16 + j) * H + f) = __uint_as_float(v2[j]);
         }
       } else {         // dW3^T [k = f lanes][o columns]
         uint32_t v[8];
@@ -660,7 +667,7 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
         MB6_WAIT_LD();
         if (mine) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) if (j < O) out[off_W3(I) + f * O + j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 8; ++j) if (j < O) out(off_W3(I) + f * O + j) = __uint_as_float(v[j]);
         }
       }
     }
@@ -688,24 +695,37 @@ __global__ void __launch_bounds__(NTH, 1) minibatch_kernel(MbArgs a) {
     }
     asm volatile("bar.sync %0, %1;" ::"r"(NB_EPI + g), "n"(NTE) : "memory");
     const int te = t - g * NTE;
-    if (te < 64) out[off_b1(I) + te] = red[te] + red[64 + te];
-    else if (te < 128) { const int j = te - 64; out[off_b2(I) + j] = red[128 + j] + red[192 + j]; }
-    else if (te < 128 + O) { const int o = te - 128; out[off_b3(I, O) + o] = hred[16 + o] + hred[24 + 16 + o]; }
+    if (te < 64) { const float v = red[te] + red[64 + te]; out(off_b1(I) + te) = v; if (a.nan_flag && v != v) atomicOr(a.nan_flag, 1); }
+    else if (te < 128) { const int j = te - 64; const float v = red[128 + j] + red[192 + j]; out(off_b2(I) + j) = v; if (a.nan_flag && v != v) atomicOr(a.nan_flag, 1); }
+    else if (te < 128 + O) { const int o = te - 128; out(off_b3(I, O) + o) = hred[16 + o] + hred[24 + 16 + o]; }
     else if (te >= 160 && te < 176) {
       // tail layout: [n_params .. +8) = dlogΣ, [n_params+8 .. +16) = obj, kl, clip, adv, ret, 0, 0, 0
       const int kk = te - 160, src = kk < 8 ? 8 + kk : kk - 8;
       float v = 0.f;
       if (src < 5 || (src >= 8 && src < 16)) v = hred[src] + hred[24 + src];
-      out[a.n_params + kk] = v;
+      if (HEAD == 0 && kk == 14 && blockIdx.x == 0 && g == 0) {   // sum(logΣ) as this kernel saw it: the entropy of the info record (policies.jl:348)
+        v = 0.f;
+        for (int j = 0; j < O; ++j) v += bias[8 + j];
+      }
+      out(a.n_params + kk) = v;
+      if (a.nan_flag && v != v) atomicOr(a.nan_flag, 1);
     }
     MB6_STAMP();   // partial gradient published
 #undef MB6_READY
 #undef MB6_WAIT_MMA
 #undef MB6_HIDDEN_EPILOGUE
 #undef MB6_ACT_OFF
+#undef out
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  {   // group 0's vector + group 1's vector -> this CTA's partial row
+    const float *a0 = reinterpret_cast<const float *>(smb + Map::ACT), *b0 = reinterpret_cast<const float *>(smb + Map::DZT) - STG_SPLIT;
+    const float *a1 = reinterpret_cast<const float *>(smb + Map::ACT + Map::ACT_G), *b1 = reinterpret_cast<const float *>(smb + Map::DZT + Map::DZT_G) - STG_SPLIT;
+    float *row = a.partials + (int64_t)blockIdx.x * a.pstride;
+    for (int e = t; e < a.n_params + 16; e += NTH) row[e] = (e < STG_SPLIT ? a0[e] : b0[e]) + (e < STG_SPLIT ? a1[e] : b1[e]);
+  }
+  if (a.trace && t == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); a.trace[2 * blockIdx.x + 1] = gt_; }
   if (w == W_ISSUE) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 #undef MB6_STAMP
 #undef MB6_ISTAMP

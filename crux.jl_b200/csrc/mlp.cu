@@ -423,7 +423,7 @@ int32_t crux_mlp_create(crux_ctx *ctx, int32_t n_layers, const int32_t *dims, co
   // params is padded: the fused kernels stage it with a 16-byte-granular TMA bulk copy
   if (cudaMalloc((void **)&m->params, bytes + 64) != cudaSuccess || cudaMalloc((void **)&m->grads, gbytes) != cudaSuccess ||
       cudaMalloc((void **)&m->m, bytes) != cudaSuccess || cudaMalloc((void **)&m->v, bytes) != cudaSuccess ||
-      cudaMalloc((void **)&m->step_dev, sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void **)&m->step_dev, 4 * sizeof(int)) != cudaSuccess ||   // [0] Adam steps, [1] ticket, [2] NaN seen (ppo_fused.cu reduce_adam_kernel)
       cudaMalloc((void **)&m->norm_part, 1024 * sizeof(double)) != cudaSuccess) {
     crux_mlp_destroy(m);
     return crux_set_err(ctx, CRUX_ERR_OOM, "crux_mlp_create: cudaMalloc failed");
@@ -432,7 +432,8 @@ int32_t crux_mlp_create(crux_ctx *ctx, int32_t n_layers, const int32_t *dims, co
   cudaMemsetAsync(m->grads, 0, gbytes, ctx->stream);
   cudaMemsetAsync(m->m, 0, bytes, ctx->stream);
   cudaMemsetAsync(m->v, 0, bytes, ctx->stream);
-  cudaMemsetAsync(m->step_dev, 0, sizeof(int), ctx->stream);
+  cudaMemsetAsync(m->step_dev, 0, 4 * sizeof(int), ctx->stream);
+  cudaMemsetAsync(m->norm_part, 0, 1024 * sizeof(double), ctx->stream);   // incl. the β-power cache of the fused PPO tails (ppo_fused.cu)
   *out = m;
   return CRUX_OK;
 }
@@ -481,7 +482,7 @@ int32_t crux_mlp_set_adam(crux_mlp *m, double eta, double beta1, double beta2, d
   const size_t bytes = (size_t)m->n_params * sizeof(float);
   CRUX_CHECK_CUDA(m->ctx, cudaMemsetAsync(m->m, 0, bytes, m->ctx->stream));
   CRUX_CHECK_CUDA(m->ctx, cudaMemsetAsync(m->v, 0, bytes, m->ctx->stream));
-  CRUX_CHECK_CUDA(m->ctx, cudaMemsetAsync(m->step_dev, 0, sizeof(int), m->ctx->stream));
+  CRUX_CHECK_CUDA(m->ctx, cudaMemsetAsync(m->step_dev, 0, 4 * sizeof(int), m->ctx->stream));
   return CRUX_OK;
 }
 

@@ -22,6 +22,7 @@
 // Bound: fp32 FFMA (SIMT).  1e-5 parity with the fp32 reference excludes TF32/BF16 tensor-core MMA for these layers.
 #include "policy.cuh"
 #include <stdlib.h>
+#include <vector>
 
 namespace {
 
@@ -499,6 +500,8 @@ struct MbArgs {
   int mb;           // index of this minibatch in the update
   const float *planes;   // mb_t5.cuh: the network's weight planes (crux_mlp::frag in plane mode)
   long long *prof;       // CRUX_MB6_PROF=1: clock64 at the phase boundaries of CTA 0 (development aid)
+  int *nan_flag;         // mb_t5.cuh: raised when a published partial holds a NaN (reduce_adam_kernel skips the update: training.jl:20)
+  unsigned long long *trace;   // CRUX_MB6_TRACE=1: %globaltimer at the start / end of every CTA: [gridDim.x][2] (development aid)
 };
 // a minibatch is skipped when an EARLIER minibatch raised the stop flag (rl/ppo.jl:59 via training.jl:46,49)
 __device__ __forceinline__ bool stopped(const int *ctl, int mb) { return ctl && ctl[1] != 0 && ctl[1] <= mb; }
@@ -1288,6 +1291,18 @@ __global__ void __launch_bounds__(NT, 2) fused_forward_tc_kernel(FwdTcArgs a) {
 // `train!` tail (training.jl:18-23) + the loss bookkeeping of the minibatch, one launch:
 //   gnorm = ||all grads||_2 (every CTA recomputes it, identical order -> identical value), NaN -> sticky error flag and no update,
 //   info record (block 0), KL early-stop vote (block 0), Flux Adam on this CTA's slice of the parameters.
+// Flux's Adam keeps the β-powers as state and multiplies them by β after every step (βp .*= β, [3P] Optimise.Adam); `pow(β, t)` in
+// double precision costs a single thread ~10 us on this part (hundreds of dependent FP64 instructions) and sat on the critical path of
+// every update tail.  The powers of the last step are cached behind the gradient-norm partials: cache = {t, β1^t, β2^t}.
+constexpr int BETA_CACHE = 1021;   // doubles [1021, 1024) of crux_mlp::norm_part
+__device__ __forceinline__ void beta_pows(const double *cache, int t, double b1, double b2, double &p1, double &p2) {
+  const int ct = (int)__ldcg(cache);
+  if (ct == t) { p1 = __ldcg(cache + 1); p2 = __ldcg(cache + 2); }
+  else if (ct == t - 1 && t > 1) { p1 = __ldcg(cache + 1) * b1; p2 = __ldcg(cache + 2) * b2; }
+  else { p1 = pow(b1, (double)t); p2 = pow(b2, (double)t); }
+}
+__device__ __forceinline__ void beta_cache_store(double *cache, int t, double p1, double p2) { cache[1] = p1; cache[2] = p2; cache[0] = (double)t; }
+
 struct AdamArgs {
   float *p, *g, *m, *v; int n;                       // network parameters
   float *ls, *ls_g, *ls_m, *ls_v; int A;             // actor only: logΣ vector (A == 0 for a critic)
@@ -1298,6 +1313,7 @@ struct AdamArgs {
   int a2c, head;                                     // head 0: actor (ppo/a2c), 1: critic (mse)
   float *rec;                                        // info record of this minibatch
   const double *norm_part; int n_norm_part;          // per-CTA sums of squares from the reduce kernel (NULL: recompute)
+  const double *beta_cache;                          // {t, β1^t, β2^t} of the step the reduce kernel has just counted
   // fused gradient all-reduce over NVLink peer memory (LL protocol): the gradient is the rank-ordered sum of the 8-byte words
   // {value, sequence number} every rank's reduce kernel stored into THIS rank's receive region of this network (double-buffered by
   // the parity of the device-resident sequence number); the last CTA of the Adam kernel advances the sequence number
@@ -1306,6 +1322,7 @@ struct AdamArgs {
   int *ctl; int mb;
   unsigned int *err_flags;
   float *frag; int fI, fO;                           // fragment buffer of the network (NULL: none) and its input / output widths
+  unsigned long long *trace;                         // development aid (CRUX_MB6_TRACE): [0] first CTA start, [1] last CTA end
   int frag_mode;                                     // 0: MMA B-fragment order (mma.sync kernel), 1: tcgen05 hi/lo weight planes (mb_t5.cuh)
 };
 __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int n_blocks);
@@ -1384,7 +1401,13 @@ __global__ void __launch_bounds__(RW * 32, FUSE ? 1 : 2) reduce_fused_partials_k
     __syncthreads();   // sh is reused by the next group
   }
   if (!FUSE || !fuse_adam) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      const int t = *step_dev + 1;
+      double p1, p2;
+      beta_pows(norm_part + BETA_CACHE, t, adam.b1, adam.b2, p1, p2);
+      beta_cache_store(norm_part + BETA_CACHE, t, p1, p2);
+      *step_dev = t;
+    }
     return;
   }
   // single GPU: no all-reduce follows, so the LAST CTA to finish runs the norm / record / Adam tail right here (one launch less)
@@ -1393,7 +1416,14 @@ __global__ void __launch_bounds__(RW * 32, FUSE ? 1 : 2) reduce_fused_partials_k
   __syncthreads();
   if (threadIdx.x == 0) {
     last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
-    if (last) { *ticket = 0u; *step_dev += 1; }
+    if (last) {
+      *ticket = 0u;
+      const int t = *step_dev + 1;
+      double p1, p2;
+      beta_pows(norm_part + BETA_CACHE, t, adam.b1, adam.b2, p1, p2);
+      beta_cache_store(norm_part + BETA_CACHE, t, p1, p2);
+      *step_dev = t;
+    }
   }
   __syncthreads();
   if (!last) return;
@@ -1445,8 +1475,10 @@ __device__ __forceinline__ void adam_body(const AdamArgs &a, int block_rank, int
     for (int q = 0; q < nw; ++q) t += sh[q];
     s_n2 = t;
     const int step = *a.step_dev;  // counts this step (incremented by the reduce kernel)
-    s_c1 = 1.0 - pow(a.b1, (double)step);
-    s_c2 = 1.0 - pow(a.b2, (double)step);
+    double p1, p2;
+    beta_pows(a.beta_cache, step, a.b1, a.b2, p1, p2);
+    s_c1 = 1.0 - p1;
+    s_c2 = 1.0 - p2;
   }
   __syncthreads();
   const double n2 = s_n2;
@@ -1572,8 +1604,10 @@ __global__ void __launch_bounds__(256) fused_adam_ll_kernel(AdamArgs a, double *
     for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(norm_slots + b);
     s_n2 = t;
     const int step = *a.step_dev;  // counts this step (incremented by the reduce kernel)
-    s_c1 = 1.0 - pow(a.b1, (double)step);
-    s_c2 = 1.0 - pow(a.b2, (double)step);
+    double p1, p2;
+    beta_pows(a.beta_cache, step, a.b1, a.b2, p1, p2);
+    s_c1 = 1.0 - p1;
+    s_c2 = 1.0 - p2;
   }
   __syncthreads();
   const double n2 = s_n2;
@@ -1620,6 +1654,131 @@ __global__ void __launch_bounds__(256) fused_adam_ll_kernel(AdamArgs a, double *
     const float vt = (float)(a.b2 * (double)a.ls_v[tid] + (1.0 - a.b2) * g * g);
     a.ls_m[tid] = mt; a.ls_v[tid] = vt;
     a.ls[tid] = a.ls[tid] - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
+  }
+}
+
+// Single-GPU tail of a t5 minibatch in ONE launch: per-CTA partials -> gradient (double accumulation, fixed order) -> Flux Adam on the
+// 32 entries the CTA has just finished -> plane scatter; the last CTA to finish (ticket) adds the per-CTA sums of squares in a fixed
+// order and writes the info record / KL vote / NaN flag.  Why it matters: the minibatch kernel leaves no room on an SM for another
+// CTA (640 threads x 96 registers), so the tail of one network cannot hide behind the other network's minibatch kernel -- the GPU
+// idles for the whole reduce -> Adam chain (measured with %globaltimer, scripts/mb6_trace.py: 17 us per minibatch pair with two
+// launches).  Adam itself does not need the gradient norm (train! only logs it, training.jl:18-23); the reference's "NaN -> error
+// BEFORE the update" is kept through a NaN flag the minibatch kernel raises while publishing its partials (state[2]).
+// state: [0] Adam steps applied, [1] ticket, [2] NaN seen in a partial.
+// RWT = 8 warps: a 256-thread CTA at <= 56 registers fits NEXT TO a resident minibatch CTA (640 threads x 80 registers, 157 KB), so that
+// the tail of one network runs under the other network's minibatch kernel instead of after it.
+template <int RWT>
+__global__ void __launch_bounds__(RWT * 32, 4) reduce_adam_kernel(const float *__restrict__ partials, int nparts, int pstride, int n_params,
+                                                                 float *__restrict__ grads, float count, float ls_shift, int n_ls,
+                                                                 double *__restrict__ norm_part, int *__restrict__ state, AdamArgs a) {
+  if (stopped(a.ctl, a.mb)) return;
+  if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); a.trace[0] = gt_; }
+  __shared__ double sh[RWT][33];
+  __shared__ double s_c1, s_c2;
+  __shared__ int s_bad;
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n_groups = (n_params + 16 + 31) / 32;
+  // warp 0 owns the finished entries: its optimiser state is requested NOW, so that the loads fly under the reduction
+  float pm = 0.f, pv = 0.f, pp = 0.f;
+  float *ap = nullptr, *am = nullptr, *av = nullptr;
+  if (w == 0 && blockIdx.x < n_groups) {
+    const int p = blockIdx.x * 32 + lane;
+    if (p < n_params) { ap = a.p + p; am = a.m + p; av = a.v + p; }
+    else if (p < n_params + n_ls) { const int j = p - n_params; ap = a.ls + j; am = a.ls_m + j; av = a.ls_v + j; }
+    if (ap) { pp = __ldcg(ap); pm = __ldcg(am); pv = __ldcg(av); }
+  }
+  if (threadIdx.x == 0) {
+    const int step = state[0] + 1;   // this step (the counter and the β-power cache are advanced by the last CTA, after every CTA has read them)
+    double p1, p2;
+    beta_pows(norm_part + BETA_CACHE, step, a.b1, a.b2, p1, p2);
+    s_c1 = 1.0 - p1;
+    s_c2 = 1.0 - p2;
+    s_bad = state[2];
+  }
+  __syncthreads();
+  const bool bad = s_bad != 0;
+  const double c1 = s_c1, c2 = s_c2;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int p = grp * 32 + lane;
+    double s = 0.0;
+    if (p < n_params + 16) {
+      const float *src = partials + p;
+#pragma unroll 10
+      for (int c = w; c < nparts; c += RWT) s += (double)__ldcg(src + (int64_t)c * pstride);
+    }
+    sh[w][lane] = s;
+    __syncthreads();
+    if (w == 0) {
+      double sq = 0.0;
+      if (p < n_params + 16) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < RWT; ++q) t += sh[q][lane];
+        float g = (float)t;
+        if (p >= n_params && p < n_params + n_ls) g += ls_shift;
+        if (p < n_params + 8) {
+          grads[p] = g;
+          if (p < n_params + n_ls) sq = (double)g * (double)g;
+        } else {
+          const int q = p - n_params - 8;   // obj, kl, clip, adv, ret | count | sum(logΣ) BEFORE this update (published by CTA 0 of the minibatch kernel)
+          if (q < 5 || q == 6) grads[n_params + 64 + q] = g;
+          else if (q == 5) grads[n_params + 64 + 5] = count;
+        }
+        if (!bad && p < n_params + n_ls) {   // Flux Adam on this entry (float32 moments, Float64 scalars)
+          if (grp != (int)blockIdx.x) {      // grid-strided launch (never the case today): state not prefetched
+            if (p < n_params) { ap = a.p + p; am = a.m + p; av = a.v + p; } else { const int j = p - n_params; ap = a.ls + j; am = a.ls_m + j; av = a.ls_v + j; }
+            pp = __ldcg(ap); pm = __ldcg(am); pv = __ldcg(av);
+          }
+          const double gd = (double)g;
+          const float mt = (float)(a.b1 * (double)pm + (1.0 - a.b1) * gd);
+          const float vt = (float)(a.b2 * (double)pv + (1.0 - a.b2) * gd * gd);
+          *am = mt; *av = vt;
+          const float pn = pp - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
+          *ap = pn;
+          if (a.frag && p < n_params) { if (a.frag_mode) mb6::plane_scatter(a.frag, a.fI, a.fO, p, pn); else frag_scatter(a.frag, a.fI, a.fO, p, pn); }
+        }
+      }
+      sq = warp_sum_d(sq);
+      if (lane == 0) norm_part[grp] = sq;
+    }
+    __syncthreads();   // sh is reused by the next group
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<unsigned int *>(state + 1), 1u) == gridDim.x - 1u;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (w == 0) {   // ||g||^2: lane l adds groups l, l + 32, ... in order, the 32 lane sums are combined by a fixed shuffle tree: bit-reproducible
+    double t = 0.0;
+    for (int q = lane; q < n_groups; q += 32) t += __ldcg(norm_part + q);
+    t = warp_sum_d(t);
+    if (lane == 0) {
+      beta_cache_store(norm_part + BETA_CACHE, state[0] + 1, 1.0 - s_c1, 1.0 - s_c2);
+      state[0] += 1; state[1] = 0; state[2] = 0;
+      const double n2 = t;
+      const float *sums = grads + n_params + 64;
+      const float cnt = count;
+      if (a.head == 0) {
+        const float entropy = 1.4189385332046727f + __ldcg(sums + 6);   // policies.jl:348, logΣ as the minibatch kernel saw it
+        const float p_loss = -(__ldcg(sums + 0) / cnt);
+        a.rec[CRUX_PPO_LOSS] = a.lambda_p * p_loss + a.lambda_e * (-entropy);
+        a.rec[CRUX_PPO_ENTROPY] = entropy;
+        const float kl = __ldcg(sums + 1) / cnt;
+        a.rec[CRUX_PPO_KL] = kl;
+        a.rec[CRUX_PPO_CLIP_FRAC] = a.a2c ? 0.f : __ldcg(sums + 2) / cnt;
+        a.rec[CRUX_PPO_AVG_ADV] = __ldcg(sums + 3) / cnt;
+        a.rec[CRUX_PPO_AVG_RET] = __ldcg(sums + 4) / cnt;
+        if (a.ctl && kl > a.target_kl) a.ctl[1] = a.mb + 1;         // this minibatch is still applied; later ones are skipped
+      } else {
+        a.rec[CRUX_PPO_LOSS] = __ldcg(sums + 0) / cnt;
+      }
+      a.rec[CRUX_PPO_GRAD_NORM] = (float)sqrt(n2);
+      a.rec[CRUX_PPO_VALID] = 1.f;
+      if (bad || isnan(n2)) atomicOr(a.err_flags, CRUX_FLAG_NAN);   // training.jl:20: error before Flux.update!
+      if (a.trace) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); a.trace[1] = gt_; }
+    }
   }
 }
 
@@ -1813,7 +1972,7 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   const bool tc5_grid = !big && !no_mma() && mb5_env0 && mb5_env0[0] == '1' && mlp->dims[0] <= mb5::KX && mlp->dims[3] <= 8;
   const bool t5k = minibatch_kernel_is_t5(mlp) && !big;
   const int grid = big ? (int)i64min(cdiv(bm, RB), (int64_t)ctx->num_sms)
-                       : t5k ? (int)i64min(cdiv(cdiv(bm, mb6::NR), 2), (int64_t)ctx->num_sms)
+                       : t5k ? (int)i64min(cdiv(cdiv(bm, mb6::NR), 2), (int64_t)(getenv("CRUX_MB_HALF") ? ctx->num_sms / 2 : ctx->num_sms))
                        : tc5_grid ? (int)i64min(cdiv(bm, mb5::TR), (int64_t)ctx->num_sms) : (int)i64min(cdiv(bm, R), (int64_t)sms * 2);
   const int pstride = (int)((mlp->n_params + 16 + 31) / 32 * 32);
   const size_t need = (size_t)ctx->num_sms * 2 * pstride * sizeof(float);
@@ -1831,7 +1990,7 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   const bool tc5k = !big && !no_mma() && mb5_env && mb5_env[0] == '1' && mlp->dims[0] <= mb5::KX && mlp->dims[3] <= 8;
   const bool tc = !big && !tc5k && !t5k && !no_mma() && mlp->frag;   // mma.sync kernel: stages the fragment buffer instead of the raw parameters
   if (tc) { a.net.params = mlp->frag; a.net.bytes16 = (uint32_t)(Frag::TOTAL * sizeof(float)); }
-  if (t5k) a.planes = mlp->frag;
+  if (t5k) { a.planes = mlp->frag; a.nan_flag = mlp->step_dev + 2; }
   {
   CruxTimed timed(ctx, CRUX_T_MINIBATCH);
   if (big) {
@@ -1840,6 +1999,8 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   } else if (t5k) {   // default: every GEMM on tcgen05, features on the TMEM lanes (mb_t5.cuh), one 256-thread CTA per SM, 64-row tiles
     static bool attr6 = false;
     if (!attr6) {
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute((mb6::minibatch_kernel<0, CRUX_ACT_TANH>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute((mb6::minibatch_kernel<1, CRUX_ACT_TANH>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute((mb6::minibatch_kernel<0, CRUX_ACT_TANH>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb6::Map::TOTAL));
       CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute((mb6::minibatch_kernel<1, CRUX_ACT_TANH>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb6::Map::TOTAL));
       CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute((mb6::minibatch_kernel<0, CRUX_ACT_RELU>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mb6::Map::TOTAL));
@@ -1851,6 +2012,26 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
       if (!prof_dev) CRUX_CHECK_CUDA(ctx, cudaMalloc(&prof_dev, 128 * sizeof(long long)));
       CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(prof_dev, 0, 128 * sizeof(long long), ctx->stream));
       a.prof = prof_dev;
+    }
+    static unsigned long long *trace_dev = nullptr;
+    static int trace_n = 0;
+    if (getenv("CRUX_MB6_TRACE")) {
+      if (!trace_dev) { CRUX_CHECK_CUDA(ctx, cudaMalloc(&trace_dev, 256 * 160 * 2 * sizeof(unsigned long long))); CRUX_CHECK_CUDA(ctx, cudaMemset(trace_dev, 0, 256 * 160 * 2 * sizeof(unsigned long long))); }
+      if (trace_n < 256) a.trace = trace_dev + (size_t)(trace_n++) * 160 * 2;
+      if (trace_n == 192) {   // dump once: per launch the first / last CTA start and first / last CTA end, in us from the first start
+        std::vector<unsigned long long> h(192 * 160 * 2);
+        CRUX_CHECK_CUDA(ctx, cudaDeviceSynchronize());
+        CRUX_CHECK_CUDA(ctx, cudaMemcpy(h.data(), trace_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ULL;
+        for (int L = 128; L < 191; ++L) for (int c = 0; c < 148; ++c) if (h[(L * 160 + c) * 2]) t0 = t0 < h[(L * 160 + c) * 2] ? t0 : h[(L * 160 + c) * 2];
+        for (int L = 128; L < 191; ++L) {
+          unsigned long long s0 = ~0ULL, s1 = 0, e0 = ~0ULL, e1 = 0; int n = 0;
+          for (int c = 0; c < 148; ++c) { const unsigned long long a0 = h[(L * 160 + c) * 2], a1 = h[(L * 160 + c) * 2 + 1]; if (!a0) continue; ++n;
+            s0 = s0 < a0 ? s0 : a0; s1 = s1 > a0 ? s1 : a0; e0 = e0 < a1 ? e0 : a1; e1 = e1 > a1 ? e1 : a1; }
+          fprintf(stderr, "trace launch %3d ctas %3d: start %8.2f .. %8.2f  end %8.2f .. %8.2f us   tail %8.2f .. %8.2f\n", L, n, (s0 - t0) * 1e-3, (s1 - t0) * 1e-3, (e0 - t0) * 1e-3, (e1 - t0) * 1e-3,
+                  (h[(L * 160 + 150) * 2] - t0) * 1e-3, (h[(L * 160 + 150) * 2 + 1] - t0) * 1e-3);
+        }
+      }
     }
     const bool tanh_act = mlp->acts[0] == CRUX_ACT_TANH;   // the activation is a compile-time parameter: branch-free epilogues
     if (head == 0 && tanh_act) mb6::minibatch_kernel<0, CRUX_ACT_TANH><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
@@ -1887,7 +2068,7 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   }
   }
   CRUX_LAUNCHED(ctx);
-  const int nparts = t5k ? 2 * grid : grid;   // mb_t5.cuh: each CTA runs two pipelines, each publishes its own partial
+  const int nparts = grid;
   const int n_out = (int)mlp->n_params + 16;
   const int rblocks = (n_out + 31) / 32;   // <= 1024 doubles of norm_part (n_params <= 6792)
   const int rgrid = reserve > 0 ? (int)i64min(rblocks, 2 * reserve) : rblocks;   // two 1024-thread CTAs per reserved SM
@@ -1897,6 +2078,8 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   g.p = mlp->params; g.g = mlp->grads; g.m = mlp->m; g.v = mlp->v; g.n = (int)mlp->n_params;
   if (head == 0) { g.ls = actor->log_sigma; g.ls_g = tail_ls_grad(mlp); g.ls_m = actor->ls_m; g.ls_v = actor->ls_v; g.A = actor->adim; }
   g.lambda_e = hp->lambda_e;
+  g.beta_cache = mlp->norm_part + BETA_CACHE;
+  g.trace = a.trace ? a.trace + 2 * 150 : nullptr;
   g.sums = tail_sums(mlp); g.eta = mlp->eta; g.b1 = mlp->beta1; g.b2 = mlp->beta2; g.eps = mlp->eps; g.step_dev = mlp->step_dev;
   g.lambda_p = hp->lambda_p; g.target_kl = hp->target_kl; g.a2c = hp->a2c; g.head = head; g.rec = rec; g.ctl = ctl; g.mb = mb;
   g.err_flags = ctx->flags_dev;
@@ -1919,6 +2102,19 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
     for (int q = 0; q < ctx->world; ++q) po.ll[q] = ctx->peer_ll_remote[q] + net_off;
     g.peer = 1; g.world = ctx->world; g.peer_cap = ctx->peer_cap; g.ll_recv = ctx->peer_ll + net_off;
     g.ll_seq = ctx->peer_flags + 40 + head; g.ll_ticket = reinterpret_cast<unsigned int *>(ctx->peer_flags + 48 + head);
+  }
+  static const bool no_fused_tail = getenv("CRUX_NO_FUSED_TAIL") != nullptr;
+  if (t5k && ctx->world == 1 && !no_fused_tail) {   // single GPU: reduce + Adam + record in ONE launch (reduce_adam_kernel)
+    static bool carve = false;
+    if (!carve) {   // same shared-memory carve-out as the minibatch kernel: CTAs of kernels with different carve-outs do not share an SM
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(reduce_adam_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      carve = true;
+    }
+    CruxTimed timed(ctx, CRUX_T_REDUCE);
+    reduce_adam_kernel<8><<<rgrid, 8 * 32, 0, ctx->stream>>>(mlp->partials, nparts, pstride, (int)mlp->n_params, mlp->grads, (float)bm, ls_shift,
+                                                           head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, g);
+    CRUX_LAUNCHED(ctx);
+    return CRUX_OK;
   }
   { CruxTimed timed(ctx, CRUX_T_REDUCE);
   if (fuse_adam)
