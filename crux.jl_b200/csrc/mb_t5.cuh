@@ -236,7 +236,7 @@ __global__ void __maxnreg__(80) minibatch_kernel(MbArgs a) {
 #define MB6_ISTAMP() do { if (a.prof && blockIdx.x == 0 && w == W_ISSUE && lane == 0 && prof_n < 64) a.prof[64 + prof_n++] = clock64(); } while (0)
   MB6_STAMP();
   if (a.trace && t == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); a.trace[2 * blockIdx.x] = gt_; }
-  const int stop_at = a.ctl ? a.ctl[1] : 0;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // this network's tail kernel may be scheduled (it waits for this grid to complete)
   const uint32_t bar_par = smem_u32(smb + Map::BAR);
   const uint32_t bar_mma = smem_u32(smb + Map::BAR + 8 + 48 * g), bar_g = bar_mma + 8, bar_free = bar_mma + 24, bar_dw3 = bar_mma + 40;   // bar_g[2], bar_free[2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + Map::BAR + 112);
@@ -271,6 +271,15 @@ __global__ void __maxnreg__(80) minibatch_kernel(MbArgs a) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  // Everything above and the first tile's gather are independent of the previous Adam step: with a programmatic dependent launch they
+  // run while this network's previous tail kernel is still in flight.  Parameters, planes and the KL-stop flag are read behind the wait.
+  if (w >= 2 * NEW && tile0 < n_tiles) {
+    // the group's FIRST tile is loaded by its issuer + loader warps (64 threads) while the epilogue warps fill tensor memory with W2
+    load_tile<HEAD>(smb, a, I, O, g, 0, tile0, gt - NTE, 64, [&]() { asm volatile("bar.sync %0, %1;" ::"r"(NB_PRO + g), "n"(64) : "memory"); });
+    asm volatile("bar.sync %0, %1;" ::"r"(NB_PRO + g), "n"(64) : "memory");
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int stop_at = a.ctl ? a.ctl[1] : 0;
   const bool skip = stop_at != 0 && stop_at <= a.mb;   // an EARLIER minibatch raised the KL stop flag (rl/ppo.jl:59): nothing to do
   if (t == 0) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_par), "r"((uint32_t)Map::PLANES) : "memory");
@@ -287,12 +296,7 @@ __global__ void __maxnreg__(80) minibatch_kernel(MbArgs a) {
     return;
   }
   if (w >= 2 * NEW) {
-    // the group's FIRST tile is loaded by its issuer + loader warps (64 threads) while the epilogue warps fill tensor memory with W2
-    if (tile0 < n_tiles) {
-      load_tile<HEAD>(smb, a, I, O, g, 0, tile0, gt - NTE, 64, [&]() { asm volatile("bar.sync %0, %1;" ::"r"(NB_PRO + g), "n"(64) : "memory"); });
-      asm volatile("bar.sync %0, %1;" ::"r"(NB_PRO + g), "n"(64) : "memory");
-      if (w >= W_LOAD) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_g) : "memory");   // buffer 0 of this group is ready
-    }
+    if (w >= W_LOAD && tile0 < n_tiles) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_g) : "memory");   // buffer 0 of this group is ready
   } else {   // W2 (A of L2) and W2^T (A of G5) -> tensor memory, hi | lo, replicated in both data-path halves:
     // warp (quarter wq, part) owns lanes [32 wq, +32) (feature m = 16 wq + lane % 16 in either half) x 32 of the 128 K-columns
     const int wq = w & 3, part = w >> 2, m = 16 * wq + (lane & 15);

@@ -1665,12 +1665,14 @@ __global__ void __launch_bounds__(256) fused_adam_ll_kernel(AdamArgs a, double *
 // launches).  Adam itself does not need the gradient norm (train! only logs it, training.jl:18-23); the reference's "NaN -> error
 // BEFORE the update" is kept through a NaN flag the minibatch kernel raises while publishing its partials (state[2]).
 // state: [0] Adam steps applied, [1] ticket, [2] NaN seen in a partial.
-// RWT = 8 warps: a 256-thread CTA at <= 56 registers fits NEXT TO a resident minibatch CTA (640 threads x 80 registers, 157 KB), so that
-// the tail of one network runs under the other network's minibatch kernel instead of after it.
+// RWT = 4 warps: two 128-thread CTAs at <= 56 registers fit NEXT TO a resident minibatch CTA (640 threads x 80 registers, 157 KB), so that
+// the tail of one network runs -- in a single wave -- under the other network's minibatch kernel instead of after it.
 template <int RWT>
-__global__ void __launch_bounds__(RWT * 32, 4) reduce_adam_kernel(const float *__restrict__ partials, int nparts, int pstride, int n_params,
+__global__ void __launch_bounds__(RWT * 32, 8) reduce_adam_kernel(const float *__restrict__ partials, int nparts, int pstride, int n_params,
                                                                  float *__restrict__ grads, float count, float ls_shift, int n_ls,
                                                                  double *__restrict__ norm_part, int *__restrict__ state, AdamArgs a) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next minibatch kernel of this network may start its prologue
+  asm volatile("griddepcontrol.wait;" ::: "memory");                // the minibatch kernel's partials (and its KL-stop flag) are complete
   if (stopped(a.ctl, a.mb)) return;
   if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); a.trace[0] = gt_; }
   __shared__ double sh[RWT][33];
@@ -1943,6 +1945,22 @@ extern "C" int32_t crux_rollout_step_rows_mapped(crux_gaussian *actor, const flo
   return launch_forward(ctx, a, 1);
 }
 
+// Programmatic dependent launch: the kernel may start (its prologue up to griddepcontrol.wait) while the previous kernel of the stream
+// is still running, once that kernel has executed griddepcontrol.launch_dependents (or finished).  Used for the
+// minibatch -> tail -> minibatch chain of one network, whose launch gaps (3 - 4 us each) are otherwise exposed.
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+static bool pdl_enabled() { static const bool on = getenv("CRUX_NO_PDL") == nullptr; return on; }
+
 // CRUX_MB_KERNEL selects the minibatch kernel: "t5" (default: all GEMMs on tcgen05, mb_t5.cuh), "mma" (warp-level mma.sync 3xTF32),
 // "tc5" (= CRUX_MB_TC5=1: row GEMMs on tcgen05, weight gradients on mma.sync), "ffma" (= CRUX_NO_MMA=1)
 static const char *mb_kernel_env() { const char *env = getenv("CRUX_MB_KERNEL"); return env ? env : ""; }   // read per call: tests switch kernels
@@ -1958,7 +1976,7 @@ static bool minibatch_kernel_is_t5(const crux_mlp *mlp) {
 // one minibatch = 3 launches: fused forward/loss/backward -> partial reduction (+ step count) -> [all-reduce] -> norm/record/Adam
 static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const float *s, const float *act, const float *logp_old,
                            const float *adv, const float *ret, const int32_t *order, int64_t bm, const crux_ppo_hp *hp, float *rec,
-                           int *ctl, int mb) {
+                           int *ctl, int mb, bool pdl_ok = false) {
   crux_ctx *ctx = mlp->ctx;
   // 128-row tiles (1 CTA/SM, 8x4 register tiles) measured SLOWER than 2 x 64-row CTAs per SM (occupancy halves; profiles/): opt-in
   const bool big = cdiv(bm, RB) >= (int64_t)ctx->num_sms && getenv("CRUX_RB");
@@ -2034,10 +2052,14 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
       }
     }
     const bool tanh_act = mlp->acts[0] == CRUX_ACT_TANH;   // the activation is a compile-time parameter: branch-free epilogues
-    if (head == 0 && tanh_act) mb6::minibatch_kernel<0, CRUX_ACT_TANH><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
-    else if (head == 0) mb6::minibatch_kernel<0, CRUX_ACT_RELU><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
-    else if (tanh_act) mb6::minibatch_kernel<1, CRUX_ACT_TANH><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
-    else mb6::minibatch_kernel<1, CRUX_ACT_RELU><<<grid, mb6::NTH, mb6::Map::TOTAL, ctx->stream>>>(a);
+    // Measured (scripts/mb6_trace.py): launched as a programmatic dependent of its network's previous tail kernel, the minibatch kernel
+    // takes over every SM as soon as one frees up and then idles at griddepcontrol.wait -- the OTHER network's minibatch kernel waits
+    // behind it (1.40 ms per iteration against 1.34).  Only the small tail kernels use the early launch; CRUX_PDL_MB=1 re-enables it here.
+    static const bool pdl_mb = getenv("CRUX_PDL_MB") != nullptr;
+    const bool pdl = pdl_enabled() && pdl_ok && pdl_mb;   // never for the first minibatch of an epoch: its row order comes from the kernel right before it
+    void (*kern)(MbArgs) = head == 0 ? (tanh_act ? mb6::minibatch_kernel<0, CRUX_ACT_TANH> : mb6::minibatch_kernel<0, CRUX_ACT_RELU>)
+                                     : (tanh_act ? mb6::minibatch_kernel<1, CRUX_ACT_TANH> : mb6::minibatch_kernel<1, CRUX_ACT_RELU>);
+    CRUX_CHECK_CUDA(ctx, launch_pdl(kern, dim3(grid), dim3(mb6::NTH), (size_t)mb6::Map::TOTAL, ctx->stream, pdl, a));
     if (a.prof) {
       long long h[128];
       CRUX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2107,12 +2129,12 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   if (t5k && ctx->world == 1 && !no_fused_tail) {   // single GPU: reduce + Adam + record in ONE launch (reduce_adam_kernel)
     static bool carve = false;
     if (!carve) {   // same shared-memory carve-out as the minibatch kernel: CTAs of kernels with different carve-outs do not share an SM
-      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(reduce_adam_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(reduce_adam_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       carve = true;
     }
     CruxTimed timed(ctx, CRUX_T_REDUCE);
-    reduce_adam_kernel<8><<<rgrid, 8 * 32, 0, ctx->stream>>>(mlp->partials, nparts, pstride, (int)mlp->n_params, mlp->grads, (float)bm, ls_shift,
-                                                           head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, g);
+    CRUX_CHECK_CUDA(ctx, launch_pdl(reduce_adam_kernel<4>, dim3(rgrid), dim3(4 * 32), 0, ctx->stream, pdl_enabled(), (const float *)mlp->partials, nparts, pstride,
+                                    (int)mlp->n_params, mlp->grads, (float)bm, ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, g));
     CRUX_LAUNCHED(ctx);
     return CRUX_OK;
   }
@@ -2195,7 +2217,7 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
     for (int64_t mbi = 0; mbi < nmb_a && total < maxb_a; ++mbi, ++total) {
       const int64_t off = mbi * hp->actor_batch, bm = i64min(hp->actor_batch, n - off);
       float *rec = actor->info_actor + ((int64_t)e * nmb_a + mbi) * CRUX_PPO_INFO_STRIDE;
-      rc = fused_minibatch(actor, mu, 0, s, a, logprob, advantage, ret, order + off, bm, hp, rec, actor->ctl, (int)total);
+      rc = fused_minibatch(actor, mu, 0, s, a, logprob, advantage, ret, order + off, bm, hp, rec, actor->ctl, (int)total, mbi > 0);
       if (rc) return rc;
     }
   }
@@ -2222,7 +2244,7 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
     for (int64_t mbi = 0; mbi < nmb_c && total < maxb_c; ++mbi, ++total) {
       const int64_t off = mbi * hp->critic_batch, bm = i64min(hp->critic_batch, n - off);
       float *rec = actor->info_critic + ((int64_t)e * nmb_c + mbi) * CRUX_PPO_INFO_STRIDE;
-      rc = fused_minibatch(actor, critic, 1, s, nullptr, nullptr, nullptr, ret, order + off, bm, hp, rec, nullptr, (int)total);
+      rc = fused_minibatch(actor, critic, 1, s, nullptr, nullptr, nullptr, ret, order + off, bm, hp, rec, nullptr, (int)total, mbi > 0);
       if (rc) { ctx->stream = main_stream; return rc; }
     }
   }
