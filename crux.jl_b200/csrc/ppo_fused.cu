@@ -1668,13 +1668,40 @@ __global__ void __launch_bounds__(256) fused_adam_ll_kernel(AdamArgs a, double *
 // RWT = 4 warps: two 128-thread CTAs at <= 56 registers fit NEXT TO a resident minibatch CTA (640 threads x 80 registers, 157 KB), so that
 // the tail of one network runs -- in a single wave -- under the other network's minibatch kernel instead of after it.
 template <int RWT>
-__global__ void __launch_bounds__(RWT * 32, 8) reduce_adam_kernel(const float *__restrict__ partials, int nparts, int pstride, int n_params,
+__global__ void __launch_bounds__(RWT * 32, 9) reduce_adam_kernel(const float *__restrict__ partials, int nparts, int pstride, int n_params,
                                                                  float *__restrict__ grads, float count, float ls_shift, int n_ls,
-                                                                 double *__restrict__ norm_part, int *__restrict__ state, AdamArgs a) {
+                                                                 double *__restrict__ norm_part, int *__restrict__ state, AdamArgs a, PeerOut peer) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next minibatch kernel of this network may start its prologue
   asm volatile("griddepcontrol.wait;" ::: "memory");                // the minibatch kernel's partials (and its KL-stop flag) are complete
   if (stopped(a.ctl, a.mb)) return;
   if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); a.trace[0] = gt_; }
+  // several GPUs: the gradient all-reduce is fused in with the LL (flag-in-data) protocol.  The CTA that finishes entry i stores it as one
+  // 8-byte {value, sequence} word into the receive region of EVERY rank over NVLink and then polls the `world` words of the same entry
+  // in its own region: rank-ordered sum (bit-identical on all ranks) -> Adam on that entry.  No fence, no flag, no collective launch.
+  unsigned long long pseq = 0ULL;
+  if (peer.enabled) pseq = *(volatile const unsigned long long *)peer.seq_dev + 1ULL;   // advanced by the last CTA of this kernel
+  const int64_t pbase = ((int64_t)(pseq & 1ULL) * 16 + peer.rank) * peer.cap;
+  const unsigned long long *slot0 = a.ll_recv + (int64_t)(pseq & 1ULL) * 16 * a.peer_cap;
+  auto exchange = [&](int idx, float v) -> float {
+    if (!peer.enabled) return v;
+    const unsigned long long word = ((unsigned long long)(unsigned int)pseq << 32) | (unsigned long long)__float_as_uint(v);
+    for (int q = 0; q < peer.world; ++q) *(volatile unsigned long long *)(peer.ll[q] + pbase + idx) = word;
+    float sum = 0.f;
+    const volatile unsigned long long *src = slot0 + idx;
+    for (int base = 0; base < peer.world; base += 4) {   // 4 loads in flight, rank order kept
+      unsigned long long wd[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (base + u < peer.world) wd[u] = src[(int64_t)(base + u) * a.peer_cap];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (base + u < peer.world) {
+          while ((unsigned int)(wd[u] >> 32) != (unsigned int)pseq) wd[u] = src[(int64_t)(base + u) * a.peer_cap];
+          sum += __uint_as_float((unsigned int)wd[u]);
+        }
+    }
+    return sum;
+  };
   __shared__ double sh[RWT][33];
   __shared__ double s_c1, s_c2;
   __shared__ int s_bad;
@@ -1718,14 +1745,16 @@ __global__ void __launch_bounds__(RWT * 32, 8) reduce_adam_kernel(const float *_
 #pragma unroll
         for (int q = 0; q < RWT; ++q) t += sh[q][lane];
         float g = (float)t;
-        if (p >= n_params && p < n_params + n_ls) g += ls_shift;
+        if (p >= n_params && p < n_params + n_ls) g += ls_shift;   // d(λe e_loss)/dlogΣ = -λe, scaled by 1/world: the sum over ranks restores it
         if (p < n_params + 8) {
+          g = exchange(p, g);
           grads[p] = g;
           if (p < n_params + n_ls) sq = (double)g * (double)g;
         } else {
           const int q = p - n_params - 8;   // obj, kl, clip, adv, ret | count | sum(logΣ) BEFORE this update (published by CTA 0 of the minibatch kernel)
-          if (q < 5 || q == 6) grads[n_params + 64 + q] = g;
-          else if (q == 5) grads[n_params + 64 + 5] = count;
+          if (q < 5) grads[n_params + 64 + q] = exchange(n_params + 64 + q, g);
+          else if (q == 5) grads[n_params + 64 + 5] = exchange(n_params + 64 + 5, count);
+          else if (q == 6) grads[n_params + 64 + 6] = g;   // identical on every rank: not exchanged
         }
         if (!bad && p < n_params + n_ls) {   // Flux Adam on this entry (float32 moments, Float64 scalars)
           if (grp != (int)blockIdx.x) {      // grid-strided launch (never the case today): state not prefetched
@@ -1759,9 +1788,10 @@ __global__ void __launch_bounds__(RWT * 32, 8) reduce_adam_kernel(const float *_
     if (lane == 0) {
       beta_cache_store(norm_part + BETA_CACHE, state[0] + 1, 1.0 - s_c1, 1.0 - s_c2);
       state[0] += 1; state[1] = 0; state[2] = 0;
+      if (peer.enabled) *(volatile unsigned long long *)a.ll_seq = pseq;   // every CTA has read the sequence number and all of its words: close the exchange
       const double n2 = t;
       const float *sums = grads + n_params + 64;
-      const float cnt = count;
+      const float cnt = __ldcg(sums + 5);   // rows of this minibatch over all ranks
       if (a.head == 0) {
         const float entropy = 1.4189385332046727f + __ldcg(sums + 6);   // policies.jl:348, logΣ as the minibatch kernel saw it
         const float p_loss = -(__ldcg(sums + 0) / cnt);
@@ -2126,7 +2156,7 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
     g.ll_seq = ctx->peer_flags + 40 + head; g.ll_ticket = reinterpret_cast<unsigned int *>(ctx->peer_flags + 48 + head);
   }
   static const bool no_fused_tail = getenv("CRUX_NO_FUSED_TAIL") != nullptr;
-  if (t5k && ctx->world == 1 && !no_fused_tail) {   // single GPU: reduce + Adam + record in ONE launch (reduce_adam_kernel)
+  if (t5k && (ctx->world == 1 || use_peer) && !no_fused_tail) {   // reduce [+ LL gradient exchange over NVLink] + Adam + record in ONE launch
     static bool carve = false;
     if (!carve) {   // same shared-memory carve-out as the minibatch kernel: CTAs of kernels with different carve-outs do not share an SM
       CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(reduce_adam_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -2134,7 +2164,7 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
     }
     CruxTimed timed(ctx, CRUX_T_REDUCE);
     CRUX_CHECK_CUDA(ctx, launch_pdl(reduce_adam_kernel<4>, dim3(rgrid), dim3(4 * 32), 0, ctx->stream, pdl_enabled(), (const float *)mlp->partials, nparts, pstride,
-                                    (int)mlp->n_params, mlp->grads, (float)bm, ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, g));
+                                    (int)mlp->n_params, mlp->grads, (float)bm, ls_shift, head == 0 ? actor->adim : 0, mlp->norm_part, mlp->step_dev, g, po));
     CRUX_LAUNCHED(ctx);
     return CRUX_OK;
   }

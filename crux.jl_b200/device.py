@@ -114,6 +114,10 @@ class Context:
         self.check(self.lib.crux_memcpy_d2h(self.h, C.c_void_p(dst_np.ctypes.data), ptr(src), dst_np.nbytes))
 
     # ---- multi-GPU -------------------------------------------------------------------------
+    def peer_ll_active(self):
+        """True when the gradient exchange of the fused PPO update goes over the mapped peer buffers (LL protocol) rather than NCCL."""
+        return bool(getattr(self, "peer_mapped", False)) and not os.environ.get("CRUX_NO_PEER_LL")
+
     def init_distributed(self, rank, world, peer_floats=None):
         """One rank per GPU.  The NCCL unique id travels through torch.distributed (any backend).  ``peer_floats`` > 0 (default
         8192, or ``CRUX_PEER_FLOATS``) also maps every rank's peer buffer over CUDA IPC (NVLink): the gradient all-reduce of the PPO
