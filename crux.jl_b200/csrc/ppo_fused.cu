@@ -1875,7 +1875,7 @@ static int forward_fused_impl(crux_mlp *mlp, const float *x, int64_t B, float *y
   int rc = set_smem_attr(ctx); if (rc) return rc;
   // whole-column plain forwards: tcgen05 + TMEM kernel (fwd_tc5.cuh), one 128-row tile per SM and round
   // (CRUX_FWD_TC5=0: the mma.sync kernel below; =1s: the variant that keeps the activations in shared memory)
-  static const char *tc5_env = getenv("CRUX_FWD_TC5") ? getenv("CRUX_FWD_TC5") : "1";
+  const char *tc5_env = getenv("CRUX_FWD_TC5") ? getenv("CRUX_FWD_TC5") : "1";   // read per call: tests switch variants
   const bool alt_ok = x_alt && y_alt && mlp->dims[3] == 1 && ((uintptr_t)x_alt & 15) == 0 && !getenv("CRUX_NO_VALUE_REUSE");
   if (tc5_env[0] == '1' && (!alt_ok || tc5_env[1] != 's') && mlp->dims[0] <= tc5::KX && mlp->dims[3] <= 8 && cdiv(B, tc5::TR) >= (int64_t)ctx->num_sms &&
       ((uintptr_t)x & 15) == 0 && !getenv("CRUX_NO_MMA")) {

@@ -487,9 +487,17 @@ class FirstExplorePolicy(Policy):
     def __init__(self, N, initial_policy, after_policy=None):
         self.N, self.initial_policy, self.after_policy = N, initial_policy, after_policy
 
-    def exploration(self, s, pi_on, i, **kw):
+    def resolve(self, i):
+        """The policy that acts at step ``i``: (policy, True) = take its plain ``action`` (no exploration noise, logprob NaN),
+        (policy, False) = call its own ``exploration``; ``policy is None`` stands for the on-policy network."""
         if i < self.N:
-            return self.initial_policy(s), float("nan")
+            return self.initial_policy, True
         if self.after_policy is None:
-            return action(pi_on, s), float("nan")
-        return self.after_policy.exploration(s, pi_on, i, **kw)
+            return None, True
+        return self.after_policy, False
+
+    def exploration(self, s, pi_on, i, **kw):
+        pol, plain = self.resolve(i)
+        if plain:   # policies.jl:527-530: action(π.initial_policy, s) / action(π_on, s), NaN
+            return action(pi_on if pol is None else pol, s), float("nan")
+        return pol.exploration(s, pi_on, i, **kw)   # a MixedPolicy returns (index, one-hot, logprob): Sampler._act dispatches on the resolved policy

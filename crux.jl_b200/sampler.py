@@ -18,7 +18,7 @@ import torch
 from . import _abi
 from .buffer import ExperienceBuffer, mdp_data, _TORCH
 from .device import ptr
-from .policies import (ActorCritic, ContinuousNetwork, DiscreteNetwork, GaussianPolicy, MixedPolicy, Policy, PolicyParams,
+from .policies import (ActorCritic, ContinuousNetwork, DiscreteNetwork, FirstExplorePolicy, GaussianPolicy, MixedPolicy, Policy, PolicyParams,
                        action, actor, critic, exploration, fusable)
 from .spaces import ContinuousSpace, DiscreteSpace
 
@@ -110,6 +110,19 @@ class Sampler:
             if logp_out is not None:
                 logp_out.fill_(float("nan"))
             return a_out
+        if isinstance(pe, FirstExplorePolicy):   # policies.jl:526-534: dispatch on the policy that acts at this step
+            pol, plain = pe.resolve(i)
+            if plain:
+                a = action(pi if pol is None else pol, obs)
+                if logp_out is not None:
+                    logp_out.fill_(float("nan"))
+                if discrete:
+                    a_out.zero_()
+                    a_out.scatter_(1, a.long().reshape(-1, 1), 1.0)
+                    return a
+                a_out.copy_(a.reshape(a_out.shape))
+                return a_out
+            pe = pol
         if isinstance(pe, Policy) and hasattr(pe, "exploration") and not isinstance(pe, (GaussianPolicy, ActorCritic, DiscreteNetwork, ContinuousNetwork)):
             if isinstance(pe, MixedPolicy):
                 idx, oh, lp = pe.exploration(obs, pi, i, u=noise, seed=self.seed, ctr=ctr)
