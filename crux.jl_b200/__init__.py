@@ -17,5 +17,8 @@ from .buffer import (ExperienceBuffer, PriorityParams, buffer_like, mdp_data, pr
                      uniform_sample_)
 from .envs import DeviceLinQuad, HostLinQuad, NativeHostLinQuad, SimpleGridWorld, linquad_matrices  # noqa: F401
 from .sampler import Sampler, fill_gae_, fill_returns_, steps_  # noqa: F401
-from .solvers import (A2C, DDPG, DQN, PPO, LagrangePPO, REINFORCE, SAC, TD3, Adam, SoftQ, LoggerParams, OffPolicySolver, OnPolicySolver, TrainingParams,  # noqa: F401
-                      log_undiscounted_return, solve)
+from .logger import (LoggerParams, TBLogger, aggregate_info, log_discounted_return, log_episode_averages, log_experience_sums,  # noqa: F401
+                     log_exploration, log_failure, log_metric_by_key, log_metrics_by_key, log_performance, log_undiscounted_return,
+                     log_validation_error, read_scalars, tb_increment)
+from .solvers import (A2C, DDPG, DQN, PPO, LagrangePPO, REINFORCE, SAC, TD3, Adam, SoftQ, OffPolicySolver, OnPolicySolver, TrainingParams,  # noqa: F401
+                      solve)

@@ -47,7 +47,6 @@ class Sampler:
         self.cur = self.ctx.empty((self.n, self.sdim))   # current observation of every stream (device)
         self._pinned = None
         self._scratch = {}
-        self._carry = np.zeros(self.n, dtype=bool)
         self.reset_()
 
     # ---- reset_sampler! (sampler.jl:31-43) for every stream
@@ -61,7 +60,6 @@ class Sampler:
             self._pinned["obs"][...] = o
             self.ctx.h2d(self.cur, self._pinned["obs"])
         self.episode_length[:] = 0
-        self._carry = np.zeros(self.n, dtype=bool)
 
     def _tovec(self, o):
         """tovec(o, S) spaces.jl:24-25 for a ContinuousSpace: (o - μ)/σ."""
@@ -332,41 +330,56 @@ class Sampler:
                                                 ptr(adv), ptr(ret)))
 
     # ---- episodes! (sampler.jl:175-200): whole episodes only, each one contiguous in the returned columns
+    def _episode_quota(self, Neps):
+        """The reference runs ``Neps`` episodes one after the other, each to completion (sampler.jl:181-193).  With n parallel
+        streams the unbiased equivalent assigns episode k (0-based) to stream ``k % used`` as that stream's ``k // used``-th
+        episode after the reset, ``used = min(n, Neps)``: WHICH episodes count is fixed before the rollout (start order), never
+        by finishing order -- picking the first finishers would favour short episodes."""
+        used = min(self.n, int(Neps))
+        quota = (int(Neps) - np.arange(used) + used - 1) // used
+        return used, quota
+
     def episodes_(self, buffer=None, Neps=1, explore=False, i=0, cb=None, return_episodes=False):
-        """Resets every stream, then collects ``Neps`` complete episodes (in stream-major order of completion within chunks of
-        ``max_steps`` vector steps).  Returns the columns (episodes concatenated); with ``return_episodes`` also the 1-based
-        inclusive (start, end) pairs like ``episodes(data)``."""
+        """Resets every stream, then collects ``Neps`` complete episodes: stream ``e < min(n, Neps)`` contributes its first
+        ``quota[e]`` episodes after the reset, every one run to its end however many vector steps that takes (episodes are
+        stitched across rollout chunks).  Returns the columns (episodes concatenated, episode k = stream ``k % used``, slot
+        ``k // used``); with ``return_episodes`` also the 1-based inclusive (start, end) pairs like ``episodes(data)``."""
         self.reset_()
-        n, T = self.n, self.max_steps
-        picked, pairs, total = [], [], 0
-        cols = None
-        while len(pairs) < Neps:
-            data = {k: v.clone() for k, v in self.steps_(None, Nsteps=n * T, explore=explore, i=i, reset=False).items()}
-            ee = data["episode_end"].reshape(T, n).cpu().numpy().astype(bool)
-            idx = []
-            for e in range(n):
+        n = self.n
+        used, quota = self._episode_quota(Neps)
+        T = max(1, min(self.max_steps, max(16, (1 << 22) // n)))     # rows per chunk bounded (~4 M), any chunk length stitches
+        slot = np.zeros(used, dtype=np.int64)
+        parts, tags = [], []
+        while np.any(slot < quota):
+            data = self.steps_(None, Nsteps=n * T, explore=explore, i=i, reset=False)
+            ee = data["episode_end"].reshape(T, n)[:, :used].cpu().numpy().astype(bool)
+            idx, tag = [], []
+            for e in np.flatnonzero(slot < quota):
                 start = 0
                 for end in np.flatnonzero(ee[:, e]):
-                    if len(pairs) >= Neps:
-                        break
-                    # an episode that began in a previous chunk is incomplete here: skip a first segment that does not start at a reset
-                    if start == 0 and cols is not None and self._carry[e]:
-                        start = end + 1
-                        continue
-                    rows = np.arange(start, end + 1) * n + e
-                    idx.append(rows)
-                    pairs.append((total + 1, total + len(rows)))
-                    total += len(rows)
+                    idx.append(np.arange(start, end + 1) * n + e)
+                    tag.append(np.full(end + 1 - start, e + slot[e] * used))
+                    slot[e] += 1
                     start = end + 1
-            self._carry = ~ee[-1]            # streams whose episode continues into the next chunk
+                    if slot[e] >= quota[e]:
+                        break
+                else:                                                 # the episode in progress continues in the next chunk
+                    if start < T:
+                        idx.append(np.arange(start, T) * n + e)
+                        tag.append(np.full(T - start, e + slot[e] * used))
             if idx:
                 sel = torch.as_tensor(np.concatenate(idx), device=self.ctx.device)
-                part = {k: v.index_select(0, sel) for k, v in data.items()}
-                cols = part if cols is None or not picked else {k: torch.cat([cols[k], part[k]]) for k in part}
-                picked.append(True)
-            elif cols is None:
-                cols = {k: v[:0] for k, v in data.items()}
+                parts.append({k: v.index_select(0, sel) for k, v in data.items()})   # copies: the rollout scratch is reused
+                tags.append(np.concatenate(tag))
             i += n * T
+        cols = {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
+        tag = np.concatenate(tags)
+        order = np.argsort(tag, kind="stable")                        # episode-major, time order kept inside an episode
+        cols = {k: v.index_select(0, torch.as_tensor(order, device=self.ctx.device)) for k, v in cols.items()}
+        lens = np.bincount(tag, minlength=int(Neps))
+        stops = np.cumsum(lens)
+        pairs = [(int(b - l + 1), int(b)) for l, b in zip(lens, stops)]
+        self.reset_()                                                 # unfinished episodes of the other streams are dropped
         if cb is not None:
             cb(cols)
         if buffer is not None:
@@ -410,15 +423,17 @@ class Sampler:
 
     def undiscounted_return(self, Neps=10, **kw):
         """``undiscounted_return(s::Sampler; Neps)`` (:216): on a device env through ``episodes_`` + the device scan; on a host env
-        the batched greedy loop below (episodes counted in finishing order)."""
+        the batched greedy loop below
+        (which episodes count is fixed by ``_episode_quota``: start order, not finishing order)."""
         if self.on_device:
             return self.metric_by_key("r", Neps=Neps, **kw)
         self.reset_()
+        used, quota = self._episode_quota(Neps)
         total = np.zeros(self.n)
-        finished = []
-        discrete = isinstance(self.agent.space, DiscreteSpace)
+        count = np.zeros(self.n, dtype=np.int64)
+        result = np.zeros(int(Neps))
         steps = np.zeros(self.n, dtype=np.int64)
-        while len(finished) < Neps:
+        while np.any(count[:used] < quota):
             obs = self.cur
             a = action(self.agent.pi, obs)
             sp, r, dn = self.mdp.step(a.cpu().numpy())
@@ -428,14 +443,17 @@ class Sampler:
             nxt = self._tovec(sp)
             if end.any():
                 idx = np.flatnonzero(end)
-                finished += total[idx].tolist()
+                for e in idx[idx < used]:
+                    if count[e] < quota[e]:
+                        result[e + count[e] * used] = total[e]
+                count[idx] += 1
                 total[idx] = 0
                 steps[idx] = 0
                 nxt = nxt.copy()
                 nxt[idx] = self._tovec(self.mdp.reset(idx))
             self.cur.copy_(torch.from_numpy(nxt))
         self.reset_()
-        return float(np.mean(finished[:Neps]))
+        return float(np.mean(result))
 
 
 def steps_(sampler, buffer=None, **kw):

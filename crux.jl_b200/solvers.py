@@ -21,6 +21,7 @@ from .device import ptr, view
 from .policies import (ActorCritic, ContinuousNetwork, DiscreteNetwork, DoubleNetwork, GaussianNoiseExplorationPolicy,
                        GaussianPolicy, LinearDecaySchedule, PolicyParams, SquashedGaussianPolicy, action_space, actor,
                        critic, deepcopy, eps_greedy_policy, polyak_average_)
+from .logger import LoggerParams, log_undiscounted_return  # noqa: F401  (re-exported: logging.jl lives in logger.py)
 from .sampler import Sampler
 from .spaces import DiscreteSpace, dim
 
@@ -45,39 +46,14 @@ class TrainingParams:
         self.target_kl = target_kl  # the only early-stopping rule the fused update evaluates (rl/ppo.jl:59, a2c.jl:46)
 
 
-class LoggerParams:
-    """logging.jl:12-25 reduced to what the solve loops touch: ``period``, ``fns``, ``verbose``, ``sampler``; scalars are
-    appended to ``history`` (the TensorBoard writer is out of scope)."""
-
-    def __init__(self, dir="log/", period=500, fns=None, verbose=False, sampler=None):
-        self.dir, self.period, self.verbose, self.sampler = dir, int(period), verbose, sampler
-        self.fns = [] if fns is None else list(fns)
-        self.history = []
-
-    @staticmethod
-    def elapsed(i, N):
-        """logging.jl:1-2 (``i`` an int or an inclusive (lo, hi) range)."""
-        if isinstance(i, tuple):
-            lo, hi = i
-            return hi // N > (lo - 1) // N
-        return i % N == 0
-
-    def log(self, i, *dicts, solver=None):
-        if not self.elapsed(i, self.period):
-            return
-        step = i[1] if isinstance(i, tuple) else i
-        rec = {"step": step}
-        for d in list(self.fns) + list(dicts):
-            d = d(s=self.sampler, i=step, solver=solver) if callable(d) else d
-            rec.update({str(k): (v() if callable(v) else v) for k, v in d.items()})
-        self.history.append(rec)
-        if self.verbose:
-            print(", ".join(f"{k}: {v}" for k, v in rec.items()))
+# Philox domain separation: every device RNG consumer keys Philox on (seed, counter, row); the sampler's exploration noise
+# uses the solver seed itself, replay sampling and the update-time noise (SAC re-sampling, DDPG/TD3 target smoothing) use disjoint keys,
+# so that e.g. the replay index of batch row i never comes from the same 128 bits as env stream i's exploration noise.
+_DOM_REPLAY, _DOM_UPDATE = 0xA5A55A5A00010001, 0xC3C33C3C00020002
 
 
-def log_undiscounted_return(Neps=10):
-    """logging.jl:69-76: greedy evaluation episodes on the logger's sampler (which resets it)."""
-    return lambda s, i, solver=None: {"undiscounted_return": s.undiscounted_return(Neps)}
+def _dom(seed, domain):
+    return (int(seed) ^ domain) & 0xFFFFFFFFFFFFFFFF
 
 
 def _set_adam(mlp, opt):
@@ -369,9 +345,17 @@ class OffPolicySolver:
         ctx, lib = self.agent.pi.ctx, self.agent.pi.ctx.lib
         B = D.capacity
         infos = []
+        if self.kind in ("sac", "ddpg", "td3"):
+            # off_policy.jl:83-89,93 for these solvers is not fused into crux_sac_train / crux_ddpg_train: refuse instead of silently
+            # leaving every priority at max_priority / ignoring the importance weights
+            if self.buffer.isprioritized() or self.weighted_loss:
+                raise NotImplementedError(f"{self.kind}: prioritized replay / weighted_loss are only wired for DQN and SoftQ (off_policy.jl:83-93)")
+            if self.kind == "sac" and (self.c_opt.update_every != 1 or self.a_opt.update_every != 1):
+                raise NotImplementedError("sac: c_opt/a_opt.update_every != 1 is not supported by the fused SAC update (off_policy.jl:91,96)")
         for epoch in range(self.c_opt.epochs):
             self.train_count += 1
-            rand_(D, self.buffer, i=self.i, draws=None if draws is None else [draws[epoch]], seed=self.seed, ctr=2 * self.train_count)
+            rand_(D, self.buffer, i=self.i, draws=None if draws is None else [draws[epoch]], seed=_dom(self.seed, _DOM_REPLAY),
+                  ctr=2 * self.train_count)
             s, a, sp, r, dn = D.column("s"), D.column("a"), D.column("sp"), D.column("r"), D.column("done")
             if self.kind in ("dqn", "softq"):
                 pi, tgt = self.agent.pi, self.agent.pi_target
@@ -401,12 +385,12 @@ class OffPolicySolver:
                 ctx.check(lib.crux_ddpg_train(self._ddpg, ptr(s), ptr(a), ptr(sp), ptr(r), ptr(dn), B, float(gamma), 0 if sm is None else 1,
                                               0.0 if sm is None else float(F32(sm.sigma(self.i))), -math.inf if sm is None else float(sm.eps_min),
                                               math.inf if sm is None else float(sm.eps_max), ptr(lo), 0 if lo is None else lo.size, ptr(hi),
-                                              0 if hi is None else hi.size, ptr(e), self.seed, 3 * self.train_count, 1 if do_c else 0,
+                                              0 if hi is None else hi.size, ptr(e), _dom(self.seed, _DOM_UPDATE), 3 * self.train_count, 1 if do_c else 0,
                                               1 if do_a else 0, None, None))
             else:
                 e = (None, None, None) if noise is None else [ctx.to_device(x, torch.float32) for x in noise[epoch]]
                 ctx.check(lib.crux_sac_train(self._sac, ptr(s), ptr(a), ptr(sp), ptr(r), ptr(dn), B, float(gamma), ptr(e[0]), ptr(e[1]), ptr(e[2]),
-                                             self.seed, 3 * self.train_count, None, None))
+                                             _dom(self.seed, _DOM_UPDATE), 3 * self.train_count, None, None))
         if self.kind in ("dqn", "softq"):  # no separate actor: target update after the epoch loop (off_policy.jl:108)
             polyak_average_(self.agent.pi_target, self.agent.pi, self.tau)
         return infos

@@ -4,7 +4,7 @@ Writes profiles/<round>_launches_step.csv (raw ncu launch list of one PPO iterat
 import csv, io, os, re, shutil, subprocess, sys, collections, json
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-G = os.path.join(ROOT, "gpurun_out")
+G = os.environ.get("CRUX_PROFILE_SRC", os.path.join(ROOT, "gpurun_out"))
 rnd = sys.argv[1] if len(sys.argv) > 1 else "r1"
 out = []
 
@@ -57,11 +57,11 @@ if os.path.exists(lp):
     for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append(f"| `{k}` | {c} | {v:.1f} | {v / c:.2f} | {100 * v / tot:.1f}% |")
     out.append("")
-for name, title in (("prof_minibatch", "fused_minibatch_kernel (dominant kernel of the step)"), ("prof_gae_tma", "gae_tma_kernel at [2048, 16384] (738 MB): TMA-fed streaming scan, the kernel crux_fill_gae_returns runs for N >= 8192"),
+for name, title in (("r2_prof_minibatch", "mb6::minibatch_kernel<0> (actor; dominant kernel of the step): every GEMM on tcgen05, TMEM accumulators"), ("prof_minibatch", "fused_minibatch_kernel (dominant kernel of the step)"), ("prof_gae_tma", "gae_tma_kernel at [2048, 16384] (738 MB): TMA-fed streaming scan, the kernel crux_fill_gae_returns runs for N >= 8192"),
                     ("prof_gae", "gae_returns_kernel at [2048, 16384] (738 MB): register-resident scan (narrow / short rollouts; CRUX_GAE=scan)"),
                     ("prof_fwd_tc5", "tc5::forward_kernel_tmem: value(V, s) over 131072 rows on tcgen05, activations resident in tensor memory"),
                     ("prof_mb5", "mb5::minibatch_kernel (opt-in CRUX_MB_TC5=1): PPO minibatch with the row GEMMs on tcgen05 / TMEM"),
-                    ("prof_rollout", "rollout_linquad_kernel: T = 32 vector steps of 4096 env streams in one persistent launch"),
+                    ("r2_prof_rollout", "rollout_linquad_kernel (r2 capture)"), ("prof_rollout", "rollout_linquad_kernel: T = 32 vector steps of 4096 env streams in one persistent launch"),
                     ("prof_forward", "fused_forward_kernel")):
     rep = os.path.join(G, name + ".ncu-rep")
     if not os.path.exists(rep):

@@ -210,13 +210,14 @@ def test_ppo_two_iterations_match_oracle(crux, ctx):
 
 
 @pytest.mark.parametrize("device_env", [False, True])
-def test_solve_ppo_and_a2c_run(crux, ctx, device_env):
+def test_solve_ppo_and_a2c_run(crux, ctx, device_env, tmp_path):
     n, T = 64, 8
     for ctor in (crux.PPO, crux.A2C):
         pi = _actor_critic(crux, ctx, seed=4)
         before = pi.A.mu.mlp.get_flat().copy()
         opt = dict(epochs=2, batch_size=128)
-        log = crux.LoggerParams(period=n * T, verbose=False)
+        # the reference's default logger: TBLogger(dir, tb_increment) + fns = [log_undiscounted_return(10), log_episode_averages([:r], period)]
+        log = crux.LoggerParams(dir=str(tmp_path / "log"), period=n * T, verbose=False)
         S = ctor(pi, crux.ContinuousSpace(17), a_opt=dict(opt), c_opt=dict(opt), N=3 * n * T, dN=n * T, max_steps=50, log=log)
         env = crux.DeviceLinQuad(n, seed=1, max_steps=50, ctx=ctx) if device_env else crux.HostLinQuad(n, seed=1)
         out = crux.solve(S, env)
@@ -225,6 +226,15 @@ def test_solve_ppo_and_a2c_run(crux, ctx, device_env):
         assert np.isfinite(info["actor_loss"]) and np.isfinite(info["critic_loss"]) and info["actor_batches_trained"] >= 1
         assert not np.array_equal(before, pi.A.mu.mlp.get_flat())
         assert len(log.history) >= 3 and "actor_loss" in log.history[-1]
+        # logging.jl:21,48-54: every logged value went through log_value into a TensorBoard event file that reads back CRC-clean
+        rec = crux.read_scalars(log.logger.path)
+        tags = {t for _, t, _ in rec}
+        assert {"undiscounted_return", "avg_r", "actor_loss", "critic_loss", "kl"} <= tags, tags
+        last = log.history[-1]
+        back = {t: v for st, t, v in rec if st == last["step"]}
+        for k in ("undiscounted_return", "avg_r", "actor_loss"):
+            assert back[k] == pytest.approx(np.float32(last[k]), rel=1e-6, nan_ok=True), k
+        assert sorted({st for st, _, _ in rec}) == [h["step"] for h in log.history]
         crux.solve(S, env)  # calling solve again continues (on_policy.jl:38,107)
         assert S.i == 6 * n * T
 
@@ -495,3 +505,53 @@ def test_episode_metrics_on_device(crux, ctx, device_env):
     assert s.failure(threshold=1e9, Neps=5) == 1.0 and s.failure(threshold=-1e9, Neps=5) == 0.0
     m = s.metrics_by_key(["r", "done"], Neps=6)
     assert np.isfinite(m[0]) and 0.0 <= m[1] <= 1.0      # at most one terminal transition per episode
+
+
+class _BimodalEnv:
+    """Host env whose episode lengths are bimodal and known in advance: episode c (0-based, counted per stream since construction or
+    the last full reset) of stream e lasts 2 steps when (e + c) is even and 20 steps otherwise; r = 1 per step.  A selection of the
+    first episodes to FINISH would report ~2, the reference's sequential evaluation (sampler.jl:181-193) the true mix."""
+    on_device = False
+
+    def __init__(self, n, crux):
+        self.n_envs, self.obs_dim, self.act_dim, self.gamma = n, 17, 6, F32(0.99)
+        self.action_space = crux.ContinuousSpace(6)
+        self.c = np.zeros(n, dtype=np.int64)
+        self.t = np.zeros(n, dtype=np.int64)
+
+    def length(self, e, c):
+        return np.where((e + c) % 2 == 0, 2, 20)
+
+    def reset(self, idx=None):
+        if idx is None:
+            self.c[:] = 0
+            self.t[:] = 0
+            idx = np.arange(self.n_envs)
+        else:
+            self.c[idx] += 1
+            self.t[idx] = 0
+        return np.zeros((len(idx), self.obs_dim), dtype=F32)
+
+    def step(self, a):
+        self.t += 1
+        done = self.t >= self.length(np.arange(self.n_envs), self.c)
+        return np.zeros((self.n_envs, self.obs_dim), dtype=F32), np.ones(self.n_envs, dtype=F32), done
+
+
+@pytest.mark.parametrize("n,Neps", [(16, 10), (4, 10), (3, 7)])
+def test_evaluation_is_unbiased_for_bimodal_episode_lengths(crux, ctx, n, Neps):
+    """ADVICE r1 (medium): episodes are chosen by start order (stream k % used, slot k // used), never by finishing order, and every
+    chosen episode runs to completion across rollout chunks."""
+    pi = _actor_critic(crux, ctx, seed=2)
+    env = _BimodalEnv(n, crux)
+    s = crux.Sampler(env, pi, max_steps=50)
+    used = min(n, Neps)
+    expect = [int(env.length(k % used, k // used)) for k in range(Neps)]
+    assert 2 in expect and 20 in expect
+    assert s.undiscounted_return(Neps=Neps) == pytest.approx(np.mean(expect))
+    data, eps = s.episodes_(Neps=Neps, return_episodes=True)
+    assert [b - a + 1 for a, b in eps] == expect
+    ee = host(data["episode_end"])[:, 0].astype(bool)
+    assert ee.sum() == Neps and all(ee[b - 1] for _, b in eps)
+    assert s.metric_by_key("r", Neps=Neps) == pytest.approx(np.mean(expect))
+    assert s.failure(threshold=10.0, Neps=Neps) == pytest.approx(np.mean(np.array(expect) < 10))
