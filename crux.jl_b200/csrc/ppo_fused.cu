@@ -2491,6 +2491,259 @@ __global__ void __launch_bounds__(NT, 2) rollout_linquad_kernel(RolloutArgs g) {
   if (last && t == 0) { g.tick_dev[0] += (unsigned long long)g.T; g.tick_dev[1] = 0ULL; __threadfence(); }
 }
 
+
+// ---- register-tiled variants: a WARP owns WS = 2 RPT env streams, a thread an RPT-stream x 4-feature tile of the two hidden layers ----
+// The kernel above gives every stream a half-warp, thread = (1 stream, 4 features): per k one scalar + one 128-bit shared load feed
+// 4 FFMA, and ncu shows what that costs -- 82 % of the issued instructions are not FFMAs, 50.6 M shared-memory wavefronts, short
+// scoreboard 1.8 per issue (profiles/r2_ncu_summary.md).  Here lane (rg, jg) = (lane >> 4, lane & 15) owns streams RPT rg .. + RPT - 1
+// of the warp's WS and features 4 jg .. 4 jg + 3: one RPT-wide and one 128-bit load feed 4 RPT FFMA.  The phases outside the two
+// 64-wide layers use lane (rs, slot) = (lane % WS, lane / WS): stream rs, task slot 0 .. 32 / WS - 1.  A stream's whole step still
+// lives in ONE warp (phases ordered by __syncwarp(), no block barrier in the T-step loop), every value is computed by the same
+// instruction sequence as before (accumulation order over k, noise counters, libdevice calls), so the rollout stays bit-identical to
+// T x (crux_rollout_step + crux_linquad_step).  CTA = 16 / WS warps = up to 16 streams (`rows`), two CTAs per SM.
+template <int RPT> struct RowVec;
+template <> struct RowVec<4> { using T = float4; };
+template <> struct RowVec<2> { using T = float2; };
+template <int RPT> __device__ __forceinline__ void ld_rows(const float *p, float (&v)[RPT]) {
+  const typename RowVec<RPT>::T x = *reinterpret_cast<const typename RowVec<RPT>::T *>(p);
+  const float *f = reinterpret_cast<const float *>(&x);
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) v[i] = f[i];
+}
+template <int RPT> __device__ __forceinline__ void st_rows(float *p, const float (&v)[RPT]) {
+  typename RowVec<RPT>::T x;
+  float *f = reinterpret_cast<float *>(&x);
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) f[i] = v[i];
+  *reinterpret_cast<typename RowVec<RPT>::T *>(p) = x;
+}
+template <int RPT>
+__device__ __forceinline__ void layer_fwd_rt(const float *__restrict__ AT, int K, const float *__restrict__ W, const float *__restrict__ b,
+                                             float *__restrict__ CT, int act, int r0, int jg) {
+  float acc[RPT][4];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+  const float *ap = AT + r0, *wp = W + 4 * jg;
+#pragma unroll 8
+  for (int k = 0; k < K; ++k) {
+    float a4[RPT];
+    ld_rows<RPT>(ap + k * LD16, a4);
+    const float4 w = *reinterpret_cast<const float4 *>(wp + k * H);
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      acc[i][0] = fmaf(a4[i], w.x, acc[i][0]); acc[i][1] = fmaf(a4[i], w.y, acc[i][1]);
+      acc[i][2] = fmaf(a4[i], w.z, acc[i][2]); acc[i][3] = fmaf(a4[i], w.w, acc[i][3]);
+    }
+  }
+  const float4 bb = *reinterpret_cast<const float4 *>(b + 4 * jg);
+  const float b4[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float o[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) o[i] = act_fused(act, acc[i][c] + b4[c]);
+    st_rows<RPT>(CT + (4 * jg + c) * LD16 + r0, o);
+  }
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(32 * 16 / (2 * RPT), 2) rollout_linquad_kernel_rt(RolloutArgs g) {
+  constexpr int WS = 2 * RPT, NS = 32 / WS, NTH = 32 * 16 / WS;   // streams per warp, task slots per stream, threads per CTA
+  using M = SmemMapT<R>;
+  extern __shared__ __align__(16) float sm[];
+  float *sA = sm + M::W2T;                       // [32*32] env A   (regions of the carve-up the 16-row forward does not touch)
+  float *sB = sm + M::W2T + LQ_MAX_S * LQ_MAX_S; // [32*16] env B
+  float *aT = sm + M::AT;                        // [8][LD16] sampled actions
+  float *taT = sm + M::AT + MAX_O * LD16;        // [8][LD16] tanh(a), later the |s'|^2 partials
+  const NetDesc nd = g.net;
+  const int I = nd.I, O = nd.O, sdim = I, adim = g.adim;
+  const int t = threadIdx.x;
+  stage_params(sm, nd, M::MBAR);
+  float *spT = sm + M::H2T + H * LD16;           // [32][LD16] s'
+  int *s_len = reinterpret_cast<int *>(spT + LQ_MAX_S * LD16);  // [16] episode lengths
+  int *s_end = s_len + 16;                                      // [16] end flags of the current step
+  float *nzT = spT + LQ_MAX_S * LD16 + 32;       // [32][LD16] env noise of the step
+  for (int i = t; i < sdim * sdim; i += NTH) sA[i] = g.A[i];
+  for (int i = t; i < sdim * adim; i += NTH) sB[i] = g.B[i];
+  const float *P = sm + M::P;
+  float *XT = sm + M::XT, *H1T = sm + M::H1T, *H2T = sm + M::H2T, *OT = sm + M::OT;
+  const int rows = g.rows;
+  const int64_t e0 = (int64_t)blockIdx.x * rows;
+  const int lane = t & 31, rb = (t >> 5) * WS;    // first stream of this warp inside the tile
+  const int r0 = rb + RPT * (lane >> 4), jg = lane & 15;
+  const int rs = rb + (lane % WS), slot = lane / WS;
+  const int64_t e = e0 + rs;
+  const bool live = rs < rows && e < g.N;
+  const int nlive = (int)max((int64_t)0, min((int64_t)min(WS, rows - rb), g.N - e0 - rb));   // live streams of this warp (a prefix of its WS)
+  const unsigned long long tick0 = *(volatile unsigned long long *)g.tick_dev;
+  const uint32_t inv_s = (65536u + (uint32_t)sdim - 1u) / (uint32_t)sdim, inv_o = (65536u + (uint32_t)O - 1u) / (uint32_t)O;   // q / d for q < 1024
+  for (int q = t; q < R16 * sdim; q += NTH) {
+    const int rr = q / sdim, i = q - rr * sdim;
+    XT[i * LD16 + rr] = (rr < rows && e0 + rr < g.N) ? g.obs_io[(e0 + rr) * sdim + i] : 0.f;
+  }
+  if (t < R16) s_len[t] = (t < rows && e0 + t < g.N) ? g.ep_len[e0 + t] : 0;
+  __syncthreads();
+
+  const int n_steps = nlive > 0 ? g.T : 0;
+  for (int step = 0; step < n_steps; ++step) {
+    const int64_t row0 = (int64_t)step * g.N + e0 + rb;   // rollout row of this warp's first stream
+    // s rows of this step: the warp's live streams are nlive * sdim contiguous floats
+    for (int q = lane; q < nlive * sdim; q += 32) {
+      const int rr = (int)(((uint32_t)q * inv_s) >> 16), kk = q - rr * sdim;
+      g.s[row0 * sdim + q] = XT[kk * LD16 + rb + rr];
+    }
+    layer_fwd_rt<RPT>(XT, I, P, P + off_b1(I), H1T, nd.act, r0, jg);
+    __syncwarp();
+    layer_fwd_rt<RPT>(H1T, H, P + off_W2(I), P + off_b2(I), H2T, nd.act, r0, jg);
+    __syncwarp();
+    {   // output layer: lane (rs, slot) owns the outputs slot, slot + NS, ... (independent chains; bias first, then k ascending)
+      const float *W3 = P + off_W3(I);
+      constexpr int NO = (MAX_O + NS - 1) / NS;
+      int oo[NO]; float a0[NO];
+#pragma unroll
+      for (int u = 0; u < NO; ++u) { oo[u] = slot + NS * u < O ? slot + NS * u : 0; a0[u] = P[off_b3(I, O) + oo[u]]; }
+#pragma unroll 8
+      for (int k = 0; k < H; ++k) {
+        const float h = H2T[k * LD16 + rs];
+#pragma unroll
+        for (int u = 0; u < NO; ++u) a0[u] = fmaf(h, W3[k * O + oo[u]], a0[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < NO; ++u)
+        if (slot + NS * u < O) OT[(slot + NS * u) * LD16 + rs] = a0[u];
+    }
+    __syncwarp();
+    // Gaussian head, lane (stream, action-dimension pair): one Philox block + one Box-Muller yield both normals of the pair
+    for (int j0 = 2 * slot; j0 < O; j0 += 2 * NS) {
+      const Philox4 p = philox4x32_10(g.seed_pi, g.ctr0 + (uint64_t)step, (uint64_t)e * ((O + 3) / 4) + (j0 >> 2));
+      float n0, n1;
+      if ((j0 & 2) == 0) box_muller(p.x, p.y, n0, n1); else box_muller(p.z, p.w, n0, n1);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = j0 + u;
+        if (j < O) {
+          const float mu = OT[j * LD16 + rs];
+          const float ls = g.ls[j];
+          const float sigma = expf(ls);
+          const float var = sigma * sigma;
+          const float ev = u ? n1 : n0;
+          const float act = ev * sigma + mu;
+          aT[j * LD16 + rs] = act;
+          const float dd = act - mu;
+          OT[j * LD16 + rs] = -(dd * dd) / (2.f * var) - LOG_SQRT_2PI - ls;
+        }
+      }
+    }
+    __syncwarp();
+    for (int q = lane; q < nlive * O; q += 32) {   // action rows out (contiguous)
+      const int rr = (int)(((uint32_t)q * inv_o) >> 16), j = q - rr * O;
+      g.a[row0 * O + q] = aT[j * LD16 + rb + rr];
+    }
+    // ---- env transition (identical arithmetic to linquad_step_kernel)
+    for (int j = slot; j < adim; j += NS) taT[j * LD16 + rs] = tanhf(aT[j * LD16 + rs]);
+    if (slot == NS - 1 && g.logp) {
+      float logp = 0.f;
+      for (int j = 0; j < O; ++j) logp += OT[j * LD16 + rs];
+      if (live) g.logp[row0 - rb + rs] = logp;
+    }
+    const unsigned long long tick = tick0 + (unsigned long long)step;
+    // env noise: lane (stream, pair slot) owns the dimension pairs slot, slot + NS, ... (one Philox block + one Box-Muller per pair)
+    for (int k0 = 2 * slot; k0 < sdim; k0 += 2 * NS) {
+      const Philox4 p = philox4x32_10(g.seed_env, tick, (uint64_t)(live ? e : 0) * 16 + (k0 >> 2));
+      float x0, x1;
+      if ((k0 & 2) == 0) box_muller(p.x, p.y, x0, x1); else box_muller(p.z, p.w, x0, x1);
+      nzT[k0 * LD16 + rs] = x0;
+      if (k0 + 1 < sdim) nzT[(k0 + 1) * LD16 + rs] = x1;
+    }
+    __syncwarp();
+    // s'[kk] of RPT streams per lane: one scalar (matrix entry) + one RPT-wide load per RPT FFMA
+    for (int kk = jg; kk < sdim; kk += 16) {
+      float v[RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) v[i] = 0.f;
+      const float *ar = sA + kk * sdim, *br = sB + kk * adim;
+#pragma unroll 4
+      for (int j = 0; j < sdim; ++j) {
+        float x[RPT];
+        ld_rows<RPT>(XT + j * LD16 + r0, x);
+        const float c = ar[j];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) v[i] = fmaf(c, x[i], v[i]);
+      }
+#pragma unroll 2
+      for (int j = 0; j < adim; ++j) {
+        float x[RPT];
+        ld_rows<RPT>(taT + j * LD16 + r0, x);
+        const float c = br[j];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) v[i] = fmaf(c, x[i], v[i]);
+      }
+      float nz[RPT];
+      ld_rows<RPT>(nzT + kk * LD16 + r0, nz);
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) v[i] = fminf(fmaxf(fmaf(0.01f, nz[i], v[i]), -10.f), 10.f);
+      st_rows<RPT>(spT + kk * LD16 + r0, v);
+    }
+    __syncwarp();
+    // |s'|^2 in the exact order of linquad_step_kernel: 8 sequential 4-dim partials, combined below like the xor-1/2/4 butterfly
+    for (int q = slot; q < 8; q += NS) {
+      float n2 = 0.f;
+      for (int i = 0; i < 4 && 4 * q + i < sdim; ++i) { const float v = spT[(4 * q + i) * LD16 + rs]; n2 = fmaf(v, v, n2); }
+      taT[q * LD16 + rs] = n2;
+    }
+    __syncwarp();
+    if (slot == 0) {   // reward, termination and episode bookkeeping of stream rs
+      float pq[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pq[q] = taT[q * LD16 + rs];
+      const float n2 = ((pq[0] + pq[1]) + (pq[2] + pq[3])) + ((pq[4] + pq[5]) + (pq[6] + pq[7]));
+      float a2 = 0.f;
+      for (int j = 0; j < adim; ++j) { const float av = aT[j * LD16 + rs]; a2 = fmaf(av, av, a2); }
+      const float rew = 1.f - n2 / (float)sdim - 0.1f * a2 / (float)adim;
+      const bool dn = fabsf(spT[rs]) > 5.f;
+      const int len = s_len[rs] + 1;
+      const bool end = dn || len >= g.max_steps || (g.force_end && step == g.T - 1);
+      s_len[rs] = end ? 0 : len;
+      s_end[rs] = end ? 1 : 0;
+      if (live) { g.r[row0 - rb + rs] = rew; g.done[row0 - rb + rs] = dn ? 1 : 0; g.ee[row0 - rb + rs] = end ? 1 : 0; }
+    }
+    __syncwarp();
+    // ---- s' rows out (contiguous); next observation tile: s', or a fresh initial state where the episode ended
+    for (int q = lane; q < WS * sdim; q += 32) {
+      const int rr = (int)(((uint32_t)q * inv_s) >> 16), kk = q - rr * sdim;
+      const float v = spT[kk * LD16 + rb + rr];
+      if (rr < nlive) g.sp[row0 * sdim + q] = v;
+      XT[kk * LD16 + rb + rr] = v;
+    }
+    __syncwarp();
+    if (s_end[rs]) {   // rare outside the forced end of the rollout: one Philox block yields 4 dimensions of the reset state
+      for (int blk = slot; 4 * blk < sdim; blk += NS) {
+        const Philox4 p = philox4x32_10(g.seed_env ^ 0x5851F42D4C957F2DULL, tick + 0x100000000ULL, (uint64_t)(live ? e : 0) * 16 + blk);
+        const uint32_t u[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (4 * blk + c < sdim) XT[(4 * blk + c) * LD16 + rs] = (u32_to_unit_open(u[c]) * 2.f - 1.f) * 0.1f;
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int q = t; q < R16 * sdim; q += NTH) {
+    const int rr = q / sdim, i = q - rr * sdim;
+    if (rr < rows && e0 + rr < g.N) g.obs_io[(e0 + rr) * sdim + i] = XT[i * LD16 + rr];
+  }
+  if (t < rows && e0 + t < g.N) g.ep_len[e0 + t] = s_len[t];
+  // the last block to finish advances the env tick by T (every block has read it by then)
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (t == 0) last = atomicAdd(g.tick_dev + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL;
+  __syncthreads();
+  if (last && t == 0) { g.tick_dev[0] += (unsigned long long)g.T; g.tick_dev[1] = 0ULL; __threadfence(); }
+}
+
 }  // namespace
 
 extern "C" int32_t crux_linquad_rollout(crux_linquad *env, crux_gaussian *actor, int32_t T, int32_t force_end_last, float *obs_io,
@@ -2503,7 +2756,12 @@ extern "C" int32_t crux_linquad_rollout(crux_linquad *env, crux_gaussian *actor,
   CRUX_REQUIRE(ctx, actor->mu->dims[0] == env->sdim && actor->adim == env->adim && env->adim <= MAX_O, "crux_linquad_rollout: policy / env shapes differ");
   int rc = set_smem_attr(ctx); if (rc) return rc;
   static bool attr = false;
-  if (!attr) { CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(rollout_linquad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMapT<R>::BYTES)); attr = true; }
+  if (!attr) {
+    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(rollout_linquad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMapT<R>::BYTES));
+    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(rollout_linquad_kernel_rt<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMapT<R>::BYTES));
+    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(rollout_linquad_kernel_rt<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemMapT<R>::BYTES));
+    attr = true;
+  }
   RolloutArgs g;
   memset(&g, 0, sizeof(g));
   g.net = describe(actor->mu); g.ls = actor->log_sigma; g.A = env->A; g.B = env->B; g.N = env->n_env; g.T = T; g.adim = env->adim;
@@ -2515,7 +2773,11 @@ extern "C" int32_t crux_linquad_rollout(crux_linquad *env, crux_gaussian *actor,
   g.rows = (int)i64max(1, i64min(R16, cdiv(env->n_env, (int64_t)2 * ctx->num_sms)));
   {
     CruxTimed timed(ctx, CRUX_T_ENV);
-    rollout_linquad_kernel<<<(unsigned)cdiv(env->n_env, g.rows), NT, SmemMapT<R>::BYTES, ctx->stream>>>(g);
+    static const int rpt = getenv("CRUX_ROLLOUT_RPT") ? atoi(getenv("CRUX_ROLLOUT_RPT")) : 2;   // A/B: streams per thread (1 = the half-warp-per-stream kernel)
+    const unsigned grid = (unsigned)cdiv(env->n_env, g.rows);
+    if (rpt == 1) rollout_linquad_kernel<<<grid, NT, SmemMapT<R>::BYTES, ctx->stream>>>(g);
+    else if (rpt == 4) rollout_linquad_kernel_rt<4><<<grid, 64, SmemMapT<R>::BYTES, ctx->stream>>>(g);
+    else rollout_linquad_kernel_rt<2><<<grid, 128, SmemMapT<R>::BYTES, ctx->stream>>>(g);
   }
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;

@@ -434,10 +434,12 @@ def test_native_rollout_loop_equals_python_loop(crux, ctx):
     assert ee[-1].all() and 0 < ee[:-1].mean() < 0.5
 
 
-def test_persistent_device_rollout_equals_step_kernels(crux, ctx):
+@pytest.mark.parametrize("n", [1000, 4100, 37, 4736])
+def test_persistent_device_rollout_equals_step_kernels(crux, ctx, n):
     """crux_linquad_rollout (T vector steps in one persistent launch) is bit-identical to T x (crux_rollout_step +
-    crux_linquad_step): same noise counters, same FMA order, same bookkeeping."""
-    n, T, max_steps = 1000, 20, 7   # not a multiple of the 16-stream CTA tile
+    crux_linquad_step): same noise counters, same FMA order, same bookkeeping.  The stream counts exercise 4-, 14- and 16-stream CTA
+    tiles (a warp owns 8 streams: full, partial and empty second warps), a single-stream tile and a ragged last CTA."""
+    T, max_steps = 20, 7
     outs = []
     for force_steps in (False, True):
         pi = _actor_critic(crux, ctx, seed=21)
