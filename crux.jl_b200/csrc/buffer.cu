@@ -365,7 +365,7 @@ int32_t crux_buffer_push(crux_buffer *b, int64_t n_rows, int32_t n_src_cols, con
   CRUX_REQUIRE(ctx, n_rows >= 0 && n_src_cols >= 0, "crux_buffer_push: negative count");
   if (first_index_out) *first_index_out = b->next_ind;
   if (n_rows == 0) return CRUX_OK;
-  CRUX_REQUIRE(ctx, col_ids && col_ptrs, "crux_buffer_push: NULL column table");
+  CRUX_REQUIRE(ctx, n_src_cols == 0 || (col_ids && col_ptrs), "crux_buffer_push: NULL column table");
   const int64_t C = b->capacity, start = b->next_ind;
   const int64_t j0 = n_rows > C ? n_rows - C : 0;  // N > capacity: the later rows win (experience_buffer.jl:236,249-252)
   const int32_t *ids_dev = ids;

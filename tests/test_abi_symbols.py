@@ -62,3 +62,30 @@ def test_split_batches_host_abi(crux):
         assert list(out) == want
     out = (C.c_int64 * 1)()
     assert lib.crux_split_batches(100, (C.c_double * 1)(0.4), 1, out) != 0  # @assert sum(fracs) ≈ 1
+
+
+def test_c_client_struct_layouts_match_ctypes():
+    """tests/abi_smoke.c (plain C, built by build()) prints sizeof / offsetof of every struct that crosses the ABI: they must equal the
+    ctypes Structures' and the constants the Julia package asserts in julia/CruxB200.jl/test/runtests.jl."""
+    import ctypes as C
+    import subprocess
+    import __graft_entry__ as g
+    from crux_b200 import _abi
+    exe = g.build_abi_smoke()
+    out = subprocess.run([exe, "layout"], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    seen = {}
+    for line in out:
+        tok = line.split()
+        seen[tok[0]] = (int(tok[1]), {tok[i]: int(tok[i + 1]) for i in range(2, len(tok), 2)})
+    for name, cls in (("crux_ppo_hp", _abi.PPOHp), ("crux_lagrange_hp", _abi.LagrangeHp), ("crux_rollout_cols", _abi.RolloutCols),
+                      ("crux_col_desc", _abi.ColDesc)):
+        size, offs = seen[name]
+        assert size == C.sizeof(cls), name
+        for f, o in offs.items():
+            assert getattr(cls, f).offset == o, (name, f)
+    assert seen["abi_version"][0] == 1
+    # the same numbers, as julia/CruxB200.jl/test/runtests.jl states them
+    jl = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "julia", "CruxB200.jl", "test", "runtests.jl")).read()
+    for name in ("PPOHp", "LagrangeHp", "RolloutCols", "ColDesc"):
+        c_name = {"PPOHp": "crux_ppo_hp", "LagrangeHp": "crux_lagrange_hp", "RolloutCols": "crux_rollout_cols", "ColDesc": "crux_col_desc"}[name]
+        assert f"sizeof(CruxB200.{name}) == {seen[c_name][0]}" in jl, name
