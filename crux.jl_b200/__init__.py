@@ -8,11 +8,11 @@ from . import _abi  # noqa: F401
 from ._abi import CruxError, NaNError  # noqa: F401
 from .device import Context, default_context  # noqa: F401
 from .spaces import ContinuousSpace, DiscreteSpace, dim, state_space, tovec, whiten  # noqa: F401
-from .policies import (ActorCritic, Chain, ContinuousNetwork, Dense, DiscreteNetwork, DoubleNetwork,  # noqa: F401
+from .policies import (ActorCritic, Chain, ContinuousNetwork, Conv, Dense, DiscreteNetwork, DoubleNetwork,  # noqa: F401
                        FirstExplorePolicy, GaussianNoiseExplorationPolicy, GaussianPolicy, LinearDecaySchedule,
                        MixedPolicy, PolicyParams, SquashedGaussianPolicy, action, action_space, actor, copyto_,
-                       critic, deepcopy, entropy, eps_greedy_policy, exploration, glorot_uniform, identity, logpdf,
-                       polyak_average_, relu, tanh, value)
+                       critic, deepcopy, entropy, eps_greedy_policy, exploration, flatten, glorot_uniform, identity, logpdf,
+                       polyak_average_, relu, scale255, tanh, value)
 from .buffer import (ExperienceBuffer, PriorityParams, buffer_like, mdp_data, prioritized_sample_, rand_, split_batches,  # noqa: F401
                      uniform_sample_)
 from .envs import DeviceLinQuad, HostLinQuad, NativeHostLinQuad, SimpleGridWorld, linquad_matrices  # noqa: F401

@@ -130,6 +130,18 @@ _SIGS = {
     "crux_lagrange_ppo_update": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(PPOHp), C.POINTER(LagrangeHp),
                                  _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp],
     "crux_dqn_train": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "crux_convq_create": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _pp],
+    "crux_convq_destroy": [_vp],
+    "crux_convq_num_params": [_vp, C.POINTER(_i64)],
+    "crux_convq_shape": [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)],
+    "crux_convq_set_params": [_vp, _vp],
+    "crux_convq_get_params": [_vp, _vp],
+    "crux_convq_grads": [_vp, _vp],
+    "crux_convq_set_adam": [_vp, _f64, _f64, _f64, _f64, _f32],
+    "crux_convq_forward": [_vp, _vp, _i32, _i64, _vp],
+    "crux_convq_copy": [_vp, _vp],
+    "crux_convq_polyak": [_vp, _vp, _f32],
+    "crux_convq_dqn_train": [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp],
     "crux_sac_create": [_vp, _vp, _vp, _vp, _vp, _f32, _f32, _f64, _f32, _pp],
     "crux_sac_destroy": [_vp],
     "crux_sac_log_alpha": [_vp, _vp],

@@ -172,7 +172,8 @@ __global__ void adam_kernel(AdamSegs segs, const double *__restrict__ part, int 
   for (int q = 0; q < segs.n; ++q) {
     const AdamSeg sg = segs.s[q];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += (int64_t)gridDim.x * blockDim.x) {
-      const double g = (double)sg.g[i];
+      double g = (double)sg.g[i];
+      if (segs.clip > 0.f) g = fmin(fmax(g, -(double)segs.clip), (double)segs.clip);   // ClipValue (examples/rl/atari.jl:10)
       const float mt = (float)(beta1 * (double)sg.m[i] + (1.0 - beta1) * g);
       const float vt = (float)(beta2 * (double)sg.v[i] + (1.0 - beta2) * g * g);
       sg.m[i] = mt; sg.v[i] = vt;

@@ -43,7 +43,7 @@ int mlp_backward(crux_mlp *mlp, const float *x, int64_t B, float *dY, bool need_
 // Flux `train!` tail (training.jl:18-21) for up to 4 parameter segments sharing one optimiser:
 // gnorm = ||g||_2 (NaN -> sticky CRUX_FLAG_NAN, no update), then the Adam step.
 struct AdamSeg { float *p; float *g; float *m; float *v; int64_t n; };
-struct AdamSegs { AdamSeg s[4]; int n; };
+struct AdamSegs { AdamSeg s[4]; int n; float clip = 0.f; };   // clip > 0: Flux.Optimiser(ClipValue(clip), Adam(...)) -- every gradient entry clamped to [-clip, clip] before Adam
 // step_dev: device step counter (incremented here).  gnorm_out_dev nullable.  skip_dev nullable: *skip != 0 -> no-op.
 int adam_step_segments(crux_ctx *ctx, const AdamSegs &segs, double eta, double beta1, double beta2, double eps,
                        int *step_dev, float *gnorm_out_dev, const int *skip_dev, double *norm_part);

@@ -2,6 +2,7 @@
 // one SAC value_training epoch (rl/sac.jl:4-52): target -> temperature -> double-Q critic -> actor -> polyak,
 // and one DDPG / TD3 epoch (rl/ddpg.jl:6-25, rl/td3.jl:4-12): (smoothed) target -> critic(s) -> deterministic actor -> polyak.
 #include "policy.cuh"
+#include "conv.cuh"
 
 namespace {
 
@@ -328,6 +329,36 @@ int32_t crux_dqn_train(crux_mlp *q, const float *s, const float *a_onehot, const
   dqn_record_kernel<<<1, 1, 0, ctx->stream>>>(sums, (float)B, ctx->world, info_dev);
   CRUX_LAUNCHED(ctx);
   rc = mlp_adam_step(q, info_dev + 1, nullptr); if (rc) return rc;
+  if (info_out_host) {
+    CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(info_out_host, info_dev, 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return crux_ctx_check(ctx);
+  }
+  return CRUX_OK;
+}
+
+int32_t crux_convq_dqn_train(crux_convq *net, const void *s, int32_t s_is_u8, const float *a_onehot, const float *y, const float *weight, int64_t B,
+                             float *info_out_host) {
+  if (!net) return CRUX_ERR_INVALID;
+  crux_ctx *ctx = net->ctx;
+  CRUX_REQUIRE(ctx, B >= 1 && s && a_onehot && y, "crux_convq_dqn_train: bad arguments");
+  CRUX_REQUIRE(ctx, ctx->world == 1, "crux_convq_dqn_train: single rank only (the conv gradients are not exchanged yet)");
+  crux_mlp *h = net->head;
+  const int L = h->n_layers, nA = h->dims[L];
+  int rc = convq_forward_keep(net, s, s_is_u8, B); if (rc) return rc;
+  const int nb = (int)i64min(cdiv(B, 256), 256);
+  char *sc = (char *)crux_scratch(ctx, 3, 512 * sizeof(double) + 64);
+  if (!sc) return CRUX_ERR_OOM;
+  float *info_dev = (float *)sc;
+  double *part = (double *)(sc + 64);
+  dqn_head_kernel<<<nb, 256, 0, ctx->stream>>>(h->act[L], a_onehot, y, weight, B, nA, 1.0f / (float)B, h->dz[L], part);
+  CRUX_LAUNCHED(ctx);
+  float *sums = h->grads + h->n_params + 64;
+  dqn_finalize_kernel<<<1, 32, 0, ctx->stream>>>(part, nb, sums);
+  CRUX_LAUNCHED(ctx);
+  rc = convq_backward(net, s, s_is_u8, B, h->dz[L]); if (rc) return rc;
+  dqn_record_kernel<<<1, 1, 0, ctx->stream>>>(sums, (float)B, 1, info_dev);
+  CRUX_LAUNCHED(ctx);
+  rc = convq_adam_step(net, info_dev + 1); if (rc) return rc;
   if (info_out_host) {
     CRUX_CHECK_CUDA(ctx, cudaMemcpyAsync(info_out_host, info_dev, 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     return crux_ctx_check(ctx);

@@ -36,15 +36,53 @@ class Dense:
         self.bias = np.zeros(out, dtype=np.float32) if bias is None else np.asarray(bias, dtype=np.float32).reshape(out)
 
 
+class Conv:
+    """``Flux.Conv((k, k), cin => cout, σ; stride)``: weight ``[kw, kh, cin, cout]`` (held here as its memory ``[cout, cin, kh, kw]``), bias
+    ``[cout]``; a true convolution (flipped kernel), no padding (the defaults of examples/rl/atari.jl:8)."""
+
+    def __init__(self, k, cin, cout, act=identity, stride=1, weight=None, bias=None, rng=None):
+        k = k[0] if isinstance(k, (tuple, list)) else k
+        self.k, self.cin, self.cout, self.stride = int(k), int(cin), int(cout), int(stride)
+        self.act = _ACT.get(act, act)
+        rng = rng if rng is not None else np.random.default_rng()
+        lim = math.sqrt(6.0 / (self.k * self.k * (self.cin + self.cout)))     # Flux.glorot_uniform on the 4-d array
+        self.weight = (((rng.random((cout, cin, self.k, self.k), dtype=np.float32) * 2 - 1) * lim).astype(np.float32) if weight is None
+                       else np.asarray(weight, dtype=np.float32).reshape(cout, cin, self.k, self.k))
+        self.bias = np.zeros(cout, dtype=np.float32) if bias is None else np.asarray(bias, dtype=np.float32).reshape(cout)
+
+
+class _Marker:
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return self.name
+
+
+flatten = _Marker("flatten")      # Flux.flatten
+scale255 = _Marker("x -> x ./ 255f0")
+
+
 class Chain:
     def __init__(self, *layers):
         self.layers = list(layers)
         for a, b in zip(self.layers[:-1], self.layers[1:]):
-            assert a.out == b.inp, "Chain: layer widths do not match"
+            if isinstance(a, Dense) and isinstance(b, Dense):
+                assert a.out == b.inp, "Chain: layer widths do not match"
+
+    @property
+    def is_conv(self):
+        return any(isinstance(l, Conv) for l in self.layers)
 
     def flat(self):
-        """Flux.params order, W in Julia memory order (row-major [in][out])."""
-        return np.concatenate([np.concatenate([l.weight.T.reshape(-1), l.bias]) for l in self.layers]).astype(np.float32)
+        """Flux.params order, W in Julia memory order (Dense: row-major [in][out]; Conv: [cout][cin][kh][kw])."""
+        parts = []
+        for l in self.layers:
+            if isinstance(l, Dense):
+                parts += [l.weight.T.reshape(-1), l.bias]
+            elif isinstance(l, Conv):
+                parts += [l.weight.reshape(-1), l.bias]
+        return np.concatenate(parts).astype(np.float32)
 
 
 class Policy:
@@ -110,6 +148,16 @@ class _MLP:
         self.ctx.check(self.ctx.lib.crux_value_next(self.h, ptr(sp), ptr(s), ptr(v_s), T, N, ptr(out)))
         return out
 
+    def train_dqn(self, s, a_onehot, y, weight, B, info=None):
+        """one DQN critic ``train!`` (off_policy.jl:91-93 with td_loss)"""
+        self.ctx.check(self.ctx.lib.crux_dqn_train(self.h, ptr(s), ptr(a_onehot), ptr(y), ptr(weight), B, None if info is None else ptr(info)))
+
+    def polyak_from(self, frm, tau):
+        self.ctx.check(self.ctx.lib.crux_mlp_polyak(self.h, frm.h, float(tau)))
+
+    def copy_from(self, frm):
+        self.ctx.check(self.ctx.lib.crux_mlp_copy(self.h, frm.h))
+
     def forward_sa(self, s, a):
         s, a = _as_dev(self.ctx, s), _as_dev(self.ctx, a)
         B = s.shape[0]
@@ -121,6 +169,90 @@ class _MLP:
         try:
             if getattr(self, "h", None) and self.ctx.h:
                 self.ctx.lib.crux_mlp_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class _ConvNet:
+    """Owner of one crux_convq handle: ``Chain([scale255,] Conv, Conv, flatten, Dense, Dense)`` over ``[C, H, W]`` observations (u8 or f32).
+    Same surface as ``_MLP`` where the DQN paths use it (forward, flat parameters, Adam, train_dqn, polyak / copy)."""
+
+    def __init__(self, chain, input_dims, ctx=None):
+        self.ctx = ctx or default_context()
+        self.chain = chain
+        ls = [l for l in chain.layers if l is not flatten and l is not scale255]
+        assert (len(ls) == 4 and isinstance(ls[0], Conv) and isinstance(ls[1], Conv) and isinstance(ls[2], Dense) and isinstance(ls[3], Dense)
+                and ls[0].act == relu and ls[1].act == relu and ls[2].act == relu and ls[3].act == identity), \
+            "the pixel network is Chain([x -> x ./ 255f0,] Conv(relu), Conv(relu), flatten, Dense(relu), Dense) (examples/rl/atari.jl:8)"
+        W, H, Cin = (int(d) for d in input_dims)                 # Julia (w, h, c) like ContinuousSpace((84, 84, 4))
+        c1, c2, d1, d2 = ls
+        assert c1.cin == Cin and c2.cin == c1.cout and d2.inp == d1.out
+        self.input_shape = (Cin, H, W)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.crux_convq_create(self.ctx.h, Cin, H, W, 1 if scale255 in chain.layers else 0, c1.k, c1.stride, c1.cout,
+                                                      c2.k, c2.stride, c2.cout, d1.out, d2.out, C.byref(h)))
+        self.h = h
+        F = C.c_int32()
+        self.ctx.check(self.ctx.lib.crux_convq_shape(self.h, C.byref(F), None, None, None, None))
+        assert d1.inp == F.value, f"Dense after flatten expects {d1.inp} inputs, the convolutions produce {F.value}"
+        self.dims = [Cin * H * W, d2.out]
+        self.acts = []
+        self.set_flat(chain.flat())
+
+    @property
+    def n_params(self):
+        n = C.c_int64()
+        self.ctx.check(self.ctx.lib.crux_convq_num_params(self.h, C.byref(n)))
+        return n.value
+
+    def set_flat(self, flat):
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        assert flat.size == self.n_params
+        self.ctx.check(self.ctx.lib.crux_convq_set_params(self.h, ptr(flat)))
+
+    def get_flat(self):
+        out = np.empty(self.n_params, dtype=np.float32)
+        self.ctx.check(self.ctx.lib.crux_convq_get_params(self.h, ptr(out)))
+        return out
+
+    def grads(self):
+        out = np.empty(self.n_params, dtype=np.float32)
+        self.ctx.check(self.ctx.lib.crux_convq_grads(self.h, ptr(out)))
+        return out
+
+    def set_adam(self, eta=np.float32(3e-4), beta=(0.9, 0.999), eps=1e-8, clip_value=0.0):
+        self.ctx.check(self.ctx.lib.crux_convq_set_adam(self.h, float(eta), float(beta[0]), float(beta[1]), float(eps), float(clip_value)))
+
+    def _obs(self, x):
+        if not isinstance(x, torch.Tensor):
+            x = torch.as_tensor(np.ascontiguousarray(x))
+        x = x.to(self.ctx.device)
+        if x.dtype != torch.uint8:
+            x = x.to(torch.float32)
+        x = x.reshape(-1, self.dims[0]).contiguous()
+        return x, 1 if x.dtype == torch.uint8 else 0
+
+    def forward(self, x, out=None):
+        x, u8 = self._obs(x)
+        out = self.ctx.empty((x.shape[0], self.dims[-1])) if out is None else out
+        self.ctx.check(self.ctx.lib.crux_convq_forward(self.h, ptr(x), u8, x.shape[0], ptr(out)))
+        return out
+
+    def train_dqn(self, s, a_onehot, y, weight, B, info=None):
+        s, u8 = self._obs(s)
+        self.ctx.check(self.ctx.lib.crux_convq_dqn_train(self.h, ptr(s), u8, ptr(a_onehot), ptr(y), ptr(weight), B, None if info is None else ptr(info)))
+
+    def polyak_from(self, frm, tau):
+        self.ctx.check(self.ctx.lib.crux_convq_polyak(self.h, frm.h, float(tau)))
+
+    def copy_from(self, frm):
+        self.ctx.check(self.ctx.lib.crux_convq_copy(self.h, frm.h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.ctx.h:
+                self.ctx.lib.crux_convq_destroy(self.h)
                 self.h = None
         except Exception:
             pass
@@ -158,9 +290,14 @@ class ContinuousNetwork(NetworkPolicy):
 class DiscreteNetwork(NetworkPolicy):
     """policies.jl:104-157.  Actions cross as one-hot rows (``a_oh``)."""
 
-    def __init__(self, network, outputs, always_stochastic=False, ctx=None, temperature=1.0):
+    def __init__(self, network, outputs, always_stochastic=False, ctx=None, temperature=1.0, input_dims=None):
         self.network = network
-        self.mlp = _MLP(network, ctx)
+        self.input_dims = input_dims
+        if getattr(network, "is_conv", False):
+            assert input_dims is not None, "a convolutional DiscreteNetwork needs input_dims = (w, h, c) (Flux infers it from the first input)"
+            self.mlp = _ConvNet(network, input_dims, ctx)          # pixel DQN (examples/rl/atari.jl:8)
+        else:
+            self.mlp = _MLP(network, ctx)
         self.ctx = self.mlp.ctx
         self.outputs = list(outputs)
         self.always_stochastic = always_stochastic
@@ -359,7 +496,7 @@ def _mlps(pi):
 def polyak_average_(to, frm, tau=1.0):
     """``polyak_average!(to, from, τ)`` policies.jl:48-59: to ← τ·from + (1-τ)·to for every parameter array."""
     for t, f in zip(_mlps(to), _mlps(frm)):
-        t.ctx.check(t.ctx.lib.crux_mlp_polyak(t.h, f.h, float(tau)))
+        t.polyak_from(f, tau)
     if isinstance(actor(to), GaussianPolicy) and actor(to).log_sigma is not None:
         lt, lf = actor(to).log_sigma, actor(frm).log_sigma
         lt.copy_(np.float32(tau) * lf + (np.float32(1) - np.float32(tau)) * lt)
@@ -368,7 +505,7 @@ def polyak_average_(to, frm, tau=1.0):
 def copyto_(to, frm):
     """``copyto!(to, from)`` policies.jl:61-65."""
     for t, f in zip(_mlps(to), _mlps(frm)):
-        t.ctx.check(t.ctx.lib.crux_mlp_copy(t.h, f.h))
+        t.copy_from(f)
     if isinstance(actor(to), GaussianPolicy) and actor(to).log_sigma is not None:
         actor(to).log_sigma.copy_(actor(frm).log_sigma)
 
@@ -393,6 +530,10 @@ def deepcopy(pi):
     if isinstance(pi, GaussianPolicy):
         return GaussianPolicy(deepcopy(pi.mu), pi.log_sigma.cpu().numpy(), pi.always_stochastic)
     if isinstance(pi, DiscreteNetwork):
+        if isinstance(pi.mlp, _ConvNet):
+            cp = DiscreteNetwork(pi.network, pi.outputs, pi.always_stochastic, pi.ctx, pi.temperature, pi.input_dims)
+            cp.mlp.copy_from(pi.mlp)
+            return cp
         return DiscreteNetwork(chain_of(pi.mlp), pi.outputs, pi.always_stochastic, pi.ctx, pi.temperature)
     if isinstance(pi, ContinuousNetwork):
         return ContinuousNetwork(chain_of(pi.mlp), pi.output_dim, pi.ctx)

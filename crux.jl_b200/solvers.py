@@ -29,10 +29,11 @@ F32 = np.float32
 
 
 class Adam:
-    """``Flux.Adam(η, β, ϵ)`` [3P]: float32 moments, Float64 scalars."""
+    """``Flux.Adam(η, β, ϵ)`` [3P]: float32 moments, Float64 scalars.  ``clip_value`` > 0 is
+    ``Flux.Optimiser(ClipValue(clip_value), Adam(η, β, ϵ))`` (examples/rl/atari.jl:10), implemented for the pixel network."""
 
-    def __init__(self, eta=F32(3e-4), beta=(0.9, 0.999), eps=1e-8):
-        self.eta, self.beta, self.eps = float(eta), (float(beta[0]), float(beta[1])), float(eps)
+    def __init__(self, eta=F32(3e-4), beta=(0.9, 0.999), eps=1e-8, clip_value=0.0):
+        self.eta, self.beta, self.eps, self.clip_value = float(eta), (float(beta[0]), float(beta[1])), float(eps), float(clip_value)
 
 
 class TrainingParams:
@@ -57,7 +58,10 @@ def _dom(seed, domain):
 
 
 def _set_adam(mlp, opt):
-    mlp.set_adam(opt.eta, opt.beta, opt.eps)
+    if getattr(opt, "clip_value", 0.0):
+        mlp.set_adam(opt.eta, opt.beta, opt.eps, clip_value=opt.clip_value)    # only the pixel network takes it: others raise TypeError
+    else:
+        mlp.set_adam(opt.eta, opt.beta, opt.eps)
 
 
 # =============================================================================================== on-policy
@@ -375,7 +379,7 @@ class OffPolicySolver:
                     self.buffer.update_priorities_(D.indices_dev(), td)
                 w = D.column("weight") if (self.weighted_loss and "weight" in D.schema) else None
                 if epoch % self.c_opt.update_every == 0:
-                    ctx.check(lib.crux_dqn_train(pi.mlp.h, ptr(s), ptr(a), ptr(y), ptr(w), B, None))                 # off_policy.jl:91-93
+                    pi.mlp.train_dqn(s, a, y, w, B)                                                                   # off_policy.jl:91-93
             elif self.kind in ("ddpg", "td3"):
                 sm = self.P.get("pi_smooth")                      # None: plain ddpg_target (rl/ddpg.jl:6-8)
                 e = None if noise is None else ctx.to_device(noise[epoch], torch.float32)

@@ -279,6 +279,33 @@ int32_t crux_lagrange_ppo_update(crux_gaussian *actor, crux_mlp *critic, crux_ml
 int32_t crux_dqn_train(crux_mlp *q, const float *s, const float *a_onehot, const float *y,
                        const float *weight /* nullable */, int64_t B, float *info_out_host);
 
+/* Pixel-DQN network (examples/rl/atari.jl:8):
+ *   Chain(x -> x ./ 255f0, Conv((k1,k1), C => c1, relu, stride = s1), Conv((k2,k2), c1 => c2, relu, stride = s2), flatten,
+ *         Dense(F, hidden, relu), Dense(hidden, nA))                F = c2 * OH2 * OW2
+ * Observations are [B][C][H][W] with W fastest (the memory of a Flux WHCN array), uint8 (s_is_u8 = 1: the replay buffer keeps pixels as
+ * bytes, the conversion and the 1/255 scale are fused into the first layer's operand fetch) or float32.  Flux's Conv is a true convolution
+ * (flipped kernel), no padding, dilation 1.  Flat parameters in Flux.params order and memory: W1 [kw,kh,ci,co] | b1 | W2 | b2 | Dense
+ * W [out,in] | b | ...  scale255 = 0 drops the leading scale layer.  Channels per conv layer <= 32. */
+typedef struct crux_convq crux_convq;
+int32_t crux_convq_create(crux_ctx *ctx, int32_t C, int32_t H, int32_t W, int32_t scale255, int32_t k1, int32_t s1, int32_t c1,
+                          int32_t k2, int32_t s2, int32_t c2, int32_t hidden, int32_t nA, crux_convq **out);
+int32_t crux_convq_destroy(crux_convq *net);
+int32_t crux_convq_num_params(crux_convq *net, int64_t *out);
+int32_t crux_convq_shape(crux_convq *net, int32_t *flatten_out, int32_t *oh1, int32_t *ow1, int32_t *oh2, int32_t *ow2);
+int32_t crux_convq_set_params(crux_convq *net, const float *flat_host);
+int32_t crux_convq_get_params(crux_convq *net, float *flat_host); /* synchronises */
+int32_t crux_convq_grads(crux_convq *net, float *flat_host);      /* gradient of the last train step (parity hook; synchronises) */
+/* Flux.Optimiser(ClipValue(clip_value), Adam(eta, (beta1, beta2), eps)) (atari.jl:10); clip_value = 0: plain Adam.  Resets the moments. */
+int32_t crux_convq_set_adam(crux_convq *net, double eta, double beta1, double beta2, double eps, float clip_value);
+/* value(π, s): Q values [B][nA] */
+int32_t crux_convq_forward(crux_convq *net, const void *s, int32_t s_is_u8, int64_t B, float *q_out);
+int32_t crux_convq_copy(crux_convq *to, crux_convq *from);
+int32_t crux_convq_polyak(crux_convq *to, crux_convq *from, float tau);
+/* One DQN critic `train!` like crux_dqn_train on the pixel network: forward, td_loss head, backward through the head and both
+ * convolutions, ||g||, [ClipValue] + Adam.  info_out_host[0..2] = loss, grad_norm, Qavg (NULL skips the readback).  Single rank. */
+int32_t crux_convq_dqn_train(crux_convq *net, const void *s, int32_t s_is_u8, const float *a_onehot, const float *y,
+                             const float *weight /* nullable */, int64_t B, float *info_out_host);
+
 /* One SAC value_training epoch (off_policy.jl:66-111 with rl/sac.jl:4-52) on a sampled minibatch:
  * target -> temperature step -> double-Q critic step -> actor step -> polyak of the targets.
  *   eps_target / eps_temp / eps_actor : [B][adim] noise for the three exploration() draws (NULL => Philox)
