@@ -86,7 +86,28 @@ out["c3_dqn_per"] = {
     "scan_bytes": 8 * rows, "push_4096_rows_ms": ms_push, "push_GBps": 2 * push_rows * row_bytes / (ms_push * 1e-3) / 1e9,
     "note": "u8 observations stay u8 in HBM (56 GB for 1M rows); sample = device prefix scan (when priorities changed) + stratified binary search "
             "+ IS weights + row gather of s, sp, a, r, done, weight"}
-del buf, tgt
+# the whole DQN + PER update on the pixel network of examples/rl/atari.jl:8 (value_training, off_policy.jl:66-111): prioritized sample ->
+# Q-(sp) and dqn_target -> Q(s), td_error, update_priorities! -> weighted td_loss train! (ClipValue(1) + Adam(1e-3)); polyak once per call
+rngc = np.random.default_rng(5)
+chain = crux.Chain(crux.scale255, crux.Conv((8, 8), 4, 16, crux.relu, stride=4, rng=rngc), crux.Conv((4, 4), 16, 32, crux.relu, stride=2, rng=rngc), crux.flatten,
+                   crux.Dense(2592, 256, crux.relu, rng=rngc), crux.Dense(256, 4, rng=rngc))
+piq = crux.DiscreteNetwork(chain, [0, 1, 2, 3], ctx=ctx, input_dims=(84, 84, 4))
+Sq = crux.DQN(piq, S, N=10, dN=1, c_opt=dict(batch_size=B, epochs=1, optimizer=crux.Adam(F32(1e-3), clip_value=1.0)), buffer=buf, prioritized=True,
+              weighted_loss=True, buffer_init=0)
+Dq = crux.buffer_like(buf, capacity=B)
+ms_update = timed(lambda: Sq.value_training(Dq, F32(0.99)), reps=20)
+sB = Dq.column("s")
+ms_fwd = timed(lambda: piq.mlp.forward(sB), reps=20)
+yB, aB, wB = torch.randn(B, device=ctx.device), Dq.column("a"), torch.rand(B, device=ctx.device)
+ms_train = timed(lambda: piq.mlp.train_dqn(sB, aB, yB, wB, B), reps=20)
+f_fwd = 2 * (400 * 16 * 256 + 81 * 32 * 256 + 2592 * 256 + 256 * 4)        # forward FLOP per sample
+out["c3_dqn_per"].update({
+    "pixel_dqn_update_ms": ms_update, "pixel_dqn_samples_per_s": B * 1e3 / ms_update,
+    "conv_forward_ms": ms_fwd, "conv_forward_TFLOPs": B * f_fwd / (ms_fwd * 1e-3) / 1e12,
+    "conv_train_step_ms": ms_train, "conv_train_step_TFLOPs": 3 * B * f_fwd / (ms_train * 1e-3) / 1e12,
+    "conv_note": "implicit-GEMM fp32 FFMA convolutions (csrc/conv.cu), u8 observations dequantised inside the operand fetch; one update = PER sample + "
+                 "target forward + priorities + train step + polyak; train step = forward + backward (2 x forward FLOP) + ClipValue/Adam"})
+del buf, tgt, Sq, Dq
 torch.cuda.empty_cache()
 
 # ------------------------------------------------------------------ C4: SAC update, Humanoid-shaped
