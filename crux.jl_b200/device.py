@@ -6,6 +6,7 @@ never hops per call.  torch is used only for device memory, streams and ``torch.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch

@@ -192,3 +192,12 @@ def test_logger_params_defaults_and_log(crux, tmp_path):
     assert crux.aggregate_info([{"a": 1.0, "b": 2.0}, {"a": 3.0}]) == {"a": 2.0, "b": 2.0}
     fe = crux.FirstExplorePolicy(100, None, FakeSampler.agent.pi_explore)
     assert crux.log_exploration(fe)(i=5) == {"first_explore_on": True, "eps": crux.LinearDecaySchedule(1.0, 0.1, 10)(1)}
+
+
+def test_context_helpers_without_a_device(crux, monkeypatch):
+    """Host-only helpers of Context must not need a device (the 2-GPU bench died on a missing import inside peer_ll_active in round 2)."""
+    from types import SimpleNamespace
+    assert crux.Context.peer_ll_active(SimpleNamespace(peer_mapped=True)) is True
+    assert crux.Context.peer_ll_active(SimpleNamespace()) is False
+    monkeypatch.setenv("CRUX_NO_PEER_LL", "1")
+    assert crux.Context.peer_ll_active(SimpleNamespace(peer_mapped=True)) is False
