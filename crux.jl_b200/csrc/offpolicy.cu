@@ -88,16 +88,21 @@ __global__ void sac_sample_kernel(const float *__restrict__ net, int A, float as
 
 // temperature: loss = -mean(exp(logα)(logp + H)); single block: reduce, Flux Adam on the 1-element array.
 // st = {m, v} float, step counter int. info[0] = temp_loss
+// mode 0: the whole step on one rank.  Several ranks: mode 1 leaves this rank's sum of (logp + H) in sum_io[0], the caller all-reduces
+// it, mode 2 applies the step with the mean over all world * B rows (identical on every rank).
 __global__ void sac_temp_kernel(const float *__restrict__ logp, int64_t B, float h_target, float *__restrict__ log_alpha,
                                 float *__restrict__ st, int *__restrict__ step, double eta, float *__restrict__ info,
-                                unsigned int *__restrict__ err_flags) {
+                                unsigned int *__restrict__ err_flags, int mode, int world, float *__restrict__ sum_io) {
   __shared__ double sh[32];
   double s = 0.0;
-  for (int64_t i = threadIdx.x; i < B; i += blockDim.x) s += (double)(logp[i] + h_target);
-  const double tot = block_sum_d(s, sh);
+  if (mode != 2)
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) s += (double)(logp[i] + h_target);
+  double tot = block_sum_d(s, sh);
   if (threadIdx.x == 0) {
+    if (mode == 1) { sum_io[0] = (float)tot; return; }
+    if (mode == 2) tot = (double)sum_io[0];
     const float alpha = expf(log_alpha[0]);
-    const float mean_t = (float)(tot / (double)B);
+    const float mean_t = (float)(tot / ((double)B * (double)world));
     const float loss = -(alpha * mean_t);
     const float g = -(alpha * mean_t);  // d/dlogα of -mean(exp(logα) t) = -exp(logα) mean(t)
     info[0] = loss;
@@ -418,8 +423,12 @@ int32_t crux_sac_train(crux_sac_state *st, const float *s, const float *a, const
   if (!st) return CRUX_ERR_INVALID;
   crux_ctx *ctx = st->ctx;
   CRUX_REQUIRE(ctx, B >= 1 && s && a && sp && r && done, "crux_sac_train: bad arguments");
-  CRUX_REQUIRE(ctx, ctx->world == 1, "crux_sac_train: single rank only (the three optimisers' gradients and the temperature mean are not all-reduced; "
-                                     "run replicas with separate contexts instead)");
+  // Several ranks (replicas with per-rank replay shards): every loss is a mean over the world * B rows of all ranks -- the heads
+  // scale by 1 / (world B), the gradients of the critics and of the actor are summed over ranks before their optimiser steps, the
+  // temperature step uses the all-reduced sum; parameters, targets and log α stay identical on every rank.  Device noise streams are
+  // decorrelated per rank.  Info values are this rank's means.
+  const int world = ctx->world;
+  if (world > 1) seed ^= 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->rank + 1);
   crux_gaussian *pol = st->actor;
   crux_mlp *net = pol->mu;
   const int sdim = net->dims[0], A = pol->adim, ld = sdim + A, La = net->n_layers;
@@ -437,7 +446,7 @@ int32_t crux_sac_train(crux_sac_state *st, const float *s, const float *a, const
   const unsigned rb = (unsigned)cdiv(B, 128);
   const unsigned eb = (unsigned)i64min(cdiv(B * ld, 256), (int64_t)ctx->num_sms * 8);
   const int nb = (int)i64min(cdiv(B, 256), 256);
-  const float inv_b = 1.0f / (float)B;
+  const float inv_b = 1.0f / ((float)B * (float)world);
   int rc;
 
   // 1. y = sac_target (rl/sac.jl:4-9): a' ~ online actor(sp), target critics
@@ -455,9 +464,19 @@ int32_t crux_sac_train(crux_sac_state *st, const float *s, const float *a, const
   rc = mlp_forward_keep(net, s, B, nullptr); if (rc) return rc;
   sac_sample_kernel<<<rb, 128, 0, ctx->stream>>>(net->act[La], A, pol->ascale, eps_temp, seed, ctr + 1, B, nullptr, logp, nullptr);
   CRUX_LAUNCHED(ctx);
-  sac_temp_kernel<<<1, 256, 0, ctx->stream>>>(logp, B, st->h_target, st->log_alpha, st->log_alpha + 1, st->alpha_step, st->alpha_eta,
-                                              st->info, ctx->flags_dev);
-  CRUX_LAUNCHED(ctx);
+  if (world == 1) {
+    sac_temp_kernel<<<1, 256, 0, ctx->stream>>>(logp, B, st->h_target, st->log_alpha, st->log_alpha + 1, st->alpha_step, st->alpha_eta,
+                                                st->info, ctx->flags_dev, 0, 1, nullptr);
+    CRUX_LAUNCHED(ctx);
+  } else {
+    sac_temp_kernel<<<1, 256, 0, ctx->stream>>>(logp, B, st->h_target, st->log_alpha, st->log_alpha + 1, st->alpha_step, st->alpha_eta,
+                                                st->info, ctx->flags_dev, 1, world, st->log_alpha + 3);
+    CRUX_LAUNCHED(ctx);
+    rc = grads_allreduce(ctx, st->log_alpha + 3, 1); if (rc) return rc;
+    sac_temp_kernel<<<1, 32, 0, ctx->stream>>>(logp, B, st->h_target, st->log_alpha, st->log_alpha + 1, st->alpha_step, st->alpha_eta,
+                                               st->info, ctx->flags_dev, 2, world, st->log_alpha + 3);
+    CRUX_LAUNCHED(ctx);
+  }
 
   // 3. critic step (off_policy.jl:91-93, double_Q_loss utils.jl:89-96): one optimiser over (Q1, Q2)
   concat2_kernel<<<eb, 256, 0, ctx->stream>>>(s, sdim, a, A, B, cat);
@@ -471,6 +490,8 @@ int32_t crux_sac_train(crux_sac_state *st, const float *s, const float *a, const
   CRUX_LAUNCHED(ctx);
   rc = mlp_backward(st->q1, cat, B, dq1, false, false, true, nullptr); if (rc) return rc;
   rc = mlp_backward(st->q2, cat, B, dq2, false, false, true, nullptr); if (rc) return rc;
+  rc = grads_allreduce(ctx, st->q1->grads, st->q1->n_params); if (rc) return rc;
+  rc = grads_allreduce(ctx, st->q2->grads, st->q2->n_params); if (rc) return rc;
   {
     AdamSegs segs;
     segs.n = 2;
@@ -500,6 +521,7 @@ int32_t crux_sac_train(crux_sac_state *st, const float *s, const float *a, const
                                                         st->log_alpha, B, inv_b, net->dz[La]);
   CRUX_LAUNCHED(ctx);
   rc = mlp_backward(net, s, B, net->dz[La], false, false, true, nullptr); if (rc) return rc;
+  rc = grads_allreduce(ctx, net->grads, net->n_params); if (rc) return rc;
   rc = mlp_adam_step(net, st->info + 4, nullptr); if (rc) return rc;
 
   // 5. target_update (off_policy.jl:100): polyak τ on the critics (the actor copy inside π⁻ is never read)
@@ -574,7 +596,9 @@ int32_t crux_ddpg_train(crux_ddpg_state *st, const float *s, const float *a, con
   if (!st) return CRUX_ERR_INVALID;
   crux_ctx *ctx = st->ctx;
   CRUX_REQUIRE(ctx, B >= 1 && s && a && sp && r && done, "crux_ddpg_train: bad arguments");
-  CRUX_REQUIRE(ctx, ctx->world == 1, "crux_ddpg_train: single rank only (gradients are not all-reduced; run replicas with separate contexts instead)");
+  // several ranks: like crux_sac_train -- means over world * B rows, gradients summed over ranks before every optimiser step
+  const int world = ctx->world;
+  if (world > 1) seed ^= 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->rank + 1);
   crux_mlp *act = st->actor;
   const int sdim = act->dims[0], La = act->n_layers, A = act->dims[La], ld = sdim + A;
   NoiseBounds nb;
@@ -593,7 +617,7 @@ int32_t crux_ddpg_train(crux_ddpg_state *st, const float *s, const float *a, con
   const unsigned rb = (unsigned)cdiv(B, 128);
   const unsigned eb = (unsigned)i64min(cdiv(B * ld, 256), (int64_t)ctx->num_sms * 8);
   const int nb_ = (int)i64min(cdiv(B, 256), 256);
-  const float inv_b = 1.0f / (float)B;
+  const float inv_b = 1.0f / ((float)B * (float)world);
 
   // 1. target (off_policy.jl:80): a' = action(π⁻, sp) [+ clipped smoothing noise, then the action clamp], y from the TARGET critic(s)
   rc = mlp_forward_out(st->actor_t, sp, B, ap); if (rc) return rc;
@@ -623,6 +647,8 @@ int32_t crux_ddpg_train(crux_ddpg_state *st, const float *s, const float *a, con
       CRUX_LAUNCHED(ctx);
       rc = mlp_backward(st->q1, cat, B, dq1, false, false, true, nullptr); if (rc) return rc;
       rc = mlp_backward(st->q2, cat, B, dq2, false, false, true, nullptr); if (rc) return rc;
+      rc = grads_allreduce(ctx, st->q1->grads, st->q1->n_params); if (rc) return rc;
+      rc = grads_allreduce(ctx, st->q2->grads, st->q2->n_params); if (rc) return rc;
       AdamSegs segs;
       segs.n = 2;
       segs.s[0] = AdamSeg{st->q1->params, st->q1->grads, st->q1->m, st->q1->v, st->q1->n_params};
@@ -636,6 +662,7 @@ int32_t crux_ddpg_train(crux_ddpg_state *st, const float *s, const float *a, con
       q_mse_record_kernel<<<1, 32, 0, ctx->stream>>>(st->part, nb_, B, st->info);
       CRUX_LAUNCHED(ctx);
       rc = mlp_backward(st->q1, cat, B, dq1, false, false, true, nullptr); if (rc) return rc;
+      rc = grads_allreduce(ctx, st->q1->grads, st->q1->n_params); if (rc) return rc;
       rc = mlp_adam_step(st->q1, st->info + 2, nullptr); if (rc) return rc;
     }
   }
@@ -654,6 +681,7 @@ int32_t crux_ddpg_train(crux_ddpg_state *st, const float *s, const float *a, con
     slice_action_grad_kernel<<<(unsigned)i64min(cdiv(B * A, 256), (int64_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(st->q1->dz[0], sdim, A, B, da);
     CRUX_LAUNCHED(ctx);
     rc = mlp_backward(act, s, B, da, false, false, true, nullptr); if (rc) return rc;
+    rc = grads_allreduce(ctx, act->grads, act->n_params); if (rc) return rc;
     rc = mlp_adam_step(act, st->info + 4, nullptr); if (rc) return rc;
     // target_update(π⁻, π) = polyak_average!(π⁻, π, τ) over every parameter of the policy (off_policy.jl:55,100)
     rc = crux_mlp_polyak(st->actor_t, act, st->tau); if (rc) return rc;

@@ -310,7 +310,10 @@ int32_t crux_convq_dqn_train(crux_convq *net, const void *s, int32_t s_is_u8, co
  * target -> temperature step -> double-Q critic step -> actor step -> polyak of the targets.
  *   eps_target / eps_temp / eps_actor : [B][adim] noise for the three exploration() draws (NULL => Philox)
  *   log_alpha_dev : 1 float, trained by Adam(alpha_eta) with moments alpha_state_dev[2] + betas on host side
- * info_out_host[0..7] = temp_loss, critic_loss, critic_grad_norm, actor_loss, actor_grad_norm, entropy, Q1avg, Q2avg */
+ * info_out_host[0..7] = temp_loss, critic_loss, critic_grad_norm, actor_loss, actor_grad_norm, entropy, Q1avg, Q2avg
+ * Several ranks (crux_nccl_init): every rank passes its own minibatch of B rows (per-rank replay shards); the losses are
+ * means over world * B rows, the gradients of every optimiser and the temperature mean are summed over ranks before the step, so
+ * parameters, targets and log α stay bit-identical on every rank; device noise streams differ per rank; info values are rank-local. */
 typedef struct crux_sac_state crux_sac_state;
 int32_t crux_sac_create(crux_gaussian *actor, crux_mlp *q1, crux_mlp *q2, crux_mlp *q1_target, crux_mlp *q2_target,
                         float log_alpha, float h_target, double alpha_eta, float tau, crux_sac_state **out);
@@ -334,7 +337,8 @@ int32_t crux_noise_explore(crux_ctx *ctx, float *a, int64_t B, int32_t A, float 
  *   critic  td_loss (utils.jl:76-87) or double_Q_loss (:89-96), skipped when train_critic == 0 (c_opt.update_every)
  *   actor   ddpg_actor_loss rl/ddpg.jl:25 / td3_actor_loss rl/td3.jl:12: -mean(Q1(s, μ(s))), then polyak τ of the whole π⁻
  *           (actor and critics, off_policy.jl:55,100); both skipped when train_actor == 0 (a_opt.update_every)
- * q2 / q2_target NULL => DDPG.  info_out_host[0..7] = -, critic_loss, critic_grad_norm, actor_loss, actor_grad_norm, -, Q1avg, Q2avg */
+ * q2 / q2_target NULL => DDPG.  info_out_host[0..7] = -, critic_loss, critic_grad_norm, actor_loss, actor_grad_norm, -, Q1avg, Q2avg
+ * Several ranks: like crux_sac_train (means over world * B rows, gradients summed over ranks before each optimiser step). */
 typedef struct crux_ddpg_state crux_ddpg_state;
 int32_t crux_ddpg_create(crux_mlp *actor, crux_mlp *actor_target, crux_mlp *q1, crux_mlp *q1_target,
                          crux_mlp *q2 /* nullable */, crux_mlp *q2_target /* nullable */, float tau, crux_ddpg_state **out);

@@ -111,6 +111,98 @@ def main():
 
     ppo_check("nccl all-reduce")
 
+    # ---- data-parallel SAC update (replicas with per-rank replay shards + gradient all-reduce): every rank trains on its shard
+    # of a union minibatch with injected noise; parameters, targets and log α must equal the oracle's update on the union batch
+    def sac_check(tag):
+        import test_gpu_offpolicy as T
+        from gpu_util import mlp_params, p as gp, dev as gdev
+        sdim, A, H, B = 11, 3, 32, 64
+        rng_s, nets, hs, pol = T._sac_setup(ctx, sdim, A, H, seed=77)
+        actor, q1, q2, q1t, q2t = nets
+        pis = o.SquashedGaussianPolicy(lambda s_: actor(s_)[:, :A], lambda s_: actor(s_)[:, A:], 1.0, actor.params())
+        log_alpha0, h_target, tau, gamma = F32(math.log(0.2)), F32(-A), F32(0.005), F32(0.99)
+        st = C.c_void_p()
+        ctx.check(ctx.lib.crux_sac_create(pol, hs[1], hs[2], hs[3], hs[4], log_alpha0, h_target, float(F32(3e-4)), tau, C.byref(st)))
+        log_alpha = torch.tensor([float(log_alpha0)], requires_grad=True)
+        opt_t, opt_c, opt_a = o.Adam(F32(3e-4)), o.Adam(F32(3e-4)), o.Adam(F32(3e-4))
+        n_u = B * world
+        for step in range(2):
+            Du = {"s": rng_s.standard_normal((n_u, sdim)).astype(F32), "a": np.tanh(rng_s.standard_normal((n_u, A))).astype(F32),
+                  "sp": rng_s.standard_normal((n_u, sdim)).astype(F32), "r": rng_s.standard_normal(n_u).astype(F32),
+                  "done": (rng_s.random(n_u) < 0.2).astype(np.uint8)}
+            e1, e2, e3 = (rng_s.standard_normal((n_u, A)).astype(F32) for _ in range(3))
+            y = o.sac_target(pis, q1t, q2t, Du, gamma, float(log_alpha.detach()[0]), e1)
+            o.train_step([log_alpha], lambda inf: o.sac_temp_loss(pis, Du, log_alpha[0], h_target, e2), opt_t, {}, "temp_")
+            sa = np.concatenate([Du["s"], Du["a"]], 1)
+            o.train_step(q1.params() + q2.params(), lambda inf: 0.5 * (o.td_loss(q1(sa), y, None, inf, "Q1avg") + o.td_loss(q2(sa), y, None, inf, "Q2avg")),
+                         opt_c, {}, "critic_")
+            o.train_step(actor.params(), lambda inf: o.sac_actor_loss(pis, q1, q2, Du, float(log_alpha.detach()[0]), e3, inf), opt_a, {}, "actor_")
+            o.polyak_average(q1t.params(), q1.params(), tau)
+            o.polyak_average(q2t.params(), q2.params(), tau)
+            shd = slice(rank * B, (rank + 1) * B)
+            ctx.check(ctx.lib.crux_sac_train(st, gp(gdev(ctx, Du["s"][shd])), gp(gdev(ctx, Du["a"][shd])), gp(gdev(ctx, Du["sp"][shd])), gp(gdev(ctx, Du["r"][shd])),
+                                             gp(gdev(ctx, Du["done"][shd])), B, gamma, gp(gdev(ctx, e1[shd])), gp(gdev(ctx, e2[shd])), gp(gdev(ctx, e3[shd])),
+                                             0, 0, None, None))
+            la = np.zeros(1, F32); ctx.check(ctx.lib.crux_sac_log_alpha(st, gp(la)))
+            assert abs(la[0] - float(log_alpha.detach()[0])) < 1e-5, f"{tag}: log alpha {la[0]} vs {float(log_alpha.detach()[0])}"
+            for name, h, m in (("q1", hs[1], q1), ("q2", hs[2], q2), ("actor", hs[0], actor), ("q1 target", hs[3], q1t)):
+                got, want = mlp_params(ctx, h), m.flat()
+                err = np.abs(got - want)
+                assert err.max() < 2 * 3e-4 * (step + 1) + 2e-6, f"{tag} {name}: {err.max()}"
+                assert (err > 2e-6 + 1e-5 * np.abs(want)).mean() < 5e-3, f"{tag} {name}: {(err > 2e-6 + 1e-5 * np.abs(want)).sum()} coordinates off"
+                t_ = dev(got); gl_ = [torch.empty_like(t_) for _ in range(world)]
+                dist.all_gather(gl_, t_)
+                assert all(torch.equal(gl_[0], g) for g in gl_), f"{tag} {name}: replicas diverged"
+        # device noise: ranks draw different streams, replicas stay identical
+        ctx.check(ctx.lib.crux_sac_train(st, gp(gdev(ctx, Du["s"][shd])), gp(gdev(ctx, Du["a"][shd])), gp(gdev(ctx, Du["sp"][shd])), gp(gdev(ctx, Du["r"][shd])),
+                                         gp(gdev(ctx, Du["done"][shd])), B, gamma, None, None, None, 5, 9, None, None))
+        t_ = dev(mlp_params(ctx, hs[0])); gl_ = [torch.empty_like(t_) for _ in range(world)]
+        dist.all_gather(gl_, t_)
+        assert all(torch.equal(gl_[0], g) for g in gl_), f"{tag}: replicas diverged with device noise"
+        ctx.lib.crux_sac_destroy(st)
+        if rank == 0:
+            print(f"sac update parity OK ({tag})")
+
+    def ddpg_check(tag):
+        import test_gpu_offpolicy as T
+        from gpu_util import mlp_params, p as gp, dev as gdev
+        sdim, A, H, B = 9, 2, 32, 64
+        rng_d, actor, at, crit, ct, ha, hat, hc, hct = T._ddpg_setup(ctx, sdim, A, H, True, seed=31)
+        st = C.c_void_p()
+        ctx.check(ctx.lib.crux_ddpg_create(ha, hat, hc[0], hct[0], hc[1], hct[1], F32(0.005), C.byref(st)))
+        n_u = B * world
+        Du = [rng_d.standard_normal((n_u, sdim)).astype(F32), np.tanh(rng_d.standard_normal((n_u, A))).astype(F32), rng_d.standard_normal((n_u, sdim)).astype(F32),
+              rng_d.standard_normal(n_u).astype(F32), (rng_d.random(n_u) < 0.2).astype(np.uint8)]
+        es = rng_d.standard_normal((n_u, A)).astype(F32)
+
+        def run(data, eps, Bx):
+            ctx.check(ctx.lib.crux_ddpg_train(st, *[gp(gdev(ctx, x)) for x in data], Bx, F32(0.99), 1, F32(0.2), F32(-0.5), F32(0.5), None, 0, None, 0,
+                                              gp(gdev(ctx, eps)), 0, 0, 1, 1, None, None))
+        shd = slice(rank * B, (rank + 1) * B)
+        run([x[shd] for x in Du], es[shd], B)
+        sharded = [mlp_params(ctx, h).copy() for h in (ha, hc[0], hc[1], hat)]
+        for t_ in sharded:
+            tt = dev(t_); gl_ = [torch.empty_like(tt) for _ in range(world)]
+            dist.all_gather(gl_, tt)
+            assert all(torch.equal(gl_[0], g) for g in gl_), f"{tag}: replicas diverged"
+        # the oracle's TD3 update (off_policy.jl:71-101 order) on the union batch
+        y = o.ddpg_target(at, ct, {"sp": Du[2], "r": Du[3], "done": Du[4]}, F32(0.99),
+                          dict(eps=es, sigma=F32(0.2), eps_min=-0.5, eps_max=0.5, a_min=-math.inf, a_max=math.inf))
+        sa = np.concatenate([Du[0], Du[1]], 1)
+        oc_, oa_ = o.Adam(F32(3e-4)), o.Adam(F32(3e-4))
+        o.train_step(crit[0].params() + crit[1].params(), lambda inf: 0.5 * (o.td_loss(crit[0](sa), y, None, inf, "Q1avg") + o.td_loss(crit[1](sa), y, None, inf, "Q2avg")),
+                     oc_, {}, "critic_")
+        o.train_step(actor.params(), lambda inf: o.ddpg_actor_loss(actor, crit[0], {"s": Du[0]}), oa_, {}, "actor_")
+        for name, got, m in (("actor", sharded[0], actor), ("q1", sharded[1], crit[0]), ("q2", sharded[2], crit[1])):
+            err = np.abs(got - m.flat())
+            assert err.max() < 2 * 3e-4 + 2e-6 and (err > 2e-6 + 1e-5 * np.abs(m.flat())).mean() < 5e-3, f"{tag} {name}: {err.max()}"
+        ctx.lib.crux_ddpg_destroy(st)
+        if rank == 0:
+            print(f"td3 update parity OK ({tag})")
+
+    sac_check("nccl all-reduce")
+    ddpg_check("nccl all-reduce")
+
     # ---- global whitening: every rank whitens its shard with the all-reduced moments
     x = np.random.default_rng(5).standard_normal(4000).astype(F32) * 3 + 1
     t = dev(x[rank::world].copy())
