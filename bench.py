@@ -285,10 +285,11 @@ def phase_breakdown(crux, ctx, S, env, torch):
     tf = flops_launch / (mb_ms * 1e-3) / 1e12
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal fp32 SIMT FFMA peak at max clock (what the all-FFMA variant is bounded by)
     share = fam_ms[0] / 2.0 / acc.sum()
-    traffic = None
+    traffic = traffic_warm = None
     try:
         with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
-            traffic = json.load(f).get("mb6::minibatch_kernel")
+            tj = json.load(f)
+            traffic, traffic_warm = tj.get("mb6::minibatch_kernel"), tj.get("mb6::minibatch_kernel (warm L2, ncu --cache-control none)")
     except Exception:
         pass
     try:
@@ -300,6 +301,7 @@ def phase_breakdown(crux, ctx, S, env, torch):
     roof = {"kernel": "mb6::minibatch_kernel (csrc/mb_t5.cuh: gather + forward + loss + backward + weight gradients of one 32768-row minibatch, "
                       "every GEMM on tcgen05 with TMEM accumulators; avg of actor and critic launches)",
             "bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak, "traffic": traffic,
+            "traffic_warm_l2": traffic_warm, "algorithmic_bytes_per_launch": MB * (104 + 4),
             "flops_per_launch": flops_launch, "ms_per_launch": mb_ms, "launches_per_step": int(fam_n[0]) // 2, "share_of_step": share,
             "peak_source": tensor_src,
             "tensor_passes_per_flop": 3, "tensor_tflops_issued": 3 * tf, "frac_of_fp32_simt_nominal": tf / fp32_peak,
