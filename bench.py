@@ -178,6 +178,14 @@ def run_ours(args):
     # ---------------- phase breakdown + dominant-kernel roofline (rank-local, untimed extra iterations) -------------
     phases = phase_breakdown(crux, ctx, S, env, torch)  # every rank: the update all-reduces gradients
     gae = gae_roofline(crux, ctx, torch, hbm_peak, peak_src) if rank == 0 else None
+    # the same PPO step with the REFERENCE-DEFAULT TrainingParams (epochs 80, batch 128: training.jl:3-6), one iteration, single GPU only
+    ref_defaults = None
+    if world == 1 and not os.environ.get("CRUX_BENCH_SKIP_REF_DEFAULTS"):
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_ref_defaults
+        r = bench_ref_defaults.run(iters=1, ctx=ctx)
+        ref_defaults = {k: r[k] for k in ("workload", "env_steps_per_s", "ms_per_iteration", "us_per_minibatch_update", "launches_per_iteration",
+                                          "actor_batches_trained", "critic_batches_trained")}
 
     # ---------------- e2e leg: host env through the public API --------------------------------------
     S2 = build_solver(crux, ctx, seed=2)
@@ -233,6 +241,7 @@ def run_ours(args):
                "gpu_launches": int(launches),
                "roofline": phases["roofline"] if phases else None,
                "roofline_gae": gae,
+               "ref_defaults": ref_defaults,
                "phases_ms": phases["phases_ms"] if phases else None,
                "kernels": phases["kernels"] if phases else None,
                "cpu_baseline": cpu,

@@ -21,6 +21,7 @@
 // copy (cp.async.bulk ... mbarrier::complete_tx) per CTA.
 // Bound: fp32 FFMA (SIMT).  1e-5 parity with the fp32 reference excludes TF32/BF16 tensor-core MMA for these layers.
 #include "policy.cuh"
+#include <cooperative_groups.h>
 #include <stdlib.h>
 #include <vector>
 
@@ -1157,6 +1158,7 @@ __global__ void __launch_bounds__(NT, 2) fused_minibatch_tc_kernel(MbArgs a) {
 
 #include "mb_tc5.cuh"
 #include "mb_t5.cuh"
+#include "mb_persist.cuh"
 
 // =================================================================================================== tensor-core forward kernel
 // value(π, s) over a whole rollout column (the two critic passes that feed the GAE scan, policies.jl:94-98) on the building blocks of
@@ -2193,6 +2195,41 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
   return CRUX_OK;
 }
 
+// batch_train! of one network as one cluster launch (mb_persist.cuh).  Row orders of ALL epochs are needed up front: the caller's, or
+// device-generated permutations written behind each other.
+static int persistent_epochs(crux_gaussian *actor, crux_mlp *mlp, int head, const float *s, const float *act, const float *logp_old, const float *adv,
+                             const float *ret, int64_t n, const crux_ppo_hp *hp, const int32_t *order_in, uint64_t seed) {
+  crux_ctx *ctx = mlp->ctx;
+  const int epochs = head == 0 ? hp->actor_epochs : hp->critic_epochs, batch = head == 0 ? hp->actor_batch : hp->critic_batch;
+  const int32_t *order = order_in;
+  if (!order) {
+    int32_t **buf = head == 0 ? &actor->order : &actor->order2;
+    size_t *have = head == 0 ? &actor->order_bytes : &actor->order2_bytes;
+    int rc = ppo_ensure_bytes(ctx, (void **)buf, have, (size_t)epochs * n * sizeof(int32_t)); if (rc) return rc;
+    for (int e = 0; e < epochs; ++e) { rc = ppo_fill_order(ctx, *buf + (int64_t)e * n, n, seed, (uint32_t)e); if (rc) return rc; }
+    order = *buf;
+  }
+  mbp::Args a;
+  memset(&a, 0, sizeof(a));
+  a.net = describe(mlp); a.s = s; a.act = act; a.logp_old = logp_old; a.adv = adv; a.ret = ret; a.order = order; a.n = n; a.batch = batch;
+  a.epochs = epochs; a.max_batches = head == 0 ? hp->actor_max_batches : hp->critic_max_batches;
+  if (head == 0) { a.ls = actor->log_sigma; a.ls_m = actor->ls_m; a.ls_v = actor->ls_v; a.ctl = actor->ctl; }
+  a.m = mlp->m; a.v = mlp->v; a.step_dev = mlp->step_dev; a.beta_cache = mlp->norm_part + BETA_CACHE;
+  a.eta = mlp->eta; a.b1 = mlp->beta1; a.b2 = mlp->beta2; a.eps = mlp->eps;
+  a.eps_clip = hp->eps_clip; a.lambda_p = hp->lambda_p; a.lambda_e = hp->lambda_e; a.target_kl = hp->target_kl; a.a2c = hp->a2c;
+  a.info = head == 0 ? actor->info_actor : actor->info_critic; a.err_flags = ctx->flags_dev; a.n_params = (int)mlp->n_params;
+  static bool attr = false;
+  if (!attr) {
+    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(mbp::epoch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mbp::Map::BYTES));
+    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(mbp::epoch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mbp::Map::BYTES));
+    attr = true;
+  }
+  if (head == 0) mbp::epoch_kernel<0><<<mbp::C, NT, mbp::Map::BYTES, ctx->stream>>>(a);
+  else mbp::epoch_kernel<1><<<mbp::C, NT, mbp::Map::BYTES, ctx->stream>>>(a);
+  CRUX_LAUNCHED(ctx);
+  return CRUX_OK;
+}
+
 // policy_gradient_training (on_policy.jl:56-78) for fusable shapes: all actor epochs, then all critic epochs
 int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, const float *a, const float *logprob, const float *advantage,
                      const float *ret, int64_t n, const crux_ppo_hp *hp, const int32_t *order_actor, const int32_t *order_critic,
@@ -2238,9 +2275,15 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
     CRUX_CHECK_CUDA(ctx, cudaEventRecord(ctx->side_fork, ctx->stream));
     CRUX_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_fork, 0));
   }
+  // Small minibatches (the reference-default batch_size = 128): the whole batch_train! of a network is ONE launch of a thread-block
+  // cluster that keeps parameters and Adam state on chip (mb_persist.cuh) instead of 4 launches per 27 us train! step.
+  const bool no_persist = getenv("CRUX_NO_PERSIST") != nullptr;   // read per call: tests compare both paths
+  const bool persist_a = !no_persist && ctx->world == 1 && !ctx->timing && hp->actor_batch <= mbp::MAXB && hp->actor_epochs * nmb_a >= 8;
+  const bool persist_c = !no_persist && ctx->world == 1 && !ctx->timing && critic && hp->critic_batch <= mbp::MAXB && hp->critic_epochs * nmb_c >= 8;
+  if (persist_a) { rc = persistent_epochs(actor, mu, 0, s, a, logprob, advantage, ret, n, hp, order_actor, seed); if (rc) return rc; }
   int64_t total = 0;
   const int64_t maxb_a = hp->actor_max_batches > 0 ? hp->actor_max_batches : INT64_MAX;
-  for (int e = 0; e < hp->actor_epochs && total < maxb_a; ++e) {
+  for (int e = 0; e < hp->actor_epochs && total < maxb_a && !persist_a; ++e) {
     const int32_t *order;
     if (order_actor) order = order_actor + (int64_t)e * n;
     else { rc = ppo_fill_order(ctx, actor->order, n, seed, (uint32_t)e); if (rc) return rc; order = actor->order; }
@@ -2261,9 +2304,13 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
   const bool side = (ctx->world == 1 || ll || (ctx->nccl_comm_side && !ctx->peer_ready)) && nmb_c > 0 && hp->critic_epochs > 0 && !ctx->timing &&
                     !getenv("CRUX_NO_SIDE_STREAM") && ctx->side_stream;
   if (side) ctx->stream = ctx->side_stream;   // every launch helper below enqueues on ctx->stream
+  if (persist_c) {
+    rc = persistent_epochs(actor, critic, 1, s, nullptr, nullptr, nullptr, ret, n, hp, order_critic, seed ^ 0xC2B2AE3D27D4EB4FULL);
+    if (rc) { ctx->stream = main_stream; return rc; }
+  }
   total = 0;
   const int64_t maxb_c = hp->critic_max_batches > 0 ? hp->critic_max_batches : INT64_MAX;
-  for (int e = 0; e < hp->critic_epochs && nmb_c && total < maxb_c; ++e) {
+  for (int e = 0; e < hp->critic_epochs && nmb_c && total < maxb_c && !persist_c; ++e) {
     const int32_t *order;
     if (order_critic) order = order_critic + (int64_t)e * n;
     else {

@@ -1,7 +1,8 @@
 """the PPO step of BASELINE config[1] (4096 env streams x T=32, 17-64-64-6 / 17-64-64-1) once more with the
 REFERENCE-DEFAULT training hyper-parameters instead of the large-batch ones the headline uses: TrainingParams defaults
 epochs = 80, batch_size = 128 (training.jl:3-6), PPO defaults λe = 0.1, target_kl = 0.012 (ppo.jl:42-45).  That is up to
-80 x 1024 minibatch updates of 128 rows per network and iteration: a launch-latency regime, reported for honesty, not tuned.
+80 x 1024 minibatch updates of 128 rows per network and iteration: each network's batch_train! runs as ONE launch of the persistent
+cluster kernel (csrc/mb_persist.cuh); bench.py reports the result as `ref_defaults`.
 Usage (GPU box): python scripts/bench_ref_defaults.py [--iters 2] > gpurun_out/ref_defaults.json"""
 import argparse
 import json
@@ -19,9 +20,17 @@ def main():
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--no-early-stop", action="store_true", help="target_kl = Inf: all 80 actor epochs run")
     args = ap.parse_args()
+    print(json.dumps(run(args.iters, args.no_early_stop)))
+
+
+def run(iters=2, no_early_stop=False, ctx=None):
     import torch
     import crux_b200 as crux
-    ctx = crux.Context(0)
+
+    class args:
+        pass
+    args.iters, args.no_early_stop = iters, no_early_stop
+    ctx = ctx or crux.Context(0)
     n_envs, T, obs, act, hid = 4096, 32, 17, 6, 64
     rng = np.random.default_rng(1)
     D = crux.Dense
@@ -54,7 +63,7 @@ def main():
            "critic_batches_trained": [i.get("critic_batches_trained") for i in infos],
            "us_per_minibatch_update": ms * 1e3 / max(1, max(infos[-1]["actor_batches_trained"], infos[-1].get("critic_batches_trained", 0))),
            "last_info": {k: (round(v, 6) if isinstance(v, float) else v) for k, v in infos[-1].items()}}
-    print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":
