@@ -83,7 +83,12 @@ for name, key in (("prof_minibatch", "fused_minibatch_kernel"), ("prof_gae", "ga
             v = float(v.replace(",", ""))
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
         traffic[key] = sum(to_bytes(*m[k]) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in m)
-json.dump(traffic, open(os.path.join(ROOT, "profiles", f"{rnd}_traffic.json"), "w"), indent=1)
+tpath = os.path.join(ROOT, "profiles", f"{rnd}_traffic.json")
+if os.path.exists(tpath):          # hand-annotated entries (cold / warm L2 captures, notes) are kept; captured kernels are refreshed
+    old = json.load(open(tpath))
+    old.update(traffic)
+    traffic = old
+json.dump(traffic, open(tpath, "w"), indent=1)
 path = os.path.join(ROOT, "profiles", f"{rnd}_ncu_summary.md")
 hdr = [f"# ncu evidence, {rnd} (generated by scripts/make_profile_summary.py from gpurun_out/ captures on a B200)", ""]
 notes = os.path.join(ROOT, "profiles", f"{rnd}_notes.md")
