@@ -2300,7 +2300,10 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
   cudaStream_t main_stream = ctx->stream;
   // With several ranks the critic's gradient exchange uses its own LL region (or, without peer buffers, the second NCCL
   // communicator of nccl.cu).
-  const bool ll = ctx->peer_ready && ctx->peer_ll && !getenv("CRUX_NO_PEER_LL");   // per-network exchange regions: safe to run both at once
+  // per-network LL exchange regions: safe to run both networks at once -- but only if BOTH gradients fit the mapped regions (a network that
+  // does not fit falls back to NCCL, and two streams must never share one communicator: ADVICE r1)
+  const bool ll = ctx->peer_ready && ctx->peer_ll && !getenv("CRUX_NO_PEER_LL") && mu->n_params + CRUX_GRAD_TAIL <= ctx->peer_cap &&
+                  (!critic || critic->n_params + CRUX_GRAD_TAIL <= ctx->peer_cap);
   const bool side = (ctx->world == 1 || ll || (ctx->nccl_comm_side && !ctx->peer_ready)) && nmb_c > 0 && hp->critic_epochs > 0 && !ctx->timing &&
                     !getenv("CRUX_NO_SIDE_STREAM") && ctx->side_stream;
   if (side) ctx->stream = ctx->side_stream;   // every launch helper below enqueues on ctx->stream
