@@ -226,6 +226,12 @@ __global__ void sum_parts_kernel(const double *__restrict__ part, int n, double 
 
 }  // namespace
 
+// gemm_tc5.cu: the same three GEMMs on tcgen05 (3xTF32) for shapes that fill a 128 x 64 tile; the FFMA kernel above serves the rest
+bool gemm_tc5_eligible(int64_t M, int64_t N, int64_t K);
+int gemm_tc5_fwd(crux_ctx *ctx, const float *x, int K, const float *W, int N, float *y, int64_t B, const float *b, int act, const int *skip);
+int gemm_tc5_bwd_data(crux_ctx *ctx, const float *dz, int N, const float *W, float *dx, int K, int64_t B, const float *yprev, int prev_act, const int *skip);
+int gemm_tc5_wgrad(crux_ctx *ctx, const float *x, int K, const float *dz, int N, float *part, int64_t B, int slabs, int rows_per_slab, const int *skip);
+
 // ------------------------------------------------------------------------------------------------
 int mlp_ensure_workspace(crux_mlp *mlp, int64_t B) {
   crux_ctx *ctx = mlp->ctx;
@@ -251,6 +257,7 @@ static int launch_fwd_layer(crux_mlp *mlp, int l /*1-based*/, const float *x, in
   const int K = mlp->dims[l - 1], N = mlp->dims[l];
   const float *W = mlp->params + mlp->w_off[l - 1];
   const float *b = W + (int64_t)K * N;
+  if (gemm_tc5_eligible(B, N, K)) return gemm_tc5_fwd(ctx, x, K, W, N, y, B, b, mlp->acts[l - 1], skip);
   dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(B, BM), 1);
   sgemm_kernel<false, false, EPI_FWD><<<grid, 256, 0, ctx->stream>>>(x, K, W, N, y, N, (int)B, N, K, b, mlp->acts[l - 1],
                                                                     nullptr, 0, 0, 0, skip);
@@ -305,10 +312,11 @@ int mlp_backward(crux_mlp *mlp, const float *x, int64_t B, float *dY, bool need_
     int kps[CRUX_MAX_LAYERS];
     for (int l = 1; l <= L; ++l) {
       const int K = mlp->dims[l - 1], N = mlp->dims[l];
-      const int64_t tiles = cdiv(K, BM) * cdiv(N, BN);
+      const bool tc = gemm_tc5_eligible(K, N, B);                       // 128 x 64 tiles, 32-row k-tiles
+      const int64_t tiles = tc ? cdiv(K, 128) * cdiv(N, 64) : cdiv(K, BM) * cdiv(N, BN);
       int64_t S = cdiv(2 * (int64_t)ctx->num_sms, tiles);
-      S = i64max(1, i64min(S, cdiv(B, 64)));
-      int64_t per = cdiv(cdiv(B, S), BK) * BK;
+      S = i64max(1, i64min(S, cdiv(B, tc ? 128 : 64)));
+      int64_t per = cdiv(cdiv(B, S), 32) * 32;
       S = cdiv(B, per);
       slabs[l - 1] = (int)S; kps[l - 1] = (int)per;
       need += (size_t)S * (K + 1) * N * sizeof(float);
@@ -335,17 +343,27 @@ int mlp_backward(crux_mlp *mlp, const float *x, int64_t B, float *dY, bool need_
       const int K = mlp->dims[l - 1], N = mlp->dims[l];
       const float *xin = (l == 1) ? x : mlp->act[l - 1];
       const float *dzl = (l == L) ? dz_cur : mlp->dz[l];
-      dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(K, BM), (unsigned)slabs[l - 1]);
-      sgemm_kernel<true, false, EPI_PARTIAL><<<grid, 256, 0, ctx->stream>>>(
-          xin, K, dzl, N, (float *)tab.src[l - 1], N, K, N, (int)B, nullptr, 0, nullptr, 0, kps[l - 1], 1, skip);
-      CRUX_LAUNCHED(ctx);
+      if (gemm_tc5_eligible(K, N, B)) {
+        int rc2 = gemm_tc5_wgrad(ctx, xin, K, dzl, N, (float *)tab.src[l - 1], B, slabs[l - 1], kps[l - 1], skip);
+        if (rc2) return rc2;
+      } else {
+        dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(K, BM), (unsigned)slabs[l - 1]);
+        sgemm_kernel<true, false, EPI_PARTIAL><<<grid, 256, 0, ctx->stream>>>(
+            xin, K, dzl, N, (float *)tab.src[l - 1], N, K, N, (int)B, nullptr, 0, nullptr, 0, kps[l - 1], 1, skip);
+        CRUX_LAUNCHED(ctx);
+      }
       if (l > 1 || need_dx) {
         const float *W = mlp->params + mlp->w_off[l - 1];
-        dim3 g2((unsigned)cdiv(K, BN), (unsigned)cdiv(B, BM), 1);
-        sgemm_kernel<false, true, EPI_BWD_DATA><<<g2, 256, 0, ctx->stream>>>(
-            dzl, N, W, N, mlp->dz[l - 1], K, (int)B, K, N, nullptr, 0, (l > 1) ? mlp->act[l - 1] : nullptr,
-            (l > 1) ? mlp->acts[l - 2] : 0, 0, 0, skip);
-        CRUX_LAUNCHED(ctx);
+        const float *yp = (l > 1) ? mlp->act[l - 1] : nullptr;
+        const int pa = (l > 1) ? mlp->acts[l - 2] : 0;
+        if (gemm_tc5_eligible(B, K, N)) {
+          int rc2 = gemm_tc5_bwd_data(ctx, dzl, N, W, mlp->dz[l - 1], K, B, yp, pa, skip);
+          if (rc2) return rc2;
+        } else {
+          dim3 g2((unsigned)cdiv(K, BN), (unsigned)cdiv(B, BM), 1);
+          sgemm_kernel<false, true, EPI_BWD_DATA><<<g2, 256, 0, ctx->stream>>>(dzl, N, W, N, mlp->dz[l - 1], K, (int)B, K, N, nullptr, 0, yp, pa, 0, 0, skip);
+          CRUX_LAUNCHED(ctx);
+        }
       }
     }
     int64_t maxc = 0;
@@ -359,11 +377,16 @@ int mlp_backward(crux_mlp *mlp, const float *x, int64_t B, float *dY, bool need_
       const float *dzl = (l == L) ? dz_cur : mlp->dz[l];
       if (l > 1 || need_dx) {
         const float *W = mlp->params + mlp->w_off[l - 1];
-        dim3 g2((unsigned)cdiv(K, BN), (unsigned)cdiv(B, BM), 1);
-        sgemm_kernel<false, true, EPI_BWD_DATA><<<g2, 256, 0, ctx->stream>>>(
-            dzl, N, W, N, mlp->dz[l - 1], K, (int)B, K, N, nullptr, 0, (l > 1) ? mlp->act[l - 1] : nullptr,
-            (l > 1) ? mlp->acts[l - 2] : 0, 0, 0, skip);
-        CRUX_LAUNCHED(ctx);
+        const float *yp = (l > 1) ? mlp->act[l - 1] : nullptr;
+        const int pa = (l > 1) ? mlp->acts[l - 2] : 0;
+        if (gemm_tc5_eligible(B, K, N)) {
+          int rc2 = gemm_tc5_bwd_data(ctx, dzl, N, W, mlp->dz[l - 1], K, B, yp, pa, skip);
+          if (rc2) return rc2;
+        } else {
+          dim3 g2((unsigned)cdiv(K, BN), (unsigned)cdiv(B, BM), 1);
+          sgemm_kernel<false, true, EPI_BWD_DATA><<<g2, 256, 0, ctx->stream>>>(dzl, N, W, N, mlp->dz[l - 1], K, (int)B, K, N, nullptr, 0, yp, pa, 0, 0, skip);
+          CRUX_LAUNCHED(ctx);
+        }
       }
     }
   }

@@ -96,7 +96,7 @@ def test_conv_dqn_train_matches_oracle(crux, ctx, geom, B, weighted, clip):
         sd, ad, yd = ctx.to_device(s.reshape(B, -1), torch.uint8), ctx.to_device(a), ctx.to_device(y)
         wd = None if w is None else ctx.to_device(w)
         pi.mlp.train_dqn(sd, ad, yd, wd, B, info)
-        assert_close(info[0], info_ref["loss"], rtol=1e-5, atol=1e-6, what=f"loss step {step}")
+        assert_close(info[0], info_ref["loss"], rtol=5e-5, atol=1e-6, what=f"loss step {step}")   # mean of squared TD errors: 2 x the relative error of Q
         assert_close(info[1], info_ref["grad_norm"], rtol=1e-4, atol=1e-6, what=f"grad_norm step {step}")
         assert_close(info[2], info_ref["Qavg"], rtol=1e-5, atol=1e-5, what=f"Qavg step {step}")
         g = pi.mlp.grads()

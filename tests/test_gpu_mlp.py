@@ -76,6 +76,16 @@ def test_train_mse_steps(ctx, dims, acts, B):
     ctx.lib.crux_mlp_destroy(h)
 
 
+@pytest.mark.parametrize("dims,acts,B", [([40, 256, 256, 3], [2, 1, 1], 300), ([393, 256, 256, 34], [1, 1, 0], 2048), ([130, 64, 17], [1, 0], 129)])
+def test_train_mse_steps_tcgen05_gemm(ctx, dims, acts, B, monkeypatch):
+    """The same train! steps with the generic engine's GEMMs on tcgen05 (csrc/gemm_tc5.cu, CRUX_GEMM_TC5=1: forward, data-gradient and split-K
+    weight-gradient GEMMs as 128 x 64 tiles with TMEM accumulators, 3xTF32): gradients against autograd, loss, grad-norm, Adam updates."""
+    monkeypatch.setenv("CRUX_GEMM_TC5", "1")
+    l0 = ctx.launch_count()
+    test_train_mse_steps(ctx, dims, acts, B)
+    assert ctx.launch_count() > l0
+
+
 def test_polyak_and_copy(ctx):
     rng = np.random.default_rng(0)
     a, b = o.MLP([4, 8, 2], [1, 0], rng), o.MLP([4, 8, 2], [1, 0], rng)
