@@ -189,7 +189,7 @@ def run_ours(args):
 
     # ---------------- e2e leg: host env through the public API --------------------------------------
     S2 = build_solver(crux, ctx, seed=2)
-    henv = crux.NativeHostLinQuad(N_ENVS, OBS, ACT, seed=2000 + rank, n_threads=max(1, cpu_threads() // world))
+    henv = crux.NativeHostLinQuad(N_ENVS, OBS, ACT, seed=2000 + rank, n_threads=int(os.environ.get("CRUX_BENCH_ENV_THREADS", 0)) or max(1, cpu_threads() // world))
     S2.N = dN
     for _ in range(max(1, args.warmup // 2)):
         crux.solve(S2, henv)

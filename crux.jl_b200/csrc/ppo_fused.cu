@@ -37,11 +37,16 @@ constexpr int P_SMEM = (P_MAX + 3) / 4 * 4 + 8;
 
 #define LOG_SQRT_2PI 0.9189385332046727f
 
-// tanh(x) = 1 - 2/(exp(2x) + 1) on the SFU (ex2.approx + rcp.approx): absolute error ~1e-7, against ~30 instructions for
-// libdevice tanhf (which was 27 % of the minibatch kernel's instruction stream).  Saturates correctly for |x| large.
+// tanh(x) = 1 - 2/(exp(2x) + 1) on the SFU: ex2.approx.ftz + rcp.approx.ftz + one FMA (4 instructions; __expf / __fdividef expand to ~12
+// with their range fix-ups, libdevice tanhf to ~30).  Absolute error ~2e-7 (the rounding of e + 1 and of the final subtraction: the RELATIVE
+// error grows as x -> 0, which is why every forward tolerance carries an absolute term of 1e-6 or more: a deliberate divergence from the
+// reference's tanh).  Saturates correctly for |x| large (ex2 -> +inf gives rcp -> 0, ex2 -> 0 gives 1 - 2 = -1).  The same
+// formula as mb_t5.cuh's tanh_t5, so rollout, value passes and every minibatch-kernel variant evaluate the activation identically.
 __device__ __forceinline__ float tanh_fast(float x) {
-  const float e = __expf(2.0f * x);
-  return 1.0f - __fdividef(2.0f, e + 1.0f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((2.0f * x) * 1.4426950216293334961f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
 }
 __device__ __forceinline__ float act_fused(int act, float z) { return act == CRUX_ACT_TANH ? tanh_fast(z) : fmaxf(z, 0.0f); }
 

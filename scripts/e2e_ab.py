@@ -12,7 +12,7 @@ import bench
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 ctx = crux.Context(0)
 S = bench.build_solver(crux, ctx, seed=2)
-env = crux.NativeHostLinQuad(bench.N_ENVS, bench.OBS, bench.ACT, seed=5, n_threads=bench.cpu_threads())
+env = crux.NativeHostLinQuad(bench.N_ENVS, bench.OBS, bench.ACT, seed=5, n_threads=int(os.environ.get("ENV_THREADS", 0)) or bench.cpu_threads())
 S.N = bench.N_ENVS * bench.HORIZON
 for _ in range(3):
     crux.solve(S, env)
