@@ -11,8 +11,9 @@
 //   * cluster barrier; the owner of entry i sums the 8 partials through distributed shared memory (fixed order, double), applies Flux
 //     Adam and stores the new weight into EVERY CTA's copies; cluster barrier; CTA 0 writes the info record; all CTAs take the same
 //     KL early-stop decision from the summed head terms (rl/ppo.jl:59 via training.jl:46,49).
-// Same head arithmetic, gradient layout and record fields as fused_minibatch_kernel / adam_body.  A non-finite partial gradient
-// raises the sticky NaN flag, skips that update and ends the loop (training.jl:20).  Single rank; minibatches of up to 128 rows.
+// Same head arithmetic, gradient layout and record fields as fused_minibatch_kernel / adam_body.  A non-finite gradient raises the
+// sticky NaN flag and ends the loop (training.jl:20; unlike the step-by-step path the failing step's update has been applied by then --
+// the host raises either way).  Single rank; minibatches of up to 128 rows.
 // Included by ppo_fused.cu.
 #pragma once
 // (<cooperative_groups.h> is included at the top of ppo_fused.cu: this file is included inside its anonymous namespace)
@@ -37,11 +38,15 @@ struct Map {   // floats; P / W2T / W3T sit where stage_params / build_transpose
   static constexpr int LS = OT + MAX_O * LD16;              // logΣ[8] (every CTA's copy)
   static constexpr int LSP = LS + 8;                        // logΣ the current minibatch's gradient was taken at (the record's entropy)
   static constexpr int RED = LSP + 8;                       // [8 warps][16] head reduction scratch
-  static constexpr int SLOT = RED + 8 * 16;                 // cluster mailboxes: bad[C] (ints) | norm2[C] (doubles, 8-byte aligned)
-  static constexpr int MBAR = (SLOT + C + 2 * C + 3) / 4 * 4;
+  static constexpr int SLOT = RED + 8 * 16;                 // cluster mailboxes: (C unused ints) | norm2[C] (doubles, 8-byte aligned)
+  static constexpr int TOT = SLOT + C + 2 * C;              // head sums of the whole minibatch (obj, kl, clip, adv, ret) + pad
+  static constexpr int IDX = TOT + 8;                       // [2][16] ints: source rows of this CTA's tile, one minibatch ahead
+  static constexpr int NEWV = (IDX + 2 * TR + 3) / 4 * 4;   // the owner's freshly updated slice (pulled by every CTA after the barrier)
+  static constexpr int PER_MAX = ((GMAX + C - 1) / C + 3) / 4 * 4;
+  static constexpr int MBAR = (NEWV + PER_MAX + 3) / 4 * 4;
   static constexpr int TOTAL = MBAR + 2;
   static constexpr size_t BYTES = (size_t)TOTAL * sizeof(float);
-  static_assert(XT % 4 == 0 && H1T % 4 == 0 && H2T % 4 == 0 && OT % 4 == 0 && MBAR % 2 == 0 && (SLOT + C) % 2 == 0, "alignment");
+  static_assert(XT % 4 == 0 && H1T % 4 == 0 && H2T % 4 == 0 && OT % 4 == 0 && MBAR % 2 == 0 && (SLOT + C) % 2 == 0 && NEWV % 4 == 0, "alignment");
 };
 
 struct Args {
@@ -89,15 +94,15 @@ __global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(NT, 1) epoch_kernel(
   const int A = HEAD == 0 ? O : 0;                 // logΣ entries trained with the actor
   stage_params(sm, nd, Map::MBAR);
   build_transposes(sm, I, O);
-  float *P = sm + Map::P, *G = sm + Map::G, *H1T = sm + Map::H1T, *H2T = sm + Map::H2T, *OT = sm + Map::OT, *LS = sm + Map::LS;
-  int *bad_slot = reinterpret_cast<int *>(sm + Map::SLOT);
+  float *P = sm + Map::P, *G = sm + Map::G, *H1T = sm + Map::H1T, *H2T = sm + Map::H2T, *OT = sm + Map::OT;
+  float *LS = P + NP;   // logΣ sits right behind the parameters (P_SMEM reserves 8 floats there): (parameters | logΣ) is ONE vector
   double *norm_slot = reinterpret_cast<double *>(sm + Map::SLOT + C);
+  __syncthreads();      // (stage_params' bulk copy may pad up to 16 bytes behind the parameters)
   if (t < 8) LS[t] = (HEAD == 0 && t < O) ? a.ls[t] : 0.f;
   for (int e = t; e < 2 * MAX_I * LD16 + 2 * MAX_O * LD16 + 2 * 3 * TR; e += NT) sm[Map::XT + e] = 0.f;
-  if (t < C) bad_slot[t] = 0;
 
   // ---- the slice of (parameters | logΣ) this CTA owns: entries lo + t + NT u; master copy and Adam moments in registers
-  const int NE = NP + A, per = (NE + C - 1) / C, lo = c * per, hi = min(NE, lo + per);
+  const int NE = NP + A, per = ((NE + C - 1) / C + 3) / 4 * 4, lo = c * per, hi = min(NE, lo + per);   // slices of a multiple of 4 entries
   constexpr int NU = (GMAX / C + NT) / NT;          // entries per thread (<= 4)
   float pw[NU], pm[NU], pv[NU];
 #pragma unroll
@@ -122,27 +127,31 @@ __global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(NT, 1) epoch_kernel(
     bm = (int)min((int64_t)a.batch, a.n - k * a.batch);
   };
   // gather of this CTA's 16 rows of minibatch q into buffer b (cp.async, 4 bytes per element, transposed on the fly)
-  auto gather = [&](int64_t q, int b) {
+  int *IDXs = reinterpret_cast<int *>(sm + Map::IDX);
+  auto load_idx = [&](int64_t q) -> int {   // source row of this CTA's tile row t (t < 16) in minibatch q, -1 beyond the minibatch
     int64_t off; int bm;
     mb_rows(q, off, bm);
+    const int row_in_mb = c * TR + t;
+    return row_in_mb < bm ? __ldg(a.order + off + row_in_mb) : -1;
+  };
+  auto gather = [&](int64_t q, int b) {   // rows from IDXs[b] (filled before the preceding block barrier)
+    const int *idx = IDXs + b * TR;
     float *XTb = sm + Map::XT + b * MAX_I * LD16, *ATb = sm + Map::AT + b * MAX_O * LD16, *HDb = sm + Map::HD + b * 3 * TR;
     for (int e = t; e < TR * I; e += NT) {
-      const int r = e / I, i = e - r * I, row_in_mb = c * TR + r;
-      const bool live = row_in_mb < bm;
-      const int row = live ? a.order[off + row_in_mb] : 0;
-      cp_async4(XTb + i * LD16 + r, a.s + (int64_t)row * I + i, live);
+      const int r = e / I, i = e - r * I;
+      const int row = idx[r];
+      cp_async4(XTb + i * LD16 + r, a.s + (int64_t)(row >= 0 ? row : 0) * I + i, row >= 0);
     }
     if (HEAD == 0)
       for (int e = t; e < TR * O; e += NT) {
-        const int r = e / O, o = e - r * O, row_in_mb = c * TR + r;
-        const bool live = row_in_mb < bm;
-        const int row = live ? a.order[off + row_in_mb] : 0;
-        cp_async4(ATb + o * LD16 + r, a.act + (int64_t)row * O + o, live);
+        const int r = e / O, o = e - r * O;
+        const int row = idx[r];
+        cp_async4(ATb + o * LD16 + r, a.act + (int64_t)(row >= 0 ? row : 0) * O + o, row >= 0);
       }
     if (t < TR) {
-      const int row_in_mb = c * TR + t;
-      const bool live = row_in_mb < bm;
-      const int row = live ? a.order[off + row_in_mb] : 0;
+      const int rowi = idx[t];
+      const bool live = rowi >= 0;
+      const int row = live ? rowi : 0;
       if (HEAD == 0) {
         cp_async4(HDb + t, a.logp_old + row, live);
         cp_async4(HDb + TR + t, a.adv + row, live);
@@ -151,6 +160,9 @@ __global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(NT, 1) epoch_kernel(
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  int nidx = -1;                                   // index of tile row t for the minibatch AFTER the next one (threads 0..15)
+  if (t < TR && total_mb > 0) IDXs[t] = load_idx(0);
+  if (t < TR && total_mb > 1) nidx = load_idx(1);
   __syncthreads();
   if (total_mb > 0) gather(0, 0);
   cluster.sync();
@@ -164,9 +176,11 @@ __global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(NT, 1) epoch_kernel(
     mb_rows(q, off, bm);
     const float inv_bg = 1.0f / (float)bm;
     float *XT = sm + Map::XT + b * MAX_I * LD16, *AT_ = sm + Map::AT + b * MAX_O * LD16, *HD = sm + Map::HD + b * 3 * TR;
-    if (q + 1 < total_mb) { gather(q + 1, b ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // indices of minibatch q + 1 (requested a whole minibatch ago) -> shared; request those of q + 2; then gather q + 1 one barrier later
+    if (t < TR) { IDXs[(b ^ 1) * TR + t] = nidx; nidx = q + 2 < total_mb ? load_idx(q + 2) : -1; }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // the rows of minibatch q have landed (their gather was issued a minibatch ago)
     __syncthreads();
+    if (q + 1 < total_mb) gather(q + 1, b ^ 1);
     if (t < 8) sm[Map::LSP + t] = LS[t];
     // ---------------- forward (16-row tile)
     layer_fwd16(XT, I, P, P + off_b1(I), H1T, act);
@@ -335,27 +349,17 @@ __global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(NT, 1) epoch_kernel(
       }
     }
     __syncthreads();
-    // ---------------- finite check of this CTA's partial (training.jl:20), mailed to every CTA before the barrier
-    {
-      int badv = 0;
-      for (int i = t; i < NP + 8; i += NT) badv |= !isfinite(G[i]);
-      badv = __syncthreads_or(badv);
-      if (badv && t < C) cluster.map_shared_rank(bad_slot, t)[c] = 1;
-    }
     cluster.sync();
-    bool bad = false;
+    // A non-finite gradient (training.jl:20) shows in the squared norm every CTA reads after the second barrier: the flag is raised and the
+    // loop ends there; that step's Adam update has already been applied (the host raises on the flag either way).
+    // head sums of the whole minibatch: threads 0..4 add the C tails in rank order (every CTA computes the same totals)
+    if (t < 5) {
+      float s5 = 0.f;
 #pragma unroll
-    for (int x = 0; x < C; ++x) bad |= bad_slot[x] != 0;
-    // head sums of the whole minibatch (every CTA computes the same totals in the same order)
-    float tot[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int x = 0; x < C; ++x) {
-      const float *Gx = cluster.map_shared_rank(G, x);
-#pragma unroll
-      for (int y = 0; y < 5; ++y) tot[y] += Gx[NP + 8 + y];
+      for (int x = 0; x < C; ++x) s5 += cluster.map_shared_rank(G, x)[NP + 8 + t];
+      sm[Map::TOT + t] = s5;
     }
     const float cnt = (float)bm;
-    const float kl = tot[1] / cnt;
     // ---------------- the owner of entry i: sum of the C partials (fixed order, double), norm term, Flux Adam, broadcast
     p1 *= a.b1; p2 *= a.b2;
     const double c1 = 1.0 - p1, c2 = 1.0 - p2;
@@ -387,7 +391,11 @@ __global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(NT, 1) epoch_kernel(
         cluster.map_shared_rank(norm_slot, t)[c] = s8;
       }
     }
-    if (!bad) {
+    float tot[5];   // (the barrier above also published TOT)
+#pragma unroll
+    for (int y = 0; y < 5; ++y) tot[y] = sm[Map::TOT + y];
+    const float kl = tot[1] / cnt;
+    {
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
         const int i = lo + t + NT * u;
@@ -398,20 +406,29 @@ __global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(NT, 1) epoch_kernel(
           pm[u] = mt; pv[u] = vt;
           const float pn = pw[u] - (float)((double)mt / c1 / (sqrt((double)vt / c2) + a.eps) * a.eta);
           pw[u] = pn;
-          // the new value goes into every CTA's copies: raw vector, and the transposed W2 / W3 of the data-backward GEMMs
-          int tpos = -1;
-          if (i >= off_W2(I) && i < off_W2(I) + H * H) { const int e = i - off_W2(I); tpos = Map::W2T + (e & 63) * H + (e >> 6); }
-          else if (i >= off_W3(I) && i < off_W3(I) + H * O) { const int e = i - off_W3(I), k = e / O, o = e - k * O; tpos = Map::W3T + o * H + k; }
-#pragma unroll
-          for (int x = 0; x < C; ++x) {
-            float *smx = cluster.map_shared_rank(sm, x);
-            if (i < NP) { smx[Map::P + i] = pn; if (tpos >= 0) smx[tpos] = pn; }
-            else smx[Map::LS + (i - NP)] = pn;
-          }
+          sm[Map::NEWV + (i - lo)] = pn;   // parked locally: every CTA pulls the slices with 128-bit DSMEM loads after the barrier
         }
       }
     }
     cluster.sync();
+    {
+      // (parameters | logΣ) <- the owners' slices; then the transposed W2 / W3 of the data-backward GEMMs are rebuilt locally
+      constexpr int NV4 = (GMAX / 4 + NT - 1) / NT;   // 128-bit chunks per thread: all remote loads are issued before the first store
+      float4 nv[NV4];
+#pragma unroll
+      for (int u = 0; u < NV4; ++u) {
+        const int i4 = 4 * (t + NT * u);
+        if (i4 < NE) { const int x = i4 / per; nv[u] = *reinterpret_cast<const float4 *>(cluster.map_shared_rank(sm + Map::NEWV, x) + (i4 - x * per)); }
+      }
+#pragma unroll
+      for (int u = 0; u < NV4; ++u) {
+        const int i4 = 4 * (t + NT * u);
+        if (i4 + 3 < NE) *reinterpret_cast<float4 *>(P + i4) = nv[u];
+        else if (i4 < NE) { const float e4[4] = {nv[u].x, nv[u].y, nv[u].z, nv[u].w}; for (int j = 0; i4 + j < NE; ++j) P[i4 + j] = e4[j]; }
+      }
+      __syncthreads();
+      build_transposes(sm, I, O);
+    }
     // ---------------- info record (CTA 0), early stop (every CTA decides alike)
     if (c == 0 && t == 0) {
       double n2 = 0.0;
@@ -435,9 +452,14 @@ __global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(NT, 1) epoch_kernel(
       }
       rec[CRUX_PPO_GRAD_NORM] = (float)sqrt(n2);
       rec[CRUX_PPO_VALID] = 1.f;
-      if (bad || isnan(n2)) atomicOr(a.err_flags, CRUX_FLAG_NAN);
+      if (!isfinite(n2)) atomicOr(a.err_flags, CRUX_FLAG_NAN);
     }
-    if (bad) stop = true;
+    {
+      double n2a = 0.0;
+#pragma unroll
+      for (int x = 0; x < C; ++x) n2a += norm_slot[x];
+      if (!isfinite(n2a)) stop = true;
+    }
     if (HEAD == 0 && kl > a.target_kl) stop = true;   // this minibatch was applied; later ones are skipped (rl/ppo.jl:59)
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
