@@ -37,4 +37,5 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
                      const float *ret, int64_t n, const crux_ppo_hp *hp, const int32_t *order_actor, const int32_t *order_critic,
                      uint64_t seed, int *handled);
 int ppo_fill_order(crux_ctx *ctx, int32_t *out, int64_t n, uint64_t seed, uint32_t epoch);
+int ppo_fill_orders(crux_ctx *ctx, int32_t *out, int64_t n, uint64_t seed, uint32_t epoch0, int epochs);
 int ppo_ensure_bytes(crux_ctx *ctx, void **p, size_t *have, size_t need);

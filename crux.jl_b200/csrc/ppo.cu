@@ -17,9 +17,12 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
+// blockIdx.y = epoch offset: the row orders of several epochs are written behind each other ([epochs][n]) by one launch
 __global__ void perm_fill_kernel(int32_t *__restrict__ out, int64_t n, int half_bits, uint64_t seed, uint32_t epoch) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  out += (int64_t)blockIdx.y * n;
+  epoch += blockIdx.y;
   const uint32_t mask = (1u << half_bits) - 1u;
   uint64_t x = (uint64_t)i;
   do {
@@ -256,6 +259,15 @@ int ppo_fill_order(crux_ctx *ctx, int32_t *out, int64_t n, uint64_t seed, uint32
   int half_bits = 1;
   while ((1ll << (2 * half_bits)) < n) ++half_bits;
   perm_fill_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(out, n, half_bits, seed, epoch);
+  CRUX_LAUNCHED(ctx);
+  return CRUX_OK;
+}
+// the row orders of `epochs` consecutive epochs, [epochs][n], in ONE launch (epoch e of the result == ppo_fill_order(..., epoch0 + e))
+int ppo_fill_orders(crux_ctx *ctx, int32_t *out, int64_t n, uint64_t seed, uint32_t epoch0, int epochs) {
+  if (epochs <= 0) return CRUX_OK;
+  int half_bits = 1;
+  while ((1ll << (2 * half_bits)) < n) ++half_bits;
+  perm_fill_kernel<<<dim3((unsigned)cdiv(n, 256), (unsigned)epochs), 256, 0, ctx->stream>>>(out, n, half_bits, seed, epoch0);
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;
 }

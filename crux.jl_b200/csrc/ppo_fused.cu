@@ -2211,7 +2211,7 @@ static int persistent_epochs(crux_gaussian *actor, crux_mlp *mlp, int head, cons
     int32_t **buf = head == 0 ? &actor->order : &actor->order2;
     size_t *have = head == 0 ? &actor->order_bytes : &actor->order2_bytes;
     int rc = ppo_ensure_bytes(ctx, (void **)buf, have, (size_t)epochs * n * sizeof(int32_t)); if (rc) return rc;
-    for (int e = 0; e < epochs; ++e) { rc = ppo_fill_order(ctx, *buf + (int64_t)e * n, n, seed, (uint32_t)e); if (rc) return rc; }
+    rc = ppo_fill_orders(ctx, *buf, n, seed, 0u, epochs); if (rc) return rc;
     order = *buf;
   }
   mbp::Args a;
@@ -2253,9 +2253,11 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
   rc = ppo_ensure_bytes(ctx, (void **)&actor->info_critic, &actor->info_critic_bytes, ic); if (rc) return rc;
   CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(actor->info_actor, 0, ia, ctx->stream));
   CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(actor->info_critic, 0, ic, ctx->stream));
+  // device-generated row orders: ALL epochs of both networks in two launches at the start of the update (the per-epoch launch used to sit
+  // on each network's dependency chain in front of the epoch's first minibatch)
   if (!order_actor || (nmb_c && !order_critic)) {
-    rc = ppo_ensure_bytes(ctx, (void **)&actor->order, &actor->order_bytes, (size_t)n * sizeof(int32_t)); if (rc) return rc;
-    rc = ppo_ensure_bytes(ctx, (void **)&actor->order2, &actor->order2_bytes, (size_t)n * sizeof(int32_t)); if (rc) return rc;
+    rc = ppo_ensure_bytes(ctx, (void **)&actor->order, &actor->order_bytes, (size_t)i64max(1, hp->actor_epochs) * n * sizeof(int32_t)); if (rc) return rc;
+    rc = ppo_ensure_bytes(ctx, (void **)&actor->order2, &actor->order2_bytes, (size_t)i64max(1, hp->critic_epochs) * n * sizeof(int32_t)); if (rc) return rc;
   }
   fused_ctl_reset_kernel<<<1, 1, 0, ctx->stream>>>(actor->ctl);
   CRUX_LAUNCHED(ctx);
@@ -2285,13 +2287,14 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
   const bool no_persist = getenv("CRUX_NO_PERSIST") != nullptr;   // read per call: tests compare both paths
   const bool persist_a = !no_persist && ctx->world == 1 && !ctx->timing && hp->actor_batch <= mbp::MAXB && hp->actor_epochs * nmb_a >= 8;
   const bool persist_c = !no_persist && ctx->world == 1 && !ctx->timing && critic && hp->critic_batch <= mbp::MAXB && hp->critic_epochs * nmb_c >= 8;
+  if (!order_actor && !persist_a) { rc = ppo_fill_orders(ctx, actor->order, n, seed, 0u, hp->actor_epochs); if (rc) return rc; }
+  if (nmb_c && !order_critic && !persist_c) { rc = ppo_fill_orders(ctx, actor->order2, n, seed ^ 0xC2B2AE3D27D4EB4FULL, 0u, hp->critic_epochs); if (rc) return rc; }
   if (persist_a) { rc = persistent_epochs(actor, mu, 0, s, a, logprob, advantage, ret, n, hp, order_actor, seed); if (rc) return rc; }
   int64_t total = 0;
   const int64_t maxb_a = hp->actor_max_batches > 0 ? hp->actor_max_batches : INT64_MAX;
   for (int e = 0; e < hp->actor_epochs && total < maxb_a && !persist_a; ++e) {
     const int32_t *order;
-    if (order_actor) order = order_actor + (int64_t)e * n;
-    else { rc = ppo_fill_order(ctx, actor->order, n, seed, (uint32_t)e); if (rc) return rc; order = actor->order; }
+    order = (order_actor ? order_actor : actor->order) + (int64_t)e * n;
     for (int64_t mbi = 0; mbi < nmb_a && total < maxb_a; ++mbi, ++total) {
       const int64_t off = mbi * hp->actor_batch, bm = i64min(hp->actor_batch, n - off);
       float *rec = actor->info_actor + ((int64_t)e * nmb_a + mbi) * CRUX_PPO_INFO_STRIDE;
@@ -2320,12 +2323,7 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
   const int64_t maxb_c = hp->critic_max_batches > 0 ? hp->critic_max_batches : INT64_MAX;
   for (int e = 0; e < hp->critic_epochs && nmb_c && total < maxb_c && !persist_c; ++e) {
     const int32_t *order;
-    if (order_critic) order = order_critic + (int64_t)e * n;
-    else {
-      rc = ppo_fill_order(ctx, actor->order2, n, seed ^ 0xC2B2AE3D27D4EB4FULL, (uint32_t)e);
-      if (rc) { ctx->stream = main_stream; return rc; }
-      order = actor->order2;
-    }
+    order = (order_critic ? order_critic : actor->order2) + (int64_t)e * n;
     for (int64_t mbi = 0; mbi < nmb_c && total < maxb_c; ++mbi, ++total) {
       const int64_t off = mbi * hp->critic_batch, bm = i64min(hp->critic_batch, n - off);
       float *rec = actor->info_critic + ((int64_t)e * nmb_c + mbi) * CRUX_PPO_INFO_STRIDE;
