@@ -68,8 +68,8 @@ struct Map {   // bytes; every operand is a pair of planes hi | lo
   static constexpr int SA = SX + 2 * SX_G;                       // per (g, b) head inputs: actions [32][8] | logprob, advantage, return [32] each | rows [32] ints
   static constexpr int HEAD_BUF = NR * 8 * 4 + 3 * NR * 4 + NR * 4;
   static constexpr int BIAS = SA + 4 * HEAD_BUF;                 // b3[8] | logΣ[8] | 1/σ²[8]
-  static constexpr int RED = BIAS + 24 * 4;                      // per group: [2 ch][64] db1 | [2 ch][64] db2 | [2][24] head scratch
-  static constexpr int RED_G = (2 * 64 * 2 + 2 * 24) * 4;
+  static constexpr int RED = BIAS + 24 * 4;                      // per group: [2 ch][64] db1 | [2 ch][64] db2 | [8][24] head scratch
+  static constexpr int RED_G = (2 * 64 * 2 + 8 * 24) * 4;
   static constexpr int BAR = RED + 2 * RED_G;                    // bar_par | per group: bar_mma, bar_g[2], bar_free[2] | tmem slot
   static constexpr int TOTAL = BAR + 128;
   static_assert(ACT % 16 == 0 && DZT % 16 == 0 && DO % 16 == 0 && SX % 16 == 0 && BAR % 8 == 0, "alignment");
@@ -491,6 +491,70 @@ __global__ void __maxnreg__(80) minibatch_kernel(MbArgs a) {
       MB6_READY();
       MB6_WAIT_MMA();
       MB6_STAMP();   // E2 + L3 done
+      if (HEAD == 0) {
+        // Actor loss head, spread over (row, action dimension) pairs.  With one thread per row the head was a 2 700-cycle serial stretch on
+        // two half-warps per tile (the critic's takes 350: scripts/mb6_prof.py), four times per launch on the update's critical chain.
+        // Phase A: the 32 threads that can address the rows' TMEM lanes park mu = out + b3 in the dOut rows [row][8].
+        const float *SAp = reinterpret_cast<const float *>(smb + Map::SA + (2 * g + b) * Map::HEAD_BUF), *SHp = SAp + NR * 8;
+        const int *sidx = reinterpret_cast<const int *>(SHp + 3 * NR);
+        float *DOp = reinterpret_cast<float *>(smb + Map::DO + g * Map::DO_G);
+        tc5::mbar_wait(bar_g + 8 * b, (uint32_t)((k >> 1) & 1));   // (long complete) the cp.async data of this tile is visible
+        if (ch == 0 && q < 2) {
+          uint32_t v[8];
+          MB6_LD8(v, quad_addr + OUTC);
+          MB6_WAIT_LD();
+          if ((lane >> 4) == g) {
+            const int row = 16 * q + (lane & 15);
+            float4 *p = reinterpret_cast<float4 *>(DOp + row * 8);
+            p[0] = make_float4(__uint_as_float(v[0]) + bias[0], __uint_as_float(v[1]) + bias[1], __uint_as_float(v[2]) + bias[2], __uint_as_float(v[3]) + bias[3]);
+            p[1] = make_float4(__uint_as_float(v[4]) + bias[4], __uint_as_float(v[5]) + bias[5], __uint_as_float(v[6]) + bias[6], __uint_as_float(v[7]) + bias[7]);
+          }
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(NB_EPI + g), "n"(NTE) : "memory");
+        // Phase B: thread (row, j) = (te >> 3, te & 7) of the group's 256 epilogue threads; the 8 lanes of a row add their logpdf terms with
+        // a shuffle tree, every lane evaluates the (cheap) ratio / clip logic of its row, lane j owns dOut_j, dlogΣ_j and db3_j.
+        {
+          const int te_ = t - g * NTE, hrow = te_ >> 3, hj = te_ & 7;
+          const bool live = sidx[hrow] >= 0;
+          float d = 0.f, ivar = 0.f, logp = 0.f;
+          if (hj < O) {
+            d = SAp[hrow * O + hj] - DOp[hrow * 8 + hj];
+            ivar = bias[16 + hj];
+            logp = -(d * d) * (0.5f * ivar) - LOG_SQRT_2PI - bias[8 + hj];
+          }
+          logp += __shfl_xor_sync(0xffffffffu, logp, 1);
+          logp += __shfl_xor_sync(0xffffffffu, logp, 2);
+          logp += __shfl_xor_sync(0xffffffffu, logp, 4);
+          const float Ai = SHp[NR + hrow], old = SHp[hrow];
+          float dlogp = 0.f;
+          if (live) {
+            float obj, clipv = 0.f;
+            if (a.a2c) {
+              obj = logp * Ai;
+              dlogp = -a.lambda_p * a.inv_bg * Ai;
+            } else {
+              const float rt = expf(logp - old);
+              const float lo = 1.f - a.eps_clip, hi = 1.f + a.eps_clip;
+              const float x = rt * Ai, y = fminf(fmaxf(rt, lo), hi) * Ai;
+              const bool firstb = !(y < x);  // min(x, y) keeps x on ties
+              obj = firstb ? x : y;
+              dlogp = firstb ? -a.lambda_p * a.inv_bg * x : 0.f;
+              clipv = (rt > hi || rt < lo) ? 1.f : 0.f;
+            }
+            if (hj == 0) { s_obj += obj; s_clip += clipv; s_kl += old - logp; s_adv += Ai; s_ret += SHp[2 * NR + hrow]; }
+          }
+          const float dout = dlogp * d * ivar;             // 0 for j >= O (d = ivar = 0) and for padding rows (dlogp = 0)
+          if (hj < O) dls[0] += dlogp * (d * d * ivar - 1.f);   // this thread's OWN action dimension hj (the accumulator slots are per thread)
+          db3[0] += dout;
+          __syncwarp();                                        // every lane of the row has read mu before lane j overwrites its slot
+          DOp[hrow * 8 + hj] = dout;
+          float hi_, lo_;
+          tc5::split(dout, hi_, lo_);
+          unsigned char *pt = smb + Map::DOT + g * Map::DOT_G + canon(0, hrow, NR) + 16 * hj;
+          *reinterpret_cast<float *>(pt) = hi_;
+          *reinterpret_cast<float *>(pt + Map::DOT_PLANE) = lo_;
+        }
+      } else
       if (ch == 0 && q < 2) {   // loss head (thread = row: the group's 16 lanes of warps q = 0, 1)
         const float *SAp = reinterpret_cast<const float *>(smb + Map::SA + (2 * g + b) * Map::HEAD_BUF), *SHp = SAp + NR * 8;
         const int *sidx = reinterpret_cast<const int *>(SHp + 3 * NR);
@@ -675,7 +739,8 @@ __global__ void __maxnreg__(80) minibatch_kernel(MbArgs a) {
         }
       }
     }
-    float *red = reinterpret_cast<float *>(smb + Map::RED + g * Map::RED_G);   // [2 ch][64] db1 | [2 ch][64] db2 | [2][24] head
+    float *red = reinterpret_cast<float *>(smb + Map::RED + g * Map::RED_G);   // [2 ch][64] db1 | [2 ch][64] db2 | [HRED_ROWS][24] head
+    constexpr int HRED_ROWS = HEAD == 0 ? 8 : 2;   // actor: one row per epilogue warp; critic: the two row-owning warps
     // a feature's rows are spread over the 4 lanes with the same lane / 4 (and over the two column halves ch)
 #pragma unroll
     for (int o = 1; o <= 2; o <<= 1) {
@@ -684,6 +749,21 @@ __global__ void __maxnreg__(80) minibatch_kernel(MbArgs a) {
     }
     if ((lane & 3) == 0) { red[ch * 64 + fa] = db1a; red[ch * 64 + fa + 8] = db1b; red[128 + ch * 64 + fa] = db2a; red[128 + ch * 64 + fa + 8] = db2b; }
     float *hred = red + 256;
+    if (HEAD == 0) {
+      // (row, j) threads: s_* live in the j = 0 lanes, dls[0] / db3[0] are this thread's action dimension j = lane & 7 -> per-warp rows of
+      // hred [8 warps][24]: [0..5) sums, [8 + j] dlogΣ_j, [16 + j] db3_j; added over the 8 warps in a fixed order below
+      const int we_ = (t - g * NTE) >> 5;
+      float v;
+      v = warp_sum(s_obj); if (lane == 0) hred[we_ * 24 + 0] = v;
+      v = warp_sum(s_kl); if (lane == 0) hred[we_ * 24 + 1] = v;
+      v = warp_sum(s_clip); if (lane == 0) hred[we_ * 24 + 2] = v;
+      v = warp_sum(s_adv); if (lane == 0) hred[we_ * 24 + 3] = v;
+      v = warp_sum(s_ret); if (lane == 0) hred[we_ * 24 + 4] = v;
+      float dl = dls[0], d3 = db3[0];
+      dl += __shfl_xor_sync(0xffffffffu, dl, 8); dl += __shfl_xor_sync(0xffffffffu, dl, 16);
+      d3 += __shfl_xor_sync(0xffffffffu, d3, 8); d3 += __shfl_xor_sync(0xffffffffu, d3, 16);
+      if (lane < 8) { hred[we_ * 24 + 8 + lane] = dl; hred[we_ * 24 + 16 + lane] = d3; }
+    } else
     if (ch == 0 && q < 2) {   // head sums: this group's rows live in 16 lanes of warps q = 0, 1 (the other lanes hold zeros)
       float v;
       v = warp_sum(s_obj); if (lane == 0) hred[q * 24 + 0] = v;
@@ -701,12 +781,21 @@ __global__ void __maxnreg__(80) minibatch_kernel(MbArgs a) {
     const int te = t - g * NTE;
     if (te < 64) { const float v = red[te] + red[64 + te]; out(off_b1(I) + te) = v; if (a.nan_flag && v != v) atomicOr(a.nan_flag, 1); }
     else if (te < 128) { const int j = te - 64; const float v = red[128 + j] + red[192 + j]; out(off_b2(I) + j) = v; if (a.nan_flag && v != v) atomicOr(a.nan_flag, 1); }
-    else if (te < 128 + O) { const int o = te - 128; out(off_b3(I, O) + o) = hred[16 + o] + hred[24 + 16 + o]; }
+    else if (te < 128 + O) {
+      const int o = te - 128;
+      float v = 0.f;
+#pragma unroll
+      for (int r_ = 0; r_ < HRED_ROWS; ++r_) v += hred[r_ * 24 + 16 + o];
+      out(off_b3(I, O) + o) = v;
+    }
     else if (te >= 160 && te < 176) {
       // tail layout: [n_params .. +8) = dlogΣ, [n_params+8 .. +16) = obj, kl, clip, adv, ret, 0, 0, 0
       const int kk = te - 160, src = kk < 8 ? 8 + kk : kk - 8;
       float v = 0.f;
-      if (src < 5 || (src >= 8 && src < 16)) v = hred[src] + hred[24 + src];
+      if (src < 5 || (src >= 8 && src < 16)) {
+#pragma unroll
+        for (int r_ = 0; r_ < HRED_ROWS; ++r_) v += hred[r_ * 24 + src];
+      }
       if (HEAD == 0 && kk == 14 && blockIdx.x == 0 && g == 0) {   // sum(logΣ) as this kernel saw it: the entropy of the info record (policies.jl:348)
         v = 0.f;
         for (int j = 0; j < O; ++j) v += bias[8 + j];
