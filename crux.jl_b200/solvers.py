@@ -356,7 +356,11 @@ class OffPolicySolver:
                 raise NotImplementedError(f"{self.kind}: prioritized replay / weighted_loss are only wired for DQN and SoftQ (off_policy.jl:83-93)")
             if self.kind == "sac" and (self.c_opt.update_every != 1 or self.a_opt.update_every != 1):
                 raise NotImplementedError("sac: c_opt/a_opt.update_every != 1 is not supported by the fused SAC update (off_policy.jl:91,96)")
+        # Training info of the cycle's LAST epoch is read back when a logger is attached (one synchronisation per value_training call; the
+        # reference aggregates every epoch's Dict, off_policy.jl:104-110 -- reading all of them would put a host sync behind every train! step)
+        want_info = self.log is not None or getattr(self, "collect_info", False)
         for epoch in range(self.c_opt.epochs):
+            info_buf = np.zeros(8, F32) if (want_info and epoch == self.c_opt.epochs - 1) else None
             self.train_count += 1
             rand_(D, self.buffer, i=self.i, draws=None if draws is None else [draws[epoch]], seed=_dom(self.seed, _DOM_REPLAY),
                   ctr=2 * self.train_count)
@@ -379,7 +383,10 @@ class OffPolicySolver:
                     self.buffer.update_priorities_(D.indices_dev(), td)
                 w = D.column("weight") if (self.weighted_loss and "weight" in D.schema) else None
                 if epoch % self.c_opt.update_every == 0:
-                    pi.mlp.train_dqn(s, a, y, w, B)                                                                   # off_policy.jl:91-93
+                    pi.mlp.train_dqn(s, a, y, w, B, info_buf)                                                         # off_policy.jl:91-93
+                    if info_buf is not None:
+                        n_ = self.c_opt.name
+                        self.last_info = {n_ + "loss": float(info_buf[0]), n_ + "grad_norm": float(info_buf[1]), "Qavg": float(info_buf[2])}
             elif self.kind in ("ddpg", "td3"):
                 sm = self.P.get("pi_smooth")                      # None: plain ddpg_target (rl/ddpg.jl:6-8)
                 e = None if noise is None else ctx.to_device(noise[epoch], torch.float32)
@@ -390,14 +397,26 @@ class OffPolicySolver:
                                               0.0 if sm is None else float(F32(sm.sigma(self.i))), -math.inf if sm is None else float(sm.eps_min),
                                               math.inf if sm is None else float(sm.eps_max), ptr(lo), 0 if lo is None else lo.size, ptr(hi),
                                               0 if hi is None else hi.size, ptr(e), _dom(self.seed, _DOM_UPDATE), 3 * self.train_count, 1 if do_c else 0,
-                                              1 if do_a else 0, None, None))
+                                              1 if do_a else 0, None, ptr(info_buf)))
+                if info_buf is not None:
+                    cn, an = self.c_opt.name, self.a_opt.name
+                    self.last_info = {cn + "loss": float(info_buf[1]), cn + "grad_norm": float(info_buf[2]), "Q1avg": float(info_buf[6])}
+                    if do_a:
+                        self.last_info.update({an + "loss": float(info_buf[3]), an + "grad_norm": float(info_buf[4])})
+                    if self.kind == "td3":
+                        self.last_info["Q2avg"] = float(info_buf[7])
             else:
                 e = (None, None, None) if noise is None else [ctx.to_device(x, torch.float32) for x in noise[epoch]]
                 ctx.check(lib.crux_sac_train(self._sac, ptr(s), ptr(a), ptr(sp), ptr(r), ptr(dn), B, float(gamma), ptr(e[0]), ptr(e[1]), ptr(e[2]),
-                                             _dom(self.seed, _DOM_UPDATE), 3 * self.train_count, None, None))
+                                             _dom(self.seed, _DOM_UPDATE), 3 * self.train_count, None, ptr(info_buf)))
+                if info_buf is not None:
+                    cn, an = self.c_opt.name, self.a_opt.name
+                    self.last_info = {"temp_loss": float(info_buf[0]), cn + "loss": float(info_buf[1]), cn + "grad_norm": float(info_buf[2]),
+                                      an + "loss": float(info_buf[3]), an + "grad_norm": float(info_buf[4]), "entropy": float(info_buf[5]),
+                                      "Q1avg": float(info_buf[6]), "Q2avg": float(info_buf[7])}
         if self.kind in ("dqn", "softq"):  # no separate actor: target update after the epoch loop (off_policy.jl:108)
             polyak_average_(self.agent.pi_target, self.agent.pi, self.tau)
-        return infos
+        return [self.last_info] if (want_info and self.last_info) else infos
 
     def __del__(self):
         try:

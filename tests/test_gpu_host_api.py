@@ -406,11 +406,16 @@ def test_solve_sac_runs(crux, ctx):
     Q = lambda: crux.ContinuousNetwork(crux.Chain(D(obs + act, hid, crux.relu, rng=rng), D(hid, hid, crux.relu, rng=rng), D(hid, 1, rng=rng)), ctx=ctx)
     pi = crux.ActorCritic(A, crux.DoubleNetwork(Q(), Q()))
     before = A.mu.mlp.get_flat().copy()
-    S = crux.SAC(pi, crux.ContinuousSpace(obs), N=512, dN=64, c_opt=dict(batch_size=64, epochs=4), buffer_size=2000, buffer_init=256)
+    log = crux.LoggerParams(period=64, verbose=False, logger=None, fns=[])
+    S = crux.SAC(pi, crux.ContinuousSpace(obs), N=512, dN=64, c_opt=dict(batch_size=64, epochs=4), buffer_size=2000, buffer_init=256, log=log)
     crux.solve(S, crux.HostLinQuad(16, seed=0))
     after = A.mu.mlp.get_flat()
     assert np.isfinite(after).all() and not np.array_equal(before, after)
     assert len(S.buffer) == 512 and S.i == 512  # the initial fill counts toward N (off_policy.jl:122-133)
+    # the off-policy training log is filled from the update's info record (off_policy.jl:104-110, logging.jl:48-54)
+    last = log.history[-1]
+    assert {"temp_loss", "critic_loss", "critic_grad_norm", "actor_loss", "actor_grad_norm", "entropy", "Q1avg", "Q2avg", "noise_std"} <= set(last), last
+    assert all(np.isfinite(last[k]) for k in ("critic_loss", "actor_loss", "critic_grad_norm"))
 
 
 def test_native_rollout_loop_equals_python_loop(crux, ctx):
