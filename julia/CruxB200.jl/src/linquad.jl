@@ -8,11 +8,17 @@ struct LinQuadMDP <: MDP{Vector{Float32},Vector{Float32}}
     γ::Float32
 end
 function LinQuadMDP(; sdim::Int=17, adim::Int=6, γ=0.99f0, rng=Random.MersenneTwister(0))
-    A = 0.95f0 * Matrix{Float32}(Flux.I, sdim, sdim) .+ 0.02f0 .* randn(rng, Float32, sdim, sdim)
+    A = Float32[i == j ? 0.95f0 : 0f0 for i in 1:sdim, j in 1:sdim] .+ 0.02f0 .* randn(rng, Float32, sdim, sdim)
     LinQuadMDP(A, 0.1f0 .* randn(rng, Float32, sdim, adim), Float32(γ))
 end
 POMDPs.discount(m::LinQuadMDP) = m.γ
-POMDPs.initialstate(m::LinQuadMDP) = POMDPs.ImplicitDistribution(rng -> (rand(rng, Float32, size(m.A, 1)) .* 2f0 .- 1f0) .* 0.1f0)
+"s0 ~ U(-0.1, 0.1)^S as a distribution object: `rand(initialstate(m))` (sampler.jl:44) and `rand(rng, initialstate(m))` both work"
+struct LinQuadInit
+    n::Int
+end
+Base.eltype(::Type{LinQuadInit}) = Vector{Float32}
+Random.rand(rng::Random.AbstractRNG, d::Random.SamplerTrivial{LinQuadInit}) = (rand(rng, Float32, d[].n) .* 2f0 .- 1f0) .* 0.1f0
+POMDPs.initialstate(m::LinQuadMDP) = LinQuadInit(size(m.A, 1))
 POMDPs.isterminal(m::LinQuadMDP, s) = abs(s[1]) > 5f0
 POMDPs.convert_s(::Type{<:AbstractArray}, s::Vector{Float32}, ::LinQuadMDP) = s
 POMDPs.actions(m::LinQuadMDP) = Crux.ContinuousSpace(size(m.B, 2))

@@ -71,17 +71,17 @@ function solve(𝒮::OffPolicySolver, envs::Vector{<:MDP})
         q, q⁻ = mirror(π), mirror(𝒮.agent.π⁻)
         set_adam!(q.q, 𝒮.c_opt.optimizer)
         ϵ = 𝒮.agent.π_explore isa MixedPolicy ? 𝒮.agent.π_explore.ϵ : error("CruxB200: DQN needs an ϵ-greedy π_explore (MixedPolicy)")
-        collect!(n, i) = steps!(s, q, ϵ, buffer; Nsteps=n, i=i)
-        train!() = value_training_dqn(𝒮, q, q⁻, 𝒟, buffer, γ, count)
-        back() = (pull!(q); pull!(q⁻); nothing)
+        collect! = (n, i) -> steps!(s, q, ϵ, buffer; Nsteps=n, i=i)      # anonymous: named local methods must not be defined per branch
+        train! = () -> value_training_dqn(𝒮, q, q⁻, 𝒟, buffer, γ, count)
+        back = () -> (pull!(q); pull!(q⁻); nothing)
         return offpolicy_loop(𝒮, N, istart, collect!, train!, back)
     elseif π isa ActorCritic && π.A isa SquashedGaussianPolicy && π.C isa DoubleNetwork
         ss = sac_session(𝒮)
         ne = 𝒮.agent.π_explore isa GaussianNoiseExplorationPolicy ? 𝒮.agent.π_explore : error("CruxB200: SAC needs a GaussianNoiseExplorationPolicy π_explore (rl/sac.jl:81)")
         prioritized && error("CruxB200: prioritized replay is wired for DQN only (off_policy.jl:83)")
-        collect!(n, i) = steps!(s, ss.g, ne, buffer; Nsteps=n, i=i)
-        train!() = value_training_sac(𝒮, ss.st, 𝒟, buffer, γ, count)
-        back() = (pull!(ss.g); pull!(ss.c); pull_log_alpha!(𝒮, ss.st); nothing)
+        collect! = (n, i) -> steps!(s, ss.g, ne, buffer; Nsteps=n, i=i)
+        train! = () -> value_training_sac(𝒮, ss.st, 𝒟, buffer, γ, count)
+        back = () -> (pull!(ss.g); pull!(ss.c); pull_log_alpha!(𝒮, ss.st); nothing)
         try
             return offpolicy_loop(𝒮, N, istart, collect!, train!, back)
         finally
