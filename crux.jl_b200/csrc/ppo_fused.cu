@@ -1678,23 +1678,37 @@ template <int RWT>
 __global__ void __launch_bounds__(RWT * 32, 9) reduce_adam_kernel(const float *__restrict__ partials, int nparts, int pstride, int n_params,
                                                                  float *__restrict__ grads, float count, float ls_shift, int n_ls,
                                                                  double *__restrict__ norm_part, int *__restrict__ state, AdamArgs a, PeerOut peer) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next minibatch kernel of this network may start its prologue
+  static_assert(RWT == 4, "16 row subsets = 4 warps x 4 lane groups");
   asm volatile("griddepcontrol.wait;" ::: "memory");                // the minibatch kernel's partials (and its KL-stop flag) are complete
-  if (stopped(a.ctl, a.mb)) return;
-  if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); a.trace[0] = gt_; }
+#define TAIL_TRACE(slot) do { if (a.trace) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); a.trace[slot] = gt_; } } while (0)
+  if (blockIdx.x == 0 && threadIdx.x == 0) TAIL_TRACE(0);
+  // Latency is what this kernel costs (it sits on its network's dependency chain, scripts/mb6_trace.py).  The CTA's whole slice of the
+  // partials is requested at once (10 x 16 bytes per thread in flight); everything else it will need -- the optimiser state of its 32
+  // entries, the step counter, the β-power cache, the stop flag -- is PREFETCHED into L1 first (no destination registers: at 56
+  // registers per thread, loads would be spilled, and a spill store waits for its load) and read once the partial rows are summed.
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n_groups = (n_params + 16 + 31) / 32;
+  auto prefetch = [](const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); };
+  if (w == 0 && blockIdx.x < n_groups) {   // warp 0 owns the finished entries
+    const int p = blockIdx.x * 32 + lane;
+    if (p < n_params) { prefetch(a.p + p); prefetch(a.m + p); prefetch(a.v + p); }
+    else if (p < n_params + n_ls) { const int j = p - n_params; prefetch(a.ls + j); prefetch(a.ls_m + j); prefetch(a.ls_v + j); }
+  } else if (w == 1 && lane < 3) {
+    if (lane == 0) prefetch(state);
+    else if (lane == 1) prefetch(norm_part + BETA_CACHE);
+    else if (a.ctl) prefetch(a.ctl + 1);
+  }
   // several GPUs: the gradient all-reduce is fused in with the LL (flag-in-data) protocol.  The CTA that finishes entry i stores it as one
   // 8-byte {value, sequence} word into the receive region of EVERY rank over NVLink and then polls the `world` words of the same entry
   // in its own region: rank-ordered sum (bit-identical on all ranks) -> Adam on that entry.  No fence, no flag, no collective launch.
-  unsigned long long pseq = 0ULL;
-  if (peer.enabled) pseq = *(volatile const unsigned long long *)peer.seq_dev + 1ULL;   // advanced by the last CTA of this kernel
-  const int64_t pbase = ((int64_t)(pseq & 1ULL) * 16 + peer.rank) * peer.cap;
-  const unsigned long long *slot0 = a.ll_recv + (int64_t)(pseq & 1ULL) * 16 * a.peer_cap;
+  unsigned int pseq = 0u;   // low word of the sequence number (advanced by the last CTA of this kernel); bit 0 selects the receive buffer
   auto exchange = [&](int idx, float v) -> float {
     if (!peer.enabled) return v;
-    const unsigned long long word = ((unsigned long long)(unsigned int)pseq << 32) | (unsigned long long)__float_as_uint(v);
+    const int64_t pbase = ((int64_t)(pseq & 1u) * 16 + peer.rank) * peer.cap;
+    const unsigned long long word = ((unsigned long long)pseq << 32) | (unsigned long long)__float_as_uint(v);
     for (int q = 0; q < peer.world; ++q) *(volatile unsigned long long *)(peer.ll[q] + pbase + idx) = word;
     float sum = 0.f;
-    const volatile unsigned long long *src = slot0 + idx;
+    const volatile unsigned long long *src = a.ll_recv + (int64_t)(pseq & 1u) * 16 * a.peer_cap + idx;
     for (int base = 0; base < peer.world; base += 4) {   // 4 loads in flight, rank order kept
       unsigned long long wd[4];
 #pragma unroll
@@ -1703,49 +1717,84 @@ __global__ void __launch_bounds__(RWT * 32, 9) reduce_adam_kernel(const float *_
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         if (base + u < peer.world) {
-          while ((unsigned int)(wd[u] >> 32) != (unsigned int)pseq) wd[u] = src[(int64_t)(base + u) * a.peer_cap];
+          while ((unsigned int)(wd[u] >> 32) != pseq) wd[u] = src[(int64_t)(base + u) * a.peer_cap];
           sum += __uint_as_float((unsigned int)wd[u]);
         }
     }
     return sum;
   };
   __shared__ double sh[RWT][33];
+  __shared__ float4 stage[10][RWT * 32];   // this CTA's slice of the partials: [row k of the thread][thread]
   __shared__ double s_c1, s_c2;
   __shared__ int s_bad;
   __shared__ bool last;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int n_groups = (n_params + 16 + 31) / 32;
-  // warp 0 owns the finished entries: its optimiser state is requested NOW, so that the loads fly under the reduction
+  // partial rows: thread (w, sub = lane >> 3) adds rows 4w + sub, + 16, ... of the four entries 4 (lane & 7) .. + 3 -- 128-bit loads,
+  // double accumulation in a fixed order (lane groups by a shuffle tree, then the four warps in order): bit-reproducible
+  const int q4 = (lane & 7) * 4, sub = lane >> 3, r0 = w * 4 + sub;
   float pm = 0.f, pv = 0.f, pp = 0.f;
-  float *ap = nullptr, *am = nullptr, *av = nullptr;
-  if (w == 0 && blockIdx.x < n_groups) {
-    const int p = blockIdx.x * 32 + lane;
-    if (p < n_params) { ap = a.p + p; am = a.m + p; av = a.v + p; }
-    else if (p < n_params + n_ls) { const int j = p - n_params; ap = a.ls + j; am = a.ls_m + j; av = a.ls_v + j; }
-    if (ap) { pp = __ldcg(ap); pm = __ldcg(am); pv = __ldcg(av); }
-  }
-  if (threadIdx.x == 0) {
-    const int step = state[0] + 1;   // this step (the counter and the β-power cache are advanced by the last CTA, after every CTA has read them)
-    double p1, p2;
-    beta_pows(norm_part + BETA_CACHE, step, a.b1, a.b2, p1, p2);
-    s_c1 = 1.0 - p1;
-    s_c2 = 1.0 - p2;
-    s_bad = state[2];
-  }
-  __syncthreads();
-  const bool bad = s_bad != 0;
-  const double c1 = s_c1, c2 = s_c2;
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int p = grp * 32 + lane;
-    double s = 0.0;
-    if (p < n_params + 16) {
-      const float *src = partials + p;
-#pragma unroll 10
-      for (int c = w; c < nparts; c += RWT) s += (double)__ldcg(src + (int64_t)c * pstride);
+    const float *src = partials + (int64_t)grp * 32 + q4 + (int64_t)r0 * pstride;   // grp * 32 + 31 < pstride: whole float4s inside the row
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const bool first = grp == (int)blockIdx.x;
+    if (nparts <= 160) {
+      // the slice lands in shared memory through cp.async: ten 16-byte requests per thread in flight without a single destination register
+#pragma unroll
+      for (int k = 0; k < 10; ++k)
+        if (r0 + 16 * k < nparts)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&stage[k][threadIdx.x])), "l"(src + (int64_t)(16 * k) * pstride) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (first) {   // everything is in flight: now the first dependent instructions
+        const int stop_at = a.ctl ? *(volatile const int *)(a.ctl + 1) : 0;
+        if (peer.enabled) pseq = (unsigned int)(*(volatile const unsigned long long *)peer.seq_dev + 1ULL);
+        if (stop_at != 0 && stop_at <= a.mb) {   // an EARLIER minibatch raised the KL stop flag (uniform over the grid): nothing is written
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          return;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) TAIL_TRACE(2);
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (blockIdx.x == 0 && threadIdx.x == 0) TAIL_TRACE(7);
+#pragma unroll
+      for (int k = 0; k < 10; ++k)
+        if (r0 + 16 * k < nparts) { const float4 v = stage[k][threadIdx.x]; s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w; }
+    } else {   // (more partial rows than any current GPU has SMs)
+      if (first) {
+        const int stop_at = a.ctl ? *(volatile const int *)(a.ctl + 1) : 0;
+        if (peer.enabled) pseq = (unsigned int)(*(volatile const unsigned long long *)peer.seq_dev + 1ULL);
+        if (stop_at != 0 && stop_at <= a.mb) return;
+      }
+      for (int r = r0; r < nparts; r += 16) {
+        const float4 v = __ldcg(reinterpret_cast<const float4 *>(src + (int64_t)(r - r0) * pstride));
+        s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+      }
     }
-    sh[w][lane] = s;
+    if (w == 0) {   // optimiser state of this group's entries (L1 hits for the CTA's first group)
+      const int p = grp * 32 + lane;
+      if (p < n_params) { pp = a.p[p]; pm = a.m[p]; pv = a.v[p]; }
+      else if (p < n_params + n_ls) { const int j = p - n_params; pp = a.ls[j]; pm = a.ls_m[j]; pv = a.ls_v[j]; }
+    } else if (w == 1 && first && lane == 0) {   // β^t of this step from the cache of the previous one (the cache is advanced by the last CTA, after every CTA has read it)
+      const int step = *(volatile const int *)state + 1;
+      const int nan_seen = *(volatile const int *)(state + 2);
+      const volatile double *bc = norm_part + BETA_CACHE;
+      const double bc0 = bc[0], bc1 = bc[1], bc2 = bc[2];
+      double p1, p2;
+      if ((int)bc0 == step) { p1 = bc1; p2 = bc2; }
+      else if ((int)bc0 == step - 1 && step > 1) { p1 = bc1 * a.b1; p2 = bc2 * a.b2; }
+      else { p1 = pow(a.b1, (double)step); p2 = pow(a.b2, (double)step); }
+      s_c1 = 1.0 - p1; s_c2 = 1.0 - p2; s_bad = nan_seen;   // read by warp 0 behind the barrier below
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    }
+    if (sub == 0) { sh[w][q4] = s0; sh[w][q4 + 1] = s1; sh[w][q4 + 2] = s2; sh[w][q4 + 3] = s3; }
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) TAIL_TRACE(3);
     if (w == 0) {
+      const int p = grp * 32 + lane;
+      const double c1 = s_c1, c2 = s_c2;
+      const bool bad = s_bad != 0;
       double sq = 0.0;
       if (p < n_params + 16) {
         double t = 0.0;
@@ -1764,10 +1813,8 @@ __global__ void __launch_bounds__(RWT * 32, 9) reduce_adam_kernel(const float *_
           else if (q == 6) grads[n_params + 64 + 6] = g;   // identical on every rank: not exchanged
         }
         if (!bad && p < n_params + n_ls) {   // Flux Adam on this entry (float32 moments, Float64 scalars)
-          if (grp != (int)blockIdx.x) {      // grid-strided launch (never the case today): state not prefetched
-            if (p < n_params) { ap = a.p + p; am = a.m + p; av = a.v + p; } else { const int j = p - n_params; ap = a.ls + j; am = a.ls_m + j; av = a.ls_v + j; }
-            pp = __ldcg(ap); pm = __ldcg(am); pv = __ldcg(av);
-          }
+          float *ap, *am, *av;
+          if (p < n_params) { ap = a.p + p; am = a.m + p; av = a.v + p; } else { const int j = p - n_params; ap = a.ls + j; am = a.ls_m + j; av = a.ls_v + j; }
           const double gd = (double)g;
           const float mt = (float)(a.b1 * (double)pm + (1.0 - a.b1) * gd);
           const float vt = (float)(a.b2 * (double)pv + (1.0 - a.b2) * gd * gd);
@@ -1782,43 +1829,69 @@ __global__ void __launch_bounds__(RWT * 32, 9) reduce_adam_kernel(const float *_
     }
     __syncthreads();   // sh is reused by the next group
   }
+  if (blockIdx.x >= n_groups && a.ctl && *(volatile const int *)(a.ctl + 1) != 0 && *(volatile const int *)(a.ctl + 1) <= a.mb) return;   // (a CTA without a group)
+  if (blockIdx.x == 0 && threadIdx.x == 0) TAIL_TRACE(4);
+  // parameters, moments and planes of this CTA's entries are on their way: this network's next minibatch kernel may be scheduled.  It runs its
+  // weight-independent prologue (barriers, tensor memory, the first tile's gather) under the record keeping below and reads the weights
+  // behind its own griddepcontrol.wait, i.e. after this grid has completed.  (Triggered at the START of this kernel, the dependent took
+  // over every SM the other network's minibatch kernel was about to get and idled there: 1.40 against 1.34 ms per iteration.)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<unsigned int *>(state + 1), 1u) == gridDim.x - 1u;
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) TAIL_TRACE(5);
   if (!last) return;
+  if (threadIdx.x == 0) TAIL_TRACE(6);
   __threadfence();
   if (w == 0) {   // ||g||^2: lane l adds groups l, l + 32, ... in order, the 32 lane sums are combined by a fixed shuffle tree: bit-reproducible
+    const float *sums = grads + n_params + 64;
+    float sv[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) sv[q] = lane == 0 ? __ldcg(sums + q) : 0.f;   // obj, kl, clip, adv, ret | rows of this minibatch over all ranks | sum(logΣ)
+    double np[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) np[k] = lane + 32 * k < n_groups ? __ldcg(norm_part + lane + 32 * k) : 0.0;
     double t = 0.0;
-    for (int q = lane; q < n_groups; q += 32) t += __ldcg(norm_part + q);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += np[k];
+    for (int q = lane + 256; q < n_groups; q += 32) t += __ldcg(norm_part + q);
     t = warp_sum_d(t);
     if (lane == 0) {
-      beta_cache_store(norm_part + BETA_CACHE, state[0] + 1, 1.0 - s_c1, 1.0 - s_c2);
-      state[0] += 1; state[1] = 0; state[2] = 0;
-      if (peer.enabled) *(volatile unsigned long long *)a.ll_seq = pseq;   // every CTA has read the sequence number and all of its words: close the exchange
+      const int step = __ldcg(state) + 1;
+      double c1 = s_c1, c2 = s_c2;
+      int nan_seen = s_bad;
+      if (blockIdx.x >= n_groups) {   // (a last CTA that owned no group has not derived the β powers)
+        double p1, p2;
+        beta_pows(norm_part + BETA_CACHE, step, a.b1, a.b2, p1, p2);
+        c1 = 1.0 - p1; c2 = 1.0 - p2; nan_seen = __ldcg(state + 2);
+      }
+      beta_cache_store(norm_part + BETA_CACHE, step, 1.0 - c1, 1.0 - c2);
+      state[0] = step; state[1] = 0; state[2] = 0;
+      if (peer.enabled) *(volatile unsigned long long *)a.ll_seq = *(volatile const unsigned long long *)peer.seq_dev + 1ULL;   // every CTA has read the sequence number and all of its words: close the exchange
       const double n2 = t;
-      const float *sums = grads + n_params + 64;
-      const float cnt = __ldcg(sums + 5);   // rows of this minibatch over all ranks
+      const float cnt = sv[5];
       if (a.head == 0) {
-        const float entropy = 1.4189385332046727f + __ldcg(sums + 6);   // policies.jl:348, logΣ as the minibatch kernel saw it
-        const float p_loss = -(__ldcg(sums + 0) / cnt);
+        const float entropy = 1.4189385332046727f + sv[6];   // policies.jl:348, logΣ as the minibatch kernel saw it
+        const float p_loss = -(sv[0] / cnt);
         a.rec[CRUX_PPO_LOSS] = a.lambda_p * p_loss + a.lambda_e * (-entropy);
         a.rec[CRUX_PPO_ENTROPY] = entropy;
-        const float kl = __ldcg(sums + 1) / cnt;
+        const float kl = sv[1] / cnt;
         a.rec[CRUX_PPO_KL] = kl;
-        a.rec[CRUX_PPO_CLIP_FRAC] = a.a2c ? 0.f : __ldcg(sums + 2) / cnt;
-        a.rec[CRUX_PPO_AVG_ADV] = __ldcg(sums + 3) / cnt;
-        a.rec[CRUX_PPO_AVG_RET] = __ldcg(sums + 4) / cnt;
+        a.rec[CRUX_PPO_CLIP_FRAC] = a.a2c ? 0.f : sv[2] / cnt;
+        a.rec[CRUX_PPO_AVG_ADV] = sv[3] / cnt;
+        a.rec[CRUX_PPO_AVG_RET] = sv[4] / cnt;
         if (a.ctl && kl > a.target_kl) a.ctl[1] = a.mb + 1;         // this minibatch is still applied; later ones are skipped
       } else {
-        a.rec[CRUX_PPO_LOSS] = __ldcg(sums + 0) / cnt;
+        a.rec[CRUX_PPO_LOSS] = sv[0] / cnt;
       }
       a.rec[CRUX_PPO_GRAD_NORM] = (float)sqrt(n2);
       a.rec[CRUX_PPO_VALID] = 1.f;
-      if (bad || isnan(n2)) atomicOr(a.err_flags, CRUX_FLAG_NAN);   // training.jl:20: error before Flux.update!
-      if (a.trace) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); a.trace[1] = gt_; }
+      if (nan_seen || isnan(n2)) atomicOr(a.err_flags, CRUX_FLAG_NAN);   // training.jl:20: error before Flux.update!
+      TAIL_TRACE(1);
     }
   }
+#undef TAIL_TRACE
 }
 
 __global__ void fused_ctl_reset_kernel(int *ctl) { ctl[0] = 0; ctl[1] = 0; }
@@ -2085,15 +2158,21 @@ static int fused_minibatch(crux_gaussian *actor, crux_mlp *mlp, int head, const 
             s0 = s0 < a0 ? s0 : a0; s1 = s1 > a0 ? s1 : a0; e0 = e0 < a1 ? e0 : a1; e1 = e1 > a1 ? e1 : a1; }
           fprintf(stderr, "trace launch %3d ctas %3d: start %8.2f .. %8.2f  end %8.2f .. %8.2f us   tail %8.2f .. %8.2f\n", L, n, (s0 - t0) * 1e-3, (s1 - t0) * 1e-3, (e0 - t0) * 1e-3, (e1 - t0) * 1e-3,
                   (h[(L * 160 + 150) * 2] - t0) * 1e-3, (h[(L * 160 + 150) * 2 + 1] - t0) * 1e-3);
+          const unsigned long long *tt = &h[(L * 160 + 150) * 2];   // tail phases relative to the tail's start: prologue, reduce, Adam, ticket (CTA 0), last CTA's ticket, end
+          fprintf(stderr, "      tail phases (us from wait-return): prologue %.2f  reduce %.2f  adam %.2f  ticket %.2f | last CTA at %.2f  end %.2f\n", (tt[2] - tt[0]) * 1e-3,
+                  (tt[3] - tt[0]) * 1e-3, (tt[4] - tt[0]) * 1e-3, (tt[5] - tt[0]) * 1e-3, (tt[6] - tt[0]) * 1e-3, (tt[1] - tt[0]) * 1e-3);
+          fprintf(stderr, "      slice landed %.2f\n", (tt[7] - tt[0]) * 1e-3);
         }
       }
     }
     const bool tanh_act = mlp->acts[0] == CRUX_ACT_TANH;   // the activation is a compile-time parameter: branch-free epilogues
-    // Measured (scripts/mb6_trace.py): launched as a programmatic dependent of its network's previous tail kernel, the minibatch kernel
-    // takes over every SM as soon as one frees up and then idles at griddepcontrol.wait -- the OTHER network's minibatch kernel waits
-    // behind it (1.40 ms per iteration against 1.34).  Only the small tail kernels use the early launch; CRUX_PDL_MB=1 re-enables it here.
+    // Programmatic dependent launch of the MINIBATCH kernel behind its network's previous tail kernel is opt-in (CRUX_PDL_MB=1).  Measured
+    // (scripts/mb6_trace.py, bench.py): with the tail's trigger at its START the minibatch kernel took over every SM as soon as one freed
+    // up and idled at griddepcontrol.wait while the OTHER network's minibatch kernel waited behind it (1.40 ms per iteration against
+    // 1.34); with the trigger after the tail's Adam stores (where it is now) the prologue does overlap the tail's record keeping, but
+    // the step is no faster (1.163 against 1.156 ms): the SMs the early CTAs hold are the ones the other network's kernel would use.
     static const bool pdl_mb = getenv("CRUX_PDL_MB") != nullptr;
-    const bool pdl = pdl_enabled() && pdl_ok && pdl_mb;   // never for the first minibatch of an epoch: its row order comes from the kernel right before it
+    const bool pdl = pdl_enabled() && pdl_ok && pdl_mb;   // never for a network's first minibatch: the row orders come from the kernels right before it
     void (*kern)(MbArgs) = head == 0 ? (tanh_act ? mb6::minibatch_kernel<0, CRUX_ACT_TANH> : mb6::minibatch_kernel<0, CRUX_ACT_RELU>)
                                      : (tanh_act ? mb6::minibatch_kernel<1, CRUX_ACT_TANH> : mb6::minibatch_kernel<1, CRUX_ACT_RELU>);
     CRUX_CHECK_CUDA(ctx, launch_pdl(kern, dim3(grid), dim3(mb6::NTH), (size_t)mb6::Map::TOTAL, ctx->stream, pdl, a));
@@ -2298,7 +2377,7 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
     for (int64_t mbi = 0; mbi < nmb_a && total < maxb_a; ++mbi, ++total) {
       const int64_t off = mbi * hp->actor_batch, bm = i64min(hp->actor_batch, n - off);
       float *rec = actor->info_actor + ((int64_t)e * nmb_a + mbi) * CRUX_PPO_INFO_STRIDE;
-      rc = fused_minibatch(actor, mu, 0, s, a, logprob, advantage, ret, order + off, bm, hp, rec, actor->ctl, (int)total, mbi > 0);
+      rc = fused_minibatch(actor, mu, 0, s, a, logprob, advantage, ret, order + off, bm, hp, rec, actor->ctl, (int)total, total > 0);
       if (rc) return rc;
     }
   }
@@ -2327,7 +2406,7 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
     for (int64_t mbi = 0; mbi < nmb_c && total < maxb_c; ++mbi, ++total) {
       const int64_t off = mbi * hp->critic_batch, bm = i64min(hp->critic_batch, n - off);
       float *rec = actor->info_critic + ((int64_t)e * nmb_c + mbi) * CRUX_PPO_INFO_STRIDE;
-      rc = fused_minibatch(actor, critic, 1, s, nullptr, nullptr, nullptr, ret, order + off, bm, hp, rec, nullptr, (int)total, mbi > 0);
+      rc = fused_minibatch(actor, critic, 1, s, nullptr, nullptr, nullptr, ret, order + off, bm, hp, rec, nullptr, (int)total, total > 0);
       if (rc) { ctx->stream = main_stream; return rc; }
     }
   }
