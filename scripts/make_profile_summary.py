@@ -61,6 +61,7 @@ for name, title in (("r2_prof_minibatch", "mb6::minibatch_kernel<0> (actor; domi
                     ("prof_gae", "gae_returns_kernel at [2048, 16384] (738 MB): register-resident scan (narrow / short rollouts; CRUX_GAE=scan)"),
                     ("prof_fwd_tc5", "tc5::forward_kernel_tmem: value(V, s) over 131072 rows on tcgen05, activations resident in tensor memory"),
                     ("prof_mb5", "mb5::minibatch_kernel (opt-in CRUX_MB_TC5=1): PPO minibatch with the row GEMMs on tcgen05 / TMEM"),
+                    ("r2_prof_tail", "reduce_adam_kernel: the single-launch update tail (partials -> gradient -> [LL exchange] -> Adam -> planes -> record), 187 CTAs of 128 threads"),
                     ("r2_prof_rollout", "rollout_linquad_kernel (r2 capture)"), ("prof_rollout", "rollout_linquad_kernel: T = 32 vector steps of 4096 env streams in one persistent launch"),
                     ("prof_persist", "mbp::epoch_kernel (persistent 8-CTA cluster kernel, 256 minibatches of 128 rows in one launch)"),
                     ("prof_forward", "fused_forward_kernel")):
