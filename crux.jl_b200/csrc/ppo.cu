@@ -185,10 +185,26 @@ __global__ void ppo_record_kernel(const float *__restrict__ sums, float *__restr
 //   smooth_Δ, smooth_Jc: EMA with the Float64 α rounded to the Float32 state; ∂ = max(0, smooth_Jc - Jc_prev);
 //   penalty = clamp(Kp smooth_Δ + I + Kd ∂, 0, penalty_max).   state = {I, smooth_Δ, smooth_Jc, Jc_prev}, one block.
 struct LagrangePid { float target_cost, penalty_max, Ki_max, Ki, Kp, Kd; double ema_alpha; };
+// the PID step itself (rl/ppo.jl:79-106) from the minibatch sums c = sum(cost), e = sum(episode_end): one thread
+__device__ __forceinline__ void lagrange_pid_step(float c, float e, const LagrangePid &h, float *__restrict__ state, float *__restrict__ penalty,
+                                                  float *__restrict__ lrec) {
+  const float Jc = c / e;
+  const float d = Jc - h.target_cost;
+  const float I = fminf(fmaxf(state[0] + h.Ki * d, 0.f), h.Ki_max);
+  const float sd = (float)(h.ema_alpha * (double)state[1] + (1.0 - h.ema_alpha) * (double)d);
+  const float sj = (float)(h.ema_alpha * (double)state[2] + (1.0 - h.ema_alpha) * (double)Jc);
+  const float der = fmaxf(0.f, sj - state[3]);
+  state[0] = I; state[1] = sd; state[2] = sj; state[3] = sj;
+  const float pen = fminf(fmaxf(h.Kp * sd + I + h.Kd * der, 0.f), h.penalty_max);
+  penalty[0] = pen;
+  lrec[0] = pen; lrec[1] = Jc; lrec[2] = h.Kp * sd; lrec[3] = der; lrec[4] = I; lrec[7] = 1.f;
+}
+// One rank: sums and PID step in one launch.  Several ranks (sums_out != NULL): this rank's sums are written out, all-reduced like the
+// gradient, and lagrange_pid_apply_kernel runs the identical PID step on every rank -- the cost estimate is that of the UNION minibatch.
 __global__ void lagrange_pid_kernel(const float *__restrict__ cost, const uint8_t *__restrict__ episode_end, const int32_t *__restrict__ idx,
                                     int64_t bm, LagrangePid h, float *__restrict__ state, float *__restrict__ penalty,
-                                    float *__restrict__ lrec, const int *__restrict__ skip) {
-  if (skip && *skip) return;
+                                    float *__restrict__ lrec, const int *__restrict__ skip, float *__restrict__ sums_out) {
+  if (skip && *skip) { if (sums_out && threadIdx.x < 2) sums_out[threadIdx.x] = 0.f; return; }
   __shared__ double sh[2][32];
   double c = 0.0, e = 0.0;
   for (int64_t i = threadIdx.x; i < bm; i += blockDim.x) { const int64_t r = idx[i]; c += (double)cost[r]; e += (double)episode_end[r]; }
@@ -198,17 +214,14 @@ __global__ void lagrange_pid_kernel(const float *__restrict__ cost, const uint8_
   if (threadIdx.x == 0) {
     c = 0.0; e = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { c += sh[0][w]; e += sh[1][w]; }
-    const float Jc = (float)c / (float)e;
-    const float d = Jc - h.target_cost;
-    const float I = fminf(fmaxf(state[0] + h.Ki * d, 0.f), h.Ki_max);
-    const float sd = (float)(h.ema_alpha * (double)state[1] + (1.0 - h.ema_alpha) * (double)d);
-    const float sj = (float)(h.ema_alpha * (double)state[2] + (1.0 - h.ema_alpha) * (double)Jc);
-    const float der = fmaxf(0.f, sj - state[3]);
-    state[0] = I; state[1] = sd; state[2] = sj; state[3] = sj;
-    const float pen = fminf(fmaxf(h.Kp * sd + I + h.Kd * der, 0.f), h.penalty_max);
-    penalty[0] = pen;
-    lrec[0] = pen; lrec[1] = Jc; lrec[2] = h.Kp * sd; lrec[3] = der; lrec[4] = I; lrec[7] = 1.f;
+    if (sums_out) { sums_out[0] = (float)c; sums_out[1] = (float)e; }
+    else lagrange_pid_step((float)c, (float)e, h, state, penalty, lrec);
   }
+}
+__global__ void lagrange_pid_apply_kernel(const float *__restrict__ sums, LagrangePid h, float *__restrict__ state, float *__restrict__ penalty,
+                                          float *__restrict__ lrec, const int *__restrict__ skip) {
+  if (skip && *skip) return;
+  lagrange_pid_step(sums[0], sums[1], h, state, penalty, lrec);
 }
 
 // critic: mse head, dz = 2 (V - R) / Bg, block partial sums of squared error
@@ -283,6 +296,7 @@ struct LagrangeArgs {
   int cost_epochs; int64_t cost_batch, cost_max_batches;
   const int32_t *order_cost;
   float *info_l, *info_cost;    // device records, CRUX_PPO_INFO_STRIDE floats per minibatch
+  float *sums;                  // device float[4] (16-byte aligned): this minibatch's {sum(cost), sum(episode_end)} for the all-reduce over ranks
 };
 
 // batch_train!(V, opt, 𝒫, 𝒟) with Flux.mse(value(V, s), target) (ppo.jl:60, :208): the critic and the cost critic
@@ -415,9 +429,15 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
         gather_cols_kernel<<<gg, 256, 0, ctx->stream>>>(g, order + off, bm, skip);
         CRUX_LAUNCHED(ctx);
         if (lg) {   // the PID step of the loss evaluation (rl/ppo.jl:79-106) on this minibatch's rows
-          lagrange_pid_kernel<<<1, 1024, 0, ctx->stream>>>(lg->cost, lg->episode_end, order + off, bm, lg->pid, lg->state, lg->state + 4,
-                                                         lg->info_l + ((int64_t)e * nmb_a + mbi) * CRUX_PPO_INFO_STRIDE, skip);
+          float *lrec = lg->info_l + ((int64_t)e * nmb_a + mbi) * CRUX_PPO_INFO_STRIDE;
+          lagrange_pid_kernel<<<1, 1024, 0, ctx->stream>>>(lg->cost, lg->episode_end, order + off, bm, lg->pid, lg->state, lg->state + 4, lrec, skip,
+                                                         ctx->world > 1 ? lg->sums : nullptr);
           CRUX_LAUNCHED(ctx);
+          if (ctx->world > 1) {
+            rc = grads_allreduce(ctx, lg->sums, 4); if (rc) return rc;
+            lagrange_pid_apply_kernel<<<1, 1, 0, ctx->stream>>>(lg->sums, lg->pid, lg->state, lg->state + 4, lrec, skip);
+            CRUX_LAUNCHED(ctx);
+          }
         }
         rc = mlp_forward_keep(mu, mb_s, bm, skip); if (rc) return rc;
         const int hb = (int)cdiv(bm, 128);
@@ -482,7 +502,6 @@ int32_t crux_lagrange_ppo_update(crux_gaussian *actor, crux_mlp *critic, crux_ml
   crux_ctx *ctx = actor->ctx;
   CRUX_REQUIRE(ctx, hp && lhp && cost && cost_advantage && episode_end && pid_state_dev && n >= 1, "crux_lagrange_ppo_update: NULL argument");
   CRUX_REQUIRE(ctx, !hp->a2c, "crux_lagrange_ppo_update: the Lagrange loss extends ppo_loss");
-  CRUX_REQUIRE(ctx, ctx->world == 1, "crux_lagrange_ppo_update: the PID cost estimate is not all-reduced (single rank only)");
   const int64_t nmb_a = cdiv(n, hp->actor_batch);
   const bool train_cost = cost_critic && lhp->cost_epochs > 0;
   if (train_cost) {
@@ -493,16 +512,16 @@ int32_t crux_lagrange_ppo_update(crux_gaussian *actor, crux_mlp *critic, crux_ml
   const int64_t nmb_k = train_cost ? cdiv(n, lhp->cost_batch) : 0;
   const size_t il = (size_t)i64max(1, hp->actor_epochs * nmb_a) * CRUX_PPO_INFO_STRIDE * sizeof(float);
   const size_t ik = (size_t)i64max(1, (int64_t)lhp->cost_epochs * nmb_k) * CRUX_PPO_INFO_STRIDE * sizeof(float);
-  float *info = (float *)crux_scratch(ctx, 5, il + ik);
+  float *info = (float *)crux_scratch(ctx, 5, il + ik + 64);
   if (!info) return CRUX_ERR_OOM;
-  CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(info, 0, il + ik, ctx->stream));
+  CRUX_CHECK_CUDA(ctx, cudaMemsetAsync(info, 0, il + ik + 64, ctx->stream));
   LagrangeArgs lg;
   lg.cost_critic = cost_critic; lg.cost = cost; lg.cost_adv = cost_advantage; lg.cost_ret = cost_return; lg.episode_end = episode_end;
   lg.pid = LagrangePid{lhp->target_cost, lhp->penalty_max, lhp->Ki_max, lhp->Ki, lhp->Kp, lhp->Kd, lhp->ema_alpha};
   lg.state = pid_state_dev;
   lg.cost_epochs = train_cost ? lhp->cost_epochs : 0; lg.cost_batch = lhp->cost_batch; lg.cost_max_batches = lhp->cost_max_batches;
   lg.order_cost = order_cost;
-  lg.info_l = info; lg.info_cost = (float *)((char *)info + il);
+  lg.info_l = info; lg.info_cost = (float *)((char *)info + il); lg.sums = (float *)((char *)info + il + ik);
   int rc = ppo_update_impl(actor, critic, s, a, logprob, advantage, ret, n, hp, order_actor, order_critic, seed, &lg);
   if (rc) return rc;
   const int64_t nmb_c = (critic && hp->critic_epochs > 0) ? cdiv(n, hp->critic_batch) : 0;

@@ -1709,13 +1709,13 @@ __global__ void __launch_bounds__(RWT * 32, 9) reduce_adam_kernel(const float *_
     for (int q = 0; q < peer.world; ++q) *(volatile unsigned long long *)(peer.ll[q] + pbase + idx) = word;
     float sum = 0.f;
     const volatile unsigned long long *src = a.ll_recv + (int64_t)(pseq & 1u) * 16 * a.peer_cap + idx;
-    for (int base = 0; base < peer.world; base += 4) {   // 4 loads in flight, rank order kept
-      unsigned long long wd[4];
+    for (int base = 0; base < peer.world; base += 8) {   // the words of 8 ranks in flight at once, summed in rank order
+      unsigned long long wd[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 8; ++u)
         if (base + u < peer.world) wd[u] = src[(int64_t)(base + u) * a.peer_cap];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 8; ++u)
         if (base + u < peer.world) {
           while ((unsigned int)(wd[u] >> 32) != pseq) wd[u] = src[(int64_t)(base + u) * a.peer_cap];
           sum += __uint_as_float((unsigned int)wd[u]);
@@ -1802,16 +1802,14 @@ __global__ void __launch_bounds__(RWT * 32, 9) reduce_adam_kernel(const float *_
         for (int q = 0; q < RWT; ++q) t += sh[q][lane];
         float g = (float)t;
         if (p >= n_params && p < n_params + n_ls) g += ls_shift;   // d(λe e_loss)/dlogΣ = -λe, scaled by 1/world: the sum over ranks restores it
-        if (p < n_params + 8) {
-          g = exchange(p, g);
-          grads[p] = g;
-          if (p < n_params + n_ls) sq = (double)g * (double)g;
-        } else {
-          const int q = p - n_params - 8;   // obj, kl, clip, adv, ret | count | sum(logΣ) BEFORE this update (published by CTA 0 of the minibatch kernel)
-          if (q < 5) grads[n_params + 64 + q] = exchange(n_params + 64 + q, g);
-          else if (q == 5) grads[n_params + 64 + 5] = exchange(n_params + 64 + 5, count);
-          else if (q == 6) grads[n_params + 64 + 6] = g;   // identical on every rank: not exchanged
-        }
+        // entries < n_params + 8: gradient (+ dlogΣ); then obj, kl, clip, adv, ret | count | sum(logΣ) BEFORE this update (published by CTA 0 of
+        // the minibatch kernel; identical on every rank, not exchanged).  ONE exchange call site: the polling loop is inlined once.
+        const int q = p - n_params - 8;
+        const int slot = q < 0 ? p : n_params + 64 + q;
+        if (q == 5) g = count;
+        if (q < 6) g = exchange(slot, g);
+        if (q < 7) grads[slot] = g;
+        if (p < n_params + n_ls) sq = (double)g * (double)g;
         if (!bad && p < n_params + n_ls) {   // Flux Adam on this entry (float32 moments, Float64 scalars)
           float *ap, *am, *av;
           if (p < n_params) { ap = a.p + p; am = a.m + p; av = a.v + p; } else { const int j = p - n_params; ap = a.ls + j; am = a.ls_m + j; av = a.ls_v + j; }

@@ -254,7 +254,8 @@ int32_t crux_ppo_info_ptrs(crux_gaussian *actor, float **info_actor_dev, float *
  * pid_state_dev: device float[5] = {I, smooth_Δ, smooth_Jc, Jc_prev, penalty}, zero-initialised by the caller, persists
  * across updates (the reference keeps them in 𝒫).  Runs on the layer-by-layer engine (the fused kernels cover ppo/a2c/mse).
  * info_lagrange_host [actor minibatches][8] = penalty, cur_cost, prop_term, deriv_term, integral term, λp·p_loss, cost_loss, valid;
- * info_cost_host [cost minibatches][8] like info_critic_host.  Single rank only. */
+ * info_cost_host [cost minibatches][8] like info_critic_host.  Several ranks: sum(cost) and sum(episode_end) of the minibatch are summed
+ * over ranks before the PID step (the cost estimate of the UNION minibatch, identical state on every rank), gradients as in crux_ppo_update. */
 typedef struct crux_lagrange_hp {
   float target_cost;  /* 𝒫[:target_cost] ppo.jl:146 */
   float penalty_max;  /* Inf32 */

@@ -200,8 +200,89 @@ def main():
         if rank == 0:
             print(f"td3 update parity OK ({tag})")
 
+    # ---- data-parallel LagrangePPO: the PID cost estimate sum(cost)/sum(episode_end) is that of the UNION minibatch (summed over ranks in front
+    # of the PID step), the three networks' gradients are all-reduced like PPO's; parameters, PID state and the info records == the oracle's
+    def lagrange_check(tag):
+        rngl = np.random.default_rng(31)
+        mul = o.MLP([17, 64, 64, 6], [1, 1, 0], rngl); crl = o.MLP([17, 64, 64, 1], [1, 1, 0], rngl); vcl = o.MLP([17, 64, 64, 1], [1, 1, 0], rngl)
+        flat0 = [m.flat().copy() for m in (mul, crl, vcl)]
+        pil = o.GaussianPolicy(mul, ls.copy())
+        Dl = dict(D)
+        Dl["cost"] = (rngl.random(n) < 0.3).astype(F32) * rngl.random(n).astype(F32)
+        Dl["cost_advantage"] = rngl.standard_normal(n).astype(F32)
+        Dl["cost_return"] = rngl.standard_normal(n).astype(F32)
+        Dl["episode_end"] = rngl.random(n) < 0.1
+        ok_ = [[rngl.permutation(n_loc) for _ in range(epochs)] for _ in range(world)]
+        Pl = o.lagrange_params(eps=0.2, lp=1.0, le=0.1, target_cost=0.025, Ki=0.05, Kp=1, Kd=0.5)
+        recs = []
+
+        def union(orders, e, k):
+            idx = np.concatenate([r * n_loc + orders[r][e][k * ab:(k + 1) * ab] for r in range(world)])
+            return {kk: v[idx] for kk, v in Dl.items()}
+        opts = [o.Adam(F32(3e-4)) for _ in range(3)]
+        for e in range(epochs):
+            for k in range(n_loc // ab):
+                inf = {}
+                o.train_step(pil.params(), lambda i_, mb=union(orders_a, e, k): o.lagrange_ppo_loss(pil, Pl, mb, i_), opts[0], inf)
+                recs.append(inf)
+        for e in range(epochs):
+            for k in range(n_loc // ab):
+                o.train_step(crl.params(), lambda i_, mb=union(orders_c, e, k): o.value_mse_loss(crl, mb), opts[1], {})
+        for e in range(epochs):
+            for k in range(n_loc // ab):
+                o.train_step(vcl.params(), lambda i_, mb=union(ok_, e, k): o.value_mse_loss(vcl, dict(mb, **{"return": mb["cost_return"]})), opts[2], {})
+
+        def net(dims, acts, flat):
+            ws, off = [], 0
+            layers = []
+            for l in range(3):
+                nw = dims[l] * dims[l + 1]
+                W = flat[off:off + nw].reshape(dims[l], dims[l + 1]).T.copy(); off += nw      # flat holds Julia memory order [in][out]
+                b = flat[off:off + dims[l + 1]].copy(); off += dims[l + 1]
+                layers.append(crux.Dense(dims[l], dims[l + 1], acts[l], W, b))
+            return crux.ContinuousNetwork(crux.Chain(*layers), ctx=ctx)
+        am, cm, km = net(mul.dims, mul.acts, flat0[0]), net(crl.dims, crl.acts, flat0[1]), net(vcl.dims, vcl.acts, flat0[2])
+        assert np.array_equal(am.mlp.get_flat(), flat0[0]), "network construction order"
+        pol = crux.ActorCritic(crux.GaussianPolicy(am, ls.copy()), cm)
+        for m_ in (am, cm, km):
+            m_.mlp.set_adam(F32(3e-4))
+        sh = slice(rank * n_loc, (rank + 1) * n_loc)
+        d = {k: dev(v[sh].astype(np.uint8) if v.dtype == bool else v[sh]) for k, v in Dl.items()}
+        hp = crux._abi.PPOHp(eps_clip=0.2, lambda_p=1.0, lambda_e=0.1, target_kl=math.inf, a2c=0, actor_epochs=epochs, actor_batch=ab,
+                             critic_epochs=epochs, critic_batch=ab, actor_max_batches=0, critic_max_batches=0)
+        lhp = crux._abi.LagrangeHp(target_cost=0.025, penalty_max=math.inf, Ki_max=10.0, Ki=0.05, Kp=1.0, Kd=0.5, ema_alpha=0.95,
+                                   cost_epochs=epochs, cost_batch=ab, cost_max_batches=0)
+        oa = dev(np.stack(orders_a[rank]).astype(np.int32), torch.int32); oc = dev(np.stack(orders_c[rank]).astype(np.int32), torch.int32)
+        okd = dev(np.stack(ok_[rank]).astype(np.int32), torch.int32)
+        nm = epochs * (n_loc // ab)
+        ia, il, ic, ik = (np.zeros((nm, 8), F32) for _ in range(4))
+        state = dev(np.zeros(5, F32))
+        ctx.check(ctx.lib.crux_lagrange_ppo_update(pol.A.h, cm.mlp.h, km.mlp.h, ptr(d["s"]), ptr(d["a"]), ptr(d["logprob"]), ptr(d["advantage"]), ptr(d["return"]),
+                                                   ptr(d["cost"]), ptr(d["cost_advantage"]), ptr(d["cost_return"]), ptr(d["episode_end"]), n_loc, C.byref(hp),
+                                                   C.byref(lhp), ptr(state), ptr(oa), ptr(oc), ptr(okd), 0, ptr(ia), ptr(ic), ptr(il), ptr(ik)))
+        assert any(r_["penalty"] > 0 for r_ in recs), "the check must exercise a non-zero penalty"
+        for k, r_ in enumerate(recs):
+            want = np.array([r_["penalty"], r_["cur_cost"], r_["prop_term"], r_["deriv_term"], r_["integral term"], r_["p_loss"], r_["cost_loss"]], F32)
+            assert il[k, 7] == 1.0 and np.allclose(il[k, :7], want, rtol=3e-4, atol=3e-6), f"{tag}: lagrange record {k}: {il[k, :7]} vs {want}"
+        st = state.cpu().numpy()
+        want_st = np.array([Pl["I"], Pl["smooth_D"], Pl["smooth_Jc"], Pl["Jc_prev"], recs[-1]["penalty"]], F32)
+        assert np.allclose(st, want_st, rtol=3e-4, atol=3e-6), f"{tag}: PID state {st} vs {want_st}"
+        for name, got, want in (("actor", am.mlp.get_flat(), mul.flat()), ("critic", cm.mlp.get_flat(), crl.flat()), ("cost critic", km.mlp.get_flat(), vcl.flat())):
+            err = np.abs(got - want)
+            assert err.max() < 2 * 3e-4 * 8 + 2e-6, f"{tag} {name}: {err.max()}"
+            assert (err > 2e-6 + 1e-5 * np.abs(want)).mean() < 5e-3, f"{tag} {name}: {(err > 2e-6 + 1e-5 * np.abs(want)).sum()} coordinates off"
+            t_ = dev(got); gl_ = [torch.empty_like(t_) for _ in range(world)]
+            dist.all_gather(gl_, t_)
+            assert all(torch.equal(gl_[0], g) for g in gl_), f"{tag} {name}: replicas diverged"
+        gs = [torch.empty_like(state) for _ in range(world)]
+        dist.all_gather(gs, state)
+        assert all(torch.equal(gs[0], g) for g in gs), f"{tag}: PID state differs between ranks"
+        if rank == 0:
+            print(f"lagrange ppo update parity OK ({tag})")
+
     sac_check("nccl all-reduce")
     ddpg_check("nccl all-reduce")
+    lagrange_check("nccl all-reduce")
 
     # ---- global whitening: every rank whitens its shard with the all-reduced moments
     x = np.random.default_rng(5).standard_normal(4000).astype(F32) * 3 + 1
@@ -225,6 +306,7 @@ def main():
     ppo_check("one-shot peer all-reduce between reduce and Adam")
     os.environ.pop("CRUX_NO_PEER_LL")
     ppo_check("fused LL peer exchange, 3rd")
+    lagrange_check("one-shot peer all-reduce")
     allreduce_check("peer after ppo", 5)
     # timing of the two paths for the 44 KB gradient payload
     for tag in ("peer",):
