@@ -96,6 +96,7 @@ _SIGS = {
     "crux_mlp_train_mse": [_vp, _vp, _vp, _i64, _vp],
     "crux_gaussian_create": [_vp, _vp, _i32, _vp, _i32, _f32, _pp],
     "crux_gaussian_destroy": [_vp],
+    "crux_categorical_create": [_vp, _vp, _i32, _pp],
     "crux_gaussian_log_sigma_ptr": [_vp, _pp],
     "crux_gaussian_explore": [_vp, _vp, _i64, _vp, _u64, _u64, _vp, _vp],
     "crux_gaussian_action": [_vp, _vp, _i64, _vp],

@@ -177,6 +177,23 @@ int32_t crux_gaussian_create(crux_ctx *ctx, crux_mlp *mu, int32_t adim, const fl
   return CRUX_OK;
 }
 
+// DiscreteNetwork actor (policies.jl:104-157) for the on-policy updates: ppo_loss / a2c_loss / reinforce_loss are generic over the policy
+// through logpdf (categorical_logpdf :135: log(sum(softmax(net(s)) .* a_onehot))) and entropy (:152-155: -sum(p log(p + eps(Float32)))).
+int32_t crux_categorical_create(crux_ctx *ctx, crux_mlp *logits, int32_t n_actions, crux_gaussian **out) {
+  if (!ctx) return CRUX_ERR_INVALID;
+  CRUX_REQUIRE(ctx, logits && out, "crux_categorical_create: NULL argument");
+  CRUX_REQUIRE(ctx, n_actions >= 2 && n_actions <= CRUX_MAX_ADIM, "crux_categorical_create: 2..64 actions");
+  CRUX_REQUIRE(ctx, logits->dims[logits->n_layers] == n_actions, "crux_categorical_create: network output width != number of actions");
+  crux_gaussian *p = new crux_gaussian();
+  p->ctx = ctx; p->mu = logits; p->adim = n_actions; p->categorical = true;
+  if (cudaMalloc((void **)&p->ctl, 4 * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&p->partials, 4096 * sizeof(double)) != cudaSuccess) {
+    delete p; return crux_set_err(ctx, CRUX_ERR_OOM, "crux_categorical_create: cudaMalloc");
+  }
+  cudaMemsetAsync(p->ctl, 0, 4 * sizeof(int), ctx->stream);
+  *out = p;
+  return CRUX_OK;
+}
+
 int32_t crux_gaussian_destroy(crux_gaussian *p) {
   if (!p) return CRUX_OK;
   cudaStreamSynchronize(p->ctx->stream);
@@ -201,6 +218,7 @@ int32_t crux_gaussian_log_sigma_ptr(crux_gaussian *p, float **dev_out) {
 static int gaussian_head(crux_gaussian *p, const float *s, int64_t B, int mode, const float *eps_in, const float *a_in,
                          uint64_t seed, uint64_t ctr, float *a_out, float *logp_out) {
   crux_ctx *ctx = p->ctx;
+  CRUX_REQUIRE(ctx, !p->categorical, "gaussian: the handle is a categorical (DiscreteNetwork) actor: use the crux_discrete_* entry points");
   CRUX_REQUIRE(ctx, B >= 0, "gaussian: negative batch");
   if (B == 0) return CRUX_OK;
   CRUX_REQUIRE(ctx, s, "gaussian: NULL states");

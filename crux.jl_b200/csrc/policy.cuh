@@ -12,6 +12,8 @@ struct crux_gaussian {
   bool squashed = false;
   float ascale = 1.0f;
   bool head_mode = false;       // mu has 2*adim outputs: [mu | log_sigma]
+  bool categorical = false;     // crux_categorical_create: `mu` is the logits network of a DiscreteNetwork actor, adim = number of actions
+                                // (accepted by the on-policy updates only: a = one-hot rows, logprob = categorical_logpdf)
   // state-independent log-sigma (ConstantLayer): parameter, gradient (aliases mu->grads tail), Adam moments
   float *log_sigma = nullptr;
   float *ls_m = nullptr, *ls_v = nullptr;

@@ -134,6 +134,69 @@ ppo_head_kernel(const float *__restrict__ mu, const float *__restrict__ a, const
   }
 }
 
+// The same losses for a DiscreteNetwork actor (policies.jl:104-157): p = softmax(net(s)) (logits, :110,133), logpdf = categorical_logpdf
+// (:135: log(sum(p .* a_onehot))), entropy = -sum(p .* log.(p .+ eps(Float32))) per sample (:152-155), e_loss = -mean(entropy).
+// One thread per sample; writes dL/dz for the nA network outputs.  part[b][7] = sum of the per-sample entropies.
+__global__ void __launch_bounds__(128)
+ppo_head_cat_kernel(const float *__restrict__ z, const float *__restrict__ a, const float *__restrict__ old_logp,
+                    const float *__restrict__ adv, const float *__restrict__ ret, int nA, int64_t bm, float inv_bg, float eps_clip,
+                    float lambda_p, float lambda_e, int a2c, float *__restrict__ dz, double *__restrict__ part, const int *__restrict__ skip) {
+  if (skip && *skip) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float s_obj = 0.f, s_kl = 0.f, s_clip = 0.f, s_adv = 0.f, s_ret = 0.f, s_ent = 0.f;
+  if (i < bm) {
+    const float *zi = z + i * nA, *ai = a + i * nA;
+    float m = zi[0];
+    for (int j = 1; j < nA; ++j) m = fmaxf(m, zi[j]);
+    float S = 0.f;
+    for (int j = 0; j < nA; ++j) S += expf(zi[j] - m);
+    float q = 0.f, H = 0.f, gp = 0.f;   // q = sum(p a); gp = sum_i g_i p_i with g_i = dH/dp_i
+    for (int j = 0; j < nA; ++j) {
+      const float p = expf(zi[j] - m) / S;
+      const float lg = logf(p + 1.1920929e-07f);
+      q += p * ai[j];
+      H -= p * lg;
+      gp += -(lg + p / (p + 1.1920929e-07f)) * p;
+    }
+    const float logp = logf(q);
+    const float Ai = adv[i], old = old_logp[i];
+    float dlogp;
+    if (a2c) {
+      s_obj = logp * Ai;
+      dlogp = -lambda_p * inv_bg * Ai;
+    } else {
+      const float r = expf(logp - old);
+      const float lo = 1.f - eps_clip, hi = 1.f + eps_clip;
+      const float x = r * Ai, y = fminf(fmaxf(r, lo), hi) * Ai;
+      const bool first = !(y < x);  // min(x, y) keeps x on ties (Base.min)
+      s_obj = first ? x : y;
+      dlogp = first ? -lambda_p * inv_bg * x : 0.f;
+      s_clip = (r > hi || r < lo) ? 1.f : 0.f;
+    }
+    s_kl = old - logp; s_adv = Ai; s_ret = ret ? ret[i] : 0.f; s_ent = H;
+    const float de = -lambda_e * inv_bg;   // d(λe e_loss)/dH_i
+    for (int k = 0; k < nA; ++k) {
+      const float p = expf(zi[k] - m) / S;
+      const float g = -(logf(p + 1.1920929e-07f) + p / (p + 1.1920929e-07f));
+      dz[i * nA + k] = dlogp * p * (ai[k] - q) / q + de * p * (g - gp);
+    }
+  }
+  __shared__ double sh[4][8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double v;
+  v = warp_sum_d((double)s_obj); if (lane == 0) sh[w][0] = v;
+  v = warp_sum_d((double)s_kl); if (lane == 0) sh[w][1] = v;
+  v = warp_sum_d((double)s_clip); if (lane == 0) sh[w][2] = v;
+  v = warp_sum_d((double)s_adv); if (lane == 0) sh[w][3] = v;
+  v = warp_sum_d((double)s_ret); if (lane == 0) sh[w][4] = v;
+  v = warp_sum_d((double)s_ent); if (lane == 0) sh[w][7] = v;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int k = threadIdx.x;
+    part[(int64_t)blockIdx.x * HEAD_STRIDE + k] = (k == 5 || k == 6) ? 0.0 : sh[0][k] + sh[1][k] + sh[2][k] + sh[3][k];
+  }
+}
+
 // one block: reduce head partials -> gradient tail (logΣ gradient, sums).  sums: [obj, kl, clip, adv, ret, count]
 __global__ void ppo_finalize_kernel(const double *__restrict__ part, int nblocks, int A, int64_t bm, float lambda_e,
                                     float *__restrict__ ls_grad, float *__restrict__ sums, const int *__restrict__ skip) {
@@ -142,7 +205,7 @@ __global__ void ppo_finalize_kernel(const double *__restrict__ part, int nblocks
   if (k >= 8 + A) return;
   double s = 0.0;
   for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * HEAD_STRIDE + k];
-  if (k < 5 || k == 6) sums[k] = (float)s;
+  if (k < 5 || k == 6 || k == 7) sums[k] = (float)s;   // [7]: sum of per-sample entropies (categorical actor; 0 otherwise)
   else if (k == 5) sums[5] = (float)bm;
   else if (k >= 8) ls_grad[k - 8] = (float)s;  // entropy term added after the all-reduce (record kernel)
   (void)lambda_e;
@@ -152,12 +215,12 @@ __global__ void ppo_finalize_kernel(const double *__restrict__ part, int nblocks
 __global__ void ppo_record_kernel(const float *__restrict__ sums, float *__restrict__ ls_grad, const float *__restrict__ ls,
                                   int A, float lambda_p, float lambda_e, float target_kl, int a2c, int world,
                                   float *__restrict__ rec, int *__restrict__ ctl, const float *__restrict__ penalty,
-                                  float *__restrict__ lrec) {
+                                  float *__restrict__ lrec, int categorical) {
   if (ctl[0]) return;
   const float cnt = sums[5];
   float sls = 0.f;
   for (int j = 0; j < A; ++j) sls += ls[j];
-  const float entropy = ENT_CONST + sls;     // policies.jl:348
+  const float entropy = categorical ? sums[7] / cnt : ENT_CONST + sls;     // policies.jl:152-155 (mean over the minibatch) / :348
   const float p_loss = -(sums[0] / cnt);
   const float e_loss = -entropy;
   if (penalty) {                             // lagrange_ppo_loss rl/ppo.jl:108-131
@@ -353,7 +416,9 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
   CRUX_REQUIRE(ctx, hp, "crux_ppo_update: NULL hyper-parameters");
   CRUX_REQUIRE(ctx, n >= 1, "crux_ppo_update: empty buffer");
   CRUX_REQUIRE(ctx, s && a && logprob && advantage, "crux_ppo_update: NULL column");
-  CRUX_REQUIRE(ctx, !actor->head_mode && !actor->squashed, "crux_ppo_update: needs GaussianPolicy with a logΣ vector (ppo.jl examples)");
+  CRUX_REQUIRE(ctx, !actor->head_mode && !actor->squashed, "crux_ppo_update: needs GaussianPolicy with a logΣ vector (ppo.jl examples) or a categorical actor");
+  const bool cat = actor->categorical;   // DiscreteNetwork actor: a = one-hot rows [n][nA], logprob = categorical_logpdf
+  CRUX_REQUIRE(ctx, !(cat && lg), "crux_lagrange_ppo_update: Gaussian actors only");
   CRUX_REQUIRE(ctx, hp->actor_batch >= 1 && hp->actor_epochs >= 0, "crux_ppo_update: bad actor batch/epochs");
   CRUX_REQUIRE(ctx, n < (1ll << 31), "crux_ppo_update: n must fit int32 indices");
   crux_mlp *mu = actor->mu;
@@ -444,21 +509,25 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
         // head partials live in scratch slot 4 (hb blocks x HEAD_STRIDE doubles)
         double *part = (double *)crux_scratch(ctx, 4, (size_t)hb * HEAD_STRIDE * sizeof(double));
         if (!part) return CRUX_ERR_OOM;
+        if (cat)
+          ppo_head_cat_kernel<<<hb, 128, 0, ctx->stream>>>(mu->act[L], mb_a, mb_lp, mb_adv, ret ? mb_ret : nullptr, A, bm, inv_bg, hp->eps_clip,
+                                                           hp->lambda_p, hp->lambda_e, hp->a2c, mu->dz[L], part, skip);
+        else
         ppo_head_kernel<<<hb, 128, 0, ctx->stream>>>(mu->act[L], mb_a, mb_lp, mb_adv, ret ? mb_ret : nullptr, actor->log_sigma, A, bm,
                                                      inv_bg, hp->eps_clip, hp->lambda_p, hp->a2c, mu->dz[L], part, skip,
                                                      lg ? mb_cadv : nullptr, lg ? lg->state + 4 : nullptr);
         CRUX_LAUNCHED(ctx);
-        ppo_finalize_kernel<<<1, 128, 0, ctx->stream>>>(part, hb, A, bm, hp->lambda_e, tail_ls_grad(mu), tail_sums(mu), skip);
+        ppo_finalize_kernel<<<1, 128, 0, ctx->stream>>>(part, hb, cat ? 0 : A, bm, hp->lambda_e, tail_ls_grad(mu), tail_sums(mu), skip);
         CRUX_LAUNCHED(ctx);
         rc = mlp_backward(mu, mb_s, bm, mu->dz[L], false, false, true, skip); if (rc) return rc;
       }
       if (ctx->world > 1) { rc = grads_allreduce(ctx, mu->grads, mu->n_params + CRUX_GRAD_TAIL); if (rc) return rc; }
-      ppo_record_kernel<<<1, 1, 0, ctx->stream>>>(tail_sums(mu), tail_ls_grad(mu), actor->log_sigma, A, hp->lambda_p, hp->lambda_e,
+      ppo_record_kernel<<<1, 1, 0, ctx->stream>>>(tail_sums(mu), tail_ls_grad(mu), actor->log_sigma, cat ? 0 : A, hp->lambda_p, hp->lambda_e,
                                                   hp->target_kl, hp->a2c, ctx->world, rec, actor->ctl, lg ? lg->state + 4 : nullptr,
-                                                  lg ? lg->info_l + ((int64_t)e * nmb_a + mbi) * CRUX_PPO_INFO_STRIDE : nullptr);
+                                                  lg ? lg->info_l + ((int64_t)e * nmb_a + mbi) * CRUX_PPO_INFO_STRIDE : nullptr, cat ? 1 : 0);
       CRUX_LAUNCHED(ctx);
       AdamSegs segs;
-      segs.n = 2;
+      segs.n = cat ? 1 : 2;   // a categorical actor has no logΣ vector
       segs.s[0] = AdamSeg{mu->params, mu->grads, mu->m, mu->v, mu->n_params};
       segs.s[1] = AdamSeg{actor->log_sigma, tail_ls_grad(mu), actor->ls_m, actor->ls_v, (int64_t)A};
       rc = adam_step_segments(ctx, segs, mu->eta, mu->beta1, mu->beta2, mu->eps, mu->step_dev, rec + CRUX_PPO_GRAD_NORM, skip,

@@ -2010,7 +2010,7 @@ int mlp_value_next_fused(crux_mlp *mlp, const float *sp, const float *s, const f
 }
 
 bool fused_rows_supported(const crux_gaussian *actor) {
-  return !getenv("CRUX_NO_FUSED") && fusable(actor->mu) && !actor->head_mode && !actor->squashed && actor->adim == actor->mu->dims[3];
+  return !getenv("CRUX_NO_FUSED") && !actor->categorical && fusable(actor->mu) && !actor->head_mode && !actor->squashed && actor->adim == actor->mu->dims[3];
 }
 
 extern "C" int32_t crux_rollout_step_fused(crux_gaussian *actor, crux_mlp *critic, const float *obs, int64_t N, const float *eps_in,
@@ -2018,7 +2018,7 @@ extern "C" int32_t crux_rollout_step_fused(crux_gaussian *actor, crux_mlp *criti
                                            int64_t row0) {
   *handled = 0;
   if (getenv("CRUX_NO_FUSED")) return CRUX_OK;
-  if (!fusable(actor->mu) || actor->head_mode || actor->squashed || actor->adim != actor->mu->dims[3]) return CRUX_OK;
+  if (actor->categorical || !fusable(actor->mu) || actor->head_mode || actor->squashed || actor->adim != actor->mu->dims[3]) return CRUX_OK;
   const bool with_critic = critic && v_out;
   if (with_critic && (!fusable(critic) || critic->dims[3] != 1 || critic->dims[0] != actor->mu->dims[0])) return CRUX_OK;
   crux_ctx *ctx = actor->ctx;
@@ -2318,7 +2318,7 @@ int ppo_update_fused(crux_gaussian *actor, crux_mlp *critic, const float *s, con
                      uint64_t seed, int *handled) {
   *handled = 0;
   crux_mlp *mu = actor->mu;
-  if (getenv("CRUX_NO_FUSED") || !fusable(mu) || actor->head_mode || actor->squashed || actor->adim != mu->dims[3]) return CRUX_OK;
+  if (getenv("CRUX_NO_FUSED") || actor->categorical || !fusable(mu) || actor->head_mode || actor->squashed || actor->adim != mu->dims[3]) return CRUX_OK;
   if (critic && (!fusable(critic) || critic->dims[3] != 1)) return CRUX_OK;
   crux_ctx *ctx = actor->ctx;
   int rc = set_smem_attr(ctx); if (rc) return rc;

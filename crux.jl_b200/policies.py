@@ -305,6 +305,27 @@ class DiscreteNetwork(NetworkPolicy):
         self.temperature = float(np.float32(temperature))
         self.device = self.ctx.device
         assert network.layers[-1].out == len(self.outputs)
+        self._cat_h = None
+
+    @property
+    def h(self):
+        """Handle of this network as a categorical ACTOR (on-policy updates: ppo_loss / a2c_loss / reinforce_loss through
+        categorical_logpdf and entropy, policies.jl:135,152-155), created on first use."""
+        if self._cat_h is None:
+            assert isinstance(self.mlp, _MLP), "a categorical actor needs a Chain(Dense...) network"
+            assert self.temperature == 1.0, "the on-policy categorical head implements the default logit_conversion softmax(value(π, s))"
+            h = C.c_void_p()
+            self.ctx.check(self.ctx.lib.crux_categorical_create(self.ctx.h, self.mlp.h, len(self.outputs), C.byref(h)))
+            self._cat_h = h
+        return self._cat_h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_cat_h", None) is not None:
+                self.ctx.lib.crux_gaussian_destroy(self._cat_h)
+                self._cat_h = None
+        except Exception:
+            pass
 
 
 class DoubleNetwork(NetworkPolicy):

@@ -87,12 +87,13 @@ class OnPolicySolver:
             _set_adam(Vc.mlp, cost_opt.optimizer)
             self._pid_state = pi.ctx.zeros((5,))  # I, smooth_Δ, smooth_Jc, Jc_prev, penalty (the 1-element arrays of 𝒫, ppo.jl:190-201)
         A = pi.A if isinstance(pi, ActorCritic) else pi
-        assert isinstance(A, GaussianPolicy) and not A.squashed, \
-            "the fused on-policy update supports GaussianPolicy(μ, logΣ vector) actors (rl/ppo.jl, rl/reinforce.jl examples)"
+        assert (isinstance(A, GaussianPolicy) and not A.squashed) or isinstance(A, DiscreteNetwork), \
+            "the on-policy update supports GaussianPolicy(μ, logΣ vector) and DiscreteNetwork (categorical) actors (rl/ppo.jl, examples/rl/cartpole.jl)"
         assert c_opt is None or (isinstance(pi, ActorCritic) and isinstance(pi.C, ContinuousNetwork)), \
-            "a critic optimiser needs ActorCritic(GaussianPolicy, ContinuousNetwork)"
+            "a critic optimiser needs ActorCritic(actor, ContinuousNetwork)"
+        assert Vc is None or isinstance(A, GaussianPolicy), "LagrangePPO: Gaussian actors"
         self._actor = A
-        _set_adam(A.mu.mlp, a_opt.optimizer)
+        _set_adam(A.mu.mlp if isinstance(A, GaussianPolicy) else A.mlp, a_opt.optimizer)
         if c_opt is not None:
             _set_adam(pi.C.mlp, c_opt.optimizer)
         self.buffer = None

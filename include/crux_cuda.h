@@ -126,6 +126,12 @@ int32_t crux_mlp_train_mse(crux_mlp *mlp, const float *x, const float *y, int64_
 int32_t crux_gaussian_create(crux_ctx *ctx, crux_mlp *mu, int32_t adim, const float *log_sigma_host,
                              int32_t squashed, float ascale, crux_gaussian **out);
 int32_t crux_gaussian_destroy(crux_gaussian *pol);
+/* A DiscreteNetwork ACTOR (policies.jl:104-157) for the on-policy updates: ppo_loss / a2c_loss / reinforce_loss (rl/ppo.jl:4-21, a2c.jl:4-16,
+ * reinforce.jl:4-13) are generic over the policy through logpdf = categorical_logpdf (:135: log(sum(softmax(net(s)) .* a_onehot))) and
+ * entropy (:152-155: -sum(p .* log.(p .+ eps(Float32))), e_loss = -mean over the minibatch) -- the reference's cartpole PPO / A2C / REINFORCE
+ * examples (examples/rl/cartpole.jl:8-9).  The handle is accepted by crux_ppo_update / crux_ppo_update_async only (a = one-hot rows [n][n_actions],
+ * logprob as written by crux_discrete_explore); the crux_gaussian_* / rollout entry points reject it.  Destroy with crux_gaussian_destroy. */
+int32_t crux_categorical_create(crux_ctx *ctx, crux_mlp *logits, int32_t n_actions, crux_gaussian **out);
 int32_t crux_gaussian_log_sigma_ptr(crux_gaussian *pol, float **dev_out);
 /* exploration(π, s): a = ε·σ + μ (tanh-squashed if squashed), logprob.  eps_in NULL => Philox(seed, ctr). */
 int32_t crux_gaussian_explore(crux_gaussian *pol, const float *s, int64_t B, const float *eps_in,

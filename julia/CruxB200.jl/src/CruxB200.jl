@@ -34,6 +34,6 @@ include("onpolicy.jl")
 include("offpolicy.jl")
 include("linquad.jl")
 
-export Ctx, DevMLP, DevGaussian, DevBuffer, VecSampler, LinQuadMDP, DeviceLinQuad, mirror, pull!, fill_gae_returns!, whiten!
+export Ctx, DevMLP, DevGaussian, DevCategorical, DevBuffer, VecSampler, LinQuadMDP, DeviceLinQuad, mirror, pull!, fill_gae_returns!, whiten!
 
 end # module

@@ -143,6 +143,32 @@ function eps_greedy(d::DevDiscrete, s::CuArray{Float32}, ϵ::Real; seed::Integer
     idx .+ Int32(1), oh, lp
 end
 
+"""
+A `DiscreteNetwork` used as an on-policy ACTOR (examples/rl/cartpole.jl:8,17-25): `ppo_loss` / `a2c_loss` / `reinforce_loss` see it through
+`logpdf` = `categorical_logpdf` (policies.jl:135) and `entropy` (:152-155); `crux_categorical_create` gives the update its handle.
+"""
+mutable struct DevCategorical
+    h::Ptr{Cvoid}
+    d::DevDiscrete
+end
+function DevCategorical(π::DiscreteNetwork)
+    d = DevDiscrete(π)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    chk(ccall(sym(:crux_categorical_create), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), ctx().h, d.q.h, length(d.outputs), out), ctx().h)
+    c = DevCategorical(out[], d)
+    finalizer(c -> (c.h != C_NULL && ccall(sym(:crux_gaussian_destroy), Int32, (Ptr{Cvoid},), c.h); c.h = C_NULL), c)
+end
+pull!(c::DevCategorical) = pull!(c.d)
+"`exploration(π::DiscreteNetwork, s)` policies.jl:137-142 over all streams: softmax -> categorical draw -> (1-based indices, one-hot `[nA, B]`, logprob `[1, B]`)"
+function Crux.exploration(c::DevCategorical, s::CuArray{Float32}; seed::Integer=0, ctr::Integer=0, kwargs...)
+    q = value(c.d.q, s); nA, B = size(q)
+    idx = CUDA.zeros(Int32, B); oh = CUDA.zeros(Float32, nA, B); lp = CUDA.zeros(Float32, 1, B)
+    chk(ccall(sym(:crux_discrete_explore), Int32,
+              (Ptr{Cvoid}, CuPtr{Float32}, Int64, Int32, Ptr{Float64}, UInt64, UInt64, CuPtr{Int32}, CuPtr{Float32}, CuPtr{Float32}),
+              ctx().h, q, B, nA, C_NULL, seed, ctr, idx, oh, lp), ctx().h)
+    idx .+ Int32(1), oh, lp
+end
+
 # ---- mirror(π): device twins of the policy trees the hot path supports ---------------------------------------------------------------------------
 struct DevActorCritic{TA,TC}
     A::TA

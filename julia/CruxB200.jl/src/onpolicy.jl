@@ -21,12 +21,14 @@ function target_kl(es)
     lo                                                  # kl > lo stops: lo is the largest KL that still continues
 end
 
+actor_mlp(g::DevGaussian) = g.mu
+actor_mlp(g::DevCategorical) = g.d.q
 loss_kind(f) = f === Crux.ppo_loss ? :ppo : f === Crux.a2c_loss ? :a2c : f === Crux.reinforce_loss ? :reinforce :
                error("CruxB200: the fused on-policy update implements ppo_loss, a2c_loss and reinforce_loss (got $f)")
 maxb(p) = isinf(p.max_batches) ? Int64(0) : Int64(p.max_batches)
 
 "`policy_gradient_training(𝒮, 𝒟)` on_policy.jl:56-78: batch_train!(actor) then batch_train!(critic) (training.jl:28-55) -> info Dict"
-function policy_gradient_training(𝒮::OnPolicySolver, g::DevGaussian, V::Union{DevMLP,Nothing}, 𝒟::DevBuffer; orders=(nothing, nothing), seed::Integer=rand(UInt64))
+function policy_gradient_training(𝒮::OnPolicySolver, g::Union{DevGaussian,DevCategorical}, V::Union{DevMLP,Nothing}, 𝒟::DevBuffer; orders=(nothing, nothing), seed::Integer=rand(UInt64))
     isempty(𝒮.param_optimizers) || error("CruxB200: param_optimizers are not supported by the fused on-policy update")
     𝒮.cost_opt === nothing || error("CruxB200: cost critics (LagrangePPO) go through crux_lagrange_ppo_update; bind it the same way")
     n = length(𝒟)
@@ -66,10 +68,11 @@ log call, so `LoggerParams.fns` evaluate the current policy with stock Crux code
 function solve(𝒮::OnPolicySolver, envs::Vector{<:MDP})
     π = 𝒮.agent.π
     A = π isa ActorCritic ? π.A : π
-    A isa GaussianPolicy || error("CruxB200: the fused on-policy path supports GaussianPolicy(μ, logΣ vector) actors (got $(typeof(A)))")
-    g = mirror(A)
+    (A isa GaussianPolicy || A isa DiscreteNetwork) ||
+        error("CruxB200: the on-policy path supports GaussianPolicy(μ, logΣ vector) and DiscreteNetwork (categorical) actors (got $(typeof(A)))")
+    g = A isa DiscreteNetwork ? DevCategorical(A) : mirror(A)
     V = (π isa ActorCritic && 𝒮.c_opt !== nothing) ? mirror(π.C) : nothing
-    set_adam!(g.mu, 𝒮.a_opt.optimizer)
+    set_adam!(actor_mlp(g), 𝒮.a_opt.optimizer)
     V !== nothing && set_adam!(V, 𝒮.c_opt.optimizer)
     N = length(envs)
     𝒮.ΔN % N == 0 || error("ΔN = $(𝒮.ΔN) must be a multiple of the $N env streams")

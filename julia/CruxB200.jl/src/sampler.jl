@@ -90,19 +90,21 @@ function Crux.steps!(s::VecSampler, π::DevGaussian, 𝒟::DevBuffer; Nsteps::In
 end
 
 """
-    host_loop!(s, 𝒟, Nsteps, act)
+    host_loop!(s, 𝒟, Nsteps, act; reset=false)
 
 The generic `steps!` loop for policies without a one-call rollout: per vector step ONE upload of the observations, `act(s_dev, t)` ->
-`(stored action rows [adim, N] on the device, per-stream env actions on the host)`, the envs stepped on the host, the rows pushed to `𝒟`.
+`(stored action rows [adim, N] on the device, per-stream env actions on the host[, extra columns as a Dict])`, the envs stepped on the host,
+the rows pushed to `𝒟`.  `reset=true`: every stream's episode is terminated at the last vector step (`steps!(reset=true)`, sampler.jl:148-151).
 """
-function host_loop!(s::VecSampler, 𝒟::DevBuffer, Nsteps::Int, act)
+function host_loop!(s::VecSampler, 𝒟::DevBuffer, Nsteps::Int, act; reset::Bool=false)
     N, sd = length(s.mdps), size(s.obs, 1)
     T = cld(Nsteps, N)
     sp, r = zeros(Float32, sd, N), zeros(Float32, 1, N)
     done, ee = zeros(UInt8, 1, N), zeros(UInt8, 1, N)
     for t in 1:T
         sdev = CuArray(s.obs)                                                     # H2D: svec of every stream
-        a_rows, a_env = act(sdev, t)                                              # D2H inside: the env needs the action
+        res = act(sdev, t)                                                        # D2H inside: the env needs the action
+        a_rows, a_env = res[1], res[2]
         sobs = copy(s.obs)
         for e in 1:N
             spe, re = @gen(:sp, :r)(s.mdps[e], s.states[e], a_env[e])
@@ -110,7 +112,7 @@ function host_loop!(s::VecSampler, 𝒟::DevBuffer, Nsteps::Int, act)
             sp[:, e] .= svec(s.mdps[e], spe, s.S); r[1, e] = re
             done[1, e] = isterminal(s.mdps[e], spe)
             s.episode_length[e] += 1                                              # sampler.jl:130
-            fin = done[1, e] != 0 || s.episode_length[e] >= s.max_steps
+            fin = done[1, e] != 0 || s.episode_length[e] >= s.max_steps || (reset && t == T)
             ee[1, e] = fin
             if fin                                                                # terminate_episode! -> reset_sampler!
                 s.states[e] = rand(initialstate(s.mdps[e])); s.episode_length[e] = 0
@@ -119,9 +121,20 @@ function host_loop!(s::VecSampler, 𝒟::DevBuffer, Nsteps::Int, act)
                 s.obs[:, e] .= sp[:, e]
             end
         end
-        push!(𝒟, Dict{Symbol,Any}(:s => sobs, :a => Array(a_rows), :sp => sp, :r => r, :done => done, :episode_end => ee))
+        row = Dict{Symbol,Any}(:s => sobs, :a => Array(a_rows), :sp => sp, :r => r, :done => done, :episode_end => ee)
+        length(res) >= 3 && merge!(row, res[3])
+        push!(𝒟, row)
     end
     T * N
+end
+
+"on-policy rollouts of a categorical actor (examples/rl/cartpole.jl): one batched forward + `crux_discrete_explore` per vector step, `:logprob` stored"
+function Crux.steps!(s::VecSampler, c::DevCategorical, 𝒟::DevBuffer; Nsteps::Int, reset::Bool=true)
+    host_loop!(s, 𝒟, Nsteps, (sdev, t) -> begin
+        idx, oh, lp = exploration(c, sdev; seed=s.seed, ctr=s.noise_ctr)
+        s.noise_ctr += 1
+        oh, [c.d.outputs[k] for k in Array(idx)], Dict{Symbol,Any}(:logprob => Array(lp))
+    end; reset=reset)
 end
 
 "DQN: ϵ-greedy exploration of a DiscreteNetwork (policies.jl:474-494): one batched forward + `crux_discrete_eps_greedy` per vector step"

@@ -347,6 +347,40 @@ def test_softq_value_training_matches_oracle(crux, ctx):
     assert np.isfinite(host(S2.buffer["logprob"])[:len(S2.buffer)]).all() if "logprob" in S2.buffer.schema else True
 
 
+@pytest.mark.parametrize("algo", ["ppo", "a2c", "reinforce"])
+def test_solve_on_policy_discrete_actor_gridworld(crux, ctx, algo):
+    """examples/rl/cartpole.jl:8-9,17-25: PPO / A2C / REINFORCE with a DiscreteNetwork ACTOR (categorical exploration with its log-probability,
+    one-hot action rows, categorical_logpdf / entropy inside the loss) and a ContinuousNetwork critic, through solve() on the grid world."""
+    rng = np.random.default_rng(3)
+    D = crux.Dense
+    acts = [0, 1, 2, 3]
+    A = crux.DiscreteNetwork(crux.Chain(D(2, 64, crux.relu, rng=rng), D(64, 64, crux.relu, rng=rng), D(64, 4, rng=rng)), acts, ctx=ctx)
+    V = crux.ContinuousNetwork(crux.Chain(D(2, 64, crux.relu, rng=rng), D(64, 64, crux.relu, rng=rng), D(64, 1, rng=rng)), ctx=ctx)
+    before_a, before_v = A.mlp.get_flat().copy(), V.mlp.get_flat().copy()
+    n, T = 16, 16
+    opt = dict(epochs=3, batch_size=64)
+    S_ = crux.ContinuousSpace(2)
+    if algo == "ppo":
+        S = crux.PPO(crux.ActorCritic(A, V), S_, a_opt=dict(opt), c_opt=dict(opt), N=3 * n * T, dN=n * T, max_steps=30, target_kl=1e9)
+    elif algo == "a2c":
+        S = crux.A2C(crux.ActorCritic(A, V), S_, a_opt=dict(opt), c_opt=dict(opt), N=3 * n * T, dN=n * T, max_steps=30)
+    else:
+        S = crux.REINFORCE(A, S_, a_opt=dict(opt), N=3 * n * T, dN=n * T, max_steps=30)
+    env = crux.SimpleGridWorld(n, seed=0)
+    crux.solve(S, env)
+    assert S.i == 3 * n * T
+    info = S.training_info()
+    assert np.isfinite(info["actor_loss"]) and np.isfinite(info["kl"]) and 0.0 < info["entropy"] <= math.log(4) + 1e-5
+    a = host(S.buffer["a"])
+    assert a.shape[1] == 4 and np.all(a.sum(1) == 1) and set(np.unique(a)) <= {0.0, 1.0}
+    # the stored log-probabilities are those of the categorical draw: log softmax(net(s))[a] under the parameters that sampled them
+    lp = host(S.buffer["logprob"])[:, 0]
+    assert np.all(lp <= 1e-6) and np.all(lp > -20)
+    assert not np.array_equal(before_a, A.mlp.get_flat()) and np.isfinite(A.mlp.get_flat()).all()
+    if algo != "reinforce":
+        assert not np.array_equal(before_v, V.mlp.get_flat()) and np.isfinite(info["critic_loss"])
+
+
 def test_solve_dqn_gridworld_readme_example(crux, ctx):
     # README.md:72-82 / test/readme.jl (N reduced): DQN(π=DiscreteNetwork(Chain(Dense(2,8,relu), Dense(8,4)), actions), S, N)
     rng = np.random.default_rng(0)

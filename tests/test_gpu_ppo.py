@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import crux_oracle as o
-from gpu_util import F32, assert_close, assert_params_close, dev, host, make_mlp, mlp_params, p
+from gpu_util import F32, assert_close, assert_params_close, dev, host, make_mlp, mlp_grads, mlp_params, p
 
 pytestmark = pytest.mark.gpu
 
@@ -221,6 +221,82 @@ def test_lagrange_ppo_update_matches_oracle(ctx, crux):
     lsp = C.c_void_p(); ctx.check(ctx.lib.crux_gaussian_log_sigma_ptr(h, C.byref(lsp)))
     ls = np.empty(6, F32); ctx.check(ctx.lib.crux_memcpy_d2h(ctx.h, p(ls), lsp, 24)); ctx.sync()
     assert_close(ls, pi.log_sigma.detach().numpy(), rtol=1e-5, atol=2e-6, what="logΣ")
+
+
+def _setup_categorical(ctx, crux, n, seed, sdim=4, nA=3, hidden=64, act=o.ACT_RELU):
+    rng = np.random.default_rng(seed)
+    net = o.MLP([sdim, hidden, hidden, nA], [act, act, o.ACT_IDENTITY], rng)
+    cr = o.MLP([sdim, hidden, hidden, 1], [act, act, o.ACT_IDENTITY], rng)
+    pi = o.DiscreteNetwork(net, list(range(nA)))
+    hm = make_mlp(ctx, net.dims, net.acts, net.flat())
+    hc = make_mlp(ctx, cr.dims, cr.acts, cr.flat())
+    h = C.c_void_p()
+    ctx.check(ctx.lib.crux_categorical_create(ctx.h, hm, nA, C.byref(h)))
+    s = rng.standard_normal((n, sdim)).astype(F32)
+    # actions / log-probabilities from a slightly different (older) policy so that the ratios differ from 1
+    old = o.DiscreteNetwork(o.MLP(net.dims, net.acts, Ws=[w.detach().numpy() * F32(0.9) for w in net.W], bs=[b.detach().numpy() for b in net.b]),
+                            list(range(nA)))
+    ai, lp = old.exploration(s, rng.random(n))
+    a_oh = np.eye(nA, dtype=F32)[ai.numpy()]
+    D = {"s": s, "a": a_oh, "logprob": lp.detach().numpy()[:, 0].astype(F32), "advantage": o.whiten(rng.standard_normal(n).astype(F32)),
+         "return": rng.standard_normal(n).astype(F32)}
+    return rng, pi, cr, (hm, hc, h), D
+
+
+@pytest.mark.parametrize("loss,n,ab,nA", [("ppo", 512, 128, 2), ("ppo", 1000, 256, 5), ("a2c", 600, 200, 3), ("reinforce", 384, 128, 4)])
+def test_categorical_actor_update_matches_oracle(ctx, crux, loss, n, ab, nA):
+    """ppo_loss / a2c_loss / reinforce_loss with a DiscreteNetwork actor (examples/rl/cartpole.jl:8-9: Chain(Dense(4,64,relu), Dense(64,64,relu),
+    Dense(64,nA))): logpdf = categorical_logpdf (policies.jl:135), entropy per sample (:152-155) averaged by e_loss -- crux_categorical_create +
+    crux_ppo_update against the oracle's autograd train_step loop on the same minibatch orders."""
+    rng, pi, cr, handles, D = _setup_categorical(ctx, crux, n, seed=n + nA, nA=nA)
+    hm, hc, h = handles
+    a2c = loss != "ppo"
+    le = 0.0 if loss == "reinforce" else 0.1
+    hp = _hp(crux, actor_batch=ab, critic_batch=ab, a2c=1 if a2c else 0, lambda_e=le)
+    oa = _orders(rng, n, hp.actor_epochs); oc = _orders(rng, n, hp.critic_epochs, start=oa[-1])
+    P = {"eps": F32(0.2), "lp": F32(1.0), "le": F32(le)}
+    Dd = dict(D)
+    if loss == "reinforce":      # reinforce_loss = -mean(logp .* return): the a2c head with the return as the weight and no entropy term
+        Dd["advantage"] = D["return"]
+        fn = lambda mb, inf: o.reinforce_loss(pi, P, mb, inf)
+    elif loss == "a2c":
+        fn = lambda mb, inf: o.a2c_loss(pi, P, mb, inf)
+    else:
+        fn = lambda mb, inf: o.ppo_loss(pi, P, mb, inf)
+    # raw gradient of the FIRST minibatch against autograd (the update below starts from the same parameters)
+    mb0 = {k: v[oa[0][:ab]] for k, v in Dd.items()}
+    for q_ in pi.params():
+        q_.grad = None
+    fn(mb0, {}).backward()
+    g_want = o.flat_grads(pi.params())
+    hp1 = _hp(crux, actor_batch=ab, critic_batch=ab, a2c=1 if a2c else 0, lambda_e=le, actor_epochs=1, critic_epochs=0, actor_max_batches=1)
+    saved = mlp_params(ctx, hm).copy()
+    _run(ctx, crux, handles, Dd, hp1, oa[:1], None, n)
+    g_got = mlp_grads(ctx, hm)
+    assert_close(g_got, g_want, rtol=2e-4, atol=2e-7 + 1e-5 * float(np.abs(g_want).max()), what="raw gradient of the first minibatch")
+    ctx.check(ctx.lib.crux_mlp_set_params(hm, p(saved)))
+    ctx.check(ctx.lib.crux_mlp_set_adam(hm, float(F32(3e-4)), 0.9, 0.999, 1e-8))
+    ra = _oracle_train(pi.params(), fn, o.Adam(F32(3e-4)), Dd, oa, ab)
+    rc_ = _oracle_train(cr.params(), lambda mb, inf: o.value_mse_loss(cr, mb), o.Adam(F32(3e-4)), D, oc, ab)
+    ia, ic = _run(ctx, crux, handles, Dd, hp, oa, oc, n)
+    A = crux._abi
+    assert len(ra) == ia.shape[0]
+    for k, rec in enumerate(ra):
+        assert ia[k, A.PPO_VALID] == 1.0
+        assert_close(ia[k, A.PPO_LOSS], rec["loss"], rtol=1e-4, atol=1e-5, what=f"actor loss mb {k}")
+        assert_close(ia[k, A.PPO_KL], rec["kl"], rtol=1e-3, atol=2e-6, what=f"kl mb {k}")
+        assert_close(ia[k, A.PPO_ENTROPY], rec["entropy"], rtol=1e-5, atol=1e-6, what="entropy")
+        assert_close(ia[k, A.PPO_GRAD_NORM], rec["grad_norm"], rtol=1e-3, what="grad_norm")
+        if loss == "ppo":
+            assert_close(ia[k, A.PPO_CLIP_FRAC], rec["clip_fraction"], rtol=0, atol=2.0 / ab, what="clip_fraction")
+    for k, rec in enumerate(rc_):
+        assert_close(ic[k, A.PPO_LOSS], rec["loss"], rtol=1e-4, what=f"critic loss mb {k}")
+    assert_params_close(mlp_params(ctx, hm), pi.net.flat(), 3e-4, len(ra), what="actor params")
+    assert_params_close(mlp_params(ctx, hc), cr.flat(), 3e-4, len(rc_), what="critic params")
+    # the Gaussian entry points refuse the handle instead of misreading it
+    out = dev(ctx, np.zeros((4, nA), F32))
+    assert ctx.lib.crux_gaussian_action(h, p(dev(ctx, D["s"][:4])), 4, p(out)) != 0
+    ctx.lib.crux_gaussian_destroy(h)
 
 
 def test_device_permutation_is_a_permutation_and_trains(ctx, crux):
