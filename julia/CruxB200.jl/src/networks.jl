@@ -162,11 +162,13 @@ pull!(c::DevCategorical) = pull!(c.d)
 "`exploration(π::DiscreteNetwork, s)` policies.jl:137-142 over all streams: softmax -> categorical draw -> (1-based indices, one-hot `[nA, B]`, logprob `[1, B]`)"
 function Crux.exploration(c::DevCategorical, s::CuArray{Float32}; seed::Integer=0, ctr::Integer=0, kwargs...)
     q = value(c.d.q, s); nA, B = size(q)
-    idx = CUDA.zeros(Int32, B); oh = CUDA.zeros(Float32, nA, B); lp = CUDA.zeros(Float32, 1, B)
+    idx = CUDA.zeros(Int32, B); lp = CUDA.zeros(Float32, 1, B)
     chk(ccall(sym(:crux_discrete_explore), Int32,
-              (Ptr{Cvoid}, CuPtr{Float32}, Int64, Int32, Ptr{Float64}, UInt64, UInt64, CuPtr{Int32}, CuPtr{Float32}, CuPtr{Float32}),
-              ctx().h, q, B, nA, C_NULL, seed, ctr, idx, oh, lp), ctx().h)
-    idx .+ Int32(1), oh, lp
+              (Ptr{Cvoid}, CuPtr{Float32}, Int64, Int32, Ptr{Float64}, UInt64, UInt64, CuPtr{Int32}, CuPtr{Float32}),
+              ctx().h, q, B, nA, C_NULL, seed, ctr, idx, lp), ctx().h)
+    idx1 = idx .+ Int32(1)
+    oh = Float32.(Int32.(1:nA) .== reshape(idx1, 1, B))          # Flux.onehotbatch(π, a) as a dense `[nA, B]` array on the device
+    idx1, oh, lp
 end
 
 # ---- mirror(π): device twins of the policy trees the hot path supports ---------------------------------------------------------------------------
