@@ -18,12 +18,14 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 32, NTH = 256;
+constexpr int BM = 128, BN = 64, BK = 32, NTH = 256, NST = 4;               // NST stages of one k-tile each
 constexpr int A_PLANE = BM * BK * 4, B_PLANE = BN * BK * 4;                 // bytes
-constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;                            // A hi | A lo | B hi | B lo
-constexpr int SM_BAR = 2 * STAGE;                                           // bar[2] (stage free), bar_done, tmem slot
-constexpr int SM_BSUM = SM_BAR + 64;                                        // [4][64] column-sum scratch (EPI_PARTIAL)
-constexpr int SM_TOTAL = SM_BSUM + 4 * BN * 4;
+constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;                            // A hi | A lo | B hi | B lo   (48 KB)
+constexpr int SM_BAR = NST * STAGE;                                         // bar[NST] (stage free), bar_done, tmem slot
+constexpr int SM_BSUM = SM_BAR + 64;                                        // [8][64] column-sum scratch (EPI_PARTIAL)
+constexpr int SM_TOTAL = SM_BSUM + 8 * BN * 4;
+constexpr int LDC_S = BN + 1;                                               // padded row of the C tile staged for coalesced stores
+static_assert(BM * LDC_S * 4 <= STAGE, "the C tile is staged in stage 0");
 enum { EPI_FWD = 0, EPI_BWD_DATA = 1, EPI_PARTIAL = 2 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -58,24 +60,72 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!done)
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
+// asynchronous global -> shared copies; `bytes` of the source are read, the rest of the destination is zero-filled (edges of the matrices)
+__device__ __forceinline__ void cp16(uint32_t dst, const void *src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp4(uint32_t dst, const void *src, int bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+// One operand tile (ROWS x BK, canonical K-major) of k-tile [k0, k0 + BK): element (row, k) = TR ? src[(k0 + k) * ld + r0 + row] : src[(r0 + row) * ld + k0 + k].
+// The copies land DIRECTLY in the canonical layout: a 16-byte chunk of four consecutive k of one row is one core-matrix row, so a
+// k-contiguous, 16-byte-aligned source needs one cp.async per chunk; every other source (row-contiguous = transposed, or rows that are
+// not 16-byte aligned such as the 393-wide vcat(s, a) input of a critic) is copied element by element, coalesced along its contiguous index.
+template <int ROWS, bool TR>
+__device__ __forceinline__ void stage_tile(uint32_t dst, const float *__restrict__ src, int ld, int r0, int n_rows, int k0, int k_end, bool vec, int t) {
+  if (!TR && vec) {
+#pragma unroll
+    for (int i = 0; i < ROWS * (BK / 4) / NTH; ++i) {
+      const int c = t + i * NTH, row = c >> 3, kc = c & 7;      // 8 chunks per row: a warp reads 4 rows x 128 contiguous bytes
+      const int gr = r0 + row, gk = k0 + 4 * kc;
+      const int nb = (gr < n_rows && gk < k_end) ? min(16, 4 * (k_end - gk)) : 0;
+      cp16(dst + canon(row, 4 * kc), nb ? (const void *)(src + (int64_t)gr * ld + gk) : (const void *)src, nb);
+    }
+  } else if (TR) {
+    // consecutive threads walk the rows (contiguous in memory); thread t: row = t % ROWS, k = t / ROWS + (NTH / ROWS) i
+    constexpr int KS = NTH / ROWS, NI = ROWS * BK / NTH;
+    const int row = t % ROWS, kb = t / ROWS;
+    const bool row_ok = r0 + row < n_rows;
+    const float *g = src + (int64_t)(k0 + kb) * ld + r0 + row;
+    const uint32_t d0 = dst + (row >> 3) * (32 * BK) + (row & 7) * 16;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int k = kb + KS * i;
+      const bool ok = row_ok && k0 + k < k_end;
+      cp4(d0 + (k >> 2) * 128 + (k & 3) * 4, ok ? (const void *)(g + (int64_t)(KS * i) * ld) : (const void *)src, ok ? 4 : 0);
+    }
+  } else {
+    // k-contiguous rows that are not 16-byte aligned: thread t: k = t % 32, row = t / 32 + 8 i
+    constexpr int NI = ROWS * BK / NTH;
+    const int k = t & (BK - 1), rb = t >> 5;
+    const bool k_ok = k0 + k < k_end;
+    const float *g = src + (int64_t)(r0 + rb) * ld + k0 + k;
+    const uint32_t d0 = dst + (k >> 2) * 128 + (k & 3) * 4 + rb * 16;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const bool ok = k_ok && r0 + rb + 8 * i < n_rows;
+      cp4(d0 + i * (32 * BK), ok ? (const void *)(g + (int64_t)(8 * i) * ld) : (const void *)src, ok ? 4 : 0);
+    }
+  }
+}
 
 template <bool TA, bool TB, int EPI>
-__global__ void __launch_bounds__(NTH, 2) gemm_tc5_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bm, int ldb, float *__restrict__ C,
+__global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bm, int ldb, float *__restrict__ C,
                                                           int ldc, int M, int N, int K, const float *__restrict__ bias, int act,
                                                           const float *__restrict__ yprev, int prev_act, int k_per_slab, int bias_row,
-                                                          const int *__restrict__ skip) {
+                                                          const int *__restrict__ skip, int vec_a, int vec_b) {
   if (skip && *skip) return;
   extern __shared__ __align__(1024) unsigned char smb[];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   int k_begin = 0, k_end = K;
   if (EPI == EPI_PARTIAL) { k_begin = blockIdx.z * k_per_slab; k_end = min(K, k_begin + k_per_slab); }
-  const uint32_t bar0 = smem_u32(smb + SM_BAR), bar_done = bar0 + 16;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + SM_BAR + 24);
+  const uint32_t sb = smem_u32(smb);
+  const uint32_t bar0 = sb + SM_BAR, bar_done = bar0 + 8 * NST;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + SM_BAR + 8 * NST + 8);
   if (t == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0), "r"(1) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8), "r"(1) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_done), "r"(1) : "memory");
+    for (int i = 0; i <= NST; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -83,58 +133,55 @@ __global__ void __launch_bounds__(NTH, 2) gemm_tc5_kernel(const float *__restric
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  const int n_kt = (k_end - k_begin + BK - 1) / BK;
+  // prologue of the copy pipeline: tiles 0 .. NST-2 in flight (one commit group per tile, empty past the end so that the counts stay uniform)
+#pragma unroll
+  for (int p = 0; p < NST - 1; ++p) {
+    if (p < n_kt) {
+      stage_tile<BM, TA>(sb + p * STAGE, A, lda, m0, M, k_begin + p * BK, k_end, vec_a != 0, t);
+      stage_tile<BN, !TB>(sb + p * STAGE + 2 * A_PLANE, Bm, ldb, n0, N, k_begin + p * BK, k_end, vec_b != 0, t);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
   const uint32_t idesc = make_idesc(BM, BN);
-  // element -> thread maps of the staging loops: consecutive threads walk the index that is contiguous in global memory
-  //   A tile: 128 x 32 = 4096 elements, 16 per thread;  B tile: 64 x 32 = 2048 elements, 8 per thread
   const bool do_bias = (EPI == EPI_PARTIAL) && bias_row && blockIdx.y == 0;
-  float bsum[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
+  float bsum[2] = {0.f, 0.f};   // column sums of the B tile: chunk i of this thread always belongs to column n = 8 (t / 64 + 4 i) + t % 8
 
-  const int n_kt = (k_end - k_begin + BK - 1) / BK;
   for (int kt = 0; kt < n_kt; ++kt) {
-    const int s = kt & 1, k0 = k_begin + kt * BK;
+    const int s = kt % NST;
     unsigned char *st = smb + s * STAGE;
-    if (kt >= 2) mbar_wait(bar0 + 8 * s, (uint32_t)(((kt >> 1) - 1) & 1));   // the MMAs that read this buffer two tiles ago have completed
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const int idx = t + i * NTH;
-      int m, k;
-      if (TA) { m = idx & (BM - 1); k = idx >> 7; } else { k = idx & (BK - 1); m = idx >> 5; }
-      const int gm = m0 + m, gk = k0 + k;
-      float v = 0.f;
-      if (gm < M && gk < k_end) v = TA ? __ldg(A + (int64_t)gk * lda + gm) : __ldg(A + (int64_t)gm * lda + gk);
-      float hi, lo;
-      split(v, hi, lo);
-      const int off = canon(m, k);
-      *reinterpret_cast<float *>(st + off) = hi;
-      *reinterpret_cast<float *>(st + A_PLANE + off) = lo;
+    asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");   // this thread's copies of tile kt have landed
+    __syncthreads();                                                      // ... and everybody else's
+    // x -> hi (in place) | lo: every thread walks the planes linearly in 16-byte chunks (conflict-free)
+#pragma unroll
+    for (int i = 0; i < A_PLANE / 16 / NTH; ++i) {
+      float4 *ph = reinterpret_cast<float4 *>(st) + t + i * NTH;
+      const float4 x = *ph;
+      float4 h, l;
+      split(x.x, h.x, l.x); split(x.y, h.y, l.y); split(x.z, h.z, l.z); split(x.w, h.w, l.w);
+      *ph = h;
+      *(ph + A_PLANE / 16) = l;
     }
-#pragma unroll 4
-    for (int i = 0; i < 8; ++i) {
-      const int idx = t + i * NTH;
-      int n, k;
-      if (TB) { k = idx & (BK - 1); n = idx >> 5; } else { n = idx & (BN - 1); k = idx >> 6; }
-      const int gn = n0 + n, gk = k0 + k;
-      float v = 0.f;
-      if (gn < N && gk < k_end) v = TB ? __ldg(Bm + (int64_t)gn * ldb + gk) : __ldg(Bm + (int64_t)gk * ldb + gn);
-      if (do_bias) bsum[i] += v;   // (!TB in the weight-gradient call: this thread's n = t & 63 for every i)
-      float hi, lo;
-      split(v, hi, lo);
-      const int off = canon(n, k);
-      *reinterpret_cast<float *>(st + 2 * A_PLANE + off) = hi;
-      *reinterpret_cast<float *>(st + 2 * A_PLANE + B_PLANE + off) = lo;
+#pragma unroll
+    for (int i = 0; i < B_PLANE / 16 / NTH; ++i) {
+      float4 *ph = reinterpret_cast<float4 *>(st + 2 * A_PLANE) + t + i * NTH;
+      const float4 x = *ph;
+      if (do_bias) bsum[i] += (x.x + x.y) + (x.z + x.w);
+      float4 h, l;
+      split(x.x, h.x, l.x); split(x.y, h.y, l.y); split(x.z, h.z, l.z); split(x.w, h.w, l.w);
+      *ph = h;
+      *(ph + B_PLANE / 16) = l;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor cores
     __syncthreads();
     if (w == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
-        const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_PLANE, b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + B_PLANE;
+        const uint32_t a_hi = sb + s * STAGE, a_lo = a_hi + A_PLANE, b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + B_PLANE;
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) mma_tf32_ss(tmem, make_desc(a_lo + ks * 256), make_desc(b_hi + ks * 256), idesc, (kt || ks) ? 1u : 0u);
 #pragma unroll
@@ -146,8 +193,19 @@ __global__ void __launch_bounds__(NTH, 2) gemm_tc5_kernel(const float *__restric
       }
       __syncwarp();
     }
+    // refill: tile kt + NST - 1 goes into the stage tile kt - 1 used; its MMAs were committed one iteration ago
+    const int nt = kt + NST - 1;
+    if (nt < n_kt) {
+      const int sn = nt % NST;
+      if (kt >= 1) mbar_wait(bar0 + 8 * sn, (uint32_t)(((kt - 1) / NST) & 1));
+      stage_tile<BM, TA>(sb + sn * STAGE, A, lda, m0, M, k_begin + nt * BK, k_end, vec_a != 0, t);
+      stage_tile<BN, !TB>(sb + sn * STAGE + 2 * A_PLANE, Bm, ldb, n0, N, k_begin + nt * BK, k_end, vec_b != 0, t);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  // ---- epilogue: warp w reads TMEM lanes [32 (w & 3), +32) x columns [32 (w >> 2), +32)
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // ---- epilogue: warp w reads TMEM lanes [32 (w & 3), +32) x columns [32 (w >> 2), +32), stages the C tile in shared memory (stage 0 is
+  //      free once every MMA has completed) and the CTA writes it out row by row: coalesced stores, coalesced reads of the mask operand
   float *Cz = C;
   if (EPI == EPI_PARTIAL) Cz = C + (int64_t)blockIdx.z * (int64_t)(M + (bias_row ? 1 : 0)) * ldc;
   if (n_kt > 0) {
@@ -165,17 +223,19 @@ __global__ void __launch_bounds__(NTH, 2) gemm_tc5_kernel(const float *__restric
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    const int gm = m0 + 32 * (w & 3) + lane;
-    if (gm < M) {
+    float *sC = reinterpret_cast<float *>(smb);
+    const int r = 32 * (w & 3) + lane;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int gn = n0 + c0 + j;
-        if (gn < N) {
-          float x = __uint_as_float(v[j]);
-          if (EPI == EPI_FWD) x = act_fwd_rt(act, x + bias[gn]);
-          if (EPI == EPI_BWD_DATA && yprev) x *= act_bwd_from_out(prev_act, yprev[(int64_t)gm * ldc + gn]);
-          Cz[(int64_t)gm * ldc + gn] = x;
-        }
+    for (int j = 0; j < 32; ++j) sC[r * LDC_S + c0 + j] = __uint_as_float(v[j]);
+    __syncthreads();
+    for (int e = t; e < BM * BN; e += NTH) {
+      const int row = e >> 6, col = e & 63;
+      const int gm = m0 + row, gn = n0 + col;
+      if (gm < M && gn < N) {
+        float x = sC[row * LDC_S + col];
+        if (EPI == EPI_FWD) x = act_fwd_rt(act, x + bias[gn]);
+        if (EPI == EPI_BWD_DATA && yprev) x *= act_bwd_from_out(prev_act, yprev[(int64_t)gm * ldc + gn]);
+        Cz[(int64_t)gm * ldc + gn] = x;
       }
     }
   } else if (EPI == EPI_PARTIAL) {   // empty slab: zeros
@@ -184,14 +244,17 @@ __global__ void __launch_bounds__(NTH, 2) gemm_tc5_kernel(const float *__restric
       if (gm < M && gn < N) Cz[(int64_t)gm * ldc + gn] = 0.f;
     }
   }
-  if (do_bias) {   // bias gradient of this slab: sum over k of B(k, n); with !TB thread t owns column n = t & 63 in all of its 8 elements
-    float sloc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sloc += bsum[i];
+  if (do_bias) {   // bias gradient of this slab: column sums of B over k.  Chunk i of thread t is k-chunk (t % 64) / 8 of column 8 (t / 64 + 4 i) + t % 8
     float *sc = reinterpret_cast<float *>(smb + SM_BSUM);
-    sc[(t >> 6) * BN + (t & 63)] = sloc;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) sc[((t & 63) >> 3) * BN + 8 * ((t >> 6) + 4 * i) + (t & 7)] = bsum[i];
     __syncthreads();
-    if (t < BN && n0 + t < N) Cz[(int64_t)M * ldc + n0 + t] = (sc[t] + sc[BN + t]) + (sc[2 * BN + t] + sc[3 * BN + t]);
+    if (t < BN && n0 + t < N) {
+      float sum = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sum += sc[q * BN + t];   // fixed order: bit-reproducible
+      Cz[(int64_t)M * ldc + n0 + t] = sum;
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -206,7 +269,11 @@ int launch(crux_ctx *ctx, dim3 grid, const float *A, int lda, const float *B, in
     CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(gemm_tc5_kernel<TA, TB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     attr = true;
   }
-  gemm_tc5_kernel<TA, TB, EPI><<<grid, NTH, SM_TOTAL, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, act, yprev, prev_act, k_per_slab, bias_row, skip);
+  // 16-byte copies need a k-contiguous operand whose rows start 16-byte aligned
+  const int vec_a = (!TA && lda % 4 == 0 && ((uintptr_t)A & 15) == 0) ? 1 : 0;
+  const int vec_b = (TB && ldb % 4 == 0 && ((uintptr_t)B & 15) == 0) ? 1 : 0;
+  gemm_tc5_kernel<TA, TB, EPI><<<grid, NTH, SM_TOTAL, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, act, yprev, prev_act, k_per_slab, bias_row, skip,
+                                                                     vec_a, vec_b);
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;
 }
