@@ -18,14 +18,21 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 32, NTH = 256, NST = 4;               // NST stages of one k-tile each
-constexpr int A_PLANE = BM * BK * 4, B_PLANE = BN * BK * 4;                 // bytes
-constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;                            // A hi | A lo | B hi | B lo   (48 KB)
-constexpr int SM_BAR = NST * STAGE;                                         // bar[NST] (stage free), bar_done, tmem slot
-constexpr int SM_BSUM = SM_BAR + 64;                                        // [8][64] column-sum scratch (EPI_PARTIAL)
-constexpr int SM_TOTAL = SM_BSUM + 8 * BN * 4;
-constexpr int LDC_S = BN + 1;                                               // padded row of the C tile staged for coalesced stores
-static_assert(BM * LDC_S * 4 <= STAGE, "the C tile is staged in stage 0");
+constexpr int BM = 128, BN = 64, BK = 32, NW = 256, NTH = 288, NTB = 128, NST = 4;   // NW worker threads (warps 0..7) + the MMA issuer warp 8
+constexpr int B_PLANE = BN * BK * 4;                                        // bytes
+constexpr int LDA_S = BK + 4;                                               // padded row of the raw A tile [m][k] (floats): rows and chunks conflict-free
+constexpr int A_RAW = BM * LDA_S * 4;                                       // 18 KB (the transposed form [k][m] needs 16 KB)
+constexpr int B_RAW = BK * BN * 4;                                          // raw B tile [k][n] of an n-contiguous source (8 KB)
+constexpr int OFF_A = 2 * B_PLANE, OFF_BR = OFF_A + A_RAW;
+constexpr int STAGE = OFF_BR + B_RAW;                                       // B hi | B lo | A raw | B raw   (42 KB)
+constexpr int C_STAGE = BM * (BN + 1) * 4;                                  // the C tile staged for coalesced stores (padded rows)
+constexpr int SM_B = C_STAGE > NST * STAGE ? C_STAGE : NST * STAGE;
+constexpr int SM_BAR = SM_B;                                                // bar_free[2], bar_ready[2], bar_done, tmem slot
+constexpr int SM_BSUM = SM_BAR + 64;                                        // [4][64] column-sum scratch (EPI_PARTIAL)
+constexpr int SM_TOTAL = SM_BSUM + 4 * BN * 4;
+constexpr int LDC_S = BN + 1;
+// tensor memory: accumulator D [128 lanes][64 columns] | two A buffers, each hi [32 columns] | lo [32 columns]
+constexpr uint32_t TM_D = 0, TM_A = 64, TM_COLS = 256;
 enum { EPI_FWD = 0, EPI_BWD_DATA = 1, EPI_PARTIAL = 2 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -41,8 +48,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {   // K-major, no
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {   // D = F32, A = B = TF32, both K-major
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da),
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem), "r"(a_tmem),
                "l"(db), "r"(idesc), "r"(acc)
                : "memory");
 }
@@ -67,49 +74,125 @@ __device__ __forceinline__ void cp16(uint32_t dst, const void *src, int bytes) {
 __device__ __forceinline__ void cp4(uint32_t dst, const void *src, int bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
+#define G5_ST32(taddr, v)                                                                                                                              \
+  asm volatile(                                                                                                                                          \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, " \
+      "%24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),                                                                                      \
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]),      \
+      "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),    \
+      "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])                                                               \
+      : "memory")
 
-// One operand tile (ROWS x BK, canonical K-major) of k-tile [k0, k0 + BK): element (row, k) = TR ? src[(k0 + k) * ld + r0 + row] : src[(r0 + row) * ld + k0 + k].
-// The copies land DIRECTLY in the canonical layout: a 16-byte chunk of four consecutive k of one row is one core-matrix row, so a
-// k-contiguous, 16-byte-aligned source needs one cp.async per chunk; every other source (row-contiguous = transposed, or rows that are
-// not 16-byte aligned such as the 393-wide vcat(s, a) input of a critic) is copied element by element, coalesced along its contiguous index.
-template <int ROWS, bool TR>
-__device__ __forceinline__ void stage_tile(uint32_t dst, const float *__restrict__ src, int ld, int r0, int n_rows, int k0, int k_end, bool vec, int t) {
-  if (!TR && vec) {
+// ---- operand staging (all 256 worker threads copy; one k-tile = [k0, k0 + BK)) -------------------------------------------------------------------
+// A raw tile.  !TA: element (m, k) = A[(m0 + m) * lda + k0 + k] -> shared [m][LDA_S]; aligned rows: 16-byte chunks, lanes = 8 rows x 4 chunks (whole
+// 32-byte sectors in global memory, distinct bank groups in shared memory), else element copies.  TA: element (m, k) = A[(k0 + k) * lda + m0 + m]
+// -> shared [k][BM] (the A-side thread m then reads a column: consecutive lanes, consecutive words); 16-byte chunks along m when aligned.
+template <bool TA>
+__device__ __forceinline__ void stage_a(uint32_t dst, const float *__restrict__ A, int lda, int m0, int M, int k0, int k_end, bool vec, int t) {
+  if (!TA) {
+    if (vec) {
+      const int w = t >> 5, l = t & 31;
 #pragma unroll
-    for (int i = 0; i < ROWS * (BK / 4) / NTH; ++i) {
-      const int c = t + i * NTH, row = c >> 3, kc = c & 7;      // 8 chunks per row: a warp reads 4 rows x 128 contiguous bytes
-      const int gr = r0 + row, gk = k0 + 4 * kc;
-      const int nb = (gr < n_rows && gk < k_end) ? min(16, 4 * (k_end - gk)) : 0;
-      cp16(dst + canon(row, 4 * kc), nb ? (const void *)(src + (int64_t)gr * ld + gk) : (const void *)src, nb);
-    }
-  } else if (TR) {
-    // consecutive threads walk the rows (contiguous in memory); thread t: row = t % ROWS, k = t / ROWS + (NTH / ROWS) i
-    constexpr int KS = NTH / ROWS, NI = ROWS * BK / NTH;
-    const int row = t % ROWS, kb = t / ROWS;
-    const bool row_ok = r0 + row < n_rows;
-    const float *g = src + (int64_t)(k0 + kb) * ld + r0 + row;
-    const uint32_t d0 = dst + (row >> 3) * (32 * BK) + (row & 7) * 16;
+      for (int i = 0; i < 4; ++i) {
+        const int u = w * 4 + i, row = (u >> 1) * 8 + (l & 7), kc = (u & 1) * 4 + (l >> 3);
+        const int gr = m0 + row, gk = k0 + 4 * kc;
+        const int nb = (gr < M && gk < k_end) ? min(16, 4 * (k_end - gk)) : 0;
+        cp16(dst + (row * LDA_S + 4 * kc) * 4, nb ? (const void *)(A + (int64_t)gr * lda + gk) : (const void *)A, nb);
+      }
+    } else {           // unaligned k-contiguous rows: thread t: k = t % 32, row = t / 32 + 8 i
+      const int k = t & (BK - 1), rb = t >> 5;
+      const bool k_ok = k0 + k < k_end;
+      const float *g = A + (int64_t)(m0 + rb) * lda + k0 + k;
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int k = kb + KS * i;
-      const bool ok = row_ok && k0 + k < k_end;
-      cp4(d0 + (k >> 2) * 128 + (k & 3) * 4, ok ? (const void *)(g + (int64_t)(KS * i) * ld) : (const void *)src, ok ? 4 : 0);
+      for (int i = 0; i < 16; ++i) {
+        const int row = rb + 8 * i;
+        const bool ok = k_ok && m0 + row < M;
+        cp4(dst + (row * LDA_S + k) * 4, ok ? (const void *)(g + (int64_t)(8 * i) * lda) : (const void *)A, ok ? 4 : 0);
+      }
     }
   } else {
-    // k-contiguous rows that are not 16-byte aligned: thread t: k = t % 32, row = t / 32 + 8 i
-    constexpr int NI = ROWS * BK / NTH;
-    const int k = t & (BK - 1), rb = t >> 5;
-    const bool k_ok = k0 + k < k_end;
-    const float *g = src + (int64_t)(r0 + rb) * ld + k0 + k;
-    const uint32_t d0 = dst + (k >> 2) * 128 + (k & 3) * 4 + rb * 16;
+    if (vec) {         // 32 k-rows x 32 chunks of 4 m: thread t: chunk mc = t % 32, k = t / 32 + 8 i
+      const int mc = t & 31, kb = t >> 5;
+      const int gm = m0 + 4 * mc;
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const bool ok = k_ok && r0 + rb + 8 * i < n_rows;
-      cp4(d0 + i * (32 * BK), ok ? (const void *)(g + (int64_t)(8 * i) * ld) : (const void *)src, ok ? 4 : 0);
+      for (int i = 0; i < 4; ++i) {
+        const int k = kb + 8 * i;
+        const int nb = (k0 + k < k_end && gm < M) ? min(16, 4 * (M - gm)) : 0;
+        cp16(dst + (k * BM + 4 * mc) * 4, nb ? (const void *)(A + (int64_t)(k0 + k) * lda + gm) : (const void *)A, nb);
+      }
+    } else {           // thread t: m = t % 128, k = t / 128 + 2 i
+      const int row = t & 127, kb = t >> 7;
+      const bool row_ok = m0 + row < M;
+      const float *g = A + (int64_t)(k0 + kb) * lda + m0 + row;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = kb + 2 * i;
+        const bool ok = row_ok && k0 + k < k_end;
+        cp4(dst + (k * BM + row) * 4, ok ? (const void *)(g + (int64_t)(2 * i) * lda) : (const void *)A, ok ? 4 : 0);
+      }
+    }
+  }
+}
+// B tile.  TB (k-contiguous source, element (n, k) = B[(n0 + n) * ldb + k0 + k]): copied DIRECTLY into the canonical K-major hi plane (a 16-byte
+// chunk of four consecutive k of one row is one core-matrix row; lanes = 8 rows x 4 chunks) and split in place.  !TB (n-contiguous source,
+// element (n, k) = B[(k0 + k) * ldb + n0 + n]): copied raw as [k][BN] (16-byte chunks along n when aligned) and transposed by the split pass.
+template <bool TB>
+__device__ __forceinline__ void stage_b(uint32_t stage, const float *__restrict__ Bm, int ldb, int n0, int N, int k0, int k_end, bool vec, int t) {
+  if (TB) {
+    if (vec) {         // 64 rows x 8 chunks = 512 chunks, 2 per thread
+      const int w = t >> 5, l = t & 31;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int u = w * 2 + i, row = (u >> 1) * 8 + (l & 7), kc = (u & 1) * 4 + (l >> 3);
+        const int gr = n0 + row, gk = k0 + 4 * kc;
+        const int nb = (gr < N && gk < k_end) ? min(16, 4 * (k_end - gk)) : 0;
+        cp16(stage + canon(row, 4 * kc), nb ? (const void *)(Bm + (int64_t)gr * ldb + gk) : (const void *)Bm, nb);
+      }
+    } else {           // thread t: k = t % 32, row = t / 32 + 8 i
+      const int k = t & (BK - 1), rb = t >> 5;
+      const bool k_ok = k0 + k < k_end;
+      const float *g = Bm + (int64_t)(n0 + rb) * ldb + k0 + k;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = rb + 8 * i;
+        const bool ok = k_ok && n0 + row < N;
+        cp4(stage + canon(row, k), ok ? (const void *)(g + (int64_t)(8 * i) * ldb) : (const void *)Bm, ok ? 4 : 0);
+      }
+    }
+  } else {
+    const uint32_t dst = stage + OFF_BR;
+    if (vec) {         // 32 k-rows x 16 chunks of 4 n = 512 chunks, 2 per thread: thread t: chunk nc = t % 16, k = t / 16 + 16 i
+      const int nc = t & 15, kb = t >> 4;
+      const int gn = n0 + 4 * nc;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int k = kb + 16 * i;
+        const int nb = (k0 + k < k_end && gn < N) ? min(16, 4 * (N - gn)) : 0;
+        cp16(dst + (k * BN + 4 * nc) * 4, nb ? (const void *)(Bm + (int64_t)(k0 + k) * ldb + gn) : (const void *)Bm, nb);
+      }
+    } else {           // thread t: n = t % 64, k = t / 64 + 4 i
+      const int n = t & 63, kb = t >> 6;
+      const bool n_ok = n0 + n < N;
+      const float *g = Bm + (int64_t)(k0 + kb) * ldb + n0 + n;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = kb + 4 * i;
+        const bool ok = n_ok && k0 + k < k_end;
+        cp4(dst + (k * BN + n) * 4, ok ? (const void *)(g + (int64_t)(4 * i) * ldb) : (const void *)Bm, ok ? 4 : 0);
+      }
     }
   }
 }
 
+// One CTA = a 128 x 64 tile of C.  Shared-memory bandwidth and lock-step phases are what the first versions of this kernel ran out of: with
+// both operands written hi | lo into shared memory and every thread walking copy -> split -> barrier -> MMA issue in turn, a 32-wide k-tile
+// cost 2 300-2 700 cycles (copies 1 060, split 420, MMAs 400, barriers 400 -- strictly added up, CRUX_G5_DEBUG).  Now:
+//   * every global -> shared copy is a 16-byte cp.async whenever the source allows it (4-stage pipeline, 256 worker threads);
+//   * the A operand leaves shared memory only once: warps 0..3 (thread = row = TMEM lane) read their row of the RAW tile, split it and store
+//     hi | lo into one of two A buffers in TENSOR MEMORY (tcgen05.st); warps 4..7 split (and, for n-contiguous sources, transpose) the B tile;
+//   * warp 8 does nothing but wait for "operands of tile kt ready" (mbarrier, 256 arrivals) and issue 3 passes x 4 k-steps of
+//     tcgen05.mma.kind::tf32 (A from tensor memory, B from shared memory): the workers never wait for the tensor pipe except through the
+//     buffer-reuse barriers two tiles back.
 template <bool TA, bool TB, int EPI>
 __global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bm, int ldb, float *__restrict__ C,
                                                           int ldc, int M, int N, int K, const float *__restrict__ bias, int act,
@@ -122,98 +205,153 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restric
   int k_begin = 0, k_end = K;
   if (EPI == EPI_PARTIAL) { k_begin = blockIdx.z * k_per_slab; k_end = min(K, k_begin + k_per_slab); }
   const uint32_t sb = smem_u32(smb);
-  const uint32_t bar0 = sb + SM_BAR, bar_done = bar0 + 8 * NST;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + SM_BAR + 8 * NST + 8);
+  const uint32_t bar_free = sb + SM_BAR, bar_ready = bar_free + 16, bar_done = bar_free + 32;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + SM_BAR + 40);
   if (t == 0) {
-    for (int i = 0; i <= NST; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(1) : "memory");
+    for (int i = 0; i < 2; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_free + 8 * i), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_ready + 8 * i), "r"(NW) : "memory");
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_done), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (w == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64) : "memory");
+  if (w == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   const int n_kt = (k_end - k_begin + BK - 1) / BK;
-  // prologue of the copy pipeline: tiles 0 .. NST-2 in flight (one commit group per tile, empty past the end so that the counts stay uniform)
+  const bool worker = w < 8, a_side = w < 4;
+  const int tb = t - NTB;               // B-side thread index (warps 4..7)
+  if (worker) {   // copy pipeline: tiles 0 .. NST-2 in flight (one commit group per tile, empty past the end so that the counts stay uniform)
 #pragma unroll
-  for (int p = 0; p < NST - 1; ++p) {
-    if (p < n_kt) {
-      stage_tile<BM, TA>(sb + p * STAGE, A, lda, m0, M, k_begin + p * BK, k_end, vec_a != 0, t);
-      stage_tile<BN, !TB>(sb + p * STAGE + 2 * A_PLANE, Bm, ldb, n0, N, k_begin + p * BK, k_end, vec_b != 0, t);
+    for (int p = 0; p < NST - 1; ++p) {
+      if (p < n_kt) {
+        stage_a<TA>(sb + p * STAGE + OFF_A, A, lda, m0, M, k_begin + p * BK, k_end, vec_a != 0, t);
+        stage_b<TB>(sb + p * STAGE, Bm, ldb, n0, N, k_begin + p * BK, k_end, vec_b != 0, t);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  const uint32_t idesc = make_idesc(BM, BN);
   const bool do_bias = (EPI == EPI_PARTIAL) && bias_row && blockIdx.y == 0;
-  float bsum[2] = {0.f, 0.f};   // column sums of the B tile: chunk i of this thread always belongs to column n = 8 (t / 64 + 4 i) + t % 8
+  float bsum[2] = {0.f, 0.f};   // !TB split: thread (wb, l) owns columns l (even units) and 32 + l (odd units)
 
-  for (int kt = 0; kt < n_kt; ++kt) {
-    const int s = kt % NST;
-    unsigned char *st = smb + s * STAGE;
-    asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");   // this thread's copies of tile kt have landed
-    __syncthreads();                                                      // ... and everybody else's
-    // x -> hi (in place) | lo: every thread walks the planes linearly in 16-byte chunks (conflict-free)
-#pragma unroll
-    for (int i = 0; i < A_PLANE / 16 / NTH; ++i) {
-      float4 *ph = reinterpret_cast<float4 *>(st) + t + i * NTH;
-      const float4 x = *ph;
-      float4 h, l;
-      split(x.x, h.x, l.x); split(x.y, h.y, l.y); split(x.z, h.z, l.z); split(x.w, h.w, l.w);
-      *ph = h;
-      *(ph + A_PLANE / 16) = l;
-    }
-#pragma unroll
-    for (int i = 0; i < B_PLANE / 16 / NTH; ++i) {
-      float4 *ph = reinterpret_cast<float4 *>(st + 2 * A_PLANE) + t + i * NTH;
-      const float4 x = *ph;
-      if (do_bias) bsum[i] += (x.x + x.y) + (x.z + x.w);
-      float4 h, l;
-      split(x.x, h.x, l.x); split(x.y, h.y, l.y); split(x.z, h.z, l.z); split(x.w, h.w, l.w);
-      *ph = h;
-      *(ph + B_PLANE / 16) = l;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor cores
-    __syncthreads();
-    if (w == 0) {
+  if (!worker) {
+    // ================================================================ MMA issuer (warp 8)
+    const uint32_t idesc = make_idesc(BM, BN);
+    for (int kt = 0; kt < n_kt; ++kt) {
+      const int buf = kt & 1, s = kt % NST;
+      mbar_wait(bar_ready + 8 * buf, (uint32_t)((kt >> 1) & 1));   // the A buffer and the B planes of tile kt are complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
-        const uint32_t a_hi = sb + s * STAGE, a_lo = a_hi + A_PLANE, b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + B_PLANE;
+        const uint32_t a_hi = tmem + TM_A + 64 * buf, a_lo = a_hi + 32;
+        const uint64_t b_hi = make_desc(sb + s * STAGE), b_lo = make_desc(sb + s * STAGE + B_PLANE);
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) mma_tf32_ss(tmem, make_desc(a_lo + ks * 256), make_desc(b_hi + ks * 256), idesc, (kt || ks) ? 1u : 0u);
+        for (int ks = 0; ks < BK / 8; ++ks) mma_tf32_ts(tmem + TM_D, a_lo + 8 * ks, b_hi + 16 * ks, idesc, (kt || ks) ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) mma_tf32_ss(tmem, make_desc(a_hi + ks * 256), make_desc(b_lo + ks * 256), idesc, 1u);
+        for (int ks = 0; ks < BK / 8; ++ks) mma_tf32_ts(tmem + TM_D, a_hi + 8 * ks, b_lo + 16 * ks, idesc, 1u);
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) mma_tf32_ss(tmem, make_desc(a_hi + ks * 256), make_desc(b_hi + ks * 256), idesc, 1u);
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * s) : "memory");
+        for (int ks = 0; ks < BK / 8; ++ks) mma_tf32_ts(tmem + TM_D, a_hi + 8 * ks, b_hi + 16 * ks, idesc, 1u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_free + 8 * buf) : "memory");
         if (kt == n_kt - 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_done) : "memory");
       }
       __syncwarp();
     }
-    // refill: tile kt + NST - 1 goes into the stage tile kt - 1 used; its MMAs were committed one iteration ago
-    const int nt = kt + NST - 1;
-    if (nt < n_kt) {
-      const int sn = nt % NST;
-      if (kt >= 1) mbar_wait(bar0 + 8 * sn, (uint32_t)(((kt - 1) / NST) & 1));
-      stage_tile<BM, TA>(sb + sn * STAGE, A, lda, m0, M, k_begin + nt * BK, k_end, vec_a != 0, t);
-      stage_tile<BN, !TB>(sb + sn * STAGE + 2 * A_PLANE, Bm, ldb, n0, N, k_begin + nt * BK, k_end, vec_b != 0, t);
+  } else {
+    // ================================================================ workers (warps 0..7)
+    for (int kt = 0; kt < n_kt; ++kt) {
+      const int buf = kt & 1, s = kt % NST;
+      unsigned char *st = smb + s * STAGE;
+      asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");   // this thread's copies of tile kt have landed
+      asm volatile("bar.sync 1, %0;" ::"n"(NW) : "memory");                // ... and every other worker's
+      // refill first (asynchronous): tile kt + NST - 1 goes into the stage tile kt - 1 used.  Its raw tiles were read before the barrier
+      // above; its B planes are free once the MMAs of tile kt - 1 have completed.
+      const int nt = kt + NST - 1;
+      if (nt < n_kt) {
+        const uint32_t sn = sb + (nt % NST) * STAGE;
+        stage_a<TA>(sn + OFF_A, A, lda, m0, M, k_begin + nt * BK, k_end, vec_a != 0, t);
+        if (!TB) stage_b<TB>(sn, Bm, ldb, n0, N, k_begin + nt * BK, k_end, vec_b != 0, t);   // (into the raw region: nothing to wait for)
+      }
+      if (a_side) {   // thread = row = TMEM lane: its 32 k values -> hi | lo -> A buffer `buf` in tensor memory
+        uint32_t hi[32], lo[32];
+        if (!TA) {
+          const float4 *row = reinterpret_cast<const float4 *>(st + OFF_A + t * LDA_S * 4);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 x = row[q];
+            float h, l;
+            split(x.x, h, l); hi[4 * q] = __float_as_uint(h); lo[4 * q] = __float_as_uint(l);
+            split(x.y, h, l); hi[4 * q + 1] = __float_as_uint(h); lo[4 * q + 1] = __float_as_uint(l);
+            split(x.z, h, l); hi[4 * q + 2] = __float_as_uint(h); lo[4 * q + 2] = __float_as_uint(l);
+            split(x.w, h, l); hi[4 * q + 3] = __float_as_uint(h); lo[4 * q + 3] = __float_as_uint(l);
+          }
+        } else {
+          const float *col = reinterpret_cast<const float *>(st + OFF_A) + t;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) { float h, l; split(col[k * BM], h, l); hi[k] = __float_as_uint(h); lo[k] = __float_as_uint(l); }
+        }
+        if (kt >= 2) mbar_wait(bar_free + 8 * buf, (uint32_t)(((kt - 2) >> 1) & 1));   // the MMAs of tile kt - 2 have read this A buffer
+        const uint32_t ta = tmem + ((uint32_t)(32 * w) << 16) + TM_A + 64 * buf;
+        G5_ST32(ta, hi);
+        G5_ST32(ta + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      } else if (TB) {   // canonical hi plane: x -> hi (in place) | lo, walked linearly in 16-byte chunks (conflict-free)
+#pragma unroll
+        for (int i = 0; i < B_PLANE / 16 / NTB; ++i) {
+          float4 *ph = reinterpret_cast<float4 *>(st) + tb + i * NTB;
+          const float4 x = *ph;
+          float4 h, l;
+          split(x.x, h.x, l.x); split(x.y, h.y, l.y); split(x.z, h.z, l.z); split(x.w, h.w, l.w);
+          *ph = h;
+          *(ph + B_PLANE / 16) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor cores
+      } else {           // raw [k][n] -> canonical hi | lo: unit u = (n half, k chunk), lane = n: conflict-free reads and 16-byte stores
+        // the planes of this stage were last read by the MMAs of tile kt - NST; waiting for tile kt - 2 (the newest completed-or-pending phase
+        // of this barrier: an older phase must not be waited for by parity) covers it, the tensor pipe completes in order
+        if (kt >= 2) mbar_wait(bar_free + 8 * buf, (uint32_t)(((kt - 2) >> 1) & 1));
+        const float *raw = reinterpret_cast<const float *>(st + OFF_BR);
+        const int wb = tb >> 5;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int u = wb * 4 + i, n = 32 * (u & 1) + lane, kc = u >> 1;
+          float4 x;
+          x.x = raw[(4 * kc) * BN + n]; x.y = raw[(4 * kc + 1) * BN + n]; x.z = raw[(4 * kc + 2) * BN + n]; x.w = raw[(4 * kc + 3) * BN + n];
+          if (do_bias) bsum[i & 1] += (x.x + x.y) + (x.z + x.w);
+          float4 h, l;
+          split(x.x, h.x, l.x); split(x.y, h.y, l.y); split(x.z, h.z, l.z); split(x.w, h.w, l.w);
+          float4 *ph = reinterpret_cast<float4 *>(st + canon(n, 4 * kc));
+          *ph = h;
+          *(ph + B_PLANE / 16) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_ready + 8 * buf) : "memory");
+      if (TB && nt < n_kt) {   // the canonical planes of the stage tile kt - 1 used are free once its MMAs have completed (issued ~a split pass ago)
+        if (kt >= 1) mbar_wait(bar_free + 8 * ((kt - 1) & 1), (uint32_t)(((kt - 1) >> 1) & 1));
+        stage_b<TB>(sb + (nt % NST) * STAGE, Bm, ldb, n0, N, k_begin + nt * BK, k_end, vec_b != 0, t);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  // ---- epilogue: warp w reads TMEM lanes [32 (w & 3), +32) x columns [32 (w >> 2), +32), stages the C tile in shared memory (stage 0 is
-  //      free once every MMA has completed) and the CTA writes it out row by row: coalesced stores, coalesced reads of the mask operand
+  // ---- epilogue: warp w reads TMEM lanes [32 (w & 3), +32) x columns [32 (w >> 2), +32), stages the C tile in shared memory (the B stages
+  //      are free once every MMA has completed) and the CTA writes it out row by row: coalesced stores, coalesced reads of the mask operand
   float *Cz = C;
   if (EPI == EPI_PARTIAL) Cz = C + (int64_t)blockIdx.z * (int64_t)(M + (bias_row ? 1 : 0)) * ldc;
   if (n_kt > 0) {
     mbar_wait(bar_done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float *sC = reinterpret_cast<float *>(smb);
+    if (worker) {
     uint32_t v[32];
     const int c0 = 32 * (w >> 2);
-    const uint32_t taddr = tmem + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)c0;
+    const uint32_t taddr = tmem + ((uint32_t)(32 * (w & 3)) << 16) + TM_D + (uint32_t)c0;
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
         "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -223,42 +361,36 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restric
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    float *sC = reinterpret_cast<float *>(smb);
     const int r = 32 * (w & 3) + lane;
 #pragma unroll
     for (int j = 0; j < 32; ++j) sC[r * LDC_S + c0 + j] = __uint_as_float(v[j]);
+    }
     __syncthreads();
     for (int e = t; e < BM * BN; e += NTH) {
       const int row = e >> 6, col = e & 63;
-      const int gm = m0 + row, gn = n0 + col;
-      if (gm < M && gn < N) {
+      const int gr = m0 + row, gn = n0 + col;
+      if (gr < M && gn < N) {
         float x = sC[row * LDC_S + col];
         if (EPI == EPI_FWD) x = act_fwd_rt(act, x + bias[gn]);
-        if (EPI == EPI_BWD_DATA && yprev) x *= act_bwd_from_out(prev_act, yprev[(int64_t)gm * ldc + gn]);
-        Cz[(int64_t)gm * ldc + gn] = x;
+        if (EPI == EPI_BWD_DATA && yprev) x *= act_bwd_from_out(prev_act, yprev[(int64_t)gr * ldc + gn]);
+        Cz[(int64_t)gr * ldc + gn] = x;
       }
     }
   } else if (EPI == EPI_PARTIAL) {   // empty slab: zeros
     for (int e = t; e < BM * BN; e += NTH) {
-      const int gm = m0 + e / BN, gn = n0 + e % BN;
-      if (gm < M && gn < N) Cz[(int64_t)gm * ldc + gn] = 0.f;
+      const int gr = m0 + e / BN, gn = n0 + e % BN;
+      if (gr < M && gn < N) Cz[(int64_t)gr * ldc + gn] = 0.f;
     }
   }
-  if (do_bias) {   // bias gradient of this slab: column sums of B over k.  Chunk i of thread t is k-chunk (t % 64) / 8 of column 8 (t / 64 + 4 i) + t % 8
+  if (do_bias) {   // bias gradient of this slab: column sums of B over k (EPI_PARTIAL => !TB: B-side thread (wb, lane) holds columns lane and 32 + lane)
     float *sc = reinterpret_cast<float *>(smb + SM_BSUM);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) sc[((t & 63) >> 3) * BN + 8 * ((t >> 6) + 4 * i) + (t & 7)] = bsum[i];
+    if (worker && !a_side) { sc[(tb >> 5) * BN + lane] = bsum[0]; sc[(tb >> 5) * BN + 32 + lane] = bsum[1]; }
     __syncthreads();
-    if (t < BN && n0 + t < N) {
-      float sum = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) sum += sc[q * BN + t];   // fixed order: bit-reproducible
-      Cz[(int64_t)M * ldc + n0 + t] = sum;
-    }
+    if (t < BN && n0 + t < N) Cz[(int64_t)M * ldc + n0 + t] = (sc[t] + sc[BN + t]) + (sc[2 * BN + t] + sc[3 * BN + t]);   // fixed order: bit-reproducible
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64) : "memory");
+  if (w == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
 }
 
 template <bool TA, bool TB, int EPI>
@@ -269,9 +401,9 @@ int launch(crux_ctx *ctx, dim3 grid, const float *A, int lda, const float *B, in
     CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(gemm_tc5_kernel<TA, TB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     attr = true;
   }
-  // 16-byte copies need a k-contiguous operand whose rows start 16-byte aligned
-  const int vec_a = (!TA && lda % 4 == 0 && ((uintptr_t)A & 15) == 0) ? 1 : 0;
-  const int vec_b = (TB && ldb % 4 == 0 && ((uintptr_t)B & 15) == 0) ? 1 : 0;
+  // 16-byte copies need rows that start 16-byte aligned (along k or along m / n, whichever is contiguous)
+  const int vec_a = (lda % 4 == 0 && ((uintptr_t)A & 15) == 0) ? 1 : 0;
+  const int vec_b = (ldb % 4 == 0 && ((uintptr_t)B & 15) == 0) ? 1 : 0;
   gemm_tc5_kernel<TA, TB, EPI><<<grid, NTH, SM_TOTAL, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, act, yprev, prev_act, k_per_slab, bias_row, skip,
                                                                      vec_a, vec_b);
   CRUX_LAUNCHED(ctx);
