@@ -412,14 +412,15 @@ int launch(crux_ctx *ctx, dim3 grid, const float *A, int lda, const float *B, in
 
 }  // namespace
 
-// Opt-in (CRUX_GEMM_TC5=1, read per call: A/B runs and tests switch it).  Measured on B200 (scripts/bench_offpolicy.py): parity-green
-// through the whole generic-engine suite, but at the batch sizes of the off-policy configs the layer-by-layer engine is bound by its ~70
-// small dependent launches per update, not by the GEMM pipe -- SAC 376/17/256-256 at B = 2048: 1.60 ms per update with this kernel (64 CTAs,
-// element-wise staging through the operand accessors) against 1.17 ms with the 64 x 64 FFMA tiles (128 CTAs); pixel-DQN update 3.63 against
-// 3.29 ms.  It pays only once the layers of a network are fused around it (what mb_t5.cuh does for the 64-wide PPO networks).
+// Default for shapes that fill a tile (CRUX_GEMM_TC5=0 selects the FFMA tile kernel: read per call, A/B runs and tests switch it).
+// Measured on B200 (scripts/gemm_tc5_bench.py, scripts/sac_launches.py --time): 2048 x 256 x 2048 forward 57 us against 130 us (FFMA tiles),
+// 16384 x 256 x 256 41 against 70 us; SAC 376/17/256-256 at B = 2048: 0.81 ms per update against 1.17 ms.  The first version of this kernel
+// (both operands hi | lo through shared memory, lock-step phases) was SLOWER than the FFMA tiles (1.60 ms): profiles/r2_notes.md.
 bool gemm_tc5_eligible(int64_t M, int64_t N, int64_t K) {
   const char *on = getenv("CRUX_GEMM_TC5");
-  return on && on[0] == '1' && M >= 64 && N >= 16 && K >= 16;
+  if (on && on[0] == '0') return false;
+  if (on && on[0] == '1') return M >= 64 && N >= 16 && K >= 16;
+  return M >= 128 && N >= 32 && K >= 32;
 }
 // Dense forward: y[B][N] = act(x[B][K] W[K][N] + b)
 int gemm_tc5_fwd(crux_ctx *ctx, const float *x, int K, const float *W, int N, float *y, int64_t B, const float *b, int act, const int *skip) {
