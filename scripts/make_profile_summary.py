@@ -57,11 +57,23 @@ if os.path.exists(lp):
     for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append(f"| `{k}` | {c} | {v:.1f} | {v / c:.2f} | {100 * v / tot:.1f}% |")
     out.append("")
+lp2 = os.path.join(G, "launches_sac.csv")
+if os.path.exists(lp2):
+    shutil.copy(lp2, os.path.join(ROOT, "profiles", f"{rnd}_launches_sac.csv"))
+    agg, tot, n = launches(lp2)
+    out += [f"## One SAC update (BASELINE config[3]: 376-obs / 17-act, 256-256, batch 2048) — ncu launch list", "",
+            f"`ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off python scripts/sac_launches.py` "
+            f"(raw: `profiles/{rnd}_launches_sac.csv`).  {n} launches, {tot:.0f} us summed (cold-cache, serialised; live: `scripts/sac_launches.py --time`).", "",
+            "| kernel | launches | total us | avg us | share |", "|---|---:|---:|---:|---:|"]
+    for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
+        out.append(f"| `{k}` | {c} | {v:.1f} | {v / c:.2f} | {100 * v / tot:.1f}% |")
+    out.append("")
 for name, title in (("r2_prof_minibatch", "mb6::minibatch_kernel<0> (actor; dominant kernel of the step): every GEMM on tcgen05, TMEM accumulators"), ("prof_minibatch", "fused_minibatch_kernel (dominant kernel of the step)"), ("prof_gae_tma", "gae_tma_kernel at [2048, 16384] (738 MB): TMA-fed streaming scan, the kernel crux_fill_gae_returns runs for N >= 8192"),
                     ("prof_gae", "gae_returns_kernel at [2048, 16384] (738 MB): register-resident scan (narrow / short rollouts; CRUX_GAE=scan)"),
                     ("prof_fwd_tc5", "tc5::forward_kernel_tmem: value(V, s) over 131072 rows on tcgen05, activations resident in tensor memory"),
                     ("prof_mb5", "mb5::minibatch_kernel (opt-in CRUX_MB_TC5=1): PPO minibatch with the row GEMMs on tcgen05 / TMEM"),
                     ("r2_prof_tail", "reduce_adam_kernel: the single-launch update tail (partials -> gradient -> [LL exchange] -> Adam -> planes -> record), 187 CTAs of 128 threads"),
+                    ("r2_prof_gemm_tc5", "gemm_tc5_kernel: the layer engine's Dense GEMM on tcgen05 (SAC 376/17/256-256, B = 2048: forward 2048 x 256 x 393; A operand in tensor memory, 3xTF32)"),
                     ("r2_prof_rollout", "rollout_linquad_kernel (r2 capture)"), ("prof_rollout", "rollout_linquad_kernel: T = 32 vector steps of 4096 env streams in one persistent launch"),
                     ("prof_persist", "mbp::epoch_kernel (persistent 8-CTA cluster kernel, 256 minibatches of 128 rows in one launch)"),
                     ("prof_forward", "fused_forward_kernel")):
