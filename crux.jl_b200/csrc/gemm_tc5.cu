@@ -22,7 +22,7 @@ constexpr int BM = 128, BN = 64, BK = 32, NW = 256, NTH = 288, NTB = 128, NST = 
 constexpr int B_PLANE = BN * BK * 4;                                        // bytes
 constexpr int LDA_S = BK + 4;                                               // padded row of the raw A tile [m][k] (floats): rows and chunks conflict-free
 constexpr int A_RAW = BM * LDA_S * 4;                                       // 18 KB (the transposed form [k][m] needs 16 KB)
-constexpr int B_RAW = BK * BN * 4;                                          // raw B tile [k][n] of an n-contiguous source (8 KB)
+constexpr int B_RAW = BN * LDA_S * 4;                                       // raw B tile: [n][LDA_S] of a k-contiguous source (9 KB) or [k][BN] of an n-contiguous one (8 KB)
 constexpr int OFF_A = 2 * B_PLANE, OFF_BR = OFF_A + A_RAW;
 constexpr int STAGE = OFF_BR + B_RAW;                                       // B hi | B lo | A raw | B raw   (42 KB)
 constexpr int C_STAGE = BM * (BN + 1) * 4;                                  // the C tile staged for coalesced stores (padded rows)
@@ -133,12 +133,13 @@ __device__ __forceinline__ void stage_a(uint32_t dst, const float *__restrict__ 
     }
   }
 }
-// B tile.  TB (k-contiguous source, element (n, k) = B[(n0 + n) * ldb + k0 + k]): copied DIRECTLY into the canonical K-major hi plane (a 16-byte
-// chunk of four consecutive k of one row is one core-matrix row; lanes = 8 rows x 4 chunks) and split in place.  !TB (n-contiguous source,
-// element (n, k) = B[(k0 + k) * ldb + n0 + n]): copied raw as [k][BN] (16-byte chunks along n when aligned) and transposed by the split pass.
+// B raw tile.  TB (k-contiguous source, element (n, k) = B[(n0 + n) * ldb + k0 + k]) -> shared [n][LDA_S]; !TB (n-contiguous source, element
+// (n, k) = B[(k0 + k) * ldb + n0 + n]) -> shared [k][BN]; 16-byte chunks along the contiguous index when the rows are aligned.  The split pass
+// writes the canonical K-major hi | lo planes from it (transposing in the !TB case), so a copy never waits for the tensor pipe.
 template <bool TB>
 __device__ __forceinline__ void stage_b(uint32_t stage, const float *__restrict__ Bm, int ldb, int n0, int N, int k0, int k_end, bool vec, int t) {
   if (TB) {
+    const uint32_t dst = stage + OFF_BR;
     if (vec) {         // 64 rows x 8 chunks = 512 chunks, 2 per thread
       const int w = t >> 5, l = t & 31;
 #pragma unroll
@@ -146,7 +147,7 @@ __device__ __forceinline__ void stage_b(uint32_t stage, const float *__restrict_
         const int u = w * 2 + i, row = (u >> 1) * 8 + (l & 7), kc = (u & 1) * 4 + (l >> 3);
         const int gr = n0 + row, gk = k0 + 4 * kc;
         const int nb = (gr < N && gk < k_end) ? min(16, 4 * (k_end - gk)) : 0;
-        cp16(stage + canon(row, 4 * kc), nb ? (const void *)(Bm + (int64_t)gr * ldb + gk) : (const void *)Bm, nb);
+        cp16(dst + (row * LDA_S + 4 * kc) * 4, nb ? (const void *)(Bm + (int64_t)gr * ldb + gk) : (const void *)Bm, nb);
       }
     } else {           // thread t: k = t % 32, row = t / 32 + 8 i
       const int k = t & (BK - 1), rb = t >> 5;
@@ -156,7 +157,7 @@ __device__ __forceinline__ void stage_b(uint32_t stage, const float *__restrict_
       for (int i = 0; i < 8; ++i) {
         const int row = rb + 8 * i;
         const bool ok = k_ok && n0 + row < N;
-        cp4(stage + canon(row, k), ok ? (const void *)(g + (int64_t)(8 * i) * ldb) : (const void *)Bm, ok ? 4 : 0);
+        cp4(dst + (row * LDA_S + k) * 4, ok ? (const void *)(g + (int64_t)(8 * i) * ldb) : (const void *)Bm, ok ? 4 : 0);
       }
     }
   } else {
@@ -274,8 +275,9 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restric
       if (nt < n_kt) {
         const uint32_t sn = sb + (nt % NST) * STAGE;
         stage_a<TA>(sn + OFF_A, A, lda, m0, M, k_begin + nt * BK, k_end, vec_a != 0, t);
-        if (!TB) stage_b<TB>(sn, Bm, ldb, n0, N, k_begin + nt * BK, k_end, vec_b != 0, t);   // (into the raw region: nothing to wait for)
+        stage_b<TB>(sn, Bm, ldb, n0, N, k_begin + nt * BK, k_end, vec_b != 0, t);
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
       if (a_side) {   // thread = row = TMEM lane: its 32 k values -> hi | lo -> A buffer `buf` in tensor memory
         uint32_t hi[32], lo[32];
         if (!TA) {
@@ -300,13 +302,16 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restric
         G5_ST32(ta + 32, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      } else if (TB) {   // canonical hi plane: x -> hi (in place) | lo, walked linearly in 16-byte chunks (conflict-free)
+      } else if (TB) {   // raw [n][LDA_S] -> canonical hi | lo: lanes = 8 rows x 4 chunks, conflict-free 16-byte reads and stores
+        if (kt >= 2) mbar_wait(bar_free + 8 * buf, (uint32_t)(((kt - 2) >> 1) & 1));   // (see the !TB branch)
+        const int wb = tb >> 5;
 #pragma unroll
-        for (int i = 0; i < B_PLANE / 16 / NTB; ++i) {
-          float4 *ph = reinterpret_cast<float4 *>(st) + tb + i * NTB;
-          const float4 x = *ph;
+        for (int i = 0; i < 4; ++i) {
+          const int u = wb * 4 + i, n = (u >> 1) * 8 + (lane & 7), kc = (u & 1) * 4 + (lane >> 3);
+          const float4 x = *reinterpret_cast<const float4 *>(st + OFF_BR + (n * LDA_S + 4 * kc) * 4);
           float4 h, l;
           split(x.x, h.x, l.x); split(x.y, h.y, l.y); split(x.z, h.z, l.z); split(x.w, h.w, l.w);
+          float4 *ph = reinterpret_cast<float4 *>(st + canon(n, 4 * kc));
           *ph = h;
           *(ph + B_PLANE / 16) = l;
         }
@@ -332,11 +337,6 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restric
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_ready + 8 * buf) : "memory");
-      if (TB && nt < n_kt) {   // the canonical planes of the stage tile kt - 1 used are free once its MMAs have completed (issued ~a split pass ago)
-        if (kt >= 1) mbar_wait(bar_free + 8 * ((kt - 1) & 1), (uint32_t)(((kt - 1) >> 1) & 1));
-        stage_b<TB>(sb + (nt % NST) * STAGE, Bm, ldb, n0, N, k_begin + nt * BK, k_end, vec_b != 0, t);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
