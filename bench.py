@@ -454,6 +454,70 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def run_sac(args):
+    """Secondary line (not the headline): one SAC value_training epoch (off_policy.jl:66-111, rl/sac.jl:4-52) of BASELINE configs[3] --
+    376-obs / 17-act, 256-256 networks, batch 2048 -- on one GPU: target, temperature, double-Q critics, actor, polyak = one crux_sac_train
+    call on a device-resident batch.  The Dense GEMMs run on tcgen05 (csrc/gemm_tc5.cu, 3xTF32); roofline = algorithmic FLOPs against the
+    measured bf16 peak / 3 (three TF32 passes per product)."""
+    import torch
+    import crux_b200 as crux
+    from crux_b200.device import ptr
+    ctx = crux.Context(0)
+    obs, act, hid, Bs = 376, 17, 256, 2048
+    rng = np.random.default_rng(4)
+    g = torch.Generator(device=ctx.device).manual_seed(3)
+    D = crux.Dense
+    Apol = crux.SquashedGaussianPolicy(crux.ContinuousNetwork(crux.Chain(D(obs, hid, crux.relu, rng=rng), D(hid, hid, crux.relu, rng=rng), D(hid, 2 * act, rng=rng)), ctx=ctx))
+    Q = lambda: crux.ContinuousNetwork(crux.Chain(D(obs + act, hid, crux.relu, rng=rng), D(hid, hid, crux.relu, rng=rng), D(hid, 1, rng=rng)), ctx=ctx)
+    S4 = crux.SAC(crux.ActorCritic(Apol, crux.DoubleNetwork(Q(), Q())), crux.ContinuousSpace(obs), N=10, dN=1, c_opt=dict(batch_size=Bs, epochs=1),
+                  buffer_size=Bs, buffer_init=Bs)
+    s = torch.randn((Bs, obs), device=ctx.device, generator=g)
+    a = torch.tanh(torch.randn((Bs, act), device=ctx.device, generator=g))
+    sp = torch.randn((Bs, obs), device=ctx.device, generator=g)
+    r = torch.randn(Bs, device=ctx.device, generator=g)
+    dn = (torch.rand(Bs, device=ctx.device, generator=g) < 0.01).to(torch.uint8)
+    k = [0]
+
+    def step():
+        k[0] += 1
+        ctx.check(ctx.lib.crux_sac_train(S4._sac, ptr(s), ptr(a), ptr(sp), ptr(r), ptr(dn), Bs, np.float32(0.99), None, None, None, 4, 3 * k[0], None, None))
+    for _ in range(max(args.warmup, 3)):
+        step()
+    l0 = ctx.launch_count()
+    cs = ClockSampler(0); cs.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    blocks, t_start = [], time.time()
+    while True:                      # --steps updates per block, repeated to >= 2 s; the median block is reported
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record(); torch.cuda.synchronize()
+        blocks.append(e0.elapsed_time(e1) / args.steps)
+        if time.time() - t_start > 2.0:
+            break
+    clocks = cs.stop()
+    ms = float(np.median(blocks))
+    launches = (ctx.launch_count() - l0) // (len(blocks) * args.steps)
+    fa = 2 * (obs * hid + hid * hid + hid * 2 * act)
+    fq = 2 * ((obs + act) * hid + hid * hid + hid)
+    flops = Bs * (5 * fa + 12 * fq)       # SURVEY 8d: ~5 actor-forward + ~12 critic-forward equivalents per update
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        peak, src = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"])) / 3.0, "measured dense bf16 sustained / 3 (3xTF32)"
+    except Exception:
+        peak, src = 1500.0 / 3.0, "fallback (B200_PROFILING.md) / 3"
+    tf = flops / (ms * 1e-3) / 1e12
+    print(json.dumps({"metric": "SAC updates/sec (376-obs/17-act, 256-256, batch 2048)", "value": 1e3 / ms, "unit": "updates/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "config": {"workload": "SAC value_training epoch, BASELINE configs[3], device-resident batch (inputs larger than "
+                      "nothing: 6.3 MB batch, L2-resident by design -- a replay sample is consumed where it was gathered)", "batch": Bs},
+                      "clocks": clocks, "gpu_launches": int(launches), "blocks": len(blocks),
+                      "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None, "peak_source": src,
+                                   "kernel": "gemm_tc5_kernel (csrc/gemm_tc5.cu): 33 of the 67 launches of an update, ~70 % of its time (profiles/r2_ncu_summary.md)"},
+                      "samples_per_s": Bs * 1e3 / ms}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -461,12 +525,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-worker"])
     ap.add_argument("--threads", type=int, default=1, help="cpu-worker only (set by cpu_run)")
+    ap.add_argument("--workload", default="ppo", choices=["ppo", "sac"],
+                    help="ppo: the headline line (BASELINE configs[1]); sac: a secondary line for configs[3] (one GPU, --impl ours only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "cpu-worker":
         cpu_worker(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.workload == "sac":
+        run_sac(args)
     else:
         run_ours(args)
 
