@@ -199,7 +199,10 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restric
                                                           int ldc, int M, int N, int K, const float *__restrict__ bias, int act,
                                                           const float *__restrict__ yprev, int prev_act, int k_per_slab, int bias_row,
                                                           const int *__restrict__ skip, int vec_a, int vec_b) {
-  if (skip && *skip) return;
+  // Programmatic dependent launch: the next kernel of the stream may be scheduled at once (onto SMs this grid leaves free -- 64 CTAs at the
+  // off-policy batch sizes); this kernel's own on-chip prologue (barriers, tensor-memory allocation) runs under the tail of its predecessor,
+  // and only then waits for the predecessor's results (griddepcontrol.wait below: everything before it touches no global memory).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(1024) unsigned char smb[];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
@@ -221,7 +224,9 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restric
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  const int n_kt = (k_end - k_begin + BK - 1) / BK;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // the predecessor's activations / gradients / stop flag are complete and visible
+  const bool skipped = skip && *skip;                   // uniform over the grid; the allocation above is still released below
+  const int n_kt = skipped ? 0 : (k_end - k_begin + BK - 1) / BK;
   const bool worker = w < 8, a_side = w < 4;
   const int tb = t - NTB;               // B-side thread index (warps 4..7)
   if (worker) {   // copy pipeline: tiles 0 .. NST-2 in flight (one commit group per tile, empty past the end so that the counts stay uniform)
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restric
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  const bool do_bias = (EPI == EPI_PARTIAL) && bias_row && blockIdx.y == 0;
+  const bool do_bias = (EPI == EPI_PARTIAL) && bias_row && blockIdx.y == 0 && !skipped;
   float bsum[2] = {0.f, 0.f};   // !TB split: thread (wb, l) owns columns l (even units) and 32 + l (odd units)
 
   if (!worker) {
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restric
         Cz[(int64_t)gr * ldc + gn] = x;
       }
     }
-  } else if (EPI == EPI_PARTIAL) {   // empty slab: zeros
+  } else if (EPI == EPI_PARTIAL && !skipped) {   // empty slab: zeros
     for (int e = t; e < BM * BN; e += NTH) {
       const int gr = m0 + e / BN, gn = n0 + e % BN;
       if (gr < M && gn < N) Cz[(int64_t)gr * ldc + gn] = 0.f;
@@ -404,8 +409,16 @@ int launch(crux_ctx *ctx, dim3 grid, const float *A, int lda, const float *B, in
   // 16-byte copies need rows that start 16-byte aligned (along k or along m / n, whichever is contiguous)
   const int vec_a = (lda % 4 == 0 && ((uintptr_t)A & 15) == 0) ? 1 : 0;
   const int vec_b = (ldb % 4 == 0 && ((uintptr_t)B & 15) == 0) ? 1 : 0;
-  gemm_tc5_kernel<TA, TB, EPI><<<grid, NTH, SM_TOTAL, ctx->stream>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, act, yprev, prev_act, k_per_slab, bias_row, skip,
-                                                                     vec_a, vec_b);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(NTH); cfg.dynamicSmemBytes = SM_TOTAL; cfg.stream = ctx->stream;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  la[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = getenv("CRUX_NO_PDL") == nullptr;
+  cfg.attrs = la; cfg.numAttrs = pdl ? 1 : 0;
+  CRUX_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<TA, TB, EPI>, A, lda, B, ldb, C, ldc, M, N, K, bias, act, yprev, prev_act, k_per_slab, bias_row, skip,
+                                          vec_a, vec_b));
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;
 }
