@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 32, NW = 256, NTH = 288, NTB = 128, NST = 4;   // NW worker threads (warps 0..7) + the MMA issuer warp 8
+constexpr int BM = 128, BN = 64, BK = 32, NW = 256, NTH = 288, NTB = 128;   // NW worker threads (warps 0..7) + the MMA issuer warp 8
 constexpr int B_PLANE = BN * BK * 4;                                        // bytes
 constexpr int LDA_S = BK + 4;                                               // padded row of the raw A tile [m][k] (floats): rows and chunks conflict-free
 constexpr int A_RAW = BM * LDA_S * 4;                                       // 18 KB (the transposed form [k][m] needs 16 KB)
@@ -26,10 +26,14 @@ constexpr int B_RAW = BN * LDA_S * 4;                                       // r
 constexpr int OFF_A = 2 * B_PLANE, OFF_BR = OFF_A + A_RAW;
 constexpr int STAGE = OFF_BR + B_RAW;                                       // B hi | B lo | A raw | B raw   (42 KB)
 constexpr int C_STAGE = BM * (BN + 1) * 4;                                  // the C tile staged for coalesced stores (padded rows)
-constexpr int SM_B = C_STAGE > NST * STAGE ? C_STAGE : NST * STAGE;
-constexpr int SM_BAR = SM_B;                                                // bar_free[2], bar_ready[2], bar_done, tmem slot
-constexpr int SM_BSUM = SM_BAR + 64;                                        // [4][64] column-sum scratch (EPI_PARTIAL)
-constexpr int SM_TOTAL = SM_BSUM + 4 * BN * 4;
+// NST stages of one k-tile each: 4 (172 KB, one CTA per SM) for grids that leave SMs idle anyway, 2 (86 KB, two CTAs per SM at <= 112 registers)
+// for grids of several waves, where a second resident CTA hides the per-k-tile latencies of the first
+template <int NST> struct Smem {
+  static constexpr int B = C_STAGE > NST * STAGE ? C_STAGE : NST * STAGE;
+  static constexpr int BAR = B;                                             // bar_free[2], bar_ready[2], bar_done, tmem slot
+  static constexpr int BSUM = BAR + 64;                                     // [4][64] column-sum scratch (EPI_PARTIAL)
+  static constexpr int TOTAL = BSUM + 4 * BN * 4;
+};
 constexpr int LDC_S = BN + 1;
 // tensor memory: accumulator D [128 lanes][64 columns] | two A buffers, each hi [32 columns] | lo [32 columns]
 constexpr uint32_t TM_D = 0, TM_A = 64, TM_COLS = 256;
@@ -194,8 +198,8 @@ __device__ __forceinline__ void stage_b(uint32_t stage, const float *__restrict_
 //   * warp 8 does nothing but wait for "operands of tile kt ready" (mbarrier, 256 arrivals) and issue 3 passes x 4 k-steps of
 //     tcgen05.mma.kind::tf32 (A from tensor memory, B from shared memory): the workers never wait for the tensor pipe except through the
 //     buffer-reuse barriers two tiles back.
-template <bool TA, bool TB, int EPI>
-__global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bm, int ldb, float *__restrict__ C,
+template <bool TA, bool TB, int EPI, int NST>
+__global__ void __launch_bounds__(NTH, NST == 2 ? 2 : 1) gemm_tc5_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bm, int ldb, float *__restrict__ C,
                                                           int ldc, int M, int N, int K, const float *__restrict__ bias, int act,
                                                           const float *__restrict__ yprev, int prev_act, int k_per_slab, int bias_row,
                                                           const int *__restrict__ skip, int vec_a, int vec_b) {
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restric
   int k_begin = 0, k_end = K;
   if (EPI == EPI_PARTIAL) { k_begin = blockIdx.z * k_per_slab; k_end = min(K, k_begin + k_per_slab); }
   const uint32_t sb = smem_u32(smb);
+  constexpr int SM_BAR = Smem<NST>::BAR, SM_BSUM = Smem<NST>::BSUM;
   const uint32_t bar_free = sb + SM_BAR, bar_ready = bar_free + 16, bar_done = bar_free + 32;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + SM_BAR + 40);
   if (t == 0) {
@@ -398,12 +403,12 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc5_kernel(const float *__restric
   if (w == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
 }
 
-template <bool TA, bool TB, int EPI>
-int launch(crux_ctx *ctx, dim3 grid, const float *A, int lda, const float *B, int ldb, float *C, int ldc, int M, int N, int K, const float *bias, int act,
-           const float *yprev, int prev_act, int k_per_slab, int bias_row, const int *skip) {
+template <bool TA, bool TB, int EPI, int NST>
+int launch_ns(crux_ctx *ctx, dim3 grid, const float *A, int lda, const float *B, int ldb, float *C, int ldc, int M, int N, int K, const float *bias, int act,
+              const float *yprev, int prev_act, int k_per_slab, int bias_row, const int *skip) {
   static bool attr = false;
   if (!attr) {
-    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(gemm_tc5_kernel<TA, TB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    CRUX_CHECK_CUDA(ctx, cudaFuncSetAttribute(gemm_tc5_kernel<TA, TB, EPI, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<NST>::TOTAL));
     attr = true;
   }
   // 16-byte copies need rows that start 16-byte aligned (along k or along m / n, whichever is contiguous)
@@ -411,23 +416,33 @@ int launch(crux_ctx *ctx, dim3 grid, const float *A, int lda, const float *B, in
   const int vec_b = (ldb % 4 == 0 && ((uintptr_t)B & 15) == 0) ? 1 : 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid; cfg.blockDim = dim3(NTH); cfg.dynamicSmemBytes = SM_TOTAL; cfg.stream = ctx->stream;
+  cfg.gridDim = grid; cfg.blockDim = dim3(NTH); cfg.dynamicSmemBytes = Smem<NST>::TOTAL; cfg.stream = ctx->stream;
   cudaLaunchAttribute la[1];
   la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   la[0].val.programmaticStreamSerializationAllowed = 1;
   static const bool pdl = getenv("CRUX_NO_PDL") == nullptr;
   cfg.attrs = la; cfg.numAttrs = pdl ? 1 : 0;
-  CRUX_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<TA, TB, EPI>, A, lda, B, ldb, C, ldc, M, N, K, bias, act, yprev, prev_act, k_per_slab, bias_row, skip,
+  CRUX_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<TA, TB, EPI, NST>, A, lda, B, ldb, C, ldc, M, N, K, bias, act, yprev, prev_act, k_per_slab, bias_row, skip,
                                           vec_a, vec_b));
   CRUX_LAUNCHED(ctx);
   return CRUX_OK;
+}
+template <bool TA, bool TB, int EPI>
+int launch(crux_ctx *ctx, dim3 grid, const float *A, int lda, const float *B, int ldb, float *C, int ldc, int M, int N, int K, const float *bias, int act,
+           const float *yprev, int prev_act, int k_per_slab, int bias_row, const int *skip) {
+  // several waves of CTAs: two per SM (2 stages each) overlap each other's k-tile latencies; CRUX_G5_STAGES=2|4 forces a variant (A/B runs)
+  const char *env = getenv("CRUX_G5_STAGES");
+  const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
+  const bool two = env ? env[0] == '2' : ctas > (int64_t)ctx->num_sms;
+  if (two) return launch_ns<TA, TB, EPI, 2>(ctx, grid, A, lda, B, ldb, C, ldc, M, N, K, bias, act, yprev, prev_act, k_per_slab, bias_row, skip);
+  return launch_ns<TA, TB, EPI, 4>(ctx, grid, A, lda, B, ldb, C, ldc, M, N, K, bias, act, yprev, prev_act, k_per_slab, bias_row, skip);
 }
 
 }  // namespace
 
 // Default for shapes that fill a tile (CRUX_GEMM_TC5=0 selects the FFMA tile kernel: read per call, A/B runs and tests switch it).
 // Measured on B200 (scripts/gemm_tc5_bench.py, scripts/sac_launches.py --time): 2048 x 256 x 2048 forward 57 us against 130 us (FFMA tiles),
-// 16384 x 256 x 256 41 against 70 us; SAC 376/17/256-256 at B = 2048: 0.81 ms per update against 1.17 ms.  The first version of this kernel
+// 16384 x 256 x 256 31 against 70 us (two 2-stage CTAs per SM: 69 TFLOP/s of fp32-accurate GEMM); SAC 376/17/256-256 at B = 2048: 0.81 ms per update against 1.17 ms.  The first version of this kernel
 // (both operands hi | lo through shared memory, lock-step phases) was SLOWER than the FFMA tiles (1.60 ms): profiles/r2_notes.md.
 bool gemm_tc5_eligible(int64_t M, int64_t N, int64_t K) {
   const char *on = getenv("CRUX_GEMM_TC5");
