@@ -198,16 +198,32 @@ ppo_head_cat_kernel(const float *__restrict__ z, const float *__restrict__ a, co
 }
 
 // one block: reduce head partials -> gradient tail (logΣ gradient, sums).  sums: [obj, kl, clip, adv, ret, count]
+// launched with 8 x 32 threads: lane = entry k, warp w adds blocks w, w + 8, ... (eight loads in flight per lane), the eight warp sums are
+// combined in warp order: fixed order, bit-reproducible.  (One thread per entry walking every block in turn took 20 us for 256 blocks.)
 __global__ void ppo_finalize_kernel(const double *__restrict__ part, int nblocks, int A, int64_t bm, float lambda_e,
                                     float *__restrict__ ls_grad, float *__restrict__ sums, const int *__restrict__ skip) {
   if (skip && *skip) return;
-  const int k = threadIdx.x;
-  if (k >= 8 + A) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * HEAD_STRIDE + k];
-  if (k < 5 || k == 6 || k == 7) sums[k] = (float)s;   // [7]: sum of per-sample entropies (categorical actor; 0 otherwise)
-  else if (k == 5) sums[5] = (float)bm;
-  else if (k >= 8) ls_grad[k - 8] = (float)s;  // entropy term added after the all-reduce (record kernel)
+  __shared__ double sh[8][32];
+  const int k = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k0 = 0; k0 < 8 + A; k0 += 32) {   // (A <= 64: at most three rounds)
+    const int kk = k0 + k;
+    double s = 0.0;
+    if (kk < 8 + A) {
+#pragma unroll 8
+      for (int b = w; b < nblocks; b += 8) s += part[(int64_t)b * HEAD_STRIDE + kk];
+    }
+    sh[w][k] = s;
+    __syncthreads();
+    if (w == 0 && kk < 8 + A) {
+      s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += sh[q][k];
+      if (kk < 5 || kk == 6 || kk == 7) sums[kk] = (float)s;   // [7]: sum of per-sample entropies (categorical actor; 0 otherwise)
+      else if (kk == 5) sums[5] = (float)bm;
+      else ls_grad[kk - 8] = (float)s;  // entropy term added after the all-reduce (record kernel)
+    }
+    __syncthreads();
+  }
   (void)lambda_e;
 }
 
@@ -306,12 +322,11 @@ __global__ void critic_head_kernel(const float *__restrict__ v, const float *__r
     if (threadIdx.x == 0) part[blockIdx.x] = s;
   }
 }
-__global__ void critic_finalize_kernel(const double *__restrict__ part, int n, int64_t bm, float *__restrict__ sums) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0;
-    for (int i = 0; i < n; ++i) s += part[i];
-    sums[0] = (float)s; sums[5] = (float)bm;
-  }
+__global__ void critic_finalize_kernel(const double *__restrict__ part, int n, int64_t bm, float *__restrict__ sums) {   // one warp
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) s += part[i];
+  s = warp_sum_d(s);   // fixed shuffle tree: bit-reproducible
+  if (threadIdx.x == 0) { sums[0] = (float)s; sums[5] = (float)bm; }
 }
 __global__ void critic_record_kernel(const float *__restrict__ sums, float *__restrict__ rec) {
   rec[CRUX_PPO_LOSS] = sums[0] / sums[5];
@@ -517,7 +532,7 @@ static int ppo_update_impl(crux_gaussian *actor, crux_mlp *critic, const float *
                                                      inv_bg, hp->eps_clip, hp->lambda_p, hp->a2c, mu->dz[L], part, skip,
                                                      lg ? mb_cadv : nullptr, lg ? lg->state + 4 : nullptr);
         CRUX_LAUNCHED(ctx);
-        ppo_finalize_kernel<<<1, 128, 0, ctx->stream>>>(part, hb, cat ? 0 : A, bm, hp->lambda_e, tail_ls_grad(mu), tail_sums(mu), skip);
+        ppo_finalize_kernel<<<1, 256, 0, ctx->stream>>>(part, hb, cat ? 0 : A, bm, hp->lambda_e, tail_ls_grad(mu), tail_sums(mu), skip);
         CRUX_LAUNCHED(ctx);
         rc = mlp_backward(mu, mb_s, bm, mu->dz[L], false, false, true, skip); if (rc) return rc;
       }
