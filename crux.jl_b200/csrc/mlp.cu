@@ -120,7 +120,17 @@ __global__ void reduce_partials_kernel(PartialTable t, float *__restrict__ grads
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.count[l]; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     const float *p = t.src[l] + i;
-    for (int z = 0; z < t.slabs[l]; ++z) s += p[(int64_t)z * t.count[l]];
+    const int nz = t.slabs[l];
+    const int64_t cnt = t.count[l];
+    int z = 0;
+    for (; z + 8 <= nz; z += 8) {   // eight loads in flight, added in slab order (the sum is that of the plain loop, bit for bit)
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(p + (int64_t)(z + u) * cnt);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; z < nz; ++z) s += __ldcs(p + (int64_t)z * cnt);
     float *d = grads + t.dst_off[l] + i;
     *d = accumulate ? (*d + s) : s;
   }
@@ -252,7 +262,7 @@ int mlp_ensure_workspace(crux_mlp *mlp, int64_t B) {
   return CRUX_OK;
 }
 
-// Dense forward with a handful of outputs (the 256 -> 1 head of a critic): y[b][n] = act(sum_k x[b][k] W[k][n] + bias[n]), N <= 4.
+// Dense forward with a handful of outputs (the 256 -> 1 head of a critic, a 6-action head): y[b][n] = act(sum_k x[b][k] W[k][n] + bias[n]), N <= 8.
 // One warp per row: lanes stride k (coalesced reads of the row), a shuffle tree per output.  The 64 x 64 tile kernel spends 26 us on the
 // 2048 x 256 x 1 head of the SAC critics (32 CTAs, 63 of 64 tile columns idle); this takes the time of reading x once.
 template <int NO>
@@ -286,13 +296,17 @@ static int launch_fwd_layer(crux_mlp *mlp, int l /*1-based*/, const float *x, in
   const float *W = mlp->params + mlp->w_off[l - 1];
   const float *b = W + (int64_t)K * N;
   if (gemm_tc5_eligible(B, N, K)) return gemm_tc5_fwd(ctx, x, K, W, N, y, B, b, mlp->acts[l - 1], skip);
-  if (N <= 4 && K >= 64 && B >= 256 && !getenv("CRUX_NO_SKINNY")) {   // (small problems stay on the tile kernel: same launch, nothing to gain)
+  if (N <= 8 && K >= 64 && B >= 256 && !getenv("CRUX_NO_SKINNY")) {   // (small problems stay on the tile kernel: same launch, nothing to gain)
     const unsigned g = (unsigned)cdiv(B, 8);
     switch (N) {
       case 1: skinny_fwd_kernel<1><<<g, 256, 0, ctx->stream>>>(x, K, W, b, y, B, mlp->acts[l - 1], skip); break;
       case 2: skinny_fwd_kernel<2><<<g, 256, 0, ctx->stream>>>(x, K, W, b, y, B, mlp->acts[l - 1], skip); break;
       case 3: skinny_fwd_kernel<3><<<g, 256, 0, ctx->stream>>>(x, K, W, b, y, B, mlp->acts[l - 1], skip); break;
-      default: skinny_fwd_kernel<4><<<g, 256, 0, ctx->stream>>>(x, K, W, b, y, B, mlp->acts[l - 1], skip); break;
+      case 4: skinny_fwd_kernel<4><<<g, 256, 0, ctx->stream>>>(x, K, W, b, y, B, mlp->acts[l - 1], skip); break;
+      case 5: skinny_fwd_kernel<5><<<g, 256, 0, ctx->stream>>>(x, K, W, b, y, B, mlp->acts[l - 1], skip); break;
+      case 6: skinny_fwd_kernel<6><<<g, 256, 0, ctx->stream>>>(x, K, W, b, y, B, mlp->acts[l - 1], skip); break;
+      case 7: skinny_fwd_kernel<7><<<g, 256, 0, ctx->stream>>>(x, K, W, b, y, B, mlp->acts[l - 1], skip); break;
+      default: skinny_fwd_kernel<8><<<g, 256, 0, ctx->stream>>>(x, K, W, b, y, B, mlp->acts[l - 1], skip); break;
     }
     CRUX_LAUNCHED(ctx);
     return CRUX_OK;
