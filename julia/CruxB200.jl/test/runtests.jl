@@ -1,7 +1,7 @@
 # Run with:  LIBCRUX_CUDA=/path/to/crux.jl_b200/lib/libcrux_cuda.so julia --project -e 'using Pkg; Pkg.test()'
 # (Julia is not part of the build image of this repository: these tests have been written against include/crux_cuda.h and the numbers
 #  `tests/_build/abi_smoke layout` prints; tests/test_abi_symbols.py checks that the sizes below still match the C structs.)
-using Test, CruxB200, Crux, Flux, POMDPs, CUDA
+using Test, CruxB200, Crux, Flux, POMDPs, POMDPModels, CUDA
 
 @testset "C struct layouts (tests/abi_smoke.c layout)" begin
     @test sizeof(CruxB200.PPOHp) == 56
@@ -43,6 +43,24 @@ if CUDA.functional()
         @test Flux.params(π.A.μ.network)[1] != before
         env = DeviceLinQuad(m, 64; max_steps=50)
         @test solve(𝒮, env) === π
+    end
+    @testset "PPO with a categorical actor on 16 grid-world streams (examples/rl/cartpole.jl:8-9,17-25)" begin
+        mdp = SimpleGridWorld(size=(10, 10), tprob=0.7)
+        S = state_space(mdp)
+        as = [actions(mdp)...]
+        A = DiscreteNetwork(Chain(Dense(Crux.dim(S)..., 64, relu), Dense(64, 64, relu), Dense(64, length(as))), as)
+        V = ContinuousNetwork(Chain(Dense(Crux.dim(S)..., 64, relu), Dense(64, 64, relu), Dense(64, 1)))
+        before = deepcopy(Flux.params(A.network)[1])
+        𝒮 = PPO(π=ActorCritic(A, V), S=S, N=3 * 256, ΔN=256, max_steps=30, a_opt=(epochs=2, batch_size=64), c_opt=(epochs=2, batch_size=64),
+                log=(period=256, fns=[], verbose=false))
+        solve(𝒮, [mdp for _ in 1:16])
+        @test 𝒮.i == 3 * 256
+        @test Flux.params(A.network)[1] != before
+        c = CruxB200.DevCategorical(A)
+        s = CUDA.rand(Float32, 2, 100)
+        idx, oh, lp = exploration(c, s; seed=1, ctr=0)
+        @test all(sum(Array(oh), dims=1) .== 1) && all(Array(lp) .<= 0)
+        @test Array(lp) ≈ logpdf(A, Array(s), Array(oh)) rtol = 1e-5 atol = 1e-5
     end
     @testset "replay buffer ring semantics (test/experience_buffer_tests.jl:121-147)" begin
         b = DevBuffer(ContinuousSpace(2), ContinuousSpace(1), 5)
