@@ -7,13 +7,14 @@
 //     EPI_FWD       C = act(acc + bias[n])                                   Dense forward            (policies.jl:94-96)
 //     EPI_BWD_DATA  C = acc * act'(yprev[m][n])                              data gradient            (Zygote pullback of a Dense)
 //     EPI_PARTIAL   slab z of the split-K weight gradient [z][M + 1][N]: rows 0..M-1 = acc, row M = column sums of B (bias gradient)
-// One CTA = a 128 x 64 tile of C: TMEM lanes = rows (M = 128 MMAs), 64 fp32 accumulator columns.  Per 32-wide k-tile all 256 threads
-// fetch their elements of the A and B tiles through the accessors above (coalesced along whichever index is contiguous), split them
-// x = hi + lo (hi = rna_tf32(x)) and store both halves as canonical no-swizzle K-major planes (core matrix = 8 rows x 16 B); one elected
-// lane then issues 3 passes x 4 k-steps of tcgen05.mma.kind::tf32 (M = 128, N = 64, K = 8) and commits them to the stage's mbarrier, so the
-// tensor pipe works on tile kt while the threads stage tile kt + 1 into the other buffer.  The epilogue reads the accumulator with
-// tcgen05.ld (32 lanes x 32 columns per warp) and applies bias / activation / mask on the way to global memory.
-// 96 KB of shared memory per CTA (2 stages x 2 planes x (128 + 64) x 32 floats): two CTAs per SM, 64 TMEM columns each.
+// One CTA = a 128 x 64 tile of C: TMEM lanes = rows (M = 128 MMAs), 64 fp32 accumulator columns, 32-wide k-tiles.  Both operands are copied
+// RAW into shared memory by 16-byte cp.async (element copies for unaligned rows); x = hi + lo (hi = rna_tf32(x)) happens in registers on
+// the way to the tensor cores: the A operand into TENSOR MEMORY (tcgen05.st), the B operand into canonical no-swizzle K-major planes
+// (core matrix = 8 rows x 16 B).  One warp only issues 3 passes x 4 k-steps of tcgen05.mma.kind::tf32 (M = 128, N = 64, K = 8) per k-tile.
+// The epilogue reads the accumulator with tcgen05.ld, stages the C tile in shared memory and applies bias / activation / mask on the way
+// to global memory with coalesced accesses.  Two variants: 4 stages, one CTA per SM (172 KB) for grids that leave SMs idle anyway; 2 stages,
+// two CTAs per SM (86 KB, <= 92 registers) for grids of more than one wave.  Details and the measurements behind them: the comment on
+// gemm_tc5_kernel below and profiles/r2_notes.md.
 #include "mlp.cuh"
 
 namespace {
